@@ -1,0 +1,184 @@
+/* vloam_b200.h — C ABI of the B200-native VLOAM per-scan hot path.
+ *
+ * Drop-in boundary for the reference's LiDAR / visual odometry classes
+ * (YukunXia/VLOAM-CMU-16833).  Every entry point replaces one method the
+ * reference's caller (src/vloam_main/src/vloam_main_node.cpp:125-180) reaches
+ * through vloam::LidarOdometryMapping / vloam::VisualOdometry; the reference
+ * interface each one replaces is cited next to it.  INTEGRATION.md shows the
+ * adapter a maintainer adds on the reference side.
+ *
+ * Conventions
+ *   - plain C: opaque handles, caller-owned host buffers, int status codes
+ *     (0 = OK, negative = error; never aborts, never throws across the ABI —
+ *     the adapter maps missing-parameter errors to ROS_BREAK()).
+ *   - a handle drives `batch` independent streams in lock-step; batch = 1 is
+ *     the reference's single-sensor case.  Per-stream arrays are `batch`
+ *     consecutive slabs.
+ *   - device state is owned by the library; one CUDA stream per context;
+ *     a handle is not thread-safe, distinct contexts are.
+ *   - quaternions are (x, y, z, w) like Eigen::Quaterniond::coeffs(); clouds are
+ *     pcl::PointXYZI records (x, y, z, intensity), 16 bytes.
+ */
+#ifndef VLOAM_B200_H
+#define VLOAM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct vloam_ctx vloam_ctx;
+typedef struct vloam_lidar vloam_lidar;
+typedef struct vloam_vo vloam_vo;
+
+enum {
+  VLOAM_OK = 0,
+  VLOAM_E_INVALID = -1,     /* bad argument */
+  VLOAM_E_CUDA = -2,        /* CUDA runtime error, see vloam_last_error() */
+  VLOAM_E_NOMEM = -3,
+  VLOAM_E_STATE = -4,       /* call order violated (e.g. odometry before scan registration) */
+  VLOAM_E_CAPACITY = -5     /* a scan exceeded the capacity the handle was created with */
+};
+
+/* per-stream status bits (vloam_get_stream_status) */
+enum {
+  VLOAM_STREAM_EMPTY = 1,          /* no point survived the NaN / minimum-range filters (the reference would crash) */
+  VLOAM_STREAM_RING_OVERFLOW = 2,  /* a ring had more than 4096 points or a sector more than 1024 */
+  VLOAM_STREAM_VOXEL_OVERFLOW = 4  /* pcl::VoxelGrid's "leaf size too small" path was taken (input returned unfiltered) */
+};
+
+/* cloud selectors for vloam_get_cloud */
+enum {
+  VLOAM_CLOUD_FULL = 0,        /* laserCloud            scan_registration.cpp:507 */
+  VLOAM_CLOUD_SHARP = 1,       /* cornerPointsSharp     :508 */
+  VLOAM_CLOUD_LESS_SHARP = 2,  /* cornerPointsLessSharp :509 */
+  VLOAM_CLOUD_FLAT = 3,        /* surfPointsFlat        :510 */
+  VLOAM_CLOUD_LESS_FLAT = 4,   /* surfPointsLessFlat    :511 */
+  VLOAM_CLOUD_CORNER_LAST = 5, /* laserCloudCornerLast  laser_odometry.cpp:620 */
+  VLOAM_CLOUD_SURF_LAST = 6,   /* laserCloudSurfLast    laser_odometry.cpp:621 */
+  VLOAM_CLOUD_CORNER_STACK = 7,/* laserCloudCornerStack laser_mapping.cpp:432-435 */
+  VLOAM_CLOUD_SURF_STACK = 8,  /* laserCloudSurfStack   laser_mapping.cpp:437-440 */
+  VLOAM_CLOUD_CORNER_MAP = 9,  /* laserCloudCornerFromMap laser_mapping.cpp:422-428 */
+  VLOAM_CLOUD_SURF_MAP = 10    /* laserCloudSurfFromMap */
+};
+
+/* ------------------------------------------------------------------ context */
+int vloam_ctx_create(int device, vloam_ctx** ctx);
+int vloam_ctx_destroy(vloam_ctx* ctx);
+/* Run on a caller-provided cudaStream_t (e.g. torch's current stream); NULL = the context's own stream. */
+int vloam_ctx_set_stream(vloam_ctx* ctx, void* cuda_stream);
+int vloam_ctx_synchronize(vloam_ctx* ctx);
+const char* vloam_last_error(vloam_ctx* ctx);
+/* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
+long long vloam_ctx_launch_count(vloam_ctx* ctx);
+
+/* ------------------------------------------------------------------ LiDAR odometry + mapping
+ * Parameters = the ROS parameters the reference reads
+ * (src/lidar_odometry_mapping/launch/loam_velodyne_HDL_64_kitti.launch:3-16,
+ *  src/vloam_main/launch/vloam_main.launch:4). */
+typedef struct vloam_lidar_params {
+  int batch;                       /* independent streams driven in lock-step (>= 1) */
+  int max_points;                  /* capacity per scan (points) */
+  int scan_line;                   /* 16 / 32 / 64         scan_registration.cpp:48-59 */
+  double minimum_range;            /*                       scan_registration.cpp:51 */
+  double mapping_line_resolution;  /*                       laser_mapping.cpp:95 */
+  double mapping_plane_resolution; /*                       laser_mapping.cpp:97 */
+  int mapping_skip_frame;          /*                       laser_odometry.cpp:53 */
+  int detach_VO_LO;                /* 1: ignore the VO prior   laser_odometry.cpp:47,223 */
+  int lo_outer_passes;             /* 2                     laser_odometry.cpp:211 */
+  int lo_max_iterations;           /* 4                     laser_odometry.cpp:460 */
+  int lm_outer_passes;             /* 2                     laser_mapping.cpp:458 */
+  int lm_max_iterations;           /* 4                     laser_mapping.cpp:612 */
+  int map_capacity_points;         /* capacity of the rolling map per stream and per feature kind */
+} vloam_lidar_params;
+
+/* Fills the reference's KITTI HDL-64 launch-file values. */
+int vloam_lidar_params_default(vloam_lidar_params* p);
+
+/* LidarOdometryMapping::LidarOdometryMapping() + init()   lidar_odometry_mapping.cpp:40-63 */
+int vloam_lidar_create(vloam_ctx* ctx, const vloam_lidar_params* p, vloam_lidar** h);
+int vloam_lidar_destroy(vloam_lidar* h);
+/* LidarOdometryMapping::reset()   lidar_odometry_mapping.cpp:65-71 (call once per frame, before scan registration) */
+int vloam_lidar_reset(vloam_lidar* h);
+
+/* LidarOdometryMapping::scanRegistrationIO(cloud)   lidar_odometry_mapping.cpp:73-94
+ *   -> ScanRegistration::input   scan_registration.cpp:131-449
+ * xyz: host buffer, `batch` slabs of `slab_points` points, each point `stride_floats` floats (3 = packed xyz,
+ * 4 = pcl::PointXYZ); n_points[b] = valid points in slab b.  Pinned host memory makes the upload asynchronous. */
+int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points);
+/* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers). */
+int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats,
+                                   size_t slab_points);
+
+/* status[batch]: VLOAM_STREAM_* bits of the last scan registration. */
+int vloam_get_stream_status(vloam_lidar* h, int* status);
+/* counts[batch][5]: sizes of laserCloud, sharp, lessSharp, flat, lessFlat   (ScanRegistration::output :501-512) */
+int vloam_get_feature_counts(vloam_lidar* h, int* counts);
+/* Copy one cloud of one stream to the host (ScanRegistration::output / LaserOdometry::output hand these out as
+ * pcl::PointCloud<PointXYZI>::Ptr).  n_out receives the size; at most capacity_points records are written. */
+int vloam_get_cloud(vloam_lidar* h, int stream, int which, float* xyzi_out, int capacity_points, int* n_out);
+/* Parity / debug views of the reference's scratch arrays (scan_registration.h:90-93). */
+int vloam_get_curvature(vloam_lidar* h, int stream, float* out, int capacity, int* n_out);
+int vloam_get_labels(vloam_lidar* h, int stream, int8_t* out, int capacity, int* n_out);
+/* which = VLOAM_CLOUD_SHARP / LESS_SHARP / FLAT: indices into laserCloud, in the reference's push order. */
+int vloam_get_feature_indices(vloam_lidar* h, int stream, int which, int* out, int capacity, int* n_out);
+
+/* LidarOdometryMapping::laserOdometryIO()   lidar_odometry_mapping.cpp:96-123
+ *   -> LaserOdometry::input / solveLO / output   laser_odometry.cpp:135-146,187-536,610-629
+ * prior: NULL, or [batch][7] = (q xyzw, t) of vloam_tf->velo_last_VOT_velo_curr, used when detach_VO_LO == 0.
+ * pose_out[batch][14] = q_last_curr(4) t_last_curr(3) q_w_curr(4) t_w_curr(3); corr_out[batch][2] = corner / plane
+ * correspondences of the last outer pass.  Either output pointer may be NULL. */
+int vloam_laser_odometry(vloam_lidar* h, const double* prior, double* pose_out, int* corr_out);
+/* Same without the blocking device->host read of the poses (they stay on the device until vloam_get_lo_pose). */
+int vloam_laser_odometry_async(vloam_lidar* h, const double* prior_dev);
+int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out);
+/* Overwrite q_last_curr / t_last_curr (the motion prior the next solve starts from), motion[batch][7]. */
+int vloam_set_lo_motion(vloam_lidar* h, const double* motion);
+
+/* Parity read-out of one outer pass of the last laser odometry solve for one stream:
+ * corr[(768 + 1536)][4] = (closestPointInd, minPointInd2, minPointInd3, valid) per query slot (corner queries
+ * first), records[8][7] = cost, candidate_cost, model_cost_change, relative_decrease, radius, valid, successful;
+ * info[4] = n_records, termination, n_corner, n_plane; para[7] = parameters after the pass. */
+int vloam_get_lo_trace(vloam_lidar* h, int stream, int pass, int* corr, double* records, int* info, double* para);
+
+/* LidarOdometryMapping::laserMappingIO()   lidar_odometry_mapping.cpp:125-154
+ *   -> LaserMapping::input / solveMapping   laser_mapping.cpp:167-196,198-708
+ * pose_out[batch][14] = q_w_curr(4) t_w_curr(3) q_wmap_wodom(4) t_wmap_wodom(3) (the /aft_mapped_to_init pose,
+ * laser_mapping.cpp:720-729); NULL to skip the device->host read. */
+int vloam_laser_mapping(vloam_lidar* h, double* pose_out);
+int vloam_get_lm_pose(vloam_lidar* h, double* pose_out);
+/* Seed / read one 50 m map cube (index i + 21 j + 441 k, laser_mapping.cpp:412) of one stream; kind 0 = corner,
+ * 1 = surf.  Used to pre-build the 1 M-point map of the benchmark and by the parity tests. */
+int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const float* xyzi, int n);
+int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xyzi_out, int capacity_points, int* n_out);
+/* info[batch][8] = cenWidth, cenHeight, cenDepth, validNum, cornerFromMapNum, surfFromMapNum, cornerStackNum, surfStackNum */
+int vloam_get_lm_info(vloam_lidar* h, int* info);
+int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
+
+/* ------------------------------------------------------------------ visual odometry (depth association + residuals)
+ * VisualOdometry::setUpPointCloud   visual_odometry.cpp:132-155: cam_T_velo[16], rect0_T_cam[16], P_rect0[12], row-major float */
+int vloam_vo_create(vloam_ctx* ctx, int batch, int max_points, int max_matches, vloam_vo** h);
+int vloam_vo_destroy(vloam_vo* h);
+int vloam_vo_set_calibration(vloam_vo* h, const float* cam_T_velo, const float* rect0_T_cam, const float* P_rect0);
+/* VisualOdometry::reset()   visual_odometry.cpp:86-90 (advances the ping-pong slot) */
+int vloam_vo_reset(vloam_vo* h);
+/* VisualOdometry::processPointCloud   visual_odometry.cpp:157-186 -> PointCloudUtil::projectPointCloud / downsamplePointCloud
+ * (point_cloud_util.cpp:148-174,205-260).  Host buffers as in vloam_scan_registration. */
+int vloam_vo_process_cloud(vloam_vo* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points);
+int vloam_vo_process_cloud_device(vloam_vo* h, const float* xyz_dev, const int* n_points_dev, int stride_floats, size_t slab_points);
+/* PointCloudUtil::queryDepth   point_cloud_util.cpp:302-407; slot 0 = current frame, 1 = previous frame. */
+int vloam_vo_query_depth(vloam_vo* h, int stream, int slot, const float* xy, int n, float* depth_out);
+/* bucket grids (249 x 75, index ix * 75 + iy) of one stream: x, y, depth (float) and count (int). */
+int vloam_vo_get_buckets(vloam_vo* h, int stream, int slot, float* bx, float* by, float* bd, int* bc);
+/* VisualOdometry::solveNlsAll   visual_odometry.cpp:254-450.  prev_uv / curr_uv: [batch][max_matches][2] matched
+ * keypoint pixels (cv::KeyPoint::pt), n_matches[batch]; init: NULL (reset_VO_to_identity) or [batch][6] = angle-axis,
+ * t of cam0_curr_LOT_cam0_prev.  out[batch][8] = angles_0to1(3) t_0to1(3) counter32 counter22. */
+int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, const int* n_matches, const double* init,
+                   int remove_VO_outlier, int max_iterations, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VLOAM_B200_H */

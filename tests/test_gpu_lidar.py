@@ -1,0 +1,186 @@
+"""GPU parity tests (run with -m gpu on the B200 box): CUDA path through the C-ABI vs the CPU oracle.
+
+Bars (BASELINE.json north_star): identical edge / plane index sets; pose within 1e-4 m / 1e-4 rad after the
+same iteration count.  Integer / index / float-bit work is compared bit-exactly; the only toleranced float
+is the fractional part of `intensity` (ring + 0.1 * relTime), which goes through atan2f whose last-ulp
+behaviour differs between glibc and CUDA libm (tolerance 2e-6; the integer part, the only part the
+reference uses with DISTORTION=false, must match exactly).
+"""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+INTENSITY_TOL = 2e-6
+POSE_TOL_M = 1e-4
+POSE_TOL_RAD = 1e-4
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _assert_cloud_equal(gpu, ref, name):
+    assert gpu.shape == ref.shape, f"{name}: {gpu.shape} vs {ref.shape}"
+    if gpu.shape[0] == 0:
+        return
+    assert np.array_equal(_bits(gpu[:, :3]), _bits(ref[:, :3])), f"{name}: xyz not bit-identical"
+    assert np.array_equal(gpu[:, 3].astype(np.int32), ref[:, 3].astype(np.int32)), f"{name}: ring ids differ"
+    assert np.max(np.abs(gpu[:, 3] - ref[:, 3])) <= INTENSITY_TOL, f"{name}: intensity fraction"
+
+
+def _check_sr(lom, ref, stream=0):
+    import vloam_b200 as V
+    assert lom.stream_status()[stream] == 0
+    counts = lom.feature_counts()[stream]
+    assert list(counts) == [ref.laserCloud.shape[0], ref.cornerPointsSharp.shape[0], ref.cornerPointsLessSharp.shape[0],
+                            ref.surfPointsFlat.shape[0], ref.surfPointsLessFlat.shape[0]], counts
+    _assert_cloud_equal(lom.cloud(V.CLOUD_FULL, stream), ref.laserCloud, "laserCloud")
+    curv = lom.curvature(stream)
+    assert np.array_equal(_bits(curv), _bits(ref.curvature)), "curvature not bit-identical"
+    assert np.array_equal(lom.labels(stream).astype(np.int32), ref.label), "labels differ"
+    assert np.array_equal(lom.feature_indices(V.CLOUD_SHARP, stream), ref.sharpInd)
+    assert np.array_equal(lom.feature_indices(V.CLOUD_LESS_SHARP, stream), ref.lessSharpInd)
+    assert np.array_equal(lom.feature_indices(V.CLOUD_FLAT, stream), ref.flatInd)
+    _assert_cloud_equal(lom.cloud(V.CLOUD_SHARP, stream), ref.cornerPointsSharp, "sharp")
+    _assert_cloud_equal(lom.cloud(V.CLOUD_LESS_SHARP, stream), ref.cornerPointsLessSharp, "lessSharp")
+    _assert_cloud_equal(lom.cloud(V.CLOUD_FLAT, stream), ref.surfPointsFlat, "flat")
+    _assert_cloud_equal(lom.cloud(V.CLOUD_LESS_FLAT, stream), ref.surfPointsLessFlat, "lessFlat")
+
+
+def _quat_angle(q1, q2):
+    d = abs(float(np.dot(q1, q2)))
+    return 2.0 * np.arccos(min(1.0, d))
+
+
+def _check_lo(lom, olo, pose, stream=0, require_identical_sets=True):
+    st = olo.state
+    tr = olo.trace()
+    for p, t in enumerate(tr):
+        g = lom.lo_trace(p, stream)
+        if require_identical_sets:
+            assert np.array_equal(g["corner"], t["corner"]), f"pass {p}: corner correspondences differ"
+            assert np.array_equal(g["plane"], t["plane"]), f"pass {p}: plane correspondences differ"
+        assert g["termination"] == t["termination"], (p, g["termination"], t["termination"])
+        n = t["iterations"].shape[0]
+        assert g["n_records"] == n
+        np.testing.assert_allclose(g["iterations"][:n, 0], t["iterations"][:, 0], rtol=1e-9, atol=1e-12)  # cost
+        np.testing.assert_array_equal(g["iterations"][:n, 5:7], t["iterations"][:, 5:7])                 # valid / successful
+        np.testing.assert_allclose(g["iterations"][:n, 4], t["iterations"][:, 4], rtol=1e-6)              # radius
+        np.testing.assert_allclose(g["para"], t["para"], atol=1e-9)
+    assert np.max(np.abs(pose["t_last_curr"][stream] - st["t_last_curr"])) < POSE_TOL_M
+    assert _quat_angle(pose["q_last_curr"][stream], st["q_last_curr"]) < POSE_TOL_RAD
+    assert np.max(np.abs(pose["t_w_curr"][stream] - st["t_w_curr"])) < POSE_TOL_M
+    assert _quat_angle(pose["q_w_curr"][stream], st["q_w_curr"]) < POSE_TOL_RAD
+    assert pose["corner_correspondence"][stream] == st["corner_correspondence"]
+    assert pose["plane_correspondence"][stream] == st["plane_correspondence"]
+    return float(np.max(np.abs(pose["t_last_curr"][stream] - st["t_last_curr"])))
+
+
+def test_scan_registration_and_odometry_full_size(scans_full, oracle):
+    """BASELINE configs[1] shape: 64 x 2048 scans, scanRegistration + laserOdometry, one stream."""
+    import vloam_b200 as V
+    scans, _ = scans_full
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0])
+    olo = oracle.LaserOdometry()
+    worst = 0.0
+    for k, scan in enumerate(scans):
+        lom.reset()
+        lom.scanRegistrationIO(scan)
+        ref = oracle.scan_registration(scan)
+        _check_sr(lom, ref)
+        pose = lom.laserOdometryIO()
+        olo.solve(ref)
+        if k > 0:
+            worst = max(worst, _check_lo(lom, olo, pose))
+        else:
+            assert np.allclose(pose["q_w_curr"][0], [0, 0, 0, 1]) and np.allclose(pose["t_w_curr"][0], 0)
+        # the swap (laser_odometry.cpp:511-517): corner/surf "last" are now this scan's less-sharp / less-flat
+        _assert_cloud_equal(lom.cloud(V.CLOUD_CORNER_LAST), ref.cornerPointsLessSharp, "cornerLast")
+        _assert_cloud_equal(lom.cloud(V.CLOUD_SURF_LAST), ref.surfPointsLessFlat, "surfLast")
+    print("max |t_last_curr - oracle| =", worst)
+    lom.close()
+
+
+def test_batched_ragged_streams(synth, oracle):
+    """Three independent streams of different seeds and lengths in one handle == three oracle runs."""
+    import vloam_b200 as V
+    streams = [synth.ScanStream(seed, n_cols=c) for seed, c in ((3, 512), (4, 384), (5, 640))]
+    B = len(streams)
+    cap = max(s.n_cols for s in streams) * 64
+    lom = V.LidarOdometryMapping(batch=B, max_points=cap)
+    olos = [oracle.LaserOdometry() for _ in range(B)]
+    for k in range(3):
+        buf = np.full((B, cap, 4), np.nan, np.float32)  # pcl::PointXYZ stride (4 floats)
+        n = np.zeros(B, np.int32)
+        scans = []
+        for b, s in enumerate(streams):
+            sc = s.scan(k)
+            scans.append(sc)
+            buf[b, : sc.shape[0], :3] = sc
+            n[b] = sc.shape[0]
+        lom.reset()
+        lom.scanRegistrationIO(buf, n)
+        pose = lom.laserOdometryIO()
+        for b in range(B):
+            ref = oracle.scan_registration(scans[b])
+            _check_sr(lom, ref, b)
+            olos[b].solve(ref)
+            if k > 0:
+                _check_lo(lom, olos[b], pose, b)
+    lom.close()
+
+
+def test_edge_cases(synth, oracle):
+    """Empty scan, all-NaN scan, scan with every point inside minimum_range, tiny rings."""
+    import vloam_b200 as V
+    lom = V.LidarOdometryMapping(batch=1, max_points=4096)
+    # all NaN
+    lom.reset()
+    lom.scanRegistrationIO(np.full((1000, 3), np.nan, np.float32))
+    assert lom.stream_status()[0] & V.STREAM_EMPTY
+    assert list(lom.feature_counts()[0]) == [0, 0, 0, 0, 0]
+    assert oracle.scan_registration(np.full((1000, 3), np.nan, np.float32)).status == 1
+    # zero points
+    lom.reset()
+    lom.scanRegistrationIO(np.zeros((16, 3), np.float32), np.zeros(1, np.int32))
+    assert lom.stream_status()[0] & V.STREAM_EMPTY
+    # all closer than minimum_range
+    lom.reset()
+    near = np.random.default_rng(0).normal(0, 1.0, (2000, 3)).astype(np.float32)
+    lom.scanRegistrationIO(near)
+    assert lom.stream_status()[0] & V.STREAM_EMPTY
+    # short rings: only 10..40 points per ring -> most rings skipped by the `< 6` rule (scan_registration.cpp:314)
+    s = synth.ScanStream(11, n_cols=40)
+    sc = s.scan(0)
+    lom.reset()
+    lom.scanRegistrationIO(sc)
+    ref = oracle.scan_registration(sc)
+    _check_sr(lom, ref)
+    # laser odometry on nearly empty features must not crash and must agree with the oracle
+    pose0 = lom.laserOdometryIO()
+    olo = oracle.LaserOdometry()
+    olo.solve(ref)
+    sc1 = s.scan(1)
+    lom.reset()
+    lom.scanRegistrationIO(sc1)
+    ref1 = oracle.scan_registration(sc1)
+    _check_sr(lom, ref1)
+    pose1 = lom.laserOdometryIO()
+    olo.solve(ref1)
+    _check_lo(lom, olo, pose1)
+    lom.close()
+
+
+def test_call_order_errors():
+    import vloam_b200 as V
+    lom = V.LidarOdometryMapping(batch=1, max_points=2048)
+    with pytest.raises(V.VloamError):
+        lom.laserOdometryIO()  # before any scan registration
+    lom.scanRegistrationIO(np.full((100, 3), np.nan, np.float32))
+    lom.laserOdometryIO()
+    with pytest.raises(V.VloamError):
+        lom.laserOdometryIO()  # twice for the same scan
+    with pytest.raises(V.VloamError):
+        lom.scanRegistrationIO(np.zeros((4096, 3), np.float32))  # larger than max_points
+    lom.close()

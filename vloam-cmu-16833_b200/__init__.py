@@ -1,0 +1,354 @@
+"""vloam_b200 — host-side mirror of the reference's LiDAR / visual odometry class API over the C-ABI.
+
+The product is `lib/libvloam_b200.so` (CUDA, sm_100a; include/vloam_b200.h).  This module is the thin
+Python harness around it used by tests/ and bench.py: it loads the shared library with ctypes and exposes
+classes with the reference's method names
+
+    LidarOdometryMapping.init / reset / scanRegistrationIO / laserOdometryIO / laserMappingIO
+        (reference include/lidar_odometry_mapping/lidar_odometry_mapping.h:45-86)
+    VisualOdometry.init / reset / setUpPointCloud / processPointCloud / solveNlsAll
+        (reference include/visual_odometry/visual_odometry.h:40-121)
+
+There is NO CPU fallback: if the library is missing or no CUDA device is present the calls raise.
+The directory name contains a '-', so import it through the repo-root shim `vloam_b200.py`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libvloam_b200.so")
+HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vloam_b200.h")
+
+VLOAM_OK = 0
+CLOUD_FULL, CLOUD_SHARP, CLOUD_LESS_SHARP, CLOUD_FLAT, CLOUD_LESS_FLAT, CLOUD_CORNER_LAST, CLOUD_SURF_LAST, \
+    CLOUD_CORNER_STACK, CLOUD_SURF_STACK, CLOUD_CORNER_MAP, CLOUD_SURF_MAP = range(11)
+STREAM_EMPTY, STREAM_RING_OVERFLOW, STREAM_VOXEL_OVERFLOW = 1, 2, 4
+MAX_SHARP, MAX_FLAT = 768, 1536
+
+c_fp = C.POINTER(C.c_float)
+c_dp = C.POINTER(C.c_double)
+c_ip = C.POINTER(C.c_int)
+
+
+class VloamError(RuntimeError):
+    pass
+
+
+class LidarParams(C.Structure):
+    _fields_ = [("batch", C.c_int), ("max_points", C.c_int), ("scan_line", C.c_int), ("minimum_range", C.c_double),
+                ("mapping_line_resolution", C.c_double), ("mapping_plane_resolution", C.c_double),
+                ("mapping_skip_frame", C.c_int), ("detach_VO_LO", C.c_int), ("lo_outer_passes", C.c_int),
+                ("lo_max_iterations", C.c_int), ("lm_outer_passes", C.c_int), ("lm_max_iterations", C.c_int),
+                ("map_capacity_points", C.c_int)]
+
+
+def build(verbose: bool = False) -> str:
+    """Compile the CUDA library for sm_100a (nvcc cross-compiles without a GPU)."""
+    out = subprocess.run([os.path.join(_HERE, "build.sh")], capture_output=True, text=True)
+    if out.returncode != 0:
+        raise VloamError("build failed:\n" + out.stdout + out.stderr)
+    if verbose:
+        print(out.stdout)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    """The loaded C-ABI library; raises if it has not been built (no fallback)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VloamError(f"{LIB_PATH} missing: run __graft_entry__.build() (nvcc) first; there is no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        vp = C.c_void_p
+        pp = C.POINTER(vp)
+        sig = {
+            "vloam_ctx_create": [C.c_int, pp], "vloam_ctx_destroy": [vp], "vloam_ctx_set_stream": [vp, vp],
+            "vloam_ctx_synchronize": [vp], "vloam_lidar_params_default": [C.POINTER(LidarParams)],
+            "vloam_lidar_create": [vp, C.POINTER(LidarParams), pp], "vloam_lidar_destroy": [vp], "vloam_lidar_reset": [vp],
+            "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_get_stream_status": [vp, c_ip], "vloam_get_feature_counts": [vp, c_ip],
+            "vloam_get_cloud": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
+            "vloam_get_curvature": [vp, C.c_int, c_fp, C.c_int, c_ip],
+            "vloam_get_labels": [vp, C.c_int, vp, C.c_int, c_ip],
+            "vloam_get_feature_indices": [vp, C.c_int, C.c_int, c_ip, C.c_int, c_ip],
+            "vloam_laser_odometry": [vp, vp, vp, vp], "vloam_laser_odometry_async": [vp, vp],
+            "vloam_get_lo_pose": [vp, vp, vp], "vloam_set_lo_motion": [vp, c_dp],
+            "vloam_get_lo_trace": [vp, C.c_int, C.c_int, c_ip, c_dp, c_ip, c_dp],
+            "vloam_laser_mapping": [vp, vp], "vloam_get_lm_pose": [vp, c_dp],
+            "vloam_map_set_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int],
+            "vloam_map_get_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
+            "vloam_get_lm_info": [vp, c_ip], "vloam_get_lm_trace": [vp, C.c_int, C.c_int, c_dp, c_ip, c_dp],
+            "vloam_vo_create": [vp, C.c_int, C.c_int, C.c_int, pp], "vloam_vo_destroy": [vp],
+            "vloam_vo_set_calibration": [vp, c_fp, c_fp, c_fp], "vloam_vo_reset": [vp],
+            "vloam_vo_process_cloud": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_vo_process_cloud_device": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_vo_query_depth": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_fp],
+            "vloam_vo_get_buckets": [vp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_ip],
+            "vloam_vo_solve": [vp, vp, vp, vp, vp, C.c_int, C.c_int, c_dp],
+        }
+        for name, args in sig.items():
+            fn = getattr(L, name)
+            fn.restype = C.c_int
+            fn.argtypes = args
+        L.vloam_last_error.restype = C.c_char_p
+        L.vloam_last_error.argtypes = [vp]
+        L.vloam_ctx_launch_count.restype = C.c_longlong
+        L.vloam_ctx_launch_count.argtypes = [vp]
+        _lib = L
+    return _lib
+
+
+def exported_symbols_in_header() -> list[str]:
+    """Every function name include/vloam_b200.h declares (used by the CPU-side load test)."""
+    import re
+    txt = open(HEADER_PATH).read()
+    return sorted(set(re.findall(r"\b(vloam_[a-z0-9_]+)\s*\(", txt)))
+
+
+def _ptr(a):
+    """ctypes void* of a numpy array, a torch tensor (host or device) or an int address."""
+    if a is None:
+        return None
+    if isinstance(a, int):
+        return C.c_void_p(a)
+    if isinstance(a, np.ndarray):
+        return C.c_void_p(a.ctypes.data)
+    if hasattr(a, "data_ptr"):
+        return C.c_void_p(a.data_ptr())
+    raise TypeError(type(a))
+
+
+class Context:
+    def __init__(self, device: int = 0, cuda_stream: int | None = None):
+        self._h = C.c_void_p()
+        rc = lib().vloam_ctx_create(device, C.byref(self._h))
+        if rc != VLOAM_OK:
+            raise VloamError(f"vloam_ctx_create(device={device}) failed with {rc}: no CUDA device? (there is no CPU fallback)")
+        if cuda_stream is not None:
+            self.set_stream(cuda_stream)
+
+    def check(self, rc):
+        if rc != VLOAM_OK:
+            raise VloamError(f"vloam error {rc}: {lib().vloam_last_error(self._h).decode()}")
+
+    def set_stream(self, cuda_stream: int | None):
+        self.check(lib().vloam_ctx_set_stream(self._h, C.c_void_p(cuda_stream) if cuda_stream else None))
+
+    def synchronize(self):
+        self.check(lib().vloam_ctx_synchronize(self._h))
+
+    @property
+    def launch_count(self) -> int:
+        return int(lib().vloam_ctx_launch_count(self._h))
+
+    def close(self):
+        if self._h:
+            lib().vloam_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+
+def default_lidar_params(**kw) -> LidarParams:
+    p = LidarParams()
+    lib().vloam_lidar_params_default(C.byref(p))
+    for k, v in kw.items():
+        if not hasattr(p, k):
+            raise KeyError(k)
+        setattr(p, k, v)
+    return p
+
+
+class LidarOdometryMapping:
+    """Mirror of vloam::LidarOdometryMapping for `batch` streams driven in lock-step.
+
+    Poses come back as dicts of (batch, k) float64 arrays; clouds as (n, 4) float32 arrays.
+    """
+
+    def __init__(self, ctx: Context | None = None, **params):
+        self.ctx = ctx or Context()
+        self._own_ctx = ctx is None
+        self.params = default_lidar_params(**params)
+        self._h = C.c_void_p()
+        self.batch = self.params.batch
+        self.last_pose = None
+        self.last_map_pose = None
+        self.init()
+
+    # -- lidar_odometry_mapping.cpp:40-63
+    def init(self, vloam_tf=None):
+        if self._h:
+            lib().vloam_lidar_destroy(self._h)
+            self._h = C.c_void_p()
+        self.ctx.check(lib().vloam_lidar_create(self.ctx._h, C.byref(self.params), C.byref(self._h)))
+        self.vloam_tf = vloam_tf
+
+    # -- lidar_odometry_mapping.cpp:65-71
+    def reset(self):
+        self.ctx.check(lib().vloam_lidar_reset(self._h))
+
+    # -- lidar_odometry_mapping.cpp:73-94
+    def scanRegistrationIO(self, laserCloudIn, n_points=None):
+        """laserCloudIn: (batch, n, 3|4) or (n, 3|4) float32 host array (numpy / pinned torch), NaN = no return."""
+        a = laserCloudIn
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+        shape = tuple(a.shape)
+        if len(shape) == 2:
+            shape = (1,) + shape
+        assert shape[0] == self.batch and shape[2] in (3, 4), shape
+        if n_points is None:
+            n_points = np.full(self.batch, shape[1], np.int32)
+        n_points = np.ascontiguousarray(n_points, np.int32)
+        self._keep = (a, n_points)  # keep host buffers alive until the async upload has been consumed
+        self.ctx.check(lib().vloam_scan_registration(self._h, _ptr(a), _ptr(n_points), shape[2], shape[1]))
+
+    def scanRegistrationDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int):
+        """Scans already resident in HBM (torch CUDA tensors or raw device addresses)."""
+        self._keep = (xyz_dev, n_points_dev)
+        self.ctx.check(lib().vloam_scan_registration_device(self._h, _ptr(xyz_dev), _ptr(n_points_dev), stride, slab_points))
+
+    # -- lidar_odometry_mapping.cpp:96-123
+    def laserOdometryIO(self, prior=None, fetch=True):
+        if not fetch:
+            self.ctx.check(lib().vloam_laser_odometry_async(self._h, _ptr(prior)))
+            return None
+        pose = np.zeros((self.batch, 14))
+        corr = np.zeros((self.batch, 2), np.int32)
+        pr = np.ascontiguousarray(prior, np.float64).reshape(self.batch, 7) if prior is not None else None
+        self.ctx.check(lib().vloam_laser_odometry(self._h, _ptr(pr), _ptr(pose), _ptr(corr)))
+        self.last_pose = self._split_lo(pose, corr)
+        return self.last_pose
+
+    def lo_pose(self):
+        pose = np.zeros((self.batch, 14))
+        corr = np.zeros((self.batch, 2), np.int32)
+        self.ctx.check(lib().vloam_get_lo_pose(self._h, _ptr(pose), _ptr(corr)))
+        self.last_pose = self._split_lo(pose, corr)
+        return self.last_pose
+
+    @staticmethod
+    def _split_lo(pose, corr):
+        return {"q_last_curr": pose[:, 0:4].copy(), "t_last_curr": pose[:, 4:7].copy(), "q_w_curr": pose[:, 7:11].copy(),
+                "t_w_curr": pose[:, 11:14].copy(), "corner_correspondence": corr[:, 0].copy(),
+                "plane_correspondence": corr[:, 1].copy()}
+
+    def set_lo_motion(self, motion):
+        m = np.ascontiguousarray(motion, np.float64).reshape(self.batch, 7)
+        self.ctx.check(lib().vloam_set_lo_motion(self._h, m.ctypes.data_as(c_dp)))
+
+    # -- lidar_odometry_mapping.cpp:125-154
+    def laserMappingIO(self, fetch=True):
+        if not fetch:
+            self.ctx.check(lib().vloam_laser_mapping(self._h, None))
+            return None
+        pose = np.zeros((self.batch, 14))
+        self.ctx.check(lib().vloam_laser_mapping(self._h, _ptr(pose)))
+        self.last_map_pose = {"q_w_curr": pose[:, 0:4].copy(), "t_w_curr": pose[:, 4:7].copy(),
+                              "q_wmap_wodom": pose[:, 7:11].copy(), "t_wmap_wodom": pose[:, 11:14].copy()}
+        return self.last_map_pose
+
+    # -- read-out helpers (ScanRegistration::output / parity views)
+    def stream_status(self):
+        s = np.zeros(self.batch, np.int32)
+        self.ctx.check(lib().vloam_get_stream_status(self._h, s.ctypes.data_as(c_ip)))
+        return s
+
+    def feature_counts(self):
+        c = np.zeros((self.batch, 5), np.int32)
+        self.ctx.check(lib().vloam_get_feature_counts(self._h, c.ctypes.data_as(c_ip)))
+        return c
+
+    def cloud(self, which: int, stream: int = 0):
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_get_cloud(self._h, stream, which, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            self.ctx.check(lib().vloam_get_cloud(self._h, stream, which, out.ctypes.data_as(c_fp), n.value, C.byref(n)))
+        return out
+
+    def curvature(self, stream: int = 0):
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_get_curvature(self._h, stream, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.float32)
+        if n.value:
+            self.ctx.check(lib().vloam_get_curvature(self._h, stream, out.ctypes.data_as(c_fp), n.value, C.byref(n)))
+        return out
+
+    def labels(self, stream: int = 0):
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_get_labels(self._h, stream, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.int8)
+        if n.value:
+            self.ctx.check(lib().vloam_get_labels(self._h, stream, C.c_void_p(out.ctypes.data), n.value, C.byref(n)))
+        return out
+
+    def feature_indices(self, which: int, stream: int = 0):
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_get_feature_indices(self._h, stream, which, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.int32)
+        if n.value:
+            self.ctx.check(lib().vloam_get_feature_indices(self._h, stream, which, out.ctypes.data_as(c_ip), n.value, C.byref(n)))
+        return out
+
+    def lo_trace(self, pass_: int, stream: int = 0):
+        corr = np.zeros((MAX_SHARP + MAX_FLAT, 4), np.int32)
+        rec = np.zeros((8, 7))
+        info = np.zeros(4, np.int32)
+        para = np.zeros(7)
+        self.ctx.check(lib().vloam_get_lo_trace(self._h, stream, pass_, corr.ctypes.data_as(c_ip), rec.ctypes.data_as(c_dp),
+                                                info.ctypes.data_as(c_ip), para.ctypes.data_as(c_dp)))
+        cq = corr[:MAX_SHARP]
+        pq = corr[MAX_SHARP:]
+        ci = np.nonzero(cq[:, 3])[0]
+        pi = np.nonzero(pq[:, 3])[0]
+        return {"corner": np.column_stack([ci, cq[ci, 0], cq[ci, 1]]).astype(np.int32),
+                "plane": np.column_stack([pi, pq[pi, 0], pq[pi, 1], pq[pi, 2]]).astype(np.int32),
+                "iterations": rec[: min(int(info[0]), 8)].copy(), "n_records": int(info[0]), "termination": int(info[1]),
+                "n_corner": int(info[2]), "n_plane": int(info[3]), "para": para}
+
+    def lm_info(self):
+        info = np.zeros((self.batch, 8), np.int32)
+        self.ctx.check(lib().vloam_get_lm_info(self._h, info.ctypes.data_as(c_ip)))
+        return info
+
+    def lm_trace(self, pass_: int, stream: int = 0):
+        rec = np.zeros((8, 7))
+        info = np.zeros(4, np.int32)
+        para = np.zeros(7)
+        self.ctx.check(lib().vloam_get_lm_trace(self._h, stream, pass_, rec.ctypes.data_as(c_dp), info.ctypes.data_as(c_ip),
+                                                para.ctypes.data_as(c_dp)))
+        return {"iterations": rec[: min(int(info[0]), 8)].copy(), "n_records": int(info[0]), "termination": int(info[1]),
+                "n_corner": int(info[2]), "n_plane": int(info[3]), "para": para}
+
+    def map_set_cube(self, kind: int, cube: int, xyzi, stream: int = 0):
+        a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)
+        self.ctx.check(lib().vloam_map_set_cube(self._h, stream, kind, cube, a.ctypes.data_as(c_fp), a.shape[0]))
+
+    def map_get_cube(self, kind: int, cube: int, stream: int = 0):
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_map_get_cube(self._h, stream, kind, cube, None, 0, C.byref(n)))
+        out = np.empty((n.value, 4), np.float32)
+        if n.value:
+            self.ctx.check(lib().vloam_map_get_cube(self._h, stream, kind, cube, out.ctypes.data_as(c_fp), n.value, C.byref(n)))
+        return out
+
+    def close(self):
+        if self._h:
+            lib().vloam_lidar_destroy(self._h)
+            self._h = C.c_void_p()
+        if self._own_ctx:
+            self.ctx.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

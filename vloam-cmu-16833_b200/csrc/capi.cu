@@ -1,0 +1,479 @@
+// vloam_b200 — C-ABI implementation (include/vloam_b200.h): handles, device buffers, launch sequencing.
+// No torch types, no CPU fallback: every entry point either runs the CUDA path or returns an error code.
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/vloam_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+using namespace vb;
+
+struct vloam_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  std::string last_error;
+  long long launches = 0;
+};
+
+namespace {
+
+int fail(vloam_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) {
+    c->last_error = what;
+    if (e != cudaSuccess) { c->last_error += ": "; c->last_error += cudaGetErrorString(e); }
+  }
+  return code;
+}
+
+#define CU(ctx, call)                                                        \
+  do {                                                                       \
+    cudaError_t e__ = (call);                                                \
+    if (e__ != cudaSuccess) return fail((ctx), VLOAM_E_CUDA, #call, e__);    \
+  } while (0)
+
+template <typename T>
+cudaError_t dalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e == cudaSuccess && n) e = cudaMemset(*p, 0, n * sizeof(T));
+  return e;
+}
+
+}  // namespace
+
+struct vloam_lidar {
+  vloam_ctx* ctx = nullptr;
+  vloam_lidar_params p{};
+  int B = 0, cap = 0, nblk = 0;
+  long long frame = -1;      // index of the last registered scan; -1 = none
+  bool lo_done_for_frame = false;
+  long long lo_frames = 0;   // LaserOdometry::frameCount
+  // input staging
+  float* d_in = nullptr;     // [B][cap][4]
+  int* d_n = nullptr;        // [B]
+  // scan registration
+  SRHeader* d_hdr[2] = {nullptr, nullptr};
+  uint8_t* d_ring8 = nullptr;
+  int* d_blockHist = nullptr;
+  float4* d_cloud[2] = {nullptr, nullptr};  // laserCloud of the current / previous scan (laserCloudFullRes)
+  float* d_curv = nullptr;
+  int8_t* d_label = nullptr;
+  int* d_featIdx = nullptr;
+  float4* d_lessFlatStage = nullptr;
+  float4* d_sharp = nullptr; int* d_sharpIdx = nullptr;
+  float4* d_lessSharp[2] = {nullptr, nullptr}; int* d_lessSharpIdx = nullptr;
+  float4* d_flat = nullptr; int* d_flatIdx = nullptr;
+  float4* d_lessFlat[2] = {nullptr, nullptr};
+  // laser odometry
+  LOState* d_lo = nullptr;
+  int4* d_corr[2] = {nullptr, nullptr};  // per outer pass (kept for parity read-out)
+  double* d_prior = nullptr;             // [B][7]
+  double* d_pose = nullptr;              // [B][16]
+  double* h_pose = nullptr;              // pinned
+  // laser mapping
+  LMDevice* lm = nullptr;
+  int cur() const { return (int)(frame & 1); }
+};
+
+extern "C" {
+
+// ------------------------------------------------------------------------------------------------ context
+int vloam_ctx_create(int device, vloam_ctx** out) {
+  if (!out) return VLOAM_E_INVALID;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || device < 0 || device >= n) return VLOAM_E_CUDA;
+  vloam_ctx* c = new (std::nothrow) vloam_ctx();
+  if (!c) return VLOAM_E_NOMEM;
+  c->device = device;
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return VLOAM_E_CUDA;
+  }
+  c->stream = c->own_stream;
+  *out = c;
+  return VLOAM_OK;
+}
+int vloam_ctx_destroy(vloam_ctx* c) {
+  if (!c) return VLOAM_E_INVALID;
+  cudaSetDevice(c->device);
+  if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  delete c;
+  return VLOAM_OK;
+}
+int vloam_ctx_set_stream(vloam_ctx* c, void* s) {
+  if (!c) return VLOAM_E_INVALID;
+  c->stream = s ? (cudaStream_t)s : c->own_stream;
+  return VLOAM_OK;
+}
+int vloam_ctx_synchronize(vloam_ctx* c) {
+  if (!c) return VLOAM_E_INVALID;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+const char* vloam_last_error(vloam_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
+long long vloam_ctx_launch_count(vloam_ctx* c) { return c ? c->launches : 0; }
+
+// ------------------------------------------------------------------------------------------------ lidar handle
+int vloam_lidar_params_default(vloam_lidar_params* p) {
+  if (!p) return VLOAM_E_INVALID;
+  p->batch = 1;
+  p->max_points = 131072;
+  p->scan_line = 64;                   // loam_velodyne_HDL_64_kitti.launch:3
+  p->minimum_range = 5.0;              // :13
+  p->mapping_line_resolution = 0.4;    // :15
+  p->mapping_plane_resolution = 0.8;   // :16
+  p->mapping_skip_frame = 1;           // :6
+  p->detach_VO_LO = 1;                 // vloam_main.launch:4
+  p->lo_outer_passes = 2;
+  p->lo_max_iterations = 4;
+  p->lm_outer_passes = 2;
+  p->lm_max_iterations = 4;
+  p->map_capacity_points = 1 << 21;
+  return VLOAM_OK;
+}
+
+int vloam_lidar_destroy(vloam_lidar* h) {
+  if (!h) return VLOAM_E_INVALID;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaFree(h->d_in); cudaFree(h->d_n);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->d_hdr[i]); cudaFree(h->d_cloud[i]); cudaFree(h->d_lessSharp[i]); cudaFree(h->d_lessFlat[i]); cudaFree(h->d_corr[i]); }
+  cudaFree(h->d_ring8); cudaFree(h->d_blockHist); cudaFree(h->d_curv); cudaFree(h->d_label); cudaFree(h->d_featIdx);
+  cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
+  cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
+  if (h->h_pose) cudaFreeHost(h->h_pose);
+  if (h->lm) lm_destroy(h->lm);
+  delete h;
+  return VLOAM_OK;
+}
+
+int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** out) {
+  if (!c || !p || !out) return VLOAM_E_INVALID;
+  *out = nullptr;
+  if (p->batch < 1 || p->max_points < 64 || (p->scan_line != 16 && p->scan_line != 32 && p->scan_line != 64))
+    return fail(c, VLOAM_E_INVALID, "vloam_lidar_create: batch >= 1, max_points >= 64, scan_line in {16,32,64}");
+  CU(c, cudaSetDevice(c->device));
+  vloam_lidar* h = new (std::nothrow) vloam_lidar();
+  if (!h) return VLOAM_E_NOMEM;
+  h->ctx = c; h->p = *p; h->B = p->batch;
+  h->cap = (p->max_points + kClassifyBlock - 1) / kClassifyBlock * kClassifyBlock;
+  h->nblk = h->cap / kClassifyBlock;
+  const size_t B = h->B, cap = h->cap;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
+  A(dalloc(&h->d_in, B * cap * 4)); A(dalloc(&h->d_n, B));
+  for (int i = 0; i < 2; ++i) {
+    A(dalloc(&h->d_hdr[i], B)); A(dalloc(&h->d_cloud[i], B * cap));
+    A(dalloc(&h->d_lessSharp[i], B * kMaxLessSharp)); A(dalloc(&h->d_lessFlat[i], B * cap));
+    A(dalloc(&h->d_corr[i], B * (kMaxSharp + kMaxFlat)));
+  }
+  A(dalloc(&h->d_ring8, B * cap)); A(dalloc(&h->d_blockHist, B * h->nblk * kMaxRings));
+  A(dalloc(&h->d_curv, B * cap)); A(dalloc(&h->d_label, B * cap));
+  A(dalloc(&h->d_featIdx, B * kMaxRings * kSectors * 26)); A(dalloc(&h->d_lessFlatStage, B * cap));
+  A(dalloc(&h->d_sharp, B * kMaxSharp)); A(dalloc(&h->d_sharpIdx, B * kMaxSharp));
+  A(dalloc(&h->d_lessSharpIdx, B * kMaxLessSharp));
+  A(dalloc(&h->d_flat, B * kMaxFlat)); A(dalloc(&h->d_flatIdx, B * kMaxFlat));
+  A(dalloc(&h->d_lo, B)); A(dalloc(&h->d_prior, B * 7)); A(dalloc(&h->d_pose, B * 16));
+  A(cudaMallocHost((void**)&h->h_pose, B * 16 * sizeof(double)));
+  if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
+  launch_lo_init(c->stream, h->d_lo, h->B); c->launches++;
+  e = lm_create(c->stream, h->B, h->cap, p, &h->lm);
+  if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, VLOAM_E_CUDA, "vloam_lidar_create: map allocation", e); }
+  CU(c, cudaStreamSynchronize(c->stream));
+  *out = h;
+  return VLOAM_OK;
+}
+
+int vloam_lidar_reset(vloam_lidar* h) {
+  if (!h) return VLOAM_E_INVALID;
+  // ScanRegistration::reset clears the per-scan clouds (scan_registration.cpp:89-98) — the device buffers are
+  // overwritten by the next scan; LaserMapping::reset zeroes the valid / surround cube counts (laser_mapping.cpp:127-131).
+  lm_reset(h->lm);
+  return VLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ scan registration
+static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
+  vloam_ctx* c = h->ctx;
+  h->frame++;
+  h->lo_done_for_frame = false;
+  const int cur = h->cur();
+  launch_scan_registration(c->stream, h->B, h->cap, xyz_dev, stride, slab_points * (size_t)stride, n_dev,
+                           (float)h->p.minimum_range, h->p.scan_line, h->d_hdr[cur], h->d_ring8, h->d_blockHist,
+                           h->d_cloud[cur], h->d_curv, h->d_label, h->d_featIdx, h->d_lessFlatStage, h->d_sharp,
+                           h->d_sharpIdx, h->d_lessSharp[cur], h->d_lessSharpIdx, h->d_flat, h->d_flatIdx,
+                           h->d_lessFlat[cur]);
+  c->launches += 7;
+  CU(c, cudaGetLastError());
+  return VLOAM_OK;
+}
+
+int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride, size_t slab_points) {
+  if (!h || !xyz || !n_points || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  for (int b = 0; b < h->B; ++b) {
+    if (n_points[b] < 0 || (size_t)n_points[b] > slab_points) return fail(c, VLOAM_E_INVALID, "n_points[b] exceeds slab_points");
+    if (n_points[b] > h->cap) return fail(c, VLOAM_E_CAPACITY, "scan larger than max_points");
+  }
+  // one upload per stream slab (only the valid prefix), all on the context stream
+  for (int b = 0; b < h->B; ++b)
+    if (n_points[b])
+      CU(c, cudaMemcpyAsync(h->d_in + (size_t)b * h->cap * stride, xyz + (size_t)b * slab_points * stride,
+                            (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(h->d_n, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  return run_scan_registration(h, h->d_in, h->d_n, stride, (size_t)h->cap);
+}
+
+int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
+  if (!h || !xyz_dev || !n_dev || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  CU(h->ctx, cudaSetDevice(h->ctx->device));
+  return run_scan_registration(h, xyz_dev, n_dev, stride, slab_points);
+}
+
+static int fetch_headers(vloam_lidar* h, std::vector<SRHeader>* out, int slot) {
+  vloam_ctx* c = h->ctx;
+  out->resize(h->B);
+  CU(c, cudaMemcpyAsync(out->data(), h->d_hdr[slot], h->B * sizeof(SRHeader), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+int vloam_get_stream_status(vloam_lidar* h, int* status) {
+  if (!h || !status) return VLOAM_E_INVALID;
+  if (h->frame < 0) return fail(h->ctx, VLOAM_E_STATE, "no scan registered yet");
+  std::vector<SRHeader> hd;
+  int r = fetch_headers(h, &hd, h->cur());
+  if (r) return r;
+  for (int b = 0; b < h->B; ++b) status[b] = hd[b].status;
+  return VLOAM_OK;
+}
+
+int vloam_get_feature_counts(vloam_lidar* h, int* counts) {
+  if (!h || !counts) return VLOAM_E_INVALID;
+  if (h->frame < 0) return fail(h->ctx, VLOAM_E_STATE, "no scan registered yet");
+  std::vector<SRHeader> hd;
+  int r = fetch_headers(h, &hd, h->cur());
+  if (r) return r;
+  for (int b = 0; b < h->B; ++b) {
+    counts[b * 5 + 0] = hd[b].cloudSize; counts[b * 5 + 1] = hd[b].nSharp; counts[b * 5 + 2] = hd[b].nLessSharp;
+    counts[b * 5 + 3] = hd[b].nFlat; counts[b * 5 + 4] = hd[b].nLessFlat;
+  }
+  return VLOAM_OK;
+}
+
+static int copy_out(vloam_ctx* c, void* dst, const void* src_dev, size_t elem, int n, int capacity, int* n_out) {
+  if (n_out) *n_out = n;
+  const int m = n < capacity ? n : capacity;
+  if (m > 0 && dst) {
+    CU(c, cudaMemcpyAsync(dst, src_dev, (size_t)m * elem, cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  return VLOAM_OK;
+}
+
+int vloam_get_cloud(vloam_lidar* h, int stream, int which, float* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  if (h->frame < 0) return fail(c, VLOAM_E_STATE, "no scan registered yet");
+  CU(c, cudaSetDevice(c->device));
+  if (which >= VLOAM_CLOUD_CORNER_STACK) return lm_get_cloud(h->lm, c->stream, stream, which, out, capacity, n_out) == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "lm_get_cloud");
+  std::vector<SRHeader> hd;
+  // CORNER_LAST / SURF_LAST are the current scan's less-sharp / less-flat clouds once laser odometry has run
+  // (the swap at laser_odometry.cpp:511-517), the previous scan's before.
+  int slot = h->cur();
+  if ((which == VLOAM_CLOUD_CORNER_LAST || which == VLOAM_CLOUD_SURF_LAST) && !h->lo_done_for_frame) {
+    if (h->frame < 1) { if (n_out) *n_out = 0; return VLOAM_OK; }
+    slot ^= 1;
+  }
+  int r = fetch_headers(h, &hd, slot);
+  if (r) return r;
+  const SRHeader& H = hd[stream];
+  const size_t b = stream;
+  switch (which) {
+    case VLOAM_CLOUD_FULL: return copy_out(c, out, h->d_cloud[slot] + b * h->cap, 16, H.cloudSize, capacity, n_out);
+    case VLOAM_CLOUD_SHARP: return copy_out(c, out, h->d_sharp + b * kMaxSharp, 16, H.nSharp, capacity, n_out);
+    case VLOAM_CLOUD_LESS_SHARP:
+    case VLOAM_CLOUD_CORNER_LAST: return copy_out(c, out, h->d_lessSharp[slot] + b * kMaxLessSharp, 16, H.nLessSharp, capacity, n_out);
+    case VLOAM_CLOUD_FLAT: return copy_out(c, out, h->d_flat + b * kMaxFlat, 16, H.nFlat, capacity, n_out);
+    case VLOAM_CLOUD_LESS_FLAT:
+    case VLOAM_CLOUD_SURF_LAST: return copy_out(c, out, h->d_lessFlat[slot] + b * h->cap, 16, H.nLessFlat, capacity, n_out);
+  }
+  return fail(c, VLOAM_E_INVALID, "vloam_get_cloud: unknown selector");
+}
+
+int vloam_get_curvature(vloam_lidar* h, int stream, float* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  if (h->frame < 0) return fail(h->ctx, VLOAM_E_STATE, "no scan registered yet");
+  std::vector<SRHeader> hd;
+  int r = fetch_headers(h, &hd, h->cur());
+  if (r) return r;
+  return copy_out(h->ctx, out, h->d_curv + (size_t)stream * h->cap, 4, hd[stream].cloudSize, capacity, n_out);
+}
+int vloam_get_labels(vloam_lidar* h, int stream, int8_t* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  if (h->frame < 0) return fail(h->ctx, VLOAM_E_STATE, "no scan registered yet");
+  std::vector<SRHeader> hd;
+  int r = fetch_headers(h, &hd, h->cur());
+  if (r) return r;
+  return copy_out(h->ctx, out, h->d_label + (size_t)stream * h->cap, 1, hd[stream].cloudSize, capacity, n_out);
+}
+int vloam_get_feature_indices(vloam_lidar* h, int stream, int which, int* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  if (h->frame < 0) return fail(h->ctx, VLOAM_E_STATE, "no scan registered yet");
+  std::vector<SRHeader> hd;
+  int r = fetch_headers(h, &hd, h->cur());
+  if (r) return r;
+  const size_t b = stream;
+  switch (which) {
+    case VLOAM_CLOUD_SHARP: return copy_out(h->ctx, out, h->d_sharpIdx + b * kMaxSharp, 4, hd[stream].nSharp, capacity, n_out);
+    case VLOAM_CLOUD_LESS_SHARP: return copy_out(h->ctx, out, h->d_lessSharpIdx + b * kMaxLessSharp, 4, hd[stream].nLessSharp, capacity, n_out);
+    case VLOAM_CLOUD_FLAT: return copy_out(h->ctx, out, h->d_flatIdx + b * kMaxFlat, 4, hd[stream].nFlat, capacity, n_out);
+  }
+  return fail(h->ctx, VLOAM_E_INVALID, "vloam_get_feature_indices: which must be SHARP, LESS_SHARP or FLAT");
+}
+
+// ------------------------------------------------------------------------------------------------ laser odometry
+static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
+  vloam_ctx* c = h->ctx;
+  if (h->frame < 0) return fail(c, VLOAM_E_STATE, "laser odometry before scan registration");
+  if (h->lo_done_for_frame) return fail(c, VLOAM_E_STATE, "laser odometry already run for this scan");
+  const int cur = h->cur(), last = cur ^ 1;
+  if (h->frame >= 1) {  // systemInited (laser_odometry.cpp:196-205)
+    const double* prior = h->p.detach_VO_LO ? nullptr : prior_dev;
+    const int passes = h->p.lo_outer_passes;
+    for (int pass = 0; pass < passes; ++pass) {
+      launch_lo_pass(c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
+                     h->d_lessSharp[last], h->d_lessFlat[last], h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
+                     h->p.lo_max_iterations, pass == passes - 1, prior);
+      c->launches += prior ? 3 : 2;
+    }
+  }
+  launch_lo_export(c->stream, h->d_lo, h->d_pose, h->B); c->launches++;
+  CU(c, cudaGetLastError());
+  h->lo_done_for_frame = true;
+  h->lo_frames++;
+  return VLOAM_OK;
+}
+
+int vloam_laser_odometry_async(vloam_lidar* h, const double* prior_dev) {
+  if (!h) return VLOAM_E_INVALID;
+  CU(h->ctx, cudaSetDevice(h->ctx->device));
+  return run_laser_odometry(h, prior_dev);
+}
+
+int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out) {
+  if (!h) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int b = 0; b < h->B; ++b) {
+    if (pose_out) std::memcpy(pose_out + (size_t)b * 14, h->h_pose + (size_t)b * 16, 14 * sizeof(double));
+    if (corr_out) { corr_out[b * 2] = (int)h->h_pose[b * 16 + 14]; corr_out[b * 2 + 1] = (int)h->h_pose[b * 16 + 15]; }
+  }
+  return VLOAM_OK;
+}
+
+int vloam_laser_odometry(vloam_lidar* h, const double* prior, double* pose_out, int* corr_out) {
+  if (!h) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  const double* prior_dev = nullptr;
+  if (prior && !h->p.detach_VO_LO) {
+    CU(c, cudaMemcpyAsync(h->d_prior, prior, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    prior_dev = h->d_prior;
+  }
+  int r = run_laser_odometry(h, prior_dev);
+  if (r) return r;
+  if (pose_out || corr_out) return vloam_get_lo_pose(h, pose_out, corr_out);
+  return VLOAM_OK;
+}
+
+int vloam_set_lo_motion(vloam_lidar* h, const double* motion) {
+  if (!h || !motion) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(h->d_prior, motion, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_lo_set_motion(c->stream, h->d_lo, h->d_prior, h->B); c->launches++;
+  CU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+int vloam_get_lo_trace(vloam_lidar* h, int stream, int pass, int* corr, double* records, int* info, double* para) {
+  if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  LOState st;
+  CU(c, cudaMemcpyAsync(&st, h->d_lo + stream, sizeof(LOState), cudaMemcpyDeviceToHost, c->stream));
+  if (corr)
+    CU(c, cudaMemcpyAsync(corr, h->d_corr[pass] + (size_t)stream * (kMaxSharp + kMaxFlat),
+                          (size_t)(kMaxSharp + kMaxFlat) * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  const SolveTrace& t = st.trace[pass];
+  if (info) { info[0] = t.n_records; info[1] = t.termination; info[2] = t.n_corner; info[3] = t.n_plane; }
+  if (para) std::memcpy(para, t.para, sizeof(t.para));
+  if (records) std::memcpy(records, t.rec, sizeof(t.rec));
+  return VLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ laser mapping
+int vloam_laser_mapping(vloam_lidar* h, double* pose_out) {
+  if (!h) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  if (!h->lo_done_for_frame) return fail(c, VLOAM_E_STATE, "laser mapping before laser odometry");
+  // LaserOdometry::output (laser_odometry.cpp:618-628): frames with frameCount % mapping_skip_frame != 0 are skipped
+  const bool skip = (h->lo_frames % h->p.mapping_skip_frame) != 0;
+  const int cur = h->cur();
+  long long launches = 0;
+  cudaError_t e = lm_run(h->lm, c->stream, h->d_hdr[cur], h->d_lessSharp[cur], h->d_lessFlat[cur], h->d_lo, skip, &launches);
+  c->launches += launches;
+  if (e != cudaSuccess) return fail(c, VLOAM_E_CUDA, "vloam_laser_mapping", e);
+  if (pose_out) return vloam_get_lm_pose(h, pose_out);
+  return VLOAM_OK;
+}
+int vloam_get_lm_pose(vloam_lidar* h, double* pose_out) {
+  if (!h || !pose_out) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_pose(h->lm, c->stream, pose_out);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_pose", e);
+}
+int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const float* xyzi, int n) {
+  if (!h || stream < 0 || stream >= h->B || kind < 0 || kind > 1 || cube < 0 || cube >= 4851 || n < 0 || (n && !xyzi)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_set_cube(h->lm, c->stream, stream, kind, cube, xyzi, n);
+  if (e == cudaErrorInvalidValue) return fail(c, VLOAM_E_CAPACITY, "vloam_map_set_cube: map_capacity_points exceeded");
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_map_set_cube", e);
+}
+int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B || kind < 0 || kind > 1 || cube < 0 || cube >= 4851) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_cube(h->lm, c->stream, stream, kind, cube, out, capacity, n_out);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_map_get_cube", e);
+}
+int vloam_get_lm_info(vloam_lidar* h, int* info) {
+  if (!h || !info) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_info(h->lm, c->stream, info);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_info", e);
+}
+int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para) {
+  if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_trace(h->lm, c->stream, stream, pass, records, info, para);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_trace", e);
+}
+
+}  // extern "C"
