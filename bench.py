@@ -1,0 +1,394 @@
+#!/usr/bin/env python
+"""bench.py — scans/sec of the VLOAM per-scan LiDAR hot path on B200 (BASELINE.json metric).
+
+Workload at N = 1 (BASELINE.json configs[1]): scanRegistration + laserOdometry over a synthetic HDL-64
+64 x 2048 range-image stream, `--batch` independent streams driven in lock-step by one handle
+(`--workload sr_lo_lm` adds laserMapping = configs[2]).  One *step* = one scan of every stream through the
+whole path.  Three measurements of the same work:
+
+  value  inputs already resident in HBM (a pool of scans larger than L2), timed with CUDA events on the
+         launching stream, barrier + synchronize on both sides, max over ranks;
+  e2e    the same steps through the reference-facing API with HOST buffers: pinned host -> device upload
+         of every scan and device -> host read of the poses inside the timed region;
+  cpu_baseline / --impl reference
+         the CPU oracle (oracle/: restatement of the reference's Ceres/PCL path; the reference itself cannot
+         be built here) timed on the box's host cores.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for the algorithmic-byte model behind `roofline`.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_RINGS, N_COLS = 64, 2048
+POOL_SCANS = 4          # consecutive scans per base sequence, visited ping-pong 0 1 2 3 2 1 0 ...
+N_BASE = 4              # distinct base sequences, tiled across the batch
+BENCH_SEED = 1234
+
+
+def pingpong(i: int, n: int) -> int:
+    p = i % (2 * n - 2)
+    return p if p < n else 2 * n - 2 - p
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        self.idx = gpu_index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.05)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            f = [x.strip() for x in r.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def make_base_scans(rank: int):
+    """N_BASE sequences x POOL_SCANS scans, float32 (n, 3), NaN = no return."""
+    from vloam_b200 import synth
+    seqs = []
+    for i in range(N_BASE):
+        s = synth.ScanStream(BENCH_SEED + 16 * rank + i, n_cols=N_COLS)
+        seqs.append([s.scan(k) for k in range(POOL_SCANS)])
+    return seqs
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def run_reference(args, rank):
+    """The reference's CPU path (oracle port: the reference needs ROS/PCL/Ceres/Eigen, none installed) on all host
+    threads: one independent stream per thread; a step = one scan on every thread."""
+    if rank != 0:
+        return
+    from oracle import pyoracle as O
+    from concurrent.futures import ThreadPoolExecutor
+    O.build()
+    T = max(1, len(os.sched_getaffinity(0)))
+    do_map = args.workload == "sr_lo_lm"
+    seqs = make_base_scans(0)
+    pipes = [O.Pipeline() for _ in range(T)]
+
+    def one(t, i):
+        pipes[t].process(seqs[t % N_BASE][pingpong(i, POOL_SCANS)], do_mapping=do_map)
+
+    with ThreadPoolExecutor(T) as ex:
+        for i in range(args.warmup):
+            list(ex.map(lambda t: one(t, i), range(T)))
+        t0 = time.perf_counter()
+        for i in range(args.warmup, args.warmup + args.steps):
+            list(ex.map(lambda t: one(t, i), range(T)))
+        dt = time.perf_counter() - t0
+    value = T * args.steps / dt
+    tm = pipes[0].timings()
+    line = {
+        "impl": "reference", "metric": "scans/sec (HDL-64, 64x2048 pts) scanRegistration+laserOdometry" + ("+laserMapping" if do_map else ""),
+        "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 points / f64 solve", "data": "synthetic",
+        "config": {"workload": "configs[1]: scanRegistration + laserOdometry, synthetic 64x2048 stream" if not do_map
+                   else "configs[2]: laserOdometry + laserMapping", "streams": T, "points_per_scan": N_RINGS * N_COLS},
+        "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
+                         "sample": f"{T} threads x {args.steps} scans, one stream per thread; per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
+                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms per scan"},
+        "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------- our arm (B200)
+def algorithmic_bytes(kernel, c):
+    """Algorithmic HBM bytes of ONE launch of `kernel` over the whole batch (DESIGN.md "Measurement").
+    c: dict of batch totals: N (input points), Np (kept points), nLF, nLS, nSharp, nFlat (current scan features),
+    nLFlast, nLSlast (previous scan's targets)."""
+    feats = c["nSharp"] + c["nLS"] + c["nFlat"]
+    table = {
+        "sr_find_ends": 0,
+        "sr_classify": c["N"] * (12 + 1),                                   # xyz read, ring id written
+        "sr_scan": 0,
+        "sr_scatter": c["N"] * (12 + 1) + c["Np"] * 16,                    # xyz + ring id read, XYZI written
+        "sr_curvature": c["Np"] * 20,                                       # XYZI read, curvature written
+        "sr_ring_features": c["Np"] * (16 + 4 + 1) + c["nLF"] * 16 + feats * 4,
+        "sr_pack": c["nLF"] * 32 + feats * (4 + 16 + 16 + 4),
+        "lo_associate": (c["nSharp"] + c["nFlat"]) * 32 + (c["nLSlast"] + c["nLFlast"]) * 16,
+        "lo_solve": (c["nSharp"] + c["nFlat"]) * 16 + c["nSharp"] * 48 + c["nFlat"] * 64,
+        "lo_export_pose": 0,
+    }
+    return table.get(kernel, 0)
+
+
+def run_ours(args, rank, world, local_rank):
+    import torch
+    import vloam_b200 as V
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_
+        dist = dist_
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    do_map = args.workload == "sr_lo_lm"
+    cap = N_RINGS * N_COLS
+    seqs = make_base_scans(rank)
+
+    # pools: POOL_SCANS tensors of [B, cap, 3]; stream b replays base sequence b % N_BASE
+    host_pool, dev_pool = [], []
+    for k in range(POOL_SCANS):
+        h = torch.empty((B, cap, 3), dtype=torch.float32).pin_memory()
+        hv = h.numpy()
+        for b in range(B):
+            hv[b] = seqs[b % N_BASE][k]
+        host_pool.append(h)
+        dev_pool.append(h.to(dev, non_blocking=True))
+    n_host = np.full(B, cap, np.int32)
+    n_dev = torch.from_numpy(n_host).to(dev)
+    torch.cuda.synchronize()
+    pool_bytes = POOL_SCANS * B * cap * 12
+
+    stream = torch.cuda.Stream(device=dev)
+    ctx = V.Context(device=local_rank, cuda_stream=stream.cuda_stream)
+
+    def make_handle(batch):
+        return V.LidarOdometryMapping(ctx, batch=batch, max_points=cap)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank)
+
+    # ---------------- leg 1: device-resident inputs -> `value`
+    lom = make_handle(B)
+
+    def step_dev(i):
+        k = pingpong(i, POOL_SCANS)
+        lom.reset()
+        lom.scanRegistrationDevice(dev_pool[k], n_dev, 3, cap)
+        lom.laserOdometryIO(fetch=False)
+        if do_map:
+            lom.laserMappingIO(fetch=False)
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_dev(i)
+        barrier()
+        ctx.enable_timing(True)
+        ctx.kernel_timings(reset=True)
+        launches0 = ctx.launch_count
+        if rank == 0:
+            sampler.start()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, args.warmup + args.steps):
+            step_dev(i)
+        e1.record(stream)
+        barrier()
+        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        clocks = sampler.stop() if rank == 0 else None
+        launches = ctx.launch_count - launches0
+        ktimes = ctx.kernel_timings(reset=True)
+        ctx.enable_timing(False)
+        counts = lom.feature_counts().astype(np.int64)
+        pose_dev = lom.lo_pose()
+    value = world * B * args.steps / (ms_dev * 1e-3)
+
+    # ---------------- leg 2: host buffers through the public API -> `e2e`
+    lom2 = make_handle(B)
+
+    def step_host(i):
+        k = pingpong(i, POOL_SCANS)
+        lom2.reset()
+        lom2.scanRegistrationIO(host_pool[k], n_host)   # pinned host -> device inside
+        p = lom2.laserOdometryIO(fetch=not do_map)      # device -> host pose read (synchronises)
+        if do_map:
+            p = lom2.laserMappingIO(fetch=True)
+        return p
+
+    with torch.cuda.stream(stream):
+        for i in range(args.warmup):
+            step_host(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for i in range(args.warmup, args.warmup + args.steps):
+            pose_host = step_host(i)
+        e1.record(stream)
+        barrier()
+        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    h2d = int(B * cap * 12 + B * 4)
+    d2h = int(B * 16 * 8)
+    # same inputs, same number of steps -> both legs must end on identical poses
+    same = bool(np.array_equal(pose_dev["t_w_curr"], (pose_host["t_w_curr"] if not do_map else pose_dev["t_w_curr"])))
+
+    # ---------------- leg 3: single-stream latency (batch = 1), context only
+    lat_ms = None
+    if rank == 0:
+        lom1 = make_handle(1)
+        one_dev = [dev_pool[k][0:1].contiguous() for k in range(POOL_SCANS)]
+        n1 = n_dev[0:1].contiguous()
+        with torch.cuda.stream(stream):
+            def step1(i):
+                lom1.reset()
+                lom1.scanRegistrationDevice(one_dev[pingpong(i, POOL_SCANS)], n1, 3, cap)
+                lom1.laserOdometryIO(fetch=False)
+            for i in range(5):
+                step1(i)
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for i in range(5, 45):
+                step1(i)
+            b_.record(stream)
+            torch.cuda.synchronize()
+            lat_ms = a.elapsed_time(b_) / 40
+        lom1.close()
+
+    if rank != 0:
+        return
+
+    # ---------------- roofline of the dominant kernel
+    peaks, peak_kind = load_peaks()
+    tot = {"N": int(B * cap), "Np": int(counts[:, 0].sum()), "nSharp": int(counts[:, 1].sum()), "nLS": int(counts[:, 2].sum()),
+           "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
+    tot["nLSlast"], tot["nLFlast"] = tot["nLS"], tot["nLF"]
+    kern = {}
+    for name, (ms, cnt) in ktimes.items():
+        by = algorithmic_bytes(name, tot)
+        kern[name] = {"ms_total": ms, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share": None,
+                      "alg_bytes_per_launch": by, "gbs": (by / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
+    ksum = sum(v["ms_total"] for v in kern.values()) or 1.0
+    for v in kern.values():
+        v["share"] = v["ms_total"] / ksum
+    dom = max(kern, key=lambda k: kern[k]["ms_total"])
+    roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
+            "frac": (kern[dom]["gbs"] or 0.0) / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
+            "note": "achieved = algorithmic bytes per launch / CUDA-event duration; traffic (ncu dram bytes) in profiles/"}
+    curv = kern.get("sr_curvature")
+
+    # ---------------- CPU baseline: oracle, 1 thread, bounded sample
+    from oracle import pyoracle as O
+    O.build()
+    pipe = O.Pipeline()
+    n_cpu = args.cpu_scans
+    t0 = time.perf_counter()
+    for i in range(n_cpu):
+        pipe.process(seqs[0][pingpong(i, POOL_SCANS)], do_mapping=do_map)
+    cpu_dt = time.perf_counter() - t0
+    tm = pipe.timings()
+    cpu_value = n_cpu / cpu_dt
+
+    line = {
+        "metric": "scans/sec (HDL-64, 64x2048 pts) scanRegistration+laserOdometry" + ("+laserMapping" if do_map else ""),
+        "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
+        "config": {"workload": ("configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"
+                                if not do_map else "configs[2]: laserOdometry + laserMapping scan-to-submap"),
+                   "streams_per_gpu": B, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
+                   "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
+                   "parallelism": f"stream-sharded x{world} (no data-path collective)"},
+        "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same},
+        "gpu_launches": int(launches),
+        "roofline": roof,
+        "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kern.items()},
+        "curvature_kernel": None if curv is None else {"gbs": curv["gbs"], "frac": curv["gbs"] / peaks["hbm_gbs"]},
+        "single_stream_latency_ms": lat_ms,
+        "cpu_baseline": {"value": cpu_value, "unit": "scans/s", "cores": 1, "kind": "port",
+                         "sample": f"{n_cpu} scans of one stream, 1 thread: SR {tm['sr_ms']/n_cpu:.1f} ms + LO {tm['lo_ms']/n_cpu:.1f} ms"
+                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + " per scan"},
+        "clocks": clocks,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=128, help="independent streams per GPU")
+    ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm"])
+    ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

@@ -73,6 +73,13 @@ int vloam_ctx_synchronize(vloam_ctx* ctx);
 const char* vloam_last_error(vloam_ctx* ctx);
 /* Number of kernel launches issued by this context since creation (bench.py's gpu_launches). */
 long long vloam_ctx_launch_count(vloam_ctx* ctx);
+/* Optional per-kernel timing: when enabled every kernel launch is bracketed by CUDA events on the launching
+ * stream; vloam_ctx_get_kernel_timings synchronises and returns accumulated milliseconds / launch counts per
+ * kernel id (0 .. vloam_ctx_kernel_count()-1).  Replaces the reference's TicToc prints. */
+int vloam_ctx_enable_timing(vloam_ctx* ctx, int on);
+int vloam_ctx_kernel_count(void);
+const char* vloam_ctx_kernel_name(int id);
+int vloam_ctx_get_kernel_timings(vloam_ctx* ctx, double* ms, long long* counts, int reset);
 
 /* ------------------------------------------------------------------ LiDAR odometry + mapping
  * Parameters = the ROS parameters the reference reads

@@ -3,15 +3,15 @@
 Bars (BASELINE.json north_star): identical edge / plane index sets; pose within 1e-4 m / 1e-4 rad after the
 same iteration count.  Integer / index / float-bit work is compared bit-exactly; the only toleranced float
 is the fractional part of `intensity` (ring + 0.1 * relTime), which goes through atan2f whose last-ulp
-behaviour differs between glibc and CUDA libm (tolerance 2e-6; the integer part, the only part the
-reference uses with DISTORTION=false, must match exactly).
+behaviour differs between glibc and CUDA libm (tolerance 4e-6 = one float ulp at ring 63; the integer part,
+the only part the reference uses with DISTORTION=false, must match exactly).
 """
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
-INTENSITY_TOL = 2e-6
+INTENSITY_TOL = 4e-6
 POSE_TOL_M = 1e-4
 POSE_TOL_RAD = 1e-4
 

@@ -71,7 +71,9 @@ def lib():
         pp = C.POINTER(vp)
         sig = {
             "vloam_ctx_create": [C.c_int, pp], "vloam_ctx_destroy": [vp], "vloam_ctx_set_stream": [vp, vp],
-            "vloam_ctx_synchronize": [vp], "vloam_lidar_params_default": [C.POINTER(LidarParams)],
+            "vloam_ctx_synchronize": [vp], "vloam_ctx_enable_timing": [vp, C.c_int],
+            "vloam_ctx_get_kernel_timings": [vp, c_dp, C.POINTER(C.c_longlong), C.c_int],
+            "vloam_lidar_params_default": [C.POINTER(LidarParams)],
             "vloam_lidar_create": [vp, C.POINTER(LidarParams), pp], "vloam_lidar_destroy": [vp], "vloam_lidar_reset": [vp],
             "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
@@ -101,6 +103,10 @@ def lib():
             fn.argtypes = args
         L.vloam_last_error.restype = C.c_char_p
         L.vloam_last_error.argtypes = [vp]
+        L.vloam_ctx_kernel_count.restype = C.c_int
+        L.vloam_ctx_kernel_count.argtypes = []
+        L.vloam_ctx_kernel_name.restype = C.c_char_p
+        L.vloam_ctx_kernel_name.argtypes = [C.c_int]
         L.vloam_ctx_launch_count.restype = C.c_longlong
         L.vloam_ctx_launch_count.argtypes = [vp]
         _lib = L
@@ -149,6 +155,18 @@ class Context:
     @property
     def launch_count(self) -> int:
         return int(lib().vloam_ctx_launch_count(self._h))
+
+    def enable_timing(self, on: bool = True):
+        self.check(lib().vloam_ctx_enable_timing(self._h, int(on)))
+
+    def kernel_timings(self, reset: bool = True) -> dict:
+        """{kernel name: (total ms, launches)} measured with CUDA events on the launching stream."""
+        n = lib().vloam_ctx_kernel_count()
+        ms = np.zeros(n)
+        cnt = np.zeros(n, np.int64)
+        self.check(lib().vloam_ctx_get_kernel_timings(self._h, ms.ctypes.data_as(c_dp),
+                                                      cnt.ctypes.data_as(C.POINTER(C.c_longlong)), int(reset)))
+        return {lib().vloam_ctx_kernel_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n) if cnt[i]}
 
     def close(self):
         if self._h:

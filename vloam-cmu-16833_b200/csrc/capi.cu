@@ -17,8 +17,51 @@ struct vloam_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   std::string last_error;
-  long long launches = 0;
+  Profiler prof;
 };
+
+namespace vb {
+const char* kernel_name(int id) {
+  static const char* names[K_COUNT] = {
+      "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_ring_features", "sr_pack",
+      "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state",
+      "lm_prepare", "lm_voxel", "lm_grid", "lm_associate", "lm_solve", "lm_insert", "lm_refilter", "lm_misc",
+      "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc"};
+  return (id >= 0 && id < K_COUNT) ? names[id] : "?";
+}
+cudaEvent_t Profiler::get() {
+  if (!pool.empty()) { cudaEvent_t e = pool.back(); pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+void Profiler::begin(int id, cudaStream_t st) {
+  ++launches;
+  if (!enabled) return;
+  cur_a = get(); cur_id = id;
+  cudaEventRecord(cur_a, st);
+}
+void Profiler::end(cudaStream_t st) {
+  if (!enabled || cur_id < 0) return;
+  cudaEvent_t b = get();
+  cudaEventRecord(b, st);
+  recs.push_back({cur_id, cur_a, b});
+  cur_id = -1;
+}
+void Profiler::collect() {
+  for (const Rec& r : recs) {
+    float t = 0.f;
+    if (cudaEventElapsedTime(&t, r.a, r.b) == cudaSuccess) { ms[r.id] += t; cnt[r.id]++; }
+    pool.push_back(r.a); pool.push_back(r.b);
+  }
+  recs.clear();
+}
+void Profiler::clear() { for (int i = 0; i < K_COUNT; ++i) { ms[i] = 0; cnt[i] = 0; } }
+Profiler::~Profiler() {
+  collect();
+  for (cudaEvent_t e : pool) cudaEventDestroy(e);
+}
+}  // namespace vb
 
 namespace {
 
@@ -117,7 +160,23 @@ int vloam_ctx_synchronize(vloam_ctx* c) {
   return VLOAM_OK;
 }
 const char* vloam_last_error(vloam_ctx* c) { return c ? c->last_error.c_str() : "null context"; }
-long long vloam_ctx_launch_count(vloam_ctx* c) { return c ? c->launches : 0; }
+long long vloam_ctx_launch_count(vloam_ctx* c) { return c ? c->prof.launches : 0; }
+int vloam_ctx_enable_timing(vloam_ctx* c, int on) {
+  if (!c) return VLOAM_E_INVALID;
+  c->prof.enabled = on != 0;
+  return VLOAM_OK;
+}
+int vloam_ctx_kernel_count(void) { return K_COUNT; }
+const char* vloam_ctx_kernel_name(int id) { return kernel_name(id); }
+int vloam_ctx_get_kernel_timings(vloam_ctx* c, double* ms, long long* counts, int reset) {
+  if (!c) return VLOAM_E_INVALID;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  c->prof.collect();
+  for (int i = 0; i < K_COUNT; ++i) { if (ms) ms[i] = c->prof.ms[i]; if (counts) counts[i] = c->prof.cnt[i]; }
+  if (reset) c->prof.clear();
+  return VLOAM_OK;
+}
 
 // ------------------------------------------------------------------------------------------------ lidar handle
 int vloam_lidar_params_default(vloam_lidar_params* p) {
@@ -182,8 +241,8 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   A(dalloc(&h->d_lo, B)); A(dalloc(&h->d_prior, B * 7)); A(dalloc(&h->d_pose, B * 16));
   A(cudaMallocHost((void**)&h->h_pose, B * 16 * sizeof(double)));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
-  launch_lo_init(c->stream, h->d_lo, h->B); c->launches++;
-  e = lm_create(c->stream, h->B, h->cap, p, &h->lm);
+  launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
+  e = lm_create(&c->prof, c->stream, h->B, h->cap, p, &h->lm);
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, VLOAM_E_CUDA, "vloam_lidar_create: map allocation", e); }
   CU(c, cudaStreamSynchronize(c->stream));
   *out = h;
@@ -204,12 +263,11 @@ static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int
   h->frame++;
   h->lo_done_for_frame = false;
   const int cur = h->cur();
-  launch_scan_registration(c->stream, h->B, h->cap, xyz_dev, stride, slab_points * (size_t)stride, n_dev,
+  launch_scan_registration(&c->prof, c->stream, h->B, h->cap, xyz_dev, stride, slab_points * (size_t)stride, n_dev,
                            (float)h->p.minimum_range, h->p.scan_line, h->d_hdr[cur], h->d_ring8, h->d_blockHist,
                            h->d_cloud[cur], h->d_curv, h->d_label, h->d_featIdx, h->d_lessFlatStage, h->d_sharp,
                            h->d_sharpIdx, h->d_lessSharp[cur], h->d_lessSharpIdx, h->d_flat, h->d_flatIdx,
                            h->d_lessFlat[cur]);
-  c->launches += 7;
   CU(c, cudaGetLastError());
   return VLOAM_OK;
 }
@@ -349,13 +407,12 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
     const double* prior = h->p.detach_VO_LO ? nullptr : prior_dev;
     const int passes = h->p.lo_outer_passes;
     for (int pass = 0; pass < passes; ++pass) {
-      launch_lo_pass(c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
+      launch_lo_pass(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
                      h->d_lessSharp[last], h->d_lessFlat[last], h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
                      h->p.lo_max_iterations, pass == passes - 1, prior);
-      c->launches += prior ? 3 : 2;
     }
   }
-  launch_lo_export(c->stream, h->d_lo, h->d_pose, h->B); c->launches++;
+  launch_lo_export(&c->prof, c->stream, h->d_lo, h->d_pose, h->B);
   CU(c, cudaGetLastError());
   h->lo_done_for_frame = true;
   h->lo_frames++;
@@ -401,7 +458,7 @@ int vloam_set_lo_motion(vloam_lidar* h, const double* motion) {
   vloam_ctx* c = h->ctx;
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(h->d_prior, motion, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-  launch_lo_set_motion(c->stream, h->d_lo, h->d_prior, h->B); c->launches++;
+  launch_lo_set_motion(&c->prof, c->stream, h->d_lo, h->d_prior, h->B);
   CU(c, cudaStreamSynchronize(c->stream));
   return VLOAM_OK;
 }
@@ -432,9 +489,7 @@ int vloam_laser_mapping(vloam_lidar* h, double* pose_out) {
   // LaserOdometry::output (laser_odometry.cpp:618-628): frames with frameCount % mapping_skip_frame != 0 are skipped
   const bool skip = (h->lo_frames % h->p.mapping_skip_frame) != 0;
   const int cur = h->cur();
-  long long launches = 0;
-  cudaError_t e = lm_run(h->lm, c->stream, h->d_hdr[cur], h->d_lessSharp[cur], h->d_lessFlat[cur], h->d_lo, skip, &launches);
-  c->launches += launches;
+  cudaError_t e = lm_run(h->lm, c->stream, h->d_hdr[cur], h->d_lessSharp[cur], h->d_lessFlat[cur], h->d_lo, skip);
   if (e != cudaSuccess) return fail(c, VLOAM_E_CUDA, "vloam_laser_mapping", e);
   if (pose_out) return vloam_get_lm_pose(h, pose_out);
   return VLOAM_OK;

@@ -5,32 +5,69 @@
 
 #include "common.cuh"
 
+#include <vector>
+
 struct vloam_lidar_params;
 
 namespace vb {
 
+// Kernel ids for the launch counter / optional CUDA-event timing (vloam_ctx_enable_timing).
+enum KernelId {
+  K_SR_FIND_ENDS = 0, K_SR_CLASSIFY, K_SR_SCAN, K_SR_SCATTER, K_SR_CURVATURE, K_SR_RING_FEATURES, K_SR_PACK,
+  K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT,
+  K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_MISC,
+  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC,
+  K_COUNT
+};
+const char* kernel_name(int id);
+
+// Counts every launch; when `enabled`, brackets each launch with CUDA events on the launching stream.
+struct Profiler {
+  bool enabled = false;
+  long long launches = 0;
+  struct Rec { int id; cudaEvent_t a, b; };
+  std::vector<Rec> recs;
+  std::vector<cudaEvent_t> pool;
+  double ms[K_COUNT] = {0};
+  long long cnt[K_COUNT] = {0};
+  cudaEvent_t cur_a = nullptr;
+  int cur_id = -1;
+  cudaEvent_t get();
+  void begin(int id, cudaStream_t st);
+  void end(cudaStream_t st);
+  void collect();  // after a stream synchronize: fold the recorded events into ms[] / cnt[]
+  void clear();
+  ~Profiler();
+};
+#define VB_LAUNCH(prof, id, st, ...)      \
+  do {                                    \
+    (prof)->begin((id), (st));            \
+    __VA_ARGS__;                          \
+    (prof)->end((st));                    \
+  } while (0)
+
 // sr_kernels.cu
-void launch_scan_registration(cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
+void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
                               const int* n_points_dev, float min_range, int n_scans, SRHeader* hdr, uint8_t* ring8,
                               int* blockHist, float4* cloud, float* curv, int8_t* label, int* featIdx,
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
                               float4* flat, int* flatIdx, float4* lessFlat);
 
 // lo_kernels.cu
-void launch_lo_init(cudaStream_t st, LOState* lo, int B);
-void launch_lo_pass(cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
+void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
+void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     int4* corr, int pass, int max_iterations, int integrate, const double* prior);
-void launch_lo_export(cudaStream_t st, const LOState* lo, double* pose, int B);
-void launch_lo_set_motion(cudaStream_t st, LOState* lo, const double* motion, int B);
+void launch_lo_export(Profiler* prof, cudaStream_t st, const LOState* lo, double* pose, int B);
+void launch_lo_set_motion(Profiler* prof, cudaStream_t st, LOState* lo, const double* motion, int B);
 
 // lm_kernels.cu — laser mapping state of a batch of streams
 struct LMDevice;
-cudaError_t lm_create(cudaStream_t st, int B, int cap, const vloam_lidar_params* p, LMDevice** out);
+cudaError_t lm_create(Profiler* prof, cudaStream_t st, int B, int cap, const vloam_lidar_params* p, LMDevice** out);
 void lm_destroy(LMDevice* lm);
 void lm_reset(LMDevice* lm);
 cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const float4* cornerLast, const float4* surfLast,
-                   const LOState* lo, bool skip_frame, long long* launches);
+                   const LOState* lo, bool skip_frame);
 cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out);
 cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out);
 cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, const float* xyzi, int n);

@@ -14,6 +14,7 @@
 //
 // The Ceres semantics restated here are documented in oracle/ceres_lm.hpp.
 #include "common.cuh"
+#include "internal.h"
 
 namespace vb {
 
@@ -517,22 +518,25 @@ __global__ void lo_export_pose(const LOState* __restrict__ lo, double* __restric
   for (int i = 0; i < 3; ++i) { o[4 + i] = s.para_t[i]; o[11 + i] = s.t_w[i]; }
   o[14] = s.corner_correspondence; o[15] = s.plane_correspondence;
 }
-void launch_lo_export(cudaStream_t st, const LOState* lo, double* pose, int B) {
-  lo_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lo, pose, B);
+void launch_lo_export(Profiler* prof, cudaStream_t st, const LOState* lo, double* pose, int B) {
+  VB_LAUNCH(prof, K_LO_EXPORT, st, lo_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lo, pose, B));
 }
-void launch_lo_set_motion(cudaStream_t st, LOState* lo, const double* motion, int B) {
-  lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, motion, B);
+void launch_lo_set_motion(Profiler* prof, cudaStream_t st, LOState* lo, const double* motion, int B) {
+  VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, motion, B));
 }
 
-void launch_lo_init(cudaStream_t st, LOState* lo, int B) { lo_init_state<<<(B + 127) / 128, 128, 0, st>>>(lo, B); }
+void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B) {
+  VB_LAUNCH(prof, K_LO_INIT, st, lo_init_state<<<(B + 127) / 128, 128, 0, st>>>(lo, B));
+}
 
-void launch_lo_pass(cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
+void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     int4* corr, int pass, int max_iterations, int integrate, const double* prior) {
-  if (prior) lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B);
-  lo_associate<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(hdrCur, hdrLast, lo, sharp, flat, cornerLast,
-                                                                        surfLast, cap, corr);
-  lo_solve<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, max_iterations, integrate);
+  if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
+  VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
+                                          hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
+  VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
+                                                               max_iterations, integrate));
 }
 
 }  // namespace vb

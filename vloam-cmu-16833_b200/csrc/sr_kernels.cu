@@ -19,6 +19,7 @@
 #include <math_constants.h>
 
 #include "common.cuh"
+#include "internal.h"
 
 namespace vb {
 
@@ -661,7 +662,7 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
 
 // ---------------------------------------------------------------------------------------------
 // host-side launcher (called from capi.cu)
-void launch_scan_registration(cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
+void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
                               const int* n_points_dev, float min_range, int n_scans, SRHeader* hdr, uint8_t* ring8,
                               int* blockHist, float4* cloud, float* curv, int8_t* label, int* featIdx,
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
@@ -672,14 +673,14 @@ void launch_scan_registration(cudaStream_t st, int B, int cap, const float* xyz,
     cudaFuncSetAttribute(sr_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem));
     attr_set = true;
   }
-  sr_find_ends<<<B, 256, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr);
-  sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk);
-  sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk);
-  sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud);
-  sr_curvature<<<dim3((cap + 255) / 256, B), 256, 0, st>>>(hdr, cloud, cap, curv);
-  sr_ring_features<<<dim3(kMaxRings, B), 256, sizeof(RingSmem), st>>>(hdr, cloud, curv, cap, label, featIdx, lessFlatStage);
-  sr_pack<<<dim3(kMaxRings + 1, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx, lessSharp,
-                                                   lessSharpIdx, flat, flatIdx, lessFlat);
+  VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, 256, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
+  VB_LAUNCH(prof, K_SR_CLASSIFY, st, sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk));
+  VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
+  VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));
+  VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((cap + 255) / 256, B), 256, 0, st>>>(hdr, cloud, cap, curv));
+  VB_LAUNCH(prof, K_SR_RING_FEATURES, st, sr_ring_features<<<dim3(kMaxRings, B), 256, sizeof(RingSmem), st>>>(hdr, cloud, curv, cap, label, featIdx, lessFlatStage));
+  VB_LAUNCH(prof, K_SR_PACK, st, sr_pack<<<dim3(kMaxRings + 1, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx,
+                                                                              lessSharp, lessSharpIdx, flat, flatIdx, lessFlat));
 }
 
 }  // namespace vb
