@@ -162,10 +162,13 @@ def algorithmic_bytes(kernel, c):
         "sr_classify": c["N"] * (12 + 1),                                   # xyz read, ring id written
         "sr_scan": 0,
         "sr_scatter": c["N"] * (12 + 1) + c["Np"] * 16,                    # xyz + ring id read, XYZI written
-        "sr_curvature": c["Np"] * 20,                                       # XYZI read, curvature written
-        "sr_ring_features": c["Np"] * (16 + 4 + 1) + c["nLF"] * 16 + feats * 4,
+        "sr_curvature": c["Np"] * 21,                                       # XYZI read, curvature + gap flag written
+        "sr_pick_features": c["Np"] * (4 + 1 + 1) + feats * 4,              # curvature + gap flag read, label written
+        "sr_less_flat_voxel": c["Np"] * (1 + 16) + c["nLF"] * 16,           # label + XYZI read, centroids written
         "sr_pack": c["nLF"] * 32 + feats * (4 + 16 + 16 + 4),
-        "lo_associate": (c["nSharp"] + c["nFlat"]) * 32 + (c["nLSlast"] + c["nLFlast"]) * 16,
+        "lo_build_grid": (c["nLS"] + c["nLF"]) * (16 + 16 + 4),             # cloud read, column-sorted copy + index written
+        "lo_associate": (c["nSharp"] + c["nFlat"]) * 32 + (c["nLSlast"] + c["nLFlast"]) * 20,
+        "lo_associate_brute": (c["nSharp"] + c["nFlat"]) * 32 + (c["nLSlast"] + c["nLFlast"]) * 16,
         "lo_solve": (c["nSharp"] + c["nFlat"]) * 16 + c["nSharp"] * 48 + c["nFlat"] * 64,
         "lo_export_pose": 0,
     }

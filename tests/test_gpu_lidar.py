@@ -4,7 +4,8 @@ Bars (BASELINE.json north_star): identical edge / plane index sets; pose within 
 same iteration count.  Integer / index / float-bit work is compared bit-exactly; the only toleranced float
 is the fractional part of `intensity` (ring + 0.1 * relTime), which goes through atan2f whose last-ulp
 behaviour differs between glibc and CUDA libm (tolerance 4e-6 = one float ulp at ring 63; the integer part,
-the only part the reference uses with DISTORTION=false, must match exactly).
+the only part the reference uses with DISTORTION=false, must match exactly).  Voxel-averaged intensities (less-flat
+cloud) inherit those ulps through a float sum of up to ~10 values of magnitude <= 64: tolerance 2e-5.
 """
 import numpy as np
 import pytest
@@ -12,6 +13,7 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 INTENSITY_TOL = 4e-6
+INTENSITY_TOL_AVG = 2e-5
 POSE_TOL_M = 1e-4
 POSE_TOL_RAD = 1e-4
 
@@ -20,13 +22,13 @@ def _bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
-def _assert_cloud_equal(gpu, ref, name):
+def _assert_cloud_equal(gpu, ref, name, tol=INTENSITY_TOL):
     assert gpu.shape == ref.shape, f"{name}: {gpu.shape} vs {ref.shape}"
     if gpu.shape[0] == 0:
         return
     assert np.array_equal(_bits(gpu[:, :3]), _bits(ref[:, :3])), f"{name}: xyz not bit-identical"
     assert np.array_equal(gpu[:, 3].astype(np.int32), ref[:, 3].astype(np.int32)), f"{name}: ring ids differ"
-    assert np.max(np.abs(gpu[:, 3] - ref[:, 3])) <= INTENSITY_TOL, f"{name}: intensity fraction"
+    assert np.max(np.abs(gpu[:, 3] - ref[:, 3])) <= tol, f"{name}: intensity fraction"
 
 
 def _check_sr(lom, ref, stream=0):
@@ -45,7 +47,7 @@ def _check_sr(lom, ref, stream=0):
     _assert_cloud_equal(lom.cloud(V.CLOUD_SHARP, stream), ref.cornerPointsSharp, "sharp")
     _assert_cloud_equal(lom.cloud(V.CLOUD_LESS_SHARP, stream), ref.cornerPointsLessSharp, "lessSharp")
     _assert_cloud_equal(lom.cloud(V.CLOUD_FLAT, stream), ref.surfPointsFlat, "flat")
-    _assert_cloud_equal(lom.cloud(V.CLOUD_LESS_FLAT, stream), ref.surfPointsLessFlat, "lessFlat")
+    _assert_cloud_equal(lom.cloud(V.CLOUD_LESS_FLAT, stream), ref.surfPointsLessFlat, "lessFlat", INTENSITY_TOL_AVG)
 
 
 def _quat_angle(q1, q2):
@@ -97,7 +99,7 @@ def test_scan_registration_and_odometry_full_size(scans_full, oracle):
             assert np.allclose(pose["q_w_curr"][0], [0, 0, 0, 1]) and np.allclose(pose["t_w_curr"][0], 0)
         # the swap (laser_odometry.cpp:511-517): corner/surf "last" are now this scan's less-sharp / less-flat
         _assert_cloud_equal(lom.cloud(V.CLOUD_CORNER_LAST), ref.cornerPointsLessSharp, "cornerLast")
-        _assert_cloud_equal(lom.cloud(V.CLOUD_SURF_LAST), ref.surfPointsLessFlat, "surfLast")
+        _assert_cloud_equal(lom.cloud(V.CLOUD_SURF_LAST), ref.surfPointsLessFlat, "surfLast", INTENSITY_TOL_AVG)
     print("max |t_last_curr - oracle| =", worst)
     lom.close()
 

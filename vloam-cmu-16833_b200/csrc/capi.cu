@@ -23,8 +23,8 @@ struct vloam_ctx {
 namespace vb {
 const char* kernel_name(int id) {
   static const char* names[K_COUNT] = {
-      "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_ring_features", "sr_pack",
-      "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state",
+      "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_pick_features", "sr_less_flat_voxel", "sr_pack",
+      "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state", "lo_build_grid", "lo_associate_brute",
       "lm_prepare", "lm_voxel", "lm_grid", "lm_associate", "lm_solve", "lm_insert", "lm_refilter", "lm_misc",
       "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
@@ -104,6 +104,7 @@ struct vloam_lidar {
   int* d_blockHist = nullptr;
   float4* d_cloud[2] = {nullptr, nullptr};  // laserCloud of the current / previous scan (laserCloudFullRes)
   float* d_curv = nullptr;
+  uint8_t* d_gapflag = nullptr;
   int8_t* d_label = nullptr;
   int* d_featIdx = nullptr;
   float4* d_lessFlatStage = nullptr;
@@ -117,6 +118,7 @@ struct vloam_lidar {
   double* d_prior = nullptr;             // [B][7]
   double* d_pose = nullptr;              // [B][16]
   double* h_pose = nullptr;              // pinned
+  LOGrid grid;
   // laser mapping
   LMDevice* lm = nullptr;
   int cur() const { return (int)(frame & 1); }
@@ -203,9 +205,11 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaStreamSynchronize(h->ctx->stream);
   cudaFree(h->d_in); cudaFree(h->d_n);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_hdr[i]); cudaFree(h->d_cloud[i]); cudaFree(h->d_lessSharp[i]); cudaFree(h->d_lessFlat[i]); cudaFree(h->d_corr[i]); }
-  cudaFree(h->d_ring8); cudaFree(h->d_blockHist); cudaFree(h->d_curv); cudaFree(h->d_label); cudaFree(h->d_featIdx);
+  cudaFree(h->d_ring8); cudaFree(h->d_blockHist); cudaFree(h->d_curv); cudaFree(h->d_gapflag); cudaFree(h->d_label); cudaFree(h->d_featIdx);
   cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
   cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
+  cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); cudaFree(h->grid.sortedIdx[i]); }
   if (h->h_pose) cudaFreeHost(h->h_pose);
   if (h->lm) lm_destroy(h->lm);
   delete h;
@@ -233,12 +237,15 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
     A(dalloc(&h->d_corr[i], B * (kMaxSharp + kMaxFlat)));
   }
   A(dalloc(&h->d_ring8, B * cap)); A(dalloc(&h->d_blockHist, B * h->nblk * kMaxRings));
-  A(dalloc(&h->d_curv, B * cap)); A(dalloc(&h->d_label, B * cap));
+  A(dalloc(&h->d_curv, B * cap)); A(dalloc(&h->d_gapflag, B * cap)); A(dalloc(&h->d_label, B * cap));
   A(dalloc(&h->d_featIdx, B * kMaxRings * kSectors * 26)); A(dalloc(&h->d_lessFlatStage, B * cap));
   A(dalloc(&h->d_sharp, B * kMaxSharp)); A(dalloc(&h->d_sharpIdx, B * kMaxSharp));
   A(dalloc(&h->d_lessSharpIdx, B * kMaxLessSharp));
   A(dalloc(&h->d_flat, B * kMaxFlat)); A(dalloc(&h->d_flatIdx, B * kMaxFlat));
   A(dalloc(&h->d_lo, B)); A(dalloc(&h->d_prior, B * 7)); A(dalloc(&h->d_pose, B * 16));
+  A(dalloc(&h->grid.hdr, B * 2)); A(dalloc(&h->grid.cellStart, B * 2 * (kGridCap + 1)));
+  A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp)); A(dalloc(&h->grid.sortedIdx[0], B * kMaxLessSharp));
+  A(dalloc(&h->grid.sorted[1], B * cap)); A(dalloc(&h->grid.sortedIdx[1], B * cap));
   A(cudaMallocHost((void**)&h->h_pose, B * 16 * sizeof(double)));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
@@ -265,7 +272,7 @@ static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int
   const int cur = h->cur();
   launch_scan_registration(&c->prof, c->stream, h->B, h->cap, xyz_dev, stride, slab_points * (size_t)stride, n_dev,
                            (float)h->p.minimum_range, h->p.scan_line, h->d_hdr[cur], h->d_ring8, h->d_blockHist,
-                           h->d_cloud[cur], h->d_curv, h->d_label, h->d_featIdx, h->d_lessFlatStage, h->d_sharp,
+                           h->d_cloud[cur], h->d_curv, h->d_gapflag, h->d_label, h->d_featIdx, h->d_lessFlatStage, h->d_sharp,
                            h->d_sharpIdx, h->d_lessSharp[cur], h->d_lessSharpIdx, h->d_flat, h->d_flatIdx,
                            h->d_lessFlat[cur]);
   CU(c, cudaGetLastError());
@@ -408,10 +415,12 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
     const int passes = h->p.lo_outer_passes;
     for (int pass = 0; pass < passes; ++pass) {
       launch_lo_pass(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
-                     h->d_lessSharp[last], h->d_lessFlat[last], h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
+                     h->d_lessSharp[last], h->d_lessFlat[last], &h->grid, h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
                      h->p.lo_max_iterations, pass == passes - 1, prior);
     }
   }
+  // laser_odometry.cpp:511-526: the current less-sharp / less-flat clouds become "last" and are indexed for the next scan
+  launch_lo_build_grid(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_lessSharp[cur], h->d_lessFlat[cur], &h->grid);
   launch_lo_export(&c->prof, c->stream, h->d_lo, h->d_pose, h->B);
   CU(c, cudaGetLastError());
   h->lo_done_for_frame = true;

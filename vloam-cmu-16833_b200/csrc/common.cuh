@@ -50,6 +50,16 @@ struct SRHeader {
   int ringStartLessFlat[kMaxRings + 1];
 };
 
+// Uniform xy-column grid over one target cloud (the kd-tree replacement of laserOdometry, laser_odometry.cpp:525-526).
+// Points are counting-sorted by column; column (ix, iy) owns sorted[cellStart[iy*nx+ix] .. cellStart[iy*nx+ix+1]).
+constexpr int kGridCap = 40000;  // max columns per grid (cell table lives in shared memory while it is built)
+struct GridHeader {
+  float minx, miny, c, inv_c;
+  int nx, ny, n;
+  int monotone;                 // int(intensity) non-decreasing along the cloud (always true for ring-major clouds)
+  int firstGE[kMaxRings + 3];   // firstGE[r] = first index whose int(intensity) >= r  (r = 0 .. 65), n if none
+};
+
 // Levenberg-Marquardt trace record (mirrors oracle::LMIteration) for parity read-out.
 struct LMRecord {
   double cost, candidate_cost, model_cost_change, relative_decrease, radius;

@@ -13,8 +13,8 @@ namespace vb {
 
 // Kernel ids for the launch counter / optional CUDA-event timing (vloam_ctx_enable_timing).
 enum KernelId {
-  K_SR_FIND_ENDS = 0, K_SR_CLASSIFY, K_SR_SCAN, K_SR_SCATTER, K_SR_CURVATURE, K_SR_RING_FEATURES, K_SR_PACK,
-  K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT,
+  K_SR_FIND_ENDS = 0, K_SR_CLASSIFY, K_SR_SCAN, K_SR_SCATTER, K_SR_CURVATURE, K_SR_PICK, K_SR_VOXEL, K_SR_PACK,
+  K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT, K_LO_BUILD_GRID, K_LO_ASSOCIATE_BRUTE,
   K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_MISC,
   K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC,
   K_COUNT
@@ -49,15 +49,25 @@ struct Profiler {
 // sr_kernels.cu
 void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
                               const int* n_points_dev, float min_range, int n_scans, SRHeader* hdr, uint8_t* ring8,
-                              int* blockHist, float4* cloud, float* curv, int8_t* label, int* featIdx,
+                              int* blockHist, float4* cloud, float* curv, uint8_t* gapflag, int8_t* label, int* featIdx,
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
                               float4* flat, int* flatIdx, float4* lessFlat);
 
 // lo_kernels.cu
 void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
+// Grid index over the (corner, surf) target clouds of every stream: [B][2] headers, cell tables and sorted copies.
+struct LOGrid {
+  GridHeader* hdr = nullptr;   // [B][2]
+  int* cellStart = nullptr;    // [B][2][kGridCap + 1]
+  float4* sorted[2] = {nullptr, nullptr};  // corner: [B][kMaxLessSharp], surf: [B][cap]
+  int* sortedIdx[2] = {nullptr, nullptr};
+};
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
-                    int4* corr, int pass, int max_iterations, int integrate, const double* prior);
+                    const LOGrid* grid, int4* corr, int pass, int max_iterations, int integrate, const double* prior);
+// kd-tree rebuild of laser_odometry.cpp:525-526: index the current scan's less-sharp / less-flat clouds.
+void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
+                          const float4* lessFlat, const LOGrid* grid);
 void launch_lo_export(Profiler* prof, cudaStream_t st, const LOState* lo, double* pose, int B);
 void launch_lo_set_motion(Profiler* prof, cudaStream_t st, LOState* lo, const double* motion, int B);
 

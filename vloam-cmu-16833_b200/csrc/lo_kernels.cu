@@ -13,17 +13,76 @@
 //                           trust-region bookkeeping on-chip — no host round trip per iteration.
 //
 // The Ceres semantics restated here are documented in oracle/ceres_lm.hpp.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "internal.h"
 
 namespace vb {
 
+
+__device__ __forceinline__ int decode_order(unsigned long long k, int nT) {
+  const unsigned o = (unsigned)k;
+  return (o & 0x80000000u) ? nT - (int)(o & 0x7fffffffu) : (int)o;
+}
+
+// The reference walks the ring-major target cloud away from `closest` in both directions, classifying every point
+// by int(intensity) and stopping at the first point more than NEARBY_SCAN = 2.5 rings away (laser_odometry.cpp:
+// 279-324 / 368-417).  Literal restatement, 32 points per step: a later candidate replaces the incumbent only if
+// strictly closer, so the winner is the minimum over (distance, visiting order) with the forward walk (ascending j)
+// visited before the backward walk (descending j).  Results are warp-uniform.
+__device__ void window_walk_literal(const float4* __restrict__ T, int nT, int closest, int id, bool isCorner, float sx,
+                                    float sy, float sz, unsigned long long& k2, unsigned long long& k3) {
+  const int l = lane_id();
+  k2 = 0xffffffffffffffffull; k3 = 0xffffffffffffffffull;
+  for (int base = closest + 1; base < nT; base += 32) {  // forward
+    const int j = base + l;
+    bool brk = false, live = j < nT;
+    int rid = 0;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) { t = T[j]; rid = (int)t.w; brk = (double)rid > (double)id + 2.5; }
+    const unsigned bm = __ballot_sync(0xffffffffu, brk);
+    if (bm) live = live && l < __ffs(bm) - 1;
+    if (live) {
+      const float d = sqdist_f(t.x, t.y, t.z, sx, sy, sz);
+      if ((double)d < 25.0) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
+        if (isCorner) { if (rid > id) k2 = key < k2 ? key : k2; }
+        else if (rid <= id) k2 = key < k2 ? key : k2;
+        else k3 = key < k3 ? key : k3;
+      }
+    }
+    if (bm) break;
+  }
+  for (int base = closest - 1; base >= 0; base -= 32) {  // backward
+    const int j = base - l;
+    bool brk = false, live = j >= 0;
+    int rid = 0;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) { t = T[j]; rid = (int)t.w; brk = (double)rid < (double)id - 2.5; }
+    const unsigned bm = __ballot_sync(0xffffffffu, brk);
+    if (bm) live = live && l < __ffs(bm) - 1;
+    if (live) {
+      const float d = sqdist_f(t.x, t.y, t.z, sx, sy, sz);
+      if ((double)d < 25.0) {
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (0x80000000u + (unsigned)(nT - j));
+        if (isCorner) { if (rid < id) k2 = key < k2 ? key : k2; }
+        else if (rid >= id) k2 = key < k2 ? key : k2;
+        else k3 = key < k3 ? key : k3;
+      }
+    }
+    if (bm) break;
+  }
+  k2 = warp_min_u64(k2);
+  k3 = warp_min_u64(k3);
+}
+
 // ---------------------------------------------------------------------------------------------
-// lo_associate: one warp per query.  grid (ceil((kMaxSharp + kMaxFlat) / 8), B), block 256.
+// lo_associate_brute: one warp per query, exhaustive 1-NN (validation / fallback path, VLOAM_LO_BRUTE=1).  grid (ceil((kMaxSharp + kMaxFlat) / 8), B), block 256.
 //   query slots [0, kMaxSharp)            : corner features vs cornerLast
 //   query slots [kMaxSharp, +kMaxFlat)    : plane  features vs surfLast
 // corr[b][slot] = (closest, ind2, ind3, valid)
-__global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
+__global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
                                                      const LOState* __restrict__ lo,
                                                      const float4* __restrict__ sharp, const float4* __restrict__ flat,
                                                      const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
@@ -60,60 +119,265 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
     if (nT > 0 && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // DISTANCE_SQ_THRESHOLD (:272)
       const int closest = (int)(unsigned)best;
       const int id = (int)T[closest].w;  // closestPointScanID (:275)
-      // The reference walks the ring-major target cloud away from `closest` in both directions, classifying
-      // every point by int(intensity) and stopping at the first point more than NEARBY_SCAN = 2.5 rings away
-      // (:279-324 / :368-417).  Restated literally, 32 points per step: a later candidate replaces the
-      // incumbent only if strictly closer, so the winner is the minimum over (distance, visiting order) with
-      // the forward walk (ascending j) visited before the backward walk (descending j).
-      unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
-      for (int base = closest + 1; base < nT; base += 32) {  // forward
-        const int j = base + l;
-        bool brk = false, live = j < nT;
-        int rid = 0;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) { t = T[j]; rid = (int)t.w; brk = (double)rid > (double)id + 2.5; }
-        const unsigned bm = __ballot_sync(0xffffffffu, brk);
-        if (bm) live = live && l < __ffs(bm) - 1;
-        if (live) {
-          const float d = sqdist_f(t.x, t.y, t.z, sx, sy, sz);
-          if ((double)d < 25.0) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)j;
-            if (isCorner) { if (rid > id) k2 = key < k2 ? key : k2; }
-            else if (rid <= id) k2 = key < k2 ? key : k2;
-            else k3 = key < k3 ? key : k3;
-          }
-        }
-        if (bm) break;
-      }
-      for (int base = closest - 1; base >= 0; base -= 32) {  // backward
-        const int j = base - l;
-        bool brk = false, live = j >= 0;
-        int rid = 0;
-        float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (live) { t = T[j]; rid = (int)t.w; brk = (double)rid < (double)id - 2.5; }
-        const unsigned bm = __ballot_sync(0xffffffffu, brk);
-        if (bm) live = live && l < __ffs(bm) - 1;
-        if (live) {
-          const float d = sqdist_f(t.x, t.y, t.z, sx, sy, sz);
-          if ((double)d < 25.0) {
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (0x80000000u + (unsigned)(nT - j));
-            if (isCorner) { if (rid < id) k2 = key < k2 ? key : k2; }
-            else if (rid >= id) k2 = key < k2 ? key : k2;
-            else k3 = key < k3 ? key : k3;
-          }
-        }
-        if (bm) break;
-      }
-      k2 = warp_min_u64(k2);
-      k3 = warp_min_u64(k3);
-      auto decode = [&](unsigned long long k) {
-        const unsigned o = (unsigned)k;
-        return (o & 0x80000000u) ? nT - (int)(o & 0x7fffffffu) : (int)o;
-      };
+      unsigned long long k2, k3;
+      window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
+      auto decode = [&](unsigned long long k) { return decode_order(k, nT); };
       if (isCorner) {
         if (k2 != 0xffffffffffffffffull) out = make_int4(closest, decode(k2), -1, 1);
       } else if (k2 != 0xffffffffffffffffull && k3 != 0xffffffffffffffffull) {
         out = make_int4(closest, decode(k2), decode(k3), 1);
+      }
+    }
+  }
+  if (l == 0) corr[(size_t)b * (kMaxSharp + kMaxFlat) + slot] = out;
+}
+
+
+// ---------------------------------------------------------------------------------------------
+// Uniform xy-column grid: the exact replacement of pcl::KdTreeFLANN::setInputCloud / nearestKSearch for laser
+// odometry (laser_odometry.cpp:525-526, 269, 356).
+//
+// Exactness argument.  Columns partition the xy plane into c x c squares.  After the columns
+// [qx-k, qx+k] x [qy-k, qy+k] around the query's column have been visited, every unvisited point p satisfies
+// |p - q| >= |p - q|_xy >= R_k, where R_k is the distance from q to the border of the visited block.  The search
+// stops at the first k with best <= R_k (shrunk by a 1e-5 relative + 1e-4 m margin that dominates all float rounding
+// in the column assignment), or R_k >= 5 m: beyond 5 m the reference rejects the match (DISTANCE_SQ_THRESHOLD = 25).
+// Distances are the same float expression the brute-force kernel uses and ties break on the original index, so
+// both kernels return identical results.
+__device__ __forceinline__ int cell_coord(float v, float mn, float inv_c) { return (int)floorf((v - mn) * inv_c); }
+
+// lo_build_grid: grid (2, B), block 1024, dynamic smem = (kGridCap + 1) ints.  blockIdx.x: 0 = corner cloud, 1 = surf.
+__global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict__ hdrCur, const float4* __restrict__ lessSharp,
+                                                       const float4* __restrict__ lessFlat, int cap, GridHeader* __restrict__ ghdr,
+                                                       int* __restrict__ cellStartAll, float4* __restrict__ sortedC,
+                                                       int* __restrict__ sidxC, float4* __restrict__ sortedS, int* __restrict__ sidxS) {
+  extern __shared__ int cells[];
+  __shared__ float s_red[4][32];
+  __shared__ int s_minIdx[kMaxRings + 3];
+  __shared__ int s_mono, s_nx, s_ny;
+  __shared__ float s_c, s_minx, s_miny;
+  __shared__ int s_wsum[32];
+  const int which = blockIdx.x, b = blockIdx.y;
+  const float4* T = which == 0 ? lessSharp + (size_t)b * kMaxLessSharp : lessFlat + (size_t)b * cap;
+  float4* S = which == 0 ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
+  int* SI = which == 0 ? sidxC + (size_t)b * kMaxLessSharp : sidxS + (size_t)b * cap;
+  const int n = which == 0 ? hdrCur[b].nLessSharp : hdrCur[b].nLessFlat;
+  GridHeader& G = ghdr[b * 2 + which];
+  int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
+  const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
+  if (n == 0) {
+    if (tid == 0) { G.n = 0; G.nx = 0; G.ny = 0; G.monotone = 1; G.c = 1.f; G.inv_c = 1.f; G.minx = 0.f; G.miny = 0.f; }
+    return;
+  }
+  // ---- bounding box in xy
+  float mnx = 3.0e38f, mny = 3.0e38f, mxx = -3.0e38f, mxy = -3.0e38f;
+  for (int j = tid; j < n; j += 1024) {
+    const float4 p = T[j];
+    mnx = fminf(mnx, p.x); mxx = fmaxf(mxx, p.x); mny = fminf(mny, p.y); mxy = fmaxf(mxy, p.y);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    mnx = fminf(mnx, __shfl_xor_sync(0xffffffffu, mnx, o)); mxx = fmaxf(mxx, __shfl_xor_sync(0xffffffffu, mxx, o));
+    mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
+  }
+  if (l == 0) { s_red[0][w] = mnx; s_red[1][w] = mxx; s_red[2][w] = mny; s_red[3][w] = mxy; }
+  if (tid < kMaxRings + 3) s_minIdx[tid] = n;
+  if (tid == 0) s_mono = 1;
+  __syncthreads();
+  if (tid == 0) {
+    for (int i = 1; i < 32; ++i) {
+      mnx = fminf(mnx, s_red[0][i]); mxx = fmaxf(mxx, s_red[1][i]); mny = fminf(mny, s_red[2][i]); mxy = fmaxf(mxy, s_red[3][i]);
+    }
+    float c = 1.0f;
+    int nx, ny;
+    while (true) {
+      nx = (int)floorf((mxx - mnx) / c) + 1;
+      ny = (int)floorf((mxy - mny) / c) + 1;
+      if ((long long)nx * ny <= kGridCap) break;
+      c *= 1.25f;
+    }
+    s_c = c; s_nx = nx; s_ny = ny; s_minx = mnx; s_miny = mny;
+  }
+  __syncthreads();
+  const float c = s_c, inv_c = 1.0f / c, minx = s_minx, miny = s_miny;
+  const int nx = s_nx, ny = s_ny, ncells = nx * ny;
+  for (int i = tid; i <= ncells; i += 1024) cells[i] = 0;
+  __syncthreads();
+  // ---- histogram + ring bookkeeping
+  for (int j = tid; j < n; j += 1024) {
+    const float4 p = T[j];
+    const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
+    const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
+    atomicAdd(&cells[iy * nx + ix], 1);
+    const int rid = min(max((int)p.w, 0), kMaxRings + 1);
+    atomicMin(&s_minIdx[rid], j);
+    if (j > 0 && (int)T[j - 1].w > (int)p.w) s_mono = 0;
+  }
+  __syncthreads();
+  // ---- exclusive scan of the column counts: thread t owns a contiguous chunk
+  const int chunk = (ncells + 1023) / 1024;
+  const int c0 = min(tid * chunk, ncells), c1 = min(c0 + chunk, ncells);
+  int sum = 0;
+  for (int i = c0; i < c1; ++i) sum += cells[i];
+  int sc = sum;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
+  if (l == 31) s_wsum[w] = sc;
+  __syncthreads();
+  if (w == 0) {
+    int v = s_wsum[l], sv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sv, o); if (l >= o) sv += t; }
+    s_wsum[l] = sv - v;
+  }
+  __syncthreads();
+  int run = s_wsum[w] + sc - sum;
+  for (int i = c0; i < c1; ++i) { const int t = cells[i]; cells[i] = run; run += t; }
+  if (tid == 0) cells[ncells] = n;
+  __syncthreads();
+  for (int i = tid; i <= ncells; i += 1024) cs[i] = cells[i];
+  __syncthreads();
+  // ---- scatter (order inside a column is arbitrary; queries break ties on the original index)
+  for (int j = tid; j < n; j += 1024) {
+    const float4 p = T[j];
+    const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
+    const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
+    const int pos = atomicAdd(&cells[iy * nx + ix], 1);
+    S[pos] = p;
+    SI[pos] = j;
+  }
+  if (tid == 0) {
+    G.minx = minx; G.miny = miny; G.c = c; G.inv_c = inv_c; G.nx = nx; G.ny = ny; G.n = n; G.monotone = s_mono;
+    int acc = n;
+    for (int r = kMaxRings + 2; r >= 0; --r) { acc = min(acc, s_minIdx[r]); G.firstGE[r] = acc; }
+  }
+}
+
+// Visit shell k of the column block around (qx, qy): k == 1 -> the whole 3 x 3 block, k > 1 -> its outer ring.
+// visit(t) is called for every sorted-array position t of every column in the shell.
+template <typename F>
+__device__ __forceinline__ void grid_visit_shell(const GridHeader& G, const int* __restrict__ cs, int qx, int qy, int k, F visit) {
+  const int l = lane_id();
+  const int nseg = k == 1 ? 3 : 4 * k;
+  for (int s0 = 0; s0 < nseg; s0 += 32) {
+    int a = 0, bnd = 0;
+    const int sgi = s0 + l;
+    if (sgi < nseg) {
+      int iy, x0, x1;
+      if (k == 1) { iy = qy - 1 + sgi; x0 = qx - 1; x1 = qx + 1; }
+      else if (sgi == 0) { iy = qy - k; x0 = qx - k; x1 = qx + k; }
+      else if (sgi == 1) { iy = qy + k; x0 = qx - k; x1 = qx + k; }
+      else { const int m = sgi - 2; iy = qy - k + 1 + (m >> 1); x0 = x1 = (m & 1) ? qx + k : qx - k; }
+      if (iy >= 0 && iy < G.ny) {
+        x0 = max(x0, 0); x1 = min(x1, G.nx - 1);
+        if (x0 <= x1) { a = cs[iy * G.nx + x0]; bnd = cs[iy * G.nx + x1 + 1]; }
+      }
+    }
+    const int cnt = min(32, nseg - s0);
+    for (int sidx = 0; sidx < cnt; ++sidx) {
+      const int aa = __shfl_sync(0xffffffffu, a, sidx), bb = __shfl_sync(0xffffffffu, bnd, sidx);
+      for (int t = aa + l; t < bb; t += 32) visit(t);
+    }
+  }
+}
+// Squared radius within which the visited block [qx-k, qx+k] x [qy-k, qy+k] is guaranteed complete (0 if none).
+__device__ __forceinline__ float grid_safe_radius(const GridHeader& G, float sx, float sy, int qx, int qy, int k) {
+  const float xl = sx - (G.minx + (float)(qx - k) * G.c), xr = (G.minx + (float)(qx + k + 1) * G.c) - sx;
+  const float yl = sy - (G.miny + (float)(qy - k) * G.c), yr = (G.miny + (float)(qy + k + 1) * G.c) - sy;
+  const float R = fminf(fminf(xl, xr), fminf(yl, yr)) * (1.0f - 1e-5f) - 1e-4f;
+  return R;
+}
+
+// lo_associate: one warp per query, grid search.  Same contract as lo_associate_brute.
+__global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
+                                                     const LOState* __restrict__ lo, const float4* __restrict__ sharp,
+                                                     const float4* __restrict__ flat, const float4* __restrict__ cornerLast,
+                                                     const float4* __restrict__ surfLast, int cap,
+                                                     const GridHeader* __restrict__ ghdr, const int* __restrict__ cellStartAll,
+                                                     const float4* __restrict__ sortedC, const int* __restrict__ sidxC,
+                                                     const float4* __restrict__ sortedS, const int* __restrict__ sidxS,
+                                                     int4* __restrict__ corr) {
+  const int b = blockIdx.y;
+  const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int l = lane_id();
+  if (slot >= kMaxSharp + kMaxFlat) return;
+  const SRHeader& hc = hdrCur[b];
+  const bool isCorner = slot < kMaxSharp;
+  const int which = isCorner ? 0 : 1;
+  const int qi = isCorner ? slot : slot - kMaxSharp;
+  const int nq = isCorner ? hc.nSharp : hc.nFlat;
+  int4 out = make_int4(-1, -1, -1, 0);
+  const GridHeader& G = ghdr[b * 2 + which];
+  const int nT = G.n;
+  if (qi < nq && nT > 0) {
+    const float4 p = isCorner ? sharp[(size_t)b * kMaxSharp + qi] : flat[(size_t)b * kMaxFlat + qi];
+    double un[3];
+    quat_rotate(lo[b].para_q, (double)p.x, (double)p.y, (double)p.z, un);
+    const float sx = (float)(un[0] + lo[b].para_t[0]);
+    const float sy = (float)(un[1] + lo[b].para_t[1]);
+    const float sz = (float)(un[2] + lo[b].para_t[2]);
+    const float4* T = isCorner ? cornerLast + (size_t)b * kMaxLessSharp : surfLast + (size_t)b * cap;
+    const float4* S = isCorner ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
+    const int* SI = isCorner ? sidxC + (size_t)b * kMaxLessSharp : sidxS + (size_t)b * cap;
+    const int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
+    const int qx = cell_coord(sx, G.minx, G.inv_c), qy = cell_coord(sy, G.miny, G.inv_c);
+    // ---- phase 1: exact nearest neighbour (laser_odometry.cpp:269 / :356)
+    unsigned long long best = 0xffffffffffffffffull;
+    for (int k = 1;; ++k) {
+      grid_visit_shell(G, cs, qx, qy, k, [&](int t) {
+        const float4 tp = S[t];
+        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)SI[t];
+        best = key < best ? key : best;
+      });
+      best = warp_min_u64(best);
+      const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
+      if (R >= 5.0f) break;
+      if (best != 0xffffffffffffffffull && R > 0.f && __uint_as_float((unsigned)(best >> 32)) <= R * R) break;
+    }
+    if (best != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // :272
+      const int closest = (int)(unsigned)best;
+      const int id = (int)T[closest].w;  // closestPointScanID (:275)
+      unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
+      if (!G.monotone) {
+        window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
+      } else {
+        // ---- phase 2: nearest point per class inside the +-2.5-ring window (:279-324 / :368-417).  With ring ids
+        // non-decreasing along the cloud the reference's two walks visit exactly the indices [lo, hi) \ {closest}.
+        const int lo_j = G.firstGE[min(max(id - 2, 0), kMaxRings + 2)];
+        const int hi_j = G.firstGE[min(max(id + 3, 0), kMaxRings + 2)];
+        for (int k = 1;; ++k) {
+          grid_visit_shell(G, cs, qx, qy, k, [&](int t) {
+            const int j = SI[t];
+            if (j < lo_j || j >= hi_j || j == closest) return;
+            const float4 tp = S[t];
+            const float d = sqdist_f(tp.x, tp.y, tp.z, sx, sy, sz);
+            if (!((double)d < 25.0)) return;
+            const int rid = (int)tp.w;
+            const bool fwd = j > closest;
+            const unsigned order = fwd ? (unsigned)j : 0x80000000u + (unsigned)(nT - j);
+            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | order;
+            const bool classA = fwd ? (rid <= id) : (rid >= id);  // same-ring side of the walk
+            if (isCorner) { if (!classA) k2 = key < k2 ? key : k2; }
+            else if (classA) k2 = key < k2 ? key : k2;
+            else k3 = key < k3 ? key : k3;
+          });
+          k2 = warp_min_u64(k2);
+          k3 = warp_min_u64(k3);
+          const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
+          if (R >= 5.0f) break;
+          if (R > 0.f) {
+            const float R2 = R * R;
+            const bool ok2 = k2 != 0xffffffffffffffffull && __uint_as_float((unsigned)(k2 >> 32)) <= R2;
+            const bool ok3 = isCorner || (k3 != 0xffffffffffffffffull && __uint_as_float((unsigned)(k3 >> 32)) <= R2);
+            if (ok2 && ok3) break;
+          }
+        }
+      }
+      if (isCorner) {
+        if (k2 != 0xffffffffffffffffull) out = make_int4(closest, decode_order(k2, nT), -1, 1);
+      } else if (k2 != 0xffffffffffffffffull && k3 != 0xffffffffffffffffull) {
+        out = make_int4(closest, decode_order(k2, nT), decode_order(k3, nT), 1);
       }
     }
   }
@@ -529,12 +793,32 @@ void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B) {
   VB_LAUNCH(prof, K_LO_INIT, st, lo_init_state<<<(B + 127) / 128, 128, 0, st>>>(lo, B));
 }
 
+static bool lo_use_brute() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("VLOAM_LO_BRUTE"); v = (e && e[0] == '1') ? 1 : 0; }
+  return v == 1;
+}
+
+void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
+                          const float4* lessFlat, const LOGrid* g) {
+  static bool attr_set = false;
+  const int smem = (kGridCap + 1) * (int)sizeof(int);
+  if (!attr_set) { cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
+  VB_LAUNCH(prof, K_LO_BUILD_GRID, st, lo_build_grid<<<dim3(2, B), 1024, smem, st>>>(hdrCur, lessSharp, lessFlat, cap, g->hdr, g->cellStart,
+                                                                                     g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1]));
+}
+
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
-                    int4* corr, int pass, int max_iterations, int integrate, const double* prior) {
+                    const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior) {
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
-  VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
-                                          hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
+  if (lo_use_brute())
+    VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
+                                                  hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
+  else
+    VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
+                                            hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
+                                            g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1], corr));
   VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
                                                                max_iterations, integrate));
 }

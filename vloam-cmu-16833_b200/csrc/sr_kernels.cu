@@ -9,8 +9,8 @@
 //   sr_scan          :276-281  ring offsets (exclusive scan of the per-block histograms)
 //   sr_scatter       :264-266,276-281  stable ring-major compaction + intensity = ring + 0.1*relTime
 //   sr_curvature     :288-307  11-point curvature, strict left-to-right float sums (no FMA)
-//   sr_ring_features :312-439  per ring: 6 sector sorts, greedy sharp/flat picks with neighbour suppression,
-//                               less-flat gather + pcl::VoxelGrid(0.2) restated in shared memory
+//   sr_pick_features :312-422  warp per ring: greedy sharp / flat picks with neighbour suppression (sort-free arg-max)
+//   sr_less_flat_voxel :424-439  per ring: less-flat gather + pcl::VoxelGrid(0.2) restated in shared memory
 //   sr_pack                    ring-major packing of the four feature clouds
 //
 // Bit-level decisions (ring id, curvature, thresholds, voxel keys) use explicit
@@ -245,39 +245,56 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
 }
 
 // ---------------------------------------------------------------------------------------------
-// sr_curvature: grid (ceil(cap/256), B), block 256.  20 B of HBM traffic per point (16 read + 4 written).
+// sr_curvature: grid (ceil(cap/1024), B), block 256; every thread produces 4 consecutive curvatures from 14 points
+// held in registers.  20 B of HBM traffic per point (16 read + 4 written); the shared-memory tile is padded by one
+// float4 every 8 so the stride-4 register fill is bank-conflict free.
+__device__ __forceinline__ int curv_pad(int e) { return e + (e >> 3); }
+constexpr int kCurvTile = 1024;
 __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
-                                                     int cap, float* __restrict__ curv) {
+                                                     int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag) {
   const int b = blockIdx.y;
   const int size = hdr[b].cloudSize;
-  const int base = blockIdx.x * 256;
+  const int base = blockIdx.x * kCurvTile;
   if (base >= size) return;
   const float4* c = cloud + (size_t)b * cap;
-  __shared__ float4 tile[256 + 10];
-  const int i = base + threadIdx.x;
-  {
-    const int g = i - 5;
-    tile[threadIdx.x] = (g >= 0 && g < size) ? c[g] : make_float4(0.f, 0.f, 0.f, 0.f);
-    if (threadIdx.x < 10) {
-      const int g2 = base + 256 - 5 + threadIdx.x;
-      tile[256 + threadIdx.x] = (g2 >= 0 && g2 < size) ? c[g2] : make_float4(0.f, 0.f, 0.f, 0.f);
-    }
+  __shared__ float4 tile[kCurvTile + 10 + (kCurvTile + 10) / 8 + 1];
+  for (int e = threadIdx.x; e < kCurvTile + 10; e += 256) {  // tile[e] == cloud[base - 5 + e]
+    const int g = base - 5 + e;
+    tile[curv_pad(e)] = (g >= 0 && g < size) ? __ldg(c + g) : make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();
-  if (i >= size) return;
-  float out = 0.f;
-  if (i >= 5 && i < size - 5) {
-    const float4* t = &tile[threadIdx.x];  // t[k] == cloud[i - 5 + k]
+  const int i0 = base + 4 * threadIdx.x;
+  if (i0 >= size) return;
+  float4 t[14];
+#pragma unroll
+  for (int k = 0; k < 14; ++k) t[k] = tile[curv_pad(4 * threadIdx.x + k)];  // t[k] == cloud[i0 - 5 + k]
+  float out[4];
+  unsigned gaps = 0;  // byte o = [ |p[i+1] - p[i]|^2 > 0.05 ], the neighbour-suppression break test (:355-358, :367-370)
+#pragma unroll
+  for (int o = 0; o < 4; ++o) {
+    {
+      const float gx = __fsub_rn(t[o + 6].x, t[o + 5].x), gy = __fsub_rn(t[o + 6].y, t[o + 5].y), gz = __fsub_rn(t[o + 6].z, t[o + 5].z);
+      const float g2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+      if ((double)g2 > 0.05 || i0 + o + 1 >= size) gaps |= 1u << (8 * o);
+    }
     // :290-301: p[i-5] + p[i-4] + p[i-3] + p[i-2] + p[i-1] - 10*p[i] + p[i+1] + ... + p[i+5], left to right
-    float dx = __fadd_rn(t[0].x, t[1].x), dy = __fadd_rn(t[0].y, t[1].y), dz = __fadd_rn(t[0].z, t[1].z);
+    float dx = __fadd_rn(t[o].x, t[o + 1].x), dy = __fadd_rn(t[o].y, t[o + 1].y), dz = __fadd_rn(t[o].z, t[o + 1].z);
 #pragma unroll
-    for (int k = 2; k <= 4; ++k) { dx = __fadd_rn(dx, t[k].x); dy = __fadd_rn(dy, t[k].y); dz = __fadd_rn(dz, t[k].z); }
-    dx = __fsub_rn(dx, __fmul_rn(10.f, t[5].x)); dy = __fsub_rn(dy, __fmul_rn(10.f, t[5].y)); dz = __fsub_rn(dz, __fmul_rn(10.f, t[5].z));
+    for (int k = 2; k <= 4; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
+    dx = __fsub_rn(dx, __fmul_rn(10.f, t[o + 5].x)); dy = __fsub_rn(dy, __fmul_rn(10.f, t[o + 5].y)); dz = __fsub_rn(dz, __fmul_rn(10.f, t[o + 5].z));
 #pragma unroll
-    for (int k = 6; k <= 10; ++k) { dx = __fadd_rn(dx, t[k].x); dy = __fadd_rn(dy, t[k].y); dz = __fadd_rn(dz, t[k].z); }
-    out = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // :303
+    for (int k = 6; k <= 10; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
+    const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // :303
+    const int i = i0 + o;
+    out[o] = (i >= 5 && i < size - 5) ? v : 0.f;
   }
-  curv[(size_t)b * cap + i] = out;
+  float* dst = curv + (size_t)b * cap + i0;
+  *reinterpret_cast<unsigned*>(gapflag + (size_t)b * cap + i0) = gaps;  // cap is a multiple of 1024: always in bounds
+  if (i0 + 3 < size) {
+    *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+  } else {
+    for (int o = 0; o < 4 && i0 + o < size; ++o) dst[o] = out[o];
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -318,39 +335,132 @@ __device__ void bitonic_sort_u64_segments(unsigned long long* keys, int n, int n
 
 __device__ __forceinline__ int next_pow2(int v) { int p = 1; while (p < v) p <<= 1; return p; }
 
-__device__ __forceinline__ float gap2(const float4 a, const float4 b) {
-  // :355-358: diff = p[a] - p[b]; dx*dx + dy*dy + dz*dz
-  const float dx = __fsub_rn(a.x, b.x), dy = __fsub_rn(a.y, b.y), dz = __fsub_rn(a.z, b.z);
-  return __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+__device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(0xffffffffu, v, o);
+    v = t > v ? t : v;
+  }
+  return v;
 }
 
-// warp-cooperative neighbour suppression (:353-376 / :397-420).  `ind` is the picked index (cloud
-// coordinates), `rs` the ring start; picked[] is indexed ring-relative.
-__device__ __forceinline__ void mark_neighbours(const float4* __restrict__ c, int ind, int rs, uint8_t* picked) {
+// ---------------------------------------------------------------------------------------------
+// sr_pick_features: one WARP per ring, grid (kMaxRings / 4, B), block 128.
+// Restates the sort + greedy walk of scan_registration.cpp:319-422 without sorting: the walk over the sorted sector
+// picks, each time, the largest (sharp) or smallest (flat) still-eligible (curvature, index) key, and eligibility only
+// ever shrinks, so repeated warp-wide arg-max / arg-min over the sector yields the same picks in the same order.
+// A lane keeps its share of the sector's curvatures in registers and an "alive" bit mask; neighbour suppression uses
+// the per-pair gap flags written by sr_curvature, so the cloud itself is never read here.
+struct PickSmem {
+  uint8_t picked[4][kRingCap];
+  uint8_t gap[4][kRingCap];
+};
+
+template <int ITEMS>
+__device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const uint8_t* gap, int rs, int SI, int EI,
+                          int8_t* __restrict__ lab, int* __restrict__ fidx, int* __restrict__ secCount) {
   const int l = lane_id();
-  bool stop = false;
-  if (l < 5) stop = (double)gap2(c[ind + l + 1], c[ind + l]) > 0.05;          // forward step l+1
-  else if (l < 10) stop = (double)gap2(c[ind - (l - 5) - 1], c[ind - (l - 5)]) > 0.05;  // backward step l-4
-  const unsigned sb = __ballot_sync(0xffffffffu, stop);
-  const int nf = min(5, (int)__ffs((sb & 0x1fu) | 0x20u) - 1);          // forward steps before the first break
-  const int nb = min(5, (int)__ffs(((sb >> 5) & 0x1fu) | 0x20u) - 1);   // backward steps before the first break
-  if (l < nf) picked[ind + l + 1 - rs] = 1;
-  else if (l >= 5 && l - 5 < nb) picked[ind - (l - 5) - 1 - rs] = 1;
-  __syncwarp();
+  for (int j = 0; j < kSectors; ++j) {
+    const int sp = SI + (EI - SI) * j / 6;
+    const int ep = SI + (EI - SI) * (j + 1) / 6 - 1;
+    float c[ITEMS];
+    unsigned alive = 0;
+#pragma unroll
+    for (int m = 0; m < ITEMS; ++m) {
+      const int pos = sp + l + 32 * m;
+      c[m] = 0.f;
+      if (pos <= ep) { c[m] = cv[pos]; if (!picked[pos - rs]) alive |= 1u << m; }
+    }
+    // mark `ind` and its suppressed neighbours picked (:351-376 / :396-420); every lane updates its alive mask
+    auto suppress = [&](int ind) {
+      int nf = 0, nb = 0;
+      while (nf < 5 && !gap[ind + nf - rs]) ++nf;          // forward steps 1..5: pair (ind+l-1, ind+l)
+      while (nb < 5 && !gap[ind - nb - 1 - rs]) ++nb;      // backward steps 1..5: pair (ind-l, ind-l+1)
+      const int r0 = ind - nb, r1 = ind + nf;
+      if (l <= r1 - r0) picked[r0 + l - rs] = 1;
+      // at most one of this lane's positions (32 apart) lies in [r0, r1]
+      const int pos0 = r0 + ((l - (r0 - sp)) & 31);
+      if (pos0 <= r1 && pos0 >= sp && pos0 <= ep) alive &= ~(1u << ((pos0 - sp - l) >> 5));
+      __syncwarp();
+    };
+    int nSharp = 0, nLess = 0, nFlat = 0;
+    // sharp / less sharp (:327-378)
+    for (int pickNo = 1; pickNo <= 21; ++pickNo) {
+      unsigned long long best = 0ull;
+#pragma unroll
+      for (int m = 0; m < ITEMS; ++m)
+        if (((alive >> m) & 1u) && (double)c[m] > 0.1) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(c[m]) << 32) | (unsigned)(sp + l + 32 * m);
+          best = key > best ? key : best;
+        }
+      best = warp_max_u64(best);
+      if (best == 0ull || pickNo > 20) break;  // nothing eligible, or the 21st candidate (:346-349)
+      const int ind = (int)(unsigned)best;
+      if (l == 0) {
+        if (pickNo <= 2) { lab[ind] = 2; fidx[j * 26 + nSharp] = ind; } else lab[ind] = 1;
+        fidx[j * 26 + 2 + nLess] = ind;
+      }
+      if (pickNo <= 2) ++nSharp;
+      ++nLess;
+      suppress(ind);
+    }
+    // flat (:380-422)
+    for (int pickNo = 1; pickNo <= 4; ++pickNo) {
+      unsigned long long best = 0xffffffffffffffffull;
+#pragma unroll
+      for (int m = 0; m < ITEMS; ++m)
+        if (((alive >> m) & 1u) && (double)c[m] < 0.1) {
+          const unsigned long long key = ((unsigned long long)__float_as_uint(c[m]) << 32) | (unsigned)(sp + l + 32 * m);
+          best = key < best ? key : best;
+        }
+      best = warp_min_u64(best);
+      if (best == 0xffffffffffffffffull) break;
+      const int ind = (int)(unsigned)best;
+      if (l == 0) { lab[ind] = -1; fidx[j * 26 + 22 + nFlat] = ind; }
+      ++nFlat;
+      if (pickNo >= 4) break;  // :390-394: the 4th flat point is not suppressed
+      suppress(ind);
+    }
+    if (l == 0) { secCount[j * 3 + 0] = nSharp; secCount[j * 3 + 1] = nLess; secCount[j * 3 + 2] = nFlat; }
+  }
 }
 
-// sr_ring_features: grid (kMaxRings, B), block 256, dynamic shared memory (see sr_ring_smem_bytes()).
-struct RingSmem {
-  unsigned long long keys[kSectors * kSectorCap];  // sector sort keys; re-used for the voxel sort (kRingCap keys)
-  int lf[kRingCap];                                // cloud indices of the less-flat candidates (ring order)
-  uint8_t picked[kRingCap];
-  int8_t label[kRingCap];
+__global__ void __launch_bounds__(128) sr_pick_features(SRHeader* __restrict__ hdr, const float* __restrict__ curv,
+                                                         const uint8_t* __restrict__ gapflag, int cap,
+                                                         int8_t* __restrict__ label_out, int* __restrict__ featIdx) {
+  __shared__ PickSmem S;
+  const int b = blockIdx.y, w = threadIdx.x >> 5, ring = blockIdx.x * 4 + w, l = lane_id();
+  SRHeader& h = hdr[b];
+  const int rs = h.ringStart[ring], re = h.ringStart[ring + 1];
+  const int len = re - rs;
+  const int SI = rs + 5, EI = re - 6;  // scanStartInd / scanEndInd (:278-280)
+  int8_t* lab = label_out + (size_t)b * cap;
+  for (int i = l; i < len; i += 32) lab[rs + i] = 0;
+  if (len > kRingCap) { if (l == 0) atomicOr(&h.status, kStatusRingOverflow); return; }
+  if (EI - SI < 6) return;  // :314
+  const int maxn = (EI - SI + 5) / 6 + 1;
+  if (maxn > kSectorCap) { if (l == 0) atomicOr(&h.status, kStatusRingOverflow); return; }
+  const uint8_t* gf = gapflag + (size_t)b * cap + rs;
+  for (int i = l; i < len; i += 32) { S.picked[w][i] = 0; S.gap[w][i] = gf[i]; }
+  __syncwarp();
+  const float* cv = curv + (size_t)b * cap;
+  int* fidx = featIdx + ((size_t)b * kMaxRings + ring) * kSectors * 26;
+  int* sc = h.secCount + ring * kSectors * 3;
+  if (maxn <= 384) pick_ring<12>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+  else if (maxn <= 512) pick_ring<16>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+  else pick_ring<32>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+}
+
+// ---------------------------------------------------------------------------------------------
+// sr_less_flat_voxel: grid (kMaxRings, B), block 256, dynamic shared memory = sizeof(VoxelSmem).
+// Per ring: gather the less-flat candidates (label <= 0 inside [scanStartInd, scanEndInd), :424-430) and run
+// pcl::VoxelGrid(0.2) on them (:433-437; semantics restated in oracle/voxel_grid.hpp).
+struct VoxelSmem {
+  unsigned long long keys[kRingCap];
+  int lf[kRingCap];  // cloud indices of the less-flat candidates (ring order)
   int scan[256 + 1];
   float red[6 * 8];
-  int misc[16];
 };
-static_assert(kSectors * kSectorCap >= kRingCap, "voxel keys alias the sector keys");
-size_t sr_ring_smem_bytes() { return sizeof(RingSmem); }
 
 __device__ int block_exclusive_scan(int v, int* scan /*[257]*/) {
   // 256 threads; returns the exclusive prefix of v, scan[256] = total
@@ -368,148 +478,24 @@ __device__ int block_exclusive_scan(int v, int* scan /*[257]*/) {
   return off + s - v;
 }
 
-__global__ void __launch_bounds__(256) sr_ring_features(SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
-                                                         const float* __restrict__ curv, int cap,
-                                                         int8_t* __restrict__ label_out, int* __restrict__ featIdx,
-                                                         float4* __restrict__ lessFlatStage) {
+__global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
+                                                           const int8_t* __restrict__ label, float4* __restrict__ lessFlatStage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  RingSmem& S = *reinterpret_cast<RingSmem*>(smem_raw);
+  VoxelSmem& S = *reinterpret_cast<VoxelSmem*>(smem_raw);
   const int b = blockIdx.y, ring = blockIdx.x;
   SRHeader& h = hdr[b];
   const float4* c = cloud + (size_t)b * cap;
-  const float* cv = curv + (size_t)b * cap;
+  const int8_t* lab = label + (size_t)b * cap;
   const int rs = h.ringStart[ring], re = h.ringStart[ring + 1];
   const int len = re - rs;
-  const int SI = rs + 5, EI = re - 6;  // scanStartInd / scanEndInd (:278-280)
-  int8_t* lab = label_out + (size_t)b * cap;
-  int* fidx = featIdx + ((size_t)b * kMaxRings + ring) * kSectors * 26;
-  if (len > kRingCap || EI - SI < 6) {  // :314
-    for (int i = threadIdx.x; i < len; i += 256) lab[rs + i] = 0;
-    return;
-  }
-  int sp[kSectors], ep[kSectors];
-  int maxn = 0;
-#pragma unroll
-  for (int j = 0; j < kSectors; ++j) {
-    sp[j] = SI + (EI - SI) * j / 6;
-    ep[j] = SI + (EI - SI) * (j + 1) / 6 - 1;
-    maxn = max(maxn, ep[j] - sp[j] + 1);
-  }
-  if (maxn > kSectorCap) {
-    if (threadIdx.x == 0) atomicOr(&h.status, kStatusRingOverflow);
-    for (int i = threadIdx.x; i < len; i += 256) lab[rs + i] = 0;
-    return;
-  }
-  const int P = next_pow2(maxn);
-  // ---- phase A: keys (curvature bits, index); curvature >= 0 so the float bit pattern orders as an unsigned int
-#pragma unroll
-  for (int j = 0; j < kSectors; ++j) {
-    const int n = ep[j] - sp[j] + 1;
-    for (int k = threadIdx.x; k < P; k += 256)
-      S.keys[j * P + k] = k < n ? (((unsigned long long)__float_as_uint(cv[sp[j] + k]) << 32) | (unsigned)(sp[j] + k))
-                                : 0xffffffffffffffffull;
-  }
-  for (int i = threadIdx.x; i < len; i += 256) { S.picked[i] = 0; S.label[i] = 0; }
-  __syncthreads();
-  // ---- phase B: six sector sorts, ascending by (curvature, index)  (:323-324)
-  bitonic_sort_u64_segments(S.keys, P, kSectors);
-  // ---- phase C: greedy picks, sectors in order (suppression marks leak into the next sector, :353-376)
-  if (threadIdx.x < 32) {
-    const int l = lane_id();
-    for (int j = 0; j < kSectors; ++j) {
-      const int n = ep[j] - sp[j] + 1;
-      const unsigned long long* ks = S.keys + j * P;
-      int nSharp = 0, nLess = 0, nFlat = 0;
-      // sharp / less sharp: walk from the largest curvature (:327-378)
-      int largestPickedNum = 0;
-      int k = n - 1;
-      while (k >= 0) {
-        const int kk = k - l;
-        bool elig = false, below = false;
-        int ind = 0;
-        if (kk >= 0) {
-          const unsigned long long key = ks[kk];
-          ind = (int)(unsigned)key;
-          const float cvv = __uint_as_float((unsigned)(key >> 32));
-          below = !((double)cvv > 0.1);
-          elig = !below && S.picked[ind - rs] == 0;
-        }
-        const unsigned eb = __ballot_sync(0xffffffffu, elig);
-        const unsigned bb = __ballot_sync(0xffffffffu, below);
-        // lanes are in descending-curvature order; ignore eligibles that come after the first `below` lane
-        const int firstBelow = bb ? __ffs(bb) - 1 : 32;
-        const unsigned ebv = eb & (firstBelow == 32 ? 0xffffffffu : ((1u << firstBelow) - 1u));
-        if (!ebv) {
-          if (bb) break;
-          k -= 32;
-          continue;
-        }
-        const int f = __ffs(ebv) - 1;
-        const int pind = __shfl_sync(0xffffffffu, ind, f);
-        largestPickedNum++;
-        if (largestPickedNum > 20) break;  // :346-349
-        if (l == 0) {
-          if (largestPickedNum <= 2) { S.label[pind - rs] = 2; fidx[j * 26 + nSharp] = pind; }
-          else S.label[pind - rs] = 1;
-          fidx[j * 26 + 2 + nLess] = pind;
-          S.picked[pind - rs] = 1;
-        }
-        if (largestPickedNum <= 2) nSharp++;
-        nLess++;
-        __syncwarp();
-        mark_neighbours(c, pind, rs, S.picked);
-        k = k - f - 1;
-      }
-      // flat: walk from the smallest curvature (:380-422)
-      int smallestPickedNum = 0;
-      k = 0;
-      while (k < n) {
-        const int kk = k + l;
-        bool elig = false, above = false;
-        int ind = 0;
-        if (kk < n) {
-          const unsigned long long key = ks[kk];
-          ind = (int)(unsigned)key;
-          const float cvv = __uint_as_float((unsigned)(key >> 32));
-          above = !((double)cvv < 0.1);
-          elig = !above && S.picked[ind - rs] == 0;
-        }
-        const unsigned eb = __ballot_sync(0xffffffffu, elig);
-        const unsigned ab = __ballot_sync(0xffffffffu, above);
-        const int firstAbove = ab ? __ffs(ab) - 1 : 32;
-        const unsigned ebv = eb & (firstAbove == 32 ? 0xffffffffu : ((1u << firstAbove) - 1u));
-        if (!ebv) {
-          if (ab) break;
-          k += 32;
-          continue;
-        }
-        const int f = __ffs(ebv) - 1;
-        const int pind = __shfl_sync(0xffffffffu, ind, f);
-        if (l == 0) { S.label[pind - rs] = -1; fidx[j * 26 + 22 + nFlat] = pind; }
-        nFlat++;
-        smallestPickedNum++;
-        if (smallestPickedNum >= 4) break;  // :390-394 (before marking: SURVEY Q2)
-        if (l == 0) S.picked[pind - rs] = 1;
-        __syncwarp();
-        mark_neighbours(c, pind, rs, S.picked);
-        k = k + f + 1;
-      }
-      if (l == 0) {
-        h.secCount[(ring * kSectors + j) * 3 + 0] = nSharp;
-        h.secCount[(ring * kSectors + j) * 3 + 1] = nLess;
-        h.secCount[(ring * kSectors + j) * 3 + 2] = nFlat;
-      }
-      __syncwarp();
-    }
-  }
-  __syncthreads();
-  for (int i = threadIdx.x; i < len; i += 256) lab[rs + i] = S.label[i];
-  // ---- phase D: less-flat candidates = positions [SI, EI) with label <= 0, in order (:424-430)
-  const int span = EI - SI;  // positions SI .. EI-1
+  const int SI = rs + 5, EI = re - 6;
+  if (len > kRingCap || EI - SI < 6 || (EI - SI + 5) / 6 + 1 > kSectorCap) return;  // ringLessFlat stays 0
+  // ---- less-flat candidates = positions [SI, EI) with label <= 0, in order (:424-430)
+  const int span = EI - SI;
   int m = 0;
   for (int base = 0; base < span; base += 256) {
     const int k = base + threadIdx.x;
-    const int flag = (k < span && S.label[SI + k - rs] <= 0) ? 1 : 0;
+    const int flag = (k < span && lab[SI + k] <= 0) ? 1 : 0;
     const int pos = block_exclusive_scan(flag, S.scan);
     if (flag) S.lf[m + pos] = SI + k;
     m += S.scan[256];
@@ -664,21 +650,22 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
 // host-side launcher (called from capi.cu)
 void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
                               const int* n_points_dev, float min_range, int n_scans, SRHeader* hdr, uint8_t* ring8,
-                              int* blockHist, float4* cloud, float* curv, int8_t* label, int* featIdx,
+                              int* blockHist, float4* cloud, float* curv, uint8_t* gapflag, int8_t* label, int* featIdx,
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
                               float4* flat, int* flatIdx, float4* lessFlat) {
   const int nblk = (cap + kClassifyBlock - 1) / kClassifyBlock;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(sr_ring_features, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(RingSmem));
+    cudaFuncSetAttribute(sr_less_flat_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem));
     attr_set = true;
   }
   VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, 256, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
   VB_LAUNCH(prof, K_SR_CLASSIFY, st, sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));
-  VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((cap + 255) / 256, B), 256, 0, st>>>(hdr, cloud, cap, curv));
-  VB_LAUNCH(prof, K_SR_RING_FEATURES, st, sr_ring_features<<<dim3(kMaxRings, B), 256, sizeof(RingSmem), st>>>(hdr, cloud, curv, cap, label, featIdx, lessFlatStage));
+  VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((cap + kCurvTile - 1) / kCurvTile, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag));
+  VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
+  VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem), st>>>(hdr, cloud, cap, label, lessFlatStage));
   VB_LAUNCH(prof, K_SR_PACK, st, sr_pack<<<dim3(kMaxRings + 1, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx,
                                                                               lessSharp, lessSharpIdx, flat, flatIdx, lessFlat));
 }
