@@ -266,31 +266,37 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- leg 2: host buffers through the public API -> `e2e`
     lom2 = make_handle(B)
 
-    def step_host(i):
+    def step_host(i, first):
+        """One scan in flight: enqueue scan i (pinned host -> device upload on the copy stream + kernels), then read
+        scan i-1's poses (device -> host) while scan i runs, so uploads overlap compute."""
         k = pingpong(i, POOL_SCANS)
         lom2.reset()
-        lom2.scanRegistrationIO(host_pool[k], n_host)   # pinned host -> device inside
-        p = lom2.laserOdometryIO(fetch=not do_map)      # device -> host pose read (synchronises)
+        lom2.scanRegistrationIO(host_pool[k], n_host)
+        lom2.laserOdometryIO(fetch=False)
         if do_map:
-            p = lom2.laserMappingIO(fetch=True)
-        return p
+            lom2.laserMappingIO(fetch=False)
+        return None if first else lom2.lo_pose(prev=True)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
-            step_host(i)
+            step_host(i, i == 0)
+        lom2.lo_pose()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_host0 = time.perf_counter()
         e0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
-            pose_host = step_host(i)
+            step_host(i, i == args.warmup)
+        pose_host = lom2.lo_pose()          # drain: the last scan's result is read inside the timed region too
         e1.record(stream)
         barrier()
-        ms_e2e = max_over_ranks(e0.elapsed_time(e1))
+        t_host1 = time.perf_counter()
+        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0)))
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(B * cap * 12 + B * 4)
     d2h = int(B * 16 * 8)
     # same inputs, same number of steps -> both legs must end on identical poses
-    same = bool(np.array_equal(pose_dev["t_w_curr"], (pose_host["t_w_curr"] if not do_map else pose_dev["t_w_curr"])))
+    same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
 
     # ---------------- leg 3: single-stream latency (batch = 1), context only
     lat_ms = None

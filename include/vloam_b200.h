@@ -141,6 +141,9 @@ int vloam_laser_odometry(vloam_lidar* h, const double* prior, double* pose_out, 
 /* Same without the blocking device->host read of the poses (they stay on the device until vloam_get_lo_pose). */
 int vloam_laser_odometry_async(vloam_lidar* h, const double* prior_dev);
 int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out);
+/* Pose of the PREVIOUS scan's laser odometry.  Lets a caller keep one scan in flight: enqueue scan k (upload +
+ * kernels, asynchronous), then read scan k-1's result while k runs, so uploads overlap compute. */
+int vloam_get_lo_pose_prev(vloam_lidar* h, double* pose_out, int* corr_out);
 /* Overwrite q_last_curr / t_last_curr (the motion prior the next solve starts from), motion[batch][7]. */
 int vloam_set_lo_motion(vloam_lidar* h, const double* motion);
 

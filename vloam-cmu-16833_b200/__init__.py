@@ -83,7 +83,7 @@ def lib():
             "vloam_get_labels": [vp, C.c_int, vp, C.c_int, c_ip],
             "vloam_get_feature_indices": [vp, C.c_int, C.c_int, c_ip, C.c_int, c_ip],
             "vloam_laser_odometry": [vp, vp, vp, vp], "vloam_laser_odometry_async": [vp, vp],
-            "vloam_get_lo_pose": [vp, vp, vp], "vloam_set_lo_motion": [vp, c_dp],
+            "vloam_get_lo_pose": [vp, vp, vp], "vloam_get_lo_pose_prev": [vp, vp, vp], "vloam_set_lo_motion": [vp, c_dp],
             "vloam_get_lo_trace": [vp, C.c_int, C.c_int, c_ip, c_dp, c_ip, c_dp],
             "vloam_laser_mapping": [vp, vp], "vloam_get_lm_pose": [vp, c_dp],
             "vloam_map_set_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int],
@@ -245,10 +245,12 @@ class LidarOdometryMapping:
         self.last_pose = self._split_lo(pose, corr)
         return self.last_pose
 
-    def lo_pose(self):
+    def lo_pose(self, prev: bool = False):
+        """Pose of the current scan (or, prev=True, of the previous scan while the current one is still in flight)."""
         pose = np.zeros((self.batch, 14))
         corr = np.zeros((self.batch, 2), np.int32)
-        self.ctx.check(lib().vloam_get_lo_pose(self._h, _ptr(pose), _ptr(corr)))
+        fn = lib().vloam_get_lo_pose_prev if prev else lib().vloam_get_lo_pose
+        self.ctx.check(fn(self._h, _ptr(pose), _ptr(corr)))
         self.last_pose = self._split_lo(pose, corr)
         return self.last_pose
 

@@ -16,6 +16,7 @@ struct vloam_ctx {
   int device = 0;
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device uploads overlap the previous scan's kernels
   std::string last_error;
   Profiler prof;
 };
@@ -96,8 +97,11 @@ struct vloam_lidar {
   bool lo_done_for_frame = false;
   long long lo_frames = 0;   // LaserOdometry::frameCount
   // input staging
-  float* d_in = nullptr;     // [B][cap][4]
-  int* d_n = nullptr;        // [B]
+  float* d_in[2] = {nullptr, nullptr};  // [B][cap][4], double-buffered so the next upload overlaps this scan's kernels
+  int* d_n[2] = {nullptr, nullptr};     // [B]
+  cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
+  bool in_used[2] = {false, false};
+  long long host_scans = 0;
   // scan registration
   SRHeader* d_hdr[2] = {nullptr, nullptr};
   uint8_t* d_ring8 = nullptr;
@@ -117,7 +121,9 @@ struct vloam_lidar {
   int4* d_corr[2] = {nullptr, nullptr};  // per outer pass (kept for parity read-out)
   double* d_prior = nullptr;             // [B][7]
   double* d_pose = nullptr;              // [B][16]
-  double* h_pose = nullptr;              // pinned
+  double* h_pose[2] = {nullptr, nullptr};  // pinned, one per frame parity
+  cudaEvent_t ev_pose[2] = {nullptr, nullptr};
+  bool pose_valid[2] = {false, false};
   LOGrid grid;
   // laser mapping
   LMDevice* lm = nullptr;
@@ -135,7 +141,8 @@ int vloam_ctx_create(int device, vloam_ctx** out) {
   vloam_ctx* c = new (std::nothrow) vloam_ctx();
   if (!c) return VLOAM_E_NOMEM;
   c->device = device;
-  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
     return VLOAM_E_CUDA;
   }
@@ -147,6 +154,7 @@ int vloam_ctx_destroy(vloam_ctx* c) {
   if (!c) return VLOAM_E_INVALID;
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
+  if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
   delete c;
   return VLOAM_OK;
 }
@@ -203,14 +211,19 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   if (!h) return VLOAM_E_INVALID;
   cudaSetDevice(h->ctx->device);
   cudaStreamSynchronize(h->ctx->stream);
-  cudaFree(h->d_in); cudaFree(h->d_n);
+  for (int i = 0; i < 2; ++i) {
+    cudaFree(h->d_in[i]); cudaFree(h->d_n[i]);
+    if (h->ev_in_ready[i]) cudaEventDestroy(h->ev_in_ready[i]);
+    if (h->ev_in_free[i]) cudaEventDestroy(h->ev_in_free[i]);
+    if (h->ev_pose[i]) cudaEventDestroy(h->ev_pose[i]);
+    if (h->h_pose[i]) cudaFreeHost(h->h_pose[i]);
+  }
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_hdr[i]); cudaFree(h->d_cloud[i]); cudaFree(h->d_lessSharp[i]); cudaFree(h->d_lessFlat[i]); cudaFree(h->d_corr[i]); }
   cudaFree(h->d_ring8); cudaFree(h->d_blockHist); cudaFree(h->d_curv); cudaFree(h->d_gapflag); cudaFree(h->d_label); cudaFree(h->d_featIdx);
   cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
   cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart);
   for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); cudaFree(h->grid.sortedIdx[i]); }
-  if (h->h_pose) cudaFreeHost(h->h_pose);
   if (h->lm) lm_destroy(h->lm);
   delete h;
   return VLOAM_OK;
@@ -230,7 +243,13 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   const size_t B = h->B, cap = h->cap;
   cudaError_t e = cudaSuccess;
   auto A = [&](cudaError_t r) { if (e == cudaSuccess) e = r; };
-  A(dalloc(&h->d_in, B * cap * 4)); A(dalloc(&h->d_n, B));
+  for (int i = 0; i < 2; ++i) {
+    A(dalloc(&h->d_in[i], B * cap * 4)); A(dalloc(&h->d_n[i], B));
+    A(cudaEventCreateWithFlags(&h->ev_in_ready[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&h->ev_in_free[i], cudaEventDisableTiming));
+    A(cudaEventCreateWithFlags(&h->ev_pose[i], cudaEventDisableTiming));
+    A(cudaMallocHost((void**)&h->h_pose[i], B * 16 * sizeof(double)));
+  }
   for (int i = 0; i < 2; ++i) {
     A(dalloc(&h->d_hdr[i], B)); A(dalloc(&h->d_cloud[i], B * cap));
     A(dalloc(&h->d_lessSharp[i], B * kMaxLessSharp)); A(dalloc(&h->d_lessFlat[i], B * cap));
@@ -246,7 +265,6 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   A(dalloc(&h->grid.hdr, B * 2)); A(dalloc(&h->grid.cellStart, B * 2 * (kGridCap + 1)));
   A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp)); A(dalloc(&h->grid.sortedIdx[0], B * kMaxLessSharp));
   A(dalloc(&h->grid.sorted[1], B * cap)); A(dalloc(&h->grid.sortedIdx[1], B * cap));
-  A(cudaMallocHost((void**)&h->h_pose, B * 16 * sizeof(double)));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
   e = lm_create(&c->prof, c->stream, h->B, h->cap, p, &h->lm);
@@ -287,13 +305,23 @@ int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_point
     if (n_points[b] < 0 || (size_t)n_points[b] > slab_points) return fail(c, VLOAM_E_INVALID, "n_points[b] exceeds slab_points");
     if (n_points[b] > h->cap) return fail(c, VLOAM_E_CAPACITY, "scan larger than max_points");
   }
-  // one upload per stream slab (only the valid prefix), all on the context stream
+  // Upload on the copy stream into the input slot the previous-but-one scan used; the kernels of the previous scan
+  // (other slot) keep running meanwhile.  ev_in_free[slot] = the kernels that last read this slot have finished.
+  const int slot = (int)(h->host_scans & 1);
+  if (h->in_used[slot]) CU(c, cudaStreamWaitEvent(c->copy_stream, h->ev_in_free[slot], 0));
   for (int b = 0; b < h->B; ++b)
     if (n_points[b])
-      CU(c, cudaMemcpyAsync(h->d_in + (size_t)b * h->cap * stride, xyz + (size_t)b * slab_points * stride,
-                            (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemcpyAsync(h->d_n, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->stream));
-  return run_scan_registration(h, h->d_in, h->d_n, stride, (size_t)h->cap);
+      CU(c, cudaMemcpyAsync(h->d_in[slot] + (size_t)b * h->cap * stride, xyz + (size_t)b * slab_points * stride,
+                            (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaMemcpyAsync(h->d_n[slot], n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaEventRecord(h->ev_in_ready[slot], c->copy_stream));
+  CU(c, cudaStreamWaitEvent(c->stream, h->ev_in_ready[slot], 0));
+  int r = run_scan_registration(h, h->d_in[slot], h->d_n[slot], stride, (size_t)h->cap);
+  if (r) return r;
+  CU(c, cudaEventRecord(h->ev_in_free[slot], c->stream));
+  h->in_used[slot] = true;
+  h->host_scans++;
+  return VLOAM_OK;
 }
 
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
@@ -423,6 +451,12 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
   launch_lo_build_grid(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_lessSharp[cur], h->d_lessFlat[cur], &h->grid);
   launch_lo_export(&c->prof, c->stream, h->d_lo, h->d_pose, h->B);
   CU(c, cudaGetLastError());
+  {  // asynchronous read-back of the poses into the pinned buffer of this frame's parity
+    const int par = (int)(h->frame & 1);
+    CU(c, cudaMemcpyAsync(h->h_pose[par], h->d_pose, (size_t)h->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaEventRecord(h->ev_pose[par], c->stream));
+    h->pose_valid[par] = true;
+  }
   h->lo_done_for_frame = true;
   h->lo_frames++;
   return VLOAM_OK;
@@ -434,17 +468,26 @@ int vloam_laser_odometry_async(vloam_lidar* h, const double* prior_dev) {
   return run_laser_odometry(h, prior_dev);
 }
 
-int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out) {
-  if (!h) return VLOAM_E_INVALID;
+static int read_pose(vloam_lidar* h, int par, double* pose_out, int* corr_out) {
   vloam_ctx* c = h->ctx;
+  if (!h->pose_valid[par]) return fail(c, VLOAM_E_STATE, "no laser odometry result for that frame yet");
   CU(c, cudaSetDevice(c->device));
-  CU(c, cudaMemcpyAsync(h->h_pose, h->d_pose, (size_t)h->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaEventSynchronize(h->ev_pose[par]));  // waits for that frame's read-back only, not for the whole stream
   for (int b = 0; b < h->B; ++b) {
-    if (pose_out) std::memcpy(pose_out + (size_t)b * 14, h->h_pose + (size_t)b * 16, 14 * sizeof(double));
-    if (corr_out) { corr_out[b * 2] = (int)h->h_pose[b * 16 + 14]; corr_out[b * 2 + 1] = (int)h->h_pose[b * 16 + 15]; }
+    if (pose_out) std::memcpy(pose_out + (size_t)b * 14, h->h_pose[par] + (size_t)b * 16, 14 * sizeof(double));
+    if (corr_out) { corr_out[b * 2] = (int)h->h_pose[par][b * 16 + 14]; corr_out[b * 2 + 1] = (int)h->h_pose[par][b * 16 + 15]; }
   }
   return VLOAM_OK;
+}
+int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out) {
+  if (!h) return VLOAM_E_INVALID;
+  if (!h->lo_done_for_frame) return fail(h->ctx, VLOAM_E_STATE, "laser odometry has not run for the current scan");
+  return read_pose(h, (int)(h->frame & 1), pose_out, corr_out);
+}
+int vloam_get_lo_pose_prev(vloam_lidar* h, double* pose_out, int* corr_out) {
+  if (!h) return VLOAM_E_INVALID;
+  if (h->frame < 1) return fail(h->ctx, VLOAM_E_STATE, "no previous scan");
+  return read_pose(h, (int)((h->frame - 1) & 1), pose_out, corr_out);
 }
 
 int vloam_laser_odometry(vloam_lidar* h, const double* prior, double* pose_out, int* corr_out) {

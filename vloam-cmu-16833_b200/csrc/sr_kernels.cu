@@ -454,10 +454,14 @@ __global__ void __launch_bounds__(128) sr_pick_features(SRHeader* __restrict__ h
 // ---------------------------------------------------------------------------------------------
 // sr_less_flat_voxel: grid (kMaxRings, B), block 256, dynamic shared memory = sizeof(VoxelSmem).
 // Per ring: gather the less-flat candidates (label <= 0 inside [scanStartInd, scanEndInd), :424-430) and run
-// pcl::VoxelGrid(0.2) on them (:433-437; semantics restated in oracle/voxel_grid.hpp).
+// pcl::VoxelGrid(0.2) on them (:433-437; semantics restated in oracle/voxel_grid.hpp).  The key sort is a stable
+// LSD radix sort (8-bit digits, warp match_any ranking) of the 32-bit voxel keys: stability keeps points of one
+// voxel in input order, which fixes the float summation order of the centroid.
 struct VoxelSmem {
-  unsigned long long keys[kRingCap];
-  int lf[kRingCap];  // cloud indices of the less-flat candidates (ring order)
+  unsigned key[2][kRingCap];
+  unsigned short pos[2][kRingCap];
+  int lf[kRingCap];      // cloud indices of the less-flat candidates (ring order)
+  int off[8][256];       // per-warp digit offsets
   int scan[256 + 1];
   float red[6 * 8];
 };
@@ -476,6 +480,67 @@ __device__ int block_exclusive_scan(int v, int* scan /*[257]*/) {
   if (threadIdx.x == 255) scan[256] = off + s;
   __syncthreads();
   return off + s - v;
+}
+
+// Stable radix sort of S.key[0][0..m) / S.pos[0][0..m) by the low `bits` bits; returns the buffer index holding the result.
+__device__ int voxel_radix_sort(VoxelSmem& S, int m, int bits) {
+  const int w = threadIdx.x >> 5, l = lane_id();
+  const int per = (m + 7) / 8;                 // contiguous elements owned by each warp
+  const int w0 = min(w * per, m), w1 = min(w0 + per, m);
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    const unsigned* kin = S.key[cur];
+    const unsigned short* pin = S.pos[cur];
+    unsigned* kout = S.key[cur ^ 1];
+    unsigned short* pout = S.pos[cur ^ 1];
+    for (int d = l; d < 256; d += 32) S.off[w][d] = 0;
+    __syncwarp();
+    // (A) per-warp digit totals
+    for (int base = w0; base < w1; base += 32) {
+      const int k = base + l;
+      const bool act = k < w1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const int d = (kin[k] >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    // (B) exclusive scan in (digit, warp) order: thread t owns digit t
+    {
+      const int d = threadIdx.x;
+      int c[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { c[q] = S.off[q][d]; tot += c[q]; }
+      int run = block_exclusive_scan(tot, S.scan);
+#pragma unroll
+      for (int q = 0; q < 8; ++q) { S.off[q][d] = run; run += c[q]; }
+    }
+    __syncthreads();
+    // (C) stable scatter
+    for (int base = w0; base < w1; base += 32) {
+      const int k = base + l;
+      const bool act = k < w1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const unsigned key = kin[k];
+        const int d = (key >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        const int rank = __popc(peers & ((1u << l) - 1u));
+        const int dst = S.off[w][d] + rank;
+        kout[dst] = key;
+        pout[dst] = pin[k];
+        __syncwarp(amask);
+        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
 }
 
 __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
@@ -501,8 +566,8 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
     m += S.scan[256];
     __syncthreads();
   }
-  // ---- phase E: pcl::VoxelGrid, leaf 0.2 (:433-437); PCL semantics restated in oracle/voxel_grid.hpp
-  if (m == 0) { if (threadIdx.x == 0) h.ringLessFlat[ring] = 0; return; }
+  if (m == 0) return;
+  // ---- pcl::VoxelGrid, leaf 0.2
   const float inv = __fdiv_rn(1.0f, 0.2f);
   float mn[3] = {CUDART_INF_F, CUDART_INF_F, CUDART_INF_F}, mx[3] = {-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F};
   for (int k = threadIdx.x; k < m; k += 256) {
@@ -546,39 +611,40 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
     divb[a] = (int)floorf(__fmul_rn(mx[a], inv)) - minb[a] + 1;
   }
   const int mul1 = divb[0], mul2 = divb[0] * divb[1];
-  const int PV = next_pow2(m);
-  for (int k = threadIdx.x; k < PV; k += 256) {
-    unsigned long long key = 0xffffffffffffffffull;
-    if (k < m) {
-      const float4 p = c[S.lf[k]];
-      const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)minb[0]);
-      const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)minb[1]);
-      const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)minb[2]);
-      const unsigned idx = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
-      key = ((unsigned long long)idx << 32) | (unsigned)k;
-    }
-    S.keys[k] = key;
+  const unsigned maxKey = (unsigned)((long long)divb[0] * divb[1] * divb[2] - 1);  // divb product <= dx*dy*dz + slack; see below
+  for (int k = threadIdx.x; k < m; k += 256) {
+    const float4 p = c[S.lf[k]];
+    const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)minb[0]);
+    const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)minb[1]);
+    const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)minb[2]);
+    S.key[0][k] = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
+    S.pos[0][k] = (unsigned short)k;
   }
   __syncthreads();
-  bitonic_sort_u64(S.keys, PV);
+  // keys are < divb[0]*divb[1]*divb[2]; if that product does not fit 32 bits fall back to all 32 key bits
+  int bits = 32;
+  if ((long long)divb[0] * divb[1] * divb[2] <= 0xffffffffLL) bits = maxKey ? 32 - __clz(maxKey) : 1;
+  const int cur = voxel_radix_sort(S, m, bits);
+  const unsigned* keys = S.key[cur];
+  const unsigned short* pos = S.pos[cur];
   // segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n)
   int outBase = 0;
   for (int base = 0; base < m; base += 256) {
     const int k = base + threadIdx.x;
     int head = 0;
-    if (k < m) head = (k == 0) || ((unsigned)(S.keys[k] >> 32) != (unsigned)(S.keys[k - 1] >> 32));
-    const int pos = block_exclusive_scan(head, S.scan);
+    if (k < m) head = (k == 0) || (keys[k] != keys[k - 1]);
+    const int opos = block_exclusive_scan(head, S.scan);
     if (head) {
-      const unsigned vox = (unsigned)(S.keys[k] >> 32);
+      const unsigned vox = keys[k];
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
       int cnt = 0;
-      for (int q = k; q < m && (unsigned)(S.keys[q] >> 32) == vox; ++q) {
-        const float4 p = c[S.lf[(unsigned)S.keys[q]]];
+      for (int q = k; q < m && keys[q] == vox; ++q) {
+        const float4 p = c[S.lf[pos[q]]];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++cnt;
       }
       const float nf = (float)cnt;
-      stage[outBase + pos] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+      stage[outBase + opos] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
     }
     outBase += S.scan[256];
     __syncthreads();
