@@ -280,7 +280,8 @@ def run_ours(args, rank, world, local_rank):
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_host(i, i == 0)
-        lom2.lo_pose()
+        if args.warmup:
+            lom2.lo_pose()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_host0 = time.perf_counter()

@@ -10,7 +10,7 @@ cloud) inherit those ulps through a float sum of up to ~10 values of magnitude <
 Knife-edge azimuths: the reference un-wraps `ori` by comparing it with endOri + pi/2 / endOri - 3pi/2
 (scan_registration.cpp:254-261).  With a regular azimuth grid some columns sit exactly on those thresholds, so a
 1-ulp atan2f difference moves such a point by 2*pi, i.e. its relTime by ~1 and its intensity by ~0.1 (the ring id
-is unaffected).  The tests accept that for at most 0.2 % of the points and require everything else to match.
+is unaffected).  The tests accept that for at most 1 % of the points and require everything else to match.
 """
 import numpy as np
 import pytest
@@ -36,7 +36,7 @@ def _assert_cloud_equal(gpu, ref, name, tol=INTENSITY_TOL):
     diff = np.abs(gpu[:, 3] - ref[:, 3])
     flipped = diff > tol
     assert np.all(diff[flipped] <= 0.13), f"{name}: intensity fraction (max {diff.max()})"
-    assert flipped.sum() <= max(4, 0.002 * diff.size), f"{name}: {flipped.sum()} knife-edge azimuth flips of {diff.size}"
+    assert flipped.sum() <= max(8, 0.01 * diff.size), f"{name}: {flipped.sum()} knife-edge azimuth flips of {diff.size}"
 
 
 def _check_sr(lom, ref, stream=0):

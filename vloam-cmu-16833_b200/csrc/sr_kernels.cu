@@ -31,7 +31,7 @@ __device__ __forceinline__ bool point_valid(float x, float y, float z, float thr
 }
 
 // :192-226.  Returns ring id or -1.  atan/sqrt evaluated in double.
-__device__ __forceinline__ int ring_of(float x, float y, float z, int n_scans) {
+__device__ __noinline__ int ring_of_exact(float x, float y, float z, int n_scans) {
   const float xy2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
   const double a = atan((double)z / sqrt((double)xy2));
   const float angle = (float)(__ddiv_rn(__dmul_rn(a, 180.0), 3.14159265358979323846));
@@ -49,6 +49,33 @@ __device__ __forceinline__ int ring_of(float x, float y, float z, int n_scans) {
       id = n_scans / 2 + (int)(__dadd_rn(__dmul_rn(__dsub_rn(-8.83, (double)angle), 2.0), 0.5));
     if ((double)angle > 2.0 || (double)angle < -24.33 || id > 50 || id < 0) return -1;
   }
+  return id;
+}
+
+// Same decisions as ring_of_exact.  For the HDL-64 table a float estimate of the elevation is used when it is
+// farther than kAngleErr from every decision threshold (bin edges, -8.83, 2, -24.33): the estimate differs from the
+// exactly-rounded `angle` by far less than that (atanf / rsqrt / mul: a few ulp, < 3e-5 deg), so both give the
+// same ring; otherwise (about 0.1 % of the points) the double-precision path decides.
+__device__ __forceinline__ int ring_of(float x, float y, float z, int n_scans) {
+  if (n_scans != 64) return ring_of_exact(x, y, z, n_scans);
+  constexpr float kAngleErr = 2e-4f;
+  const float xy2 = __fadd_rn(__fmul_rn(x, x), __fmul_rn(y, y));
+  const float af = atanf(z * rsqrtf(xy2)) * 57.29577951308232f;
+  bool safe = fabsf(af - (-8.83f)) > kAngleErr && fabsf(af - 2.0f) > kAngleErr && fabsf(af - (-24.33f)) > kAngleErr && isfinite(af);
+  int id = 0;
+  if (af >= -8.83f) {
+    const float t = (2.0f - af) * 3.0f + 0.5f;
+    const float fr = t - floorf(t);
+    safe = safe && fr > 3.0f * kAngleErr + 1e-5f && fr < 1.0f - 3.0f * kAngleErr - 1e-5f;
+    id = (int)t;
+  } else {
+    const float t = (-8.83f - af) * 2.0f + 0.5f;
+    const float fr = t - floorf(t);
+    safe = safe && fr > 2.0f * kAngleErr + 1e-5f && fr < 1.0f - 2.0f * kAngleErr - 1e-5f;
+    id = 32 + (int)t;
+  }
+  if (!safe) return ring_of_exact(x, y, z, n_scans);
+  if (af > 2.0f || af < -24.33f || id > 50 || id < 0) return -1;
   return id;
 }
 
@@ -204,7 +231,7 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
   const SRHeader& h = hdr[b];
   const int n = h.n_in;
   const int i = blk * kClassifyBlock + threadIdx.x;
-  __shared__ int wh[32][kMaxRings];
+  __shared__ int wh[kMaxRings][32];  // [ring][warp]: lanes of the scan below read consecutive words
   for (int k = threadIdx.x; k < 32 * kMaxRings; k += 1024) (&wh[0][0])[k] = 0;
   __syncthreads();
   int ring = -1;
@@ -212,17 +239,17 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
   const unsigned m = __match_any_sync(0xffffffffu, ring);
   const int warp = threadIdx.x >> 5;
   const int rank = __popc(m & ((1u << lane_id()) - 1u));
-  if (ring >= 0 && rank == 0) wh[warp][ring] = __popc(m);
+  if (ring >= 0 && rank == 0) wh[ring][warp] = __popc(m);
   __syncthreads();
   // exclusive scan over the 32 warps for each ring: warp w handles rings 2w, 2w+1; lane = source warp.
 #pragma unroll
   for (int rr = 0; rr < 2; ++rr) {
     const int r = warp * 2 + rr;
-    const int v = wh[lane_id()][r];
+    const int v = wh[r][lane_id()];
     int s = v;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if ((int)lane_id() >= o) s += t; }
-    wh[lane_id()][r] = s - v + blockOff[((size_t)b * nblk + blk) * kMaxRings + r];
+    wh[r][lane_id()] = s - v + blockOff[((size_t)b * nblk + blk) * kMaxRings + r];
   }
   __syncthreads();
   if (ring >= 0) {
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
     }
     const float relTime = __fdiv_rn(__fsub_rn(ori, startOri), __fsub_rn(endOri, startOri));
     const float intensity = (float)__dadd_rn((double)ring, __dmul_rn(0.1, (double)relTime));  // :265
-    cloud[(size_t)b * cap + wh[warp][ring] + rank] = make_float4(x, y, z, intensity);
+    cloud[(size_t)b * cap + wh[ring][warp] + rank] = make_float4(x, y, z, intensity);
   }
 }
 
@@ -425,7 +452,7 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
   }
 }
 
-__global__ void __launch_bounds__(128) sr_pick_features(SRHeader* __restrict__ hdr, const float* __restrict__ curv,
+__global__ void __launch_bounds__(128, 7) sr_pick_features(SRHeader* __restrict__ hdr, const float* __restrict__ curv,
                                                          const uint8_t* __restrict__ gapflag, int cap,
                                                          int8_t* __restrict__ label_out, int* __restrict__ featIdx) {
   __shared__ PickSmem S;
@@ -555,15 +582,18 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
   const int len = re - rs;
   const int SI = rs + 5, EI = re - 6;
   if (len > kRingCap || EI - SI < 6 || (EI - SI + 5) / 6 + 1 > kSectorCap) return;  // ringLessFlat stays 0
-  // ---- less-flat candidates = positions [SI, EI) with label <= 0, in order (:424-430)
+  // ---- less-flat candidates = positions [SI, EI) with label <= 0, in order (:424-430).
+  // Thread t owns a contiguous run of positions, so one block scan yields the order-preserving compaction.
   const int span = EI - SI;
-  int m = 0;
-  for (int base = 0; base < span; base += 256) {
-    const int k = base + threadIdx.x;
-    const int flag = (k < span && lab[SI + k] <= 0) ? 1 : 0;
-    const int pos = block_exclusive_scan(flag, S.scan);
-    if (flag) S.lf[m + pos] = SI + k;
-    m += S.scan[256];
+  int m;
+  {
+    const int per = (span + 255) / 256;
+    const int k0 = min((int)threadIdx.x * per, span), k1 = min(k0 + per, span);
+    int cnt = 0;
+    for (int k = k0; k < k1; ++k) cnt += lab[SI + k] <= 0 ? 1 : 0;
+    int pos = block_exclusive_scan(cnt, S.scan);
+    for (int k = k0; k < k1; ++k) if (lab[SI + k] <= 0) S.lf[pos++] = SI + k;
+    m = S.scan[256];
     __syncthreads();
   }
   if (m == 0) return;
@@ -627,27 +657,29 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
   const int cur = voxel_radix_sort(S, m, bits);
   const unsigned* keys = S.key[cur];
   const unsigned short* pos = S.pos[cur];
-  // segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n)
-  int outBase = 0;
-  for (int base = 0; base < m; base += 256) {
-    const int k = base + threadIdx.x;
-    int head = 0;
-    if (k < m) head = (k == 0) || (keys[k] != keys[k - 1]);
-    const int opos = block_exclusive_scan(head, S.scan);
-    if (head) {
-      const unsigned vox = keys[k];
+  // segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n).
+  // Thread t owns a contiguous run of sorted entries and finishes every voxel that starts inside it.
+  int outBase;
+  {
+    const int per = (m + 255) / 256;
+    const int q0 = min((int)threadIdx.x * per, m), q1 = min(q0 + per, m);
+    int nh = 0;
+    for (int q = q0; q < q1; ++q) nh += (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+    int opos = block_exclusive_scan(nh, S.scan);
+    for (int q = q0; q < q1; ++q) {
+      if (!(q == 0 || keys[q] != keys[q - 1])) continue;
+      const unsigned vox = keys[q];
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
       int cnt = 0;
-      for (int q = k; q < m && keys[q] == vox; ++q) {
-        const float4 p = c[S.lf[pos[q]]];
+      for (int qq = q; qq < m && keys[qq] == vox; ++qq) {
+        const float4 p = c[S.lf[pos[qq]]];
         sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
         ++cnt;
       }
       const float nf = (float)cnt;
-      stage[outBase + opos] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+      stage[opos++] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
     }
-    outBase += S.scan[256];
-    __syncthreads();
+    outBase = S.scan[256];
   }
   if (threadIdx.x == 0) h.ringLessFlat[ring] = outBase;
 }
