@@ -56,8 +56,13 @@ constexpr int kGridCap = 40000;  // max columns per grid (cell table lives in sh
 struct GridHeader {
   float minx, miny, c, inv_c;
   int nx, ny, n;
-  int monotone;                 // int(intensity) non-decreasing along the cloud (always true for ring-major clouds)
-  int firstGE[kMaxRings + 3];   // firstGE[r] = first index whose int(intensity) >= r  (r = 0 .. 65), n if none
+  // The reference classifies target points by int(intensity), which equals the point's true ring R or, when its
+  // relTime is negative, R - 1.  With that property (ringsOk) the two walks of laser_odometry.cpp:279-324 / 368-417
+  // visit exactly an index interval that follows from the true ring offsets and these two per-ring tables.
+  int ringsOk;
+  int ringStart[kMaxRings + 2];  // true ring offsets of the ring-major cloud; [64] = [65] = n
+  int firstFull[kMaxRings + 1];  // first index in ring R whose int(intensity) == R      (INT_MAX if none)
+  int lastLow[kMaxRings + 1];    // last index in ring R whose int(intensity) == R - 1   (-1 if none)
 };
 
 // Levenberg-Marquardt trace record (mirrors oracle::LMIteration) for parity read-out.

@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
                                                        int* __restrict__ sidxC, float4* __restrict__ sortedS, int* __restrict__ sidxS) {
   extern __shared__ int cells[];
   __shared__ float s_red[4][32];
-  __shared__ int s_minIdx[kMaxRings + 3];
+  __shared__ int s_firstFull[kMaxRings + 1], s_lastLow[kMaxRings + 1], s_ringStart[kMaxRings + 2];
   __shared__ int s_mono, s_nx, s_ny;
   __shared__ float s_c, s_minx, s_miny;
   __shared__ int s_wsum[32];
@@ -162,11 +162,12 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   float4* S = which == 0 ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
   int* SI = which == 0 ? sidxC + (size_t)b * kMaxLessSharp : sidxS + (size_t)b * cap;
   const int n = which == 0 ? hdrCur[b].nLessSharp : hdrCur[b].nLessFlat;
+  const int* trueStart = which == 0 ? hdrCur[b].ringStartLessSharp : hdrCur[b].ringStartLessFlat;
   GridHeader& G = ghdr[b * 2 + which];
   int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   if (n == 0) {
-    if (tid == 0) { G.n = 0; G.nx = 0; G.ny = 0; G.monotone = 1; G.c = 1.f; G.inv_c = 1.f; G.minx = 0.f; G.miny = 0.f; }
+    if (tid == 0) { G.n = 0; G.nx = 0; G.ny = 0; G.ringsOk = 1; G.c = 1.f; G.inv_c = 1.f; G.minx = 0.f; G.miny = 0.f; }
     return;
   }
   // ---- bounding box in xy
@@ -181,7 +182,8 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
     mny = fminf(mny, __shfl_xor_sync(0xffffffffu, mny, o)); mxy = fmaxf(mxy, __shfl_xor_sync(0xffffffffu, mxy, o));
   }
   if (l == 0) { s_red[0][w] = mnx; s_red[1][w] = mxx; s_red[2][w] = mny; s_red[3][w] = mxy; }
-  if (tid < kMaxRings + 3) s_minIdx[tid] = n;
+  if (tid <= kMaxRings) { s_firstFull[tid] = 0x7fffffff; s_lastLow[tid] = -1; }
+  if (tid < kMaxRings + 2) s_ringStart[tid] = tid <= kMaxRings ? trueStart[tid] : n;
   if (tid == 0) s_mono = 1;
   __syncthreads();
   if (tid == 0) {
@@ -209,9 +211,14 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
     const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
     const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
     atomicAdd(&cells[iy * nx + ix], 1);
-    const int rid = min(max((int)p.w, 0), kMaxRings + 1);
-    atomicMin(&s_minIdx[rid], j);
-    if (j > 0 && (int)T[j - 1].w > (int)p.w) s_mono = 0;
+    // true ring of point j (ring-major cloud): largest R with ringStart[R] <= j
+    int R = 0;
+#pragma unroll
+    for (int step = 32; step > 0; step >>= 1) if (R + step <= kMaxRings - 1 && s_ringStart[R + step] <= j) R += step;
+    const int rid = (int)p.w;
+    if (rid == R) atomicMin(&s_firstFull[R], j);
+    else if (rid == R - 1) atomicMax(&s_lastLow[R], j);
+    else s_mono = 0;
   }
   __syncthreads();
   // ---- exclusive scan of the column counts: thread t owns a contiguous chunk
@@ -247,9 +254,9 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
     SI[pos] = j;
   }
   if (tid == 0) {
-    G.minx = minx; G.miny = miny; G.c = c; G.inv_c = inv_c; G.nx = nx; G.ny = ny; G.n = n; G.monotone = s_mono;
-    int acc = n;
-    for (int r = kMaxRings + 2; r >= 0; --r) { acc = min(acc, s_minIdx[r]); G.firstGE[r] = acc; }
+    G.minx = minx; G.miny = miny; G.c = c; G.inv_c = inv_c; G.nx = nx; G.ny = ny; G.n = n; G.ringsOk = s_mono;
+    for (int r = 0; r < kMaxRings + 2; ++r) G.ringStart[r] = s_ringStart[r];
+    for (int r = 0; r <= kMaxRings; ++r) { G.firstFull[r] = s_firstFull[r]; G.lastLow[r] = s_lastLow[r]; }
   }
 }
 
@@ -339,13 +346,17 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
       const int closest = (int)(unsigned)best;
       const int id = (int)T[closest].w;  // closestPointScanID (:275)
       unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
-      if (!G.monotone) {
+      if (!G.ringsOk) {
         window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
       } else {
-        // ---- phase 2: nearest point per class inside the +-2.5-ring window (:279-324 / :368-417).  With ring ids
-        // non-decreasing along the cloud the reference's two walks visit exactly the indices [lo, hi) \ {closest}.
-        const int lo_j = G.firstGE[min(max(id - 2, 0), kMaxRings + 2)];
-        const int hi_j = G.firstGE[min(max(id + 3, 0), kMaxRings + 2)];
+        // ---- phase 2: nearest point per class inside the +-2.5-ring window (:279-324 / :368-417).
+        // Forward walk stops at the first j > closest with int(intensity) >= id + 3: that is the first such point of
+        // true ring id + 3, else the start of ring id + 4 (every point there qualifies).  Backward walk stops at the
+        // last j < closest with int(intensity) <= id - 3: the last such point of true ring id - 2, else the point just
+        // before that ring.  So the walks visit exactly the indices [lo_j, hi_j) \ {closest}.
+        int hi_j = nT, lo_j = 0;
+        if (id + 3 <= kMaxRings - 1) hi_j = min(G.firstFull[id + 3], G.ringStart[min(id + 4, kMaxRings)]);
+        if (id - 2 >= 0) lo_j = max(G.lastLow[id - 2], G.ringStart[id - 2] - 1) + 1;
         for (int k = 1;; ++k) {
           grid_visit_shell(G, cs, qx, qy, k, [&](int t) {
             const int j = SI[t];
