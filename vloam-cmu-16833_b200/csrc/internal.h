@@ -59,6 +59,7 @@ void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
 struct LOGrid {
   GridHeader* hdr = nullptr;   // [B][2]
   int* cellStart = nullptr;    // [B][2][kGridCap + 1]
+  int* cursor = nullptr;       // [B][2][kGridCap + 1] scatter cursors (scratch)
   float4* sorted[2] = {nullptr, nullptr};  // corner: [B][kMaxLessSharp], surf: [B][cap]
   int* sortedIdx[2] = {nullptr, nullptr};
 };

@@ -146,12 +146,13 @@ __global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __rest
 // both kernels return identical results.
 __device__ __forceinline__ int cell_coord(float v, float mn, float inv_c) { return (int)floorf((v - mn) * inv_c); }
 
-// lo_build_grid: grid (2, B), block 1024, dynamic smem = (kGridCap + 1) ints.  blockIdx.x: 0 = corner cloud, 1 = surf.
+// lo_build_grid: grid (2, B), block 1024.  blockIdx.x: 0 = corner cloud, 1 = surf.  Counting sort by column with the
+// column table in global memory (L2-resident: <= 256 KB per cloud).
 __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict__ hdrCur, const float4* __restrict__ lessSharp,
                                                        const float4* __restrict__ lessFlat, int cap, GridHeader* __restrict__ ghdr,
-                                                       int* __restrict__ cellStartAll, float4* __restrict__ sortedC,
-                                                       int* __restrict__ sidxC, float4* __restrict__ sortedS, int* __restrict__ sidxS) {
-  extern __shared__ int cells[];
+                                                       int* __restrict__ cellStartAll, int* __restrict__ cursorAll,
+                                                       float4* __restrict__ sortedC, int* __restrict__ sidxC,
+                                                       float4* __restrict__ sortedS, int* __restrict__ sidxS) {
   __shared__ float s_red[4][32];
   __shared__ int s_firstFull[kMaxRings + 1], s_lastLow[kMaxRings + 1], s_ringStart[kMaxRings + 2];
   __shared__ int s_mono, s_nx, s_ny;
@@ -165,6 +166,7 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   const int* trueStart = which == 0 ? hdrCur[b].ringStartLessSharp : hdrCur[b].ringStartLessFlat;
   GridHeader& G = ghdr[b * 2 + which];
   int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
+  int* cells = cursorAll + (size_t)(b * 2 + which) * (kGridCap + 1);
   const int tid = threadIdx.x, w = tid >> 5, l = tid & 31;
   if (n == 0) {
     if (tid == 0) { G.n = 0; G.nx = 0; G.ny = 0; G.ringsOk = 1; G.c = 1.f; G.inv_c = 1.f; G.minx = 0.f; G.miny = 0.f; }
@@ -190,7 +192,7 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
     for (int i = 1; i < 32; ++i) {
       mnx = fminf(mnx, s_red[0][i]); mxx = fmaxf(mxx, s_red[1][i]); mny = fminf(mny, s_red[2][i]); mxy = fmaxf(mxy, s_red[3][i]);
     }
-    float c = 1.0f;
+    float c = kGridCell;
     int nx, ny;
     while (true) {
       nx = (int)floorf((mxx - mnx) / c) + 1;
@@ -239,10 +241,8 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   }
   __syncthreads();
   int run = s_wsum[w] + sc - sum;
-  for (int i = c0; i < c1; ++i) { const int t = cells[i]; cells[i] = run; run += t; }
-  if (tid == 0) cells[ncells] = n;
-  __syncthreads();
-  for (int i = tid; i <= ncells; i += 1024) cs[i] = cells[i];
+  for (int i = c0; i < c1; ++i) { const int t = cells[i]; cells[i] = run; cs[i] = run; run += t; }
+  if (tid == 0) { cells[ncells] = n; cs[ncells] = n; }
   __syncthreads();
   // ---- scatter (order inside a column is arbitrary; queries break ties on the original index)
   for (int j = tid; j < n; j += 1024) {
@@ -812,11 +812,8 @@ static bool lo_use_brute() {
 
 void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
                           const float4* lessFlat, const LOGrid* g) {
-  static bool attr_set = false;
-  const int smem = (kGridCap + 1) * (int)sizeof(int);
-  if (!attr_set) { cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
-  VB_LAUNCH(prof, K_LO_BUILD_GRID, st, lo_build_grid<<<dim3(2, B), 1024, smem, st>>>(hdrCur, lessSharp, lessFlat, cap, g->hdr, g->cellStart,
-                                                                                     g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1]));
+  VB_LAUNCH(prof, K_LO_BUILD_GRID, st, lo_build_grid<<<dim3(2, B), 1024, 0, st>>>(hdrCur, lessSharp, lessFlat, cap, g->hdr, g->cellStart, g->cursor,
+                                                                                  g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1]));
 }
 
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,

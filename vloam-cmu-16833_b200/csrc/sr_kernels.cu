@@ -378,9 +378,10 @@ __device__ __forceinline__ unsigned long long warp_max_u64(unsigned long long v)
 // ever shrinks, so repeated warp-wide arg-max / arg-min over the sector yields the same picks in the same order.
 // A lane keeps its share of the sector's curvatures in registers and an "alive" bit mask; neighbour suppression uses
 // the per-pair gap flags written by sr_curvature, so the cloud itself is never read here.
+template <int CAP>
 struct PickSmem {
-  uint8_t picked[4][kRingCap];
-  uint8_t gap[4][kRingCap];
+  uint8_t picked[4][CAP];
+  uint8_t gap[4][CAP];
 };
 
 template <int ITEMS>
@@ -400,9 +401,13 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
     }
     // mark `ind` and its suppressed neighbours picked (:351-376 / :396-420); every lane updates its alive mask
     auto suppress = [&](int ind) {
-      int nf = 0, nb = 0;
-      while (nf < 5 && !gap[ind + nf - rs]) ++nf;          // forward steps 1..5: pair (ind+l-1, ind+l)
-      while (nb < 5 && !gap[ind - nb - 1 - rs]) ++nb;      // backward steps 1..5: pair (ind-l, ind-l+1)
+      // lanes 0..4: forward steps 1..5 = pairs (ind+l, ind+l+1); lanes 5..9: backward steps = pairs (ind-m-1, ind-m)
+      bool stop = false;
+      if (l < 5) stop = gap[ind + l - rs] != 0;
+      else if (l < 10) stop = gap[ind - (l - 5) - 1 - rs] != 0;
+      const unsigned sb = __ballot_sync(0xffffffffu, stop);
+      const int nf = min(5, (int)__ffs((sb & 0x1fu) | 0x20u) - 1);
+      const int nb = min(5, (int)__ffs(((sb >> 5) & 0x1fu) | 0x20u) - 1);
       const int r0 = ind - nb, r1 = ind + nf;
       if (l <= r1 - r0) picked[r0 + l - rs] = 1;
       // at most one of this lane's positions (32 apart) lies in [r0, r1]
@@ -413,16 +418,17 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
     int nSharp = 0, nLess = 0, nFlat = 0;
     // sharp / less sharp (:327-378)
     for (int pickNo = 1; pickNo <= 21; ++pickNo) {
-      unsigned long long best = 0ull;
+      // arg-max of (curvature bits, index) over the eligible elements: two hardware warp reductions
+      unsigned bc = 0, bi = 0;
 #pragma unroll
       for (int m = 0; m < ITEMS; ++m)
         if (((alive >> m) & 1u) && (double)c[m] > 0.1) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(c[m]) << 32) | (unsigned)(sp + l + 32 * m);
-          best = key > best ? key : best;
+          const unsigned cb = __float_as_uint(c[m]);  // curvature >= 0: the bit pattern orders like the value
+          if (cb >= bc) { bc = cb; bi = (unsigned)(sp + l + 32 * m); }  // m ascending -> larger index wins ties
         }
-      best = warp_max_u64(best);
-      if (best == 0ull || pickNo > 20) break;  // nothing eligible, or the 21st candidate (:346-349)
-      const int ind = (int)(unsigned)best;
+      const unsigned mc = __reduce_max_sync(0xffffffffu, bc);
+      if (mc == 0u || pickNo > 20) break;  // nothing eligible (eligible curvatures are > 0.1), or the 21st candidate (:346-349)
+      const int ind = (int)__reduce_max_sync(0xffffffffu, bc == mc ? bi : 0u);
       if (l == 0) {
         if (pickNo <= 2) { lab[ind] = 2; fidx[j * 26 + nSharp] = ind; } else lab[ind] = 1;
         fidx[j * 26 + 2 + nLess] = ind;
@@ -433,16 +439,16 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
     }
     // flat (:380-422)
     for (int pickNo = 1; pickNo <= 4; ++pickNo) {
-      unsigned long long best = 0xffffffffffffffffull;
+      unsigned bc = 0xffffffffu, bi = 0xffffffffu;
 #pragma unroll
       for (int m = 0; m < ITEMS; ++m)
         if (((alive >> m) & 1u) && (double)c[m] < 0.1) {
-          const unsigned long long key = ((unsigned long long)__float_as_uint(c[m]) << 32) | (unsigned)(sp + l + 32 * m);
-          best = key < best ? key : best;
+          const unsigned cb = __float_as_uint(c[m]);
+          if (cb < bc) { bc = cb; bi = (unsigned)(sp + l + 32 * m); }  // m ascending -> smaller index wins ties
         }
-      best = warp_min_u64(best);
-      if (best == 0xffffffffffffffffull) break;
-      const int ind = (int)(unsigned)best;
+      const unsigned mc = __reduce_min_sync(0xffffffffu, bc);
+      if (mc == 0xffffffffu) break;
+      const int ind = (int)__reduce_min_sync(0xffffffffu, bc == mc ? bi : 0xffffffffu);
       if (l == 0) { lab[ind] = -1; fidx[j * 26 + 22 + nFlat] = ind; }
       ++nFlat;
       if (pickNo >= 4) break;  // :390-394: the 4th flat point is not suppressed
@@ -452,18 +458,27 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
   }
 }
 
+// CAP = 2048 handles rings of up to 2048 points (every HDL-64 ring at 10 Hz) at twice the occupancy; the CAP = 4096
+// instance only picks up the longer rings.
+template <int CAP>
 __global__ void __launch_bounds__(128, 7) sr_pick_features(SRHeader* __restrict__ hdr, const float* __restrict__ curv,
                                                          const uint8_t* __restrict__ gapflag, int cap,
                                                          int8_t* __restrict__ label_out, int* __restrict__ featIdx) {
-  __shared__ PickSmem S;
+  __shared__ PickSmem<CAP> S;
   const int b = blockIdx.y, w = threadIdx.x >> 5, ring = blockIdx.x * 4 + w, l = lane_id();
   SRHeader& h = hdr[b];
   const int rs = h.ringStart[ring], re = h.ringStart[ring + 1];
   const int len = re - rs;
   const int SI = rs + 5, EI = re - 6;  // scanStartInd / scanEndInd (:278-280)
   int8_t* lab = label_out + (size_t)b * cap;
+  if (CAP == 2048 ? len > 2048 : (len <= 2048 || len > kRingCap)) {
+    if (CAP != 2048 && len > kRingCap) {
+      for (int i = l; i < len; i += 32) lab[rs + i] = 0;
+      if (l == 0) atomicOr(&h.status, kStatusRingOverflow);
+    }
+    return;
+  }
   for (int i = l; i < len; i += 32) lab[rs + i] = 0;
-  if (len > kRingCap) { if (l == 0) atomicOr(&h.status, kStatusRingOverflow); return; }
   if (EI - SI < 6) return;  // :314
   const int maxn = (EI - SI + 5) / 6 + 1;
   if (maxn > kSectorCap) { if (l == 0) atomicOr(&h.status, kStatusRingOverflow); return; }
@@ -473,9 +488,12 @@ __global__ void __launch_bounds__(128, 7) sr_pick_features(SRHeader* __restrict_
   const float* cv = curv + (size_t)b * cap;
   int* fidx = featIdx + ((size_t)b * kMaxRings + ring) * kSectors * 26;
   int* sc = h.secCount + ring * kSectors * 3;
-  if (maxn <= 384) pick_ring<12>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
-  else if (maxn <= 512) pick_ring<16>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
-  else pick_ring<32>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+  if constexpr (CAP == 2048) {  // len <= 2048 -> sectors of at most 341 points
+    pick_ring<12>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+  } else {
+    if (maxn <= 512) pick_ring<16>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+    else pick_ring<32>(cv, S.picked[w], S.gap[w], rs, SI, EI, lab, fidx, sc);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -484,10 +502,11 @@ __global__ void __launch_bounds__(128, 7) sr_pick_features(SRHeader* __restrict_
 // pcl::VoxelGrid(0.2) on them (:433-437; semantics restated in oracle/voxel_grid.hpp).  The key sort is a stable
 // LSD radix sort (8-bit digits, warp match_any ranking) of the 32-bit voxel keys: stability keeps points of one
 // voxel in input order, which fixes the float summation order of the centroid.
+template <int CAP>
 struct VoxelSmem {
-  unsigned key[2][kRingCap];
-  unsigned short pos[2][kRingCap];
-  int lf[kRingCap];      // cloud indices of the less-flat candidates (ring order)
+  unsigned key[2][CAP];
+  unsigned short pos[2][CAP];
+  int lf[CAP];           // cloud indices of the less-flat candidates (ring order)
   int off[8][256];       // per-warp digit offsets
   int scan[256 + 1];
   float red[6 * 8];
@@ -510,7 +529,8 @@ __device__ int block_exclusive_scan(int v, int* scan /*[257]*/) {
 }
 
 // Stable radix sort of S.key[0][0..m) / S.pos[0][0..m) by the low `bits` bits; returns the buffer index holding the result.
-__device__ int voxel_radix_sort(VoxelSmem& S, int m, int bits) {
+template <int CAP>
+__device__ int voxel_radix_sort(VoxelSmem<CAP>& S, int m, int bits) {
   const int w = threadIdx.x >> 5, l = lane_id();
   const int per = (m + 7) / 8;                 // contiguous elements owned by each warp
   const int w0 = min(w * per, m), w1 = min(w0 + per, m);
@@ -570,10 +590,11 @@ __device__ int voxel_radix_sort(VoxelSmem& S, int m, int bits) {
   return cur;
 }
 
+template <int CAP>
 __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
                                                            const int8_t* __restrict__ label, float4* __restrict__ lessFlatStage) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  VoxelSmem& S = *reinterpret_cast<VoxelSmem*>(smem_raw);
+  VoxelSmem<CAP>& S = *reinterpret_cast<VoxelSmem<CAP>*>(smem_raw);
   const int b = blockIdx.y, ring = blockIdx.x;
   SRHeader& h = hdr[b];
   const float4* c = cloud + (size_t)b * cap;
@@ -581,7 +602,8 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
   const int rs = h.ringStart[ring], re = h.ringStart[ring + 1];
   const int len = re - rs;
   const int SI = rs + 5, EI = re - 6;
-  if (len > kRingCap || EI - SI < 6 || (EI - SI + 5) / 6 + 1 > kSectorCap) return;  // ringLessFlat stays 0
+  if (CAP == 2048 ? len > 2048 : (len <= 2048 || len > kRingCap)) return;  // the other instance's ring (or overflow)
+  if (EI - SI < 6 || (EI - SI + 5) / 6 + 1 > kSectorCap) return;             // ringLessFlat stays 0
   // ---- less-flat candidates = positions [SI, EI) with label <= 0, in order (:424-430).
   // Thread t owns a contiguous run of positions, so one block scan yields the order-preserving compaction.
   const int span = EI - SI;
@@ -654,7 +676,7 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
   // keys are < divb[0]*divb[1]*divb[2]; if that product does not fit 32 bits fall back to all 32 key bits
   int bits = 32;
   if ((long long)divb[0] * divb[1] * divb[2] <= 0xffffffffLL) bits = maxKey ? 32 - __clz(maxKey) : 1;
-  const int cur = voxel_radix_sort(S, m, bits);
+  const int cur = voxel_radix_sort<CAP>(S, m, bits);
   const unsigned* keys = S.key[cur];
   const unsigned short* pos = S.pos[cur];
   // segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n).
@@ -754,7 +776,8 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
   const int nblk = (cap + kClassifyBlock - 1) / kClassifyBlock;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(sr_less_flat_voxel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem));
+    cudaFuncSetAttribute(sr_less_flat_voxel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<2048>));
+    cudaFuncSetAttribute(sr_less_flat_voxel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<4096>));
     attr_set = true;
   }
   VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, 256, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
@@ -762,8 +785,12 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
   VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));
   VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((cap + kCurvTile - 1) / kCurvTile, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag));
-  VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
-  VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem), st>>>(hdr, cloud, cap, label, lessFlatStage));
+  VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<2048><<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
+  VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<2048><<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem<2048>), st>>>(hdr, cloud, cap, label, lessFlatStage));
+  if (cap > 2048 + 0) {  // rings longer than 2048 points (only possible when a scan has more than 2048 points at all)
+    VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<4096><<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
+    VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<4096><<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem<4096>), st>>>(hdr, cloud, cap, label, lessFlatStage));
+  }
   VB_LAUNCH(prof, K_SR_PACK, st, sr_pack<<<dim3(kMaxRings + 1, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx,
                                                                               lessSharp, lessSharpIdx, flat, flatIdx, lessFlat));
 }
