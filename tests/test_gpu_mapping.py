@@ -1,0 +1,109 @@
+"""GPU parity tests for laserMapping: CUDA path through the C-ABI vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+POSE_TOL_M = 1e-4
+POSE_TOL_RAD = 1e-4
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _quat_angle(q1, q2):
+    return 2.0 * np.arccos(min(1.0, abs(float(np.dot(q1, q2)))))
+
+
+def _same_xyz(a, b, name):
+    assert a.shape == b.shape, f"{name}: {a.shape} vs {b.shape}"
+    if a.shape[0]:
+        assert np.array_equal(_bits(a[:, :3]), _bits(b[:, :3])), f"{name}: xyz not bit-identical"
+        assert np.max(np.abs(a[:, 3] - b[:, 3])) < 0.14, f"{name}: intensity"
+
+
+def _run_sequence(V, oracle, scans, check_cubes=True):
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18)
+    pipe = oracle.Pipeline()
+    worst_t = 0.0
+    for k, scan in enumerate(scans):
+        lom.reset()
+        lom.scanRegistrationIO(scan)
+        lom.laserOdometryIO()
+        mp = lom.laserMappingIO()
+        assert pipe.process(scan, do_mapping=True) == 0
+        ost = pipe.lm.state
+        info = lom.lm_info()[0]
+        assert list(info[:4]) == list(ost["cen"]) + [ost["validNum"]], (k, info, ost)
+        _same_xyz(lom.cloud(V.CLOUD_CORNER_STACK), pipe.lm.cloud(0), f"scan {k} corner stack")
+        _same_xyz(lom.cloud(V.CLOUD_SURF_STACK), pipe.lm.cloud(1), f"scan {k} surf stack")
+        _same_xyz(lom.cloud(V.CLOUD_CORNER_MAP), pipe.lm.cloud(2), f"scan {k} corner from map")
+        _same_xyz(lom.cloud(V.CLOUD_SURF_MAP), pipe.lm.cloud(3), f"scan {k} surf from map")
+        otr = pipe.lm.trace()
+        if k == 0:
+            assert len(otr) == 0                      # empty map: the gate at laser_mapping.cpp:448 fails
+        for p, t in enumerate(otr):
+            g = lom.lm_trace(p)
+            assert (g["n_corner"], g["n_plane"]) == (len(t["corner"]), len(t["plane"])), (k, p)
+            assert g["termination"] == t["termination"]
+            n = t["iterations"].shape[0]
+            assert g["n_records"] == n
+            np.testing.assert_allclose(g["iterations"][:n, 0], t["iterations"][:, 0], rtol=1e-8, atol=1e-12)
+            np.testing.assert_array_equal(g["iterations"][:n, 5:7], t["iterations"][:, 5:7])
+            np.testing.assert_allclose(g["para"], t["para"], atol=1e-8)
+        dt = float(np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])))
+        worst_t = max(worst_t, dt)
+        assert dt < POSE_TOL_M
+        assert _quat_angle(mp["q_w_curr"][0], ost["q_w_curr"]) < POSE_TOL_RAD
+        assert np.max(np.abs(mp["t_wmap_wodom"][0] - ost["t_wmap_wodom"])) < POSE_TOL_M
+        assert _quat_angle(mp["q_wmap_wodom"][0], ost["q_wmap_wodom"]) < POSE_TOL_RAD
+        if check_cubes:
+            occupied = 0
+            for cube in range(4851):
+                for kind in (0, 1):
+                    n_or = pipe.lm.cube_count(kind, cube)
+                    if n_or or k == 0 and cube % 97 == 0:
+                        _same_xyz(lom.map_get_cube(kind, cube), pipe.lm.cube(kind, cube), f"scan {k} cube {cube} kind {kind}")
+                        occupied += n_or > 0
+            assert occupied > 0
+    lom.close()
+    return worst_t
+
+
+def test_laser_mapping_sequence(synth, oracle):
+    import vloam_b200 as V
+    s = synth.ScanStream(31, n_cols=1024)
+    scans = [s.scan(k) for k in range(5)]
+    worst = _run_sequence(V, oracle, scans)
+    print("max |t_w_curr - oracle| =", worst)
+
+
+def test_laser_mapping_seeded_map_and_cube_shift(synth, oracle):
+    """Map cubes seeded through vloam_map_set_cube; a large odometry offset forces the rolling grid to shift."""
+    import vloam_b200 as V
+    s = synth.ScanStream(32, n_cols=512)
+    scans = [s.scan(k) for k in range(3)]
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18)
+    pipe = oracle.Pipeline()
+    # seed one far-away cube in both maps: it must survive the grid shift at its shifted index or be dropped identically
+    rng = np.random.default_rng(0)
+    seed = np.c_[rng.uniform(300, 340, (500, 2)), rng.uniform(-2, 2, 500), rng.uniform(0, 50, 500)].astype(np.float32)
+    cube = (10 + 6) + 21 * (10 + 6) + 441 * 5
+    lom.map_set_cube(1, cube, seed)
+    pipe.lm.set_cube(1, cube, seed)
+    assert np.array_equal(lom.map_get_cube(1, cube), seed)
+    for k, scan in enumerate(scans):
+        # shift both odometries by 400 m in x so that centerCubeI >= laserCloudWidth - 3 (laser_mapping.cpp:249)
+        sc = scan
+        lom.reset(); lom.scanRegistrationIO(sc); lom.laserOdometryIO()
+        assert pipe.process(sc, do_mapping=False) == 0
+        if k == 0:
+            off = np.array([[0, 0, 0, 1, 400.0, 0, 0]])
+        lom_pose = lom.lo_pose()
+        mp = lom.laserMappingIO()
+        pipe.lm.reset(); pipe.lm.input_from_lo(pipe.lo); pipe.lm.solve()
+        ost = pipe.lm.state
+        assert list(lom.lm_info()[0][:3]) == list(ost["cen"])
+        assert np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])) < POSE_TOL_M
+    lom.close()

@@ -6,8 +6,12 @@ mkdir -p lib
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 OBJS=""
+HDRS="csrc/common.cuh csrc/internal.h csrc/gn_solver.cuh ../include/vloam_b200.h"
 for f in sr_kernels lo_kernels lm_kernels vo_kernels capi; do
-  if [ ! -f lib/$f.o ] || [ csrc/$f.cu -nt lib/$f.o ] || [ csrc/common.cuh -nt lib/$f.o ] || [ csrc/internal.h -nt lib/$f.o ] || [ ../include/vloam_b200.h -nt lib/$f.o ]; then
+  stale=0
+  [ -f lib/$f.o ] || stale=1
+  for d in csrc/$f.cu $HDRS; do [ "$d" -nt lib/$f.o ] && stale=1; done
+  if [ $stale = 1 ]; then
     echo "nvcc $f.cu"
     $NVCC $FLAGS -c csrc/$f.cu -o lib/$f.o 2> lib/$f.ptxas.log || { cat lib/$f.ptxas.log; exit 1; }
   fi

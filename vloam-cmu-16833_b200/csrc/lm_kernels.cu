@@ -1,16 +1,1063 @@
-// placeholder, replaced below
+// vloam_b200 — laserMapping on sm_100a.
+//
+// Replaces vloam::LaserMapping::input / solveMapping
+// (reference src/lidar_odometry_mapping/src/laser_mapping.cpp:167-196, 198-708):
+//
+//   lm_prepare        :186-216 initial guess, :218-402 rolling 21x21x11 cube grid shift (a permutation of the cube
+//                     table, no point moves), :404-430 the 5x5x3 valid-cube list and sub-map offsets
+//   lm_voxel_segments :432-440 / :689-702 pcl::VoxelGrid on global-memory segments (scan features, map cubes):
+//                     bbox -> voxel keys -> stable LSD radix sort -> ordered centroid sums
+//   lm_grid_*         :452-453 the kd-tree replacement: the sub-map counting-sorted into 1.001 m xy columns.  A match
+//                     needs its 5th neighbour within 1 m (:479, :547), so the 3x3 column block around a query is
+//                     always sufficient — no expansion, exact by construction.
+//   lm_associate      :472-581 exact 5-NN, PCA line test (corner) / least-squares plane fit + 0.2 m check (surf)
+//   lm_solve          :609-617 the whole ceres::Solve of one outer pass in one launch (gn_solver.cuh)
+//   lm_insert_*       :636-683 transformUpdate, scan points into cubes (stable by cube)
+//   lm_rebuild_*      :689-702 re-filter every valid cube, compact the map into the other buffer
+#include <cstdio>
+#include <vector>
+
 #include "../../include/vloam_b200.h"
+#include "common.cuh"
+#include "gn_solver.cuh"
 #include "internal.h"
+
 namespace vb {
-struct LMDevice { int B; };
-cudaError_t lm_create(Profiler*, cudaStream_t, int B, int, const vloam_lidar_params*, LMDevice** out) { *out = new LMDevice{B}; return cudaSuccess; }
-void lm_destroy(LMDevice* lm) { delete lm; }
-void lm_reset(LMDevice*) {}
-cudaError_t lm_run(LMDevice*, cudaStream_t, const SRHeader*, const float4*, const float4*, const LOState*, bool) { return cudaErrorNotSupported; }
-cudaError_t lm_get_pose(LMDevice*, cudaStream_t, double*) { return cudaErrorNotSupported; }
-cudaError_t lm_get_cloud(LMDevice*, cudaStream_t, int, int, float*, int, int*) { return cudaErrorNotSupported; }
-cudaError_t lm_set_cube(LMDevice*, cudaStream_t, int, int, int, const float*, int) { return cudaErrorNotSupported; }
-cudaError_t lm_get_cube(LMDevice*, cudaStream_t, int, int, int, float*, int, int*) { return cudaErrorNotSupported; }
-cudaError_t lm_get_info(LMDevice*, cudaStream_t, int*) { return cudaErrorNotSupported; }
-cudaError_t lm_get_trace(LMDevice*, cudaStream_t, int, int, double*, int*, double*) { return cudaErrorNotSupported; }
+
+constexpr int kCubeW = 21, kCubeH = 21, kCubeD = 11, kCubes = kCubeW * kCubeH * kCubeD;  // laser_mapping.h:110-114
+constexpr int kMaxValid = 125;                                                           // laser_mapping.h:116
+constexpr int kMaxWork = 200;   // cubes rewritten per scan: the valid ones plus cubes that received points
+constexpr float kMapCell = 1.001f;
+constexpr int kMapNX = 256, kMapNY = 256, kMapCols = kMapNX * kMapNY;  // 5 cubes x 50 m = 250 m < 256 * 1.001 m
+
+struct LMState {
+  double parameters[7];                 // q_w_curr (x,y,z,w), t_w_curr      laser_mapping.cpp:74-83
+  double q_wmap_wodom[4], t_wmap_wodom[3];
+  double q_wodom[4], t_wodom[3];
+  int cenW, cenH, cenD;                 // laserCloudCenWidth / Height / Depth
+  int validNum;
+  int validInd[kMaxValid];
+  int validPrefix[2][kMaxValid + 1];    // offsets of each valid cube inside the concatenated sub-map
+  int fromMapNum[2];
+  int stackNum[2];
+  int solved;                           // the map was large enough (:448)
+  int poolEnd[2];                       // first free slot of the current map buffer
+  float gridMinX, gridMinY;             // origin of the sub-map column index
+  int workNum[2];
+  int workCube[2][kMaxWork], workFilter[2][kMaxWork], workNew0[2][kMaxWork], workNewN[2][kMaxWork];
+  int workIn0[2][kMaxWork + 1];         // offsets of each work cube's (old ++ new) input inside the concat buffer
+  int workOutN[2][kMaxWork];
+  int error;
+  SolveTrace trace[2];
+};
+
+// Residual record produced by lm_associate for one down-sampled scan point.
+struct LMResidual {
+  double v[7];   // edge: a(3), b(3); plane: n(3), d
+  float px, py, pz;
+  int type;      // 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneNormFactor)
+};
+
+struct LMDevice {
+  int B = 0, cap = 0, mapCap = 0;
+  vloam_lidar_params p{};
+  Profiler* prof = nullptr;
+  bool allocated = false, reset_valid = true, ran = false;
+  int curPts = 0, curTab = 0;      // the map = points in mapPts[curPts] addressed by cubeOff/cubeCnt[curTab]
+  LMState* st = nullptr;
+  int* cubeOff[2] = {nullptr, nullptr};   // [B][2][kCubes]
+  int* cubeCnt[2] = {nullptr, nullptr};
+  float4* mapPts[2] = {nullptr, nullptr}; // [B][2][mapCap]
+  float4* stack = nullptr;                // [B][2][cap]  down-sampled scan (laserCloudCornerStack / SurfStack)
+  float4* stackW = nullptr;               // [B][2][cap]  the same points in the map frame (pointAssociateToMap)
+  unsigned* keyA = nullptr; unsigned* valA = nullptr; unsigned* keyB = nullptr; unsigned* valB = nullptr;  // [B][2][workCap]
+  float4* concat = nullptr;               // [B][2][workCap] refilter inputs (old ++ new per work cube)
+  float4* staged = nullptr;               // [B][2][workCap] refilter outputs
+  int* cellStart = nullptr; int* cursor = nullptr;  // [B][2][kMapCols + 1]
+  float4* sorted = nullptr;               // [B][2][mapCap] sub-map sorted by column, w = sub-map index
+  LMResidual* res = nullptr;              // [B][2][cap]
+  double* pose = nullptr;                 // [B][16]
+  short* workOf = nullptr;                // [B][2][kCubes]
+  size_t workCap = 0;
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Stable LSD radix sort of (key, val) pairs living in global memory, by one CTA of 1024 threads.
+// Warp w owns a contiguous range; digit offsets are kept per warp in shared memory (see sr_less_flat_voxel).
+struct SortSmem {
+  int off[32][256];
+  int wsum[32];
+  int total;
+};
+__device__ int block_exclusive_scan1024(int v, SortSmem& S) {  // 1024 threads; S.total = block total
+  const int w = threadIdx.x >> 5, l = lane_id();
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (l >= o) s += t; }
+  if (l == 31) S.wsum[w] = s;
+  __syncthreads();
+  if (w == 0) {
+    const int x = S.wsum[l];
+    int sx = x;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sx, o); if (l >= o) sx += t; }
+    S.wsum[l] = sx - x;
+    if (l == 31) S.total = sx;
+  }
+  __syncthreads();
+  const int r = S.wsum[w] + s - v;
+  __syncthreads();
+  return r;
 }
+// Returns 0 if the result is in (kA, vA), 1 if in (kB, vB).
+__device__ int cta_radix_sort(unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB, int n, int bits, SortSmem& S) {
+  const int w = threadIdx.x >> 5, l = lane_id();
+  const int per = (n + 31) / 32;
+  const int w0 = min(w * per, n), w1 = min(w0 + per, n);
+  int cur = 0;
+  for (int shift = 0; shift < bits; shift += 8) {
+    const unsigned* kin = cur ? kB : kA;
+    const unsigned* vin = cur ? vB : vA;
+    unsigned* kout = cur ? kA : kB;
+    unsigned* vout = cur ? vA : vB;
+    for (int d = l; d < 256; d += 32) S.off[w][d] = 0;
+    __syncwarp();
+    for (int base = w0; base < w1; base += 32) {
+      const int k = base + l;
+      const bool act = k < w1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const int d = (kin[k] >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+      const int d = threadIdx.x;
+      int tot = 0;
+      for (int q = 0; q < 32; ++q) tot += S.off[q][d];
+      // exclusive scan over the 256 digit totals by warps 0..7
+      int s = tot;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (l >= o) s += t; }
+      if (l == 31) S.wsum[w] = s;
+      __syncwarp();
+      // (threads >= 256 idle; a named barrier over the first 256 threads)
+      asm volatile("bar.sync 1, 256;");
+      int basew = 0;
+      for (int q = 0; q < w; ++q) basew += S.wsum[q];
+      int run = basew + s - tot;
+      for (int q = 0; q < 32; ++q) { const int c = S.off[q][d]; S.off[q][d] = run; run += c; }
+    }
+    __syncthreads();
+    for (int base = w0; base < w1; base += 32) {
+      const int k = base + l;
+      const bool act = k < w1;
+      const unsigned amask = __ballot_sync(0xffffffffu, act);
+      if (act) {
+        const unsigned key = kin[k];
+        const int d = (key >> shift) & 255;
+        const unsigned peers = __match_any_sync(amask, d);
+        const int rank = __popc(peers & ((1u << l) - 1u));
+        const int dst = S.off[w][d] + rank;
+        kout[dst] = key;
+        vout[dst] = vin[k];
+        __syncwarp(amask);
+        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    cur ^= 1;
+  }
+  return cur;
+}
+
+// pcl::VoxelGrid<PointXYZI> on one global-memory segment by one CTA (1024 threads).  Semantics: oracle/voxel_grid.hpp.
+// Returns the number of output points (valid in all threads).
+__device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf, float4* __restrict__ out, unsigned* kA,
+                                unsigned* vA, unsigned* kB, unsigned* vB, SortSmem& S, float* red /*[6*32]*/) {
+  if (n == 0) return 0;
+  const float inv = __fdiv_rn(1.0f, leaf);
+  float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
+  for (int k = threadIdx.x; k < n; k += 1024) {
+    const float4 p = in[k];
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  const int w = threadIdx.x >> 5, l = lane_id();
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+    }
+    if (l == 0) { red[a * 32 + w] = mn[a]; red[(3 + a) * 32 + w] = mx[a]; }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    float lo = red[a * 32], hi = red[(3 + a) * 32];
+    for (int q = 1; q < 32; ++q) { lo = fminf(lo, red[a * 32 + q]); hi = fmaxf(hi, red[(3 + a) * 32 + q]); }
+    mn[a] = lo; mx[a] = hi;
+  }
+  __syncthreads();
+  const long long dx = (long long)(__fmul_rn(__fsub_rn(mx[0], mn[0]), inv)) + 1;
+  const long long dy = (long long)(__fmul_rn(__fsub_rn(mx[1], mn[1]), inv)) + 1;
+  const long long dz = (long long)(__fmul_rn(__fsub_rn(mx[2], mn[2]), inv)) + 1;
+  if (dx * dy * dz > 2147483647LL) {  // PCL: "Leaf size is too small": output = input
+    for (int k = threadIdx.x; k < n; k += 1024) out[k] = in[k];
+    return n;
+  }
+  int minb[3], divb[3];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) {
+    minb[a] = (int)floorf(__fmul_rn(mn[a], inv));
+    divb[a] = (int)floorf(__fmul_rn(mx[a], inv)) - minb[a] + 1;
+  }
+  const int mul1 = divb[0], mul2 = divb[0] * divb[1];
+  for (int k = threadIdx.x; k < n; k += 1024) {
+    const float4 p = in[k];
+    const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)minb[0]);
+    const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)minb[1]);
+    const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)minb[2]);
+    kA[k] = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
+    vA[k] = (unsigned)k;
+  }
+  __syncthreads();
+  const long long prod = (long long)divb[0] * divb[1] * divb[2];
+  int bits = 32;
+  if (prod <= 0xffffffffLL) { const unsigned mk = (unsigned)(prod - 1); bits = mk ? 32 - __clz(mk) : 1; }
+  const int cur = cta_radix_sort(kA, vA, kB, vB, n, bits, S);
+  const unsigned* keys = cur ? kB : kA;
+  const unsigned* vals = cur ? vB : vA;
+  // heads + ordered sums: thread t owns a contiguous run of sorted entries and finishes every voxel starting in it
+  const int per = (n + 1023) / 1024;
+  const int q0 = min((int)threadIdx.x * per, n), q1 = min(q0 + per, n);
+  int nh = 0;
+  for (int q = q0; q < q1; ++q) nh += (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+  int opos = block_exclusive_scan1024(nh, S);
+  const int total = S.total;
+  for (int q = q0; q < q1; ++q) {
+    if (!(q == 0 || keys[q] != keys[q - 1])) continue;
+    const unsigned vox = keys[q];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    for (int qq = q; qq < n && keys[qq] == vox; ++qq) {
+      const float4 p = in[vals[qq]];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+      ++cnt;
+    }
+    const float nf = (float)cnt;
+    out[opos++] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+  }
+  __syncthreads();
+  return total;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ int cube_coord(double v, int cen) {  // :207-216 / :643-652
+  int c = (int)((v + 25.0) / 50.0) + cen;
+  if (v + 25.0 < 0) c--;
+  return c;
+}
+
+// lm_prepare: grid (B), block 256.  Table ping-pong: reads tables `src`, writes the shifted tables to `dst`.
+__global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, const LOState* __restrict__ lo,
+                                                   const int* __restrict__ offSrc, const int* __restrict__ cntSrc,
+                                                   int* __restrict__ offDst, int* __restrict__ cntDst, int resetValid) {
+  const int b = blockIdx.x;
+  LMState& st = stAll[b];
+  __shared__ int sh[3];
+  __shared__ int center[3];
+  if (threadIdx.x == 0) {
+    if (resetValid) st.validNum = 0;  // LaserMapping::reset (:127-131)
+    // input(), :182-195: q_w_curr = q_wmap_wodom * q_wodom_curr; t_w_curr = q_wmap_wodom * t_wodom_curr + t_wmap_wodom
+    for (int i = 0; i < 4; ++i) st.q_wodom[i] = lo[b].q_w[i];
+    for (int i = 0; i < 3; ++i) st.t_wodom[i] = lo[b].t_w[i];
+    double q[4], t[3];
+    quat_mul(st.q_wmap_wodom, st.q_wodom, q);
+    quat_rotate(st.q_wmap_wodom, st.t_wodom[0], st.t_wodom[1], st.t_wodom[2], t);
+    for (int i = 0; i < 4; ++i) st.parameters[i] = q[i];
+    for (int i = 0; i < 3; ++i) st.parameters[4 + i] = t[i] + st.t_wmap_wodom[i];
+    // :207-216
+    int cI = cube_coord(st.parameters[4], st.cenW), cJ = cube_coord(st.parameters[5], st.cenH), cK = cube_coord(st.parameters[6], st.cenD);
+    // :218-402: each while-iteration moves every cube one step and clears the plane that wrapped around
+    int sI = 0, sJ = 0, sK = 0;
+    while (cI < 3) { cI++; st.cenW++; sI++; }
+    while (cI >= kCubeW - 3) { cI--; st.cenW--; sI--; }
+    while (cJ < 3) { cJ++; st.cenH++; sJ++; }
+    while (cJ >= kCubeH - 3) { cJ--; st.cenH--; sJ--; }
+    while (cK < 3) { cK++; st.cenD++; sK++; }
+    while (cK >= kCubeD - 3) { cK--; st.cenD--; sK--; }
+    sh[0] = sI; sh[1] = sJ; sh[2] = sK;
+    center[0] = cI; center[1] = cJ; center[2] = cK;
+  }
+  __syncthreads();
+  const int sI = sh[0], sJ = sh[1], sK = sh[2];
+  for (int kind = 0; kind < 2; ++kind) {
+    const int* oS = offSrc + ((size_t)b * 2 + kind) * kCubes;
+    const int* cS = cntSrc + ((size_t)b * 2 + kind) * kCubes;
+    int* oD = offDst + ((size_t)b * 2 + kind) * kCubes;
+    int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
+    for (int c = threadIdx.x; c < kCubes; c += 256) {
+      const int i = c % kCubeW, j = (c / kCubeW) % kCubeH, k = c / (kCubeW * kCubeH);
+      const int si = i - sI, sj = j - sJ, sk = k - sK;  // new[i] = old[i - shift]; wrapped planes are cleared
+      int o = 0, n = 0;
+      if (si >= 0 && si < kCubeW && sj >= 0 && sj < kCubeH && sk >= 0 && sk < kCubeD) {
+        const int s = si + kCubeW * sj + kCubeW * kCubeH * sk;
+        o = oS[s]; n = cS[s];
+      }
+      oD[c] = o; cD[c] = n;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // :404-420 valid cubes in the reference's loop order
+    const int cI = center[0], cJ = center[1], cK = center[2];
+    int vn = st.validNum;
+    for (int i = cI - 2; i <= cI + 2; i++)
+      for (int j = cJ - 2; j <= cJ + 2; j++)
+        for (int k = cK - 1; k <= cK + 1; k++)
+          if (i >= 0 && i < kCubeW && j >= 0 && j < kCubeH && k >= 0 && k < kCubeD && vn < kMaxValid)
+            st.validInd[vn++] = i + kCubeW * j + kCubeW * kCubeH * k;
+    st.validNum = vn;
+    for (int kind = 0; kind < 2; ++kind) {
+      const int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
+      int acc = 0;
+      for (int v = 0; v < vn; ++v) { st.validPrefix[kind][v] = acc; acc += cD[st.validInd[v]]; }
+      st.validPrefix[kind][vn] = acc;
+      st.fromMapNum[kind] = acc;
+    }
+    st.solved = (st.fromMapNum[0] > 10 && st.fromMapNum[1] > 50) ? 1 : 0;  // :448
+    // origin of the column index: the 5 x 5 block of 50 m cubes around the centre cube (plus half a column of slack)
+    st.gridMinX = (float)((cI - 2 - st.cenW) * 50.0 - 25.0 - 0.5);
+    st.gridMinY = (float)((cJ - 2 - st.cenH) * 50.0 - 25.0 - 0.5);
+    st.trace[0].n_records = st.trace[1].n_records = 0;
+    st.trace[0].n_corner = st.trace[0].n_plane = st.trace[1].n_corner = st.trace[1].n_plane = 0;
+  }
+}
+
+// lm_voxel_stack: grid (2, B), block 1024.  VoxelGrid of the scan's corner (lineRes) / surf (planeRes) features (:432-440).
+__global__ void __launch_bounds__(1024) lm_voxel_stack(LMState* __restrict__ stAll, const SRHeader* __restrict__ hdr,
+                                                        const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
+                                                        int cap, float lineRes, float planeRes, float4* __restrict__ stack,
+                                                        unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB, size_t workCap) {
+  __shared__ SortSmem S;
+  __shared__ float red[6 * 32];
+  const int kind = blockIdx.x, b = blockIdx.y;
+  const float4* in = kind == 0 ? cornerLast + (size_t)b * kMaxLessSharp : surfLast + (size_t)b * cap;
+  const int n = kind == 0 ? hdr[b].nLessSharp : hdr[b].nLessFlat;
+  const size_t so = ((size_t)b * 2 + kind) * workCap;
+  const int m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, stack + ((size_t)b * 2 + kind) * cap, kA + so, vA + so,
+                                 kB + so, vB + so, S, red);
+  if (threadIdx.x == 0) stAll[b].stackNum[kind] = m;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Sub-map column index.  Sub-map index g (the position in laserCloudCornerFromMap / SurfFromMap, :422-428) maps to
+// valid cube v = upper_bound(validPrefix, g) - 1 and offset g - validPrefix[v] inside that cube.
+__device__ __forceinline__ float4 submap_point(const LMState& st, int kind, const int* __restrict__ off,
+                                               const float4* __restrict__ map, int g) {
+  int lo = 0, hi = st.validNum;  // find v with prefix[v] <= g < prefix[v + 1]
+  while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.validPrefix[kind][mid] <= g) lo = mid; else hi = mid; }
+  return map[off[st.validInd[lo]] + (g - st.validPrefix[kind][lo])];
+}
+__device__ __forceinline__ int map_col(const LMState& st, float x, float y) {
+  const int ix = min(max((int)floorf((x - st.gridMinX) * (1.0f / kMapCell)), 0), kMapNX - 1);
+  const int iy = min(max((int)floorf((y - st.gridMinY) * (1.0f / kMapCell)), 0), kMapNY - 1);
+  return iy * kMapNX + ix;
+}
+// grid (nblk, 2, B), block 256
+__global__ void __launch_bounds__(256) lm_grid_count(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
+                                                      const float4* __restrict__ mapPts, int mapCap, int* __restrict__ cells) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (!st.solved) return;
+  for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
+    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, mapPts + ((size_t)b * 2 + kind) * mapCap, g);
+    atomicAdd(&cells[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
+  }
+}
+// grid (2, B), block 1024: exclusive scan of the column counts; cells -> starts (kept in `cellStart`) and cursors
+__global__ void __launch_bounds__(1024) lm_grid_scan(const LMState* __restrict__ stAll, int* __restrict__ cellStart, int* __restrict__ cursor) {
+  __shared__ SortSmem S;
+  const int kind = blockIdx.x, b = blockIdx.y;
+  if (!stAll[b].solved) return;
+  int* cs = cellStart + ((size_t)b * 2 + kind) * (kMapCols + 1);
+  int* cu = cursor + ((size_t)b * 2 + kind) * (kMapCols + 1);
+  const int chunk = kMapCols / 1024;
+  const int c0 = threadIdx.x * chunk;
+  int sum = 0;
+  for (int i = 0; i < chunk; ++i) sum += cu[c0 + i];
+  int run = block_exclusive_scan1024(sum, S);
+  for (int i = 0; i < chunk; ++i) { const int t = cu[c0 + i]; cu[c0 + i] = run; cs[c0 + i] = run; run += t; }
+  if (threadIdx.x == 1023) { cs[kMapCols] = run; cu[kMapCols] = run; }
+}
+__global__ void __launch_bounds__(256) lm_grid_scatter(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
+                                                        const float4* __restrict__ mapPts, int mapCap, int* __restrict__ cursor,
+                                                        float4* __restrict__ sorted) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (!st.solved) return;
+  for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
+    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, mapPts + ((size_t)b * 2 + kind) * mapCap, g);
+    const int pos = atomicAdd(&cursor[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
+    sorted[((size_t)b * 2 + kind) * mapCap + pos] = make_float4(p.x, p.y, p.z, __int_as_float(g));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Small dense kernels of the association (same algorithms as oracle/small_linalg.hpp).
+__device__ void sym_eig3_dev(const double A[9], double evals[3], double evecs[3][3]) {
+  double a[3][3] = {{A[0], A[1], A[2]}, {A[3], A[4], A[5]}, {A[6], A[7], A[8]}};
+  double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
+  for (int sweep = 0; sweep < 64; ++sweep) {
+    const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
+    const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
+    if (off <= 1e-300 || off <= 1e-32 * diag) break;
+    for (int p = 0; p < 2; ++p)
+      for (int q = p + 1; q < 3; ++q) {
+        if (a[p][q] == 0.0) continue;
+        const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+        for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
+        for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
+        for (int k = 0; k < 3; ++k) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
+      }
+  }
+  int order[3] = {0, 1, 2};
+  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j) if (a[order[j + 1]][order[j + 1]] < a[order[j]][order[j]]) { const int t = order[j]; order[j] = order[j + 1]; order[j + 1] = t; }
+  for (int k = 0; k < 3; ++k) {
+    evals[k] = a[order[k]][order[k]];
+    double n = 0.0;
+    for (int r = 0; r < 3; ++r) n += v[r][order[k]] * v[r][order[k]];
+    n = sqrt(n);
+    for (int r = 0; r < 3; ++r) evecs[k][r] = v[r][order[k]] / n;
+  }
+}
+__device__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5], double x[3]) {
+  constexpr int M = 5;
+  double A[M][3], b[M];
+  for (int i = 0; i < M; ++i) { b[i] = bin[i]; for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c]; }
+  int perm[3] = {0, 1, 2};
+  double maxnorm2 = 0.0;
+  for (int c = 0; c < 3; ++c) { double s = 0; for (int i = 0; i < M; ++i) s += A[i][c] * A[i][c]; maxnorm2 = fmax(maxnorm2, s); }
+  const double eps = 2.220446049250313e-16;
+  const double thresh = maxnorm2 * (eps / M) * (eps / M);
+  int rank = 0;
+  for (int k = 0; k < 3; ++k) {
+    int best = k; double bestn = -1.0;
+    for (int c = k; c < 3; ++c) { double s = 0; for (int i = k; i < M; ++i) s += A[i][c] * A[i][c]; if (s > bestn) { bestn = s; best = c; } }
+    if (bestn <= thresh) break;
+    if (best != k) { for (int i = 0; i < M; ++i) { const double t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; } const int t = perm[k]; perm[k] = perm[best]; perm[best] = t; }
+    const double nrm = sqrt(bestn);
+    const double alpha = A[k][k] > 0 ? -nrm : nrm;
+    double v[M];
+    for (int i = k; i < M; ++i) v[i] = A[i][k];
+    v[k] -= alpha;
+    double vn = 0; for (int i = k; i < M; ++i) vn += v[i] * v[i];
+    if (vn > 0) {
+      for (int c = k; c < 3; ++c) {
+        double s = 0; for (int i = k; i < M; ++i) s += v[i] * A[i][c];
+        s = 2.0 * s / vn;
+        for (int i = k; i < M; ++i) A[i][c] -= s * v[i];
+      }
+      double s = 0; for (int i = k; i < M; ++i) s += v[i] * b[i];
+      s = 2.0 * s / vn;
+      for (int i = k; i < M; ++i) b[i] -= s * v[i];
+    }
+    ++rank;
+  }
+  double y[3] = {0, 0, 0};
+  for (int k = rank - 1; k >= 0; --k) {
+    double s = b[k];
+    for (int c = k + 1; c < rank; ++c) s -= A[k][c] * y[c];
+    y[k] = s / A[k][k];
+  }
+  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
+// lm_associate: one warp per down-sampled scan point (grid-stride).  grid (512, 2, B), block 256.
+__global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+                                                     const int* __restrict__ cellStart, const float4* __restrict__ sorted,
+                                                     int mapCap, LMResidual* __restrict__ res) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (!st.solved) return;
+  const int l = lane_id();
+  for (int qi = blockIdx.x * 8 + (threadIdx.x >> 5); qi < st.stackNum[kind]; qi += gridDim.x * 8) {
+  const float4 po = stack[((size_t)b * 2 + kind) * cap + qi];
+  LMResidual* out = res + ((size_t)b * 2 + kind) * cap + qi;
+  // pointAssociateToMap (:146-155): double transform, rounded to float
+  double w[3];
+  quat_rotate(st.parameters, (double)po.x, (double)po.y, (double)po.z, w);
+  const float sx = (float)(w[0] + st.parameters[4]), sy = (float)(w[1] + st.parameters[5]), sz = (float)(w[2] + st.parameters[6]);
+  const int* cs = cellStart + ((size_t)b * 2 + kind) * (kMapCols + 1);
+  const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
+  const int qx = (int)floorf((sx - st.gridMinX) * (1.0f / kMapCell)), qy = (int)floorf((sy - st.gridMinY) * (1.0f / kMapCell));
+  // per-lane sorted top-5 of (distance bits << 32 | sub-map index); position in `sorted` kept alongside
+  unsigned long long bk[5];
+  int bp[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
+  for (int row = qy - 1; row <= qy + 1; ++row) {
+    if (row < 0 || row >= kMapNY) continue;
+    const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kMapNX - 1);
+    if (x0 > x1) continue;
+    const int a = cs[row * kMapNX + x0], e = cs[row * kMapNX + x1 + 1];
+    for (int t = a + l; t < e; t += 32) {
+      const float4 tp = S[t];
+      const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
+      if (key < bk[4]) {
+        int pos = t;
+#pragma unroll
+        for (int i = 0; i < 5; ++i)
+          if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+      }
+    }
+  }
+  // warp merge: five rounds of "smallest head wins"
+  unsigned long long top[5];
+  int topPos[5];
+  int head = 0;
+#pragma unroll
+  for (int r = 0; r < 5; ++r) {
+    unsigned long long mine = 0xffffffffffffffffull;
+    int minePos = -1;
+#pragma unroll
+    for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
+    const unsigned long long m = warp_min_u64(mine);
+    const unsigned win = __ballot_sync(0xffffffffu, mine == m && m != 0xffffffffffffffffull);
+    top[r] = m;
+    int wp = -1;
+    if (win) {
+      const int src = __ffs(win) - 1;
+      wp = __shfl_sync(0xffffffffu, minePos, src);
+      if (l == src) head++;
+    }
+    topPos[r] = wp;
+  }
+  LMResidual R;
+  R.type = 0; R.px = po.x; R.py = po.y; R.pz = po.z;
+#pragma unroll
+  for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
+  if (top[4] != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(top[4] >> 32)) < 1.0) {  // :479 / :547
+    double P[5][3];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) { const float4 tp = S[topPos[j]]; P[j][0] = tp.x; P[j][1] = tp.y; P[j][2] = tp.z; }
+    if (kind == 0) {  // :481-516
+      double c[3] = {0, 0, 0};
+      for (int j = 0; j < 5; ++j) { c[0] = c[0] + P[j][0]; c[1] = c[1] + P[j][1]; c[2] = c[2] + P[j][2]; }
+      c[0] = c[0] / 5.0; c[1] = c[1] / 5.0; c[2] = c[2] / 5.0;
+      double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+      for (int j = 0; j < 5; ++j) {
+        const double d[3] = {P[j][0] - c[0], P[j][1] - c[1], P[j][2] - c[2]};
+        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) cov[r * 3 + q] += d[r] * d[q];
+      }
+      double ev[3], evec[3][3];
+      sym_eig3_dev(cov, ev, evec);
+      if (ev[2] > 3 * ev[1]) {
+        R.type = 1;
+        for (int i = 0; i < 3; ++i) { R.v[i] = 0.1 * evec[2][i] + c[i]; R.v[3 + i] = -0.1 * evec[2][i] + c[i]; }
+      }
+    } else {  // :545-580
+      double A[15], bb[5] = {-1, -1, -1, -1, -1}, n[3];
+      for (int j = 0; j < 5; ++j) { A[j * 3] = P[j][0]; A[j * 3 + 1] = P[j][1]; A[j * 3 + 2] = P[j][2]; }
+      colpiv_qr_solve_5x3_dev(A, bb, n);
+      const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+      const double d = 1 / nn;
+      n[0] /= nn; n[1] /= nn; n[2] /= nn;
+      bool ok = true;
+      for (int j = 0; j < 5; ++j)
+        if (fabs(n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + d) > 0.2) { ok = false; break; }
+      if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
+    }
+  }
+  if (l == 0) *out = R;
+  }
+}
+
+// lm_solve: grid (B), block 256: one outer pass of :458-626 (the association was just done by lm_associate).
+__global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res, int cap, int pass,
+                                                 int max_iterations) {
+  __shared__ LMShared S;
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x;
+  LMState& st = stAll[b];
+  if (!st.solved) return;
+  SolveTrace* tr = &st.trace[pass];
+  const LMResidual* rc = res + ((size_t)b * 2 + 0) * cap;
+  const LMResidual* rs = res + ((size_t)b * 2 + 1) * cap;
+  const int nc = st.stackNum[0], ns = st.stackNum[1];
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) for (int i = 0; i < 7; ++i) S.x[i] = st.parameters[i];
+  __syncthreads();
+  {
+    int a = 0, c = 0;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) a += rc[i].type == 1;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) c += rs[i].type == 2;
+    a = __reduce_add_sync(0xffffffffu, a); c = __reduce_add_sync(0xffffffffu, c);
+    if (lane_id() == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], c); }
+    __syncthreads();
+    if (threadIdx.x == 0) { tr->n_corner = s_cnt[0]; tr->n_plane = s_cnt[1]; }
+  }
+  auto evaluate = [&](const double* x) {
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+    const double q[4] = {x[0], x[1], x[2], x[3]};
+    const double t[3] = {x[4], x[5], x[6]};
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+      const LMResidual& R = rc[i];
+      if (R.type != 1) continue;
+      const double a[3] = {R.v[0], R.v[1], R.v[2]}, bb[3] = {R.v[3], R.v[4], R.v[5]};
+      edge_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), a, bb, acc);
+    }
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+      const LMResidual& R = rs[i];
+      if (R.type != 2) continue;
+      const double n[3] = {R.v[0], R.v[1], R.v[2]};
+      plane_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), n, R.v[3], acc);
+    }
+    block_reduce28(acc, S.red, S.scratch);
+  };
+  lm_solve_block(S, tr, max_iterations, false, evaluate);
+  if (threadIdx.x == 0) for (int i = 0; i < 7; ++i) st.parameters[i] = S.x[i];
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// lm_insert_keys: grid (2, B), block 1024.  transformUpdate (:636, :140-144), map-frame coordinates of the stack
+// points and their cube ids, stable sort by cube id (:639-683 push the points in stack order), work list.
+__global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+                                                        float4* __restrict__ stackW, const int* __restrict__ cubeCnt,
+                                                        unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB, size_t workCap) {
+  __shared__ SortSmem S;
+  __shared__ int s_res;
+  const int kind = blockIdx.x, b = blockIdx.y;
+  LMState& st = stAll[b];
+  const int n = st.stackNum[kind];
+  const float4* in = stack + ((size_t)b * 2 + kind) * cap;
+  float4* outW = stackW + ((size_t)b * 2 + kind) * cap;
+  const size_t so = ((size_t)b * 2 + kind) * workCap;
+  unsigned* ka = kA + so; unsigned* va = vA + so; unsigned* kb = kB + so; unsigned* vb = vB + so;
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const float4 p = in[i];
+    double w[3];
+    quat_rotate(st.parameters, (double)p.x, (double)p.y, (double)p.z, w);
+    const float x = (float)(w[0] + st.parameters[4]), y = (float)(w[1] + st.parameters[5]), z = (float)(w[2] + st.parameters[6]);
+    outW[i] = make_float4(x, y, z, p.w);
+    int cI = (int)(((double)x + 25.0) / 50.0) + st.cenW, cJ = (int)(((double)y + 25.0) / 50.0) + st.cenH, cK = (int)(((double)z + 25.0) / 50.0) + st.cenD;
+    if ((double)x + 25.0 < 0) cI--;
+    if ((double)y + 25.0 < 0) cJ--;
+    if ((double)z + 25.0 < 0) cK--;
+    unsigned key = 0xffffu;
+    if (cI >= 0 && cI < kCubeW && cJ >= 0 && cJ < kCubeH && cK >= 0 && cK < kCubeD) key = (unsigned)(cI + kCubeW * cJ + kCubeW * kCubeH * cK);
+    ka[i] = key; va[i] = (unsigned)i;
+  }
+  __syncthreads();
+  const int cur = cta_radix_sort(ka, va, kb, vb, n, 16, S);
+  if (threadIdx.x == 0) s_res = cur;
+  __syncthreads();
+  const unsigned* keys = s_res ? kb : ka;
+  const unsigned* vals = s_res ? vb : va;
+  // result always left in (kA, vA) so the next kernel needs no flag
+  if (s_res) { for (int i = threadIdx.x; i < n; i += 1024) { ka[i] = keys[i]; va[i] = vals[i]; } }
+  __syncthreads();
+  // runs of equal cube id in the sorted key array: heads found in parallel, then a short serial work-list build
+  __shared__ int s_nh, s_headCube[kMaxWork], s_headStart[kMaxWork], s_headEnd[kMaxWork];
+  if (threadIdx.x == 0) s_nh = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 1024) {
+    const unsigned c = ka[i];
+    if (c != 0xffffu && (i == 0 || ka[i - 1] != c)) {
+      const int h = atomicAdd(&s_nh, 1);
+      if (h < kMaxWork) { s_headCube[h] = (int)c; s_headStart[h] = i; }
+    }
+  }
+  __syncthreads();
+  const int nh = min(s_nh, kMaxWork);
+  for (int h = threadIdx.x; h < nh; h += 1024) {  // end of run h = start of the next different key
+    int lo = s_headStart[h], hi = n;               // keys are sorted: binary search the first index with key > cube
+    const unsigned c = (unsigned)s_headCube[h];
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (ka[mid] <= c) lo = mid + 1; else hi = mid; }
+    s_headEnd[h] = lo;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    // work list: every valid cube (re-filtered, :689-702) then every other cube that received points (append only)
+    const int* cnt = cubeCnt + ((size_t)b * 2 + kind) * kCubes;
+    if (s_nh > kMaxWork) st.error |= 1;
+    int wn = 0, in0 = 0;
+    for (int v = 0; v < st.validNum && wn < kMaxWork; ++v) {
+      const int c = st.validInd[v];
+      bool dup = false;
+      for (int u = 0; u < wn; ++u) if (st.workCube[kind][u] == c) { dup = true; break; }
+      if (dup) continue;
+      st.workCube[kind][wn] = c; st.workFilter[kind][wn] = 1; st.workNew0[kind][wn] = 0; st.workNewN[kind][wn] = 0; ++wn;
+    }
+    for (int h = 0; h < nh; ++h) {
+      const int c = s_headCube[h];
+      int slot = -1;
+      for (int u = 0; u < wn; ++u) if (st.workCube[kind][u] == c) { slot = u; break; }
+      if (slot < 0 && wn < kMaxWork) { slot = wn++; st.workCube[kind][slot] = c; st.workFilter[kind][slot] = 0; }
+      if (slot >= 0) { st.workNew0[kind][slot] = s_headStart[h]; st.workNewN[kind][slot] = s_headEnd[h] - s_headStart[h]; } else st.error |= 1;
+    }
+    for (int u = 0; u < wn; ++u) { st.workIn0[kind][u] = in0; in0 += cnt[st.workCube[kind][u]] + st.workNewN[kind][u]; }
+    st.workIn0[kind][wn] = in0;
+    st.workNum[kind] = wn;
+    if ((size_t)in0 + (size_t)cap > workCap) st.error |= 2;
+  }
+}
+__global__ void lm_transform_update(LMState* __restrict__ stAll, int B) {  // :140-144
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LMState& st = stAll[b];
+  const double* q = st.q_wodom;
+  const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+  const double qi[4] = {-q[0] / n2, -q[1] / n2, -q[2] / n2, q[3] / n2};  // Eigen Quaternion::inverse()
+  double qm[4], r[3];
+  quat_mul(st.parameters, qi, qm);
+  quat_rotate(qm, st.t_wodom[0], st.t_wodom[1], st.t_wodom[2], r);
+  for (int i = 0; i < 4; ++i) st.q_wmap_wodom[i] = qm[i];
+  for (int i = 0; i < 3; ++i) st.t_wmap_wodom[i] = st.parameters[4 + i] - r[i];
+}
+
+// lm_refilter: grid (kMaxWork, 2, B), block 1024.  One work cube per CTA: input = old cube ++ new points (stack order).
+__global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll, const int* __restrict__ cubeOff, const int* __restrict__ cubeCnt,
+                                                     const float4* __restrict__ mapPts, int mapCap, const float4* __restrict__ stackW,
+                                                     int cap, const unsigned* __restrict__ vAins, float lineRes, float planeRes,
+                                                     float4* __restrict__ concat, float4* __restrict__ staged, unsigned* kA, unsigned* vA,
+                                                     unsigned* kB, unsigned* vB, size_t workCap) {
+  __shared__ SortSmem S;
+  __shared__ float red[6 * 32];
+  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  LMState& st = stAll[b];
+  if (u >= st.workNum[kind] || st.error) return;
+  const int c = st.workCube[kind][u];
+  const size_t so = ((size_t)b * 2 + kind) * workCap;
+  const int in0 = st.workIn0[kind][u];
+  const int nOld = cubeCnt[((size_t)b * 2 + kind) * kCubes + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
+  const float4* old = mapPts + ((size_t)b * 2 + kind) * mapCap + cubeOff[((size_t)b * 2 + kind) * kCubes + c];
+  const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
+  const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points, in stack order
+  float4* in = concat + so + in0;
+  float4* out = staged + so + in0;
+  for (int i = threadIdx.x; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
+  __syncthreads();
+  int m;
+  if (st.workFilter[kind][u]) {
+    // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
+    m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red);
+  } else {
+    for (int i = threadIdx.x; i < n; i += 1024) out[i] = in[i];
+    m = n;
+  }
+  if (threadIdx.x == 0) st.workOutN[kind][u] = m;
+}
+
+// lm_rebuild_tables: grid (2, B), block 1024: new cube table (work cubes get their new size, the others keep theirs).
+__global__ void __launch_bounds__(1024) lm_rebuild_tables(LMState* __restrict__ stAll, const int* __restrict__ offSrc, const int* __restrict__ cntSrc,
+                                                           int* __restrict__ offDst, int* __restrict__ cntDst, short* __restrict__ workOfAll, int mapCap) {
+  __shared__ SortSmem S;
+  const int kind = blockIdx.x, b = blockIdx.y;
+  LMState& st = stAll[b];
+  const int* oS = offSrc + ((size_t)b * 2 + kind) * kCubes;
+  const int* cS = cntSrc + ((size_t)b * 2 + kind) * kCubes;
+  int* oD = offDst + ((size_t)b * 2 + kind) * kCubes;
+  int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
+  short* workOf = workOfAll + ((size_t)b * 2 + kind) * kCubes;
+  for (int c = threadIdx.x; c < kCubes; c += 1024) workOf[c] = -1;
+  __syncthreads();
+  if (!st.error) for (int u = threadIdx.x; u < st.workNum[kind]; u += 1024) workOf[st.workCube[kind][u]] = (short)u;
+  __syncthreads();
+  const int per = (kCubes + 1023) / 1024;
+  const int c0 = min((int)threadIdx.x * per, kCubes), c1 = min(c0 + per, kCubes);
+  int sum = 0;
+  for (int c = c0; c < c1; ++c) sum += workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : cS[c];
+  int run = block_exclusive_scan1024(sum, S);
+  const int total = S.total;
+  if (total > mapCap) {  // keep the old content (reported through the error bits of the pose export)
+    if (threadIdx.x == 0) st.error |= 4;
+    for (int c = c0; c < c1; ++c) { workOf[c] = -1; }
+    __syncthreads();
+    sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cS[c];
+    run = block_exclusive_scan1024(sum, S);
+  }
+  for (int c = c0; c < c1; ++c) { const int n = workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : cS[c]; oD[c] = run; cD[c] = n; run += n; }
+  if (threadIdx.x == 0) st.poolEnd[kind] = S.total;
+}
+// lm_rebuild_copy: one warp per cube, grid (ceil(kCubes / 8), 2, B), block 256: compaction into the other map buffer.
+__global__ void __launch_bounds__(256) lm_rebuild_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
+                                                        const int* __restrict__ offDst, const int* __restrict__ cntDst,
+                                                        const short* __restrict__ workOfAll, const float4* __restrict__ mapSrc,
+                                                        float4* __restrict__ mapDst, int mapCap, const float4* __restrict__ staged, size_t workCap) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
+  if (c >= kCubes) return;
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  const int n = cntDst[tb + c];
+  if (!n) return;
+  const int u = workOfAll[tb + c];
+  const float4* src = u >= 0 ? staged + ((size_t)b * 2 + kind) * workCap + stAll[b].workIn0[kind][u]
+                             : mapSrc + ((size_t)b * 2 + kind) * mapCap + offSrc[tb + c];
+  float4* dst = mapDst + ((size_t)b * 2 + kind) * mapCap + offDst[tb + c];
+  for (int i = lane_id(); i < n; i += 32) dst[i] = src[i];
+}
+
+__global__ void lm_export_pose(const LMState* __restrict__ stAll, double* __restrict__ pose, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const LMState& s = stAll[b];
+  double* o = pose + (size_t)b * 16;
+  for (int i = 0; i < 7; ++i) o[i] = s.parameters[i];
+  for (int i = 0; i < 4; ++i) o[7 + i] = s.q_wmap_wodom[i];
+  for (int i = 0; i < 3; ++i) o[11 + i] = s.t_wmap_wodom[i];
+  o[14] = s.error; o[15] = s.solved;
+}
+__global__ void lm_init_state(LMState* stAll, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LMState& s = stAll[b];
+  for (int i = 0; i < 7; ++i) s.parameters[i] = i == 3 ? 1.0 : 0.0;           // :74-83
+  for (int i = 0; i < 4; ++i) { s.q_wmap_wodom[i] = i == 3 ? 1.0 : 0.0; s.q_wodom[i] = i == 3 ? 1.0 : 0.0; }  // :87-91
+  for (int i = 0; i < 3; ++i) { s.t_wmap_wodom[i] = 0.0; s.t_wodom[i] = 0.0; }
+  s.cenW = 10; s.cenH = 10; s.cenD = 5;                                       // laser_mapping.h:76-78
+  s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
+  s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0;
+  s.trace[0].n_records = s.trace[1].n_records = 0;
+}
+
+// ===============================================================================================================
+// host side
+static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
+  if (lm->allocated) return cudaSuccess;
+  const size_t B = lm->B, cap = lm->cap, mapCap = lm->mapCap;
+  lm->workCap = mapCap + 2 * cap;  // refilter inputs (<= map + scan) after a cap-sized area for the scan's own sorts
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemsetAsync(*p, 0, bytes, st); } };
+  A((void**)&lm->st, B * sizeof(LMState));
+  for (int i = 0; i < 2; ++i) {
+    A((void**)&lm->cubeOff[i], B * 2 * kCubes * sizeof(int)); A((void**)&lm->cubeCnt[i], B * 2 * kCubes * sizeof(int));
+    A((void**)&lm->mapPts[i], B * 2 * mapCap * sizeof(float4));
+  }
+  A((void**)&lm->stack, B * 2 * cap * sizeof(float4)); A((void**)&lm->stackW, B * 2 * cap * sizeof(float4));
+  A((void**)&lm->keyA, B * 2 * lm->workCap * 4); A((void**)&lm->valA, B * 2 * lm->workCap * 4);
+  A((void**)&lm->keyB, B * 2 * lm->workCap * 4); A((void**)&lm->valB, B * 2 * lm->workCap * 4);
+  A((void**)&lm->concat, B * 2 * lm->workCap * sizeof(float4)); A((void**)&lm->staged, B * 2 * lm->workCap * sizeof(float4));
+  A((void**)&lm->cellStart, B * 2 * (kMapCols + 1) * sizeof(int)); A((void**)&lm->cursor, B * 2 * (kMapCols + 1) * sizeof(int));
+  A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
+  A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
+  A((void**)&lm->pose, B * 16 * sizeof(double));
+  A((void**)&lm->workOf, B * 2 * kCubes * sizeof(short));
+  if (e != cudaSuccess) return e;
+  VB_LAUNCH(lm->prof, K_LM_MISC, st, lm_init_state<<<(lm->B + 127) / 128, 128, 0, st>>>(lm->st, lm->B));
+  lm->allocated = true;
+  return cudaGetLastError();
+}
+
+cudaError_t lm_create(Profiler* prof, cudaStream_t, int B, int cap, const vloam_lidar_params* p, LMDevice** out) {
+  LMDevice* lm = new LMDevice();
+  lm->B = B; lm->cap = cap; lm->p = *p; lm->prof = prof;
+  lm->mapCap = p->map_capacity_points > 0 ? p->map_capacity_points : (1 << 20);
+  *out = lm;  // device memory is allocated on first use (vloam_laser_mapping / vloam_map_set_cube)
+  return cudaSuccess;
+}
+void lm_destroy(LMDevice* lm) {
+  if (!lm) return;
+  if (lm->allocated) {
+    cudaFree(lm->st);
+    for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->mapPts[i]); }
+    cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
+    cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->cellStart); cudaFree(lm->cursor); cudaFree(lm->sorted);
+    cudaFree(lm->res); cudaFree(lm->pose); cudaFree(lm->workOf);
+  }
+  delete lm;
+}
+void lm_reset(LMDevice* lm) { if (lm) lm->reset_valid = true; }
+
+cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const float4* cornerLast, const float4* surfLast,
+                   const LOState* lo, bool skip_frame) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  Profiler* prof = lm->prof;
+  const int B = lm->B, cap = lm->cap, mapCap = lm->mapCap;
+  if (skip_frame) {
+    // :186-190: a skipped frame only refreshes the high-frequency pose; the map state is untouched
+    VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
+    return cudaGetLastError();
+  }
+  // the map = mapPts[ps] addressed by tables[ts].  lm_prepare writes the shifted tables to tables[td]; everything up to
+  // the re-filter reads (tables[td], mapPts[ps]); the rebuild writes (tables[ts], mapPts[pd]).
+  const int ps = lm->curPts, pd = ps ^ 1, ts = lm->curTab, td = ts ^ 1;
+  const float lineRes = (float)lm->p.mapping_line_resolution, planeRes = (float)lm->p.mapping_plane_resolution;
+  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, lm->cubeOff[ts], lm->cubeCnt[ts], lm->cubeOff[td],
+                                                                  lm->cubeCnt[td], lm->reset_valid ? 1 : 0));
+  lm->reset_valid = false;
+  // C4: VoxelGrid of the scan features (scratch: the first `cap` entries of each key/val slab)
+  VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
+                                                                              lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
+  // C5: sub-map column index
+  e = cudaMemsetAsync(lm->cursor, 0, (size_t)B * 2 * (kMapCols + 1) * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_count<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->mapPts[ps], mapCap, lm->cursor));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scan<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->cellStart, lm->cursor));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scatter<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->mapPts[ps], mapCap, lm->cursor, lm->sorted));
+  // C6-C9: outer passes of association + LM
+  for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
+    const int tp = pass < 2 ? pass : 1;
+    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(512, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
+    VB_LAUNCH(prof, K_LM_SOLVE, st, lm_solve<<<B, 256, 0, st>>>(lm->st, lm->res, cap, tp, lm->p.lm_max_iterations));
+  }
+  // C10-C12: transformUpdate, insertion, re-filter, compaction
+  VB_LAUNCH(prof, K_LM_MISC, st, lm_transform_update<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B));
+  VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->keyA, lm->valA,
+                                                                               lm->keyB, lm->valB, lm->workCap));
+  // the cube-sorted stack indices stay in valA[0 .. n); the per-cube filters use the key/val slabs from offset `cap` on
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->mapPts[ps], mapCap,
+                                                                                         lm->stackW, cap, lm->valA, lineRes, planeRes, lm->concat, lm->staged,
+                                                                                         lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_rebuild_tables<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeOff[ts], lm->cubeCnt[ts],
+                                                                                     lm->workOf, mapCap));
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_rebuild_copy<<<dim3((kCubes + 7) / 8, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->workOf,
+                                                                                                   lm->mapPts[ps], lm->mapPts[pd], mapCap, lm->staged, lm->workCap));
+  VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
+  lm->curPts = pd;  // tables[ts] now describe mapPts[pd]; (tables[td], mapPts[ps]) still hold the pre-insertion state
+  lm->ran = true;
+  return cudaGetLastError();
+}
+
+cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  std::vector<double> h((size_t)lm->B * 16);
+  e = cudaMemcpyAsync(h.data(), lm->pose, h.size() * sizeof(double), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  for (int b = 0; b < lm->B; ++b) for (int i = 0; i < 14; ++i) pose_out[(size_t)b * 14 + i] = h[(size_t)b * 16 + i];
+  for (int b = 0; b < lm->B; ++b) if (h[(size_t)b * 16 + 14] != 0.0) return cudaErrorInvalidValue;  // capacity / work-list overflow
+  return cudaSuccess;
+}
+
+static cudaError_t lm_fetch_state(LMDevice* lm, cudaStream_t st, int stream, LMState* out) {
+  cudaError_t e = cudaMemcpyAsync(out, lm->st + stream, sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
+cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  LMState S;
+  e = lm_fetch_state(lm, st, stream, &S);
+  if (e != cudaSuccess) return e;
+  if (which == VLOAM_CLOUD_CORNER_STACK || which == VLOAM_CLOUD_SURF_STACK) {
+    const int kind = which == VLOAM_CLOUD_CORNER_STACK ? 0 : 1;
+    const int n = S.stackNum[kind], m = n < capacity ? n : capacity;
+    if (n_out) *n_out = n;
+    if (m > 0 && out) {
+      e = cudaMemcpyAsync(out, lm->stack + ((size_t)stream * 2 + kind) * lm->cap, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    }
+    return e;
+  }
+  // laserCloudCornerFromMap / SurfFromMap of the last solveMapping: the pre-insertion map state
+  const int kind = which == VLOAM_CLOUD_CORNER_MAP ? 0 : 1;
+  const int n = lm->ran ? S.fromMapNum[kind] : 0;
+  if (n_out) *n_out = n;
+  if (!out || capacity <= 0 || n == 0) return cudaSuccess;
+  const int pts = lm->curPts ^ 1, tab = lm->curTab ^ 1;
+  std::vector<int> off(kCubes), cnt(kCubes);
+  e = cudaMemcpyAsync(off.data(), lm->cubeOff[tab] + ((size_t)stream * 2 + kind) * kCubes, kCubes * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), lm->cubeCnt[tab] + ((size_t)stream * 2 + kind) * kCubes, kCubes * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  int written = 0;
+  for (int v = 0; v < S.validNum && written < capacity; ++v) {
+    const int c = S.validInd[v];
+    const int m = cnt[c] < capacity - written ? cnt[c] : capacity - written;
+    if (m > 0) {
+      e = cudaMemcpyAsync(out + (size_t)written * 4, lm->mapPts[pts] + ((size_t)stream * 2 + kind) * lm->mapCap + off[c], (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+      if (e != cudaSuccess) return e;
+      written += m;
+    }
+  }
+  return cudaStreamSynchronize(st);
+}
+
+cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, const float* xyzi, int n) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  LMState S;
+  e = lm_fetch_state(lm, st, stream, &S);
+  if (e != cudaSuccess) return e;
+  if ((long long)S.poolEnd[kind] + n > lm->mapCap) return cudaErrorInvalidValue;
+  const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
+  const int off = S.poolEnd[kind];
+  if (n) e = cudaMemcpyAsync(lm->mapPts[lm->curPts] + ((size_t)stream * 2 + kind) * lm->mapCap + off, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeOff[lm->curTab] + tb, &off, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeCnt[lm->curTab] + tb, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  const int newEnd = off + n;
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&lm->st[stream].poolEnd[kind], &newEnd, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
+cudaError_t lm_get_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, float* out, int capacity, int* n_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
+  int off = 0, n = 0;
+  e = cudaMemcpyAsync(&off, lm->cubeOff[lm->curTab] + tb, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&n, lm->cubeCnt[lm->curTab] + tb, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  if (n_out) *n_out = n;
+  const int m = n < capacity ? n : capacity;
+  if (m > 0 && out) {
+    e = cudaMemcpyAsync(out, lm->mapPts[lm->curPts] + ((size_t)stream * 2 + kind) * lm->mapCap + off, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  return e;
+}
+
+cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  std::vector<LMState> h(lm->B);
+  e = cudaMemcpyAsync(h.data(), lm->st, h.size() * sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  for (int b = 0; b < lm->B; ++b) {
+    int* o = info + (size_t)b * 8;
+    o[0] = h[b].cenW; o[1] = h[b].cenH; o[2] = h[b].cenD; o[3] = h[b].validNum;
+    o[4] = h[b].fromMapNum[0]; o[5] = h[b].fromMapNum[1]; o[6] = h[b].stackNum[0]; o[7] = h[b].stackNum[1];
+  }
+  return cudaSuccess;
+}
+
+cudaError_t lm_get_trace(LMDevice* lm, cudaStream_t st, int stream, int pass, double* records, int* info, double* para) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  LMState S;
+  e = lm_fetch_state(lm, st, stream, &S);
+  if (e != cudaSuccess) return e;
+  const SolveTrace& t = S.trace[pass];
+  if (info) { info[0] = t.n_records; info[1] = t.termination; info[2] = t.n_corner; info[3] = t.n_plane; }
+  if (para) for (int i = 0; i < 7; ++i) para[i] = t.para[i];
+  if (records) for (int i = 0; i < kMaxLMRecords; ++i) {
+    const LMRecord& r = t.rec[i];
+    double* o = records + (size_t)i * 7;
+    o[0] = r.cost; o[1] = r.candidate_cost; o[2] = r.model_cost_change; o[3] = r.relative_decrease; o[4] = r.radius;
+    o[5] = r.step_is_valid; o[6] = r.step_is_successful;
+  }
+  return cudaSuccess;
+}
+
+}  // namespace vb
