@@ -1,0 +1,88 @@
+// vloam_b200 — ROS-free C++ host mirror of the reference's LiDAR façade over the C ABI.
+//
+// Same method names, argument meaning and call order as vloam::LidarOdometryMapping
+// (reference include/lidar_odometry_mapping/lidar_odometry_mapping.h:45-86), with pcl::PointCloud replaced by plain
+// float arrays (x, y, z[, pad] per point) so it compiles without ROS / PCL.  The ROS adapter (lidar_odometry_mapping_b200.h)
+// is a thin wrapper around this class.
+#pragma once
+#include <array>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/vloam_b200.h"
+
+namespace vloam_b200 {
+
+struct Pose {
+  std::array<double, 4> q{{0, 0, 0, 1}};  // x, y, z, w (Eigen::Quaterniond::coeffs order)
+  std::array<double, 3> t{{0, 0, 0}};
+};
+
+class LidarOdometryMapping {
+ public:
+  explicit LidarOdometryMapping(int device = 0) {
+    if (vloam_ctx_create(device, &ctx_) != VLOAM_OK) throw std::runtime_error("vloam_ctx_create failed (no CUDA device?)");
+    vloam_lidar_params_default(&params_);
+  }
+  ~LidarOdometryMapping() {
+    if (h_) vloam_lidar_destroy(h_);
+    if (ctx_) vloam_ctx_destroy(ctx_);
+  }
+  LidarOdometryMapping(const LidarOdometryMapping&) = delete;
+  LidarOdometryMapping& operator=(const LidarOdometryMapping&) = delete;
+
+  vloam_lidar_params& params() { return params_; }  // fill from the ROS parameter server before init()
+
+  // lidar_odometry_mapping.cpp:40-63
+  void init() {
+    if (h_) { vloam_lidar_destroy(h_); h_ = nullptr; }
+    check(vloam_lidar_create(ctx_, &params_, &h_));
+  }
+  // lidar_odometry_mapping.cpp:65-71
+  void reset() { check(vloam_lidar_reset(h_)); }
+  // lidar_odometry_mapping.cpp:73-94: `points` = n records of `stride_floats` floats (4 for pcl::PointXYZ)
+  void scanRegistrationIO(const float* points, int n, int stride_floats = 4) {
+    check(vloam_scan_registration(h_, points, &n, stride_floats, (size_t)n));
+  }
+  // lidar_odometry_mapping.cpp:96-123: vo_prior = velo_last_VOT_velo_curr (q xyzw, t) or nullptr
+  void laserOdometryIO(const double* vo_prior = nullptr) {
+    double p[14];
+    int c[2];
+    check(vloam_laser_odometry(h_, vo_prior, p, c));
+    for (int i = 0; i < 4; ++i) { last_curr.q[i] = p[i]; odom.q[i] = p[7 + i]; }
+    for (int i = 0; i < 3; ++i) { last_curr.t[i] = p[4 + i]; odom.t[i] = p[11 + i]; }
+    corner_correspondence = c[0]; plane_correspondence = c[1];
+  }
+  // lidar_odometry_mapping.cpp:125-154
+  void laserMappingIO() {
+    double p[14];
+    check(vloam_laser_mapping(h_, p));
+    for (int i = 0; i < 4; ++i) { mapped.q[i] = p[i]; wmap_wodom.q[i] = p[7 + i]; }
+    for (int i = 0; i < 3; ++i) { mapped.t[i] = p[4 + i]; wmap_wodom.t[i] = p[11 + i]; }
+  }
+  // ScanRegistration::output / LaserOdometry::output clouds as XYZI records
+  std::vector<float> cloud(int which) {
+    int n = 0;
+    check(vloam_get_cloud(h_, 0, which, nullptr, 0, &n));
+    std::vector<float> out((size_t)n * 4);
+    if (n) check(vloam_get_cloud(h_, 0, which, out.data(), n, &n));
+    return out;
+  }
+
+  Pose last_curr;   // q_last_curr / t_last_curr  -> vloam_tf->base_prev_LOT_base_curr   (laser_odometry.cpp:563-567)
+  Pose odom;        // q_w_curr / t_w_curr        -> vloam_tf->world_LOT_base_last        (laser_odometry.cpp:570-571)
+  Pose mapped;      // mapping q_w_curr / t_w_curr -> vloam_tf->world_MOT_base_last       (laser_mapping.cpp:728-729)
+  Pose wmap_wodom;
+  int corner_correspondence = 0, plane_correspondence = 0;
+
+ private:
+  void check(int rc) {
+    if (rc != VLOAM_OK) throw std::runtime_error(std::string("vloam_b200: ") + vloam_last_error(ctx_));
+  }
+  vloam_ctx* ctx_ = nullptr;
+  vloam_lidar* h_ = nullptr;
+  vloam_lidar_params params_{};
+};
+
+}  // namespace vloam_b200

@@ -52,8 +52,8 @@ struct SRHeader {
 
 // Uniform xy-column grid over one target cloud (the kd-tree replacement of laserOdometry, laser_odometry.cpp:525-526).
 // Points are counting-sorted by column; column (ix, iy) owns sorted[cellStart[iy*nx+ix] .. cellStart[iy*nx+ix+1]).
-constexpr int kGridCap = 65536;   // max columns per grid
-constexpr float kGridCell = 0.5f; // column size (m); grows by 1.25x until the cloud's xy extent fits kGridCap columns
+constexpr int kGridCap = 40000;    // max columns per grid (the column table lives in shared memory while it is built)
+constexpr float kGridCell = 1.0f;  // column size (m); grows by 1.25x until the cloud's xy extent fits kGridCap columns
 struct GridHeader {
   float minx, miny, c, inv_c;
   int nx, ny, n;
