@@ -288,6 +288,40 @@ __device__ __forceinline__ void grid_visit_shell(const GridHeader& G, const int*
     }
   }
 }
+
+// Best-first visit of the 3 x 3 column block around the query: columns are taken in order of their lower bound on
+// the distance to any point inside them (distance from the query to the column's rectangle, shrunk by the rounding
+// margin), and the walk stops as soon as that bound exceeds `limit()` — the largest distance that could still improve
+// a result.  Replaces shell k = 1 of grid_visit_shell; later shells (k >= 2) are only needed when the block's safe
+// radius is not enough.  `visit(t)` as in grid_visit_shell; `limit()` must be warp-uniform.
+template <typename F, typename L>
+__device__ __forceinline__ void grid_visit_block_best_first(const GridHeader& G, const int* __restrict__ cs, float sx, float sy,
+                                                            int qx, int qy, F visit, L limit) {
+  const int l = lane_id();
+  int a = 0, bnd = 0;
+  unsigned lbBits = 0xffffffffu;
+  if (l < 9) {
+    const int cx = qx + (l % 3) - 1, cy = qy + (l / 3) - 1;
+    if (cx >= 0 && cx < G.nx && cy >= 0 && cy < G.ny) {
+      a = cs[cy * G.nx + cx]; bnd = cs[cy * G.nx + cx + 1];
+      if (bnd > a) {
+        const float x0 = G.minx + (float)cx * G.c, y0 = G.miny + (float)cy * G.c;
+        const float ddx = fmaxf(fmaxf(x0 - sx, sx - (x0 + G.c)), 0.f), ddy = fmaxf(fmaxf(y0 - sy, sy - (y0 + G.c)), 0.f);
+        const float lb = fmaxf(sqrtf(ddx * ddx + ddy * ddy) * (1.0f - 1e-5f) - 1e-4f, 0.f);
+        lbBits = __float_as_uint(lb * lb);
+      }
+    }
+  }
+  while (true) {
+    const unsigned m = __reduce_min_sync(0xffffffffu, lbBits);
+    if (m == 0xffffffffu || __uint_as_float(m) > limit()) break;
+    const int src = __ffs(__ballot_sync(0xffffffffu, lbBits == m)) - 1;
+    const int aa = __shfl_sync(0xffffffffu, a, src), bb = __shfl_sync(0xffffffffu, bnd, src);
+    if (l == src) lbBits = 0xffffffffu;
+    for (int t = aa + l; t < bb; t += 32) visit(t);
+  }
+}
+
 // Squared radius within which the visited block [qx-k, qx+k] x [qy-k, qy+k] is guaranteed complete (0 if none).
 __device__ __forceinline__ float grid_safe_radius(const GridHeader& G, float sx, float sy, int qx, int qy, int k) {
   const float xl = sx - (G.minx + (float)(qx - k) * G.c), xr = (G.minx + (float)(qx + k + 1) * G.c) - sx;
@@ -331,14 +365,19 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
     const int qx = cell_coord(sx, G.minx, G.inv_c), qy = cell_coord(sy, G.miny, G.inv_c);
     // ---- phase 1: exact nearest neighbour (laser_odometry.cpp:269 / :356)
     unsigned long long best = 0xffffffffffffffffull;
+    auto visit1 = [&](int t) {
+      const float4 tp = S[t];
+      const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)SI[t];
+      best = key < best ? key : best;
+    };
+    // a point at exactly the same distance could still win the index tie-break, hence `>` in the walk (limit = best)
+    grid_visit_block_best_first(G, cs, sx, sy, qx, qy, visit1, [&]() {
+      return __uint_as_float(__reduce_min_sync(0xffffffffu, (unsigned)(best >> 32)));  // +inf bits (0xffffffff -> NaN) handled below
+    });
+    best = warp_min_u64(best);
     for (int k = 1;; ++k) {
-      grid_visit_shell(G, cs, qx, qy, k, [&](int t) {
-        const float4 tp = S[t];
-        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)SI[t];
-        best = key < best ? key : best;
-      });
-      best = warp_min_u64(best);
+      if (k > 1) { grid_visit_shell(G, cs, qx, qy, k, visit1); best = warp_min_u64(best); }
       const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
       if (R >= 5.0f) break;
       if (best != 0xffffffffffffffffull && R > 0.f && __uint_as_float((unsigned)(best >> 32)) <= R * R) break;
@@ -358,24 +397,35 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
         int hi_j = nT, lo_j = 0;
         if (id + 3 <= kMaxRings - 1) hi_j = min(G.firstFull[id + 3], G.ringStart[min(id + 4, kMaxRings)]);
         if (id - 2 >= 0) lo_j = max(G.lastLow[id - 2], G.ringStart[id - 2] - 1) + 1;
+        auto visit2 = [&](int t) {
+          const int j = SI[t];
+          if (j < lo_j || j >= hi_j || j == closest) return;
+          const float4 tp = S[t];
+          const float d = sqdist_f(tp.x, tp.y, tp.z, sx, sy, sz);
+          if (!((double)d < 25.0)) return;
+          const int rid = (int)tp.w;
+          const bool fwd = j > closest;
+          const unsigned order = fwd ? (unsigned)j : 0x80000000u + (unsigned)(nT - j);
+          const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | order;
+          const bool classA = fwd ? (rid <= id) : (rid >= id);  // same-ring side of the walk
+          if (isCorner) { if (!classA) k2 = key < k2 ? key : k2; }
+          else if (classA) k2 = key < k2 ? key : k2;
+          else k3 = key < k3 ? key : k3;
+        };
+        // a column can still matter while its bound is below the worst of the needed classes (25 = none found yet)
+        grid_visit_block_best_first(G, cs, sx, sy, qx, qy, visit2, [&]() {
+          const unsigned d2 = __reduce_min_sync(0xffffffffu, (unsigned)(k2 >> 32));
+          float lim = d2 == 0xffffffffu ? 25.0f : __uint_as_float(d2);
+          if (!isCorner) {
+            const unsigned d3 = __reduce_min_sync(0xffffffffu, (unsigned)(k3 >> 32));
+            lim = fmaxf(lim, d3 == 0xffffffffu ? 25.0f : __uint_as_float(d3));
+          }
+          return lim;
+        });
+        k2 = warp_min_u64(k2);
+        k3 = warp_min_u64(k3);
         for (int k = 1;; ++k) {
-          grid_visit_shell(G, cs, qx, qy, k, [&](int t) {
-            const int j = SI[t];
-            if (j < lo_j || j >= hi_j || j == closest) return;
-            const float4 tp = S[t];
-            const float d = sqdist_f(tp.x, tp.y, tp.z, sx, sy, sz);
-            if (!((double)d < 25.0)) return;
-            const int rid = (int)tp.w;
-            const bool fwd = j > closest;
-            const unsigned order = fwd ? (unsigned)j : 0x80000000u + (unsigned)(nT - j);
-            const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | order;
-            const bool classA = fwd ? (rid <= id) : (rid >= id);  // same-ring side of the walk
-            if (isCorner) { if (!classA) k2 = key < k2 ? key : k2; }
-            else if (classA) k2 = key < k2 ? key : k2;
-            else k3 = key < k3 ? key : k3;
-          });
-          k2 = warp_min_u64(k2);
-          k3 = warp_min_u64(k3);
+          if (k > 1) { grid_visit_shell(G, cs, qx, qy, k, visit2); k2 = warp_min_u64(k2); k3 = warp_min_u64(k3); }
           const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
           if (R >= 5.0f) break;
           if (R > 0.f) {
