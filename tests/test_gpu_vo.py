@@ -1,0 +1,81 @@
+"""GPU parity tests for the visual-odometry part vs the oracle."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+@pytest.mark.parametrize("rect33", [1.0, 0.0])   # 0.0 = the ROS path's rect0_T_cam(3,3)
+def test_vo_depth_buckets_query_and_solve(synth, oracle, rect33):
+    import vloam_b200 as V
+    stream = synth.ScanStream(51, n_cols=1024)
+    cam_T_velo, rect0_T_cam, P = synth.kitti_like_calibration()
+    rect0_T_cam = rect0_T_cam.copy(); rect0_T_cam[3, 3] = rect33
+    vo = V.VisualOdometry(batch=1, max_points=64 * 1024, max_matches=1024)
+    vo.setUpPointCloud(cam_T_velo, rect0_T_cam, P)
+    ovo = oracle.VisualOdometry(cam_T_velo, rect0_T_cam, P)
+    rng = np.random.default_rng(5)
+    for k in range(3):
+        cloud = stream.scan(k)
+        vo.reset(); ovo.reset()
+        vo.processPointCloud(cloud); ovo.process_cloud(cloud)
+        slot = ovo.slot
+        for g, o, name in zip(vo.buckets(0), ovo.buckets(slot), ("x", "y", "depth", "count")):
+            if name == "count":
+                assert np.array_equal(g, o)
+            else:
+                assert np.array_equal(_bits(g), _bits(o)), f"frame {k}: bucket {name}"
+        xy = np.c_[rng.uniform(0, 1242, 400), rng.uniform(0, 375, 400)].astype(np.float32)
+        gd = vo.queryDepth(xy, slot=0)
+        od = np.array([ovo.query_depth(slot, x, y) for x, y in xy], np.float32)
+        assert np.array_equal(_bits(gd), _bits(od)), f"frame {k}: queryDepth"
+        assert (gd > 0).sum() > 50
+        if k == 0:
+            continue
+        prev_uv, curr_uv, (Rc, tc) = synth.make_matches(stream, k, n_matches=800)
+        gs = vo.solveNlsAll(prev_uv, curr_uv)
+        os_ = ovo.solve(prev_uv, curr_uv)
+        assert (gs["counter32"][0], gs["counter22"][0]) == (os_["counter32"], os_["counter22"])
+        assert gs["counter32"][0] > 100
+        np.testing.assert_allclose(gs["angles_0to1"][0], os_["angles_0to1"], atol=1e-6)
+        np.testing.assert_allclose(gs["t_0to1"][0], os_["t_0to1"], atol=1e-5)
+        # and the estimate is a sensible camera motion (about 1 m forward along z)
+        assert abs(np.linalg.norm(gs["t_0to1"][0]) - np.linalg.norm(tc)) < 0.3
+        # the LO prior as initial value (reset_VO_to_identity == false)
+        init = np.r_[0.0, 0.0, 0.0, tc]
+        g2 = vo.solveNlsAll(prev_uv, curr_uv, init=init[None])
+        o2 = ovo.solve(prev_uv, curr_uv, init_aa=init[:3], init_t=init[3:])
+        np.testing.assert_allclose(g2["t_0to1"][0], o2["t_0to1"], atol=1e-5)
+    vo.close()
+
+
+def test_vo_batched_and_edge_cases(synth, oracle):
+    import vloam_b200 as V
+    cam_T_velo, rect0_T_cam, P = synth.kitti_like_calibration()
+    streams = [synth.ScanStream(61 + i, n_cols=512) for i in range(2)]
+    vo = V.VisualOdometry(batch=2, max_points=64 * 512, max_matches=256)
+    vo.setUpPointCloud(cam_T_velo, rect0_T_cam, P)
+    with pytest.raises(V.VloamError):
+        vo.processPointCloud(np.zeros((2, 16, 3), np.float32))   # before reset()
+    ovos = [oracle.VisualOdometry(cam_T_velo, rect0_T_cam, P) for _ in streams]
+    for k in range(2):
+        vo.reset()
+        clouds = np.stack([s.scan(k) for s in streams])
+        vo.processPointCloud(clouds)
+        for b, o in enumerate(ovos):
+            o.reset(); o.process_cloud(clouds[b])
+            assert np.array_equal(vo.buckets(0, b)[3], o.buckets(o.slot)[3])
+    m = [synth.make_matches(s, 1, n_matches=200) for s in streams]
+    prev = np.stack([x[0][:200] for x in m]); curr = np.stack([x[1][:200] for x in m])
+    gs = vo.solveNlsAll(prev, curr)
+    for b, o in enumerate(ovos):
+        r = o.solve(prev[b], curr[b])
+        np.testing.assert_allclose(gs["t_0to1"][b], r["t_0to1"], atol=1e-5)
+    # no matches at all: the solve returns the initial value
+    g0 = vo.solveNlsAll(np.zeros((2, 0, 2), np.float32), np.zeros((2, 0, 2), np.float32))
+    assert np.all(g0["t_0to1"] == 0) and np.all(g0["counter32"] == 0)
+    vo.close()

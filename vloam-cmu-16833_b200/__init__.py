@@ -372,3 +372,89 @@ class LidarOdometryMapping:
             self.close()
         except Exception:
             pass
+
+
+class VisualOdometry:
+    """Mirror of the in-scope part of vloam::VisualOdometry (depth association + residuals + solve) for `batch` streams.
+
+    The OpenCV front-end (processImage: detect / describe / match) stays on the host and is out of scope; its output,
+    the matched keypoint pixels, is the input of solveNlsAll.
+    """
+
+    def __init__(self, ctx: Context | None = None, batch: int = 1, max_points: int = 131072, max_matches: int = 1024,
+                 remove_VO_outlier: int = 100, max_num_iterations: int = 100):
+        self.ctx = ctx or Context()
+        self._own_ctx = ctx is None
+        self.batch, self.max_matches = batch, max_matches
+        self.remove_VO_outlier, self.max_num_iterations = remove_VO_outlier, max_num_iterations
+        self._h = C.c_void_p()
+        self.ctx.check(lib().vloam_vo_create(self.ctx._h, batch, max_points, max_matches, C.byref(self._h)))
+
+    # -- visual_odometry.cpp:132-155
+    def setUpPointCloud(self, cam_T_velo, rect0_T_cam, P_rect0):
+        a = np.ascontiguousarray(cam_T_velo, np.float32).ravel()
+        b = np.ascontiguousarray(rect0_T_cam, np.float32).ravel()
+        c = np.ascontiguousarray(P_rect0, np.float32).ravel()
+        assert a.size == 16 and b.size == 16 and c.size == 12
+        self.ctx.check(lib().vloam_vo_set_calibration(self._h, a.ctypes.data_as(c_fp), b.ctypes.data_as(c_fp), c.ctypes.data_as(c_fp)))
+
+    # -- visual_odometry.cpp:86-90
+    def reset(self):
+        self.ctx.check(lib().vloam_vo_reset(self._h))
+
+    # -- visual_odometry.cpp:157-186
+    def processPointCloud(self, point_cloud, n_points=None):
+        a = np.ascontiguousarray(point_cloud, np.float32)
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape[0] == self.batch and a.shape[2] in (3, 4)
+        n = np.full(self.batch, a.shape[1], np.int32) if n_points is None else np.ascontiguousarray(n_points, np.int32)
+        self.ctx.check(lib().vloam_vo_process_cloud(self._h, _ptr(a), _ptr(n), a.shape[2], a.shape[1]))
+
+    def queryDepth(self, xy, slot: int = 0, stream: int = 0):
+        q = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        out = np.zeros(q.shape[0], np.float32)
+        self.ctx.check(lib().vloam_vo_query_depth(self._h, stream, slot, q.ctypes.data_as(c_fp), q.shape[0], out.ctypes.data_as(c_fp)))
+        return out
+
+    def buckets(self, slot: int = 0, stream: int = 0):
+        nb = 249 * 75
+        bx, by, bd = (np.zeros(nb, np.float32) for _ in range(3))
+        bc = np.zeros(nb, np.int32)
+        self.ctx.check(lib().vloam_vo_get_buckets(self._h, stream, slot, bx.ctypes.data_as(c_fp), by.ctypes.data_as(c_fp),
+                                                  bd.ctypes.data_as(c_fp), bc.ctypes.data_as(c_ip)))
+        return bx.reshape(249, 75), by.reshape(249, 75), bd.reshape(249, 75), bc.reshape(249, 75)
+
+    # -- visual_odometry.cpp:254-450
+    def solveNlsAll(self, prev_uv, curr_uv, n_matches=None, init=None):
+        """prev_uv / curr_uv: (batch, m, 2) or (m, 2) matched pixels; init: (batch, 6) angle-axis + t or None."""
+        p = np.ascontiguousarray(prev_uv, np.float32)
+        c = np.ascontiguousarray(curr_uv, np.float32)
+        if p.ndim == 2:
+            p, c = p[None], c[None]
+        m = p.shape[1]
+        assert p.shape == c.shape and p.shape[0] == self.batch and m <= self.max_matches
+        pp = np.zeros((self.batch, self.max_matches, 2), np.float32)
+        cc = np.zeros((self.batch, self.max_matches, 2), np.float32)
+        pp[:, :m] = p
+        cc[:, :m] = c
+        nm = np.full(self.batch, m, np.int32) if n_matches is None else np.ascontiguousarray(n_matches, np.int32)
+        ini = np.ascontiguousarray(init, np.float64).reshape(self.batch, 6) if init is not None else None
+        out = np.zeros((self.batch, 8))
+        self.ctx.check(lib().vloam_vo_solve(self._h, _ptr(pp), _ptr(cc), _ptr(nm), _ptr(ini), self.remove_VO_outlier,
+                                            self.max_num_iterations, out.ctypes.data_as(c_dp)))
+        return {"angles_0to1": out[:, 0:3].copy(), "t_0to1": out[:, 3:6].copy(), "counter32": out[:, 6].astype(int),
+                "counter22": out[:, 7].astype(int)}
+
+    def close(self):
+        if self._h:
+            lib().vloam_vo_destroy(self._h)
+            self._h = C.c_void_p()
+        if self._own_ctx:
+            self.ctx.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

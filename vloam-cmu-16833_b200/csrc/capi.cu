@@ -12,14 +12,7 @@
 
 using namespace vb;
 
-struct vloam_ctx {
-  int device = 0;
-  cudaStream_t own_stream = nullptr;
-  cudaStream_t stream = nullptr;
-  cudaStream_t copy_stream = nullptr;  // host->device uploads overlap the previous scan's kernels
-  std::string last_error;
-  Profiler prof;
-};
+
 
 namespace vb {
 const char* kernel_name(int id) {

@@ -139,7 +139,8 @@ struct LMShared {
   double H[21], g[6], cost;     // at x, unscaled
   double scale[6], diagonal[6];
   double radius, decrease_factor, model_cost_change, x_norm, gmax;
-  int reuse_diagonal, iteration, done, termination, invalid_run, eval_target;  // eval_target: 0 = x, 1 = cand
+  int reuse_diagonal, iteration, done, termination, invalid_run;
+  int euclid;  // 1: x = [angle-axis(3), t(3)] with plain addition (visual odometry); 0: x = [q(4), t(3)] on the quaternion manifold
   double red[28];
   double scratch[32 * 28];
 };
@@ -202,7 +203,8 @@ static __device__ void lm_prepare_step(LMShared& S, SolveTrace* tr, int max_iter
     S.model_cost_change = mcc;
     double delta[6];
     for (int i = 0; i < 6; ++i) delta[i] = -y[i] * S.scale[i];
-    manifold_plus(S.x, delta, S.cand);
+    if (S.euclid) { for (int i = 0; i < 6; ++i) S.cand[i] = S.x[i] + delta[i]; S.cand[6] = 0.0; }
+    else manifold_plus(S.x, delta, S.cand);
     return;
   }
 }
@@ -271,7 +273,8 @@ static __device__ void lm_begin(LMShared& S, SolveTrace* tr, const double x0[7])
 // callable that leaves (J'J, J'r, cost) at x in S.red[0..27] (e.g. via block_reduce28) and ends with a barrier.
 // On return S.x holds the solution (valid for all threads after the final barrier).
 template <typename Eval>
-__device__ void lm_solve_block(LMShared& S, SolveTrace* tr, int max_iterations, bool empty, Eval evaluate) {
+__device__ void lm_solve_block(LMShared& S, SolveTrace* tr, int max_iterations, bool empty, Eval evaluate, int euclid = 0) {
+  if (threadIdx.x == 0) S.euclid = euclid;
   double x0[7];
   for (int i = 0; i < 7; ++i) x0[i] = S.x[i];
   evaluate(x0);

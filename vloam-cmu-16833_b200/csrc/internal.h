@@ -87,3 +87,14 @@ cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info);
 cudaError_t lm_get_trace(LMDevice* lm, cudaStream_t st, int stream, int pass, double* records, int* info, double* para);
 
 }  // namespace vb
+
+#include <string>
+// The context behind the opaque vloam_ctx handle (shared by capi.cu and vo_kernels.cu).
+struct vloam_ctx {
+  int device = 0;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaStream_t copy_stream = nullptr;  // host->device uploads overlap the previous scan's kernels
+  std::string last_error;
+  vb::Profiler prof;
+};

@@ -261,19 +261,34 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   }
 }
 
-// Visit shell k of the column block around (qx, qy): k == 1 -> the whole 3 x 3 block, k > 1 -> its outer ring.
-// visit(t) is called for every sorted-array position t of every column in the shell.
+// The search runs in groups of 8 lanes (4 queries per warp): the per-query control flow (cell ordering, stopping
+// tests, window tables) costs about a thousand warp instructions, far more than the point visits themselves, so
+// sharing it between four queries is what matters.  All cross-lane operations use the group's lane mask.
+constexpr int kGroup = 8;
+__device__ __forceinline__ unsigned long long group_min_u64(unsigned gmask, unsigned long long v) {
+#pragma unroll
+  for (int o = kGroup / 2; o > 0; o >>= 1) {
+    const unsigned long long t = __shfl_xor_sync(gmask, v, o);
+    v = t < v ? t : v;
+  }
+  return v;
+}
+struct GridView {  // the GridHeader fields the search needs, in registers
+  float minx, miny, c, inv_c;
+  int nx, ny;
+};
+// Visit shell k >= 2 (the outer ring of the (2k+1)^2 column block): rows qy-k and qy+k in full, the two end columns
+// of the rows in between.  visit(t) is called for every sorted-array position t of every column in the shell.
 template <typename F>
-__device__ __forceinline__ void grid_visit_shell(const GridHeader& G, const int* __restrict__ cs, int qx, int qy, int k, F visit) {
-  const int l = lane_id();
-  const int nseg = k == 1 ? 3 : 4 * k;
-  for (int s0 = 0; s0 < nseg; s0 += 32) {
+__device__ __forceinline__ void group_visit_shell(const GridView& G, const int* __restrict__ cs, int qx, int qy, int k, unsigned gmask,
+                                                  int gl, F visit) {
+  const int nseg = 4 * k;
+  for (int s0 = 0; s0 < nseg; s0 += kGroup) {
     int a = 0, bnd = 0;
-    const int sgi = s0 + l;
+    const int sgi = s0 + gl;
     if (sgi < nseg) {
       int iy, x0, x1;
-      if (k == 1) { iy = qy - 1 + sgi; x0 = qx - 1; x1 = qx + 1; }
-      else if (sgi == 0) { iy = qy - k; x0 = qx - k; x1 = qx + k; }
+      if (sgi == 0) { iy = qy - k; x0 = qx - k; x1 = qx + k; }
       else if (sgi == 1) { iy = qy + k; x0 = qx - k; x1 = qx + k; }
       else { const int m = sgi - 2; iy = qy - k + 1 + (m >> 1); x0 = x1 = (m & 1) ? qx + k : qx - k; }
       if (iy >= 0 && iy < G.ny) {
@@ -281,27 +296,29 @@ __device__ __forceinline__ void grid_visit_shell(const GridHeader& G, const int*
         if (x0 <= x1) { a = cs[iy * G.nx + x0]; bnd = cs[iy * G.nx + x1 + 1]; }
       }
     }
-    const int cnt = min(32, nseg - s0);
+    const int cnt = min(kGroup, nseg - s0);
     for (int sidx = 0; sidx < cnt; ++sidx) {
-      const int aa = __shfl_sync(0xffffffffu, a, sidx), bb = __shfl_sync(0xffffffffu, bnd, sidx);
-      for (int t = aa + l; t < bb; t += 32) visit(t);
+      const int aa = __shfl_sync(gmask, a, sidx, kGroup), bb = __shfl_sync(gmask, bnd, sidx, kGroup);
+      for (int t = aa + gl; t < bb; t += kGroup) visit(t);
     }
   }
 }
-
-// Best-first visit of the 3 x 3 column block around the query: columns are taken in order of their lower bound on
-// the distance to any point inside them (distance from the query to the column's rectangle, shrunk by the rounding
-// margin), and the walk stops as soon as that bound exceeds `limit()` — the largest distance that could still improve
-// a result.  Replaces shell k = 1 of grid_visit_shell; later shells (k >= 2) are only needed when the block's safe
-// radius is not enough.  `visit(t)` as in grid_visit_shell; `limit()` must be warp-uniform.
+// Best-first visit of the 3 x 3 column block around the query: the query's own column first, then the 8 neighbours
+// (one per lane) in order of their lower bound on the distance to any point inside them (distance from the query to
+// the column's rectangle, shrunk by the rounding margin); the walk stops as soon as that bound exceeds `limit()` —
+// the largest squared distance that could still improve a result.  `limit()` must be uniform across the group.
 template <typename F, typename L>
-__device__ __forceinline__ void grid_visit_block_best_first(const GridHeader& G, const int* __restrict__ cs, float sx, float sy,
-                                                            int qx, int qy, F visit, L limit) {
-  const int l = lane_id();
+__device__ __forceinline__ void group_visit_block_best_first(const GridView& G, const int* __restrict__ cs, float sx, float sy, int qx, int qy,
+                                                             unsigned gmask, int gshift, int gl, F visit, L limit) {
+  if (qx >= 0 && qx < G.nx && qy >= 0 && qy < G.ny) {
+    const int a0 = cs[qy * G.nx + qx], b0 = cs[qy * G.nx + qx + 1];
+    for (int t = a0 + gl; t < b0; t += kGroup) visit(t);
+  }
   int a = 0, bnd = 0;
   unsigned lbBits = 0xffffffffu;
-  if (l < 9) {
-    const int cx = qx + (l % 3) - 1, cy = qy + (l / 3) - 1;
+  {
+    const int n = gl < 4 ? gl : gl + 1;  // neighbour cells 0..8 without the centre (4)
+    const int cx = qx + (n % 3) - 1, cy = qy + (n / 3) - 1;
     if (cx >= 0 && cx < G.nx && cy >= 0 && cy < G.ny) {
       a = cs[cy * G.nx + cx]; bnd = cs[cy * G.nx + cx + 1];
       if (bnd > a) {
@@ -313,24 +330,23 @@ __device__ __forceinline__ void grid_visit_block_best_first(const GridHeader& G,
     }
   }
   while (true) {
-    const unsigned m = __reduce_min_sync(0xffffffffu, lbBits);
+    const unsigned m = __reduce_min_sync(gmask, lbBits);
     if (m == 0xffffffffu || __uint_as_float(m) > limit()) break;
-    const int src = __ffs(__ballot_sync(0xffffffffu, lbBits == m)) - 1;
-    const int aa = __shfl_sync(0xffffffffu, a, src), bb = __shfl_sync(0xffffffffu, bnd, src);
-    if (l == src) lbBits = 0xffffffffu;
-    for (int t = aa + l; t < bb; t += 32) visit(t);
+    const int src = __ffs(__ballot_sync(gmask, lbBits == m) >> gshift) - 1;
+    const int aa = __shfl_sync(gmask, a, src, kGroup), bb = __shfl_sync(gmask, bnd, src, kGroup);
+    if (gl == src) lbBits = 0xffffffffu;
+    for (int t = aa + gl; t < bb; t += kGroup) visit(t);
   }
 }
-
-// Squared radius within which the visited block [qx-k, qx+k] x [qy-k, qy+k] is guaranteed complete (0 if none).
-__device__ __forceinline__ float grid_safe_radius(const GridHeader& G, float sx, float sy, int qx, int qy, int k) {
+// Radius within which the visited block [qx-k, qx+k] x [qy-k, qy+k] is guaranteed complete (<= 0 if none).
+__device__ __forceinline__ float grid_safe_radius(const GridView& G, float sx, float sy, int qx, int qy, int k) {
   const float xl = sx - (G.minx + (float)(qx - k) * G.c), xr = (G.minx + (float)(qx + k + 1) * G.c) - sx;
   const float yl = sy - (G.miny + (float)(qy - k) * G.c), yr = (G.miny + (float)(qy + k + 1) * G.c) - sy;
-  const float R = fminf(fminf(xl, xr), fminf(yl, yr)) * (1.0f - 1e-5f) - 1e-4f;
-  return R;
+  return fminf(fminf(xl, xr), fminf(yl, yr)) * (1.0f - 1e-5f) - 1e-4f;
 }
 
-// lo_associate: one warp per query, grid search.  Same contract as lo_associate_brute.
+// lo_associate: one 8-lane group per query, grid search.  grid (ceil((kMaxSharp + kMaxFlat) / 32), B), block 256.
+// Same contract as lo_associate_brute.
 __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
                                                      const LOState* __restrict__ lo, const float4* __restrict__ sharp,
                                                      const float4* __restrict__ flat, const float4* __restrict__ cornerLast,
@@ -340,8 +356,9 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
                                                      const float4* __restrict__ sortedS, const int* __restrict__ sidxS,
                                                      int4* __restrict__ corr) {
   const int b = blockIdx.y;
-  const int slot = blockIdx.x * 8 + (threadIdx.x >> 5);
-  const int l = lane_id();
+  const int lane = lane_id(), g = lane / kGroup, gl = lane % kGroup, gshift = g * kGroup;
+  const unsigned gmask = 0xffu << gshift;
+  const int slot = blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + g;
   if (slot >= kMaxSharp + kMaxFlat) return;
   const SRHeader& hc = hdrCur[b];
   const bool isCorner = slot < kMaxSharp;
@@ -349,10 +366,13 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
   const int qi = isCorner ? slot : slot - kMaxSharp;
   const int nq = isCorner ? hc.nSharp : hc.nFlat;
   int4 out = make_int4(-1, -1, -1, 0);
-  const GridHeader& G = ghdr[b * 2 + which];
-  const int nT = G.n;
+  const GridHeader& GH = ghdr[b * 2 + which];
+  const int nT = GH.n;
   if (qi < nq && nT > 0) {
+    GridView G;
+    G.minx = GH.minx; G.miny = GH.miny; G.c = GH.c; G.inv_c = GH.inv_c; G.nx = GH.nx; G.ny = GH.ny;
     const float4 p = isCorner ? sharp[(size_t)b * kMaxSharp + qi] : flat[(size_t)b * kMaxFlat + qi];
+    // TransformToStart, DISTORTION == false: un = q_last_curr * p + t_last_curr, rounded to float (:158-165)
     double un[3];
     quat_rotate(lo[b].para_q, (double)p.x, (double)p.y, (double)p.z, un);
     const float sx = (float)(un[0] + lo[b].para_t[0]);
@@ -371,13 +391,13 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
       const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)SI[t];
       best = key < best ? key : best;
     };
-    // a point at exactly the same distance could still win the index tie-break, hence `>` in the walk (limit = best)
-    grid_visit_block_best_first(G, cs, sx, sy, qx, qy, visit1, [&]() {
-      return __uint_as_float(__reduce_min_sync(0xffffffffu, (unsigned)(best >> 32)));  // +inf bits (0xffffffff -> NaN) handled below
-    });
-    best = warp_min_u64(best);
+    // a point at exactly the same distance could still win the index tie-break: the walk only stops on `>`.
+    // (no candidate yet: the reduced bits are 0xffffffff = NaN, every comparison is false, the walk continues)
+    group_visit_block_best_first(G, cs, sx, sy, qx, qy, gmask, gshift, gl, visit1,
+                                 [&]() { return __uint_as_float(__reduce_min_sync(gmask, (unsigned)(best >> 32))); });
+    best = group_min_u64(gmask, best);
     for (int k = 1;; ++k) {
-      if (k > 1) { grid_visit_shell(G, cs, qx, qy, k, visit1); best = warp_min_u64(best); }
+      if (k > 1) { group_visit_shell(G, cs, qx, qy, k, gmask, gl, visit1); best = group_min_u64(gmask, best); }
       const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
       if (R >= 5.0f) break;
       if (best != 0xffffffffffffffffull && R > 0.f && __uint_as_float((unsigned)(best >> 32)) <= R * R) break;
@@ -386,8 +406,33 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
       const int closest = (int)(unsigned)best;
       const int id = (int)T[closest].w;  // closestPointScanID (:275)
       unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
-      if (!G.ringsOk) {
-        window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
+      if (!GH.ringsOk) {
+        // literal walk by the whole group's warp is not possible inside a group: do it lane-serially per group
+        // (never taken for ring-major clouds produced by scan registration; kept for exactness on foreign clouds)
+        if (gl == 0) {
+          double m2 = 25.0, m3 = 25.0;
+          int i2 = -1, i3 = -1;
+          for (int j = closest + 1; j < nT; ++j) {
+            const float4 t = T[j];
+            const int rid = (int)t.w;
+            if ((double)rid > (double)id + 2.5) break;
+            const double d = (double)sqdist_f(t.x, t.y, t.z, sx, sy, sz);
+            if (isCorner) { if (rid > id && d < m2) { m2 = d; i2 = j; } }
+            else if (rid <= id && d < m2) { m2 = d; i2 = j; }
+            else if (rid > id && d < m3) { m3 = d; i3 = j; }
+          }
+          for (int j = closest - 1; j >= 0; --j) {
+            const float4 t = T[j];
+            const int rid = (int)t.w;
+            if ((double)rid < (double)id - 2.5) break;
+            const double d = (double)sqdist_f(t.x, t.y, t.z, sx, sy, sz);
+            if (isCorner) { if (rid < id && d < m2) { m2 = d; i2 = j; } }
+            else if (rid >= id && d < m2) { m2 = d; i2 = j; }
+            else if (rid < id && d < m3) { m3 = d; i3 = j; }
+          }
+          if (isCorner) { if (i2 >= 0) out = make_int4(closest, i2, -1, 1); }
+          else if (i2 >= 0 && i3 >= 0) out = make_int4(closest, i2, i3, 1);
+        }
       } else {
         // ---- phase 2: nearest point per class inside the +-2.5-ring window (:279-324 / :368-417).
         // Forward walk stops at the first j > closest with int(intensity) >= id + 3: that is the first such point of
@@ -395,8 +440,8 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
         // last j < closest with int(intensity) <= id - 3: the last such point of true ring id - 2, else the point just
         // before that ring.  So the walks visit exactly the indices [lo_j, hi_j) \ {closest}.
         int hi_j = nT, lo_j = 0;
-        if (id + 3 <= kMaxRings - 1) hi_j = min(G.firstFull[id + 3], G.ringStart[min(id + 4, kMaxRings)]);
-        if (id - 2 >= 0) lo_j = max(G.lastLow[id - 2], G.ringStart[id - 2] - 1) + 1;
+        if (id + 3 <= kMaxRings - 1) hi_j = min(GH.firstFull[id + 3], GH.ringStart[min(id + 4, kMaxRings)]);
+        if (id - 2 >= 0) lo_j = max(GH.lastLow[id - 2], GH.ringStart[id - 2] - 1) + 1;
         auto visit2 = [&](int t) {
           const int j = SI[t];
           if (j < lo_j || j >= hi_j || j == closest) return;
@@ -413,19 +458,19 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
           else k3 = key < k3 ? key : k3;
         };
         // a column can still matter while its bound is below the worst of the needed classes (25 = none found yet)
-        grid_visit_block_best_first(G, cs, sx, sy, qx, qy, visit2, [&]() {
-          const unsigned d2 = __reduce_min_sync(0xffffffffu, (unsigned)(k2 >> 32));
+        group_visit_block_best_first(G, cs, sx, sy, qx, qy, gmask, gshift, gl, visit2, [&]() {
+          const unsigned d2 = __reduce_min_sync(gmask, (unsigned)(k2 >> 32));
           float lim = d2 == 0xffffffffu ? 25.0f : __uint_as_float(d2);
           if (!isCorner) {
-            const unsigned d3 = __reduce_min_sync(0xffffffffu, (unsigned)(k3 >> 32));
+            const unsigned d3 = __reduce_min_sync(gmask, (unsigned)(k3 >> 32));
             lim = fmaxf(lim, d3 == 0xffffffffu ? 25.0f : __uint_as_float(d3));
           }
           return lim;
         });
-        k2 = warp_min_u64(k2);
-        k3 = warp_min_u64(k3);
+        k2 = group_min_u64(gmask, k2);
+        k3 = group_min_u64(gmask, k3);
         for (int k = 1;; ++k) {
-          if (k > 1) { grid_visit_shell(G, cs, qx, qy, k, visit2); k2 = warp_min_u64(k2); k3 = warp_min_u64(k3); }
+          if (k > 1) { group_visit_shell(G, cs, qx, qy, k, gmask, gl, visit2); k2 = group_min_u64(gmask, k2); k3 = group_min_u64(gmask, k3); }
           const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
           if (R >= 5.0f) break;
           if (R > 0.f) {
@@ -435,15 +480,15 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
             if (ok2 && ok3) break;
           }
         }
-      }
-      if (isCorner) {
-        if (k2 != 0xffffffffffffffffull) out = make_int4(closest, decode_order(k2, nT), -1, 1);
-      } else if (k2 != 0xffffffffffffffffull && k3 != 0xffffffffffffffffull) {
-        out = make_int4(closest, decode_order(k2, nT), decode_order(k3, nT), 1);
+        if (isCorner) {
+          if (k2 != 0xffffffffffffffffull) out = make_int4(closest, decode_order(k2, nT), -1, 1);
+        } else if (k2 != 0xffffffffffffffffull && k3 != 0xffffffffffffffffull) {
+          out = make_int4(closest, decode_order(k2, nT), decode_order(k3, nT), 1);
+        }
       }
     }
   }
-  if (l == 0) corr[(size_t)b * (kMaxSharp + kMaxFlat) + slot] = out;
+  if (gl == 0) corr[(size_t)b * (kMaxSharp + kMaxFlat) + slot] = out;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -598,7 +643,7 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
     VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
                                                   hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
   else
-    VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
+    VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 31) / 32, B), 256, 0, st>>>(
                                             hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
                                             g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1], corr));
   VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,

@@ -1,13 +1,507 @@
-// placeholder, replaced below
+// vloam_b200 — visual odometry depth association + residuals on sm_100a.
+//
+//   vo_project        VisualOdometry::processPointCloud (visual_odometry.cpp:157-172) + PointCloudUtil::projectPointCloud
+//                     (point_cloud_util.cpp:148-174): X~ * cam_T_velo' * rect0_T_cam' * P_rect0' in float with Eigen's
+//                     sequential-k accumulation, depth > 0.1 filter, pixel -> 5 px bucket id
+//   vo_bucket_sort/fold  PointCloudUtil::downsamplePointCloud (:205-260): the reference's running "mean" divides by the
+//                     count *before* the hit and is order dependent, so the points are stably sorted by
+//                     bucket and every bucket is folded sequentially in input order
+//   vo_query          PointCloudUtil::queryDepth (:302-407): 5 x 5 bucket window, >= 10 occupied, 3 nearest, inverse-
+//                     distance weights
+//   vo_build_residuals VisualOdometry::solveNlsAll (visual_odometry.cpp:283-416): integer-truncated pixels (Q7), flow gate,
+//                     depth lookup, back-projection through P_rect0 (float column-pivoted Householder 3x3)
+//   vo_solve          CostFunctor32 / CostFunctor22 (ceres_cost_function.h:54-96, 147-185) with analytic Jacobians of
+//                     ceres::AngleAxisRotatePoint + ceres::Solve (<= 100 iterations, Huber 0.1, no manifold) in one launch
+#include <cstring>
+#include <new>
+#include <vector>
+
 #include "../../include/vloam_b200.h"
-extern "C" {
-int vloam_vo_create(vloam_ctx*, int, int, int, vloam_vo**) { return VLOAM_E_STATE; }
-int vloam_vo_destroy(vloam_vo*) { return VLOAM_E_STATE; }
-int vloam_vo_set_calibration(vloam_vo*, const float*, const float*, const float*) { return VLOAM_E_STATE; }
-int vloam_vo_reset(vloam_vo*) { return VLOAM_E_STATE; }
-int vloam_vo_process_cloud(vloam_vo*, const float*, const int*, int, size_t) { return VLOAM_E_STATE; }
-int vloam_vo_process_cloud_device(vloam_vo*, const float*, const int*, int, size_t) { return VLOAM_E_STATE; }
-int vloam_vo_query_depth(vloam_vo*, int, int, const float*, int, float*) { return VLOAM_E_STATE; }
-int vloam_vo_get_buckets(vloam_vo*, int, int, float*, float*, float*, int*) { return VLOAM_E_STATE; }
-int vloam_vo_solve(vloam_vo*, const float*, const float*, const int*, const double*, int, int, double*) { return VLOAM_E_STATE; }
+#include "common.cuh"
+#include "cta_sort.cuh"
+#include "gn_solver.cuh"
+#include "internal.h"
+
+namespace vb {
+
+constexpr int kImgW = 1242, kImgH = 375, kBucket = 5;      // point_cloud_util.h:26,41-42
+constexpr int kBW = 249, kBH = 75, kBuckets = kBW * kBH;   // ceil(1242 / 5), ceil(375 / 5)
+
+struct VOCalib { float cam_T_velo[16], rect0_T_cam[16], P_rect0[12]; };
+
+struct VOResidual {
+  double obs[5];
+  int type;  // 0 none, 1 CostFunctor32 (X0(3), x1_bar, y1_bar), 2 CostFunctor22 (x0_bar, y0_bar, x1_bar, y1_bar)
+  int pad;
+};
+struct VOState {
+  double x[6];  // angles_0to1, t_0to1
+  int counter32, counter22;
+  SolveTrace trace;
+};
+
+// grid (ceil(cap / 256), B), block 256
+__global__ void __launch_bounds__(256) vo_project(const float* __restrict__ xyz, int stride, size_t slab_floats, const int* __restrict__ n_points,
+                                                   VOCalib C, int cap, float4* __restrict__ uvd, unsigned* __restrict__ key, unsigned* __restrict__ val) {
+  const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
+  const int n = n_points[b];
+  if (i >= n) return;
+  const float* p = xyz + (size_t)b * slab_floats + (size_t)i * stride;
+  const float X[4] = {p[0], p[1], p[2], 1.0f};
+  float a[4], bb[4], c[3];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s = __fadd_rn(s, __fmul_rn(X[k], C.cam_T_velo[j * 4 + k])); a[j] = s; }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s = __fadd_rn(s, __fmul_rn(a[k], C.rect0_T_cam[j * 4 + k])); bb[j] = s; }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { float s = 0.f; for (int k = 0; k < 4; ++k) s = __fadd_rn(s, __fmul_rn(bb[k], C.P_rect0[j * 4 + k])); c[j] = s; }
+  unsigned k16 = 0xffffu;
+  float u = 0.f, v = 0.f;
+  if (c[2] > 0.1f) {
+    const float inv = __fdiv_rn(1.0f, c[2]);
+    u = __fmul_rn(c[0], inv); v = __fmul_rn(c[1], inv);
+    const int ix = (int)__fdiv_rn(u, (float)kBucket), iy = (int)__fdiv_rn(v, (float)kBucket);
+    if (ix >= 0 && ix < kBW && iy >= 0 && iy < kBH) k16 = (unsigned)(ix * kBH + iy);
+  }
+  uvd[(size_t)b * cap + i] = make_float4(u, v, c[2], 0.f);
+  key[(size_t)b * cap + i] = k16;
+  val[(size_t)b * cap + i] = (unsigned)i;
 }
+// grid (B), block 1024: stable sort of the point indices by bucket id (result left in kA / vA)
+__global__ void __launch_bounds__(1024) vo_bucket_sort(const int* __restrict__ n_points, int cap, unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB) {
+  __shared__ SortSmem S;
+  const int b = blockIdx.x;
+  cta_radix_sort(kA + (size_t)b * cap, vA + (size_t)b * cap, kB + (size_t)b * cap, vB + (size_t)b * cap, n_points[b], 16, S);
+}
+// grid (ceil(kBuckets / 256), B), block 256: one thread folds one bucket in input order
+__global__ void __launch_bounds__(256) vo_bucket_fold(const int* __restrict__ n_points, int cap, const unsigned* __restrict__ key,
+                                                       const unsigned* __restrict__ val, const float4* __restrict__ uvd, float* __restrict__ bx,
+                                                       float* __restrict__ by, float* __restrict__ bd, int* __restrict__ bc) {
+  const int b = blockIdx.y, bucket = blockIdx.x * 256 + threadIdx.x;
+  if (bucket >= kBuckets) return;
+  const int n = n_points[b];
+  const unsigned* k = key + (size_t)b * cap;
+  const unsigned* v = val + (size_t)b * cap;
+  int lo = 0, hi = n;  // first position with key >= bucket
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (k[mid] < (unsigned)bucket) lo = mid + 1; else hi = mid; }
+  float x = 0.f, y = 0.f, d = 0.f;
+  int cnt = 0;
+  for (int t = lo; t < n && k[t] == (unsigned)bucket; ++t) {
+    const float4 p = uvd[(size_t)b * cap + v[t]];
+    if (cnt == 0) { x = p.x; y = p.y; d = p.z; }
+    else {  // :229-236: bucket += (value - bucket) / count, count = hits before this one
+      const float fc = (float)cnt;
+      x = __fadd_rn(x, __fdiv_rn(__fsub_rn(p.x, x), fc));
+      y = __fadd_rn(y, __fdiv_rn(__fsub_rn(p.y, y), fc));
+      d = __fadd_rn(d, __fdiv_rn(__fsub_rn(p.z, d), fc));
+    }
+    ++cnt;
+  }
+  const size_t o = (size_t)b * kBuckets + bucket;
+  bx[o] = x; by[o] = y; bd[o] = d; bc[o] = cnt;
+}
+
+// PointCloudUtil::queryDepth, searching_radius = 2
+__device__ float query_depth(const float* __restrict__ bx, const float* __restrict__ by, const float* __restrict__ bd,
+                             const int* __restrict__ bc, float x, float y) {
+  const int index_x = (int)__fdiv_rn(x, (float)kBucket), index_y = (int)__fdiv_rn(y, (float)kBucket);
+  float nd[25], nz[25];
+  int cnt = 0;
+  for (int ix = index_x - 2; ix <= index_x + 2; ++ix)
+    for (int iy = index_y - 2; iy <= index_y + 2; ++iy)
+      if (ix >= 0 && ix < kBW && iy >= 0 && iy < kBH && bc[ix * kBH + iy] > 0) {
+        const int o = ix * kBH + iy;
+        const double dx = (double)__fsub_rn(x, bx[o]), dy = (double)__fsub_rn(y, by[o]);
+        nd[cnt] = (float)sqrt(dx * dx + dy * dy);  // std::pow(., 2) in double, sqrt in double, stored as float (:332)
+        nz[cnt] = bd[o];
+        ++cnt;
+      }
+  if (cnt < 10) return -1.0f;
+  // the three nearest, ties in insertion order (stable)
+  int i0 = -1, i1 = -1, i2 = -1;
+  for (int r = 0; r < 3; ++r) {
+    int best = -1;
+    for (int i = 0; i < cnt; ++i) {
+      if (i == i0 || i == i1) continue;
+      if (best < 0 || nd[i] < nd[best]) best = i;
+    }
+    if (r == 0) i0 = best; else if (r == 1) i1 = best; else i2 = best;
+  }
+  const float d0 = nd[i0], d1 = nd[i1], d2 = nd[i2], z0 = nz[i0], z1 = nz[i1], z2 = nz[i2];
+  // :382-385, left-to-right float arithmetic
+  const float num = __fadd_rn(__fadd_rn(__fmul_rn(__fmul_rn(z0, d1), d2), __fmul_rn(__fmul_rn(z1, d0), d2)), __fmul_rn(__fmul_rn(z2, d0), d1));
+  const float den = __fadd_rn(__fadd_rn(__fadd_rn(0.0001f, __fmul_rn(d1, d2)), __fmul_rn(d0, d2)), __fmul_rn(d0, d1));
+  return __fdiv_rn(num, den);
+}
+__global__ void vo_query(const float* __restrict__ bx, const float* __restrict__ by, const float* __restrict__ bd, const int* __restrict__ bc,
+                         const float* __restrict__ xy, int n, float* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = query_depth(bx, by, bd, bc, xy[2 * i], xy[2 * i + 1]);
+}
+
+// Eigen MatrixXf(3x3).colPivHouseholderQr().solve(b) in float (same algorithm as oracle::colpiv_qr_solve3x3f)
+__device__ void colpiv_qr_solve3x3f_dev(const float Ain[9], const float bin[3], float x[3]) {
+  float A[3][3], b[3];
+  for (int i = 0; i < 3; ++i) { b[i] = bin[i]; for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c]; }
+  int perm[3] = {0, 1, 2};
+  int rank = 0;
+  for (int k = 0; k < 3; ++k) {
+    int best = k; float bestn = -1.f;
+    for (int c = k; c < 3; ++c) { float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(A[i][c], A[i][c])); if (s > bestn) { bestn = s; best = c; } }
+    if (!(bestn > 0.f)) break;
+    if (best != k) { for (int i = 0; i < 3; ++i) { const float t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; } const int t = perm[k]; perm[k] = perm[best]; perm[best] = t; }
+    const float nrm = __fsqrt_rn(bestn);
+    const float alpha = A[k][k] > 0 ? -nrm : nrm;
+    float v[3] = {0, 0, 0};
+    for (int i = k; i < 3; ++i) v[i] = A[i][k];
+    v[k] = __fsub_rn(v[k], alpha);
+    float vn = 0; for (int i = k; i < 3; ++i) vn = __fadd_rn(vn, __fmul_rn(v[i], v[i]));
+    if (vn > 0) {
+      for (int c = k; c < 3; ++c) {
+        float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(v[i], A[i][c]));
+        s = __fdiv_rn(__fmul_rn(2.0f, s), vn);
+        for (int i = k; i < 3; ++i) A[i][c] = __fsub_rn(A[i][c], __fmul_rn(s, v[i]));
+      }
+      float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(v[i], b[i]));
+      s = __fdiv_rn(__fmul_rn(2.0f, s), vn);
+      for (int i = k; i < 3; ++i) b[i] = __fsub_rn(b[i], __fmul_rn(s, v[i]));
+    }
+    ++rank;
+  }
+  float y[3] = {0, 0, 0};
+  for (int k = rank - 1; k >= 0; --k) {
+    float s = b[k];
+    for (int c = k + 1; c < rank; ++c) s = __fsub_rn(s, __fmul_rn(A[k][c], y[c]));
+    y[k] = __fdiv_rn(s, A[k][k]);
+  }
+  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+}
+
+// grid (ceil(maxM / 128), B), block 128: one thread per match
+__global__ void __launch_bounds__(128) vo_build_residuals(const float* __restrict__ prev_uv, const float* __restrict__ curr_uv,
+                                                           const int* __restrict__ n_matches, int maxM, VOCalib C, int remove_outlier,
+                                                           const float* __restrict__ pbx, const float* __restrict__ pby, const float* __restrict__ pbd,
+                                                           const int* __restrict__ pbc, VOResidual* __restrict__ res) {
+  const int b = blockIdx.y, j = blockIdx.x * 128 + threadIdx.x;
+  if (j >= maxM) return;
+  VOResidual R;
+  R.type = 0; R.pad = 0;
+  for (int i = 0; i < 5; ++i) R.obs[i] = 0.0;
+  if (j < n_matches[b]) {
+    const float* pu = prev_uv + ((size_t)b * maxM + j) * 2;
+    const float* cu = curr_uv + ((size_t)b * maxM + j) * 2;
+    const int px = (int)pu[0], py = (int)pu[1], cx = (int)cu[0], cy = (int)cu[1];  // Q7: truncation (:291-294)
+    bool keep = true;
+    if (remove_outlier > 0) {  // :309-314
+      const double dx = (double)(px - cx), dy = (double)(py - cy);
+      if (dx * dx + dy * dy > (double)(remove_outlier * remove_outlier)) keep = false;
+    }
+    if (keep) {
+      const size_t o = (size_t)b * kBuckets;
+      const float depth0 = query_depth(pbx + o, pby + o, pbd + o, pbc + o, (float)px, (float)py);  // :316
+      const float K[9] = {C.P_rect0[0], C.P_rect0[1], C.P_rect0[2], C.P_rect0[4], C.P_rect0[5], C.P_rect0[6], C.P_rect0[8], C.P_rect0[9], C.P_rect0[10]};
+      float p0[3], p1[3] = {(float)cx, (float)cy, 1.0f}, X0[3], X1[3];
+      if (depth0 > 0) {  // :345-367
+        p0[0] = __fmul_rn((float)px, depth0); p0[1] = __fmul_rn((float)py, depth0); p0[2] = depth0;
+        colpiv_qr_solve3x3f_dev(K, p0, X0);
+        colpiv_qr_solve3x3f_dev(K, p1, X1);
+        R.type = 1;
+        R.obs[0] = (double)X0[0]; R.obs[1] = (double)X0[1]; R.obs[2] = (double)X0[2];
+        R.obs[3] = (double)X1[0] / (double)X1[2]; R.obs[4] = (double)X1[1] / (double)X1[2];
+      } else {  // :394-414
+        p0[0] = (float)px; p0[1] = (float)py; p0[2] = 1.0f;
+        colpiv_qr_solve3x3f_dev(K, p0, X0);
+        colpiv_qr_solve3x3f_dev(K, p1, X1);
+        R.type = 2;
+        R.obs[0] = (double)X0[0] / (double)X0[2]; R.obs[1] = (double)X0[1] / (double)X0[2];
+        R.obs[2] = (double)X1[0] / (double)X1[2]; R.obs[3] = (double)X1[1] / (double)X1[2];
+      }
+    }
+  }
+  res[(size_t)b * maxM + j] = R;
+}
+
+// y = R(w) p and M = dy/dw exactly as differentiating ceres::AngleAxisRotatePoint (Rodrigues branch for
+// theta^2 > eps: dy/dw = -R [p]x J_r(w); first-order branch otherwise: y = p + w x p, dy/dw = -[p]x).
+__device__ void angle_axis_rotate_jac(const double w[3], const double p[3], double y[3], double M[3][3]) {
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
+  const double P[3][3] = {{0, -p[2], p[1]}, {p[2], 0, -p[0]}, {-p[1], p[0], 0}};
+  if (th2 > 2.220446049250313e-16) {
+    const double th = sqrt(th2), c = cos(th), s = sin(th), ti = 1.0 / th;
+    const double k[3] = {w[0] * ti, w[1] * ti, w[2] * ti};
+    const double kxp[3] = {k[1] * p[2] - k[2] * p[1], k[2] * p[0] - k[0] * p[2], k[0] * p[1] - k[1] * p[0]};
+    const double tmp = (k[0] * p[0] + k[1] * p[1] + k[2] * p[2]) * (1.0 - c);
+    for (int i = 0; i < 3; ++i) y[i] = p[i] * c + kxp[i] * s + k[i] * tmp;
+    // R = c I + s [k]x + (1 - c) k k'
+    const double Kx[3][3] = {{0, -k[2], k[1]}, {k[2], 0, -k[0]}, {-k[1], k[0], 0}};
+    double R[3][3], Jr[3][3];
+    const double hs = sin(0.5 * th);
+    const double A = 2.0 * hs * hs / th2;                                   // (1 - cos) / theta^2, cancellation-free
+    const double Bc = th < 1e-2 ? (1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0) : (th - s) / (th2 * th);  // (theta - sin) / theta^3
+    const double Wx[3][3] = {{0, -w[2], w[1]}, {w[2], 0, -w[0]}, {-w[1], w[0], 0}};
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        R[i][j] = (i == j ? c : 0.0) + s * Kx[i][j] + (1.0 - c) * k[i] * k[j];
+        double w2 = 0.0;
+        for (int q = 0; q < 3; ++q) w2 += Wx[i][q] * Wx[q][j];
+        Jr[i][j] = (i == j ? 1.0 : 0.0) - A * Wx[i][j] + Bc * w2;
+      }
+    double RP[3][3];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double t = 0; for (int q = 0; q < 3; ++q) t += R[i][q] * P[q][j]; RP[i][j] = t; }
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { double t = 0; for (int q = 0; q < 3; ++q) t += RP[i][q] * Jr[q][j]; M[i][j] = -t; }
+  } else {
+    y[0] = p[0] + (w[1] * p[2] - w[2] * p[1]); y[1] = p[1] + (w[2] * p[0] - w[0] * p[2]); y[2] = p[2] + (w[0] * p[1] - w[1] * p[0]);
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) M[i][j] = -P[i][j];
+  }
+}
+
+// grid (B), block 256: VisualOdometry::solveNlsAll's ceres::Solve (visual_odometry.cpp:423)
+__global__ void __launch_bounds__(256) vo_solve(VOState* __restrict__ stAll, const VOResidual* __restrict__ res, int maxM, const int* __restrict__ n_matches,
+                                                 const double* __restrict__ init, int max_iterations) {
+  __shared__ LMShared S;
+  __shared__ int s_cnt[2];
+  const int b = blockIdx.x;
+  VOState& st = stAll[b];
+  const VOResidual* rr = res + (size_t)b * maxM;
+  const int n = min(n_matches[b], maxM);
+  if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 6; ++i) S.x[i] = init ? init[b * 6 + i] : 0.0;  // :261-281
+    S.x[6] = 0.0;
+  }
+  __syncthreads();
+  {
+    int a = 0, c = 0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) { a += rr[i].type == 1; c += rr[i].type == 2; }
+    a = __reduce_add_sync(0xffffffffu, a); c = __reduce_add_sync(0xffffffffu, c);
+    if (lane_id() == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], c); }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.counter32 = s_cnt[0]; st.counter22 = s_cnt[1]; st.trace.n_corner = s_cnt[0]; st.trace.n_plane = s_cnt[1]; }
+  }
+  auto evaluate = [&](const double* x) {
+    double acc[28];
+#pragma unroll
+    for (int k = 0; k < 28; ++k) acc[k] = 0.0;
+    const double w[3] = {x[0], x[1], x[2]}, t[3] = {x[3], x[4], x[5]};
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+      const VOResidual& R = rr[i];
+      if (R.type == 1) {  // CostFunctor32
+        const double p[3] = {R.obs[0], R.obs[1], R.obs[2]};
+        double y[3], M[3][3];
+        angle_axis_rotate_jac(w, p, y, M);
+        const double X[3] = {y[0] + t[0], y[1] + t[1], y[2] + t[2]};
+        const double r0 = X[0] - X[2] * R.obs[3], r1 = X[1] - X[2] * R.obs[4];
+        const double wgt = huber_weight(r0 * r0 + r1 * r1, &acc[27]);
+        const double A0[3] = {1.0, 0.0, -R.obs[3]}, A1[3] = {0.0, 1.0, -R.obs[4]};
+        double J0[6], J1[6];
+        for (int c = 0; c < 3; ++c) {
+          J0[c] = A0[0] * M[0][c] + A0[1] * M[1][c] + A0[2] * M[2][c];
+          J1[c] = A1[0] * M[0][c] + A1[1] * M[1][c] + A1[2] * M[2][c];
+          J0[3 + c] = A0[c]; J1[3 + c] = A1[c];
+        }
+        accum_row(acc, J0, r0, wgt);
+        accum_row(acc, J1, r1, wgt);
+      } else if (R.type == 2) {  // CostFunctor22: r = x1h . (t x (R x0h))
+        const double p[3] = {R.obs[0], R.obs[1], 1.0}, x1[3] = {R.obs[2], R.obs[3], 1.0};
+        double y[3], M[3][3];
+        angle_axis_rotate_jac(w, p, y, M);
+        const double txy[3] = {t[1] * y[2] - t[2] * y[1], t[2] * y[0] - t[0] * y[2], t[0] * y[1] - t[1] * y[0]};
+        const double r = x1[0] * txy[0] + x1[1] * txy[1] + x1[2] * txy[2];
+        const double wgt = huber_weight(r * r, &acc[27]);
+        const double dy[3] = {x1[1] * t[2] - x1[2] * t[1], x1[2] * t[0] - x1[0] * t[2], x1[0] * t[1] - x1[1] * t[0]};  // x1 x t
+        const double dt[3] = {y[1] * x1[2] - y[2] * x1[1], y[2] * x1[0] - y[0] * x1[2], y[0] * x1[1] - y[1] * x1[0]};  // y x x1
+        double J[6];
+        for (int c = 0; c < 3; ++c) { J[c] = dy[0] * M[0][c] + dy[1] * M[1][c] + dy[2] * M[2][c]; J[3 + c] = dt[c]; }
+        accum_row(acc, J, r, wgt);
+      }
+    }
+    block_reduce28(acc, S.red, S.scratch);
+  };
+  lm_solve_block(S, &st.trace, max_iterations, false, evaluate, /*euclid=*/1);
+  if (threadIdx.x == 0) for (int i = 0; i < 6; ++i) st.x[i] = S.x[i];
+}
+
+}  // namespace vb
+
+// ==================================================================================================================
+using namespace vb;
+
+struct vloam_vo {
+  vloam_ctx* ctx = nullptr;
+  int B = 0, cap = 0, maxM = 0;
+  long long count = -1;  // VisualOdometry::count (visual_odometry.cpp:28)
+  VOCalib calib{};
+  bool have_calib = false;
+  float* d_in = nullptr; int* d_n = nullptr;
+  float4* d_uvd = nullptr;
+  unsigned *kA = nullptr, *vA = nullptr, *kB = nullptr, *vB = nullptr;
+  float* bx[2] = {nullptr, nullptr}; float* by[2] = {nullptr, nullptr}; float* bd[2] = {nullptr, nullptr}; int* bc[2] = {nullptr, nullptr};
+  float* d_prev = nullptr; float* d_curr = nullptr; int* d_nm = nullptr; double* d_init = nullptr;
+  VOResidual* d_res = nullptr;
+  VOState* d_st = nullptr;
+  float* d_q = nullptr; float* d_qo = nullptr;  // query scratch
+  int qcap = 0;
+  int slot() const { return (int)(count % 2); }
+};
+
+namespace {
+int vfail(vloam_ctx* c, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (c) { c->last_error = what; if (e != cudaSuccess) { c->last_error += ": "; c->last_error += cudaGetErrorString(e); } }
+  return code;
+}
+#define VCU(ctx, call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) return vfail((ctx), VLOAM_E_CUDA, #call, e__); } while (0)
+}  // namespace
+
+extern "C" {
+
+int vloam_vo_destroy(vloam_vo* h) {
+  if (!h) return VLOAM_E_INVALID;
+  cudaSetDevice(h->ctx->device);
+  cudaStreamSynchronize(h->ctx->stream);
+  cudaFree(h->d_in); cudaFree(h->d_n); cudaFree(h->d_uvd); cudaFree(h->kA); cudaFree(h->vA); cudaFree(h->kB); cudaFree(h->vB);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->bx[i]); cudaFree(h->by[i]); cudaFree(h->bd[i]); cudaFree(h->bc[i]); }
+  cudaFree(h->d_prev); cudaFree(h->d_curr); cudaFree(h->d_nm); cudaFree(h->d_init); cudaFree(h->d_res); cudaFree(h->d_st);
+  cudaFree(h->d_q); cudaFree(h->d_qo);
+  delete h;
+  return VLOAM_OK;
+}
+
+int vloam_vo_create(vloam_ctx* c, int batch, int max_points, int max_matches, vloam_vo** out) {
+  if (!c || !out || batch < 1 || max_points < 1 || max_matches < 1) return VLOAM_E_INVALID;
+  *out = nullptr;
+  VCU(c, cudaSetDevice(c->device));
+  vloam_vo* h = new (std::nothrow) vloam_vo();
+  if (!h) return VLOAM_E_NOMEM;
+  h->ctx = c; h->B = batch; h->cap = (max_points + 255) / 256 * 256; h->maxM = max_matches;
+  const size_t B = batch, cap = h->cap, M = max_matches;
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) { e = cudaMalloc(p, bytes); if (e == cudaSuccess) e = cudaMemset(*p, 0, bytes); } };
+  A((void**)&h->d_in, B * cap * 4 * sizeof(float)); A((void**)&h->d_n, B * sizeof(int));
+  A((void**)&h->d_uvd, B * cap * sizeof(float4));
+  A((void**)&h->kA, B * cap * 4); A((void**)&h->vA, B * cap * 4); A((void**)&h->kB, B * cap * 4); A((void**)&h->vB, B * cap * 4);
+  for (int i = 0; i < 2; ++i) {
+    A((void**)&h->bx[i], B * kBuckets * 4); A((void**)&h->by[i], B * kBuckets * 4); A((void**)&h->bd[i], B * kBuckets * 4); A((void**)&h->bc[i], B * kBuckets * 4);
+  }
+  A((void**)&h->d_prev, B * M * 2 * sizeof(float)); A((void**)&h->d_curr, B * M * 2 * sizeof(float)); A((void**)&h->d_nm, B * sizeof(int));
+  A((void**)&h->d_init, B * 6 * sizeof(double)); A((void**)&h->d_res, B * M * sizeof(VOResidual)); A((void**)&h->d_st, B * sizeof(VOState));
+  h->qcap = 4096;
+  A((void**)&h->d_q, h->qcap * 2 * sizeof(float)); A((void**)&h->d_qo, h->qcap * sizeof(float));
+  if (e != cudaSuccess) { vloam_vo_destroy(h); return vfail(c, VLOAM_E_CUDA, "vloam_vo_create: allocation", e); }
+  *out = h;
+  return VLOAM_OK;
+}
+
+int vloam_vo_set_calibration(vloam_vo* h, const float* cam_T_velo, const float* rect0_T_cam, const float* P_rect0) {
+  if (!h || !cam_T_velo || !rect0_T_cam || !P_rect0) return VLOAM_E_INVALID;
+  std::memcpy(h->calib.cam_T_velo, cam_T_velo, 16 * sizeof(float));
+  std::memcpy(h->calib.rect0_T_cam, rect0_T_cam, 16 * sizeof(float));
+  std::memcpy(h->calib.P_rect0, P_rect0, 12 * sizeof(float));
+  h->have_calib = true;
+  return VLOAM_OK;
+}
+
+int vloam_vo_reset(vloam_vo* h) {  // visual_odometry.cpp:86-90
+  if (!h) return VLOAM_E_INVALID;
+  ++h->count;
+  return VLOAM_OK;
+}
+
+static int vo_run_cloud(vloam_vo* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
+  vloam_ctx* c = h->ctx;
+  if (!h->have_calib) return vfail(c, VLOAM_E_STATE, "vloam_vo_process_cloud before vloam_vo_set_calibration");
+  if (h->count < 0) return vfail(c, VLOAM_E_STATE, "vloam_vo_process_cloud before vloam_vo_reset");
+  const int s = h->slot();
+  cudaStream_t st = c->stream;
+  VB_LAUNCH(&c->prof, K_VO_PROJECT, st, vo_project<<<dim3(h->cap / 256, h->B), 256, 0, st>>>(xyz_dev, stride, slab_points * (size_t)stride, n_dev, h->calib, h->cap,
+                                                                                           h->d_uvd, h->kA, h->vA));
+  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_sort<<<h->B, 1024, 0, st>>>(n_dev, h->cap, h->kA, h->vA, h->kB, h->vB));
+  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_fold<<<dim3((kBuckets + 255) / 256, h->B), 256, 0, st>>>(n_dev, h->cap, h->kA, h->vA, h->d_uvd, h->bx[s], h->by[s],
+                                                                                                        h->bd[s], h->bc[s]));
+  VCU(c, cudaGetLastError());
+  return VLOAM_OK;
+}
+
+int vloam_vo_process_cloud(vloam_vo* h, const float* xyz, const int* n_points, int stride, size_t slab_points) {
+  if (!h || !xyz || !n_points || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  for (int b = 0; b < h->B; ++b) {
+    if (n_points[b] < 0 || (size_t)n_points[b] > slab_points) return vfail(c, VLOAM_E_INVALID, "n_points[b] exceeds slab_points");
+    if (n_points[b] > h->cap) return vfail(c, VLOAM_E_CAPACITY, "cloud larger than max_points");
+    if (n_points[b]) VCU(c, cudaMemcpyAsync(h->d_in + (size_t)b * h->cap * stride, xyz + (size_t)b * slab_points * stride,
+                                            (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  }
+  VCU(c, cudaMemcpyAsync(h->d_n, n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->stream));
+  return vo_run_cloud(h, h->d_in, h->d_n, stride, (size_t)h->cap);
+}
+int vloam_vo_process_cloud_device(vloam_vo* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
+  if (!h || !xyz_dev || !n_dev || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  VCU(h->ctx, cudaSetDevice(h->ctx->device));
+  return vo_run_cloud(h, xyz_dev, n_dev, stride, slab_points);
+}
+
+// slot 0 = current frame, 1 = previous frame
+static int vo_abs_slot(const vloam_vo* h, int slot) { return slot == 0 ? h->slot() : 1 - h->slot(); }
+
+int vloam_vo_query_depth(vloam_vo* h, int stream, int slot, const float* xy, int n, float* depth_out) {
+  if (!h || stream < 0 || stream >= h->B || (slot != 0 && slot != 1) || n < 0 || (n && (!xy || !depth_out))) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  if (h->count < 0) return vfail(c, VLOAM_E_STATE, "no cloud processed yet");
+  const int s = vo_abs_slot(h, slot);
+  const size_t o = (size_t)stream * kBuckets;
+  for (int base = 0; base < n; base += h->qcap) {
+    const int m = n - base < h->qcap ? n - base : h->qcap;
+    VCU(c, cudaMemcpyAsync(h->d_q, xy + (size_t)base * 2, (size_t)m * 2 * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    VB_LAUNCH(&c->prof, K_VO_QUERY, c->stream, vo_query<<<(m + 127) / 128, 128, 0, c->stream>>>(h->bx[s] + o, h->by[s] + o, h->bd[s] + o, h->bc[s] + o, h->d_q, m, h->d_qo));
+    VCU(c, cudaMemcpyAsync(depth_out + base, h->d_qo, (size_t)m * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+    VCU(c, cudaStreamSynchronize(c->stream));
+  }
+  return VLOAM_OK;
+}
+
+int vloam_vo_get_buckets(vloam_vo* h, int stream, int slot, float* bx, float* by, float* bd, int* bc) {
+  if (!h || stream < 0 || stream >= h->B || (slot != 0 && slot != 1)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  if (h->count < 0) return vfail(c, VLOAM_E_STATE, "no cloud processed yet");
+  const int s = vo_abs_slot(h, slot);
+  const size_t o = (size_t)stream * kBuckets;
+  if (bx) VCU(c, cudaMemcpyAsync(bx, h->bx[s] + o, kBuckets * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (by) VCU(c, cudaMemcpyAsync(by, h->by[s] + o, kBuckets * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (bd) VCU(c, cudaMemcpyAsync(bd, h->bd[s] + o, kBuckets * 4, cudaMemcpyDeviceToHost, c->stream));
+  if (bc) VCU(c, cudaMemcpyAsync(bc, h->bc[s] + o, kBuckets * 4, cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, const int* n_matches, const double* init, int remove_VO_outlier,
+                   int max_iterations, double* out) {
+  if (!h || !prev_uv || !curr_uv || !n_matches || !out) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  if (h->count < 1) return vfail(c, VLOAM_E_STATE, "vloam_vo_solve needs two processed frames");
+  for (int b = 0; b < h->B; ++b) if (n_matches[b] < 0 || n_matches[b] > h->maxM) return vfail(c, VLOAM_E_CAPACITY, "n_matches exceeds max_matches");
+  cudaStream_t st = c->stream;
+  const size_t M = h->maxM;
+  VCU(c, cudaMemcpyAsync(h->d_prev, prev_uv, (size_t)h->B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  VCU(c, cudaMemcpyAsync(h->d_curr, curr_uv, (size_t)h->B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  VCU(c, cudaMemcpyAsync(h->d_nm, n_matches, h->B * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (init) VCU(c, cudaMemcpyAsync(h->d_init, init, (size_t)h->B * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
+  const int sp = 1 - h->slot();  // depth of the PREVIOUS frame's cloud is used (depth0, visual_odometry.cpp:316)
+  VB_LAUNCH(&c->prof, K_VO_QUERY, st, vo_build_residuals<<<dim3((h->maxM + 127) / 128, h->B), 128, 0, st>>>(h->d_prev, h->d_curr, h->d_nm, h->maxM, h->calib,
+                                                                                                          remove_VO_outlier, h->bx[sp], h->by[sp], h->bd[sp],
+                                                                                                          h->bc[sp], h->d_res));
+  VB_LAUNCH(&c->prof, K_VO_SOLVE, st, vo_solve<<<h->B, 256, 0, st>>>(h->d_st, h->d_res, h->maxM, h->d_nm, init ? h->d_init : nullptr, max_iterations));
+  VCU(c, cudaGetLastError());
+  std::vector<VOState> hs(h->B);
+  VCU(c, cudaMemcpyAsync(hs.data(), h->d_st, hs.size() * sizeof(VOState), cudaMemcpyDeviceToHost, st));
+  VCU(c, cudaStreamSynchronize(st));
+  for (int b = 0; b < h->B; ++b) {
+    for (int i = 0; i < 6; ++i) out[(size_t)b * 8 + i] = hs[b].x[i];
+    out[(size_t)b * 8 + 6] = hs[b].counter32; out[(size_t)b * 8 + 7] = hs[b].counter22;
+  }
+  return VLOAM_OK;
+}
+
+}  // extern "C"

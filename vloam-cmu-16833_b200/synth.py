@@ -181,3 +181,43 @@ class ScanStream:
 def make_scans(seed: int, n_scans: int, n_cols: int = N_COLS) -> tuple[list[np.ndarray], ScanStream]:
     s = ScanStream(seed, n_cols=n_cols)
     return [s.scan(k) for k in range(n_scans)], s
+
+
+# ------------------------------------------------------------------------------------------------ visual odometry inputs
+def kitti_like_calibration():
+    """cam_T_velo (4x4), rect0_T_cam (4x4), P_rect0 (3x4): KITTI-like camera 0."""
+    cam_T_velo = np.array([[0.0, -1.0, 0.0, 0.0], [0.0, 0.0, -1.0, -0.08], [1.0, 0.0, 0.0, -0.27], [0.0, 0.0, 0.0, 1.0]], np.float32)
+    rect0_T_cam = np.eye(4, dtype=np.float32)
+    P_rect0 = np.array([[718.856, 0.0, 607.1928, 0.0], [0.0, 718.856, 185.2157, 0.0], [0.0, 0.0, 1.0, 0.0]], np.float32)
+    return cam_T_velo, rect0_T_cam, P_rect0
+
+
+def make_matches(stream: "ScanStream", k: int, n_matches: int = 800, pixel_sigma: float = 0.5, outlier_frac: float = 0.1,
+                 seed: int = 0):
+    """Matched keypoint pixels between camera frames k-1 and k: scene points seen by the LiDAR in frame k-1, projected
+    into both images with Gaussian pixel noise and a fraction of gross outliers.  Returns (prev_uv, curr_uv) float32 (m, 2)
+    and the ground-truth (R, t) taking frame k-1 camera coordinates to frame k camera coordinates."""
+    rng = np.random.Generator(np.random.Philox(key=[stream.seed, 0x7A7C + 131 * k + seed]))
+    cam_T_velo, _, P = kitti_like_calibration()
+    Tcv = cam_T_velo.astype(np.float64)
+    pts = stream.scan(k - 1).astype(np.float64)
+    pts = pts[np.isfinite(pts[:, 0])]
+    cam = pts @ Tcv[:3, :3].T + Tcv[:3, 3]
+    K = P[:, :3].astype(np.float64)
+    uvw = cam @ K.T
+    uv0 = uvw[:, :2] / uvw[:, 2:3]
+    ok = (cam[:, 2] > 2.0) & (uv0[:, 0] > 5) & (uv0[:, 0] < 1236) & (uv0[:, 1] > 5) & (uv0[:, 1] < 370)
+    idx = rng.choice(np.nonzero(ok)[0], size=min(n_matches, int(ok.sum())), replace=False)
+    # velo k-1 -> velo k is the inverse of relative_pose(k); conjugate into the camera frame
+    R_lc, t_lc = stream.relative_pose(k)
+    Rv, tv = R_lc.T, -R_lc.T @ t_lc
+    Rc = Tcv[:3, :3] @ Rv @ Tcv[:3, :3].T
+    tc = Tcv[:3, :3] @ tv + Tcv[:3, 3] - Rc @ Tcv[:3, 3]
+    cam1 = cam[idx] @ Rc.T + tc
+    uvw1 = cam1 @ K.T
+    uv1 = uvw1[:, :2] / uvw1[:, 2:3]
+    prev = uv0[idx] + rng.normal(0, pixel_sigma, (len(idx), 2))
+    curr = uv1 + rng.normal(0, pixel_sigma, (len(idx), 2))
+    bad = rng.random(len(idx)) < outlier_frac
+    curr[bad] += rng.uniform(-60, 60, (int(bad.sum()), 2))
+    return prev.astype(np.float32), curr.astype(np.float32), (Rc, tc)
