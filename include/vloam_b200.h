@@ -187,6 +187,12 @@ int vloam_vo_get_buckets(vloam_vo* h, int stream, int slot, float* bx, float* by
  * t of cam0_curr_LOT_cam0_prev.  out[batch][8] = angles_0to1(3) t_0to1(3) counter32 counter22. */
 int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, const int* n_matches, const double* init,
                    int remove_VO_outlier, int max_iterations, double* out);
+/* Parity read-out of the last solve of one stream: records[8][7] (as vloam_get_lo_trace; later records are dropped),
+ * info[4] = n_records, termination, counter32, counter22; para[7] = final parameters (6 used). */
+int vloam_vo_get_trace(vloam_vo* h, int stream, double* records, int* info, double* para);
+/* Residual blocks of the last solve of one stream, per match slot: type[max_matches] = 0 none / 1 CostFunctor32 /
+ * 2 CostFunctor22; obs[max_matches][5] = the functor's constructor arguments (visual_odometry.cpp:361-365, 408-412). */
+int vloam_vo_get_residuals(vloam_vo* h, int stream, int* type, double* obs);
 
 #ifdef __cplusplus
 }

@@ -94,6 +94,8 @@ def lib():
             "orc_vo_query_depth": (C.c_float, [vp, C.c_int, C.c_float, C.c_float]),
             "orc_vo_solve": (None, [vp, c_fp, c_fp, C.c_int, c_dp, c_dp, c_dp]),
             "orc_vo_factor_eval": (C.c_int, [C.c_int, c_dp, c_dp, c_dp, c_dp]),
+            "orc_vo_trace": (C.c_int, [vp, c_dp, C.c_int]),
+            "orc_vo_residuals": (C.c_int, [vp, c_ip, c_dp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -404,6 +406,17 @@ class VisualOdometry:
 
     def query_depth(self, slot, x, y):
         return float(lib().orc_vo_query_depth(self._h, slot, float(x), float(y)))
+
+    def residuals(self, m):
+        t = np.zeros(m, np.int32)
+        o = np.zeros((m, 5))
+        n = lib().orc_vo_residuals(self._h, _ip(t), _dp(o))
+        return t[:n], o[:n]
+
+    def trace(self, max_records=128):
+        it = np.zeros((max_records, 7))
+        n = lib().orc_vo_trace(self._h, _dp(it), max_records)
+        return it[: min(n, max_records)].copy()
 
     def solve(self, prev_uv, curr_uv, init_aa=None, init_t=None):
         p, c = _f32(prev_uv).reshape(-1, 2), _f32(curr_uv).reshape(-1, 2)

@@ -212,6 +212,8 @@ struct VisualOdometry {
   double angles_0to1[3] = {0, 0, 0}, t_0to1[3] = {0, 0, 0};
   int counter32 = 0, counter22 = 0;
   LMSummary summary;
+  std::vector<int> res_type;       // per match: 0 skipped, 1 CostFunctor32, 2 CostFunctor22 (parity read-out)
+  std::vector<double> res_obs;     // 5 per match
 
   void reset() { ++count; i = count % 2; }
   void setCalibration(const float* cam_T_velo, const float* rect0_T_cam, const float* P_rect0) {
@@ -230,6 +232,7 @@ struct VisualOdometry {
   void solveNlsAll(const float* prev_uv, const float* curr_uv, int m, const double* init_aa, const double* init_t) {  // :254-450
     for (int j = 0; j < 3; ++j) { angles_0to1[j] = init_aa ? init_aa[j] : 0.0; t_0to1[j] = init_t ? init_t[j] : 0.0; }
     counter32 = counter22 = 0;
+    res_type.assign(m, 0); res_obs.assign((size_t)m * 5, 0.0);
     std::vector<CostBlock*> owned;
     const PointCloudUtil& pc_prev = point_cloud_utils[1 - i];
     const PointCloudUtil& pc_curr = point_cloud_utils[i];
@@ -253,6 +256,8 @@ struct VisualOdometry {
         CostFunctor32 f{static_cast<double>(X0[0]), static_cast<double>(X0[1]), static_cast<double>(X0[2]),
                         static_cast<double>(X1[0]) / static_cast<double>(X1[2]), static_cast<double>(X1[1]) / static_cast<double>(X1[2])};
         owned.push_back(new AutoDiffBlock33<CostFunctor32, 2>(f));
+        res_type[j] = 1; res_obs[j * 5] = f.observed_x0; res_obs[j * 5 + 1] = f.observed_y0; res_obs[j * 5 + 2] = f.observed_z0;
+        res_obs[j * 5 + 3] = f.observed_x1_bar; res_obs[j * 5 + 4] = f.observed_y1_bar;
         ++counter32;
       } else {
         p0[0] = prev_pt_x; p0[1] = prev_pt_y; p0[2] = 1.0f;
@@ -262,6 +267,8 @@ struct VisualOdometry {
         CostFunctor22 f{static_cast<double>(X0[0]) / static_cast<double>(X0[2]), static_cast<double>(X0[1]) / static_cast<double>(X0[2]),
                         static_cast<double>(X1[0]) / static_cast<double>(X1[2]), static_cast<double>(X1[1]) / static_cast<double>(X1[2])};
         owned.push_back(new AutoDiffBlock33<CostFunctor22, 1>(f));
+        res_type[j] = 2; res_obs[j * 5] = f.observed_x0_bar; res_obs[j * 5 + 1] = f.observed_y0_bar;
+        res_obs[j * 5 + 2] = f.observed_x1_bar; res_obs[j * 5 + 3] = f.observed_y1_bar;
         ++counter22;
       }
     }

@@ -41,6 +41,15 @@ def test_vo_depth_buckets_query_and_solve(synth, oracle, rect33):
         os_ = ovo.solve(prev_uv, curr_uv)
         assert (gs["counter32"][0], gs["counter22"][0]) == (os_["counter32"], os_["counter22"])
         assert gs["counter32"][0] > 100
+        gt_, go_ = vo.residuals()
+        ot_, oo_ = ovo.residuals(prev_uv.shape[0])
+        m_ = prev_uv.shape[0]
+        assert np.array_equal(gt_[:m_], ot_), "residual types differ"
+        bad = np.nonzero(np.abs(go_[:m_] - oo_).max(axis=1) > 1e-12)[0]
+        assert bad.size == 0, (bad[:5], go_[bad[:3]], oo_[bad[:3]])
+        tg, to = vo.trace(), ovo.trace()
+        np.testing.assert_allclose(tg["iterations"][0, 0], to[0, 0], rtol=1e-10)      # initial cost
+        assert tg["n_records"] == to.shape[0]
         np.testing.assert_allclose(gs["angles_0to1"][0], os_["angles_0to1"], atol=1e-6)
         np.testing.assert_allclose(gs["t_0to1"][0], os_["t_0to1"], atol=1e-5)
         # and the estimate is a sensible camera motion (about 1 m forward along z)

@@ -96,6 +96,8 @@ def lib():
             "vloam_vo_query_depth": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_fp],
             "vloam_vo_get_buckets": [vp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_ip],
             "vloam_vo_solve": [vp, vp, vp, vp, vp, C.c_int, C.c_int, c_dp],
+            "vloam_vo_get_trace": [vp, C.c_int, c_dp, c_ip, c_dp],
+            "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -445,6 +447,19 @@ class VisualOdometry:
                                             self.max_num_iterations, out.ctypes.data_as(c_dp)))
         return {"angles_0to1": out[:, 0:3].copy(), "t_0to1": out[:, 3:6].copy(), "counter32": out[:, 6].astype(int),
                 "counter22": out[:, 7].astype(int)}
+
+    def residuals(self, stream: int = 0):
+        t = np.zeros(self.max_matches, np.int32)
+        o = np.zeros((self.max_matches, 5))
+        self.ctx.check(lib().vloam_vo_get_residuals(self._h, stream, t.ctypes.data_as(c_ip), o.ctypes.data_as(c_dp)))
+        return t, o
+
+    def trace(self, stream: int = 0):
+        rec = np.zeros((8, 7))
+        info = np.zeros(4, np.int32)
+        para = np.zeros(7)
+        self.ctx.check(lib().vloam_vo_get_trace(self._h, stream, rec.ctypes.data_as(c_dp), info.ctypes.data_as(c_ip), para.ctypes.data_as(c_dp)))
+        return {"iterations": rec[: min(int(info[0]), 8)].copy(), "n_records": int(info[0]), "termination": int(info[1]), "para": para}
 
     def close(self):
         if self._h:

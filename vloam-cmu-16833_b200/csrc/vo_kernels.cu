@@ -139,42 +139,89 @@ __global__ void vo_query(const float* __restrict__ bx, const float* __restrict__
   if (i < n) out[i] = query_depth(bx, by, bd, bc, xy[2 * i], xy[2 * i + 1]);
 }
 
-// Eigen MatrixXf(3x3).colPivHouseholderQr().solve(b) in float (same algorithm as oracle::colpiv_qr_solve3x3f)
+// Eigen MatrixXf(3x3).colPivHouseholderQr().solve(b) in float: the same operations in the same order as
+// oracle::colpiv_qr_solve3x3f, written with compile-time indices only (columns are swapped through registers) so that
+// nothing is indexed dynamically.
+__device__ __forceinline__ void swap_col(float (&A)[3][3], int (&perm)[3], int k, int best) {
+  // swap columns k and best (best > k); k is a compile-time constant after unrolling, best is 1 or 2
+#pragma unroll
+  for (int c = 1; c < 3; ++c)
+    if (c == best) {
+#pragma unroll
+      for (int i = 0; i < 3; ++i) { const float t = A[i][k]; A[i][k] = A[i][c]; A[i][c] = t; }
+      const int t = perm[k]; perm[k] = perm[c]; perm[c] = t;
+    }
+}
 __device__ void colpiv_qr_solve3x3f_dev(const float Ain[9], const float bin[3], float x[3]) {
   float A[3][3], b[3];
-  for (int i = 0; i < 3; ++i) { b[i] = bin[i]; for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c]; }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+    b[i] = bin[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c];
+  }
   int perm[3] = {0, 1, 2};
   int rank = 0;
+  bool stop = false;
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    int best = k; float bestn = -1.f;
-    for (int c = k; c < 3; ++c) { float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(A[i][c], A[i][c])); if (s > bestn) { bestn = s; best = c; } }
-    if (!(bestn > 0.f)) break;
-    if (best != k) { for (int i = 0; i < 3; ++i) { const float t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; } const int t = perm[k]; perm[k] = perm[best]; perm[best] = t; }
+    if (stop) continue;
+    int best = k;
+    float bestn = -1.f;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (c < k) continue;
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) if (i >= k) s = __fadd_rn(s, __fmul_rn(A[i][c], A[i][c]));
+      if (s > bestn) { bestn = s; best = c; }
+    }
+    if (!(bestn > 0.f)) { stop = true; continue; }
+    if (best != k) swap_col(A, perm, k, best);
     const float nrm = __fsqrt_rn(bestn);
     const float alpha = A[k][k] > 0 ? -nrm : nrm;
-    float v[3] = {0, 0, 0};
-    for (int i = k; i < 3; ++i) v[i] = A[i][k];
+    float v[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (i >= k) v[i] = A[i][k];
     v[k] = __fsub_rn(v[k], alpha);
-    float vn = 0; for (int i = k; i < 3; ++i) vn = __fadd_rn(vn, __fmul_rn(v[i], v[i]));
-    if (vn > 0) {
-      for (int c = k; c < 3; ++c) {
-        float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(v[i], A[i][c]));
+    float vn = 0.f;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) if (i >= k) vn = __fadd_rn(vn, __fmul_rn(v[i], v[i]));
+    if (vn > 0.f) {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c < k) continue;
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i >= k) s = __fadd_rn(s, __fmul_rn(v[i], A[i][c]));
         s = __fdiv_rn(__fmul_rn(2.0f, s), vn);
-        for (int i = k; i < 3; ++i) A[i][c] = __fsub_rn(A[i][c], __fmul_rn(s, v[i]));
+#pragma unroll
+        for (int i = 0; i < 3; ++i) if (i >= k) A[i][c] = __fsub_rn(A[i][c], __fmul_rn(s, v[i]));
       }
-      float s = 0; for (int i = k; i < 3; ++i) s = __fadd_rn(s, __fmul_rn(v[i], b[i]));
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < 3; ++i) if (i >= k) s = __fadd_rn(s, __fmul_rn(v[i], b[i]));
       s = __fdiv_rn(__fmul_rn(2.0f, s), vn);
-      for (int i = k; i < 3; ++i) b[i] = __fsub_rn(b[i], __fmul_rn(s, v[i]));
+#pragma unroll
+      for (int i = 0; i < 3; ++i) if (i >= k) b[i] = __fsub_rn(b[i], __fmul_rn(s, v[i]));
     }
     ++rank;
   }
-  float y[3] = {0, 0, 0};
-  for (int k = rank - 1; k >= 0; --k) {
+  float y[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    if (k >= rank) continue;
     float s = b[k];
-    for (int c = k + 1; c < rank; ++c) s = __fsub_rn(s, __fmul_rn(A[k][c], y[c]));
+#pragma unroll
+    for (int c = 0; c < 3; ++c) if (c > k && c < rank) s = __fsub_rn(s, __fmul_rn(A[k][c], y[c]));
     y[k] = __fdiv_rn(s, A[k][k]);
   }
-  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+  x[0] = x[1] = x[2] = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) if (perm[k] == j) x[j] = y[k];
+  }
 }
 
 // grid (ceil(maxM / 128), B), block 128: one thread per match
@@ -500,6 +547,40 @@ int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, cons
   for (int b = 0; b < h->B; ++b) {
     for (int i = 0; i < 6; ++i) out[(size_t)b * 8 + i] = hs[b].x[i];
     out[(size_t)b * 8 + 6] = hs[b].counter32; out[(size_t)b * 8 + 7] = hs[b].counter22;
+  }
+  return VLOAM_OK;
+}
+
+
+int vloam_vo_get_residuals(vloam_vo* h, int stream, int* type, double* obs) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  std::vector<VOResidual> r(h->maxM);
+  VCU(c, cudaMemcpyAsync(r.data(), h->d_res + (size_t)stream * h->maxM, r.size() * sizeof(VOResidual), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < h->maxM; ++i) {
+    if (type) type[i] = r[i].type;
+    if (obs) for (int k = 0; k < 5; ++k) obs[(size_t)i * 5 + k] = r[i].obs[k];
+  }
+  return VLOAM_OK;
+}
+
+int vloam_vo_get_trace(vloam_vo* h, int stream, double* records, int* info, double* para) {
+  if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  VOState st;
+  VCU(c, cudaMemcpyAsync(&st, h->d_st + stream, sizeof(VOState), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  const SolveTrace& t = st.trace;
+  if (info) { info[0] = t.n_records; info[1] = t.termination; info[2] = t.n_corner; info[3] = t.n_plane; }
+  if (para) for (int i = 0; i < 7; ++i) para[i] = t.para[i];
+  if (records) for (int i = 0; i < kMaxLMRecords; ++i) {
+    const LMRecord& r = t.rec[i];
+    double* o = records + (size_t)i * 7;
+    o[0] = r.cost; o[1] = r.candidate_cost; o[2] = r.model_cost_change; o[3] = r.relative_decrease; o[4] = r.radius;
+    o[5] = r.step_is_valid; o[6] = r.step_is_successful;
   }
   return VLOAM_OK;
 }
