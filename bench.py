@@ -122,6 +122,11 @@ def run_reference(args, rank):
     do_map = args.workload == "sr_lo_lm"
     seqs = make_base_scans(0)
     pipes = [O.Pipeline() for _ in range(T)]
+    if do_map:
+        cubes = synth_map_cubes(args.map_points, BENCH_SEED)
+        for pp in pipes:
+            for (kind, cube), pts in cubes.items():
+                pp.lm.set_cube(kind, cube, pts)
 
     def one(t, i):
         pipes[t].process(seqs[t % N_BASE][pingpong(i, POOL_SCANS)], do_mapping=do_map)
@@ -151,6 +156,33 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def synth_map_cubes(n_points: int, seed: int):
+    """A synthetic pre-built map for configs[2]: ~n_points surf points (jittered 0.8 m
+    lattice on the ground plane and on stacked horizontal layers) plus 10 % as many corner points (vertical poles),
+    inside the 5 x 5 x 3 cube window around the origin.  Returns {(kind, cube_index): (n, 4) float32}."""
+    rng = np.random.default_rng(seed)
+    per_layer = 250 * 250 / 0.64
+    layers = max(1, int(round(n_points / per_layer)))
+    pts = []
+    for l in range(layers):
+        gx, gy = np.meshgrid(np.arange(-124.6, 124.6, 0.8), np.arange(-124.6, 124.6, 0.8))
+        z = -1.73 + 7.0 * l
+        p = np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, z)] + rng.uniform(-0.3, 0.3, (gx.size, 3)) * [1, 1, 0.02]
+        pts.append(p)
+    surf = np.concatenate(pts)[:n_points].astype(np.float32)
+    ncor = max(1000, n_points // 10)
+    cx, cy = rng.uniform(-120, 120, ncor // 20), rng.uniform(-120, 120, ncor // 20)
+    corner = np.c_[np.repeat(cx, 20), np.repeat(cy, 20), np.tile(np.arange(20) * 0.4 - 1.7, ncor // 20)].astype(np.float32)
+    out = {}
+    for kind, cloud in ((0, corner), (1, surf)):
+        ci = (np.floor((cloud[:, 0] + 25.0) / 50.0).astype(int) + 10) + 21 * (np.floor((cloud[:, 1] + 25.0) / 50.0).astype(int) + 10) \
+            + 441 * (np.floor((cloud[:, 2] + 25.0) / 50.0).astype(int) + 5)
+        for c in np.unique(ci):
+            sel = cloud[ci == c]
+            out[(kind, int(c))] = np.c_[sel, np.zeros(len(sel), np.float32)].astype(np.float32)
+    return out
+
+
 # --------------------------------------------------------------------------------------------- our arm (B200)
 def algorithmic_bytes(kernel, c):
     """Algorithmic HBM bytes of ONE launch of `kernel` over the whole batch (DESIGN.md "Measurement").
@@ -171,6 +203,14 @@ def algorithmic_bytes(kernel, c):
         "lo_associate_brute": (c["nSharp"] + c["nFlat"]) * 32 + (c["nLSlast"] + c["nLFlast"]) * 16,
         "lo_solve": (c["nSharp"] + c["nFlat"]) * 16 + c["nSharp"] * 48 + c["nFlat"] * 64,
         "lo_export_pose": 0,
+        # laser mapping (M = sub-map points, S = down-sampled scan points)
+        "lm_prepare": 0, "lm_misc": 0,
+        "lm_voxel": (c["nLS"] + c["nLF"]) * (16 + 16),
+        "lm_grid": c.get("M", 0) * (16 + 16) // 3,          # three launches: count, scan, scatter
+        "lm_associate": c.get("S", 0) * 96 + c.get("S", 0) * 9 * 8 * 16,
+        "lm_solve": c.get("S", 0) * 80,
+        "lm_insert": c.get("S", 0) * 48,
+        "lm_refilter": c.get("M", 0) * (16 * 4 + 20 * 4) // 3,
     }
     return table.get(kernel, 0)
 
@@ -210,8 +250,15 @@ def run_ours(args, rank, world, local_rank):
     stream = torch.cuda.Stream(device=dev)
     ctx = V.Context(device=local_rank, cuda_stream=stream.cuda_stream)
 
+    map_cubes = synth_map_cubes(args.map_points, BENCH_SEED) if do_map else {}
+    map_cap = int(2 ** np.ceil(np.log2(max(1 << 17, 1.3 * args.map_points)))) if do_map else 1 << 17
+
     def make_handle(batch):
-        return V.LidarOdometryMapping(ctx, batch=batch, max_points=cap)
+        h = V.LidarOdometryMapping(ctx, batch=batch, max_points=cap, map_capacity_points=map_cap)
+        for (kind, cube), pts in map_cubes.items():      # the same pre-built map under every stream
+            for b in range(batch):
+                h.map_set_cube(kind, cube, pts, stream=b)
+        return h
 
     def barrier():
         torch.cuda.synchronize()
@@ -219,12 +266,10 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
+    from vloam_b200 import dist as D
+
     def max_over_ranks(ms):
-        if dist is None:
-            return ms
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
+        return D.max_over_ranks(ms, dist, dev)
 
     sampler = ClockSampler(local_rank)
 
@@ -330,6 +375,10 @@ def run_ours(args, rank, world, local_rank):
     tot = {"N": int(B * cap), "Np": int(counts[:, 0].sum()), "nSharp": int(counts[:, 1].sum()), "nLS": int(counts[:, 2].sum()),
            "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
     tot["nLSlast"], tot["nLFlast"] = tot["nLS"], tot["nLF"]
+    if do_map:
+        info = lom.lm_info().astype(np.int64)
+        tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
+        tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
     kern = {}
     for name, (ms, cnt) in ktimes.items():
         by = algorithmic_bytes(name, tot)
@@ -348,7 +397,9 @@ def run_ours(args, rank, world, local_rank):
     from oracle import pyoracle as O
     O.build()
     pipe = O.Pipeline()
-    n_cpu = args.cpu_scans
+    for (kind, cube), pts in map_cubes.items():
+        pipe.lm.set_cube(kind, cube, pts)
+    n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 20)
     t0 = time.perf_counter()
     for i in range(n_cpu):
         pipe.process(seqs[0][pingpong(i, POOL_SCANS)], do_mapping=do_map)
@@ -390,6 +441,7 @@ def main():
     ap.add_argument("--batch", type=int, default=128, help="independent streams per GPU")
     ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm"])
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
+    ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -1,0 +1,67 @@
+"""Multi-GPU host logic: one process per GPU, streams sharded across ranks.
+
+The path shards by *stream* — independent sensor sequences share nothing, so there is no data-path collective; the
+only collectives are the bookkeeping ones below (barrier, max-over-ranks of the timed region, gather of per-rank
+counters).  Backend: NCCL on the GPUs, gloo in the CPU tests (tests/test_dist_gloo.py).
+"""
+from __future__ import annotations
+
+import os
+
+import numpy as np
+
+
+def env_rank_world():
+    return int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+
+
+def shard_streams(total_streams: int, world: int, rank: int) -> range:
+    """Global stream ids owned by `rank`: contiguous, balanced to within one stream, a partition of range(total)."""
+    if not (0 <= rank < world) or total_streams < 0:
+        raise ValueError((total_streams, world, rank))
+    base, extra = divmod(total_streams, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def stream_seed(bench_seed: int, global_stream: int, n_base: int) -> int:
+    """Seed of the synthetic base sequence a global stream replays (distinct sequences on distinct ranks)."""
+    return bench_seed + (global_stream % n_base) + 16 * (global_stream // max(1, n_base) % 64)
+
+
+def max_over_ranks(value: float, dist=None, device=None) -> float:
+    """Device-timed milliseconds -> max over ranks (the job is as slow as its slowest rank)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def sum_over_ranks(value: float, dist=None, device=None) -> float:
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return float(value)
+    import torch
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+def aggregate_throughput(units_this_rank: float, ms_this_rank: float, dist=None, device=None) -> float:
+    """Whole-job units/s = (sum over ranks of the units processed) / (max over ranks of the timed region)."""
+    total = sum_over_ranks(units_this_rank, dist, device)
+    ms = max_over_ranks(ms_this_rank, dist, device)
+    return total / (ms * 1e-3) if ms > 0 else 0.0
+
+
+def allreduce_normal_equations(buf, dist=None):
+    """Sum the per-rank partial normal equations [B, 28] = (21 upper J'J, 6 J'r, cost) in place.
+
+    This is the one real exchange step the path has when the residuals of one stream are split across ranks
+    (SURVEY.md section 8e layout (ii)); with stream sharding it is not needed.  Works on CPU (gloo) and GPU (NCCL)."""
+    if dist is None or not dist.is_initialized() or dist.get_world_size() == 1:
+        return buf
+    assert buf.shape[-1] == 28
+    dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf
