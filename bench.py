@@ -308,6 +308,12 @@ def run_ours(args, rank, world, local_rank):
         pose_dev = lom.lo_pose()
     value = world * B * args.steps / (ms_dev * 1e-3)
 
+    if args.legs == "device":
+        if rank == 0:
+            print(json.dumps({"value": value, "ms_per_step": ms_dev / args.steps, "gpu_launches": int(launches), "legs": "device",
+                              "kernels": {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in ktimes.items()}}), flush=True)
+        return
+
     # ---------------- leg 2: host buffers through the public API -> `e2e`
     lom2 = make_handle(B)
 
@@ -442,6 +448,7 @@ def main():
     ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm"])
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
+    ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
