@@ -274,38 +274,84 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
 
     # ---------------- leg 1: device-resident inputs -> `value`
-    lom = make_handle(B)
+    # The B streams are split over H handles, each on its own CUDA stream, so one group's single-CTA-per-stream
+    # kernels (the LM solves, ring-end scans) overlap the other groups' wide kernels instead of idling the SMs.
+    H = max(1, min(args.handles, B))
+    bounds = [(B * h) // H for h in range(H + 1)]
+    streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(H - 1)]
+    ctxs = [ctx] + [V.Context(device=local_rank, cuda_stream=s_.cuda_stream) for s_ in streams[1:]]
+    loms = []
+    for h in range(H):
+        nb = bounds[h + 1] - bounds[h]
+        hd = V.LidarOdometryMapping(ctxs[h], batch=nb, max_points=cap, map_capacity_points=map_cap)
+        for (kind, cube), pts in map_cubes.items():
+            for b in range(nb):
+                hd.map_set_cube(kind, cube, pts, stream=b)
+        loms.append(hd)
+    lom = loms[0]
 
     def step_dev(i):
         k = pingpong(i, POOL_SCANS)
-        lom.reset()
-        lom.scanRegistrationDevice(dev_pool[k], n_dev, 3, cap)
-        lom.laserOdometryIO(fetch=False)
-        if do_map:
-            lom.laserMappingIO(fetch=False)
+        for h in range(H):
+            hd = loms[h]
+            hd.reset()
+            hd.scanRegistrationDevice(dev_pool[k][bounds[h]:bounds[h + 1]], n_dev[bounds[h]:bounds[h + 1]], 3, cap)
+            hd.laserOdometryIO(fetch=False)
+            if do_map:
+                hd.laserMappingIO(fetch=False)
+
+    def join_streams():
+        for s_ in streams[1:]:
+            ev = torch.cuda.Event()
+            ev.record(s_)
+            stream.wait_event(ev)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_dev(i)
         barrier()
-        ctx.enable_timing(True)
-        ctx.kernel_timings(reset=True)
-        launches0 = ctx.launch_count
+        launches0 = sum(c_.launch_count for c_ in ctxs)
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
+        for s_ in streams[1:]:
+            s_.wait_event(e0)
         for i in range(args.warmup, args.warmup + args.steps):
             step_dev(i)
+        join_streams()
         e1.record(stream)
         barrier()
         ms_dev = max_over_ranks(e0.elapsed_time(e1))
         clocks = sampler.stop() if rank == 0 else None
-        launches = ctx.launch_count - launches0
-        ktimes = ctx.kernel_timings(reset=True)
-        ctx.enable_timing(False)
-        counts = lom.feature_counts().astype(np.int64)
-        pose_dev = lom.lo_pose()
+        launches = sum(c_.launch_count for c_ in ctxs) - launches0
+        counts = np.concatenate([hd.feature_counts() for hd in loms]).astype(np.int64)
+        pose_dev = {kk: np.concatenate([hd.lo_pose()[kk] for hd in loms]) for kk in loms[0].lo_pose()}
+        # per-kernel durations: the same steps again with a CUDA-event pair around every launch; with H > 1 the handles
+        # are run one after the other here so that the per-kernel times are not inflated by overlap
+        for c_ in ctxs:
+            c_.enable_timing(True)
+            c_.kernel_timings(reset=True)
+        for i in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
+            if H == 1:
+                step_dev(i)
+            else:
+                k = pingpong(i, POOL_SCANS)
+                for h in range(H):
+                    hd = loms[h]
+                    hd.reset()
+                    hd.scanRegistrationDevice(dev_pool[k][bounds[h]:bounds[h + 1]], n_dev[bounds[h]:bounds[h + 1]], 3, cap)
+                    hd.laserOdometryIO(fetch=False)
+                    if do_map:
+                        hd.laserMappingIO(fetch=False)
+                    torch.cuda.synchronize()
+        barrier()
+        ktimes = {}
+        for c_ in ctxs:
+            for kname, (ms_k, n_k) in c_.kernel_timings(reset=True).items():
+                a = ktimes.get(kname, (0.0, 0))
+                ktimes[kname] = (a[0] + ms_k, a[1] + n_k)
+            c_.enable_timing(False)
     value = world * B * args.steps / (ms_dev * 1e-3)
 
     if args.legs == "device":
@@ -382,12 +428,12 @@ def run_ours(args, rank, world, local_rank):
            "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
     tot["nLSlast"], tot["nLFlast"] = tot["nLS"], tot["nLF"]
     if do_map:
-        info = lom.lm_info().astype(np.int64)
+        info = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64)
         tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
         tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
     kern = {}
     for name, (ms, cnt) in ktimes.items():
-        by = algorithmic_bytes(name, tot)
+        by = algorithmic_bytes(name, tot) // H          # one launch covers one handle's B/H streams
         kern[name] = {"ms_total": ms, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share": None,
                       "alg_bytes_per_launch": by, "gbs": (by / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
     ksum = sum(v["ms_total"] for v in kern.values()) or 1.0
@@ -420,7 +466,7 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
         "config": {"workload": ("configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"
                                 if not do_map else "configs[2]: laserOdometry + laserMapping scan-to-submap"),
-                   "streams_per_gpu": B, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
+                   "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
                    "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
                    "parallelism": f"stream-sharded x{world} (no data-path collective)"},
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -448,6 +494,7 @@ def main():
     ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm"])
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
+    ap.add_argument("--handles", type=int, default=1, help="split the batch over this many handles / CUDA streams (device leg)")
     ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -456,7 +503,12 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    run_ours(args, rank, world, local_rank)
+    try:
+        run_ours(args, rank, world, local_rank)
+    finally:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
 
 
 if __name__ == "__main__":

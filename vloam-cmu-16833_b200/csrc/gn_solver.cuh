@@ -108,18 +108,23 @@ __device__ __forceinline__ void manifold_plus(const double x[7], const double d[
 }
 
 // Solve (H + diag(D2)) y = g for symmetric positive definite 6x6 by Cholesky.  H: upper triangle (21).
-static __device__ bool chol_solve6(const double Hu[21], const double D2[6], const double g[6], double y[6]) {
-  double A[6][6];
-  int k = 0;
-  for (int i = 0; i < 6; ++i) for (int j = i; j < 6; ++j) { A[i][j] = Hu[k]; A[j][i] = Hu[k]; ++k; }
-  for (int i = 0; i < 6; ++i) A[i][i] += D2[i];
+// Fully unrolled with compile-time indices so the factor lives in registers (this runs on one thread per problem and
+// sits on the critical path of every LM iteration).
+static __device__ __forceinline__ bool chol_solve6(const double Hu[21], const double D2[6], const double g[6], double y[6]) {
   double L[6][6];
+  bool ok = true;
+#pragma unroll
   for (int i = 0; i < 6; ++i) {
-    for (int j = 0; j <= i; ++j) {
-      double s = A[i][j];
-      for (int q = 0; q < j; ++q) s -= L[i][q] * L[j][q];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) {
+      if (j > i) continue;
+      // A[i][j] with j <= i is stored at upper-triangle position (j, i): index = j*6 - j*(j-1)/2 + (i - j)
+      double s = Hu[j * 6 - (j * (j - 1)) / 2 + (i - j)];
+      if (i == j) s += D2[i];
+#pragma unroll
+      for (int q = 0; q < 6; ++q) if (q < j) s -= L[i][q] * L[j][q];
       if (i == j) {
-        if (!(s > 0.0)) return false;
+        if (!(s > 0.0)) ok = false;
         L[i][i] = sqrt(s);
       } else {
         L[i][j] = s / L[j][j];
@@ -127,10 +132,23 @@ static __device__ bool chol_solve6(const double Hu[21], const double D2[6], cons
     }
   }
   double z[6];
-  for (int i = 0; i < 6; ++i) { double s = g[i]; for (int q = 0; q < i; ++q) s -= L[i][q] * z[q]; z[i] = s / L[i][i]; }
-  for (int i = 5; i >= 0; --i) { double s = z[i]; for (int q = i + 1; q < 6; ++q) s -= L[q][i] * y[q]; y[i] = s / L[i][i]; }
-  for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) return false;
-  return true;
+#pragma unroll
+  for (int i = 0; i < 6; ++i) {
+    double s = g[i];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) if (q < i) s -= L[i][q] * z[q];
+    z[i] = s / L[i][i];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; --i) {
+    double s = z[i];
+#pragma unroll
+    for (int q = 0; q < 6; ++q) if (q > i) s -= L[q][i] * y[q];
+    y[i] = s / L[i][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 6; ++i) if (!isfinite(y[i])) ok = false;
+  return ok;
 }
 
 // Trust-region LM state kept in shared memory by the solve kernels (Ceres 2.0 defaults, oracle/ceres_lm.hpp).
