@@ -216,7 +216,7 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
   cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart); cudaFree(h->grid.cursor);
-  for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); cudaFree(h->grid.sortedIdx[i]); }
+  for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); }
   if (h->lm) lm_destroy(h->lm);
   delete h;
   return VLOAM_OK;
@@ -256,8 +256,8 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   A(dalloc(&h->d_flat, B * kMaxFlat)); A(dalloc(&h->d_flatIdx, B * kMaxFlat));
   A(dalloc(&h->d_lo, B)); A(dalloc(&h->d_prior, B * 7)); A(dalloc(&h->d_pose, B * 16));
   A(dalloc(&h->grid.hdr, B * 2)); A(dalloc(&h->grid.cellStart, B * 2 * (kGridCap + 1))); A(dalloc(&h->grid.cursor, B * 2 * (kGridCap + 1)));
-  A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp)); A(dalloc(&h->grid.sortedIdx[0], B * kMaxLessSharp));
-  A(dalloc(&h->grid.sorted[1], B * cap)); A(dalloc(&h->grid.sortedIdx[1], B * cap));
+  A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp));
+  A(dalloc(&h->grid.sorted[1], B * cap));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
   e = lm_create(&c->prof, c->stream, h->B, h->cap, p, &h->lm);

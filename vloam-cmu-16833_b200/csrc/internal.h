@@ -61,7 +61,6 @@ struct LOGrid {
   int* cellStart = nullptr;    // [B][2][kGridCap + 1]
   int* cursor = nullptr;       // [B][2][kGridCap + 1] scatter cursors (scratch)
   float4* sorted[2] = {nullptr, nullptr};  // corner: [B][kMaxLessSharp], surf: [B][cap]
-  int* sortedIdx[2] = {nullptr, nullptr};
 };
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,

@@ -118,8 +118,8 @@ __global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __rest
     }
     best = warp_min_u64(best);
     if (nT > 0 && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // DISTANCE_SQ_THRESHOLD (:272)
-      const int closest = (int)(unsigned)best;
-      const int id = (int)T[closest].w;  // closestPointScanID (:275)
+      const int closest = (int)((unsigned)best >> 6);
+      const int id = (int)((unsigned)best & 63u);  // closestPointScanID = int(intensity) of the closest point (:275)
       unsigned long long k2, k3;
       window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
       auto decode = [&](unsigned long long k) { return decode_order(k, nT); };
@@ -146,14 +146,17 @@ __global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __rest
 // Distances are the same float expression the brute-force kernel uses and ties break on the original index, so
 // both kernels return identical results.
 __device__ __forceinline__ int cell_coord(float v, float mn, float inv_c) { return (int)floorf((v - mn) * inv_c); }
+// Column-sorted copies keep (original index << 6 | int(intensity)) in the w lane; int(intensity) is in [0, 63].
+__device__ __forceinline__ int pack_index_ring(int j, int rid) { return (j << 6) | (rid & 63); }
+__device__ __forceinline__ int packed_index(float w) { return (int)((unsigned)__float_as_int(w) >> 6); }
+__device__ __forceinline__ int packed_ring(float w) { return __float_as_int(w) & 63; }
 
 // lo_build_grid: grid (2, B), block 1024, dynamic smem = (kGridCap + 1) ints.  blockIdx.x: 0 = corner cloud, 1 = surf.
 // Counting sort by column with the column table in shared memory (a global-memory table was measured 14x slower).
 __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict__ hdrCur, const float4* __restrict__ lessSharp,
                                                        const float4* __restrict__ lessFlat, int cap, GridHeader* __restrict__ ghdr,
                                                        int* __restrict__ cellStartAll, int* __restrict__ /*cursorAll*/,
-                                                       float4* __restrict__ sortedC, int* __restrict__ sidxC,
-                                                       float4* __restrict__ sortedS, int* __restrict__ sidxS) {
+                                                       float4* __restrict__ sortedC, float4* __restrict__ sortedS) {
   extern __shared__ int cells[];
   __shared__ float s_red[4][32];
   __shared__ int s_firstFull[kMaxRings + 1], s_lastLow[kMaxRings + 1], s_ringStart[kMaxRings + 2];
@@ -163,7 +166,6 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   const int which = blockIdx.x, b = blockIdx.y;
   const float4* T = which == 0 ? lessSharp + (size_t)b * kMaxLessSharp : lessFlat + (size_t)b * cap;
   float4* S = which == 0 ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
-  int* SI = which == 0 ? sidxC + (size_t)b * kMaxLessSharp : sidxS + (size_t)b * cap;
   const int n = which == 0 ? hdrCur[b].nLessSharp : hdrCur[b].nLessFlat;
   const int* trueStart = which == 0 ? hdrCur[b].ringStartLessSharp : hdrCur[b].ringStartLessFlat;
   GridHeader& G = ghdr[b * 2 + which];
@@ -251,8 +253,9 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
     const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
     const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
     const int pos = atomicAdd(&cells[iy * nx + ix], 1);
-    S[pos] = p;
-    SI[pos] = j;
+    // w carries what the search needs besides the position: the original index (tie-breaks, result) and
+    // int(intensity), the "scan id" the window tests of the reference read (:275, :285, :300 ...)
+    S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, (int)p.w)));
   }
   if (tid == 0) {
     G.minx = minx; G.miny = miny; G.c = c; G.inv_c = inv_c; G.nx = nx; G.ny = ny; G.n = n; G.ringsOk = s_mono;
@@ -347,24 +350,30 @@ __device__ __forceinline__ float grid_safe_radius(const GridView& G, float sx, f
 
 // lo_associate: one 8-lane group per query, grid search.  grid (ceil((kMaxSharp + kMaxFlat) / 32), B), block 256.
 // Same contract as lo_associate_brute.
-__global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
+__device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
                                                      const LOState* __restrict__ lo, const float4* __restrict__ sharp,
                                                      const float4* __restrict__ flat, const float4* __restrict__ cornerLast,
                                                      const float4* __restrict__ surfLast, int cap,
                                                      const GridHeader* __restrict__ ghdr, const int* __restrict__ cellStartAll,
-                                                     const float4* __restrict__ sortedC, const int* __restrict__ sidxC,
-                                                     const float4* __restrict__ sortedS, const int* __restrict__ sidxS,
+                                                     const float4* __restrict__ sortedC, const float4* __restrict__ sortedS,
                                                      int4* __restrict__ corr) {
   const int b = blockIdx.y;
   const int lane = lane_id(), g = lane / kGroup, gl = lane % kGroup, gshift = g * kGroup;
   const unsigned gmask = 0xffu << gshift;
-  const int slot = blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + g;
-  if (slot >= kMaxSharp + kMaxFlat) return;
+  const int q = blockIdx.x * 32 + (threadIdx.x >> 5) * 4 + g;
+  if (q >= kMaxSharp + kMaxFlat) return;
   const SRHeader& hc = hdrCur[b];
+  // Groups are dealt to the live queries first (sharp 0..nSharp-1, then flat 0..nFlat-1), so warps are full; the
+  // remaining groups only clear the unused correspondence slots.
+  const int nS = min(hc.nSharp, kMaxSharp), nF = min(hc.nFlat, kMaxFlat);
+  int slot;
+  if (q < nS) slot = q;
+  else if (q < nS + nF) slot = kMaxSharp + (q - nS);
+  else { const int r = q - (nS + nF); slot = r < kMaxSharp - nS ? nS + r : kMaxSharp + nF + (r - (kMaxSharp - nS)); }
   const bool isCorner = slot < kMaxSharp;
   const int which = isCorner ? 0 : 1;
   const int qi = isCorner ? slot : slot - kMaxSharp;
-  const int nq = isCorner ? hc.nSharp : hc.nFlat;
+  const int nq = isCorner ? nS : nF;
   int4 out = make_int4(-1, -1, -1, 0);
   const GridHeader& GH = ghdr[b * 2 + which];
   const int nT = GH.n;
@@ -380,7 +389,6 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
     const float sz = (float)(un[2] + lo[b].para_t[2]);
     const float4* T = isCorner ? cornerLast + (size_t)b * kMaxLessSharp : surfLast + (size_t)b * cap;
     const float4* S = isCorner ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
-    const int* SI = isCorner ? sidxC + (size_t)b * kMaxLessSharp : sidxS + (size_t)b * cap;
     const int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
     const int qx = cell_coord(sx, G.minx, G.inv_c), qy = cell_coord(sy, G.miny, G.inv_c);
     // ---- phase 1: exact nearest neighbour (laser_odometry.cpp:269 / :356)
@@ -388,8 +396,8 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
     auto visit1 = [&](int t) {
       const float4 tp = S[t];
       const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)SI[t];
-      best = key < best ? key : best;
+      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
+      best = key < best ? key : best;   // order: distance, then original index (the ring bits sit below the index)
     };
     // a point at exactly the same distance could still win the index tie-break: the walk only stops on `>`.
     // (no candidate yet: the reduced bits are 0xffffffff = NaN, every comparison is false, the walk continues)
@@ -403,8 +411,8 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
       if (best != 0xffffffffffffffffull && R > 0.f && __uint_as_float((unsigned)(best >> 32)) <= R * R) break;
     }
     if (best != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // :272
-      const int closest = (int)(unsigned)best;
-      const int id = (int)T[closest].w;  // closestPointScanID (:275)
+      const int closest = (int)((unsigned)best >> 6);
+      const int id = (int)((unsigned)best & 63u);  // closestPointScanID = int(intensity) of the closest point (:275)
       unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
       if (!GH.ringsOk) {
         // literal walk by the whole group's warp is not possible inside a group: do it lane-serially per group
@@ -443,12 +451,12 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
         if (id + 3 <= kMaxRings - 1) hi_j = min(GH.firstFull[id + 3], GH.ringStart[min(id + 4, kMaxRings)]);
         if (id - 2 >= 0) lo_j = max(GH.lastLow[id - 2], GH.ringStart[id - 2] - 1) + 1;
         auto visit2 = [&](int t) {
-          const int j = SI[t];
-          if (j < lo_j || j >= hi_j || j == closest) return;
           const float4 tp = S[t];
+          const int j = packed_index(tp.w);
+          if (j < lo_j || j >= hi_j || j == closest) return;
           const float d = sqdist_f(tp.x, tp.y, tp.z, sx, sy, sz);
           if (!((double)d < 25.0)) return;
-          const int rid = (int)tp.w;
+          const int rid = packed_ring(tp.w);
           const bool fwd = j > closest;
           const unsigned order = fwd ? (unsigned)j : 0x80000000u + (unsigned)(nT - j);
           const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | order;
@@ -491,6 +499,20 @@ __global__ void __launch_bounds__(256) lo_associate(const SRHeader* __restrict__
   if (gl == 0) corr[(size_t)b * (kMaxSharp + kMaxFlat) + slot] = out;
 }
 
+#define VB_LO_ASSOC_ARGS                                                                                                         \
+  const SRHeader *__restrict__ hdrCur, const SRHeader *__restrict__ hdrLast, const LOState *__restrict__ lo,                     \
+      const float4 *__restrict__ sharp, const float4 *__restrict__ flat, const float4 *__restrict__ cornerLast,                  \
+      const float4 *__restrict__ surfLast, int cap, const GridHeader *__restrict__ ghdr, const int *__restrict__ cellStartAll,   \
+      const float4 *__restrict__ sortedC, const float4 *__restrict__ sortedS, int4 *__restrict__ corr
+#define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr
+// Two register budgets of the same body: 64 registers (4 CTAs / SM) and <= 40 (6 CTAs / SM); the kernel is latency
+// bound, so which one wins is an occupancy question settled by measurement (VLOAM_LO_ASSOC_OCC=4|5|6|8; measured on B200 at 128 streams: 334 / 314 / 293 us for 4 / 5 / 6, so 6 is the default).
+__global__ void __launch_bounds__(256) lo_associate(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 5) lo_associate_occ5(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 6) lo_associate_occ6(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 8) lo_associate_occ8(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
+
+
 // ---------------------------------------------------------------------------------------------
 // lo_solve: grid (B), block 256.  One CTA solves one stream's pass.
 __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdrCur, LOState* __restrict__ lo,
@@ -509,60 +531,85 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
   const float4* SL = surfLast + (size_t)b * cap;
   const int nSharp = hdrCur[b].nSharp, nFlat = hdrCur[b].nFlat;
 
+  // Stage the per-correspondence geometry in shared memory once: it does not change between LM iterations, and the
+  // gathers (correspondence record -> 2-3 target points) are the longest dependent chain of an evaluation.
+  //   edge : a, b as six floats packed into G[0..2];   plane: unit normal in G[0..2], d0 in G[3].
+  constexpr int kSlots = kMaxSharp + kMaxFlat;
+  extern __shared__ double lo_dyn[];
+  double* G = lo_dyn;                                            // [4][kSlots]
+  unsigned char* kind = reinterpret_cast<unsigned char*>(G + 4 * kSlots);   // 0 none, 1 edge, 2 plane
+  __shared__ int s_nc, s_np;
+  if (threadIdx.x == 0) {
+    s_nc = 0; s_np = 0;
+    for (int i = 0; i < 4; ++i) S.x[i] = st.para_q[i];
+    for (int i = 0; i < 3; ++i) S.x[4 + i] = st.para_t[i];
+  }
+  __syncthreads();
+  {
+    int nc = 0, np = 0;
+    for (int s = threadIdx.x; s < kSlots; s += blockDim.x) {
+      const bool isCorner = s < kMaxSharp;
+      const int qi = isCorner ? s : s - kMaxSharp;
+      unsigned char kd = 0;
+      if (qi < (isCorner ? nSharp : nFlat)) {
+        const int4 c = cr[s];
+        if (c.w) {
+          if (isCorner) {
+            const float4 A = CL[c.x], Bp = CL[c.y];
+            G[0 * kSlots + s] = __hiloint2double(__float_as_int(A.x), __float_as_int(A.y));
+            G[1 * kSlots + s] = __hiloint2double(__float_as_int(A.z), __float_as_int(Bp.x));
+            G[2 * kSlots + s] = __hiloint2double(__float_as_int(Bp.y), __float_as_int(Bp.z));
+            kd = 1; nc++;
+          } else {
+            const float4 Jp = SL[c.x], Lp = SL[c.y], Mp = SL[c.z];
+            // ljm_norm = normalize((j - l) x (j - m))  (lidarFactor.hpp:68-69)
+            const double ax = (double)Jp.x - (double)Lp.x, ay = (double)Jp.y - (double)Lp.y, az = (double)Jp.z - (double)Lp.z;
+            const double bx = (double)Jp.x - (double)Mp.x, by = (double)Jp.y - (double)Mp.y, bz = (double)Jp.z - (double)Mp.z;
+            double n[3] = {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx};
+            const double z2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+            if (z2 > 0.0) { const double nn = sqrt(z2); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+            G[0 * kSlots + s] = n[0]; G[1 * kSlots + s] = n[1]; G[2 * kSlots + s] = n[2];
+            G[3 * kSlots + s] = -(n[0] * (double)Jp.x + n[1] * (double)Jp.y + n[2] * (double)Jp.z);
+            kd = 2; np++;
+          }
+        }
+      }
+      kind[s] = kd;
+    }
+    // correspondence counts (:348, :441)
+    nc = __reduce_add_sync(0xffffffffu, nc);
+    np = __reduce_add_sync(0xffffffffu, np);
+    if (lane_id() == 0) { atomicAdd(&s_nc, nc); atomicAdd(&s_np, np); }
+    __syncthreads();
+    if (threadIdx.x == 0) { st.corner_correspondence = s_nc; st.plane_correspondence = s_np; tr->n_corner = s_nc; tr->n_plane = s_np; }
+  }
+
   auto evaluate = [&](const double* x) {
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; ++k) acc[k] = 0.0;
     const double q[4] = {x[0], x[1], x[2], x[3]};
     const double t[3] = {x[4], x[5], x[6]};
-    for (int s = threadIdx.x; s < kMaxSharp + kMaxFlat; s += blockDim.x) {
-      const bool isCorner = s < kMaxSharp;
-      const int qi = isCorner ? s : s - kMaxSharp;
-      if (qi >= (isCorner ? nSharp : nFlat)) continue;
-      const int4 c = cr[s];
-      if (!c.w) continue;
-      if (isCorner) {
-        const float4 p = sh[qi], A = CL[c.x], Bp = CL[c.y];
-        const double a[3] = {(double)A.x, (double)A.y, (double)A.z};
-        const double bb[3] = {(double)Bp.x, (double)Bp.y, (double)Bp.z};
+    for (int s = threadIdx.x; s < kSlots; s += blockDim.x) {
+      const int kd = kind[s];
+      if (!kd) continue;
+      if (kd == 1) {
+        const float4 p = sh[s];
+        const double g0 = G[0 * kSlots + s], g1 = G[1 * kSlots + s], g2 = G[2 * kSlots + s];
+        const double a[3] = {(double)__int_as_float(__double2hiint(g0)), (double)__int_as_float(__double2loint(g0)),
+                             (double)__int_as_float(__double2hiint(g1))};
+        const double bb[3] = {(double)__int_as_float(__double2loint(g1)), (double)__int_as_float(__double2hiint(g2)),
+                              (double)__int_as_float(__double2loint(g2))};
         edge_block(q, t, p, a, bb, acc);
       } else {
-        const float4 p = fl[qi], Jp = SL[c.x], Lp = SL[c.y], Mp = SL[c.z];
-        // ljm_norm = normalize((j - l) x (j - m))  (lidarFactor.hpp:68-69)
-        const double ax = (double)Jp.x - (double)Lp.x, ay = (double)Jp.y - (double)Lp.y, az = (double)Jp.z - (double)Lp.z;
-        const double bx = (double)Jp.x - (double)Mp.x, by = (double)Jp.y - (double)Mp.y, bz = (double)Jp.z - (double)Mp.z;
-        double n[3] = {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx};
-        const double z2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
-        if (z2 > 0.0) { const double nn = sqrt(z2); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
-        const double d0 = -(n[0] * (double)Jp.x + n[1] * (double)Jp.y + n[2] * (double)Jp.z);
-        plane_block(q, t, p, n, d0, acc);
+        const float4 p = fl[s - kMaxSharp];
+        const double n[3] = {G[0 * kSlots + s], G[1 * kSlots + s], G[2 * kSlots + s]};
+        plane_block(q, t, p, n, G[3 * kSlots + s], acc);
       }
     }
     block_reduce28(acc, S.red, S.scratch);
   };
 
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) S.x[i] = st.para_q[i];
-    for (int i = 0; i < 3; ++i) S.x[4 + i] = st.para_t[i];
-  }
-  __syncthreads();
-  // correspondence counts (:348, :441)
-  {
-    int nc = 0, np = 0;
-    for (int s = threadIdx.x; s < kMaxSharp + kMaxFlat; s += blockDim.x) {
-      const bool isCorner = s < kMaxSharp;
-      const int qi = isCorner ? s : s - kMaxSharp;
-      if (qi < (isCorner ? nSharp : nFlat) && cr[s].w) { if (isCorner) nc++; else np++; }
-    }
-    nc = __reduce_add_sync(0xffffffffu, nc);
-    np = __reduce_add_sync(0xffffffffu, np);
-    __shared__ int s_nc, s_np;
-    if (threadIdx.x == 0) { s_nc = 0; s_np = 0; }
-    __syncthreads();
-    if (lane_id() == 0) { atomicAdd(&s_nc, nc); atomicAdd(&s_np, np); }
-    __syncthreads();
-    if (threadIdx.x == 0) { st.corner_correspondence = s_nc; st.plane_correspondence = s_np; tr->n_corner = s_nc; tr->n_plane = s_np; }
-  }
   lm_solve_block(S, tr, max_iterations, false, evaluate);
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) st.para_q[i] = S.x[i];
@@ -632,21 +679,42 @@ void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const
   const int smem = (kGridCap + 1) * (int)sizeof(int);
   if (!attr_set) { cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
   VB_LAUNCH(prof, K_LO_BUILD_GRID, st, lo_build_grid<<<dim3(2, B), 1024, smem, st>>>(hdrCur, lessSharp, lessFlat, cap, g->hdr, g->cellStart, g->cursor,
-                                                                                  g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1]));
+                                                                                  g->sorted[0], g->sorted[1]));
 }
+
+constexpr int kLoSolveDynSmem = (kMaxSharp + kMaxFlat) * (4 * (int)sizeof(double) + 1);
 
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior) {
+  const cudaError_t attr = cudaFuncSetAttribute(lo_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
+  (void)attr;
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
   if (lo_use_brute())
     VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
                                                   hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
   else
-    VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<dim3((kMaxSharp + kMaxFlat + 31) / 32, B), 256, 0, st>>>(
-                                            hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                            g->sorted[0], g->sortedIdx[0], g->sorted[1], g->sortedIdx[1], corr));
-  VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
+  {
+    static const int occ = [] { const char* e = getenv("VLOAM_LO_ASSOC_OCC"); return e ? atoi(e) : 6; }();
+    const dim3 grid((kMaxSharp + kMaxFlat + 31) / 32, B);
+    if (occ >= 8)
+      VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ8<<<grid, 256, 0, st>>>(
+                                              hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
+                                              g->sorted[0], g->sorted[1], corr));
+    else if (occ >= 6)
+      VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ6<<<grid, 256, 0, st>>>(
+                                              hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
+                                              g->sorted[0], g->sorted[1], corr));
+    else if (occ == 5)
+      VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ5<<<grid, 256, 0, st>>>(
+                                              hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
+                                              g->sorted[0], g->sorted[1], corr));
+    else
+      VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<grid, 256, 0, st>>>(
+                                              hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
+                                              g->sorted[0], g->sorted[1], corr));
+  }
+  VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
                                                                max_iterations, integrate));
 }
 
