@@ -99,14 +99,84 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def make_base_scans(rank: int):
+def make_base_scans(rank: int, with_streams: bool = False):
     """N_BASE sequences x POOL_SCANS scans, float32 (n, 3), NaN = no return."""
     from vloam_b200 import synth
-    seqs = []
+    seqs, streams = [], []
     for i in range(N_BASE):
         s = synth.ScanStream(BENCH_SEED + 16 * rank + i, n_cols=N_COLS)
+        streams.append(s)
         seqs.append([s.scan(k) for k in range(POOL_SCANS)])
-    return seqs
+    return (seqs, streams) if with_streams else seqs
+
+
+class CpuChain:
+    """One stream through the oracle in the order of vloam_main_node.cpp:125-180 (CPU arm / cpu_baseline).
+    workload: sr_lo | sr_lo_lm | vloam (adds VisualOdometry and feeds its result to laserOdometry as the prior)."""
+
+    def __init__(self, O, workload, map_cubes):
+        self.O, self.workload = O, workload
+        self.t = {"sr_ms": 0.0, "lo_ms": 0.0, "lm_ms": 0.0, "vo_ms": 0.0, "scans": 0}
+        if workload == "vloam":
+            from vloam_b200 import synth
+            self.calib = synth.kitti_like_calibration()
+            self.velo_T_cam0 = np.linalg.inv(self.calib[0].astype(np.float64))
+            self.vo = O.VisualOdometry(*self.calib)
+            self.lo = O.LaserOdometry(detach_VO_LO=False)
+            self.lm = O.LaserMapping()
+            self.frames = 0
+        else:
+            self.pipe = O.Pipeline()
+            self.lm = self.pipe.lm
+        for (kind, cube), pts in map_cubes.items():
+            self.lm.set_cube(kind, cube, pts)
+
+    def process(self, scan, matches=None):
+        O = self.O
+        if self.workload != "vloam":
+            self.pipe.process(scan, do_mapping=self.workload == "sr_lo_lm")
+            self.t.update(self.pipe.timings())
+            return
+        t0 = time.perf_counter()
+        self.vo.reset()
+        self.vo.process_cloud(scan)
+        prior = np.r_[0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+        if self.frames > 0 and matches is not None:
+            r = self.vo.solve(matches[0], matches[1])
+            prior = O.vo_to_lo_prior(r["angles_0to1"], r["t_0to1"], self.velo_T_cam0)
+        t1 = time.perf_counter()
+        sr = O.scan_registration(scan)
+        t2 = time.perf_counter()
+        self.lo.solve(sr, prior_q=prior[:4], prior_t=prior[4:])
+        t3 = time.perf_counter()
+        self.lm.reset()
+        self.lm.input_from_lo(self.lo)
+        self.lm.solve()
+        t4 = time.perf_counter()
+        self.frames += 1
+        self.t["vo_ms"] += 1e3 * (t1 - t0); self.t["sr_ms"] += 1e3 * (t2 - t1); self.t["lo_ms"] += 1e3 * (t3 - t2)
+        self.t["lm_ms"] += 1e3 * (t4 - t3); self.t["scans"] += 1
+
+    def timings(self):
+        return dict(self.t)
+
+
+def cpu_matches(scan_stream, i):
+    """(prev_uv, curr_uv) for replay step i of one base sequence (None for the first frame)."""
+    from vloam_b200 import synth
+    if i == 0:
+        return None
+    kp, k = pingpong(i - 1, POOL_SCANS), pingpong(i, POOL_SCANS)
+    pu, cu, _ = synth.make_matches(scan_stream, max(kp, k), n_matches=800)
+    return (pu, cu) if k > kp else (cu, pu)
+
+
+WORKLOAD_NAME = {
+    "sr_lo": ("scanRegistration+laserOdometry", "configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"),
+    "sr_lo_lm": ("scanRegistration+laserOdometry+laserMapping", "configs[2]: laserOdometry + laserMapping scan-to-submap"),
+    "vloam": ("visualOdometry(depth+solve)+scanRegistration+laserOdometry(VO prior)+laserMapping",
+              "configs[3]: full VLOAM, visual odometry depth association + solve feeding LiDAR odometry and mapping"),
+}
 
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
@@ -119,17 +189,16 @@ def run_reference(args, rank):
     from concurrent.futures import ThreadPoolExecutor
     O.build()
     T = max(1, len(os.sched_getaffinity(0)))
-    do_map = args.workload == "sr_lo_lm"
-    seqs = make_base_scans(0)
-    pipes = [O.Pipeline() for _ in range(T)]
-    if do_map:
-        cubes = synth_map_cubes(args.map_points, BENCH_SEED)
-        for pp in pipes:
-            for (kind, cube), pts in cubes.items():
-                pp.lm.set_cube(kind, cube, pts)
+    do_map = args.workload in ("sr_lo_lm", "vloam")
+    seqs, scan_streams = make_base_scans(0, with_streams=True)
+    cubes = synth_map_cubes(args.map_points, BENCH_SEED) if do_map else {}
+    pipes = [CpuChain(O, args.workload, cubes) for _ in range(T)]
+    n_steps = args.warmup + args.steps
+    mt = {(t % N_BASE, i): cpu_matches(scan_streams[t % N_BASE], i) for t in range(min(T, N_BASE)) for i in range(n_steps)} \
+        if args.workload == "vloam" else {}
 
     def one(t, i):
-        pipes[t].process(seqs[t % N_BASE][pingpong(i, POOL_SCANS)], do_mapping=do_map)
+        pipes[t].process(seqs[t % N_BASE][pingpong(i, POOL_SCANS)], mt.get((t % N_BASE, i)))
 
     with ThreadPoolExecutor(T) as ex:
         for i in range(args.warmup):
@@ -141,15 +210,14 @@ def run_reference(args, rank):
     value = T * args.steps / dt
     tm = pipes[0].timings()
     line = {
-        "impl": "reference", "metric": "scans/sec (HDL-64, 64x2048 pts) scanRegistration+laserOdometry" + ("+laserMapping" if do_map else ""),
+        "impl": "reference", "metric": "scans/sec (HDL-64, 64x2048 pts) " + WORKLOAD_NAME[args.workload][0],
         "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": "synthetic",
-        "config": {"workload": "configs[1]: scanRegistration + laserOdometry, synthetic 64x2048 stream" if not do_map
-                   else "configs[2]: laserOdometry + laserMapping", "streams": T, "points_per_scan": N_RINGS * N_COLS},
+        "config": {"workload": WORKLOAD_NAME[args.workload][1], "streams": T, "points_per_scan": N_RINGS * N_COLS},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
                          "sample": f"{T} threads x {args.steps} scans, one stream per thread; per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
-                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms per scan"},
+                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -229,9 +297,10 @@ def run_ours(args, rank, world, local_rank):
         dist = dist_
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
-    do_map = args.workload == "sr_lo_lm"
+    do_vo = args.workload == "vloam"
+    do_map = args.workload in ("sr_lo_lm", "vloam")
     cap = N_RINGS * N_COLS
-    seqs = make_base_scans(rank)
+    seqs, scan_streams = make_base_scans(rank, with_streams=True)
 
     # pools: POOL_SCANS tensors of [B, cap, 3]; stream b replays base sequence b % N_BASE
     host_pool, dev_pool = [], []
@@ -244,8 +313,31 @@ def run_ours(args, rank, world, local_rank):
         dev_pool.append(h.to(dev, non_blocking=True))
     n_host = np.full(B, cap, np.int32)
     n_dev = torch.from_numpy(n_host).to(dev)
-    torch.cuda.synchronize()
     pool_bytes = POOL_SCANS * B * cap * 12
+
+    # configs[3]: matched keypoint pixels for every (previous scan -> current scan) pair the ping-pong replay visits
+    M = 1024
+    match_host, match_dev, velo_T_cam0, calib = {}, {}, None, None
+    if do_vo:
+        from vloam_b200 import synth
+        calib = synth.kitti_like_calibration()
+        velo_T_cam0 = np.linalg.inv(calib[0].astype(np.float64))
+        base = {}
+        for s_i, sst in enumerate(scan_streams):
+            for k in range(1, POOL_SCANS):
+                pu, cu, _ = synth.make_matches(sst, k, n_matches=800)
+                base[(s_i, k - 1, k)] = (pu, cu)
+                base[(s_i, k, k - 1)] = (cu, pu)       # the replay also runs backwards in time
+        for (kp, k) in {(kp, k) for (_, kp, k) in base}:
+            hp = torch.zeros((B, M, 2), dtype=torch.float32).pin_memory()
+            hc = torch.zeros((B, M, 2), dtype=torch.float32).pin_memory()
+            hn = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            for b in range(B):
+                pu, cu = base[(b % N_BASE, kp, k)]
+                hp[b, :len(pu)] = torch.from_numpy(pu); hc[b, :len(cu)] = torch.from_numpy(cu); hn[b] = len(pu)
+            match_host[(kp, k)] = (hp, hc, hn)
+            match_dev[(kp, k)] = (hp.to(dev), hc.to(dev), hn.to(dev))
+    torch.cuda.synchronize()
 
     stream = torch.cuda.Stream(device=dev)
     ctx = V.Context(device=local_rank, cuda_stream=stream.cuda_stream)
@@ -253,12 +345,73 @@ def run_ours(args, rank, world, local_rank):
     map_cubes = synth_map_cubes(args.map_points, BENCH_SEED) if do_map else {}
     map_cap = int(2 ** np.ceil(np.log2(max(1 << 17, 1.3 * args.map_points)))) if do_map else 1 << 17
 
-    def make_handle(batch):
-        h = V.LidarOdometryMapping(ctx, batch=batch, max_points=cap, map_capacity_points=map_cap)
-        for (kind, cube), pts in map_cubes.items():      # the same pre-built map under every stream
-            for b in range(batch):
-                h.map_set_cube(kind, cube, pts, stream=b)
-        return h
+    class Group:
+        """Streams [b0, b1) of the batch: one LidarOdometryMapping handle (+ one VisualOdometry handle for configs[3]) on
+        one context / CUDA stream, driven in the order of vloam_main_node.cpp:125-180."""
+
+        def __init__(self, ctx_, b0, b1):
+            self.ctx, self.b0, self.b1, self.nb = ctx_, b0, b1, b1 - b0
+            self.lom = V.LidarOdometryMapping(ctx_, batch=self.nb, max_points=cap, map_capacity_points=map_cap,
+                                              detach_VO_LO=0 if do_vo else 1)
+            for (kind, cube), pts in map_cubes.items():      # the same pre-built map under every stream
+                for b in range(self.nb):
+                    self.lom.map_set_cube(kind, cube, pts, stream=b)
+            self.vo, self.prior = None, None
+            if do_vo:
+                self.vo = V.VisualOdometry(ctx_, batch=self.nb, max_points=cap, max_matches=M)
+                self.vo.setUpPointCloud(*calib)
+                self.prior = torch.zeros((self.nb, 7), dtype=torch.float64, device=dev)
+                self.prior[:, 3] = 1.0
+                self.uv = [torch.zeros((self.nb, M, 2), dtype=torch.float32, device=dev) for _ in range(2)]
+                self.nm = torch.zeros((self.nb,), dtype=torch.int32, device=dev)
+            self.steps = 0
+
+        def _vo(self, i, xyz, n, stride, slab, pu, cu, nm):
+            self.vo.reset()
+            self.vo.processPointCloudDevice(xyz, n, stride, slab)
+            if self.steps > 0:
+                self.vo.solveNlsAllDevice(pu, cu, nm)
+                self.vo.exportLOPrior(velo_T_cam0, self.prior)
+
+        def step_dev(self, i):
+            k = pingpong(i, POOL_SCANS)
+            sl = slice(self.b0, self.b1)
+            self.lom.reset()
+            self.lom.scanRegistrationDevice(dev_pool[k][sl], n_dev[sl], 3, cap)
+            if do_vo:
+                pu, cu, nm = match_dev[(pingpong(i - 1, POOL_SCANS), k)] if i > 0 else (None, None, None)
+                self._vo(i, dev_pool[k][sl], n_dev[sl], 3, cap, None if pu is None else pu[sl], None if cu is None else cu[sl],
+                         None if nm is None else nm[sl])
+            self.lom.laserOdometryIO(prior=self.prior, fetch=False)
+            if do_map:
+                self.lom.laserMappingIO(fetch=False)
+            self.steps += 1
+
+        def step_host(self, i, first):
+            """One scan in flight: enqueue scan i (pinned host -> device upload on the copy stream + kernels), then read
+            scan i-1's poses (device -> host) while scan i runs, so uploads overlap compute."""
+            k = pingpong(i, POOL_SCANS)
+            sl = slice(self.b0, self.b1)
+            self.lom.reset()
+            self.lom.scanRegistrationIO(host_pool[k][sl], n_host[sl])
+            if do_vo:
+                xyz, n, stride, slab = self.lom.input_device()          # the cloud is uploaded once and read twice
+                if i > 0:
+                    hp, hc, hn = match_host[(pingpong(i - 1, POOL_SCANS), k)]
+                    self.uv[0].copy_(hp[sl], non_blocking=True); self.uv[1].copy_(hc[sl], non_blocking=True)
+                    self.nm.copy_(hn[sl], non_blocking=True)
+                self._vo(i, xyz, n, stride, slab, self.uv[0], self.uv[1], self.nm)
+                self.lom.input_consumed()
+            self.lom.laserOdometryIO(prior=self.prior, fetch=False)
+            if do_map:
+                self.lom.laserMappingIO(fetch=False)
+            self.steps += 1
+            return None if first else self.lom.lo_pose(prev=True)
+
+        def close(self):
+            if self.vo is not None:
+                self.vo.close()
+            self.lom.close()
 
     def barrier():
         torch.cuda.synchronize()
@@ -274,31 +427,24 @@ def run_ours(args, rank, world, local_rank):
     sampler = ClockSampler(local_rank)
 
     # ---------------- leg 1: device-resident inputs -> `value`
-    # The B streams are split over H handles, each on its own CUDA stream, so one group's single-CTA-per-stream
+    # The B streams are split over H groups, each on its own CUDA stream, so one group's single-CTA-per-stream
     # kernels (the LM solves, ring-end scans) overlap the other groups' wide kernels instead of idling the SMs.
     H = max(1, min(args.handles, B))
     bounds = [(B * h) // H for h in range(H + 1)]
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(H - 1)]
     ctxs = [ctx] + [V.Context(device=local_rank, cuda_stream=s_.cuda_stream) for s_ in streams[1:]]
-    loms = []
+    groups = []
     for h in range(H):
-        nb = bounds[h + 1] - bounds[h]
-        hd = V.LidarOdometryMapping(ctxs[h], batch=nb, max_points=cap, map_capacity_points=map_cap)
-        for (kind, cube), pts in map_cubes.items():
-            for b in range(nb):
-                hd.map_set_cube(kind, cube, pts, stream=b)
-        loms.append(hd)
-    lom = loms[0]
+        with torch.cuda.stream(streams[h]):
+            groups.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
+    loms = [g.lom for g in groups]
 
-    def step_dev(i):
-        k = pingpong(i, POOL_SCANS)
+    def step_dev(i, serial=False):
         for h in range(H):
-            hd = loms[h]
-            hd.reset()
-            hd.scanRegistrationDevice(dev_pool[k][bounds[h]:bounds[h + 1]], n_dev[bounds[h]:bounds[h + 1]], 3, cap)
-            hd.laserOdometryIO(fetch=False)
-            if do_map:
-                hd.laserMappingIO(fetch=False)
+            with torch.cuda.stream(streams[h]):
+                groups[h].step_dev(i)
+            if serial:
+                torch.cuda.synchronize()
 
     def join_streams():
         for s_ in streams[1:]:
@@ -327,24 +473,13 @@ def run_ours(args, rank, world, local_rank):
         launches = sum(c_.launch_count for c_ in ctxs) - launches0
         counts = np.concatenate([hd.feature_counts() for hd in loms]).astype(np.int64)
         pose_dev = {kk: np.concatenate([hd.lo_pose()[kk] for hd in loms]) for kk in loms[0].lo_pose()}
-        # per-kernel durations: the same steps again with a CUDA-event pair around every launch; with H > 1 the handles
+        # per-kernel durations: the same steps again with a CUDA-event pair around every launch; with H > 1 the groups
         # are run one after the other here so that the per-kernel times are not inflated by overlap
         for c_ in ctxs:
             c_.enable_timing(True)
             c_.kernel_timings(reset=True)
         for i in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
-            if H == 1:
-                step_dev(i)
-            else:
-                k = pingpong(i, POOL_SCANS)
-                for h in range(H):
-                    hd = loms[h]
-                    hd.reset()
-                    hd.scanRegistrationDevice(dev_pool[k][bounds[h]:bounds[h + 1]], n_dev[bounds[h]:bounds[h + 1]], 3, cap)
-                    hd.laserOdometryIO(fetch=False)
-                    if do_map:
-                        hd.laserMappingIO(fetch=False)
-                    torch.cuda.synchronize()
+            step_dev(i, serial=H > 1)
         barrier()
         ktimes = {}
         for c_ in ctxs:
@@ -359,39 +494,31 @@ def run_ours(args, rank, world, local_rank):
             print(json.dumps({"value": value, "ms_per_step": ms_dev / args.steps, "gpu_launches": int(launches), "legs": "device",
                               "kernels": {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in ktimes.items()}}), flush=True)
         return
+    lm_info_all = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64) if do_map else None
+    for g in groups[1:]:
+        g.close()               # the e2e leg below reuses the first context; free the other groups' device memory
 
     # ---------------- leg 2: host buffers through the public API -> `e2e`
-    lom2 = make_handle(B)
-
-    def step_host(i, first):
-        """One scan in flight: enqueue scan i (pinned host -> device upload on the copy stream + kernels), then read
-        scan i-1's poses (device -> host) while scan i runs, so uploads overlap compute."""
-        k = pingpong(i, POOL_SCANS)
-        lom2.reset()
-        lom2.scanRegistrationIO(host_pool[k], n_host)
-        lom2.laserOdometryIO(fetch=False)
-        if do_map:
-            lom2.laserMappingIO(fetch=False)
-        return None if first else lom2.lo_pose(prev=True)
+    g2 = Group(ctx, 0, B)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
-            step_host(i, i == 0)
+            g2.step_host(i, i == 0)
         if args.warmup:
-            lom2.lo_pose()
+            g2.lom.lo_pose()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_host0 = time.perf_counter()
         e0.record(stream)
         for i in range(args.warmup, args.warmup + args.steps):
-            step_host(i, i == args.warmup)
-        pose_host = lom2.lo_pose()          # drain: the last scan's result is read inside the timed region too
+            g2.step_host(i, i == args.warmup)
+        pose_host = g2.lom.lo_pose()          # drain: the last scan's result is read inside the timed region too
         e1.record(stream)
         barrier()
         t_host1 = time.perf_counter()
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0)))
     e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
-    h2d = int(B * cap * 12 + B * 4)
+    h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
     d2h = int(B * 16 * 8)
     # same inputs, same number of steps -> both legs must end on identical poses
     same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
@@ -399,7 +526,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- leg 3: single-stream latency (batch = 1), context only
     lat_ms = None
     if rank == 0:
-        lom1 = make_handle(1)
+        lom1 = V.LidarOdometryMapping(ctx, batch=1, max_points=cap)
         one_dev = [dev_pool[k][0:1].contiguous() for k in range(POOL_SCANS)]
         n1 = n_dev[0:1].contiguous()
         with torch.cuda.stream(stream):
@@ -428,7 +555,7 @@ def run_ours(args, rank, world, local_rank):
            "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
     tot["nLSlast"], tot["nLFlast"] = tot["nLS"], tot["nLF"]
     if do_map:
-        info = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64)
+        info = lm_info_all
         tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
         tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
     kern = {}
@@ -448,24 +575,22 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- CPU baseline: oracle, 1 thread, bounded sample
     from oracle import pyoracle as O
     O.build()
-    pipe = O.Pipeline()
-    for (kind, cube), pts in map_cubes.items():
-        pipe.lm.set_cube(kind, cube, pts)
+    pipe = CpuChain(O, args.workload, map_cubes)
     n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 20)
+    cpu_m = [cpu_matches(scan_streams[0], i) for i in range(n_cpu)] if do_vo else [None] * n_cpu
     t0 = time.perf_counter()
     for i in range(n_cpu):
-        pipe.process(seqs[0][pingpong(i, POOL_SCANS)], do_mapping=do_map)
+        pipe.process(seqs[0][pingpong(i, POOL_SCANS)], cpu_m[i])
     cpu_dt = time.perf_counter() - t0
     tm = pipe.timings()
     cpu_value = n_cpu / cpu_dt
 
     line = {
-        "metric": "scans/sec (HDL-64, 64x2048 pts) scanRegistration+laserOdometry" + ("+laserMapping" if do_map else ""),
+        "metric": "scans/sec (HDL-64, 64x2048 pts) " + WORKLOAD_NAME[args.workload][0],
         "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
-        "config": {"workload": ("configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"
-                                if not do_map else "configs[2]: laserOdometry + laserMapping scan-to-submap"),
+        "config": {"workload": WORKLOAD_NAME[args.workload][1],
                    "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
                    "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
                    "parallelism": f"stream-sharded x{world} (no data-path collective)"},
@@ -478,7 +603,7 @@ def run_ours(args, rank, world, local_rank):
         "single_stream_latency_ms": lat_ms,
         "cpu_baseline": {"value": cpu_value, "unit": "scans/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} scans of one stream, 1 thread: SR {tm['sr_ms']/n_cpu:.1f} ms + LO {tm['lo_ms']/n_cpu:.1f} ms"
-                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + " per scan"},
+                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"},
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
@@ -490,13 +615,15 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=128, help="independent streams per GPU")
-    ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm"])
+    ap.add_argument("--batch", type=int, default=0, help="independent streams per GPU (default: 256 for sr_lo, 32 for the mapping workloads)")
+    ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm", "vloam"])
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
-    ap.add_argument("--handles", type=int, default=1, help="split the batch over this many handles / CUDA streams (device leg)")
+    ap.add_argument("--handles", type=int, default=2, help="split the batch over this many handles / CUDA streams (device leg)")
     ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
+    if args.batch <= 0:
+        args.batch = 256 if args.workload == "sr_lo" else 32
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

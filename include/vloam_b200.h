@@ -118,6 +118,12 @@ int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_point
 /* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers). */
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats,
                                    size_t slab_points);
+/* The device copy of the scan most recently uploaded by vloam_scan_registration ([batch][slab_points][stride] floats and
+ * [batch] counts), so that a second consumer on the same context — VisualOdometry::processPointCloud gets the same cloud
+ * in vloam_main_node.cpp:151,164 — does not upload it again.  Valid until the second next vloam_scan_registration; call
+ * vloam_input_consumed after enqueueing the extra reader so the buffer is not recycled under it. */
+int vloam_get_input_device(vloam_lidar* h, const float** xyz_dev, const int** n_points_dev, int* stride_floats, size_t* slab_points);
+int vloam_input_consumed(vloam_lidar* h);
 
 /* status[batch]: VLOAM_STREAM_* bits of the last scan registration. */
 int vloam_get_stream_status(vloam_lidar* h, int* status);
@@ -187,6 +193,16 @@ int vloam_vo_get_buckets(vloam_vo* h, int stream, int slot, float* bx, float* by
  * t of cam0_curr_LOT_cam0_prev.  out[batch][8] = angles_0to1(3) t_0to1(3) counter32 counter22. */
 int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, const int* n_matches, const double* init,
                    int remove_VO_outlier, int max_iterations, double* out);
+/* The same solve without host involvement: matches, counts and the optional initial guess already live in device memory
+ * (same layouts), nothing is copied back and the call does not synchronise; read the result with vloam_vo_get_result. */
+int vloam_vo_solve_device_async(vloam_vo* h, const float* prev_uv_dev, const float* curr_uv_dev, const int* n_matches_dev,
+                                const double* init_dev, int remove_VO_outlier, int max_iterations);
+int vloam_vo_get_result(vloam_vo* h, double* out /* [batch][8] as vloam_vo_solve */);
+/* VO result -> LO prior, on the device: cam0_curr_T_cam0_last (visual_odometry.cpp:426-430) ->
+ * velo_last_VOT_velo_curr = velo_T_cam0 * cam0_curr_T_cam0_last^-1 * velo_T_cam0^-1 (VloamTF::VO2VeloAndBase, vloam_tf.cpp:59-63),
+ * written as [batch][7] = q(x y z w) t to prior_dev, the layout vloam_laser_odometry_async reads (laser_odometry.cpp:225-232).
+ * velo_T_cam0: row-major 4x4 (host). */
+int vloam_vo_export_lo_prior(vloam_vo* h, const double* velo_T_cam0, double* prior_dev);
 /* Parity read-out of the last solve of one stream: records[8][7] (as vloam_get_lo_trace; later records are dropped),
  * info[4] = n_records, termination, counter32, counter22; para[7] = final parameters (6 used). */
 int vloam_vo_get_trace(vloam_vo* h, int stream, double* records, int* info, double* para);

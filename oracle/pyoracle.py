@@ -96,6 +96,7 @@ def lib():
             "orc_vo_factor_eval": (C.c_int, [C.c_int, c_dp, c_dp, c_dp, c_dp]),
             "orc_vo_trace": (C.c_int, [vp, c_dp, C.c_int]),
             "orc_vo_residuals": (C.c_int, [vp, c_ip, c_dp]),
+            "orc_vo_to_lo_prior": (None, [c_dp, c_dp, c_dp, c_dp]),
         }
         for name, (res, args) in sig.items():
             fn = getattr(L, name)
@@ -205,6 +206,16 @@ def vo_factor_eval(kind, obs, x):
     J = np.zeros(12)
     n = lib().orc_vo_factor_eval(kind, _dp(obs), _dp(x), _dp(r), _dp(J))
     return r[:n].copy(), J[: n * 6].reshape(n, 6).copy()
+
+
+def vo_to_lo_prior(angles, t, velo_T_cam0):
+    """(angles_0to1, t_0to1) -> velo_last_VOT_velo_curr as q(xyzw) t  (visual_odometry.cpp:426-430, vloam_tf.cpp:59-63)."""
+    a = np.ascontiguousarray(angles, np.float64)
+    tt = np.ascontiguousarray(t, np.float64)
+    m = np.ascontiguousarray(velo_T_cam0, np.float64).reshape(16)
+    out = np.zeros(7)
+    lib().orc_vo_to_lo_prior(_dp(a), _dp(tt), _dp(m), _dp(out))
+    return out
 
 
 def _trace(L, h, prefix, npasses, widths):

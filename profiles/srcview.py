@@ -23,7 +23,10 @@ for r in csv.reader(out.splitlines()):
     if hdr is None or r[0] == "" or not r[0].isdigit():
         continue
     key = (cur_file, int(r[0]))
-    inst, samp = int(r[i_inst] or 0), int(r[i_samp] or 0)
+    try:
+        inst, samp = int(r[i_inst] or 0), int(r[i_samp] or 0)
+    except (ValueError, IndexError):
+        continue
     a = lines.setdefault(key, [0, 0, r[1].strip()])
     a[0] += inst
     a[1] += samp

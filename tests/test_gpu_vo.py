@@ -88,3 +88,61 @@ def test_vo_batched_and_edge_cases(synth, oracle):
     g0 = vo.solveNlsAll(np.zeros((2, 0, 2), np.float32), np.zeros((2, 0, 2), np.float32))
     assert np.all(g0["t_0to1"] == 0) and np.all(g0["counter32"] == 0)
     vo.close()
+
+
+def test_vo_prior_feeds_laser_odometry_on_device(synth, oracle):
+    """The coupled mode of vloam_main (detach_VO_LO = false, vloam_main_node.cpp:150-167): VO result -> VloamTF::VO2VeloAndBase
+    -> LaserOdometry prior, with the whole chain resident on the device, against the same chain through the oracle."""
+    import torch
+    import vloam_b200 as V
+    n_cols = 512
+    stream = synth.ScanStream(77, n_cols=n_cols)
+    cam_T_velo, rect0_T_cam, P = synth.kitti_like_calibration()
+    velo_T_cam0 = np.linalg.inv(cam_T_velo.astype(np.float64))
+    ctx = V.Context()
+    vo = V.VisualOdometry(ctx, batch=1, max_points=64 * n_cols, max_matches=1024)
+    vo.setUpPointCloud(cam_T_velo, rect0_T_cam, P)
+    lom = V.LidarOdometryMapping(ctx, batch=1, max_points=64 * n_cols, detach_VO_LO=0)
+    ovo = oracle.VisualOdometry(cam_T_velo, rect0_T_cam, P)
+    olo = oracle.LaserOdometry(detach_VO_LO=False)
+    dev = torch.device("cuda", 0)
+    prior_dev = torch.zeros((1, 7), dtype=torch.float64, device=dev)
+    prior_dev[0, 3] = 1.0
+    for k in range(4):
+        cloud = stream.scan(k)
+        cloud_dev = torch.from_numpy(np.ascontiguousarray(cloud[None])).to(dev)
+        n_dev = torch.tensor([cloud.shape[0]], dtype=torch.int32, device=dev)
+        vo.reset(); ovo.reset()
+        vo.processPointCloudDevice(cloud_dev, n_dev, 3, cloud.shape[0]); ovo.process_cloud(cloud)
+        o_prior = np.r_[0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
+        if k > 0:
+            prev_uv, curr_uv, _ = synth.make_matches(stream, k, n_matches=600)
+            m = prev_uv.shape[0]
+            pu = np.zeros((1, 1024, 2), np.float32); cu = np.zeros((1, 1024, 2), np.float32)
+            pu[0, :m] = prev_uv; cu[0, :m] = curr_uv
+            vo.solveNlsAllDevice(torch.from_numpy(pu).to(dev), torch.from_numpy(cu).to(dev),
+                                 torch.tensor([m], dtype=torch.int32, device=dev))
+            vo.exportLOPrior(velo_T_cam0, prior_dev)
+            os_ = ovo.solve(prev_uv, curr_uv)
+            o_prior = oracle.vo_to_lo_prior(os_["angles_0to1"], os_["t_0to1"], velo_T_cam0)
+            ctx.synchronize()
+            g_prior = prior_dev.cpu().numpy()[0]
+            np.testing.assert_allclose(g_prior[4:], o_prior[4:], atol=1e-5)
+            np.testing.assert_allclose(g_prior[:4], o_prior[:4], atol=1e-6)
+            # given the same VO result the conversion itself agrees to rounding
+            gr = vo.result()
+            o_same = oracle.vo_to_lo_prior(gr["angles_0to1"][0], gr["t_0to1"][0], velo_T_cam0)
+            np.testing.assert_allclose(g_prior, o_same, atol=1e-14)
+        lom.reset()
+        lom.scanRegistrationDevice(cloud_dev, n_dev, 3, cloud.shape[0])
+        lom.laserOdometryIO(prior=prior_dev, fetch=False)
+        pose = lom.lo_pose()
+        ref = oracle.scan_registration(cloud)
+        olo.solve(ref, prior_q=o_prior[:4], prior_t=o_prior[4:])
+        st = olo.state
+        if k > 0:
+            # the two arms start LO from VO estimates that differ by the VO solve tolerance (1e-6 rad / 1e-5 m above)
+            np.testing.assert_allclose(pose["t_last_curr"][0], st["t_last_curr"], atol=1e-4)
+            np.testing.assert_allclose(np.abs(pose["q_last_curr"][0]), np.abs(st["q_last_curr"]), atol=1e-4)
+            assert pose["corner_correspondence"][0] > 50 and pose["plane_correspondence"][0] > 200
+    vo.close(); lom.close(); ctx.close()

@@ -77,6 +77,7 @@ def lib():
             "vloam_lidar_create": [vp, C.POINTER(LidarParams), pp], "vloam_lidar_destroy": [vp], "vloam_lidar_reset": [vp],
             "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_get_input_device": [vp, pp, pp, c_ip, C.POINTER(C.c_size_t)], "vloam_input_consumed": [vp],
             "vloam_get_stream_status": [vp, c_ip], "vloam_get_feature_counts": [vp, c_ip],
             "vloam_get_cloud": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
             "vloam_get_curvature": [vp, C.c_int, c_fp, C.c_int, c_ip],
@@ -96,6 +97,8 @@ def lib():
             "vloam_vo_query_depth": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_fp],
             "vloam_vo_get_buckets": [vp, C.c_int, C.c_int, c_fp, c_fp, c_fp, c_ip],
             "vloam_vo_solve": [vp, vp, vp, vp, vp, C.c_int, C.c_int, c_dp],
+            "vloam_vo_solve_device_async": [vp, vp, vp, vp, vp, C.c_int, C.c_int], "vloam_vo_get_result": [vp, c_dp],
+            "vloam_vo_export_lo_prior": [vp, c_dp, vp],
             "vloam_vo_get_trace": [vp, C.c_int, c_dp, c_ip, c_dp],
             "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
         }
@@ -236,6 +239,16 @@ class LidarOdometryMapping:
         self.ctx.check(lib().vloam_scan_registration_device(self._h, _ptr(xyz_dev), _ptr(n_points_dev), stride, slab_points))
 
     # -- lidar_odometry_mapping.cpp:96-123
+    def input_device(self):
+        """(xyz address, n_points address, stride, slab_points) of the scan scanRegistrationIO uploaded last."""
+        xyz, n = C.c_void_p(), C.c_void_p()
+        stride, slab = C.c_int(), C.c_size_t()
+        self.ctx.check(lib().vloam_get_input_device(self._h, C.byref(xyz), C.byref(n), C.byref(stride), C.byref(slab)))
+        return xyz.value, n.value, stride.value, slab.value
+
+    def input_consumed(self):
+        self.ctx.check(lib().vloam_input_consumed(self._h))
+
     def laserOdometryIO(self, prior=None, fetch=True):
         if not fetch:
             self.ctx.check(lib().vloam_laser_odometry_async(self._h, _ptr(prior)))
@@ -413,6 +426,10 @@ class VisualOdometry:
         n = np.full(self.batch, a.shape[1], np.int32) if n_points is None else np.ascontiguousarray(n_points, np.int32)
         self.ctx.check(lib().vloam_vo_process_cloud(self._h, _ptr(a), _ptr(n), a.shape[2], a.shape[1]))
 
+    def processPointCloudDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int):
+        """processPointCloud on clouds that already live in device memory ((batch, slab_points, stride) float32)."""
+        self.ctx.check(lib().vloam_vo_process_cloud_device(self._h, _ptr(xyz_dev), _ptr(n_points_dev), stride, slab_points))
+
     def queryDepth(self, xy, slot: int = 0, stream: int = 0):
         q = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
         out = np.zeros(q.shape[0], np.float32)
@@ -447,6 +464,23 @@ class VisualOdometry:
                                             self.max_num_iterations, out.ctypes.data_as(c_dp)))
         return {"angles_0to1": out[:, 0:3].copy(), "t_0to1": out[:, 3:6].copy(), "counter32": out[:, 6].astype(int),
                 "counter22": out[:, 7].astype(int)}
+
+    def solveNlsAllDevice(self, prev_uv_dev, curr_uv_dev, n_matches_dev, init_dev=None):
+        """solveNlsAll on device-resident matches ((batch, max_matches, 2) float32, (batch,) int32); asynchronous."""
+        self.ctx.check(lib().vloam_vo_solve_device_async(self._h, _ptr(prev_uv_dev), _ptr(curr_uv_dev), _ptr(n_matches_dev),
+                                                         _ptr(init_dev), self.remove_VO_outlier, self.max_num_iterations))
+
+    def result(self):
+        out = np.zeros((self.batch, 8))
+        self.ctx.check(lib().vloam_vo_get_result(self._h, out.ctypes.data_as(c_dp)))
+        return {"angles_0to1": out[:, 0:3].copy(), "t_0to1": out[:, 3:6].copy(), "counter32": out[:, 6].astype(int),
+                "counter22": out[:, 7].astype(int)}
+
+    def exportLOPrior(self, velo_T_cam0, prior_dev):
+        """VloamTF::VO2VeloAndBase (vloam_tf.cpp:59-63) on the device: writes velo_last_VOT_velo_curr as (batch, 7)
+        float64 q(xyzw) t into prior_dev, ready for LidarOdometryMapping.laserOdometryIO(prior=prior_dev, fetch=False)."""
+        m = np.ascontiguousarray(velo_T_cam0, np.float64).reshape(4, 4)
+        self.ctx.check(lib().vloam_vo_export_lo_prior(self._h, m.ctypes.data_as(c_dp), _ptr(prior_dev)))
 
     def residuals(self, stream: int = 0):
         t = np.zeros(self.max_matches, np.int32)

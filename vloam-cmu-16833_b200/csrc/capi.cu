@@ -90,6 +90,7 @@ struct vloam_lidar {
   bool lo_done_for_frame = false;
   long long lo_frames = 0;   // LaserOdometry::frameCount
   // input staging
+  int last_stride = 3;
   float* d_in[2] = {nullptr, nullptr};  // [B][cap][4], double-buffered so the next upload overlaps this scan's kernels
   int* d_n[2] = {nullptr, nullptr};     // [B]
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
@@ -313,7 +314,27 @@ int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_point
   if (r) return r;
   CU(c, cudaEventRecord(h->ev_in_free[slot], c->stream));
   h->in_used[slot] = true;
+  h->last_stride = stride;
   h->host_scans++;
+  return VLOAM_OK;
+}
+
+int vloam_get_input_device(vloam_lidar* h, const float** xyz_dev, const int** n_dev, int* stride_floats, size_t* slab_points) {
+  if (!h || !xyz_dev || !n_dev) return VLOAM_E_INVALID;
+  if (h->host_scans == 0) return fail(h->ctx, VLOAM_E_STATE, "vloam_get_input_device before vloam_scan_registration");
+  const int slot = (int)((h->host_scans - 1) & 1);
+  *xyz_dev = h->d_in[slot]; *n_dev = h->d_n[slot];
+  if (stride_floats) *stride_floats = h->last_stride;
+  if (slab_points) *slab_points = (size_t)h->cap;
+  return VLOAM_OK;
+}
+
+int vloam_input_consumed(vloam_lidar* h) {
+  if (!h) return VLOAM_E_INVALID;
+  if (h->host_scans == 0) return fail(h->ctx, VLOAM_E_STATE, "vloam_input_consumed before vloam_scan_registration");
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaEventRecord(h->ev_in_free[(h->host_scans - 1) & 1], c->stream));
   return VLOAM_OK;
 }
 

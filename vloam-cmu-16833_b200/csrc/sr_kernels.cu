@@ -18,6 +18,8 @@
 // reference is built without FMA (CMakeLists.txt:5-6) and the index sets depend on it.
 #include <math_constants.h>
 
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -297,55 +299,73 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
 }
 
 // ---------------------------------------------------------------------------------------------
-// sr_curvature: grid (ceil(cap/1024), B), block 256; every thread produces 4 consecutive curvatures from 14 points
-// held in registers.  20 B of HBM traffic per point (16 read + 4 written); the shared-memory tile is padded by one
-// float4 every 8 so the stride-4 register fill is bank-conflict free.
+// sr_curvature: grid (ceil(tiles / tilesPerCta), B), block 256; a CTA walks `tilesPerCta` consecutive 1024-point tiles
+// with a two-stage cp.async pipeline (tile k+1 streams into shared memory while tile k is computed), so loads stay in
+// flight for the whole life of the CTA.  Every thread produces 4 consecutive curvatures from 14 points held in
+// registers.  21 B of HBM traffic per point (16 read + 4 + 1 written); the shared-memory tile is padded by one float4
+// every 8 so the stride-4 register fill is bank-conflict free.
 __device__ __forceinline__ int curv_pad(int e) { return e + (e >> 3); }
 constexpr int kCurvTile = 1024;
+constexpr int kCurvTileSmem = kCurvTile + 10 + (kCurvTile + 10) / 8 + 1;
 __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
-                                                     int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag) {
+                                                     int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag,
+                                                     int tilesPerCta) {
   const int b = blockIdx.y;
   const int size = hdr[b].cloudSize;
-  const int base = blockIdx.x * kCurvTile;
-  if (base >= size) return;
+  const int ntiles = (size + kCurvTile - 1) / kCurvTile;
+  const int first = blockIdx.x * tilesPerCta, last = min(first + tilesPerCta, ntiles);
+  if (first >= last) return;
   const float4* c = cloud + (size_t)b * cap;
-  __shared__ float4 tile[kCurvTile + 10 + (kCurvTile + 10) / 8 + 1];
-  for (int e = threadIdx.x; e < kCurvTile + 10; e += 256) {  // tile[e] == cloud[base - 5 + e]
-    const int g = base - 5 + e;
-    tile[curv_pad(e)] = (g >= 0 && g < size) ? __ldg(c + g) : make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();
-  const int i0 = base + 4 * threadIdx.x;
-  if (i0 >= size) return;
-  float4 t[14];
-#pragma unroll
-  for (int k = 0; k < 14; ++k) t[k] = tile[curv_pad(4 * threadIdx.x + k)];  // t[k] == cloud[i0 - 5 + k]
-  float out[4];
-  unsigned gaps = 0;  // byte o = [ |p[i+1] - p[i]|^2 > 0.05 ], the neighbour-suppression break test (:355-358, :367-370)
-#pragma unroll
-  for (int o = 0; o < 4; ++o) {
-    {
-      const float gx = __fsub_rn(t[o + 6].x, t[o + 5].x), gy = __fsub_rn(t[o + 6].y, t[o + 5].y), gz = __fsub_rn(t[o + 6].z, t[o + 5].z);
-      const float g2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
-      if ((double)g2 > 0.05 || i0 + o + 1 >= size) gaps |= 1u << (8 * o);
+  __shared__ __align__(16) float4 tile[2][kCurvTileSmem];
+  auto issue = [&](int tileIdx, int buf) {   // tile[buf][pad(e)] <- cloud[tileIdx * 1024 - 5 + e]
+    const int base = tileIdx * kCurvTile;
+    for (int e = threadIdx.x; e < kCurvTile + 10; e += 256) {
+      const int g = base - 5 + e;
+      if (g >= 0 && g < size) __pipeline_memcpy_async(&tile[buf][curv_pad(e)], c + g, sizeof(float4));
+      else tile[buf][curv_pad(e)] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
-    // :290-301: p[i-5] + p[i-4] + p[i-3] + p[i-2] + p[i-1] - 10*p[i] + p[i+1] + ... + p[i+5], left to right
-    float dx = __fadd_rn(t[o].x, t[o + 1].x), dy = __fadd_rn(t[o].y, t[o + 1].y), dz = __fadd_rn(t[o].z, t[o + 1].z);
+    __pipeline_commit();
+  };
+  issue(first, 0);
+  for (int tix = first; tix < last; ++tix) {
+    const int buf = (tix - first) & 1;
+    if (tix + 1 < last) { issue(tix + 1, buf ^ 1); __pipeline_wait_prior(1); }
+    else __pipeline_wait_prior(0);
+    __syncthreads();
+    const int i0 = tix * kCurvTile + 4 * threadIdx.x;
+    if (i0 < size) {
+      float4 t[14];
 #pragma unroll
-    for (int k = 2; k <= 4; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
-    dx = __fsub_rn(dx, __fmul_rn(10.f, t[o + 5].x)); dy = __fsub_rn(dy, __fmul_rn(10.f, t[o + 5].y)); dz = __fsub_rn(dz, __fmul_rn(10.f, t[o + 5].z));
+      for (int k = 0; k < 14; ++k) t[k] = tile[buf][curv_pad(4 * threadIdx.x + k)];  // t[k] == cloud[i0 - 5 + k]
+      float out[4];
+      unsigned gaps = 0;  // byte o = [ |p[i+1] - p[i]|^2 > 0.05 ], the neighbour-suppression break test (:355-358, :367-370)
 #pragma unroll
-    for (int k = 6; k <= 10; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
-    const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // :303
-    const int i = i0 + o;
-    out[o] = (i >= 5 && i < size - 5) ? v : 0.f;
-  }
-  float* dst = curv + (size_t)b * cap + i0;
-  *reinterpret_cast<unsigned*>(gapflag + (size_t)b * cap + i0) = gaps;  // cap is a multiple of 1024: always in bounds
-  if (i0 + 3 < size) {
-    *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
-  } else {
-    for (int o = 0; o < 4 && i0 + o < size; ++o) dst[o] = out[o];
+      for (int o = 0; o < 4; ++o) {
+        {
+          const float gx = __fsub_rn(t[o + 6].x, t[o + 5].x), gy = __fsub_rn(t[o + 6].y, t[o + 5].y), gz = __fsub_rn(t[o + 6].z, t[o + 5].z);
+          const float g2 = __fadd_rn(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)), __fmul_rn(gz, gz));
+          if ((double)g2 > 0.05 || i0 + o + 1 >= size) gaps |= 1u << (8 * o);
+        }
+        // :290-301: p[i-5] + p[i-4] + p[i-3] + p[i-2] + p[i-1] - 10*p[i] + p[i+1] + ... + p[i+5], left to right
+        float dx = __fadd_rn(t[o].x, t[o + 1].x), dy = __fadd_rn(t[o].y, t[o + 1].y), dz = __fadd_rn(t[o].z, t[o + 1].z);
+#pragma unroll
+        for (int k = 2; k <= 4; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
+        dx = __fsub_rn(dx, __fmul_rn(10.f, t[o + 5].x)); dy = __fsub_rn(dy, __fmul_rn(10.f, t[o + 5].y)); dz = __fsub_rn(dz, __fmul_rn(10.f, t[o + 5].z));
+#pragma unroll
+        for (int k = 6; k <= 10; ++k) { dx = __fadd_rn(dx, t[o + k].x); dy = __fadd_rn(dy, t[o + k].y); dz = __fadd_rn(dz, t[o + k].z); }
+        const float v = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));  // :303
+        const int i = i0 + o;
+        out[o] = (i >= 5 && i < size - 5) ? v : 0.f;
+      }
+      float* dst = curv + (size_t)b * cap + i0;
+      *reinterpret_cast<unsigned*>(gapflag + (size_t)b * cap + i0) = gaps;  // cap is a multiple of 1024: always in bounds
+      if (i0 + 3 < size) {
+        *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+      } else {
+        for (int o = 0; o < 4 && i0 + o < size; ++o) dst[o] = out[o];
+      }
+    }
+    __syncthreads();   // everyone is done with tile[buf] before the next iteration refills it
   }
 }
 
@@ -812,8 +832,15 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
   SRHeader& h = hdr[b];
   if (blockIdx.x < kMaxRings) {
     const int ring = blockIdx.x;
-    int off = 0;
-    for (int r = 0; r < ring; ++r) off += h.ringLessFlat[r];
+    __shared__ int s_off;
+    if (threadIdx.x < 32) {   // offset of this ring = sum of the earlier rings' counts (one warp, two loads per lane)
+      const int l = threadIdx.x;
+      int v = (l < ring ? h.ringLessFlat[l] : 0) + (l + 32 < ring ? h.ringLessFlat[l + 32] : 0);
+      v = __reduce_add_sync(0xffffffffu, v);
+      if (l == 0) s_off = v;
+    }
+    __syncthreads();
+    const int off = s_off;
     const int n = h.ringLessFlat[ring];
     const float4* src = lessFlatStage + (size_t)b * cap + h.ringStart[ring];
     float4* dst = lessFlat + (size_t)b * cap + off;
@@ -875,7 +902,12 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
   VB_LAUNCH(prof, K_SR_CLASSIFY, st, sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));
-  VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((cap + kCurvTile - 1) / kCurvTile, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag));
+  {
+    // tiles per CTA: long pipelines when the batch alone fills the machine, one tile per CTA for small batches
+    const int tiles = (cap + kCurvTile - 1) / kCurvTile;
+    const int per = (size_t)B * tiles >= 4096 ? 4 : 1;
+    VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
+  }
   VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<2048><<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
   VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<2048><<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem<2048>), st>>>(hdr, cloud, cap, label, lessFlatStage));
   if (cap > 2048 + 0) {  // rings longer than 2048 points (only possible when a scan has more than 2048 points at all)

@@ -373,6 +373,82 @@ __global__ void __launch_bounds__(256) vo_solve(VOState* __restrict__ stAll, con
 // ==================================================================================================================
 using namespace vb;
 
+// ---------------------------------------------------------------------------------------------
+// VO result -> laser-odometry prior.  VisualOdometry::solveNlsAll stores (angles_0to1, t_0to1) as the tf2 transform
+// cam0_curr_T_cam0_last (visual_odometry.cpp:426-430: axis-angle -> quaternion -> basis); VloamTF::VO2VeloAndBase
+// turns it into velo_last_VOT_velo_curr = velo_T_cam0 * cam0_curr_T_cam0_last^-1 * velo_T_cam0^-1 (vloam_tf.cpp:59-63),
+// which LaserOdometry::solveLO copies into para_q / para_t (laser_odometry.cpp:225-232).  tf2 arithmetic (double)
+// restated: Quaternion::setRotation, Matrix3x3::setRotation / getRotation, Transform::operator* / inverse.
+struct VOFrame { double R[3][3]; double t[3]; };
+__device__ __forceinline__ VOFrame frame_mul(const VOFrame& a, const VOFrame& b) {
+  VOFrame o;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.R[i][j] = a.R[i][0] * b.R[0][j] + a.R[i][1] * b.R[1][j] + a.R[i][2] * b.R[2][j];
+    o.t[i] = a.R[i][0] * b.t[0] + a.R[i][1] * b.t[1] + a.R[i][2] * b.t[2] + a.t[i];
+  }
+  return o;
+}
+__device__ __forceinline__ VOFrame frame_inv(const VOFrame& a) {
+  VOFrame o;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) o.R[i][j] = a.R[j][i];
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) o.t[i] = o.R[i][0] * -a.t[0] + o.R[i][1] * -a.t[1] + o.R[i][2] * -a.t[2];
+  return o;
+}
+__global__ void vo_export_prior(const VOState* __restrict__ st, VOFrame A, int B, double* __restrict__ prior /*[B][7]*/) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  const double* x = st[b].x;
+  const double angle = sqrt(x[0] * x[0] + x[1] * x[1] + x[2] * x[2]);
+  double q[4] = {0.0, 0.0, 0.0, 1.0};
+  if (angle > 0.0) {
+    // tf2::Quaternion::setRotation(axis = angles / angle, angle): s = sin(angle / 2) / |axis|
+    const double ax = x[0] / angle, ay = x[1] / angle, az = x[2] / angle;
+    const double d = sqrt(ax * ax + ay * ay + az * az);
+    const double s = sin(angle * 0.5) / d;
+    q[0] = ax * s; q[1] = ay * s; q[2] = az * s; q[3] = cos(angle * 0.5);
+  }
+  VOFrame T;
+  {  // tf2::Matrix3x3::setRotation
+    const double d = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double s = 2.0 / d;
+    const double xs = q[0] * s, ys = q[1] * s, zs = q[2] * s;
+    const double wx = q[3] * xs, wy = q[3] * ys, wz = q[3] * zs;
+    const double xx = q[0] * xs, xy = q[0] * ys, xz = q[0] * zs;
+    const double yy = q[1] * ys, yz = q[1] * zs, zz = q[2] * zs;
+    T.R[0][0] = 1.0 - (yy + zz); T.R[0][1] = xy - wz; T.R[0][2] = xz + wy;
+    T.R[1][0] = xy + wz; T.R[1][1] = 1.0 - (xx + zz); T.R[1][2] = yz - wx;
+    T.R[2][0] = xz - wy; T.R[2][1] = yz + wx; T.R[2][2] = 1.0 - (xx + yy);
+    T.t[0] = x[3]; T.t[1] = x[4]; T.t[2] = x[5];
+  }
+  const VOFrame V = frame_mul(frame_mul(A, frame_inv(T)), frame_inv(A));
+  // tf2::Matrix3x3::getRotation
+  double o[4];
+  const double trace = V.R[0][0] + V.R[1][1] + V.R[2][2];
+  if (trace > 0.0) {
+    double s = sqrt(trace + 1.0);
+    o[3] = s * 0.5;
+    s = 0.5 / s;
+    o[0] = (V.R[2][1] - V.R[1][2]) * s; o[1] = (V.R[0][2] - V.R[2][0]) * s; o[2] = (V.R[1][0] - V.R[0][1]) * s;
+  } else {
+    const int i = V.R[0][0] < V.R[1][1] ? (V.R[1][1] < V.R[2][2] ? 2 : 1) : (V.R[0][0] < V.R[2][2] ? 2 : 0);
+    const int j = (i + 1) % 3, k = (i + 2) % 3;
+    double s = sqrt(V.R[i][i] - V.R[j][j] - V.R[k][k] + 1.0);
+    o[i] = s * 0.5;
+    s = 0.5 / s;
+    o[3] = (V.R[k][j] - V.R[j][k]) * s; o[j] = (V.R[j][i] + V.R[i][j]) * s; o[k] = (V.R[k][i] + V.R[i][k]) * s;
+  }
+  double* out = prior + (size_t)b * 7;
+  out[0] = o[0]; out[1] = o[1]; out[2] = o[2]; out[3] = o[3];
+  out[4] = V.t[0]; out[5] = V.t[1]; out[6] = V.t[2];
+}
+
 struct vloam_vo {
   vloam_ctx* ctx = nullptr;
   int B = 0, cap = 0, maxM = 0;
@@ -522,6 +598,19 @@ int vloam_vo_get_buckets(vloam_vo* h, int stream, int slot, float* bx, float* by
   return VLOAM_OK;
 }
 
+static int vo_enqueue_solve(vloam_vo* h, const float* prev_dev, const float* curr_dev, const int* nm_dev, const double* init_dev,
+                            int remove_VO_outlier, int max_iterations) {
+  vloam_ctx* c = h->ctx;
+  cudaStream_t st = c->stream;
+  const int sp = 1 - h->slot();  // depth of the PREVIOUS frame's cloud is used (depth0, visual_odometry.cpp:316)
+  VB_LAUNCH(&c->prof, K_VO_QUERY, st, vo_build_residuals<<<dim3((h->maxM + 127) / 128, h->B), 128, 0, st>>>(prev_dev, curr_dev, nm_dev, h->maxM, h->calib,
+                                                                                                          remove_VO_outlier, h->bx[sp], h->by[sp], h->bd[sp],
+                                                                                                          h->bc[sp], h->d_res));
+  VB_LAUNCH(&c->prof, K_VO_SOLVE, st, vo_solve<<<h->B, 256, 0, st>>>(h->d_st, h->d_res, h->maxM, nm_dev, init_dev, max_iterations));
+  VCU(c, cudaGetLastError());
+  return VLOAM_OK;
+}
+
 int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, const int* n_matches, const double* init, int remove_VO_outlier,
                    int max_iterations, double* out) {
   if (!h || !prev_uv || !curr_uv || !n_matches || !out) return VLOAM_E_INVALID;
@@ -535,15 +624,27 @@ int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, cons
   VCU(c, cudaMemcpyAsync(h->d_curr, curr_uv, (size_t)h->B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
   VCU(c, cudaMemcpyAsync(h->d_nm, n_matches, h->B * sizeof(int), cudaMemcpyHostToDevice, st));
   if (init) VCU(c, cudaMemcpyAsync(h->d_init, init, (size_t)h->B * 6 * sizeof(double), cudaMemcpyHostToDevice, st));
-  const int sp = 1 - h->slot();  // depth of the PREVIOUS frame's cloud is used (depth0, visual_odometry.cpp:316)
-  VB_LAUNCH(&c->prof, K_VO_QUERY, st, vo_build_residuals<<<dim3((h->maxM + 127) / 128, h->B), 128, 0, st>>>(h->d_prev, h->d_curr, h->d_nm, h->maxM, h->calib,
-                                                                                                          remove_VO_outlier, h->bx[sp], h->by[sp], h->bd[sp],
-                                                                                                          h->bc[sp], h->d_res));
-  VB_LAUNCH(&c->prof, K_VO_SOLVE, st, vo_solve<<<h->B, 256, 0, st>>>(h->d_st, h->d_res, h->maxM, h->d_nm, init ? h->d_init : nullptr, max_iterations));
-  VCU(c, cudaGetLastError());
+  const int r = vo_enqueue_solve(h, h->d_prev, h->d_curr, h->d_nm, init ? h->d_init : nullptr, remove_VO_outlier, max_iterations);
+  if (r != VLOAM_OK) return r;
+  return vloam_vo_get_result(h, out);
+}
+
+int vloam_vo_solve_device_async(vloam_vo* h, const float* prev_uv_dev, const float* curr_uv_dev, const int* n_matches_dev,
+                                const double* init_dev, int remove_VO_outlier, int max_iterations) {
+  if (!h || !prev_uv_dev || !curr_uv_dev || !n_matches_dev) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  if (h->count < 1) return vfail(c, VLOAM_E_STATE, "vloam_vo_solve needs two processed frames");
+  return vo_enqueue_solve(h, prev_uv_dev, curr_uv_dev, n_matches_dev, init_dev, remove_VO_outlier, max_iterations);
+}
+
+int vloam_vo_get_result(vloam_vo* h, double* out) {
+  if (!h || !out) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
   std::vector<VOState> hs(h->B);
-  VCU(c, cudaMemcpyAsync(hs.data(), h->d_st, hs.size() * sizeof(VOState), cudaMemcpyDeviceToHost, st));
-  VCU(c, cudaStreamSynchronize(st));
+  VCU(c, cudaMemcpyAsync(hs.data(), h->d_st, hs.size() * sizeof(VOState), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
   for (int b = 0; b < h->B; ++b) {
     for (int i = 0; i < 6; ++i) out[(size_t)b * 8 + i] = hs[b].x[i];
     out[(size_t)b * 8 + 6] = hs[b].counter32; out[(size_t)b * 8 + 7] = hs[b].counter22;
@@ -551,6 +652,16 @@ int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, cons
   return VLOAM_OK;
 }
 
+int vloam_vo_export_lo_prior(vloam_vo* h, const double* velo_T_cam0, double* prior_dev) {
+  if (!h || !velo_T_cam0 || !prior_dev) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  VOFrame A;
+  for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) A.R[i][j] = velo_T_cam0[i * 4 + j]; A.t[i] = velo_T_cam0[i * 4 + 3]; }
+  VB_LAUNCH(&c->prof, K_VO_MISC, c->stream, vo_export_prior<<<(h->B + 63) / 64, 64, 0, c->stream>>>(h->d_st, A, h->B, prior_dev));
+  VCU(c, cudaGetLastError());
+  return VLOAM_OK;
+}
 
 int vloam_vo_get_residuals(vloam_vo* h, int stream, int* type, double* obs) {
   if (!h || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
