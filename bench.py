@@ -52,29 +52,57 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled every 200 ms while the timed region runs."""
+    """SM clock and throttle reasons sampled through NVML every ~5 ms while the timed region runs (nvidia-smi's own
+    polling is too coarse for a region of a few hundred ms; it stays as the fallback when NVML cannot be loaded)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    REASONS = ((0x8, "hw_slowdown"), (0x40, "hw_thermal_slowdown"), (0x20, "sw_thermal_slowdown"), (0x4, "sw_power_cap"))
 
-    def __init__(self, gpu_index: int):
-        self.idx = gpu_index
-        self.rows = []
-        self.proc = None
+    def __init__(self, gpu_index: int, uuid: str | None = None):
+        self.idx, self.uuid = gpu_index, uuid
+        self.rows, self.sm, self.bits = [], [], 0
+        self.proc, self.nv, self.h, self.run = None, None, None, False
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.h = pynvml.nvmlDeviceGetHandleByUUID(self.uuid) if self.uuid else pynvml.nvmlDeviceGetHandleByIndex(self.idx)
+            self.mx = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv, self.run = pynvml, True
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nv = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "200", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
+                                          "-lms", "100", "-i", str(self.idx)], stdout=subprocess.PIPE, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
         except Exception:
             self.proc = None
+
+    def _poll(self):
+        nv = self.nv
+        while self.run:
+            try:
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def _read(self):
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nv is not None:
+            self.run = False
+            self.t.join(timeout=1)
+            return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.mx, "samples": len(self.sm),
+                    "reasons": sorted(n for b, n in self.REASONS if self.bits & b), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.05)
@@ -96,7 +124,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
 def make_base_scans(rank: int, with_streams: bool = False):
@@ -424,7 +452,11 @@ def run_ours(args, rank, world, local_rank):
     def max_over_ranks(ms):
         return D.max_over_ranks(ms, dist, dev)
 
-    sampler = ClockSampler(local_rank)
+    try:
+        gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
+    except Exception:
+        gpu_uuid = None
+    sampler = ClockSampler(local_rank, gpu_uuid)
 
     # ---------------- leg 1: device-resident inputs -> `value`
     # The B streams are split over H groups, each on its own CUDA stream, so one group's single-CTA-per-stream
@@ -612,7 +644,7 @@ def run_ours(args, rank, world, local_rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="independent streams per GPU (default: 256 for sr_lo, 32 for the mapping workloads)")

@@ -173,6 +173,24 @@ int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xy
 int vloam_get_lm_info(vloam_lidar* h, int* info);
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
 
+/* ------------------------------------------------------------------ point-sharded solve (multi-GPU)
+ * BASELINE configs[4] names an all-reduce of the 6x6 normal equations per Gauss-Newton iteration.  Here every rank runs
+ * scan registration on the same scans, owns 1/world of each stream's correspondences (association + residuals) and the
+ * laser-odometry solve kernel sums the 28 accumulators (J'J upper triangle, J'r, cost) across ranks itself, through peer
+ * memory, once per LM evaluation: no host round trip and no separate collective launch.  Replaces what the reference
+ * does in one thread inside ceres::Solve (laser_odometry.cpp:457-463).  Every rank gets bit-identical poses.
+ *   vloam_shard_buffer / _ipc_handle : this handle's exchange buffer (device pointer / 64-byte cudaIpcMemHandle_t)
+ *   vloam_shard_open_ipc             : handles[world][64] gathered from all ranks (one process per GPU)
+ *   vloam_shard_enable               : the same with raw device pointers (several handles inside one process)
+ * All ranks must finish enabling before any of them runs vloam_laser_odometry (barrier on the caller's side); batch <= 128.
+ * vloam_shard_status: non-zero if a peer did not answer within the kernel's polling budget (results are then invalid). */
+int vloam_shard_buffer(vloam_lidar* h, void** dev_ptr, size_t* bytes);
+int vloam_shard_ipc_handle(vloam_lidar* h, unsigned char* handle64);
+int vloam_shard_open_ipc(vloam_lidar* h, int rank, int world, const unsigned char* handles);
+int vloam_shard_enable(vloam_lidar* h, int rank, int world, void* const* peer_ptrs);
+int vloam_shard_disable(vloam_lidar* h);
+int vloam_shard_status(vloam_lidar* h, int* error_bits);
+
 /* ------------------------------------------------------------------ visual odometry (depth association + residuals)
  * VisualOdometry::setUpPointCloud   visual_odometry.cpp:132-155: cam_T_velo[16], rect0_T_cam[16], P_rect0[12], row-major float */
 int vloam_vo_create(vloam_ctx* ctx, int batch, int max_points, int max_matches, vloam_vo** h);

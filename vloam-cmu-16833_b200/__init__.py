@@ -78,6 +78,9 @@ def lib():
             "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_get_input_device": [vp, pp, pp, c_ip, C.POINTER(C.c_size_t)], "vloam_input_consumed": [vp],
+            "vloam_shard_buffer": [vp, pp, C.POINTER(C.c_size_t)], "vloam_shard_ipc_handle": [vp, C.c_char_p],
+            "vloam_shard_open_ipc": [vp, C.c_int, C.c_int, C.c_char_p], "vloam_shard_enable": [vp, C.c_int, C.c_int, pp],
+            "vloam_shard_disable": [vp], "vloam_shard_status": [vp, c_ip],
             "vloam_get_stream_status": [vp, c_ip], "vloam_get_feature_counts": [vp, c_ip],
             "vloam_get_cloud": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
             "vloam_get_curvature": [vp, C.c_int, c_fp, C.c_int, c_ip],
@@ -248,6 +251,33 @@ class LidarOdometryMapping:
 
     def input_consumed(self):
         self.ctx.check(lib().vloam_input_consumed(self._h))
+
+    # -- point-sharded solve (multi-GPU): see include/vloam_b200.h "point-sharded solve"
+    def shard_buffer(self) -> int:
+        p, n = C.c_void_p(), C.c_size_t()
+        self.ctx.check(lib().vloam_shard_buffer(self._h, C.byref(p), C.byref(n)))
+        return p.value
+
+    def shard_ipc_handle(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self.ctx.check(lib().vloam_shard_ipc_handle(self._h, buf))
+        return buf.raw
+
+    def shard_open_ipc(self, rank: int, world: int, handles: bytes):
+        assert len(handles) == 64 * world
+        self.ctx.check(lib().vloam_shard_open_ipc(self._h, rank, world, handles))
+
+    def shard_enable(self, rank: int, world: int, peer_ptrs):
+        arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
+        self.ctx.check(lib().vloam_shard_enable(self._h, rank, world, arr))
+
+    def shard_disable(self):
+        self.ctx.check(lib().vloam_shard_disable(self._h))
+
+    def shard_status(self) -> int:
+        e = C.c_int(0)
+        self.ctx.check(lib().vloam_shard_status(self._h, C.byref(e)))
+        return e.value
 
     def laserOdometryIO(self, prior=None, fetch=True):
         if not fetch:

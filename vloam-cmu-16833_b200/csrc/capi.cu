@@ -91,6 +91,10 @@ struct vloam_lidar {
   long long lo_frames = 0;   // LaserOdometry::frameCount
   // input staging
   int last_stride = 3;
+  // point-sharded solve (vloam_shard_*): this rank's exchange slots, the peers' (IPC-mapped or raw), counters, error flag
+  ShardView shard;
+  ShardSlot* d_xbuf = nullptr;
+  void* ipc_open[kMaxShard] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   float* d_in[2] = {nullptr, nullptr};  // [B][cap][4], double-buffered so the next upload overlaps this scan's kernels
   int* d_n[2] = {nullptr, nullptr};     // [B]
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
@@ -219,7 +223,97 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart); cudaFree(h->grid.cursor);
   for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); }
   if (h->lm) lm_destroy(h->lm);
+  for (int r = 0; r < kMaxShard; ++r) if (h->ipc_open[r]) cudaIpcCloseMemHandle(h->ipc_open[r]);
+  cudaFree(h->d_xbuf); cudaFree(h->shard.seq); cudaFree(h->shard.error);
   delete h;
+  return VLOAM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ point-sharded solve
+static int shard_alloc(vloam_lidar* h) {
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  if (h->d_xbuf) return VLOAM_OK;
+  CU(c, cudaMalloc(&h->d_xbuf, (size_t)h->B * sizeof(ShardSlot)));
+  CU(c, cudaMalloc(&h->shard.seq, (size_t)h->B * sizeof(unsigned long long)));
+  CU(c, cudaMalloc(&h->shard.error, sizeof(int)));
+  CU(c, cudaMemset(h->d_xbuf, 0, (size_t)h->B * sizeof(ShardSlot)));
+  CU(c, cudaMemset(h->shard.seq, 0, (size_t)h->B * sizeof(unsigned long long)));
+  CU(c, cudaMemset(h->shard.error, 0, sizeof(int)));
+  return VLOAM_OK;
+}
+
+int vloam_shard_buffer(vloam_lidar* h, void** dev_ptr, size_t* bytes) {
+  if (!h || !dev_ptr) return VLOAM_E_INVALID;
+  const int r = shard_alloc(h);
+  if (r) return r;
+  *dev_ptr = h->d_xbuf;
+  if (bytes) *bytes = (size_t)h->B * sizeof(ShardSlot);
+  return VLOAM_OK;
+}
+
+int vloam_shard_ipc_handle(vloam_lidar* h, unsigned char* handle64) {
+  if (!h || !handle64) return VLOAM_E_INVALID;
+  const int r = shard_alloc(h);
+  if (r) return r;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t hd;
+  CU(h->ctx, cudaIpcGetMemHandle(&hd, h->d_xbuf));
+  std::memcpy(handle64, &hd, 64);
+  return VLOAM_OK;
+}
+
+int vloam_shard_enable(vloam_lidar* h, int rank, int world, void* const* peer_ptrs) {
+  if (!h || !peer_ptrs || world < 1 || world > kMaxShard || rank < 0 || rank >= world) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  if (h->B > 128) return fail(c, VLOAM_E_CAPACITY, "point-sharded mode keeps one resident CTA per stream: batch <= 128");
+  const int r = shard_alloc(h);
+  if (r) return r;
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (int i = 0; i < world; ++i) {
+    if (!peer_ptrs[i]) return VLOAM_E_INVALID;
+    h->shard.peer[i] = static_cast<ShardSlot*>(peer_ptrs[i]);
+  }
+  h->shard.peer[rank] = h->d_xbuf;
+  h->shard.rank = rank; h->shard.world = world;
+  CU(c, cudaMemset(h->d_xbuf, 0, (size_t)h->B * sizeof(ShardSlot)));
+  CU(c, cudaMemset(h->shard.seq, 0, (size_t)h->B * sizeof(unsigned long long)));
+  CU(c, cudaMemset(h->shard.error, 0, sizeof(int)));
+  CU(c, cudaDeviceSynchronize());
+  return VLOAM_OK;
+}
+
+int vloam_shard_open_ipc(vloam_lidar* h, int rank, int world, const unsigned char* handles) {
+  if (!h || !handles || world < 1 || world > kMaxShard || rank < 0 || rank >= world) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  const int r0 = shard_alloc(h);
+  if (r0) return r0;
+  void* ptrs[kMaxShard] = {nullptr};
+  for (int r = 0; r < world; ++r) {
+    if (r == rank) { ptrs[r] = h->d_xbuf; continue; }
+    cudaIpcMemHandle_t hd;
+    std::memcpy(&hd, handles + (size_t)r * 64, 64);
+    if (h->ipc_open[r]) { cudaIpcCloseMemHandle(h->ipc_open[r]); h->ipc_open[r] = nullptr; }
+    CU(c, cudaIpcOpenMemHandle(&h->ipc_open[r], hd, cudaIpcMemLazyEnablePeerAccess));
+    ptrs[r] = h->ipc_open[r];
+  }
+  return vloam_shard_enable(h, rank, world, ptrs);
+}
+
+int vloam_shard_disable(vloam_lidar* h) {
+  if (!h) return VLOAM_E_INVALID;
+  CU(h->ctx, cudaStreamSynchronize(h->ctx->stream));
+  h->shard.rank = 0; h->shard.world = 1;
+  return VLOAM_OK;
+}
+
+int vloam_shard_status(vloam_lidar* h, int* error_bits) {
+  if (!h || !error_bits) return VLOAM_E_INVALID;
+  *error_bits = 0;
+  if (!h->shard.error) return VLOAM_OK;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaMemcpyAsync(error_bits, h->shard.error, sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
   return VLOAM_OK;
 }
 
@@ -458,7 +552,7 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
     for (int pass = 0; pass < passes; ++pass) {
       launch_lo_pass(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
                      h->d_lessSharp[last], h->d_lessFlat[last], &h->grid, h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
-                     h->p.lo_max_iterations, pass == passes - 1, prior);
+                     h->p.lo_max_iterations, pass == passes - 1, prior, h->shard.world > 1 ? &h->shard : nullptr);
     }
   }
   // laser_odometry.cpp:511-526: the current less-sharp / less-flat clouds become "last" and are indexed for the next scan

@@ -91,6 +91,25 @@ struct LOState {
   SolveTrace trace[2];
 };
 
+
+// ---------------------------------------------------------------------------------------------
+// Point-sharded solve (SURVEY.md section 8e layout (ii), BASELINE configs[4]): every rank holds the same clouds, owns a
+// slice of each stream's correspondences and the per-iteration normal equations are summed across ranks INSIDE the
+// solve kernel through peer memory (NVLink P2P loads of the other ranks' exchange slots).  One slot per stream; a slot
+// holds two generations of the vector (parity of the sequence number) and the sequence number of the newest one.
+constexpr int kMaxShard = 8;
+struct ShardSlot {
+  double v[2][32];
+  unsigned long long flag;     // sequence number of the newest published vector
+  unsigned long long pad[7];
+};
+struct ShardView {
+  int rank = 0, world = 1;
+  ShardSlot* peer[kMaxShard] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // [rank][B]
+  unsigned long long* seq = nullptr;   // [B] local exchange counters (identical on every rank by construction)
+  int* error = nullptr;                // set when a peer did not answer in time
+};
+
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
 __device__ __forceinline__ double warp_sum(double v) {

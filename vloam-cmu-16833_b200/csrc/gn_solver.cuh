@@ -94,6 +94,63 @@ static __device__ void block_reduce28(double acc[28], double* red /*[28]*/, doub
   __syncthreads();
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// shard_allreduce: sum vec[0..n) (n <= 32, shared memory) over the ranks of a point-sharded group from inside a running
+// kernel.  Called by every thread of the CTA that owns stream b.  Each rank writes its vector into its OWN slot (local
+// stores), publishes a sequence number with release semantics, polls the other ranks' sequence numbers through peer
+// memory and then reads their vectors; the sum is formed in rank order, so every rank ends up with identical bits and
+// the redundant LM bookkeeping that follows stays in lock-step without any further communication.  A rank can be at
+// most one exchange ahead of its peers (it needs their next publication to advance), hence two generations per slot.
+constexpr long long kShardSpinLimit = 1ll << 22;   // ~1 s of polling before giving up (reported, never hangs)
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+static __device__ void shard_allreduce(const ShardView& sv, int b, double* vec, int n) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = sv.seq[b] + 1;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  ShardSlot* mine = sv.peer[sv.rank] + b;
+  if ((int)threadIdx.x < n) mine->v[seq & 1][threadIdx.x] = vec[threadIdx.x];
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    st_release_sys_u64(&mine->flag, seq);
+    sv.seq[b] = seq;
+  }
+  if (threadIdx.x < 32) {   // lane r polls rank r
+    bool ok = true;
+    const int r = threadIdx.x;
+    if (r < sv.world && r != sv.rank && *reinterpret_cast<volatile int*>(sv.error) == 0) {
+      const unsigned long long* f = &(sv.peer[r] + b)->flag;
+      long long spins = 0;
+      while (ld_acquire_sys_u64(f) < seq) {
+        __nanosleep(100);
+        if (++spins > kShardSpinLimit) { ok = false; break; }
+      }
+    }
+    if (!__all_sync(0xffffffffu, ok) && threadIdx.x == 0) atomicOr(sv.error, 1);
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < n) {
+    double s = 0.0;
+    for (int r = 0; r < sv.world; ++r) s += ld_relaxed_sys_f64(&(sv.peer[r] + b)->v[seq & 1][threadIdx.x]);
+    vec[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
 // EigenQuaternionParameterization::Plus / Euclidean plus.  x = [q(4), t(3)], delta[6].
 __device__ __forceinline__ void manifold_plus(const double x[7], const double d[6], double out[7]) {
   const double nd = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);

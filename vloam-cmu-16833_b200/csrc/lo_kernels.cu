@@ -356,7 +356,7 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
                                                      const float4* __restrict__ surfLast, int cap,
                                                      const GridHeader* __restrict__ ghdr, const int* __restrict__ cellStartAll,
                                                      const float4* __restrict__ sortedC, const float4* __restrict__ sortedS,
-                                                     int4* __restrict__ corr) {
+                                                     int4* __restrict__ corr, int shardRank, int shardWorld) {
   const int b = blockIdx.y;
   const int lane = lane_id(), g = lane / kGroup, gl = lane % kGroup, gshift = g * kGroup;
   const unsigned gmask = 0xffu << gshift;
@@ -377,7 +377,9 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
   int4 out = make_int4(-1, -1, -1, 0);
   const GridHeader& GH = ghdr[b * 2 + which];
   const int nT = GH.n;
-  if (qi < nq && nT > 0) {
+  // point-sharded: warps are dealt round-robin to the ranks; the other ranks' queries stay "no correspondence" here
+  const bool mine = shardWorld <= 1 || ((q >> 2) % shardWorld) == shardRank;
+  if (mine && qi < nq && nT > 0) {
     GridView G;
     G.minx = GH.minx; G.miny = GH.miny; G.c = GH.c; G.inv_c = GH.inv_c; G.nx = GH.nx; G.ny = GH.ny;
     const float4 p = isCorner ? sharp[(size_t)b * kMaxSharp + qi] : flat[(size_t)b * kMaxFlat + qi];
@@ -503,8 +505,9 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
   const SRHeader *__restrict__ hdrCur, const SRHeader *__restrict__ hdrLast, const LOState *__restrict__ lo,                     \
       const float4 *__restrict__ sharp, const float4 *__restrict__ flat, const float4 *__restrict__ cornerLast,                  \
       const float4 *__restrict__ surfLast, int cap, const GridHeader *__restrict__ ghdr, const int *__restrict__ cellStartAll,   \
-      const float4 *__restrict__ sortedC, const float4 *__restrict__ sortedS, int4 *__restrict__ corr
-#define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr
+      const float4 *__restrict__ sortedC, const float4 *__restrict__ sortedS, int4 *__restrict__ corr, int shardRank,          \
+      int shardWorld
+#define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr, shardRank, shardWorld
 // Two register budgets of the same body: 64 registers (4 CTAs / SM) and <= 40 (6 CTAs / SM); the kernel is latency
 // bound, so which one wins is an occupancy question settled by measurement (VLOAM_LO_ASSOC_OCC=4|5|6|8; measured on B200 at 128 streams: 334 / 314 / 293 us for 4 / 5 / 6, so 6 is the default).
 __global__ void __launch_bounds__(256) lo_associate(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
@@ -519,7 +522,7 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
                                                  const float4* __restrict__ sharp, const float4* __restrict__ flat,
                                                  const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
                                                  int cap, const int4* __restrict__ corr, int pass, int max_iterations,
-                                                 int integrate) {
+                                                 int integrate, const ShardView sv) {
   __shared__ LMShared S;
   const int b = blockIdx.x;
   LOState& st = lo[b];
@@ -581,6 +584,13 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
     np = __reduce_add_sync(0xffffffffu, np);
     if (lane_id() == 0) { atomicAdd(&s_nc, nc); atomicAdd(&s_np, np); }
     __syncthreads();
+    if (sv.world > 1) {   // point-sharded: this rank only holds its slice of the correspondences
+      if (threadIdx.x == 0) { S.red[0] = (double)s_nc; S.red[1] = (double)s_np; }
+      __syncthreads();
+      shard_allreduce(sv, b, S.red, 2);
+      if (threadIdx.x == 0) { s_nc = (int)S.red[0]; s_np = (int)S.red[1]; }
+      __syncthreads();
+    }
     if (threadIdx.x == 0) { st.corner_correspondence = s_nc; st.plane_correspondence = s_np; tr->n_corner = s_nc; tr->n_plane = s_np; }
   }
 
@@ -608,6 +618,7 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
       }
     }
     block_reduce28(acc, S.red, S.scratch);
+    if (sv.world > 1) shard_allreduce(sv, b, S.red, 28);   // J'J, J'r and the cost summed over the ranks, in the kernel
   };
 
   lm_solve_block(S, tr, max_iterations, false, evaluate);
@@ -686,11 +697,13 @@ constexpr int kLoSolveDynSmem = (kMaxSharp + kMaxFlat) * (4 * (int)sizeof(double
 
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
-                    const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior) {
+                    const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
+                    const ShardView* shard) {
+  const ShardView sv = shard ? *shard : ShardView();
   const cudaError_t attr = cudaFuncSetAttribute(lo_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
   (void)attr;
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
-  if (lo_use_brute())
+  if (lo_use_brute() && sv.world <= 1)
     VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
                                                   hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
   else
@@ -700,22 +713,22 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
     if (occ >= 8)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ8<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
     else if (occ >= 6)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ6<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
     else if (occ == 5)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ5<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
     else
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
   }
   VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
-                                                               max_iterations, integrate));
+                                                               max_iterations, integrate, sv));
 }
 
 }  // namespace vb

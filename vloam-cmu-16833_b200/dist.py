@@ -65,3 +65,24 @@ def allreduce_normal_equations(buf, dist=None):
     assert buf.shape[-1] == 28
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     return buf
+
+
+def gather_ipc_handles(local_handle: bytes, dist, device=None) -> bytes:
+    """All-gather the 64-byte cudaIpcMemHandle_t of every rank's exchange buffer -> world * 64 bytes, rank order.
+    Works over NCCL (device tensors) and gloo (CPU tensors, used by the CPU test)."""
+    import torch
+    assert len(local_handle) == 64
+    t = torch.tensor(list(local_handle), dtype=torch.uint8, device=device)
+    out = [torch.empty_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(out, t)
+    return b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+
+
+def enable_point_sharding(lom, dist, device=None):
+    """Switch a LidarOdometryMapping handle to the point-sharded solve (SURVEY.md section 8e layout (ii)): every rank must
+    hold the same streams and feed the same scans; afterwards laserOdometryIO associates and accumulates only this rank's
+    slice of the correspondences and the solve kernel sums the normal equations across ranks through peer memory."""
+    rank, world = dist.get_rank(), dist.get_world_size()
+    handles = gather_ipc_handles(lom.shard_ipc_handle(), dist, device)
+    lom.shard_open_ipc(rank, world, handles)
+    dist.barrier()          # nobody starts exchanging before every rank has mapped and cleared its slots
