@@ -328,7 +328,9 @@ def run_ours(args, rank, world, local_rank):
     do_vo = args.workload == "vloam"
     do_map = args.workload in ("sr_lo_lm", "vloam")
     cap = N_RINGS * N_COLS
-    seqs, scan_streams = make_base_scans(rank, with_streams=True)
+    point = args.parallelism == "point" and world > 1
+    # point-sharded: every rank replays the SAME streams (rank-independent seeds) and owns a slice of their correspondences
+    seqs, scan_streams = make_base_scans(0 if point else rank, with_streams=True)
 
     # pools: POOL_SCANS tensors of [B, cap, 3]; stream b replays base sequence b % N_BASE
     host_pool, dev_pool = [], []
@@ -461,7 +463,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- leg 1: device-resident inputs -> `value`
     # The B streams are split over H groups, each on its own CUDA stream, so one group's single-CTA-per-stream
     # kernels (the LM solves, ring-end scans) overlap the other groups' wide kernels instead of idling the SMs.
-    H = max(1, min(args.handles, B))
+    H = 1 if point else max(1, min(args.handles, B))
     bounds = [(B * h) // H for h in range(H + 1)]
     streams = [stream] + [torch.cuda.Stream(device=dev) for _ in range(H - 1)]
     ctxs = [ctx] + [V.Context(device=local_rank, cuda_stream=s_.cuda_stream) for s_ in streams[1:]]
@@ -470,6 +472,9 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(streams[h]):
             groups.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
     loms = [g.lom for g in groups]
+    from vloam_b200 import dist as D
+    if point:
+        D.enable_point_sharding(groups[0].lom, dist, dev)
 
     def step_dev(i, serial=False):
         for h in range(H):
@@ -519,7 +524,7 @@ def run_ours(args, rank, world, local_rank):
                 a = ktimes.get(kname, (0.0, 0))
                 ktimes[kname] = (a[0] + ms_k, a[1] + n_k)
             c_.enable_timing(False)
-    value = world * B * args.steps / (ms_dev * 1e-3)
+    value = (1 if point else world) * B * args.steps / (ms_dev * 1e-3)
 
     if args.legs == "device":
         if rank == 0:
@@ -532,6 +537,9 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- leg 2: host buffers through the public API -> `e2e`
     g2 = Group(ctx, 0, B)
+    if point:
+        groups[0].lom.shard_disable()
+        D.enable_point_sharding(g2.lom, dist, dev)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
@@ -549,9 +557,10 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         t_host1 = time.perf_counter()
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0)))
-    e2e_value = world * B * args.steps / (ms_e2e * 1e-3)
+    e2e_value = (1 if point else world) * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
     d2h = int(B * 16 * 8)
+    shard_err = g2.lom.shard_status() if point else 0
     # same inputs, same number of steps -> both legs must end on identical poses
     same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
 
@@ -620,12 +629,14 @@ def run_ours(args, rank, world, local_rank):
     line = {
         "metric": "scans/sec (HDL-64, 64x2048 pts) " + WORKLOAD_NAME[args.workload][0],
         "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if point else "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
         "config": {"workload": WORKLOAD_NAME[args.workload][1],
                    "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
                    "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
-                   "parallelism": f"stream-sharded x{world} (no data-path collective)"},
+                   "parallelism": (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
+                                   f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}") if point
+                                  else f"stream-sharded x{world} (no data-path collective)"},
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same},
         "gpu_launches": int(launches),
@@ -652,6 +663,9 @@ def main():
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
     ap.add_argument("--handles", type=int, default=2, help="split the batch over this many handles / CUDA streams (device leg)")
+    ap.add_argument("--parallelism", default="stream", choices=["stream", "point"],
+                    help="N > 1: stream = independent streams per rank (weak scaling, headline); point = every rank holds all "
+                         "streams and a slice of each stream's correspondences, normal equations summed in-kernel over NVLink")
     ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
     if args.batch <= 0:

@@ -28,6 +28,11 @@ def _worker(rank, world, port, q):
     # point-sharded exchange: each rank holds partial normal equations of 3 streams
     part = torch.full((3, 28), float(rank + 1), dtype=torch.float64)
     D.allreduce_normal_equations(part, dist)
+    # handle exchange of the point-sharded mode: 64 opaque bytes per rank, gathered in rank order
+    handles = D.gather_ipc_handles(bytes([rank * 16 + (i % 16) for i in range(64)]), dist)
+    assert len(handles) == 64 * world
+    for rr in range(world):
+        assert handles[64 * rr: 64 * rr + 64] == bytes([rr * 16 + (i % 16) for i in range(64)])
     dist.barrier()
     q.put((rank, mine, value, mx, part.sum().item()))
     dist.destroy_process_group()

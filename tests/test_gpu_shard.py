@@ -51,6 +51,8 @@ def test_two_rank_point_sharded_odometry_matches_unsharded(synth, oracle):
         assert t0["n_plane"] == t1["n_plane"] == tr["n_plane"]          # the counts are exchanged too
     for h in (r0, r1, ref):
         h.close()
+    for c in (c0, c1, c2):
+        c.close()
 
 
 def test_unanswered_peer_is_reported_not_hung(synth):
@@ -68,4 +70,4 @@ def test_unanswered_peer_is_reported_not_hung(synth):
         a.laserOdometryIO(fetch=False)
     a.ctx.synchronize()
     assert a.shard_status() != 0
-    a.close(); b.close()
+    b.close(); a.close()        # a owns the context b borrows

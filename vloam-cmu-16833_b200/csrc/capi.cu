@@ -373,6 +373,7 @@ int vloam_lidar_reset(vloam_lidar* h) {
 // ------------------------------------------------------------------------------------------------ scan registration
 static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
   vloam_ctx* c = h->ctx;
+  (void)cudaGetLastError();   // a stale, unrelated error must not be blamed on the launches below
   h->frame++;
   h->lo_done_for_frame = false;
   const int cur = h->cur();
@@ -543,6 +544,7 @@ int vloam_get_feature_indices(vloam_lidar* h, int stream, int which, int* out, i
 // ------------------------------------------------------------------------------------------------ laser odometry
 static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
   vloam_ctx* c = h->ctx;
+  (void)cudaGetLastError();
   if (h->frame < 0) return fail(c, VLOAM_E_STATE, "laser odometry before scan registration");
   if (h->lo_done_for_frame) return fail(c, VLOAM_E_STATE, "laser odometry already run for this scan");
   const int cur = h->cur(), last = cur ^ 1;

@@ -791,6 +791,7 @@ void lm_reset(LMDevice* lm) { if (lm) lm->reset_valid = true; }
 
 cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const float4* cornerLast, const float4* surfLast,
                    const LOState* lo, bool skip_frame) {
+  (void)cudaGetLastError();
   cudaError_t e = lm_alloc(lm, st);
   if (e != cudaSuccess) return e;
   Profiler* prof = lm->prof;

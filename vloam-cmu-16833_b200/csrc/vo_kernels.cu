@@ -535,6 +535,7 @@ static int vo_run_cloud(vloam_vo* h, const float* xyz_dev, const int* n_dev, int
   if (h->count < 0) return vfail(c, VLOAM_E_STATE, "vloam_vo_process_cloud before vloam_vo_reset");
   const int s = h->slot();
   cudaStream_t st = c->stream;
+  (void)cudaGetLastError();   // a stale, unrelated error must not be blamed on the launches below
   VB_LAUNCH(&c->prof, K_VO_PROJECT, st, vo_project<<<dim3(h->cap / 256, h->B), 256, 0, st>>>(xyz_dev, stride, slab_points * (size_t)stride, n_dev, h->calib, h->cap,
                                                                                            h->d_uvd, h->kA, h->vA));
   VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_sort<<<h->B, 1024, 0, st>>>(n_dev, h->cap, h->kA, h->vA, h->kB, h->vB));
@@ -602,6 +603,7 @@ static int vo_enqueue_solve(vloam_vo* h, const float* prev_dev, const float* cur
                             int remove_VO_outlier, int max_iterations) {
   vloam_ctx* c = h->ctx;
   cudaStream_t st = c->stream;
+  (void)cudaGetLastError();
   const int sp = 1 - h->slot();  // depth of the PREVIOUS frame's cloud is used (depth0, visual_odometry.cpp:316)
   VB_LAUNCH(&c->prof, K_VO_QUERY, st, vo_build_residuals<<<dim3((h->maxM + 127) / 128, h->B), 128, 0, st>>>(prev_dev, curr_dev, nm_dev, h->maxM, h->calib,
                                                                                                           remove_VO_outlier, h->bx[sp], h->by[sp], h->bd[sp],
