@@ -323,6 +323,8 @@ def run_ours(args, rank, world, local_rank):
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
+        if not os.environ.get("VLOAM_KEEP_NCCL_DEBUG"):
+            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, which carries exactly one JSON line
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     do_vo = args.workload == "vloam"
