@@ -610,9 +610,20 @@ def run_ours(args, rank, world, local_rank):
     for v in kern.values():
         v["share"] = v["ms_total"] / ksum
     dom = max(kern, key=lambda k: kern[k]["ms_total"])
+    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/ncu_traffic.json, per launch
+    # and per stream there; scaled to this run's streams per launch)
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
+            tj = json.load(f)
+        traffic = tj["kernels"][dom]["dram_bytes_per_launch_per_stream"] * (B / H)
+    except Exception:
+        traffic = None
     roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
-            "frac": (kern[dom]["gbs"] or 0.0) / peaks["hbm_gbs"], "traffic": None, "peak_source": peak_kind,
-            "note": "achieved = algorithmic bytes per launch / CUDA-event duration; traffic (ncu dram bytes) in profiles/"}
+            "frac": (kern[dom]["gbs"] or 0.0) / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
+            "alg_bytes_per_launch": kern[dom]["alg_bytes_per_launch"],
+            "note": "achieved = algorithmic bytes per launch / CUDA-event duration; traffic = ncu dram read+write bytes per launch "
+                    "(profiles/ncu_traffic.json, from profiles/r01_ncu_full_summary.md)"}
     curv = kern.get("sr_curvature")
 
     # ---------------- CPU baseline: oracle, 1 thread, bounded sample

@@ -1,48 +1,97 @@
 """Turns the ncu artefacts brought back in gpurun_out/ into the small summaries committed here.
-usage: python profiles/summarize.py gpurun_out/r01_launches.csv gpurun_out/r01_full.ncu-rep r01"""
+usage: python profiles/summarize.py LAUNCHES.csv FULL.ncu-rep TAG STREAMS_PER_LAUNCH
+writes profiles/TAG_ncu_launches_summary.md, profiles/TAG_ncu_full_summary.md and profiles/ncu_traffic.json
+(DRAM bytes per launch and per stream of every kernel, read by bench.py for `roofline.traffic`)."""
 import collections
 import csv
+import json
 import subprocess
 import sys
 
-launch_csv, rep, tag = sys.argv[1:4]
+launch_csv, rep, tag, streams = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
+
+
+def base(name):
+    return name.split("(")[0].replace("void ", "").replace("vb::", "").split("<")[0].replace("_occ6", "").replace("_occ5", "").replace("_occ8", "")
+
+
 # ---- launch list: per-kernel time share (cold-cache, serialised: compare shares, not absolutes)
 rows = []
 with open(launch_csv) as f:
     for r in csv.reader(l for l in f if not l.startswith("==")):
         rows.append(r)
 hdr = rows[0]
-ki, vi = hdr.index("Kernel Name"), hdr.index("Metric Value")
+ki, vi, mi, ui = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Name"), hdr.index("Metric Unit")
 agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows[1:]:
-    if len(r) <= vi or r[hdr.index("Metric Name")] != "gpu__time_duration.sum":
+    if len(r) <= vi or r[mi] != "gpu__time_duration.sum":
         continue
-    name = r[ki].split("(")[0].replace("void ", "")
-    agg[name][0] += 1
-    agg[name][1] += float(r[vi].replace(",", "")) / (1000.0 if r[hdr.index("Metric Unit")] in ("ns", "nsecond") else 1.0)
+    us = float(r[vi].replace(",", ""))
+    us = us / 1000.0 if r[ui] in ("ns", "nsecond") else us * (1000.0 if r[ui] in ("ms", "msecond") else 1.0)
+    a = agg[base(r[ki])]
+    a[0] += 1
+    a[1] += us
 tot = sum(v[1] for v in agg.values())
 with open(f"profiles/{tag}_ncu_launches_summary.md", "w") as out:
-    out.write(f"# ncu launch list ({tag}): `ncu --metrics gpu__time_duration.sum --clock-control none` over bench.py --batch 128\n\n")
-    out.write("Per-launch times under ncu are cold-cache and serialised; the SHARE is what must agree with bench.py's CUDA-event shares.\n\n")
-    out.write("| kernel | launches | total us | share |\n|---|---|---|---|\n")
+    out.write(f"# ncu launch list ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over "
+              f"`bench.py --legs device --batch {streams} --handles 1` (scanRegistration + laserOdometry).\n"
+              "Per-launch times under ncu are cold-cache and serialised; the SHARE is what must agree with the CUDA-event shares in\n"
+              "`profiles/r01_bench_default.json` (`kernels.*.share`).\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.write(f"| {k} | {n} | {us:.1f} | {us / tot:.3f} |\n")
+
 # ---- full capture: DRAM traffic and the main limiter per kernel
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rr = list(csv.reader(raw.splitlines()))
 h, units = rr[0], rr[1]
 idx = {n: i for i, n in enumerate(h)}
-want = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
-        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
-        "smsp__inst_executed.sum", "smsp__issue_active.avg.per_cycle_active", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
+
+
+def val(r, name):
+    try:
+        v = float(r[idx[name]].replace(",", ""))
+    except (KeyError, ValueError):
+        return None
+    u = units[idx[name]]
+    return v * {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(u, 1.0) if "byte" in u else v
+
+
+cols = [("gpu__time_duration.sum", "time us"), ("dram__bytes_read.sum", "dram read MB"), ("dram__bytes_write.sum", "dram write MB"),
+        ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram % of ncu peak"),
+        ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"), ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+        ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"), ("launch__registers_per_thread", "regs"),
+        ("smsp__inst_executed.sum", "warp instr"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %")]
+traffic = {}
 with open(f"profiles/{tag}_ncu_full_summary.md", "w") as out:
-    out.write(f"# ncu --set full ({tag}), bench.py --batch 128, one launch per kernel\n\n| kernel | " + " | ".join(w.split(".")[0].replace("__", " ") for w in want) + " |\n|---|" + "---|" * len(want) + "\n")
-    seen = set()
+    out.write(f"# ncu --set full ({tag})\n\nOne scan of `bench.py --legs device --batch {streams} --handles 1` (second scan of the run, so laserOdometry "
+              "is active); one row per launch.\nDRAM bytes are per launch (all streams of the launch).\n\n| kernel | "
+              + " | ".join(c[1] for c in cols) + " |\n|---|" + "---|" * len(cols) + "\n")
     for r in rr[2:]:
-        name = r[idx["Kernel Name"]].split("(")[0].replace("void ", "")
-        if name in seen:
-            continue
-        seen.add(name)
-        out.write(f"| {name} | " + " | ".join(f"{r[idx[w]]} {units[idx[w]]}" if w in idx else "-" for w in want) + " |\n")
+        name = base(r[idx["Kernel Name"]])
+        cells = []
+        for m, label in cols:
+            v = val(r, m)
+            if v is None:
+                cells.append("-")
+            elif "MB" in label:
+                cells.append(f"{v / 1e6:.1f}")
+            elif label == "time us":
+                u = units[idx[m]]
+                cells.append(f"{v / 1000.0 if u.startswith('n') else v:.1f}")
+            elif label in ("regs", "warp instr"):
+                cells.append(f"{int(v)}")
+            else:
+                cells.append(f"{v:.1f}")
+        out.write(f"| {name} | " + " | ".join(cells) + " |\n")
+        rd, wr = val(r, "dram__bytes_read.sum") or 0.0, val(r, "dram__bytes_write.sum") or 0.0
+        t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0})
+        t["launches"] += 1
+        t["dram_bytes"] += rd + wr
+for k, t in traffic.items():
+    t["dram_bytes_per_launch"] = t["dram_bytes"] / t["launches"]
+    t["dram_bytes_per_launch_per_stream"] = t["dram_bytes_per_launch"] / streams
+    del t["dram_bytes"]
+json.dump({"source": f"profiles/{tag}_ncu_full_summary.md", "streams_per_launch": streams, "kernels": traffic},
+          open("profiles/ncu_traffic.json", "w"), indent=1)
 print(open(f"profiles/{tag}_ncu_full_summary.md").read())
 print(open(f"profiles/{tag}_ncu_launches_summary.md").read())
