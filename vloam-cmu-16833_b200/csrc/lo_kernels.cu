@@ -118,7 +118,7 @@ __global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __rest
     }
     best = warp_min_u64(best);
     if (nT > 0 && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // DISTANCE_SQ_THRESHOLD (:272)
-      const int closest = (int)((unsigned)best >> 6);
+      const int closest = (int)((unsigned)best >> 12);
       const int id = (int)((unsigned)best & 63u);  // closestPointScanID = int(intensity) of the closest point (:275)
       unsigned long long k2, k3;
       window_walk_literal(T, nT, closest, id, isCorner, sx, sy, sz, k2, k3);
@@ -146,10 +146,12 @@ __global__ void __launch_bounds__(256) lo_associate_brute(const SRHeader* __rest
 // Distances are the same float expression the brute-force kernel uses and ties break on the original index, so
 // both kernels return identical results.
 __device__ __forceinline__ int cell_coord(float v, float mn, float inv_c) { return (int)floorf((v - mn) * inv_c); }
-// Column-sorted copies keep (original index << 6 | int(intensity)) in the w lane; int(intensity) is in [0, 63].
-__device__ __forceinline__ int pack_index_ring(int j, int rid) { return (j << 6) | (rid & 63); }
-__device__ __forceinline__ int packed_index(float w) { return (int)((unsigned)__float_as_int(w) >> 6); }
+// Column-sorted copies keep (original index << 12 | true ring << 6 | int(intensity)) in the w lane; both ring fields are in
+// [0, 63].  int(intensity) is the "scan id" the reference's window tests read; the true ring orders a column (below).
+__device__ __forceinline__ int pack_index_ring(int j, int trueRing, int rid) { return (j << 12) | ((trueRing & 63) << 6) | (rid & 63); }
+__device__ __forceinline__ int packed_index(float w) { return (int)((unsigned)__float_as_int(w) >> 12); }
 __device__ __forceinline__ int packed_ring(float w) { return __float_as_int(w) & 63; }
+__device__ __forceinline__ int packed_pair(float w) { return (__float_as_int(w) >> 7) & 31; }   // true ring / 2
 
 // lo_build_grid: grid (2, B), block 1024, dynamic smem = (kGridCap + 1) ints.  blockIdx.x: 0 = corner cloud, 1 = surf.
 // Counting sort by column with the column table in shared memory (a global-memory table was measured 14x slower).
@@ -247,15 +249,28 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   for (int i = c0; i < c1; ++i) { const int t = cells[i]; cells[i] = run; cs[i] = run; run += t; }
   if (tid == 0) { cells[ncells] = n; cs[ncells] = n; }
   __syncthreads();
-  // ---- scatter (order inside a column is arbitrary; queries break ties on the original index)
-  for (int j = tid; j < n; j += 1024) {
+  // ---- scatter, one pair of rings at a time: inside a column the points end up grouped by ring pair in ascending
+  // order (arbitrary inside a pair), so the ring-window pass of the search can jump to its rings instead of reading the
+  // whole column.  The cloud is ring-major, so a ring pair is a contiguous index range; w carries the original index
+  // (tie-breaks, result), the true ring and int(intensity), the "scan id" of the reference's window tests (:275, :285 ...).
+  for (int pr = 0; pr < kMaxRings / 2; ++pr) {
+    const int j0 = s_ringStart[2 * pr], jm = s_ringStart[2 * pr + 1], j1 = s_ringStart[2 * pr + 2];
+    if (j1 <= j0) continue;                     // uniform: empty pair
+    for (int j = j0 + tid; j < j1; j += 1024) {
+      const float4 p = T[j];
+      const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
+      const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
+      const int pos = atomicAdd(&cells[iy * nx + ix], 1);
+      S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, j >= jm ? 2 * pr + 1 : 2 * pr, (int)p.w)));
+    }
+    __syncthreads();
+  }
+  for (int j = s_ringStart[kMaxRings] + tid; j < n; j += 1024) {   // points past the last ring offset (foreign clouds only)
     const float4 p = T[j];
     const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
     const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
     const int pos = atomicAdd(&cells[iy * nx + ix], 1);
-    // w carries what the search needs besides the position: the original index (tie-breaks, result) and
-    // int(intensity), the "scan id" the window tests of the reference read (:275, :285, :300 ...)
-    S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, (int)p.w)));
+    S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, kMaxRings - 1, (int)p.w)));
   }
   if (tid == 0) {
     G.minx = minx; G.miny = miny; G.c = c; G.inv_c = inv_c; G.nx = nx; G.ny = ny; G.n = n; G.ringsOk = s_mono;
@@ -281,10 +296,11 @@ struct GridView {  // the GridHeader fields the search needs, in registers
   int nx, ny;
 };
 // Visit shell k >= 2 (the outer ring of the (2k+1)^2 column block): rows qy-k and qy+k in full, the two end columns
-// of the rows in between.  visit(t) is called for every sorted-array position t of every column in the shell.
+// of the rows in between.  range(aa, bb) is called (by the whole group) for every run [aa, bb) of sorted-array positions
+// the shell is made of.
 template <typename F>
 __device__ __forceinline__ void group_visit_shell(const GridView& G, const int* __restrict__ cs, int qx, int qy, int k, unsigned gmask,
-                                                  int gl, F visit) {
+                                                  int gl, F range) {
   const int nseg = 4 * k;
   for (int s0 = 0; s0 < nseg; s0 += kGroup) {
     int a = 0, bnd = 0;
@@ -302,7 +318,7 @@ __device__ __forceinline__ void group_visit_shell(const GridView& G, const int* 
     const int cnt = min(kGroup, nseg - s0);
     for (int sidx = 0; sidx < cnt; ++sidx) {
       const int aa = __shfl_sync(gmask, a, sidx, kGroup), bb = __shfl_sync(gmask, bnd, sidx, kGroup);
-      for (int t = aa + gl; t < bb; t += kGroup) visit(t);
+      range(aa, bb);
     }
   }
 }
@@ -312,10 +328,10 @@ __device__ __forceinline__ void group_visit_shell(const GridView& G, const int* 
 // the largest squared distance that could still improve a result.  `limit()` must be uniform across the group.
 template <typename F, typename L>
 __device__ __forceinline__ void group_visit_block_best_first(const GridView& G, const int* __restrict__ cs, float sx, float sy, int qx, int qy,
-                                                             unsigned gmask, int gshift, int gl, F visit, L limit) {
+                                                             unsigned gmask, int gshift, int gl, F range, L limit) {
   if (qx >= 0 && qx < G.nx && qy >= 0 && qy < G.ny) {
     const int a0 = cs[qy * G.nx + qx], b0 = cs[qy * G.nx + qx + 1];
-    for (int t = a0 + gl; t < b0; t += kGroup) visit(t);
+    range(a0, b0);
   }
   int a = 0, bnd = 0;
   unsigned lbBits = 0xffffffffu;
@@ -338,7 +354,7 @@ __device__ __forceinline__ void group_visit_block_best_first(const GridView& G, 
     const int src = __ffs(__ballot_sync(gmask, lbBits == m) >> gshift) - 1;
     const int aa = __shfl_sync(gmask, a, src, kGroup), bb = __shfl_sync(gmask, bnd, src, kGroup);
     if (gl == src) lbBits = 0xffffffffu;
-    for (int t = aa + gl; t < bb; t += kGroup) visit(t);
+    range(aa, bb);
   }
 }
 // Radius within which the visited block [qx-k, qx+k] x [qy-k, qy+k] is guaranteed complete (<= 0 if none).
@@ -395,11 +411,13 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
     const int qx = cell_coord(sx, G.minx, G.inv_c), qy = cell_coord(sy, G.miny, G.inv_c);
     // ---- phase 1: exact nearest neighbour (laser_odometry.cpp:269 / :356)
     unsigned long long best = 0xffffffffffffffffull;
-    auto visit1 = [&](int t) {
-      const float4 tp = S[t];
-      const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-      const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
-      best = key < best ? key : best;   // order: distance, then original index (the ring bits sit below the index)
+    auto visit1 = [&](int aa, int bb) {
+      for (int t = aa + gl; t < bb; t += kGroup) {
+        const float4 tp = S[t];
+        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
+        best = key < best ? key : best;   // order: distance, then original index (the ring bits sit below the index)
+      }
     };
     // a point at exactly the same distance could still win the index tie-break: the walk only stops on `>`.
     // (no candidate yet: the reduced bits are 0xffffffff = NaN, every comparison is false, the walk continues)
@@ -413,7 +431,7 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
       if (best != 0xffffffffffffffffull && R > 0.f && __uint_as_float((unsigned)(best >> 32)) <= R * R) break;
     }
     if (best != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(best >> 32)) < 25.0) {  // :272
-      const int closest = (int)((unsigned)best >> 6);
+      const int closest = (int)((unsigned)best >> 12);
       const int id = (int)((unsigned)best & 63u);  // closestPointScanID = int(intensity) of the closest point (:275)
       unsigned long long k2 = 0xffffffffffffffffull, k3 = 0xffffffffffffffffull;
       if (!GH.ringsOk) {
@@ -452,8 +470,11 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
         int hi_j = nT, lo_j = 0;
         if (id + 3 <= kMaxRings - 1) hi_j = min(GH.firstFull[id + 3], GH.ringStart[min(id + 4, kMaxRings)]);
         if (id - 2 >= 0) lo_j = max(GH.lastLow[id - 2], GH.ringStart[id - 2] - 1) + 1;
-        auto visit2 = [&](int t) {
-          const float4 tp = S[t];
+        // Columns are ordered by ring pair (true ring / 2).  [lo_j, hi_j) only holds rings id-2 .. id+3, so a column
+        // contributes the sub-range of pairs [pairLo, pairHi]: found by an 8-way probing lower bound (one probe per
+        // lane), then walked until the first pair beyond pairHi.
+        const int pairLo = max(id - 2, 0) >> 1, pairHi = min(id + 3, kMaxRings - 1) >> 1;
+        auto consider = [&](const float4 tp) {
           const int j = packed_index(tp.w);
           if (j < lo_j || j >= hi_j || j == closest) return;
           const float d = sqdist_f(tp.x, tp.y, tp.z, sx, sy, sz);
@@ -466,6 +487,32 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
           if (isCorner) { if (!classA) k2 = key < k2 ? key : k2; }
           else if (classA) k2 = key < k2 ? key : k2;
           else k3 = key < k3 ? key : k3;
+        };
+        // one column [aa, bb): jump to the window's ring pairs, stop after them
+        auto visit2 = [&](int aa, int bb) {
+          int lo = aa, hi = bb;
+          while (hi - lo > kGroup) {
+            const int step = (hi - lo + kGroup) / (kGroup + 1);
+            const int pidx = lo + (gl + 1) * step - 1;
+            const bool ge = pidx >= hi || packed_pair(S[pidx].w) >= pairLo;
+            const unsigned m = (__ballot_sync(gmask, ge) >> gshift) & 0xffu;
+            if (m == 0u) { lo = min(lo + kGroup * step, hi); }
+            else { const int f = __ffs(m) - 1; hi = min(lo + (f + 1) * step, hi); lo += f * step; }
+          }
+          for (int base = lo; base < bb; base += kGroup) {
+            const int t = base + gl;
+            bool beyond = false;
+            if (t < bb) {
+              const float4 tp = S[t];
+              beyond = packed_pair(tp.w) > pairHi;
+              consider(tp);
+            }
+            if (__ballot_sync(gmask, beyond) & gmask) break;   // sorted by pair: nothing of interest further on
+          }
+        };
+        // a run of several columns (shell rows): not ordered as a whole, every point is tested
+        auto visit2_run = [&](int aa, int bb) {
+          for (int t = aa + gl; t < bb; t += kGroup) consider(S[t]);
         };
         // a column can still matter while its bound is below the worst of the needed classes (25 = none found yet)
         group_visit_block_best_first(G, cs, sx, sy, qx, qy, gmask, gshift, gl, visit2, [&]() {
@@ -480,7 +527,7 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
         k2 = group_min_u64(gmask, k2);
         k3 = group_min_u64(gmask, k3);
         for (int k = 1;; ++k) {
-          if (k > 1) { group_visit_shell(G, cs, qx, qy, k, gmask, gl, visit2); k2 = group_min_u64(gmask, k2); k3 = group_min_u64(gmask, k3); }
+          if (k > 1) { group_visit_shell(G, cs, qx, qy, k, gmask, gl, visit2_run); k2 = group_min_u64(gmask, k2); k3 = group_min_u64(gmask, k3); }
           const float R = grid_safe_radius(G, sx, sy, qx, qy, k);
           if (R >= 5.0f) break;
           if (R > 0.f) {
