@@ -307,6 +307,7 @@ def algorithmic_bytes(kernel, c):
         "lm_solve": c.get("S", 0) * 80,
         "lm_insert": c.get("S", 0) * 48,
         "lm_refilter": c.get("M", 0) * (16 * 4 + 20 * 4) // 3,
+        "lm_place": 0,
     }
     return table.get(kernel, 0)
 

@@ -99,6 +99,8 @@ typedef struct vloam_lidar_params {
   int lm_outer_passes;             /* 2                     laser_mapping.cpp:458 */
   int lm_max_iterations;           /* 4                     laser_mapping.cpp:612 */
   int map_capacity_points;         /* capacity of the rolling map per stream and per feature kind */
+  int debug_keep_submap;           /* 1: keep a copy of laserCloudCornerFromMap / SurfFromMap (laser_mapping.cpp:422-428) of the
+                                      last scan for vloam_get_cloud(VLOAM_CLOUD_*_MAP); costs one sub-map copy per scan */
 } vloam_lidar_params;
 
 /* Fills the reference's KITTI HDL-64 launch-file values. */
@@ -172,6 +174,11 @@ int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xy
 /* info[batch][8] = cenWidth, cenHeight, cenDepth, validNum, cornerFromMapNum, surfFromMapNum, cornerStackNum, surfStackNum */
 int vloam_get_lm_info(vloam_lidar* h, int* info);
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
+/* Map storage read-out, stats[batch][2][8] per stream and feature kind (0 corner, 1 surf): points in the map, high-water
+ * mark of the slab pool, pool index, non-empty cubes, cubes known to be fixed points of their voxel filter (skipped by
+ * the per-scan re-filter of laser_mapping.cpp:689-702 until they receive a point), cubes rewritten by the last scan,
+ * re-packs so far, slab capacity in use. */
+int vloam_get_map_stats(vloam_lidar* h, int* stats);
 
 /* ------------------------------------------------------------------ point-sharded solve (multi-GPU)
  * BASELINE configs[4] names an all-reduce of the 6x6 normal equations per Gauss-Newton iteration.  Here every rank runs

@@ -23,8 +23,8 @@ def _same_xyz(a, b, name):
         assert np.max(np.abs(a[:, 3] - b[:, 3])) < 0.14, f"{name}: intensity"
 
 
-def _run_sequence(V, oracle, scans, check_cubes=True):
-    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18)
+def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None):
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=map_capacity, debug_keep_submap=1)
     pipe = oracle.Pipeline()
     worst_t = 0.0
     for k, scan in enumerate(scans):
@@ -67,6 +67,12 @@ def _run_sequence(V, oracle, scans, check_cubes=True):
                         _same_xyz(lom.map_get_cube(kind, cube), pipe.lm.cube(kind, cube), f"scan {k} cube {cube} kind {kind}")
                         occupied += n_or > 0
             assert occupied > 0
+        ms = lom.map_stats()[0]
+        for kind in (0, 1):      # storage bookkeeping: the tables account for exactly the oracle's map
+            assert ms[kind, 0] == sum(pipe.lm.cube_count(kind, c) for c in range(4851))
+            assert ms[kind, 0] <= ms[kind, 7] <= ms[kind, 1] <= map_capacity
+        if stats_out is not None:
+            stats_out.append(ms.copy())
     lom.close()
     return worst_t
 
@@ -79,12 +85,28 @@ def test_laser_mapping_sequence(synth, oracle):
     print("max |t_w_curr - oracle| =", worst)
 
 
+def test_laser_mapping_incremental_refilter_and_repack(synth, oracle):
+    """The per-scan re-filter of every valid cube (laser_mapping.cpp:689-702) is skipped for cubes that are fixed points
+    of their voxel filter and received nothing; rewritten cubes keep their slab, move to a fresh one or trigger a re-pack
+    of the whole map into the other pool.  A tight map capacity forces all three placements; the map must stay identical
+    to the oracle's (which re-filters everything, like the reference) cube by cube after every scan."""
+    import vloam_b200 as V
+    s = synth.ScanStream(31, n_cols=1024)
+    scans = [s.scan(k) for k in range(8)]
+    stats = []
+    _run_sequence(V, oracle, scans, map_capacity=9000, stats_out=stats)
+    st = np.stack(stats)                                  # (scan, kind, 8)
+    assert st[-1, :, 6].max() >= 1, st[:, :, 6]           # at least one re-pack happened
+    assert (st[1:, :, 4] > 0).any()                       # some cubes were found in fixed-point form ...
+    assert (st[2:, :, 5] < st[2:, :, 3]).any(), st[:, :, [3, 5]]   # ... so later scans rewrote fewer cubes than the map holds
+
+
 def test_laser_mapping_seeded_map_and_cube_shift(synth, oracle):
     """Map cubes seeded through vloam_map_set_cube; a large odometry offset forces the rolling grid to shift."""
     import vloam_b200 as V
     s = synth.ScanStream(32, n_cols=512)
     scans = [s.scan(k) for k in range(3)]
-    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18)
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18, debug_keep_submap=1)
     pipe = oracle.Pipeline()
     # seed one far-away cube in both maps: it must survive the grid shift at its shifted index or be dropped identically
     rng = np.random.default_rng(0)

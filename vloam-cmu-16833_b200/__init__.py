@@ -44,7 +44,7 @@ class LidarParams(C.Structure):
                 ("mapping_line_resolution", C.c_double), ("mapping_plane_resolution", C.c_double),
                 ("mapping_skip_frame", C.c_int), ("detach_VO_LO", C.c_int), ("lo_outer_passes", C.c_int),
                 ("lo_max_iterations", C.c_int), ("lm_outer_passes", C.c_int), ("lm_max_iterations", C.c_int),
-                ("map_capacity_points", C.c_int)]
+                ("map_capacity_points", C.c_int), ("debug_keep_submap", C.c_int)]
 
 
 def build(verbose: bool = False) -> str:
@@ -92,7 +92,7 @@ def lib():
             "vloam_laser_mapping": [vp, vp], "vloam_get_lm_pose": [vp, c_dp],
             "vloam_map_set_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int],
             "vloam_map_get_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
-            "vloam_get_lm_info": [vp, c_ip], "vloam_get_lm_trace": [vp, C.c_int, C.c_int, c_dp, c_ip, c_dp],
+            "vloam_get_lm_info": [vp, c_ip], "vloam_get_map_stats": [vp, c_ip], "vloam_get_lm_trace": [vp, C.c_int, C.c_int, c_dp, c_ip, c_dp],
             "vloam_vo_create": [vp, C.c_int, C.c_int, C.c_int, pp], "vloam_vo_destroy": [vp],
             "vloam_vo_set_calibration": [vp, c_fp, c_fp, c_fp], "vloam_vo_reset": [vp],
             "vloam_vo_process_cloud": [vp, vp, vp, C.c_int, C.c_size_t],
@@ -383,6 +383,13 @@ class LidarOdometryMapping:
         info = np.zeros((self.batch, 8), np.int32)
         self.ctx.check(lib().vloam_get_lm_info(self._h, info.ctypes.data_as(c_ip)))
         return info
+
+    def map_stats(self):
+        """(batch, 2, 8) int32 per stream and kind: points, pool high-water mark, pool index, non-empty cubes, fixed-point
+        cubes, cubes rewritten by the last scan, re-packs so far, slab capacity in use."""
+        st = np.zeros((self.batch, 2, 8), np.int32)
+        self.ctx.check(lib().vloam_get_map_stats(self._h, st.ctypes.data_as(c_ip)))
+        return st
 
     def lm_trace(self, pass_: int, stream: int = 0):
         rec = np.zeros((8, 7))

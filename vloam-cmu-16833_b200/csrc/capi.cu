@@ -19,7 +19,7 @@ const char* kernel_name(int id) {
   static const char* names[K_COUNT] = {
       "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_pick_features", "sr_less_flat_voxel", "sr_pack",
       "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state", "lo_build_grid", "lo_associate_brute",
-      "lm_prepare", "lm_voxel", "lm_grid", "lm_associate", "lm_solve", "lm_insert", "lm_refilter", "lm_misc",
+      "lm_prepare", "lm_voxel", "lm_grid", "lm_associate", "lm_solve", "lm_insert", "lm_refilter", "lm_place", "lm_misc",
       "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
@@ -202,6 +202,7 @@ int vloam_lidar_params_default(vloam_lidar_params* p) {
   p->lm_outer_passes = 2;
   p->lm_max_iterations = 4;
   p->map_capacity_points = 1 << 21;
+  p->debug_keep_submap = 0;
   return VLOAM_OK;
 }
 
@@ -684,6 +685,13 @@ int vloam_get_lm_info(vloam_lidar* h, int* info) {
   CU(c, cudaSetDevice(c->device));
   cudaError_t e = lm_get_info(h->lm, c->stream, info);
   return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_info", e);
+}
+int vloam_get_map_stats(vloam_lidar* h, int* stats) {
+  if (!h || !stats) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_map_stats(h->lm, c->stream, stats);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_map_stats", e);
 }
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para) {
   if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1) return VLOAM_E_INVALID;

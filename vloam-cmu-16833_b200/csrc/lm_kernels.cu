@@ -42,12 +42,15 @@ struct LMState {
   int fromMapNum[2];
   int stackNum[2];
   int solved;                           // the map was large enough (:448)
-  int poolEnd[2];                       // first free slot of the current map buffer
+  int poolEnd[2];                       // first free slot of the current map pool (bump allocator of cube slabs)
+  int cur[2];                           // which of the two pools holds this stream's corner / surf map
+  int compact[2];                       // this scan's write-back re-packs the whole map into the other pool
+  int repacks[2];                       // re-packs so far
   float gridMinX, gridMinY;             // origin of the sub-map column index
   int workNum[2];
   int workCube[2][kMaxWork], workFilter[2][kMaxWork], workNew0[2][kMaxWork], workNewN[2][kMaxWork];
   int workIn0[2][kMaxWork + 1];         // offsets of each work cube's (old ++ new) input inside the concat buffer
-  int workOutN[2][kMaxWork];
+  int workOutN[2][kMaxWork], workFixed[2][kMaxWork];
   int error;
   SolveTrace trace[2];
 };
@@ -64,11 +67,16 @@ struct LMDevice {
   vloam_lidar_params p{};
   Profiler* prof = nullptr;
   bool allocated = false, reset_valid = true, ran = false;
-  int curPts = 0, curTab = 0;      // the map = points in mapPts[curPts] addressed by cubeOff/cubeCnt[curTab]
+  int curTab = 0;                  // the map = cube slabs in mapPts[LMState::cur] addressed by the tables [curTab]
   LMState* st = nullptr;
-  int* cubeOff[2] = {nullptr, nullptr};   // [B][2][kCubes]
+  // Cube tables [B][2][kCubes]: a cube is the slab [off, off + cap) of its pool holding cnt points; fix = the cube is a
+  // fixed point of its voxel filter (cta_voxel_filter) and has not received a point since.
+  int* cubeOff[2] = {nullptr, nullptr};
   int* cubeCnt[2] = {nullptr, nullptr};
-  float4* mapPts[2] = {nullptr, nullptr}; // [B][2][mapCap]
+  int* cubeCap[2] = {nullptr, nullptr};
+  int* cubeFix[2] = {nullptr, nullptr};
+  float4* mapPts[2] = {nullptr, nullptr}; // two pools [B][2][mapCap]; a stream changes pool only when its map is re-packed
+  float4* snap = nullptr;                 // [B][2][mapCap] laserCloud{Corner,Surf}FromMap of the last scan (debug_keep_submap)
   float4* stack = nullptr;                // [B][2][cap]  down-sampled scan (laserCloudCornerStack / SurfStack)
   float4* stackW = nullptr;               // [B][2][cap]  the same points in the map frame (pointAssociateToMap)
   unsigned* keyA = nullptr; unsigned* valA = nullptr; unsigned* keyB = nullptr; unsigned* valB = nullptr;  // [B][2][workCap]
@@ -79,13 +87,23 @@ struct LMDevice {
   LMResidual* res = nullptr;              // [B][2][cap]
   double* pose = nullptr;                 // [B][16]
   short* workOf = nullptr;                // [B][2][kCubes]
+  short* liveList = nullptr;              // [B][2][kCubes] cubes a re-pack has to move
+  int* liveNum = nullptr;                 // [B][2]
   size_t workCap = 0;
 };
 
 // pcl::VoxelGrid<PointXYZI> on one global-memory segment by one CTA (1024 threads).  Semantics: oracle/voxel_grid.hpp.
 // Returns the number of output points (valid in all threads).
+//
+// *fixedPoint (uniform) is set when the OUTPUT is provably a fixed point of the filter, i.e. filtering it again would
+// return it bit for bit: every centroid lies in the voxel it was averaged over.  Then the next filter sees one point
+// per voxel, the same voxel lattice (floor(x / leaf) does not depend on the bounding box) and hence the same
+// lexicographic key order, and the "mean" of a single point is the point itself ((0 + x) / 1 == x; sums never produce
+// -0).  The map re-filter (laser_mapping.cpp:689-702) uses this to skip cubes that received no point since they were
+// last filtered — the reference filters them again and gets the same cloud back.
 __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf, float4* __restrict__ out, unsigned* kA,
-                                unsigned* vA, unsigned* kB, unsigned* vB, SortSmem& S, float* red /*[6*32]*/) {
+                                unsigned* vA, unsigned* kB, unsigned* vB, SortSmem& S, float* red /*[6*32]*/, int* fixedPoint) {
+  *fixedPoint = 1;
   if (n == 0) return 0;
   const float inv = __fdiv_rn(1.0f, leaf);
   float mn[3] = {3.0e38f, 3.0e38f, 3.0e38f}, mx[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -117,6 +135,7 @@ __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf
   const long long dz = (long long)(__fmul_rn(__fsub_rn(mx[2], mn[2]), inv)) + 1;
   if (dx * dy * dz > 2147483647LL) {  // PCL: "Leaf size is too small": output = input
     for (int k = threadIdx.x; k < n; k += 1024) out[k] = in[k];
+    *fixedPoint = 0;
     return n;
   }
   int minb[3], divb[3];
@@ -148,20 +167,25 @@ __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf
   for (int q = q0; q < q1; ++q) nh += (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
   int opos = block_exclusive_scan1024(nh, S);
   const int total = S.total;
+  int inside = 1;
   for (int q = q0; q < q1; ++q) {
     if (!(q == 0 || keys[q] != keys[q - 1])) continue;
     const unsigned vox = keys[q];
     float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // lattice coordinates of the voxel (those of its first member)
     int cnt = 0;
     for (int qq = q; qq < n && keys[qq] == vox; ++qq) {
       const float4 p = in[vals[qq]];
+      if (cnt == 0) { v0 = floorf(__fmul_rn(p.x, inv)); v1 = floorf(__fmul_rn(p.y, inv)); v2 = floorf(__fmul_rn(p.z, inv)); }
       sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
       ++cnt;
     }
     const float nf = (float)cnt;
-    out[opos++] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+    const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+    if (floorf(__fmul_rn(c.x, inv)) != v0 || floorf(__fmul_rn(c.y, inv)) != v1 || floorf(__fmul_rn(c.z, inv)) != v2) inside = 0;
+    out[opos++] = c;
   }
-  __syncthreads();
+  *fixedPoint = __syncthreads_and(inside);
   return total;
 }
 
@@ -172,10 +196,15 @@ __device__ __forceinline__ int cube_coord(double v, int cen) {  // :207-216 / :6
   return c;
 }
 
+struct CubeTables { int* off; int* cnt; int* cap; int* fix; };   // [B][2][kCubes] each
+struct MapPools { float4* p[2]; };                                // [B][2][mapCap] each
+__device__ __forceinline__ float4* stream_map(const MapPools& pools, const LMState& st, int b, int kind, int mapCap) {
+  return (st.cur[kind] ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap;
+}
+
 // lm_prepare: grid (B), block 256.  Table ping-pong: reads tables `src`, writes the shifted tables to `dst`.
 __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, const LOState* __restrict__ lo,
-                                                   const int* __restrict__ offSrc, const int* __restrict__ cntSrc,
-                                                   int* __restrict__ offDst, int* __restrict__ cntDst, int resetValid) {
+                                                   const CubeTables src, const CubeTables dst, int resetValid) {
   const int b = blockIdx.x;
   LMState& st = stAll[b];
   __shared__ int sh[3];
@@ -206,19 +235,16 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
   __syncthreads();
   const int sI = sh[0], sJ = sh[1], sK = sh[2];
   for (int kind = 0; kind < 2; ++kind) {
-    const int* oS = offSrc + ((size_t)b * 2 + kind) * kCubes;
-    const int* cS = cntSrc + ((size_t)b * 2 + kind) * kCubes;
-    int* oD = offDst + ((size_t)b * 2 + kind) * kCubes;
-    int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
+    const size_t tb = ((size_t)b * 2 + kind) * kCubes;
     for (int c = threadIdx.x; c < kCubes; c += 256) {
       const int i = c % kCubeW, j = (c / kCubeW) % kCubeH, k = c / (kCubeW * kCubeH);
       const int si = i - sI, sj = j - sJ, sk = k - sK;  // new[i] = old[i - shift]; wrapped planes are cleared
-      int o = 0, n = 0;
+      int o = 0, n = 0, cp = 0, fx = 0;                  // (a cleared cube's slab is reclaimed by the next re-pack)
       if (si >= 0 && si < kCubeW && sj >= 0 && sj < kCubeH && sk >= 0 && sk < kCubeD) {
         const int s = si + kCubeW * sj + kCubeW * kCubeH * sk;
-        o = oS[s]; n = cS[s];
+        o = src.off[tb + s]; n = src.cnt[tb + s]; cp = src.cap[tb + s]; fx = src.fix[tb + s];
       }
-      oD[c] = o; cD[c] = n;
+      dst.off[tb + c] = o; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp; dst.fix[tb + c] = fx;
     }
   }
   __syncthreads();
@@ -233,7 +259,7 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
             st.validInd[vn++] = i + kCubeW * j + kCubeW * kCubeH * k;
     st.validNum = vn;
     for (int kind = 0; kind < 2; ++kind) {
-      const int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
+      const int* cD = dst.cnt + ((size_t)b * 2 + kind) * kCubes;
       int acc = 0;
       for (int v = 0; v < vn; ++v) { st.validPrefix[kind][v] = acc; acc += cD[st.validInd[v]]; }
       st.validPrefix[kind][vn] = acc;
@@ -259,8 +285,9 @@ __global__ void __launch_bounds__(1024) lm_voxel_stack(LMState* __restrict__ stA
   const float4* in = kind == 0 ? cornerLast + (size_t)b * kMaxLessSharp : surfLast + (size_t)b * cap;
   const int n = kind == 0 ? hdr[b].nLessSharp : hdr[b].nLessFlat;
   const size_t so = ((size_t)b * 2 + kind) * workCap;
+  int fixedPoint;
   const int m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, stack + ((size_t)b * 2 + kind) * cap, kA + so, vA + so,
-                                 kB + so, vB + so, S, red);
+                                 kB + so, vB + so, S, red, &fixedPoint);
   if (threadIdx.x == 0) stAll[b].stackNum[kind] = m;
 }
 
@@ -280,12 +307,13 @@ __device__ __forceinline__ int map_col(const LMState& st, float x, float y) {
 }
 // grid (nblk, 2, B), block 256
 __global__ void __launch_bounds__(256) lm_grid_count(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
-                                                      const float4* __restrict__ mapPts, int mapCap, int* __restrict__ cells) {
+                                                      const MapPools pools, int mapCap, int* __restrict__ cells) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
+  const float4* map = stream_map(pools, st, b, kind, mapCap);
   for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
-    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, mapPts + ((size_t)b * 2 + kind) * mapCap, g);
+    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, map, g);
     atomicAdd(&cells[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
   }
 }
@@ -305,16 +333,27 @@ __global__ void __launch_bounds__(1024) lm_grid_scan(const LMState* __restrict__
   if (threadIdx.x == 1023) { cs[kMapCols] = run; cu[kMapCols] = run; }
 }
 __global__ void __launch_bounds__(256) lm_grid_scatter(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
-                                                        const float4* __restrict__ mapPts, int mapCap, int* __restrict__ cursor,
+                                                        const MapPools pools, int mapCap, int* __restrict__ cursor,
                                                         float4* __restrict__ sorted) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
+  const float4* map = stream_map(pools, st, b, kind, mapCap);
   for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
-    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, mapPts + ((size_t)b * 2 + kind) * mapCap, g);
+    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, map, g);
     const int pos = atomicAdd(&cursor[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
     sorted[((size_t)b * 2 + kind) * mapCap + pos] = make_float4(p.x, p.y, p.z, __int_as_float(g));
   }
+}
+
+// laserCloudCornerFromMap / SurfFromMap (:422-428) kept for inspection (debug_keep_submap): grid (nblk, 2, B), block 256
+__global__ void __launch_bounds__(256) lm_snapshot_submap(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
+                                                           const MapPools pools, int mapCap, float4* __restrict__ snap) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  const float4* map = stream_map(pools, st, b, kind, mapCap);
+  for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256)
+    snap[((size_t)b * 2 + kind) * mapCap + g] = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, map, g);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -541,8 +580,14 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
 // ---------------------------------------------------------------------------------------------------------------
 // lm_insert_keys: grid (2, B), block 1024.  transformUpdate (:636, :140-144), map-frame coordinates of the stack
 // points and their cube ids, stable sort by cube id (:639-683 push the points in stack order), work list.
+//
+// Work list = the cubes this scan rewrites: every cube that receives points (a valid cube is re-filtered, :689-702; any
+// other cube only grows) plus every non-empty valid cube that is not known to be a fixed point of its filter.  A valid
+// cube that received nothing since a filter left it in fixed-point form would come out of pcl::VoxelGrid unchanged
+// (cta_voxel_filter), so it is not touched at all.
 __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                         float4* __restrict__ stackW, const int* __restrict__ cubeCnt,
+                                                        const int* __restrict__ cubeFix,
                                                         unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB, size_t workCap) {
   __shared__ SortSmem S;
   __shared__ int s_res;
@@ -577,9 +622,13 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
   if (s_res) { for (int i = threadIdx.x; i < n; i += 1024) { ka[i] = keys[i]; va[i] = vals[i]; } }
   __syncthreads();
   // runs of equal cube id in the sorted key array: heads found in parallel, then a short serial work-list build
+  constexpr int kBitWords = (kCubes + 31) / 32;
   __shared__ int s_nh, s_headCube[kMaxWork], s_headStart[kMaxWork], s_headEnd[kMaxWork];
+  __shared__ unsigned s_validBits[kBitWords], s_listed[kBitWords];
   if (threadIdx.x == 0) s_nh = 0;
+  for (int i = threadIdx.x; i < kBitWords; i += 1024) { s_validBits[i] = 0u; s_listed[i] = 0u; }
   __syncthreads();
+  for (int v = threadIdx.x; v < st.validNum; v += 1024) { const int c = st.validInd[v]; atomicOr(&s_validBits[c >> 5], 1u << (c & 31)); }
   for (int i = threadIdx.x; i < n; i += 1024) {
     const unsigned c = ka[i];
     if (c != 0xffffu && (i == 0 || ka[i - 1] != c)) {
@@ -597,24 +646,25 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    // work list: every valid cube (re-filtered, :689-702) then every other cube that received points (append only)
     const int* cnt = cubeCnt + ((size_t)b * 2 + kind) * kCubes;
+    const int* fix = cubeFix + ((size_t)b * 2 + kind) * kCubes;
     if (s_nh > kMaxWork) st.error |= 1;
-    int wn = 0, in0 = 0;
-    for (int v = 0; v < st.validNum && wn < kMaxWork; ++v) {
+    int wn = 0;
+    for (int h = 0; h < nh; ++h) {                 // cubes that receive points (distinct by construction)
+      const int c = s_headCube[h];
+      s_listed[c >> 5] |= 1u << (c & 31);
+      st.workCube[kind][wn] = c; st.workFilter[kind][wn] = (s_validBits[c >> 5] >> (c & 31)) & 1u;
+      st.workNew0[kind][wn] = s_headStart[h]; st.workNewN[kind][wn] = s_headEnd[h] - s_headStart[h]; ++wn;
+    }
+    for (int v = 0; v < st.validNum; ++v) {        // valid cubes whose filter result is not known to be a fixed point
       const int c = st.validInd[v];
-      bool dup = false;
-      for (int u = 0; u < wn; ++u) if (st.workCube[kind][u] == c) { dup = true; break; }
-      if (dup) continue;
+      if ((s_listed[c >> 5] >> (c & 31)) & 1u) continue;
+      if (cnt[c] == 0 || fix[c]) continue;
+      if (wn >= kMaxWork) { st.error |= 1; break; }
+      s_listed[c >> 5] |= 1u << (c & 31);
       st.workCube[kind][wn] = c; st.workFilter[kind][wn] = 1; st.workNew0[kind][wn] = 0; st.workNewN[kind][wn] = 0; ++wn;
     }
-    for (int h = 0; h < nh; ++h) {
-      const int c = s_headCube[h];
-      int slot = -1;
-      for (int u = 0; u < wn; ++u) if (st.workCube[kind][u] == c) { slot = u; break; }
-      if (slot < 0 && wn < kMaxWork) { slot = wn++; st.workCube[kind][slot] = c; st.workFilter[kind][slot] = 0; }
-      if (slot >= 0) { st.workNew0[kind][slot] = s_headStart[h]; st.workNewN[kind][slot] = s_headEnd[h] - s_headStart[h]; } else st.error |= 1;
-    }
+    int in0 = 0;
     for (int u = 0; u < wn; ++u) { st.workIn0[kind][u] = in0; in0 += cnt[st.workCube[kind][u]] + st.workNewN[kind][u]; }
     st.workIn0[kind][wn] = in0;
     st.workNum[kind] = wn;
@@ -637,7 +687,7 @@ __global__ void lm_transform_update(LMState* __restrict__ stAll, int B) {  // :1
 
 // lm_refilter: grid (kMaxWork, 2, B), block 1024.  One work cube per CTA: input = old cube ++ new points (stack order).
 __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll, const int* __restrict__ cubeOff, const int* __restrict__ cubeCnt,
-                                                     const float4* __restrict__ mapPts, int mapCap, const float4* __restrict__ stackW,
+                                                     const MapPools pools, int mapCap, const float4* __restrict__ stackW,
                                                      int cap, const unsigned* __restrict__ vAins, float lineRes, float planeRes,
                                                      float4* __restrict__ concat, float4* __restrict__ staged, unsigned* kA, unsigned* vA,
                                                      unsigned* kB, unsigned* vB, size_t workCap) {
@@ -650,78 +700,140 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
   const size_t so = ((size_t)b * 2 + kind) * workCap;
   const int in0 = st.workIn0[kind][u];
   const int nOld = cubeCnt[((size_t)b * 2 + kind) * kCubes + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
-  const float4* old = mapPts + ((size_t)b * 2 + kind) * mapCap + cubeOff[((size_t)b * 2 + kind) * kCubes + c];
+  const float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[((size_t)b * 2 + kind) * kCubes + c];
   const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
   const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points, in stack order
   float4* in = concat + so + in0;
   float4* out = staged + so + in0;
   for (int i = threadIdx.x; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
   __syncthreads();
-  int m;
+  int m, fixed = 0;
   if (st.workFilter[kind][u]) {
     // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
-    m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red);
+    m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red, &fixed);
   } else {
     for (int i = threadIdx.x; i < n; i += 1024) out[i] = in[i];
     m = n;
   }
-  if (threadIdx.x == 0) st.workOutN[kind][u] = m;
+  if (threadIdx.x == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; }
 }
 
-// lm_rebuild_tables: grid (2, B), block 1024: new cube table (work cubes get their new size, the others keep theirs).
-__global__ void __launch_bounds__(1024) lm_rebuild_tables(LMState* __restrict__ stAll, const int* __restrict__ offSrc, const int* __restrict__ cntSrc,
-                                                           int* __restrict__ offDst, int* __restrict__ cntDst, short* __restrict__ workOfAll, int mapCap) {
+// lm_place: grid (2, B), block 1024.  New cube tables `dst` from the post-shift tables `src`: a rewritten cube keeps its
+// slab when the result fits, else gets a new slab (with head-room) from the pool's bump allocator; when the pool is
+// exhausted the whole map is re-packed into the stream's other pool (st.compact, done by lm_compact_copy) with fresh
+// head-room for every cube.  liveList: the non-empty cubes a re-pack has to move (the rewritten ones come from `staged`).
+__device__ __forceinline__ int slab_headroom(int n) { return (n >> 2) + 256; }
+__global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, const CubeTables src, const CubeTables dst,
+                                                  short* __restrict__ workOfAll, short* __restrict__ liveListAll, int* __restrict__ liveNumAll,
+                                                  int mapCap) {
   __shared__ SortSmem S;
+  __shared__ int s_compact, s_nlive, s_err;
   const int kind = blockIdx.x, b = blockIdx.y;
   LMState& st = stAll[b];
-  const int* oS = offSrc + ((size_t)b * 2 + kind) * kCubes;
-  const int* cS = cntSrc + ((size_t)b * 2 + kind) * kCubes;
-  int* oD = offDst + ((size_t)b * 2 + kind) * kCubes;
-  int* cD = cntDst + ((size_t)b * 2 + kind) * kCubes;
-  short* workOf = workOfAll + ((size_t)b * 2 + kind) * kCubes;
-  for (int c = threadIdx.x; c < kCubes; c += 1024) workOf[c] = -1;
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  short* workOf = workOfAll + tb;
+  short* liveList = liveListAll + tb;
+  for (int c = threadIdx.x; c < kCubes; c += 1024) {
+    workOf[c] = -1;
+    dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
+  }
+  // (the other kind's CTA may raise st.error concurrently: one read, shared, keeps the barriers below uniform)
+  if (threadIdx.x == 0) { s_compact = 0; s_nlive = 0; st.compact[kind] = 0; s_err = st.error & 3; }
   __syncthreads();
-  if (!st.error) for (int u = threadIdx.x; u < st.workNum[kind]; u += 1024) workOf[st.workCube[kind][u]] = (short)u;
+  if (s_err) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }   // the map keeps its pre-insertion state
+  const int wn = st.workNum[kind];
+  for (int u = threadIdx.x; u < wn; u += 1024) workOf[st.workCube[kind][u]] = (short)u;
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int poolEnd = st.poolEnd[kind];
+    for (int u = 0; u < wn; ++u) {
+      const int c = st.workCube[kind][u], m = st.workOutN[kind][u];
+      if (m > src.cap[tb + c]) {
+        const int need = m + slab_headroom(m);
+        if ((long long)poolEnd + need > (long long)mapCap) { s_compact = 1; break; }
+        dst.off[tb + c] = poolEnd; dst.cap[tb + c] = need; poolEnd += need;
+      }
+      dst.cnt[tb + c] = m;
+      dst.fix[tb + c] = st.workFilter[kind][u] ? st.workFixed[kind][u] : 0;
+    }
+    if (!s_compact) st.poolEnd[kind] = poolEnd;
+  }
+  __syncthreads();
+  if (!s_compact) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }
+  // ---- re-pack: every cube gets a fresh slab in the other pool
   const int per = (kCubes + 1023) / 1024;
   const int c0 = min((int)threadIdx.x * per, kCubes), c1 = min(c0 + per, kCubes);
   int sum = 0;
-  for (int c = c0; c < c1; ++c) sum += workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : cS[c];
-  int run = block_exclusive_scan1024(sum, S);
-  const int total = S.total;
-  if (total > mapCap) {  // keep the old content (reported through the error bits of the pose export)
-    if (threadIdx.x == 0) st.error |= 4;
-    for (int c = c0; c < c1; ++c) { workOf[c] = -1; }
-    __syncthreads();
-    sum = 0;
-    for (int c = c0; c < c1; ++c) sum += cS[c];
-    run = block_exclusive_scan1024(sum, S);
+  for (int c = c0; c < c1; ++c) sum += workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : src.cnt[tb + c];
+  block_exclusive_scan1024(sum, S);
+  const long long total = S.total;
+  __syncthreads();
+  if (total > (long long)mapCap) {   // capacity exceeded: keep the old content (reported through the error bits of the pose export)
+    for (int c = threadIdx.x; c < kCubes; c += 1024) {
+      dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
+    }
+    if (threadIdx.x == 0) { st.error |= 4; liveNumAll[b * 2 + kind] = 0; }
+    return;
   }
-  for (int c = c0; c < c1; ++c) { const int n = workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : cS[c]; oD[c] = run; cD[c] = n; run += n; }
-  if (threadIdx.x == 0) st.poolEnd[kind] = S.total;
+  const long long spare = ((long long)mapCap - total) / 2;    // half of the free space becomes head-room, half stays for the bump allocator
+  int capsum = 0;
+  for (int c = c0; c < c1; ++c) {
+    const int n = workOf[c] >= 0 ? st.workOutN[kind][workOf[c]] : src.cnt[tb + c];
+    const long long share = total > 0 ? spare * n / total : 0;
+    capsum += n > 0 ? n + (int)min((long long)slab_headroom(n), share) : 0;
+  }
+  int run = block_exclusive_scan1024(capsum, S);
+  for (int c = c0; c < c1; ++c) {
+    const int u = workOf[c];
+    const int n = u >= 0 ? st.workOutN[kind][u] : src.cnt[tb + c];
+    const long long share = total > 0 ? spare * n / total : 0;
+    const int cp = n > 0 ? n + (int)min((long long)slab_headroom(n), share) : 0;
+    dst.off[tb + c] = run; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp;
+    dst.fix[tb + c] = u >= 0 ? (st.workFilter[kind][u] ? st.workFixed[kind][u] : 0) : src.fix[tb + c];
+    run += cp;
+    if (u < 0 && n > 0) liveList[atomicAdd(&s_nlive, 1)] = (short)c;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) { st.poolEnd[kind] = S.total; st.compact[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive; }
 }
-// lm_rebuild_copy: one warp per cube, grid (ceil(kCubes / 8), 2, B), block 256: compaction into the other map buffer.
-__global__ void __launch_bounds__(256) lm_rebuild_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
+// lm_write_back: grid (kMaxWork, 2, B), block 256: filtered cube -> its slab (in the other pool when the map is re-packed).
+__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const int* __restrict__ offDst,
+                                                      const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap) {
+  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (u >= st.workNum[kind] || st.error) return;
+  const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
+  const float4* src = staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
+  float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + offDst[((size_t)b * 2 + kind) * kCubes + c];
+  for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+}
+// lm_compact_copy: grid (128, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
+__global__ void __launch_bounds__(256) lm_compact_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
                                                         const int* __restrict__ offDst, const int* __restrict__ cntDst,
-                                                        const short* __restrict__ workOfAll, const float4* __restrict__ mapSrc,
-                                                        float4* __restrict__ mapDst, int mapCap, const float4* __restrict__ staged, size_t workCap) {
+                                                        const short* __restrict__ liveListAll, const int* __restrict__ liveNumAll,
+                                                        const MapPools pools, int mapCap) {
   const int kind = blockIdx.y, b = blockIdx.z;
-  const int c = blockIdx.x * 8 + (threadIdx.x >> 5);
-  if (c >= kCubes) return;
+  const LMState& st = stAll[b];
+  if (!st.compact[kind]) return;
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
-  const int n = cntDst[tb + c];
-  if (!n) return;
-  const int u = workOfAll[tb + c];
-  const float4* src = u >= 0 ? staged + ((size_t)b * 2 + kind) * workCap + stAll[b].workIn0[kind][u]
-                             : mapSrc + ((size_t)b * 2 + kind) * mapCap + offSrc[tb + c];
-  float4* dst = mapDst + ((size_t)b * 2 + kind) * mapCap + offDst[tb + c];
-  for (int i = lane_id(); i < n; i += 32) dst[i] = src[i];
+  const float4* from = (st.cur[kind] ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap;
+  float4* to = (st.cur[kind] ? pools.p[0] : pools.p[1]) + ((size_t)b * 2 + kind) * mapCap;
+  const int nl = liveNumAll[b * 2 + kind];
+  for (int i = blockIdx.x; i < nl; i += gridDim.x) {
+    const int c = liveListAll[tb + i];
+    const float4* src = from + offSrc[tb + c];
+    float4* dst = to + offDst[tb + c];
+    const int n = cntDst[tb + c];
+    for (int k = threadIdx.x; k < n; k += 256) dst[k] = src[k];
+  }
 }
 
-__global__ void lm_export_pose(const LMState* __restrict__ stAll, double* __restrict__ pose, int B) {
+// Also completes a re-pack: the stream's map now lives in its other pool.
+__global__ void lm_export_pose(LMState* __restrict__ stAll, double* __restrict__ pose, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
-  const LMState& s = stAll[b];
+  LMState& s = stAll[b];
+  for (int kind = 0; kind < 2; ++kind) if (s.compact[kind]) { s.cur[kind] ^= 1; s.compact[kind] = 0; s.repacks[kind]++; }
   double* o = pose + (size_t)b * 16;
   for (int i = 0; i < 7; ++i) o[i] = s.parameters[i];
   for (int i = 0; i < 4; ++i) o[7 + i] = s.q_wmap_wodom[i];
@@ -738,8 +850,10 @@ __global__ void lm_init_state(LMState* stAll, int B) {
   s.cenW = 10; s.cenH = 10; s.cenD = 5;                                       // laser_mapping.h:76-78
   s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
   s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0;
+  s.cur[0] = s.cur[1] = 0; s.compact[0] = s.compact[1] = 0; s.repacks[0] = s.repacks[1] = 0;
   s.trace[0].n_records = s.trace[1].n_records = 0;
 }
+
 
 // ===============================================================================================================
 // host side
@@ -752,8 +866,11 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->st, B * sizeof(LMState));
   for (int i = 0; i < 2; ++i) {
     A((void**)&lm->cubeOff[i], B * 2 * kCubes * sizeof(int)); A((void**)&lm->cubeCnt[i], B * 2 * kCubes * sizeof(int));
+    A((void**)&lm->cubeCap[i], B * 2 * kCubes * sizeof(int)); A((void**)&lm->cubeFix[i], B * 2 * kCubes * sizeof(int));
     A((void**)&lm->mapPts[i], B * 2 * mapCap * sizeof(float4));
   }
+  if (lm->p.debug_keep_submap) A((void**)&lm->snap, B * 2 * mapCap * sizeof(float4));
+  A((void**)&lm->liveList, B * 2 * kCubes * sizeof(short)); A((void**)&lm->liveNum, B * 2 * sizeof(int));
   A((void**)&lm->stack, B * 2 * cap * sizeof(float4)); A((void**)&lm->stackW, B * 2 * cap * sizeof(float4));
   A((void**)&lm->keyA, B * 2 * lm->workCap * 4); A((void**)&lm->valA, B * 2 * lm->workCap * 4);
   A((void**)&lm->keyB, B * 2 * lm->workCap * 4); A((void**)&lm->valB, B * 2 * lm->workCap * 4);
@@ -780,7 +897,8 @@ void lm_destroy(LMDevice* lm) {
   if (!lm) return;
   if (lm->allocated) {
     cudaFree(lm->st);
-    for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->mapPts[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->cubeCap[i]); cudaFree(lm->cubeFix[i]); cudaFree(lm->mapPts[i]); }
+    cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->cellStart); cudaFree(lm->cursor); cudaFree(lm->sorted);
     cudaFree(lm->res); cudaFree(lm->pose); cudaFree(lm->workOf);
@@ -801,42 +919,45 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
     VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
     return cudaGetLastError();
   }
-  // the map = mapPts[ps] addressed by tables[ts].  lm_prepare writes the shifted tables to tables[td]; everything up to
-  // the re-filter reads (tables[td], mapPts[ps]); the rebuild writes (tables[ts], mapPts[pd]).
-  const int ps = lm->curPts, pd = ps ^ 1, ts = lm->curTab, td = ts ^ 1;
+  // the map = cube slabs in mapPts[LMState::cur] addressed by tables[ts].  lm_prepare writes the shifted tables to
+  // tables[td]; everything up to the re-filter reads tables[td]; lm_place writes the post-insertion tables back to [ts].
+  const int ts = lm->curTab, td = ts ^ 1;
+  const CubeTables T_s{lm->cubeOff[ts], lm->cubeCnt[ts], lm->cubeCap[ts], lm->cubeFix[ts]};
+  const CubeTables T_d{lm->cubeOff[td], lm->cubeCnt[td], lm->cubeCap[td], lm->cubeFix[td]};
+  const MapPools pools{{lm->mapPts[0], lm->mapPts[1]}};
   const float lineRes = (float)lm->p.mapping_line_resolution, planeRes = (float)lm->p.mapping_plane_resolution;
-  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, lm->cubeOff[ts], lm->cubeCnt[ts], lm->cubeOff[td],
-                                                                  lm->cubeCnt[td], lm->reset_valid ? 1 : 0));
+  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, T_s, T_d, lm->reset_valid ? 1 : 0));
   lm->reset_valid = false;
+  if (lm->snap)
+    VB_LAUNCH(prof, K_LM_MISC, st, lm_snapshot_submap<<<dim3(256, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->snap));
   // C4: VoxelGrid of the scan features (scratch: the first `cap` entries of each key/val slab)
   VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
                                                                               lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // C5: sub-map column index
   e = cudaMemsetAsync(lm->cursor, 0, (size_t)B * 2 * (kMapCols + 1) * sizeof(int), st);
   if (e != cudaSuccess) return e;
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_count<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->mapPts[ps], mapCap, lm->cursor));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_count<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->cursor));
   VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scan<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->cellStart, lm->cursor));
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scatter<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->mapPts[ps], mapCap, lm->cursor, lm->sorted));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scatter<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->cursor, lm->sorted));
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
     VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(512, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
     VB_LAUNCH(prof, K_LM_SOLVE, st, lm_solve<<<B, 256, 0, st>>>(lm->st, lm->res, cap, tp, lm->p.lm_max_iterations));
   }
-  // C10-C12: transformUpdate, insertion, re-filter, compaction
+  // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back
   VB_LAUNCH(prof, K_LM_MISC, st, lm_transform_update<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B));
-  VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->keyA, lm->valA,
-                                                                               lm->keyB, lm->valB, lm->workCap));
+  VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->cubeFix[td],
+                                                                               lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // the cube-sorted stack indices stay in valA[0 .. n); the per-cube filters use the key/val slabs from offset `cap` on
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->mapPts[ps], mapCap,
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], pools, mapCap,
                                                                                          lm->stackW, cap, lm->valA, lineRes, planeRes, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_rebuild_tables<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeOff[ts], lm->cubeCnt[ts],
-                                                                                     lm->workOf, mapCap));
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_rebuild_copy<<<dim3((kCubes + 7) / 8, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->workOf,
-                                                                                                   lm->mapPts[ps], lm->mapPts[pd], mapCap, lm->staged, lm->workCap));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
+                                                                                   lm->liveNum, pools, mapCap));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[ts], pools, mapCap, lm->staged, lm->workCap));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
-  lm->curPts = pd;  // tables[ts] now describe mapPts[pd]; (tables[td], mapPts[ps]) still hold the pre-insertion state
   lm->ran = true;
   return cudaGetLastError();
 }
@@ -875,42 +996,35 @@ cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, f
     }
     return e;
   }
-  // laserCloudCornerFromMap / SurfFromMap of the last solveMapping: the pre-insertion map state
+  // laserCloudCornerFromMap / SurfFromMap of the last solveMapping (the pre-insertion sub-map): kept only on request
   const int kind = which == VLOAM_CLOUD_CORNER_MAP ? 0 : 1;
+  if (!lm->snap) return cudaErrorNotSupported;   // vloam_lidar_params::debug_keep_submap was not set
   const int n = lm->ran ? S.fromMapNum[kind] : 0;
   if (n_out) *n_out = n;
   if (!out || capacity <= 0 || n == 0) return cudaSuccess;
-  const int pts = lm->curPts ^ 1, tab = lm->curTab ^ 1;
-  std::vector<int> off(kCubes), cnt(kCubes);
-  e = cudaMemcpyAsync(off.data(), lm->cubeOff[tab] + ((size_t)stream * 2 + kind) * kCubes, kCubes * sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), lm->cubeCnt[tab] + ((size_t)stream * 2 + kind) * kCubes, kCubes * sizeof(int), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e != cudaSuccess) return e;
-  int written = 0;
-  for (int v = 0; v < S.validNum && written < capacity; ++v) {
-    const int c = S.validInd[v];
-    const int m = cnt[c] < capacity - written ? cnt[c] : capacity - written;
-    if (m > 0) {
-      e = cudaMemcpyAsync(out + (size_t)written * 4, lm->mapPts[pts] + ((size_t)stream * 2 + kind) * lm->mapCap + off[c], (size_t)m * 16, cudaMemcpyDeviceToHost, st);
-      if (e != cudaSuccess) return e;
-      written += m;
-    }
+  {
+    const int m = n < capacity ? n : capacity;
+    e = cudaMemcpyAsync(out, lm->snap + ((size_t)stream * 2 + kind) * lm->mapCap, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    return e;
   }
-  return cudaStreamSynchronize(st);
 }
-
 cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, const float* xyzi, int n) {
   cudaError_t e = lm_alloc(lm, st);
   if (e != cudaSuccess) return e;
   LMState S;
   e = lm_fetch_state(lm, st, stream, &S);
   if (e != cudaSuccess) return e;
+  // a fresh slab from the pool's bump allocator (a slab the cube may have had is reclaimed by the next re-pack); the
+  // content is arbitrary, so the cube is not marked as a fixed point of its voxel filter
   if ((long long)S.poolEnd[kind] + n > lm->mapCap) return cudaErrorInvalidValue;
   const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
-  const int off = S.poolEnd[kind];
-  if (n) e = cudaMemcpyAsync(lm->mapPts[lm->curPts] + ((size_t)stream * 2 + kind) * lm->mapCap + off, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, st);
+  const int off = S.poolEnd[kind], zero = 0;
+  if (n) e = cudaMemcpyAsync(lm->mapPts[S.cur[kind]] + ((size_t)stream * 2 + kind) * lm->mapCap + off, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeOff[lm->curTab] + tb, &off, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeCnt[lm->curTab] + tb, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeCap[lm->curTab] + tb, &n, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeFix[lm->curTab] + tb, &zero, sizeof(int), cudaMemcpyHostToDevice, st);
   const int newEnd = off + n;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&lm->st[stream].poolEnd[kind], &newEnd, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -921,15 +1035,16 @@ cudaError_t lm_get_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int
   cudaError_t e = lm_alloc(lm, st);
   if (e != cudaSuccess) return e;
   const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
-  int off = 0, n = 0;
+  int off = 0, n = 0, cur = 0;
   e = cudaMemcpyAsync(&off, lm->cubeOff[lm->curTab] + tb, sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(&n, lm->cubeCnt[lm->curTab] + tb, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(&cur, &lm->st[stream].cur[kind], sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return e;
   if (n_out) *n_out = n;
   const int m = n < capacity ? n : capacity;
   if (m > 0 && out) {
-    e = cudaMemcpyAsync(out, lm->mapPts[lm->curPts] + ((size_t)stream * 2 + kind) * lm->mapCap + off, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+    e = cudaMemcpyAsync(out, lm->mapPts[cur & 1] + ((size_t)stream * 2 + kind) * lm->mapCap + off, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
     if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   }
   return e;
@@ -947,6 +1062,33 @@ cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info) {
     o[0] = h[b].cenW; o[1] = h[b].cenH; o[2] = h[b].cenD; o[3] = h[b].validNum;
     o[4] = h[b].fromMapNum[0]; o[5] = h[b].fromMapNum[1]; o[6] = h[b].stackNum[0]; o[7] = h[b].stackNum[1];
   }
+  return cudaSuccess;
+}
+
+// stats[B][2][8] per stream and kind: points in the map, pool high-water mark, pool index, non-empty cubes, cubes in
+// fixed-point form, cubes rewritten by the last scan, re-packs so far, slab capacity in use
+cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  std::vector<LMState> h(lm->B);
+  std::vector<int> cnt((size_t)lm->B * 2 * kCubes), fix(cnt.size()), cp(cnt.size());
+  e = cudaMemcpyAsync(h.data(), lm->st, h.size() * sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cnt.data(), lm->cubeCnt[lm->curTab], cnt.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(fix.data(), lm->cubeFix[lm->curTab], fix.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(cp.data(), lm->cubeCap[lm->curTab], cp.size() * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  for (int b = 0; b < lm->B; ++b)
+    for (int kind = 0; kind < 2; ++kind) {
+      int* o = stats + ((size_t)b * 2 + kind) * 8;
+      long long pts = 0, caps = 0; int occ = 0, fx = 0;
+      for (int c = 0; c < kCubes; ++c) {
+        const size_t i = ((size_t)b * 2 + kind) * kCubes + c;
+        if (cnt[i] > 0) { pts += cnt[i]; caps += cp[i]; ++occ; fx += fix[i] ? 1 : 0; }
+      }
+      o[0] = (int)pts; o[1] = h[b].poolEnd[kind]; o[2] = h[b].cur[kind]; o[3] = occ; o[4] = fx; o[5] = h[b].workNum[kind];
+      o[6] = h[b].repacks[kind]; o[7] = (int)caps;
+    }
   return cudaSuccess;
 }
 
