@@ -14,6 +14,8 @@
 //   lm_solve          :609-617 the whole ceres::Solve of one outer pass in one launch (gn_solver.cuh)
 //   lm_insert_*       :636-683 transformUpdate, scan points into cubes (stable by cube)
 //   lm_rebuild_*      :689-702 re-filter every valid cube, compact the map into the other buffer
+#include <cooperative_groups.h>
+
 #include <cstdio>
 #include <vector>
 
@@ -428,123 +430,163 @@ __device__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5
   for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
 }
 
-// lm_associate: one warp per down-sampled scan point (grid-stride).  grid (512, 2, B), block 256.
+// lm_associate: grid (nblk, 2, B), block 256.  A CTA takes chunks of 256 down-sampled scan points (grid-stride):
+//   phase A  exact 5-NN, one 8-lane group per point (4 points per warp at a time): the candidates of the 3 x 3 column
+//            block are dealt to the lanes, every lane keeps its own sorted top-5, the group merges them;
+//   phase B  one THREAD per point: PCA line test (corner) or least-squares plane fit + 0.2 m check (surf) on the five
+//            neighbours, in double like the reference.  (Done by whole warps this part ran 32 times redundantly and was
+//            the bulk of the kernel.)
+constexpr int kLmGroup = 8;
 __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                      const int* __restrict__ cellStart, const float4* __restrict__ sorted,
                                                      int mapCap, LMResidual* __restrict__ res) {
+  __shared__ int s_pos[256][5];      // positions (in `sorted`) of the five nearest map points, -1 = no match (:479 / :547)
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
-  const int l = lane_id();
-  for (int qi = blockIdx.x * 8 + (threadIdx.x >> 5); qi < st.stackNum[kind]; qi += gridDim.x * 8) {
-  const float4 po = stack[((size_t)b * 2 + kind) * cap + qi];
-  LMResidual* out = res + ((size_t)b * 2 + kind) * cap + qi;
-  // pointAssociateToMap (:146-155): double transform, rounded to float
-  double w[3];
-  quat_rotate(st.parameters, (double)po.x, (double)po.y, (double)po.z, w);
-  const float sx = (float)(w[0] + st.parameters[4]), sy = (float)(w[1] + st.parameters[5]), sz = (float)(w[2] + st.parameters[6]);
+  const int nq = st.stackNum[kind];
+  const int lane = lane_id(), warp = threadIdx.x >> 5;
+  const int g = lane / kLmGroup, gl = lane % kLmGroup;
+  const unsigned gmask = 0xffu << (g * kLmGroup);
   const int* cs = cellStart + ((size_t)b * 2 + kind) * (kMapCols + 1);
   const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
-  const int qx = (int)floorf((sx - st.gridMinX) * (1.0f / kMapCell)), qy = (int)floorf((sy - st.gridMinY) * (1.0f / kMapCell));
-  // per-lane sorted top-5 of (distance bits << 32 | sub-map index); position in `sorted` kept alongside
-  unsigned long long bk[5];
-  int bp[5];
+  const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
+  const double q0 = st.parameters[0], q1 = st.parameters[1], q2 = st.parameters[2], q3 = st.parameters[3];
+  const double t0 = st.parameters[4], t1 = st.parameters[5], t2 = st.parameters[6];
+  const double qq[4] = {q0, q1, q2, q3};
+  for (int chunk = blockIdx.x * 256; chunk < nq; chunk += gridDim.x * 256) {
+    // ---- phase A
+    for (int r = 0; r < 8; ++r) {
+      const int slot = warp * 32 + r * 4 + g;
+      const int qi = chunk + slot;
+      unsigned long long bk[5];
+      int bp[5];
 #pragma unroll
-  for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
-  for (int row = qy - 1; row <= qy + 1; ++row) {
-    if (row < 0 || row >= kMapNY) continue;
-    const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kMapNX - 1);
-    if (x0 > x1) continue;
-    const int a = cs[row * kMapNX + x0], e = cs[row * kMapNX + x1 + 1];
-    for (int t = a + l; t < e; t += 32) {
-      const float4 tp = S[t];
-      const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
-      if (key < bk[4]) {
-        int pos = t;
+      for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
+      if (qi < nq) {
+        const float4 po = stk[qi];
+        // pointAssociateToMap (:146-155): double transform, rounded to float
+        double w[3];
+        quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
+        const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
+        const int qx = (int)floorf((sx - st.gridMinX) * (1.0f / kMapCell)), qy = (int)floorf((sy - st.gridMinY) * (1.0f / kMapCell));
+        const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kMapNX - 1);
+        for (int row = qy - 1; row <= qy + 1; ++row) {
+          if (row < 0 || row >= kMapNY || x0 > x1) continue;
+          const int a = cs[row * kMapNX + x0], e = cs[row * kMapNX + x1 + 1];
+          for (int t = a + gl; t < e; t += kLmGroup) {
+            const float4 tp = S[t];
+            const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+            unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
+            if (key < bk[4]) {
+              int pos = t;
 #pragma unroll
-        for (int i = 0; i < 5; ++i)
-          if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+              for (int i = 0; i < 5; ++i)
+                if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+            }
+          }
+        }
+      }
+      // group merge: five rounds of "smallest head wins" (keys are unique: the low word is the sub-map index)
+      int head = 0, myPos[5];
+      unsigned long long fifth = 0xffffffffffffffffull;
+#pragma unroll
+      for (int rr = 0; rr < 5; ++rr) {
+        unsigned long long mine = 0xffffffffffffffffull;
+        int minePos = -1;
+#pragma unroll
+        for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
+        unsigned long long m = mine;
+#pragma unroll
+        for (int o = kLmGroup / 2; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(gmask, m, o); m = t < m ? t : m; }
+        const bool won = mine == m && m != 0xffffffffffffffffull;
+        const unsigned win = __ballot_sync(gmask, won) & gmask;
+        int wp = -1;
+        if (win) { wp = __shfl_sync(gmask, minePos, __ffs(win) - 1); if (won) head++; }
+        myPos[rr] = wp;
+        if (rr == 4) fifth = m;
+      }
+      if (gl == 0) {
+        const bool ok = fifth != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(fifth >> 32)) < 1.0;  // :479 / :547
+#pragma unroll
+        for (int i = 0; i < 5; ++i) s_pos[slot][i] = ok ? myPos[i] : -1;
       }
     }
-  }
-  // warp merge: five rounds of "smallest head wins"
-  unsigned long long top[5];
-  int topPos[5];
-  int head = 0;
+    __syncthreads();
+    // ---- phase B
+    const int qi = chunk + threadIdx.x;
+    if (qi < nq) {
+      const float4 po = stk[qi];
+      LMResidual R;
+      R.type = 0; R.px = po.x; R.py = po.y; R.pz = po.z;
 #pragma unroll
-  for (int r = 0; r < 5; ++r) {
-    unsigned long long mine = 0xffffffffffffffffull;
-    int minePos = -1;
+      for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
+      if (s_pos[threadIdx.x][4] >= 0) {
+        double P[5][3];
 #pragma unroll
-    for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
-    const unsigned long long m = warp_min_u64(mine);
-    const unsigned win = __ballot_sync(0xffffffffu, mine == m && m != 0xffffffffffffffffull);
-    top[r] = m;
-    int wp = -1;
-    if (win) {
-      const int src = __ffs(win) - 1;
-      wp = __shfl_sync(0xffffffffu, minePos, src);
-      if (l == src) head++;
-    }
-    topPos[r] = wp;
-  }
-  LMResidual R;
-  R.type = 0; R.px = po.x; R.py = po.y; R.pz = po.z;
-#pragma unroll
-  for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
-  if (top[4] != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(top[4] >> 32)) < 1.0) {  // :479 / :547
-    double P[5][3];
-#pragma unroll
-    for (int j = 0; j < 5; ++j) { const float4 tp = S[topPos[j]]; P[j][0] = tp.x; P[j][1] = tp.y; P[j][2] = tp.z; }
-    if (kind == 0) {  // :481-516
-      double c[3] = {0, 0, 0};
-      for (int j = 0; j < 5; ++j) { c[0] = c[0] + P[j][0]; c[1] = c[1] + P[j][1]; c[2] = c[2] + P[j][2]; }
-      c[0] = c[0] / 5.0; c[1] = c[1] / 5.0; c[2] = c[2] / 5.0;
-      double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-      for (int j = 0; j < 5; ++j) {
-        const double d[3] = {P[j][0] - c[0], P[j][1] - c[1], P[j][2] - c[2]};
-        for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) cov[r * 3 + q] += d[r] * d[q];
+        for (int j = 0; j < 5; ++j) { const float4 tp = S[s_pos[threadIdx.x][j]]; P[j][0] = tp.x; P[j][1] = tp.y; P[j][2] = tp.z; }
+        if (kind == 0) {  // :481-516
+          double c[3] = {0, 0, 0};
+          for (int j = 0; j < 5; ++j) { c[0] = c[0] + P[j][0]; c[1] = c[1] + P[j][1]; c[2] = c[2] + P[j][2]; }
+          c[0] = c[0] / 5.0; c[1] = c[1] / 5.0; c[2] = c[2] / 5.0;
+          double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+          for (int j = 0; j < 5; ++j) {
+            const double d[3] = {P[j][0] - c[0], P[j][1] - c[1], P[j][2] - c[2]};
+            for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) cov[r * 3 + q] += d[r] * d[q];
+          }
+          double ev[3], evec[3][3];
+          sym_eig3_dev(cov, ev, evec);
+          if (ev[2] > 3 * ev[1]) {
+            R.type = 1;
+            for (int i = 0; i < 3; ++i) { R.v[i] = 0.1 * evec[2][i] + c[i]; R.v[3 + i] = -0.1 * evec[2][i] + c[i]; }
+          }
+        } else {  // :545-580
+          double A[15], bb[5] = {-1, -1, -1, -1, -1}, n[3];
+          for (int j = 0; j < 5; ++j) { A[j * 3] = P[j][0]; A[j * 3 + 1] = P[j][1]; A[j * 3 + 2] = P[j][2]; }
+          colpiv_qr_solve_5x3_dev(A, bb, n);
+          const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+          const double d = 1 / nn;
+          n[0] /= nn; n[1] /= nn; n[2] /= nn;
+          bool ok = true;
+          for (int j = 0; j < 5; ++j)
+            if (fabs(n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + d) > 0.2) { ok = false; break; }
+          if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
+        }
       }
-      double ev[3], evec[3][3];
-      sym_eig3_dev(cov, ev, evec);
-      if (ev[2] > 3 * ev[1]) {
-        R.type = 1;
-        for (int i = 0; i < 3; ++i) { R.v[i] = 0.1 * evec[2][i] + c[i]; R.v[3 + i] = -0.1 * evec[2][i] + c[i]; }
-      }
-    } else {  // :545-580
-      double A[15], bb[5] = {-1, -1, -1, -1, -1}, n[3];
-      for (int j = 0; j < 5; ++j) { A[j * 3] = P[j][0]; A[j * 3 + 1] = P[j][1]; A[j * 3 + 2] = P[j][2]; }
-      colpiv_qr_solve_5x3_dev(A, bb, n);
-      const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-      const double d = 1 / nn;
-      n[0] /= nn; n[1] /= nn; n[2] /= nn;
-      bool ok = true;
-      for (int j = 0; j < 5; ++j)
-        if (fabs(n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + d) > 0.2) { ok = false; break; }
-      if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
+      res[((size_t)b * 2 + kind) * cap + qi] = R;
     }
-  }
-  if (l == 0) *out = R;
+    __syncthreads();
   }
 }
 
-// lm_solve: grid (B), block 256: one outer pass of :458-626 (the association was just done by lm_associate).
-__global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res, int cap, int pass,
-                                                 int max_iterations) {
+
+// lm_solve: one outer pass of :458-626 (the association was just done by lm_associate).  grid (kLmCluster, B), block 256,
+// one thread-block CLUSTER per stream: ~13 k residual blocks of double-precision Jacobians are too much for one SM per
+// evaluation (the kernel was FP64-bound at one CTA per stream), so the residuals are dealt to the cluster's CTAs, every
+// CTA reduces its share to 28 doubles, and the partial sums are exchanged through distributed shared memory.  Every CTA
+// adds them in rank order and runs the (cheap, deterministic) trust-region bookkeeping itself, so all of them hold
+// bit-identical state and no broadcast is needed; only rank 0 writes results.
+constexpr int kLmCluster = 8;
+__global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
+                                                                                    int cap, int pass, int max_iterations) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ LMShared S;
   __shared__ int s_cnt[2];
-  const int b = blockIdx.x;
+  __shared__ double s_part[2][28];     // this CTA's partial sums, two generations (one cluster barrier per evaluation)
+  __shared__ SolveTrace s_trace;       // ranks > 0 keep their (identical) trace here
+  const int b = blockIdx.y;
+  const int rank = (int)cluster.block_rank();
   LMState& st = stAll[b];
-  if (!st.solved) return;
-  SolveTrace* tr = &st.trace[pass];
+  if (!st.solved) return;              // uniform over the cluster
+  SolveTrace* tr = rank == 0 ? &st.trace[pass] : &s_trace;
   const LMResidual* rc = res + ((size_t)b * 2 + 0) * cap;
   const LMResidual* rs = res + ((size_t)b * 2 + 1) * cap;
   const int nc = st.stackNum[0], ns = st.stackNum[1];
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) for (int i = 0; i < 7; ++i) S.x[i] = st.parameters[i];
   __syncthreads();
-  {
+  if (rank == 0) {
     int a = 0, c = 0;
     for (int i = threadIdx.x; i < nc; i += blockDim.x) a += rc[i].type == 1;
     for (int i = threadIdx.x; i < ns; i += blockDim.x) c += rs[i].type == 2;
@@ -553,28 +595,40 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
     __syncthreads();
     if (threadIdx.x == 0) { tr->n_corner = s_cnt[0]; tr->n_plane = s_cnt[1]; }
   }
+  int gen = 0;
+  const int first = rank * blockDim.x + threadIdx.x, stride = kLmCluster * blockDim.x;
   auto evaluate = [&](const double* x) {
     double acc[28];
 #pragma unroll
     for (int k = 0; k < 28; ++k) acc[k] = 0.0;
     const double q[4] = {x[0], x[1], x[2], x[3]};
     const double t[3] = {x[4], x[5], x[6]};
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) {
+    for (int i = first; i < nc; i += stride) {
       const LMResidual& R = rc[i];
       if (R.type != 1) continue;
       const double a[3] = {R.v[0], R.v[1], R.v[2]}, bb[3] = {R.v[3], R.v[4], R.v[5]};
       edge_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), a, bb, acc);
     }
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) {
+    for (int i = first; i < ns; i += stride) {
       const LMResidual& R = rs[i];
       if (R.type != 2) continue;
       const double n[3] = {R.v[0], R.v[1], R.v[2]};
       plane_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), n, R.v[3], acc);
     }
     block_reduce28(acc, S.red, S.scratch);
+    if (threadIdx.x < 28) s_part[gen][threadIdx.x] = S.red[threadIdx.x];
+    cluster.sync();
+    if (threadIdx.x < 28) {
+      double sum = 0.0;
+      for (int r = 0; r < kLmCluster; ++r) sum += cluster.map_shared_rank(&s_part[gen][0], r)[threadIdx.x];
+      S.red[threadIdx.x] = sum;
+    }
+    gen ^= 1;
+    __syncthreads();
   };
   lm_solve_block(S, tr, max_iterations, false, evaluate);
-  if (threadIdx.x == 0) for (int i = 0; i < 7; ++i) st.parameters[i] = S.x[i];
+  if (rank == 0 && threadIdx.x == 0) for (int i = 0; i < 7; ++i) st.parameters[i] = S.x[i];
+  cluster.sync();                      // nobody leaves while a peer may still read its partial sums
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -942,8 +996,8 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
-    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(512, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
-    VB_LAUNCH(prof, K_LM_SOLVE, st, lm_solve<<<B, 256, 0, st>>>(lm->st, lm->res, cap, tp, lm->p.lm_max_iterations));
+    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(64, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
+    VB_LAUNCH(prof, K_LM_SOLVE, st, lm_solve<<<dim3(kLmCluster, B), 256, 0, st>>>(lm->st, lm->res, cap, tp, lm->p.lm_max_iterations));
   }
   // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back
   VB_LAUNCH(prof, K_LM_MISC, st, lm_transform_update<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B));
