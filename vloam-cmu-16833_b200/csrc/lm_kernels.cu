@@ -17,6 +17,7 @@
 #include <cooperative_groups.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "../../include/vloam_b200.h"
@@ -566,8 +567,8 @@ __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ 
 // CTA reduces its share to 28 doubles, and the partial sums are exchanged through distributed shared memory.  Every CTA
 // adds them in rank order and runs the (cheap, deterministic) trust-region bookkeeping itself, so all of them hold
 // bit-identical state and no broadcast is needed; only rank 0 writes results.
-constexpr int kLmCluster = 8;
-__global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
+constexpr int kLmClusterMax = 8;     // cluster size is a launch attribute (1, 2, 4 or 8): see lm_run
+__global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
                                                                                     int cap, int pass, int max_iterations) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -576,7 +577,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(256) lm_sol
   __shared__ double s_part[2][28];     // this CTA's partial sums, two generations (one cluster barrier per evaluation)
   __shared__ SolveTrace s_trace;       // ranks > 0 keep their (identical) trace here
   const int b = blockIdx.y;
-  const int rank = (int)cluster.block_rank();
+  const int rank = (int)cluster.block_rank(), csize = (int)cluster.num_blocks();
   LMState& st = stAll[b];
   if (!st.solved) return;              // uniform over the cluster
   SolveTrace* tr = rank == 0 ? &st.trace[pass] : &s_trace;
@@ -596,7 +597,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(256) lm_sol
     if (threadIdx.x == 0) { tr->n_corner = s_cnt[0]; tr->n_plane = s_cnt[1]; }
   }
   int gen = 0;
-  const int first = rank * blockDim.x + threadIdx.x, stride = kLmCluster * blockDim.x;
+  const int first = rank * blockDim.x + threadIdx.x, stride = csize * blockDim.x;
   auto evaluate = [&](const double* x) {
     double acc[28];
 #pragma unroll
@@ -620,7 +621,7 @@ __global__ void __cluster_dims__(kLmCluster, 1, 1) __launch_bounds__(256) lm_sol
     cluster.sync();
     if (threadIdx.x < 28) {
       double sum = 0.0;
-      for (int r = 0; r < kLmCluster; ++r) sum += cluster.map_shared_rank(&s_part[gen][0], r)[threadIdx.x];
+      for (int r = 0; r < csize; ++r) sum += cluster.map_shared_rank(&s_part[gen][0], r)[threadIdx.x];
       S.red[threadIdx.x] = sum;
     }
     gen ^= 1;
@@ -997,7 +998,20 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
     VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(64, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
-    VB_LAUNCH(prof, K_LM_SOLVE, st, lm_solve<<<dim3(kLmCluster, B), 256, 0, st>>>(lm->st, lm->res, cap, tp, lm->p.lm_max_iterations));
+    {
+      // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
+      // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
+      static const int forced = [] { const char* e = getenv("VLOAM_LM_CLUSTER"); return e ? atoi(e) : 0; }();
+      int cs = forced > 0 ? forced : (B <= 37 ? 4 : B <= 74 ? 2 : 1);
+      cs = cs >= 8 ? kLmClusterMax : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(cs, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.attrs = at; cfg.numAttrs = 1;
+      VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve, lm->st, (const LMResidual*)lm->res, cap, tp, lm->p.lm_max_iterations));
+    }
   }
   // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back
   VB_LAUNCH(prof, K_LM_MISC, st, lm_transform_update<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B));
