@@ -302,12 +302,12 @@ def algorithmic_bytes(kernel, c):
         # laser mapping (M = sub-map points, S = down-sampled scan points)
         "lm_prepare": 0, "lm_misc": 0,
         "lm_voxel": (c["nLS"] + c["nLF"]) * (16 + 16),
-        "lm_grid": c.get("M", 0) * (16 + 16) // 3,          # three launches: count, scan, scatter
+        "lm_index": 0,                                      # only cubes without a column index are (re)indexed: none in steady state
         "lm_associate": c.get("S", 0) * 96 + c.get("S", 0) * 9 * 8 * 16,
         "lm_solve": c.get("S", 0) * 80,
         "lm_insert": c.get("S", 0) * 48,
-        "lm_refilter": c.get("M", 0) * (16 * 4 + 20 * 4) // 3,
-        "lm_place": 0,
+        "lm_refilter": c.get("Mw", 0) * (16 * 3 + 8 * 4),   # rewritten cubes: slab read, concat written + read, keys/values, staged written
+        "lm_place": c.get("Mw", 0) * (16 * 3 + 16) // 3,    # three launches; write-back: staged read, slab + sorted copy written
     }
     return table.get(kernel, 0)
 
@@ -535,6 +535,7 @@ def run_ours(args, rank, world, local_rank):
                               "kernels": {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in ktimes.items()}}), flush=True)
         return
     lm_info_all = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64) if do_map else None
+    map_stats_all = np.concatenate([hd.map_stats() for hd in loms]).astype(np.int64) if do_map else None
     for g in groups[1:]:
         g.close()               # the e2e leg below reuses the first context; free the other groups' device memory
 
@@ -602,6 +603,7 @@ def run_ours(args, rank, world, local_rank):
         info = lm_info_all
         tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
         tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
+        tot["Mw"] = int(map_stats_all[:, :, 8].sum())
     kern = {}
     for name, (ms, cnt) in ktimes.items():
         by = algorithmic_bytes(name, tot) // H          # one launch covers one handle's B/H streams
@@ -658,6 +660,13 @@ def run_ours(args, rank, world, local_rank):
         "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kern.items()},
         "curvature_kernel": None if curv is None else {"gbs": curv["gbs"], "frac": curv["gbs"] / peaks["hbm_gbs"]},
         "single_stream_latency_ms": lat_ms,
+        "map": None if not do_map else {
+            "points_per_stream": float(map_stats_all[:, :, 0].sum() / B), "cubes_per_stream": float(map_stats_all[:, :, 3].sum() / B),
+            "cubes_rewritten_last_scan_per_stream": float(map_stats_all[:, :, 5].sum() / B),
+            "points_rewritten_last_scan_per_stream": float(map_stats_all[:, :, 8].sum() / B),
+            "fixed_point_cubes_per_stream": float(map_stats_all[:, :, 4].sum() / B), "repacks": int(map_stats_all[:, :, 6].sum()),
+            "note": "valid cubes that are fixed points of their voxel filter and received no point are not re-filtered "
+                    "(the reference filters them again and gets the same cloud back)"},
         "cpu_baseline": {"value": cpu_value, "unit": "scans/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} scans of one stream, 1 thread: SR {tm['sr_ms']/n_cpu:.1f} ms + LO {tm['lo_ms']/n_cpu:.1f} ms"
                                    + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"},

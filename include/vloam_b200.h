@@ -168,16 +168,18 @@ int vloam_get_lo_trace(vloam_lidar* h, int stream, int pass, int* corr, double* 
 int vloam_laser_mapping(vloam_lidar* h, double* pose_out);
 int vloam_get_lm_pose(vloam_lidar* h, double* pose_out);
 /* Seed / read one 50 m map cube (index i + 21 j + 441 k, laser_mapping.cpp:412) of one stream; kind 0 = corner,
- * 1 = surf.  Used to pre-build the 1 M-point map of the benchmark and by the parity tests. */
+ * 1 = surf.  Used to pre-build the 1 M-point map of the benchmark and by the parity tests.  Seeded points must lie inside
+ * the cube (laser_mapping.cpp:643-652 with the stream's current centre offsets), like every point the mapping inserts:
+ * VLOAM_E_CAPACITY otherwise, or when map_capacity_points is exceeded. */
 int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const float* xyzi, int n);
 int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xyzi_out, int capacity_points, int* n_out);
 /* info[batch][8] = cenWidth, cenHeight, cenDepth, validNum, cornerFromMapNum, surfFromMapNum, cornerStackNum, surfStackNum */
 int vloam_get_lm_info(vloam_lidar* h, int* info);
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
-/* Map storage read-out, stats[batch][2][8] per stream and feature kind (0 corner, 1 surf): points in the map, high-water
+/* Map storage read-out, stats[batch][2][10] per stream and feature kind (0 corner, 1 surf): points in the map, high-water
  * mark of the slab pool, pool index, non-empty cubes, cubes known to be fixed points of their voxel filter (skipped by
  * the per-scan re-filter of laser_mapping.cpp:689-702 until they receive a point), cubes rewritten by the last scan,
- * re-packs so far, slab capacity in use. */
+ * re-packs so far, slab capacity in use, points in the rewritten cubes, column-index table slots in use. */
 int vloam_get_map_stats(vloam_lidar* h, int* stats);
 
 /* ------------------------------------------------------------------ point-sharded solve (multi-GPU)

@@ -385,9 +385,10 @@ class LidarOdometryMapping:
         return info
 
     def map_stats(self):
-        """(batch, 2, 8) int32 per stream and kind: points, pool high-water mark, pool index, non-empty cubes, fixed-point
-        cubes, cubes rewritten by the last scan, re-packs so far, slab capacity in use."""
-        st = np.zeros((self.batch, 2, 8), np.int32)
+        """(batch, 2, 10) int32 per stream and kind: points, pool high-water mark, pool index, non-empty cubes, fixed-point
+        cubes, cubes rewritten by the last scan, re-packs so far, slab capacity in use, points in the rewritten cubes,
+        column-index table slots in use."""
+        st = np.zeros((self.batch, 2, 10), np.int32)
         self.ctx.check(lib().vloam_get_map_stats(self._h, st.ctypes.data_as(c_ip)))
         return st
 

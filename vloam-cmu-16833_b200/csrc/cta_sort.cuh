@@ -46,16 +46,13 @@ static __device__ int cta_radix_sort(unsigned* kA, unsigned* vA, unsigned* kB, u
     unsigned* vout = cur ? vA : vB;
     for (int d = l; d < 256; d += 32) S.off[w][d] = 0;
     __syncwarp();
-    for (int base = w0; base < w1; base += 32) {
-      const int k = base + l;
-      const bool act = k < w1;
-      const unsigned amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const int d = (kin[k] >> shift) & 255;
-        const unsigned peers = __match_any_sync(amask, d);
-        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
-      }
-      __syncwarp();
+    // per-warp digit histogram: four independent loads in flight per lane, shared-memory atomics (order is irrelevant here)
+    for (int base = w0; base < w1; base += 128) {
+      unsigned kk[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const int k = base + u * 32 + l; kk[u] = k < w1 ? kin[k] : 0u; }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (base + u * 32 + l < w1) atomicAdd(&S.off[w][(kk[u] >> shift) & 255], 1);
     }
     __syncthreads();
     if (threadIdx.x < 256) {
@@ -76,22 +73,31 @@ static __device__ int cta_radix_sort(unsigned* kA, unsigned* vA, unsigned* kB, u
       for (int q = 0; q < 32; ++q) { const int c = S.off[q][d]; S.off[q][d] = run; run += c; }
     }
     __syncthreads();
-    for (int base = w0; base < w1; base += 32) {
-      const int k = base + l;
-      const bool act = k < w1;
-      const unsigned amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const unsigned key = kin[k];
-        const int d = (key >> shift) & 255;
-        const unsigned peers = __match_any_sync(amask, d);
-        const int rank = __popc(peers & ((1u << l) - 1u));
-        const int dst = S.off[w][d] + rank;
-        kout[dst] = key;
-        vout[dst] = vin[k];
-        __syncwarp(amask);
-        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+    // stable scatter: ranks inside a 32-key step by match_any; four steps' keys and values are loaded up front
+    for (int base = w0; base < w1; base += 128) {
+      unsigned kk[4], vv[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int k = base + u * 32 + l;
+        kk[u] = k < w1 ? kin[k] : 0u;
+        vv[u] = k < w1 ? vin[k] : 0u;
       }
-      __syncwarp();
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const bool act = base + u * 32 + l < w1;
+        const unsigned amask = __ballot_sync(0xffffffffu, act);
+        if (act) {
+          const int d = (kk[u] >> shift) & 255;
+          const unsigned peers = __match_any_sync(amask, d);
+          const int rank = __popc(peers & ((1u << l) - 1u));
+          const int dst = S.off[w][d] + rank;
+          kout[dst] = kk[u];
+          vout[dst] = vv[u];
+          __syncwarp(amask);
+          if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
+        }
+        __syncwarp();
+      }
     }
     __syncthreads();
     cur ^= 1;

@@ -31,8 +31,10 @@ namespace vb {
 constexpr int kCubeW = 21, kCubeH = 21, kCubeD = 11, kCubes = kCubeW * kCubeH * kCubeD;  // laser_mapping.h:110-114
 constexpr int kMaxValid = 125;                                                           // laser_mapping.h:116
 constexpr int kMaxWork = 200;   // cubes rewritten per scan: the valid ones plus cubes that received points
-constexpr float kMapCell = 1.001f;
-constexpr int kMapNX = 256, kMapNY = 256, kMapCols = kMapNX * kMapNY;  // 5 cubes x 50 m = 250 m < 256 * 1.001 m
+// Column index of a cube (the kd-tree replacement, see lm_associate): 50 x 50 xy-columns of 1.001 m per 50 m cube.
+constexpr float kCubeCell = 1.001f;
+constexpr int kCubeCellsX = 50, kCubeCells = kCubeCellsX * kCubeCellsX;
+constexpr int kTabSlots = 512;   // column tables per stream and kind (>= the 125 valid cubes + the cubes one scan can touch)
 
 struct LMState {
   double parameters[7];                 // q_w_curr (x,y,z,w), t_w_curr      laser_mapping.cpp:74-83
@@ -49,7 +51,9 @@ struct LMState {
   int cur[2];                           // which of the two pools holds this stream's corner / surf map
   int compact[2];                       // this scan's write-back re-packs the whole map into the other pool
   int repacks[2];                       // re-packs so far
-  float gridMinX, gridMinY;             // origin of the sub-map column index
+  int tabEnd[2];                        // column-table slots handed out so far
+  int buildNum[2], buildList[2][kMaxValid];   // valid cubes whose column index has to be (re)built before the association
+  short entryNext[kMaxValid];           // next valid-list entry naming the same cube (-1: none); heads in LMDevice::entryHead
   int workNum[2];
   int workCube[2][kMaxWork], workFilter[2][kMaxWork], workNew0[2][kMaxWork], workNewN[2][kMaxWork];
   int workIn0[2][kMaxWork + 1];         // offsets of each work cube's (old ++ new) input inside the concat buffer
@@ -78,6 +82,9 @@ struct LMDevice {
   int* cubeCnt[2] = {nullptr, nullptr};
   int* cubeCap[2] = {nullptr, nullptr};
   int* cubeFix[2] = {nullptr, nullptr};
+  int* cubeTab[2] = {nullptr, nullptr};   // slot of the cube's column table in tabPool, -1 = no valid index
+  int* tabPool = nullptr;                 // [B][2][kTabSlots][kCubeCells + 1] column starts inside the cube's sorted copy
+  short* entryHead = nullptr;             // [B][kCubes] first entry of the valid list naming this cube, -1 = not in the sub-map
   float4* mapPts[2] = {nullptr, nullptr}; // two pools [B][2][mapCap]; a stream changes pool only when its map is re-packed
   float4* snap = nullptr;                 // [B][2][mapCap] laserCloud{Corner,Surf}FromMap of the last scan (debug_keep_submap)
   float4* stack = nullptr;                // [B][2][cap]  down-sampled scan (laserCloudCornerStack / SurfStack)
@@ -85,8 +92,7 @@ struct LMDevice {
   unsigned* keyA = nullptr; unsigned* valA = nullptr; unsigned* keyB = nullptr; unsigned* valB = nullptr;  // [B][2][workCap]
   float4* concat = nullptr;               // [B][2][workCap] refilter inputs (old ++ new per work cube)
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
-  int* cellStart = nullptr; int* cursor = nullptr;  // [B][2][kMapCols + 1]
-  float4* sorted = nullptr;               // [B][2][mapCap] sub-map sorted by column, w = sub-map index
+  float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
   LMResidual* res = nullptr;              // [B][2][cap]
   double* pose = nullptr;                 // [B][16]
   short* workOf = nullptr;                // [B][2][kCubes]
@@ -163,30 +169,85 @@ __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf
   const int cur = cta_radix_sort(kA, vA, kB, vB, n, bits, S);
   const unsigned* keys = cur ? kB : kA;
   const unsigned* vals = cur ? vB : vA;
-  // heads + ordered sums: thread t owns a contiguous run of sorted entries and finishes every voxel starting in it
-  const int per = (n + 1023) / 1024;
-  const int q0 = min((int)threadIdx.x * per, n), q1 = min(q0 + per, n);
-  int nh = 0;
-  for (int q = q0; q < q1; ++q) nh += (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
-  int opos = block_exclusive_scan1024(nh, S);
+  // Segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n).
+  // A warp takes 32 consecutive sorted entries at a time: every lane loads its own point (independent gathers, one
+  // latency per window instead of one per point), then each head lane adds the points of its voxel strictly left to
+  // right, fetching them from the following lanes (this window or the next, already in registers) by shuffle.
+  unsigned* winHeads = cur ? kA : kB;                 // the sort's spare key buffer: heads per window -> exclusive prefix
+  const int nwin = (n + 31) >> 5;
+  for (int v = w; v < nwin; v += 32) {
+    const int q = v * 32 + l;
+    const bool head = q < n && (q == 0 || keys[q] != keys[q - 1]);
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    if (l == 0) winHeads[v] = __popc(hm);
+  }
+  __syncthreads();
+  {
+    const int per = (nwin + 1023) / 1024;
+    const int v0 = min((int)threadIdx.x * per, nwin), v1 = min(v0 + per, nwin);
+    int sum = 0;
+    for (int v = v0; v < v1; ++v) sum += (int)winHeads[v];
+    int run = block_exclusive_scan1024(sum, S);
+    for (int v = v0; v < v1; ++v) { const int t = (int)winHeads[v]; winHeads[v] = (unsigned)run; run += t; }
+  }
   const int total = S.total;
+  __syncthreads();
   int inside = 1;
-  for (int q = q0; q < q1; ++q) {
-    if (!(q == 0 || keys[q] != keys[q - 1])) continue;
-    const unsigned vox = keys[q];
-    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-    float v0 = 0.f, v1 = 0.f, v2 = 0.f;   // lattice coordinates of the voxel (those of its first member)
-    int cnt = 0;
-    for (int qq = q; qq < n && keys[qq] == vox; ++qq) {
-      const float4 p = in[vals[qq]];
-      if (cnt == 0) { v0 = floorf(__fmul_rn(p.x, inv)); v1 = floorf(__fmul_rn(p.y, inv)); v2 = floorf(__fmul_rn(p.z, inv)); }
-      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
-      ++cnt;
+  {
+    const int perw = (nwin + 31) / 32;
+    const int v0 = min(w * perw, nwin), v1 = min(v0 + perw, nwin);
+    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1;
+    unsigned k0 = 0, bnd0 = 0xffffffffu, hd0 = 0, bnd1, hd1;
+    auto load_window = [&](int u, float4& p, unsigned& k, unsigned& bnd, unsigned& hd) {
+      const int q = u * 32 + l;
+      const bool ok = q < n;
+      k = ok ? keys[q] : 0u;
+      const bool head = ok && (q == 0 || keys[q - 1] != k);
+      p = ok ? in[vals[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
+      hd = __ballot_sync(0xffffffffu, head);
+      bnd = hd | ~__ballot_sync(0xffffffffu, ok);       // a run ends at the next head or at the end of the data
+    };
+    if (v0 < v1) load_window(v0, p0, k0, bnd0, hd0);
+    for (int v = v0; v < v1; ++v) {
+      unsigned k1;
+      load_window(v + 1, p1, k1, bnd1, hd1);
+      const bool head = (hd0 >> l) & 1u;
+      // run length of the voxel starting at this lane, seen through the 64-entry window pair
+      const unsigned long long Bm = (unsigned long long)bnd0 | ((unsigned long long)bnd1 << 32);
+      const unsigned long long rest = Bm >> (l + 1);
+      const bool open = rest == 0ull;                    // no boundary in sight: the run leaves the window pair
+      int len = head ? (open ? 64 - l : (int)__ffsll((long long)rest)) : 0;
+      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      sx = __fadd_rn(sx, p0.x); sy = __fadd_rn(sy, p0.y); sz = __fadd_rn(sz, p0.z); si = __fadd_rn(si, p0.w);
+      for (int j = 1; j < maxlen; ++j) {
+        // entry l + j lives in lane (l + j) & 31 of this window (if l + j < 32) or of the next one; lane s is asked
+        // for its current-window point by reader s - j and for its next-window point by reader s + 32 - j, never both
+        const bool curw = l >= j;
+        const int src = (l + j) & 31;
+        const float gx = __shfl_sync(0xffffffffu, curw ? p0.x : p1.x, src);
+        const float gy = __shfl_sync(0xffffffffu, curw ? p0.y : p1.y, src);
+        const float gz = __shfl_sync(0xffffffffu, curw ? p0.z : p1.z, src);
+        const float gi = __shfl_sync(0xffffffffu, curw ? p0.w : p1.w, src);
+        if (j < len) { sx = __fadd_rn(sx, gx); sy = __fadd_rn(sy, gy); sz = __fadd_rn(sz, gz); si = __fadd_rn(si, gi); }
+      }
+      if (head) {
+        if (open) {   // rare: more than 64 - l points of one voxel; finish from memory
+          for (int qq = v * 32 + 64; qq < n && keys[qq] == k0; ++qq) {
+            const float4 pp = in[vals[qq]];
+            sx = __fadd_rn(sx, pp.x); sy = __fadd_rn(sy, pp.y); sz = __fadd_rn(sz, pp.z); si = __fadd_rn(si, pp.w);
+            ++len;
+          }
+        }
+        const float nf = (float)len;
+        const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+        // the voxel's lattice coordinates are those of its first member, this lane's own point
+        if (floorf(__fmul_rn(c.x, inv)) != floorf(__fmul_rn(p0.x, inv)) || floorf(__fmul_rn(c.y, inv)) != floorf(__fmul_rn(p0.y, inv)) ||
+            floorf(__fmul_rn(c.z, inv)) != floorf(__fmul_rn(p0.z, inv))) inside = 0;
+        out[(int)winHeads[v] + __popc(hd0 & ((1u << l) - 1u))] = c;
+      }
+      p0 = p1; k0 = k1; bnd0 = bnd1; hd0 = hd1;
     }
-    const float nf = (float)cnt;
-    const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
-    if (floorf(__fmul_rn(c.x, inv)) != v0 || floorf(__fmul_rn(c.y, inv)) != v1 || floorf(__fmul_rn(c.z, inv)) != v2) inside = 0;
-    out[opos++] = c;
   }
   *fixedPoint = __syncthreads_and(inside);
   return total;
@@ -199,19 +260,24 @@ __device__ __forceinline__ int cube_coord(double v, int cen) {  // :207-216 / :6
   return c;
 }
 
-struct CubeTables { int* off; int* cnt; int* cap; int* fix; };   // [B][2][kCubes] each
+struct CubeTables { int* off; int* cnt; int* cap; int* fix; int* tab; };   // [B][2][kCubes] each
 struct MapPools { float4* p[2]; };                                // [B][2][mapCap] each
 __device__ __forceinline__ float4* stream_map(const MapPools& pools, const LMState& st, int b, int kind, int mapCap) {
   return (st.cur[kind] ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap;
 }
 
 // lm_prepare: grid (B), block 256.  Table ping-pong: reads tables `src`, writes the shifted tables to `dst`.
+// Also: the valid-cube list, the cube -> valid-entry lists the association walks, and column-table slots for the valid
+// cubes that have no usable column index yet (built next by lm_index_build).
 __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, const LOState* __restrict__ lo,
-                                                   const CubeTables src, const CubeTables dst, int resetValid) {
+                                                   const CubeTables src, const CubeTables dst, short* __restrict__ entryHeadAll,
+                                                   int resetValid) {
   const int b = blockIdx.x;
   LMState& st = stAll[b];
+  short* entryHead = entryHeadAll + (size_t)b * kCubes;
   __shared__ int sh[3];
   __shared__ int center[3];
+  __shared__ int s_gc[2];
   if (threadIdx.x == 0) {
     if (resetValid) st.validNum = 0;  // LaserMapping::reset (:127-131)
     // input(), :182-195: q_w_curr = q_wmap_wodom * q_wodom_curr; t_w_curr = q_wmap_wodom * t_wodom_curr + t_wmap_wodom
@@ -242,14 +308,15 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
     for (int c = threadIdx.x; c < kCubes; c += 256) {
       const int i = c % kCubeW, j = (c / kCubeW) % kCubeH, k = c / (kCubeW * kCubeH);
       const int si = i - sI, sj = j - sJ, sk = k - sK;  // new[i] = old[i - shift]; wrapped planes are cleared
-      int o = 0, n = 0, cp = 0, fx = 0;                  // (a cleared cube's slab is reclaimed by the next re-pack)
+      int o = 0, n = 0, cp = 0, fx = 0, tbs = -1;        // (a cleared cube's slab and table slot are reclaimed later)
       if (si >= 0 && si < kCubeW && sj >= 0 && sj < kCubeH && sk >= 0 && sk < kCubeD) {
         const int s = si + kCubeW * sj + kCubeW * kCubeH * sk;
-        o = src.off[tb + s]; n = src.cnt[tb + s]; cp = src.cap[tb + s]; fx = src.fix[tb + s];
+        o = src.off[tb + s]; n = src.cnt[tb + s]; cp = src.cap[tb + s]; fx = src.fix[tb + s]; tbs = src.tab[tb + s];
       }
-      dst.off[tb + c] = o; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp; dst.fix[tb + c] = fx;
+      dst.off[tb + c] = o; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp; dst.fix[tb + c] = fx; dst.tab[tb + c] = n > 0 ? tbs : -1;
     }
   }
+  for (int c = threadIdx.x; c < kCubes; c += 256) entryHead[c] = -1;
   __syncthreads();
   if (threadIdx.x == 0) {
     // :404-420 valid cubes in the reference's loop order
@@ -261,19 +328,41 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
           if (i >= 0 && i < kCubeW && j >= 0 && j < kCubeH && k >= 0 && k < kCubeD && vn < kMaxValid)
             st.validInd[vn++] = i + kCubeW * j + kCubeW * kCubeH * k;
     st.validNum = vn;
+    // cube -> entries of the valid list naming it (one entry unless the caller skipped reset()), ascending
+    for (int v = vn - 1; v >= 0; --v) { const int c = st.validInd[v]; st.entryNext[v] = entryHead[c]; entryHead[c] = (short)v; }
     for (int kind = 0; kind < 2; ++kind) {
-      const int* cD = dst.cnt + ((size_t)b * 2 + kind) * kCubes;
-      int acc = 0;
-      for (int v = 0; v < vn; ++v) { st.validPrefix[kind][v] = acc; acc += cD[st.validInd[v]]; }
+      const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+      int acc = 0, need = 0;
+      for (int v = 0; v < vn; ++v) {
+        const int c = st.validInd[v];
+        st.validPrefix[kind][v] = acc; acc += dst.cnt[tb + c];
+        if (entryHead[c] == v && dst.cnt[tb + c] > 0 && dst.tab[tb + c] < 0) ++need;
+      }
       st.validPrefix[kind][vn] = acc;
       st.fromMapNum[kind] = acc;
+      s_gc[kind] = st.tabEnd[kind] + need > kTabSlots ? 1 : 0;   // out of table slots: drop every index of this kind, start over
     }
     st.solved = (st.fromMapNum[0] > 10 && st.fromMapNum[1] > 50) ? 1 : 0;  // :448
-    // origin of the column index: the 5 x 5 block of 50 m cubes around the centre cube (plus half a column of slack)
-    st.gridMinX = (float)((cI - 2 - st.cenW) * 50.0 - 25.0 - 0.5);
-    st.gridMinY = (float)((cJ - 2 - st.cenH) * 50.0 - 25.0 - 0.5);
     st.trace[0].n_records = st.trace[1].n_records = 0;
     st.trace[0].n_corner = st.trace[0].n_plane = st.trace[1].n_corner = st.trace[1].n_plane = 0;
+  }
+  __syncthreads();
+  for (int kind = 0; kind < 2; ++kind)
+    if (s_gc[kind]) for (int c = threadIdx.x; c < kCubes; c += 256) dst.tab[((size_t)b * 2 + kind) * kCubes + c] = -1;
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int kind = threadIdx.x;
+    const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+    int te = s_gc[kind] ? 0 : st.tabEnd[kind], nb = 0;
+    if (st.solved)
+      for (int v = 0; v < st.validNum; ++v) {
+        const int c = st.validInd[v];
+        if (entryHead[c] != v || dst.cnt[tb + c] == 0 || dst.tab[tb + c] >= 0) continue;
+        dst.tab[tb + c] = te++;               // <= kMaxValid new slots after a reset of the slot counter: always fits
+        st.buildList[kind][nb++] = c;
+      }
+    st.tabEnd[kind] = te;
+    st.buildNum[kind] = nb;
   }
 }
 
@@ -303,50 +392,63 @@ __device__ __forceinline__ float4 submap_point(const LMState& st, int kind, cons
   while (hi - lo > 1) { const int mid = (lo + hi) >> 1; if (st.validPrefix[kind][mid] <= g) lo = mid; else hi = mid; }
   return map[off[st.validInd[lo]] + (g - st.validPrefix[kind][lo])];
 }
-__device__ __forceinline__ int map_col(const LMState& st, float x, float y) {
-  const int ix = min(max((int)floorf((x - st.gridMinX) * (1.0f / kMapCell)), 0), kMapNX - 1);
-  const int iy = min(max((int)floorf((y - st.gridMinY) * (1.0f / kMapCell)), 0), kMapNY - 1);
-  return iy * kMapNX + ix;
-}
-// grid (nblk, 2, B), block 256
-__global__ void __launch_bounds__(256) lm_grid_count(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
-                                                      const MapPools pools, int mapCap, int* __restrict__ cells) {
-  const int kind = blockIdx.y, b = blockIdx.z;
-  const LMState& st = stAll[b];
-  if (!st.solved) return;
-  const float4* map = stream_map(pools, st, b, kind, mapCap);
-  for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
-    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, map, g);
-    atomicAdd(&cells[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
+// ---------------------------------------------------------------------------------------------------------------
+// Column index of one cube: the cube's points counting-sorted into 50 x 50 xy-columns of 1.001 m (origin = the cube's
+// min corner), kept beside the cube until the cube's content changes.  Replaces the kd-trees the reference rebuilds
+// over the whole sub-map on every scan (:452-453): here only the cubes a scan rewrites are re-indexed.
+// A match needs its 5th neighbour within 1 m (:479, :547) and |dx| < 1 m moves a point by at most one 1.001 m column
+// (the 0.1 % margin dominates the float rounding of the column coordinate), so the 3 x 3 column block around the query
+// in every cube the 1.001 m box around the query touches holds every point that can matter: one visit, exact.
+__device__ __forceinline__ float cube_min_coord(int idx, int cen) { return (float)((idx - cen) * 50.0 - 25.0); }
+__device__ __forceinline__ int cube_cell(float v, float mn) { return (int)floorf((v - mn) * (1.0f / kCubeCell)); }
+__device__ __forceinline__ int cube_cell_clamped(float v, float mn) { return min(max(cube_cell(v, mn), 0), kCubeCellsX - 1); }
+// One CTA of 256 threads.  pts[0..n): the cube's slab; tab[kCubeCells + 1] (global) receives the column starts; sortedOut[0..n)
+// the column-sorted copy with w = index inside the cube.  s_cells: kCubeCells + 1 ints of shared memory, s_w: 8 ints.
+__device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, float minX, float minY, int* __restrict__ tab,
+                                     float4* __restrict__ sortedOut, int* s_cells, int* s_w) {
+  for (int i = threadIdx.x; i <= kCubeCells; i += 256) s_cells[i] = 0;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float4 p = pts[i];
+    atomicAdd(&s_cells[cube_cell_clamped(p.y, minY) * kCubeCellsX + cube_cell_clamped(p.x, minX)], 1);
   }
-}
-// grid (2, B), block 1024: exclusive scan of the column counts; cells -> starts (kept in `cellStart`) and cursors
-__global__ void __launch_bounds__(1024) lm_grid_scan(const LMState* __restrict__ stAll, int* __restrict__ cellStart, int* __restrict__ cursor) {
-  __shared__ SortSmem S;
-  const int kind = blockIdx.x, b = blockIdx.y;
-  if (!stAll[b].solved) return;
-  int* cs = cellStart + ((size_t)b * 2 + kind) * (kMapCols + 1);
-  int* cu = cursor + ((size_t)b * 2 + kind) * (kMapCols + 1);
-  const int chunk = kMapCols / 1024;
-  const int c0 = threadIdx.x * chunk;
+  __syncthreads();
+  constexpr int per = (kCubeCells + 255) / 256;
+  const int c0 = min((int)threadIdx.x * per, kCubeCells), c1 = min(c0 + per, kCubeCells);
   int sum = 0;
-  for (int i = 0; i < chunk; ++i) sum += cu[c0 + i];
-  int run = block_exclusive_scan1024(sum, S);
-  for (int i = 0; i < chunk; ++i) { const int t = cu[c0 + i]; cu[c0 + i] = run; cs[c0 + i] = run; run += t; }
-  if (threadIdx.x == 1023) { cs[kMapCols] = run; cu[kMapCols] = run; }
-}
-__global__ void __launch_bounds__(256) lm_grid_scatter(const LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
-                                                        const MapPools pools, int mapCap, int* __restrict__ cursor,
-                                                        float4* __restrict__ sorted) {
-  const int kind = blockIdx.y, b = blockIdx.z;
-  const LMState& st = stAll[b];
-  if (!st.solved) return;
-  const float4* map = stream_map(pools, st, b, kind, mapCap);
-  for (int g = blockIdx.x * 256 + threadIdx.x; g < st.fromMapNum[kind]; g += gridDim.x * 256) {
-    const float4 p = submap_point(st, kind, cubeOff + ((size_t)b * 2 + kind) * kCubes, map, g);
-    const int pos = atomicAdd(&cursor[((size_t)b * 2 + kind) * (kMapCols + 1) + map_col(st, p.x, p.y)], 1);
-    sorted[((size_t)b * 2 + kind) * mapCap + pos] = make_float4(p.x, p.y, p.z, __int_as_float(g));
+  for (int c = c0; c < c1; ++c) sum += s_cells[c];
+  int sc = sum;
+  const int l = lane_id(), w = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
+  if (l == 31) s_w[w] = sc;
+  __syncthreads();
+  int run = sc - sum;
+  for (int q = 0; q < w; ++q) run += s_w[q];
+  for (int c = c0; c < c1; ++c) { const int t = s_cells[c]; s_cells[c] = run; tab[c] = run; run += t; }
+  if (threadIdx.x == 255) tab[kCubeCells] = n;
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += 256) {
+    const float4 p = pts[i];
+    const int pos = atomicAdd(&s_cells[cube_cell_clamped(p.y, minY) * kCubeCellsX + cube_cell_clamped(p.x, minX)], 1);
+    sortedOut[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
   }
+  __syncthreads();
+}
+// lm_index_build: grid (kMaxValid, 2, B), block 256: CTA u indexes the u-th cube of lm_prepare's build list.
+__global__ void __launch_bounds__(256) lm_index_build(const LMState* __restrict__ stAll, const CubeTables T, const MapPools pools,
+                                                       int mapCap, int* __restrict__ tabPool, float4* __restrict__ sorted) {
+  __shared__ int s_cells[kCubeCells + 1];
+  __shared__ int s_w[8];
+  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (u >= st.buildNum[kind]) return;
+  const int c = st.buildList[kind][u];
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  const int off = T.off[tb + c], n = T.cnt[tb + c], slot = T.tab[tb + c];
+  cta_build_cube_index(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
+                       cube_min_coord((c / kCubeW) % kCubeH, st.cenH), tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1),
+                       sorted + ((size_t)b * 2 + kind) * mapCap + off, s_cells, s_w);
 }
 
 // laserCloudCornerFromMap / SurfFromMap (:422-428) kept for inspection (debug_keep_submap): grid (nblk, 2, B), block 256
@@ -439,7 +541,8 @@ __device__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5
 //            the bulk of the kernel.)
 constexpr int kLmGroup = 8;
 __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
-                                                     const int* __restrict__ cellStart, const float4* __restrict__ sorted,
+                                                     const CubeTables T, const short* __restrict__ entryHeadAll,
+                                                     const int* __restrict__ tabPool, const float4* __restrict__ sorted,
                                                      int mapCap, LMResidual* __restrict__ res) {
   __shared__ int s_pos[256][5];      // positions (in `sorted`) of the five nearest map points, -1 = no match (:479 / :547)
   const int kind = blockIdx.y, b = blockIdx.z;
@@ -449,8 +552,11 @@ __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ 
   const int lane = lane_id(), warp = threadIdx.x >> 5;
   const int g = lane / kLmGroup, gl = lane % kLmGroup;
   const unsigned gmask = 0xffu << (g * kLmGroup);
-  const int* cs = cellStart + ((size_t)b * 2 + kind) * (kMapCols + 1);
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  const short* entryHead = entryHeadAll + (size_t)b * kCubes;
+  const int* tabs = tabPool + ((size_t)b * 2 + kind) * kTabSlots * (kCubeCells + 1);
   const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
+  const int cenW = st.cenW, cenH = st.cenH, cenD = st.cenD;
   const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
   const double q0 = st.parameters[0], q1 = st.parameters[1], q2 = st.parameters[2], q3 = st.parameters[3];
   const double t0 = st.parameters[4], t1 = st.parameters[5], t2 = st.parameters[6];
@@ -470,23 +576,44 @@ __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ 
         double w[3];
         quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
         const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
-        const int qx = (int)floorf((sx - st.gridMinX) * (1.0f / kMapCell)), qy = (int)floorf((sy - st.gridMinY) * (1.0f / kMapCell));
-        const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kMapNX - 1);
-        for (int row = qy - 1; row <= qy + 1; ++row) {
-          if (row < 0 || row >= kMapNY || x0 > x1) continue;
-          const int a = cs[row * kMapNX + x0], e = cs[row * kMapNX + x1 + 1];
-          for (int t = a + gl; t < e; t += kLmGroup) {
-            const float4 tp = S[t];
-            const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-            unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
-            if (key < bk[4]) {
-              int pos = t;
+        // every cube the 1.001 m box around the query touches (one, unless the query sits at a cube border) ...
+        const int ci0 = max(cube_coord((double)sx - 1.001, cenW), 0), ci1 = min(cube_coord((double)sx + 1.001, cenW), kCubeW - 1);
+        const int cj0 = max(cube_coord((double)sy - 1.001, cenH), 0), cj1 = min(cube_coord((double)sy + 1.001, cenH), kCubeH - 1);
+        const int ck0 = max(cube_coord((double)sz - 1.001, cenD), 0), ck1 = min(cube_coord((double)sz + 1.001, cenD), kCubeD - 1);
+        for (int ck = ck0; ck <= ck1; ++ck)
+          for (int cj = cj0; cj <= cj1; ++cj)
+            for (int ci = ci0; ci <= ci1; ++ci) {
+              const int c = ci + kCubeW * cj + kCubeW * kCubeH * ck;
+              int e = entryHead[c];
+              if (e < 0) continue;                       // not part of the sub-map (:404-420)
+              const int slot = T.tab[tb + c];
+              if (slot < 0) continue;                    // empty cube
+              const int* tab = tabs + (size_t)slot * (kCubeCells + 1);
+              const int off = T.off[tb + c];
+              const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH);
+              const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
+              const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
+              if (x0 > x1) continue;
+              // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
+              // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
+              for (; e >= 0; e = st.entryNext[e]) {
+                const unsigned gBase = (unsigned)st.validPrefix[kind][e];
+                for (int row = max(qy - 1, 0); row <= min(qy + 1, kCubeCellsX - 1); ++row) {
+                  const int a = tab[row * kCubeCellsX + x0], en = tab[row * kCubeCellsX + x1 + 1];
+                  for (int t = a + gl; t < en; t += kLmGroup) {
+                    const float4 tp = S[off + t];
+                    const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+                    unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
+                    if (key < bk[4]) {
+                      int pos = off + t;
 #pragma unroll
-              for (int i = 0; i < 5; ++i)
-                if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+                      for (int i = 0; i < 5; ++i)
+                        if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+                    }
+                  }
+                }
+              }
             }
-          }
-        }
       }
       // group merge: five rounds of "smallest head wins" (keys are unique: the low word is the sub-map index)
       int head = 0, myPos[5];
@@ -791,6 +918,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
   for (int c = threadIdx.x; c < kCubes; c += 1024) {
     workOf[c] = -1;
     dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
+    dst.tab[tb + c] = src.tab[tb + c];
   }
   // (the other kind's CTA may raise st.error concurrently: one read, shared, keeps the barriers below uniform)
   if (threadIdx.x == 0) { s_compact = 0; s_nlive = 0; st.compact[kind] = 0; s_err = st.error & 3; }
@@ -811,7 +939,18 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
       dst.cnt[tb + c] = m;
       dst.fix[tb + c] = st.workFilter[kind][u] ? st.workFixed[kind][u] : 0;
     }
-    if (!s_compact) st.poolEnd[kind] = poolEnd;
+    if (!s_compact) {
+      st.poolEnd[kind] = poolEnd;
+      // a rewritten cube is re-indexed by lm_write_back: in its old table slot, a new one, or (no slot left) lazily by
+      // the next lm_prepare
+      int te = st.tabEnd[kind];
+      for (int u = 0; u < wn; ++u) {
+        const int c = st.workCube[kind][u];
+        if (st.workOutN[kind][u] == 0) dst.tab[tb + c] = -1;
+        else if (dst.tab[tb + c] < 0 && te < kTabSlots) dst.tab[tb + c] = te++;
+      }
+      st.tabEnd[kind] = te;
+    }
   }
   __syncthreads();
   if (!s_compact) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }
@@ -826,6 +965,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
   if (total > (long long)mapCap) {   // capacity exceeded: keep the old content (reported through the error bits of the pose export)
     for (int c = threadIdx.x; c < kCubes; c += 1024) {
       dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
+      dst.tab[tb + c] = src.tab[tb + c];
     }
     if (threadIdx.x == 0) { st.error |= 4; liveNumAll[b * 2 + kind] = 0; }
     return;
@@ -845,22 +985,38 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
     const int cp = n > 0 ? n + (int)min((long long)slab_headroom(n), share) : 0;
     dst.off[tb + c] = run; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp;
     dst.fix[tb + c] = u >= 0 ? (st.workFilter[kind][u] ? st.workFixed[kind][u] : 0) : src.fix[tb + c];
+    dst.tab[tb + c] = -1;              // every slab moves: the sorted copies (kept at the slab offsets) are void
     run += cp;
     if (u < 0 && n > 0) liveList[atomicAdd(&s_nlive, 1)] = (short)c;
   }
   __syncthreads();
-  if (threadIdx.x == 0) { st.poolEnd[kind] = S.total; st.compact[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive; }
+  if (threadIdx.x == 0) {
+    st.poolEnd[kind] = S.total; st.compact[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive;
+    int te = 0;                        // table slots start over; the rewritten cubes are re-indexed right away
+    for (int u = 0; u < wn && te < kTabSlots; ++u) if (st.workOutN[kind][u] > 0) dst.tab[tb + st.workCube[kind][u]] = te++;
+    st.tabEnd[kind] = te;
+  }
 }
-// lm_write_back: grid (kMaxWork, 2, B), block 256: filtered cube -> its slab (in the other pool when the map is re-packed).
-__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const int* __restrict__ offDst,
-                                                      const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap) {
+// lm_write_back: grid (kMaxWork, 2, B), block 256: filtered cube -> its slab (in the other pool when the map is re-packed),
+// then the cube's column index is rebuilt from the new content.
+__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const CubeTables T,
+                                                      const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap,
+                                                      int* __restrict__ tabPool, float4* __restrict__ sorted) {
+  __shared__ int s_cells[kCubeCells + 1];
+  __shared__ int s_w[8];
   const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (u >= st.workNum[kind] || st.error) return;
   const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  const int off = T.off[tb + c], slot = T.tab[tb + c];
   const float4* src = staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
-  float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + offDst[((size_t)b * 2 + kind) * kCubes + c];
+  float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
   for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+  if (slot < 0 || n == 0) return;
+  cta_build_cube_index(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
+                       tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
+                       s_cells, s_w);
 }
 // lm_compact_copy: grid (128, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
 __global__ void __launch_bounds__(256) lm_compact_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
@@ -906,6 +1062,7 @@ __global__ void lm_init_state(LMState* stAll, int B) {
   s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
   s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0;
   s.cur[0] = s.cur[1] = 0; s.compact[0] = s.compact[1] = 0; s.repacks[0] = s.repacks[1] = 0;
+  s.tabEnd[0] = s.tabEnd[1] = 0; s.buildNum[0] = s.buildNum[1] = 0;
   s.trace[0].n_records = s.trace[1].n_records = 0;
 }
 
@@ -922,6 +1079,8 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   for (int i = 0; i < 2; ++i) {
     A((void**)&lm->cubeOff[i], B * 2 * kCubes * sizeof(int)); A((void**)&lm->cubeCnt[i], B * 2 * kCubes * sizeof(int));
     A((void**)&lm->cubeCap[i], B * 2 * kCubes * sizeof(int)); A((void**)&lm->cubeFix[i], B * 2 * kCubes * sizeof(int));
+    A((void**)&lm->cubeTab[i], B * 2 * kCubes * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemsetAsync(lm->cubeTab[i], 0xff, B * 2 * kCubes * sizeof(int), st);   // -1: no index
     A((void**)&lm->mapPts[i], B * 2 * mapCap * sizeof(float4));
   }
   if (lm->p.debug_keep_submap) A((void**)&lm->snap, B * 2 * mapCap * sizeof(float4));
@@ -930,7 +1089,8 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->keyA, B * 2 * lm->workCap * 4); A((void**)&lm->valA, B * 2 * lm->workCap * 4);
   A((void**)&lm->keyB, B * 2 * lm->workCap * 4); A((void**)&lm->valB, B * 2 * lm->workCap * 4);
   A((void**)&lm->concat, B * 2 * lm->workCap * sizeof(float4)); A((void**)&lm->staged, B * 2 * lm->workCap * sizeof(float4));
-  A((void**)&lm->cellStart, B * 2 * (kMapCols + 1) * sizeof(int)); A((void**)&lm->cursor, B * 2 * (kMapCols + 1) * sizeof(int));
+  A((void**)&lm->tabPool, B * 2 * (size_t)kTabSlots * (kCubeCells + 1) * sizeof(int));
+  A((void**)&lm->entryHead, B * kCubes * sizeof(short));
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
   A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
   A((void**)&lm->pose, B * 16 * sizeof(double));
@@ -952,10 +1112,10 @@ void lm_destroy(LMDevice* lm) {
   if (!lm) return;
   if (lm->allocated) {
     cudaFree(lm->st);
-    for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->cubeCap[i]); cudaFree(lm->cubeFix[i]); cudaFree(lm->mapPts[i]); }
+    for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->cubeCap[i]); cudaFree(lm->cubeFix[i]); cudaFree(lm->cubeTab[i]); cudaFree(lm->mapPts[i]); }
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
-    cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->cellStart); cudaFree(lm->cursor); cudaFree(lm->sorted);
+    cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
     cudaFree(lm->res); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
@@ -977,27 +1137,23 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // the map = cube slabs in mapPts[LMState::cur] addressed by tables[ts].  lm_prepare writes the shifted tables to
   // tables[td]; everything up to the re-filter reads tables[td]; lm_place writes the post-insertion tables back to [ts].
   const int ts = lm->curTab, td = ts ^ 1;
-  const CubeTables T_s{lm->cubeOff[ts], lm->cubeCnt[ts], lm->cubeCap[ts], lm->cubeFix[ts]};
-  const CubeTables T_d{lm->cubeOff[td], lm->cubeCnt[td], lm->cubeCap[td], lm->cubeFix[td]};
+  const CubeTables T_s{lm->cubeOff[ts], lm->cubeCnt[ts], lm->cubeCap[ts], lm->cubeFix[ts], lm->cubeTab[ts]};
+  const CubeTables T_d{lm->cubeOff[td], lm->cubeCnt[td], lm->cubeCap[td], lm->cubeFix[td], lm->cubeTab[td]};
   const MapPools pools{{lm->mapPts[0], lm->mapPts[1]}};
   const float lineRes = (float)lm->p.mapping_line_resolution, planeRes = (float)lm->p.mapping_plane_resolution;
-  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, T_s, T_d, lm->reset_valid ? 1 : 0));
+  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, T_s, T_d, lm->entryHead, lm->reset_valid ? 1 : 0));
   lm->reset_valid = false;
   if (lm->snap)
     VB_LAUNCH(prof, K_LM_MISC, st, lm_snapshot_submap<<<dim3(256, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->snap));
   // C4: VoxelGrid of the scan features (scratch: the first `cap` entries of each key/val slab)
   VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
                                                                               lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
-  // C5: sub-map column index
-  e = cudaMemsetAsync(lm->cursor, 0, (size_t)B * 2 * (kMapCols + 1) * sizeof(int), st);
-  if (e != cudaSuccess) return e;
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_count<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->cursor));
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scan<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->cellStart, lm->cursor));
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_grid_scatter<<<dim3(1024, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->cursor, lm->sorted));
+  // C5: column index of the valid cubes that do not have one yet (new in the sub-map, seeded, or after a re-pack)
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(kMaxValid, 2, B), 256, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
-    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(64, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, lm->cellStart, lm->sorted, mapCap, lm->res));
+    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(64, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->res));
     {
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
@@ -1024,7 +1180,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[ts], pools, mapCap, lm->staged, lm->workCap));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
   lm->ran = true;
   return cudaGetLastError();
@@ -1083,16 +1239,26 @@ cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int
   LMState S;
   e = lm_fetch_state(lm, st, stream, &S);
   if (e != cudaSuccess) return e;
+  // the association looks a point up through the cube its coordinates fall in (:643-652), like every point the
+  // mapping itself inserts: refuse content that lies outside the cube
+  for (int i = 0; i < n; ++i) {
+    const double v[3] = {(double)xyzi[4 * i], (double)xyzi[4 * i + 1], (double)xyzi[4 * i + 2]};
+    const int cen[3] = {S.cenW, S.cenH, S.cenD};
+    int cc[3];
+    for (int a = 0; a < 3; ++a) { cc[a] = (int)((v[a] + 25.0) / 50.0) + cen[a]; if (v[a] + 25.0 < 0) cc[a]--; }
+    if (cc[0] + kCubeW * cc[1] + kCubeW * kCubeH * cc[2] != cube || cc[0] < 0 || cc[0] >= kCubeW || cc[1] < 0 || cc[1] >= kCubeH) return cudaErrorInvalidValue;
+  }
   // a fresh slab from the pool's bump allocator (a slab the cube may have had is reclaimed by the next re-pack); the
   // content is arbitrary, so the cube is not marked as a fixed point of its voxel filter
   if ((long long)S.poolEnd[kind] + n > lm->mapCap) return cudaErrorInvalidValue;
   const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
-  const int off = S.poolEnd[kind], zero = 0;
+  const int off = S.poolEnd[kind], zero = 0, none = -1;
   if (n) e = cudaMemcpyAsync(lm->mapPts[S.cur[kind]] + ((size_t)stream * 2 + kind) * lm->mapCap + off, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeOff[lm->curTab] + tb, &off, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeCnt[lm->curTab] + tb, &n, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeCap[lm->curTab] + tb, &n, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeFix[lm->curTab] + tb, &zero, sizeof(int), cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(lm->cubeTab[lm->curTab] + tb, &none, sizeof(int), cudaMemcpyHostToDevice, st);
   const int newEnd = off + n;
   if (e == cudaSuccess) e = cudaMemcpyAsync(&lm->st[stream].poolEnd[kind], &newEnd, sizeof(int), cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
@@ -1133,8 +1299,9 @@ cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info) {
   return cudaSuccess;
 }
 
-// stats[B][2][8] per stream and kind: points in the map, pool high-water mark, pool index, non-empty cubes, cubes in
-// fixed-point form, cubes rewritten by the last scan, re-packs so far, slab capacity in use
+// stats[B][2][10] per stream and kind: points in the map, pool high-water mark, pool index, non-empty cubes, cubes in
+// fixed-point form, cubes rewritten by the last scan, re-packs so far, slab capacity in use, points in the rewritten
+// cubes, column-table slots in use
 cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats) {
   cudaError_t e = lm_alloc(lm, st);
   if (e != cudaSuccess) return e;
@@ -1148,7 +1315,7 @@ cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats) {
   if (e != cudaSuccess) return e;
   for (int b = 0; b < lm->B; ++b)
     for (int kind = 0; kind < 2; ++kind) {
-      int* o = stats + ((size_t)b * 2 + kind) * 8;
+      int* o = stats + ((size_t)b * 2 + kind) * 10;
       long long pts = 0, caps = 0; int occ = 0, fx = 0;
       for (int c = 0; c < kCubes; ++c) {
         const size_t i = ((size_t)b * 2 + kind) * kCubes + c;
@@ -1156,6 +1323,9 @@ cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats) {
       }
       o[0] = (int)pts; o[1] = h[b].poolEnd[kind]; o[2] = h[b].cur[kind]; o[3] = occ; o[4] = fx; o[5] = h[b].workNum[kind];
       o[6] = h[b].repacks[kind]; o[7] = (int)caps;
+      long long wpts = 0;
+      for (int u = 0; u < h[b].workNum[kind] && u < kMaxWork; ++u) wpts += h[b].workOutN[kind][u];
+      o[8] = (int)wpts; o[9] = h[b].tabEnd[kind];
     }
   return cudaSuccess;
 }
