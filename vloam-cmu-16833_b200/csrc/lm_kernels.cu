@@ -94,6 +94,7 @@ struct LMDevice {
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
   float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
   LMResidual* res = nullptr;              // [B][2][cap]
+  int* nnPos = nullptr;                   // [B][2][cap][5] positions (in `sorted`) of the five nearest map points per query
   double* pose = nullptr;                 // [B][16]
   short* workOf = nullptr;                // [B][2][kCubes]
   short* liveList = nullptr;              // [B][2][kCubes] cubes a re-pack has to move
@@ -533,18 +534,18 @@ __device__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5
   for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
 }
 
-// lm_associate: grid (nblk, 2, B), block 256.  A CTA takes chunks of 256 down-sampled scan points (grid-stride):
-//   phase A  exact 5-NN, one 8-lane group per point (4 points per warp at a time): the candidates of the 3 x 3 column
-//            block are dealt to the lanes, every lane keeps its own sorted top-5, the group merges them;
-//   phase B  one THREAD per point: PCA line test (corner) or least-squares plane fit + 0.2 m check (surf) on the five
-//            neighbours, in double like the reference.  (Done by whole warps this part ran 32 times redundantly and was
-//            the bulk of the kernel.)
+// Association (:472-581) in two kernels, so that each runs at its own register budget / occupancy:
+//   lm_knn  exact 5-NN, one 8-lane group per down-sampled scan point (4 points per warp): the candidates of the 3 x 3
+//           column block (in every cube the query's 1.001 m box touches) are dealt to the lanes, every lane keeps its own
+//           sorted top-5, the group merges them; writes the five positions (or -1: fifth neighbour not within 1 m).
+//   lm_fit  one THREAD per point: PCA line test (corner) or least-squares plane fit + 0.2 m check (surf) on the five
+//           neighbours, in double like the reference.  (Done by whole warps this part ran 32 times redundantly.)
 constexpr int kLmGroup = 8;
-__global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
-                                                     const CubeTables T, const short* __restrict__ entryHeadAll,
-                                                     const int* __restrict__ tabPool, const float4* __restrict__ sorted,
-                                                     int mapCap, LMResidual* __restrict__ res) {
-  __shared__ int s_pos[256][5];      // positions (in `sorted`) of the five nearest map points, -1 = no match (:479 / :547)
+// grid (nblk, 2, B), block 256: a CTA takes chunks of 64 points (8 warps x 2 rounds x 4 groups), grid-stride
+__global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+                                                  const CubeTables T, const short* __restrict__ entryHeadAll,
+                                                  const int* __restrict__ tabPool, const float4* __restrict__ sorted,
+                                                  int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
@@ -558,135 +559,143 @@ __global__ void __launch_bounds__(256) lm_associate(const LMState* __restrict__ 
   const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
   const int cenW = st.cenW, cenH = st.cenH, cenD = st.cenD;
   const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
-  const double q0 = st.parameters[0], q1 = st.parameters[1], q2 = st.parameters[2], q3 = st.parameters[3];
+  int* outPos = nnPos + ((size_t)b * 2 + kind) * cap * 5;
+  const double qq[4] = {st.parameters[0], st.parameters[1], st.parameters[2], st.parameters[3]};
   const double t0 = st.parameters[4], t1 = st.parameters[5], t2 = st.parameters[6];
-  const double qq[4] = {q0, q1, q2, q3};
-  for (int chunk = blockIdx.x * 256; chunk < nq; chunk += gridDim.x * 256) {
-    // ---- phase A
-    for (int r = 0; r < 8; ++r) {
-      const int slot = warp * 32 + r * 4 + g;
-      const int qi = chunk + slot;
-      unsigned long long bk[5];
-      int bp[5];
+  for (int base = (blockIdx.x * 8 + warp) * 4; base < nq; base += gridDim.x * 32) {
+    const int qi = base + g;
+    unsigned long long bk[5];
+    int bp[5];
 #pragma unroll
-      for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
-      if (qi < nq) {
-        const float4 po = stk[qi];
-        // pointAssociateToMap (:146-155): double transform, rounded to float
-        double w[3];
-        quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
-        const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
-        // every cube the 1.001 m box around the query touches (one, unless the query sits at a cube border) ...
-        const int ci0 = max(cube_coord((double)sx - 1.001, cenW), 0), ci1 = min(cube_coord((double)sx + 1.001, cenW), kCubeW - 1);
-        const int cj0 = max(cube_coord((double)sy - 1.001, cenH), 0), cj1 = min(cube_coord((double)sy + 1.001, cenH), kCubeH - 1);
-        const int ck0 = max(cube_coord((double)sz - 1.001, cenD), 0), ck1 = min(cube_coord((double)sz + 1.001, cenD), kCubeD - 1);
-        for (int ck = ck0; ck <= ck1; ++ck)
-          for (int cj = cj0; cj <= cj1; ++cj)
-            for (int ci = ci0; ci <= ci1; ++ci) {
-              const int c = ci + kCubeW * cj + kCubeW * kCubeH * ck;
-              int e = entryHead[c];
-              if (e < 0) continue;                       // not part of the sub-map (:404-420)
-              const int slot = T.tab[tb + c];
-              if (slot < 0) continue;                    // empty cube
-              const int* tab = tabs + (size_t)slot * (kCubeCells + 1);
-              const int off = T.off[tb + c];
-              const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH);
-              const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
-              const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
-              if (x0 > x1) continue;
-              // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
-              // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
-              for (; e >= 0; e = st.entryNext[e]) {
-                const unsigned gBase = (unsigned)st.validPrefix[kind][e];
-                for (int row = max(qy - 1, 0); row <= min(qy + 1, kCubeCellsX - 1); ++row) {
-                  const int a = tab[row * kCubeCellsX + x0], en = tab[row * kCubeCellsX + x1 + 1];
-                  for (int t = a + gl; t < en; t += kLmGroup) {
-                    const float4 tp = S[off + t];
-                    const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-                    unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
-                    if (key < bk[4]) {
-                      int pos = off + t;
+    for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
+    if (qi < nq) {
+      const float4 po = stk[qi];
+      // pointAssociateToMap (:146-155): double transform, rounded to float
+      double w[3];
+      quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
+      const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
+      // every cube the 1.001 m box around the query touches (one, unless the query sits at a cube border) ...
+      const int ci0 = max(cube_coord((double)sx - 1.001, cenW), 0), ci1 = min(cube_coord((double)sx + 1.001, cenW), kCubeW - 1);
+      const int cj0 = max(cube_coord((double)sy - 1.001, cenH), 0), cj1 = min(cube_coord((double)sy + 1.001, cenH), kCubeH - 1);
+      const int ck0 = max(cube_coord((double)sz - 1.001, cenD), 0), ck1 = min(cube_coord((double)sz + 1.001, cenD), kCubeD - 1);
+      for (int ck = ck0; ck <= ck1; ++ck)
+        for (int cj = cj0; cj <= cj1; ++cj)
+          for (int ci = ci0; ci <= ci1; ++ci) {
+            const int c = ci + kCubeW * cj + kCubeW * kCubeH * ck;
+            int e = entryHead[c];
+            if (e < 0) continue;                       // not part of the sub-map (:404-420)
+            const int slot = T.tab[tb + c];
+            if (slot < 0) continue;                    // empty cube
+            const int* tab = tabs + (size_t)slot * (kCubeCells + 1);
+            const int off = T.off[tb + c];
+            const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH);
+            const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
+            const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
+            if (x0 > x1) continue;
+            // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
+            // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
+            for (; e >= 0; e = st.entryNext[e]) {
+              const unsigned gBase = (unsigned)st.validPrefix[kind][e];
+              for (int row = max(qy - 1, 0); row <= min(qy + 1, kCubeCellsX - 1); ++row) {
+                const int a = tab[row * kCubeCellsX + x0], en = tab[row * kCubeCellsX + x1 + 1];
+                for (int t = a + gl; t < en; t += kLmGroup) {
+                  const float4 tp = S[off + t];
+                  const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+                  unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
+                  if (key < bk[4]) {
+                    int pos = off + t;
 #pragma unroll
-                      for (int i = 0; i < 5; ++i)
-                        if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
-                    }
+                    for (int i = 0; i < 5; ++i)
+                      if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
                   }
                 }
               }
             }
-      }
-      // group merge: five rounds of "smallest head wins" (keys are unique: the low word is the sub-map index)
-      int head = 0, myPos[5];
-      unsigned long long fifth = 0xffffffffffffffffull;
-#pragma unroll
-      for (int rr = 0; rr < 5; ++rr) {
-        unsigned long long mine = 0xffffffffffffffffull;
-        int minePos = -1;
-#pragma unroll
-        for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
-        unsigned long long m = mine;
-#pragma unroll
-        for (int o = kLmGroup / 2; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(gmask, m, o); m = t < m ? t : m; }
-        const bool won = mine == m && m != 0xffffffffffffffffull;
-        const unsigned win = __ballot_sync(gmask, won) & gmask;
-        int wp = -1;
-        if (win) { wp = __shfl_sync(gmask, minePos, __ffs(win) - 1); if (won) head++; }
-        myPos[rr] = wp;
-        if (rr == 4) fifth = m;
-      }
-      if (gl == 0) {
-        const bool ok = fifth != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(fifth >> 32)) < 1.0;  // :479 / :547
-#pragma unroll
-        for (int i = 0; i < 5; ++i) s_pos[slot][i] = ok ? myPos[i] : -1;
-      }
-    }
-    __syncthreads();
-    // ---- phase B
-    const int qi = chunk + threadIdx.x;
-    if (qi < nq) {
-      const float4 po = stk[qi];
-      LMResidual R;
-      R.type = 0; R.px = po.x; R.py = po.y; R.pz = po.z;
-#pragma unroll
-      for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
-      if (s_pos[threadIdx.x][4] >= 0) {
-        double P[5][3];
-#pragma unroll
-        for (int j = 0; j < 5; ++j) { const float4 tp = S[s_pos[threadIdx.x][j]]; P[j][0] = tp.x; P[j][1] = tp.y; P[j][2] = tp.z; }
-        if (kind == 0) {  // :481-516
-          double c[3] = {0, 0, 0};
-          for (int j = 0; j < 5; ++j) { c[0] = c[0] + P[j][0]; c[1] = c[1] + P[j][1]; c[2] = c[2] + P[j][2]; }
-          c[0] = c[0] / 5.0; c[1] = c[1] / 5.0; c[2] = c[2] / 5.0;
-          double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
-          for (int j = 0; j < 5; ++j) {
-            const double d[3] = {P[j][0] - c[0], P[j][1] - c[1], P[j][2] - c[2]};
-            for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) cov[r * 3 + q] += d[r] * d[q];
           }
-          double ev[3], evec[3][3];
-          sym_eig3_dev(cov, ev, evec);
-          if (ev[2] > 3 * ev[1]) {
-            R.type = 1;
-            for (int i = 0; i < 3; ++i) { R.v[i] = 0.1 * evec[2][i] + c[i]; R.v[3 + i] = -0.1 * evec[2][i] + c[i]; }
-          }
-        } else {  // :545-580
-          double A[15], bb[5] = {-1, -1, -1, -1, -1}, n[3];
-          for (int j = 0; j < 5; ++j) { A[j * 3] = P[j][0]; A[j * 3 + 1] = P[j][1]; A[j * 3 + 2] = P[j][2]; }
-          colpiv_qr_solve_5x3_dev(A, bb, n);
-          const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
-          const double d = 1 / nn;
-          n[0] /= nn; n[1] /= nn; n[2] /= nn;
-          bool ok = true;
-          for (int j = 0; j < 5; ++j)
-            if (fabs(n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + d) > 0.2) { ok = false; break; }
-          if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
-        }
-      }
-      res[((size_t)b * 2 + kind) * cap + qi] = R;
     }
-    __syncthreads();
+    // group merge: five rounds of "smallest head wins" (keys are unique: the low word is the sub-map index)
+    int head = 0, myPos[5];
+    unsigned long long fifth = 0xffffffffffffffffull;
+#pragma unroll
+    for (int rr = 0; rr < 5; ++rr) {
+      unsigned long long mine = 0xffffffffffffffffull;
+      int minePos = -1;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
+      unsigned long long m = mine;
+#pragma unroll
+      for (int o = kLmGroup / 2; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(gmask, m, o); m = t < m ? t : m; }
+      const bool won = mine == m && m != 0xffffffffffffffffull;
+      const unsigned win = __ballot_sync(gmask, won) & gmask;
+      int wp = -1;
+      if (win) { wp = __shfl_sync(gmask, minePos, __ffs(win) - 1); if (won) head++; }
+      myPos[rr] = wp;
+      if (rr == 4) fifth = m;
+    }
+    if (qi < nq && gl < 5) {
+      const bool ok = fifth != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(fifth >> 32)) < 1.0;  // :479 / :547
+      int v = -1;
+#pragma unroll
+      for (int i = 0; i < 5; ++i) if (i == gl) v = myPos[i];
+      outPos[(size_t)qi * 5 + gl] = ok ? v : -1;
+    }
   }
 }
-
+// grid (nblk, 2, B), block 128: one thread per point
+__global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+                                               const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
+                                               LMResidual* __restrict__ res) {
+  const int kind = blockIdx.y, b = blockIdx.z;
+  const LMState& st = stAll[b];
+  if (!st.solved) return;
+  const int nq = st.stackNum[kind];
+  const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
+  const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
+  const int* inPos = nnPos + ((size_t)b * 2 + kind) * cap * 5;
+  for (int qi = blockIdx.x * 128 + threadIdx.x; qi < nq; qi += gridDim.x * 128) {
+    const float4 po = stk[qi];
+    LMResidual R;
+    R.type = 0; R.px = po.x; R.py = po.y; R.pz = po.z;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
+    int pos[5];
+#pragma unroll
+    for (int j = 0; j < 5; ++j) pos[j] = inPos[(size_t)qi * 5 + j];
+    if (pos[4] >= 0) {
+      double P[5][3];
+#pragma unroll
+      for (int j = 0; j < 5; ++j) { const float4 tp = S[pos[j]]; P[j][0] = tp.x; P[j][1] = tp.y; P[j][2] = tp.z; }
+      if (kind == 0) {  // :481-516
+        double c[3] = {0, 0, 0};
+        for (int j = 0; j < 5; ++j) { c[0] = c[0] + P[j][0]; c[1] = c[1] + P[j][1]; c[2] = c[2] + P[j][2]; }
+        c[0] = c[0] / 5.0; c[1] = c[1] / 5.0; c[2] = c[2] / 5.0;
+        double cov[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+        for (int j = 0; j < 5; ++j) {
+          const double d[3] = {P[j][0] - c[0], P[j][1] - c[1], P[j][2] - c[2]};
+          for (int r = 0; r < 3; ++r) for (int q = 0; q < 3; ++q) cov[r * 3 + q] += d[r] * d[q];
+        }
+        double ev[3], evec[3][3];
+        sym_eig3_dev(cov, ev, evec);
+        if (ev[2] > 3 * ev[1]) {
+          R.type = 1;
+          for (int i = 0; i < 3; ++i) { R.v[i] = 0.1 * evec[2][i] + c[i]; R.v[3 + i] = -0.1 * evec[2][i] + c[i]; }
+        }
+      } else {  // :545-580
+        double A[15], bb[5] = {-1, -1, -1, -1, -1}, n[3];
+        for (int j = 0; j < 5; ++j) { A[j * 3] = P[j][0]; A[j * 3 + 1] = P[j][1]; A[j * 3 + 2] = P[j][2]; }
+        colpiv_qr_solve_5x3_dev(A, bb, n);
+        const double nn = sqrt(n[0] * n[0] + n[1] * n[1] + n[2] * n[2]);
+        const double d = 1 / nn;
+        n[0] /= nn; n[1] /= nn; n[2] /= nn;
+        bool ok = true;
+        for (int j = 0; j < 5; ++j)
+          if (fabs(n[0] * P[j][0] + n[1] * P[j][1] + n[2] * P[j][2] + d) > 0.2) { ok = false; break; }
+        if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
+      }
+    }
+    res[((size_t)b * 2 + kind) * cap + qi] = R;
+  }
+}
 
 // lm_solve: one outer pass of :458-626 (the association was just done by lm_associate).  grid (kLmCluster, B), block 256,
 // one thread-block CLUSTER per stream: ~13 k residual blocks of double-precision Jacobians are too much for one SM per
@@ -1093,6 +1102,7 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->entryHead, B * kCubes * sizeof(short));
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
   A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
+  A((void**)&lm->nnPos, B * 2 * cap * 5 * sizeof(int));
   A((void**)&lm->pose, B * 16 * sizeof(double));
   A((void**)&lm->workOf, B * 2 * kCubes * sizeof(short));
   if (e != cudaSuccess) return e;
@@ -1116,7 +1126,7 @@ void lm_destroy(LMDevice* lm) {
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
-    cudaFree(lm->res); cudaFree(lm->pose); cudaFree(lm->workOf);
+    cudaFree(lm->res); cudaFree(lm->nnPos); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
 }
@@ -1153,7 +1163,8 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
-    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_associate<<<dim3(64, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->res));
+    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
+    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res));
     {
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
