@@ -58,6 +58,7 @@ struct LMState {
   int workCube[2][kMaxWork], workFilter[2][kMaxWork], workNew0[2][kMaxWork], workNewN[2][kMaxWork];
   int workIn0[2][kMaxWork + 1];         // offsets of each work cube's (old ++ new) input inside the concat buffer
   int workOutN[2][kMaxWork], workFixed[2][kMaxWork];
+  int workDirect[2][kMaxWork];          // the cube's new content already sits in its slab (patched in place by lm_refilter)
   int error;
   SolveTrace trace[2];
 };
@@ -94,6 +95,7 @@ struct LMDevice {
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
   float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
   LMResidual* res = nullptr;              // [B][2][cap]
+  int* cubeOf = nullptr;                  // [B][2][cap] cube id of every down-sampled scan point (map frame)
   int* nnPos = nullptr;                   // [B][2][cap][5] positions (in `sorted`) of the five nearest map points per query
   double* pose = nullptr;                 // [B][16]
   short* workOf = nullptr;                // [B][2][kCubes]
@@ -769,6 +771,36 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// Position of a point on the voxel lattice of its cube's filter (pcl::VoxelGrid: voxel = floor(p / leaf) per axis), relative
+// to the cube's min corner, packed z | y | x with `s` bits per axis.  pcl::VoxelGrid emits voxels in ascending
+// i + j * dx + k * dx * dy of bounding-box-relative coordinates, i.e. in lexicographic (z, y, x) lattice order whatever the
+// box: ascending order of this key.  Valid for points inside the cube (all points of a cube are) and 3 s <= 30 bits.
+struct VoxLattice { float inv; int bx, by, bz, s; };
+__device__ __forceinline__ VoxLattice vox_lattice(int cube, int cenW, int cenH, int cenD, float leaf, int s) {
+  VoxLattice L;
+  L.inv = __fdiv_rn(1.0f, leaf);
+  L.bx = (int)floorf(__fmul_rn(cube_min_coord(cube % kCubeW, cenW), L.inv)) - 1;
+  L.by = (int)floorf(__fmul_rn(cube_min_coord((cube / kCubeW) % kCubeH, cenH), L.inv)) - 1;
+  L.bz = (int)floorf(__fmul_rn(cube_min_coord(cube / (kCubeW * kCubeH), cenD), L.inv)) - 1;
+  L.s = s;
+  return L;
+}
+__device__ __forceinline__ unsigned vox_key(const VoxLattice& L, float x, float y, float z) {
+  const unsigned mask = (1u << L.s) - 1u;
+  const unsigned rx = (unsigned)((int)floorf(__fmul_rn(x, L.inv)) - L.bx) & mask;
+  const unsigned ry = (unsigned)((int)floorf(__fmul_rn(y, L.inv)) - L.by) & mask;
+  const unsigned rz = (unsigned)((int)floorf(__fmul_rn(z, L.inv)) - L.bz) & mask;
+  return (rz << (2 * L.s)) | (ry << L.s) | rx;
+}
+// bits per axis for a leaf size (host): the lattice spans 50 / leaf + 3 voxels of a 50 m cube; 0 = too fine for a 30-bit key
+static int vox_axis_bits(double leaf) {
+  if (!(leaf > 0.0)) return 0;
+  const double span = 50.0 / leaf + 4.0;
+  int s = 1;
+  while ((double)(1 << s) < span && s < 31) ++s;
+  return 3 * s <= 30 ? s : 0;
+}
+
 // lm_insert_keys: grid (2, B), block 1024.  transformUpdate (:636, :140-144), map-frame coordinates of the stack
 // points and their cube ids, stable sort by cube id (:639-683 push the points in stack order), work list.
 //
@@ -778,8 +810,9 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
 // (cta_voxel_filter), so it is not touched at all.
 __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                         float4* __restrict__ stackW, const int* __restrict__ cubeCnt,
-                                                        const int* __restrict__ cubeFix,
-                                                        unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB, size_t workCap) {
+                                                        const int* __restrict__ cubeFix, int* __restrict__ cubeOfAll, float lineRes,
+                                                        float planeRes, int bitsLine, int bitsPlane, unsigned* kA, unsigned* vA,
+                                                        unsigned* kB, unsigned* vB, size_t workCap) {
   __shared__ SortSmem S;
   __shared__ int s_res;
   const int kind = blockIdx.x, b = blockIdx.y;
@@ -789,6 +822,9 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
   float4* outW = stackW + ((size_t)b * 2 + kind) * cap;
   const size_t so = ((size_t)b * 2 + kind) * workCap;
   unsigned* ka = kA + so; unsigned* va = vA + so; unsigned* kb = kB + so; unsigned* vb = vB + so;
+  int* cubeOf = cubeOfAll + ((size_t)b * 2 + kind) * cap;
+  const float leaf = kind == 0 ? lineRes : planeRes;
+  const int axisBits = kind == 0 ? bitsLine : bitsPlane;
   for (int i = threadIdx.x; i < n; i += 1024) {
     const float4 p = in[i];
     double w[3];
@@ -799,12 +835,28 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
     if ((double)x + 25.0 < 0) cI--;
     if ((double)y + 25.0 < 0) cJ--;
     if ((double)z + 25.0 < 0) cK--;
-    unsigned key = 0xffffu;
-    if (cI >= 0 && cI < kCubeW && cJ >= 0 && cJ < kCubeH && cK >= 0 && cK < kCubeD) key = (unsigned)(cI + kCubeW * cJ + kCubeW * kCubeH * cK);
-    ka[i] = key; va[i] = (unsigned)i;
+    unsigned key = 0xffffu, vkey = 0u;
+    if (cI >= 0 && cI < kCubeW && cJ >= 0 && cJ < kCubeH && cK >= 0 && cK < kCubeD) {
+      key = (unsigned)(cI + kCubeW * cJ + kCubeW * kCubeH * cK);
+      if (axisBits) vkey = vox_key(vox_lattice((int)key, st.cenW, st.cenH, st.cenD, leaf, axisBits), x, y, z);
+    }
+    cubeOf[i] = (int)key; ka[i] = vkey; va[i] = (unsigned)i;
   }
   __syncthreads();
-  const int cur = cta_radix_sort(ka, va, kb, vb, n, 16, S);
+  // Order: by cube, inside a cube by voxel of the cube's filter lattice, inside a voxel by stack index (the reference
+  // pushes the points in stack order, :639-683; only the order inside a voxel matters to the filter's sums).  Two stable
+  // sorts: voxel key first, cube id second.
+  int cur = 0;
+  if (axisBits) {
+    cur = cta_radix_sort(ka, va, kb, vb, n, 3 * axisBits, S);
+    unsigned* kr = cur ? kb : ka;
+    const unsigned* vr = cur ? vb : va;
+    for (int i = threadIdx.x; i < n; i += 1024) kr[i] = (unsigned)cubeOf[vr[i]];
+  } else {
+    for (int i = threadIdx.x; i < n; i += 1024) ka[i] = (unsigned)cubeOf[i];
+  }
+  __syncthreads();
+  cur ^= cur ? cta_radix_sort(kb, vb, ka, va, n, 16, S) : cta_radix_sort(ka, va, kb, vb, n, 16, S);
   if (threadIdx.x == 0) s_res = cur;
   __syncthreads();
   const unsigned* keys = s_res ? kb : ka;
@@ -876,10 +928,21 @@ __global__ void lm_transform_update(LMState* __restrict__ stAll, int B) {  // :1
   for (int i = 0; i < 3; ++i) st.t_wmap_wodom[i] = st.parameters[4 + i] - r[i];
 }
 
-// lm_refilter: grid (kMaxWork, 2, B), block 1024.  One work cube per CTA: input = old cube ++ new points (stack order).
+// lm_refilter: grid (kMaxWork, 2, B), block 1024.  One work cube per CTA; input = old cube ++ new points.
+//
+// Three paths (uniform per CTA):
+//   merge   the cube is a fixed point of its filter (one point per voxel, in lattice order) and its new points arrive
+//           sorted by voxel (lm_insert_keys): nothing is sorted.  The new points' voxel runs are located in the old cube
+//           by binary search; a run that hits an occupied voxel replaces that point by the voxel's new centroid
+//           ((0 + old) + new_1 + ... in stack order, exactly the sum pcl::VoxelGrid forms over old ++ new), a run in an
+//           empty voxel is inserted.  No insertion -> the few changed points are patched in the slab itself (workDirect),
+//           else the merged cube is written to `staged`.
+//   filter  any other valid cube: the full voxel filter (sort) over old ++ new.
+//   append  a cube outside the valid list only grows (:639-683), in stack order.
 __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll, const int* __restrict__ cubeOff, const int* __restrict__ cubeCnt,
-                                                     const MapPools pools, int mapCap, const float4* __restrict__ stackW,
-                                                     int cap, const unsigned* __restrict__ vAins, float lineRes, float planeRes,
+                                                     const int* __restrict__ cubeFix, const MapPools pools, int mapCap,
+                                                     const float4* __restrict__ stackW,
+                                                     int cap, const unsigned* __restrict__ vAins, float lineRes, float planeRes, int bitsLine, int bitsPlane,
                                                      float4* __restrict__ concat, float4* __restrict__ staged, unsigned* kA, unsigned* vA,
                                                      unsigned* kB, unsigned* vB, size_t workCap) {
   __shared__ SortSmem S;
@@ -889,24 +952,111 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
   if (u >= st.workNum[kind] || st.error) return;
   const int c = st.workCube[kind][u];
   const size_t so = ((size_t)b * 2 + kind) * workCap;
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int in0 = st.workIn0[kind][u];
-  const int nOld = cubeCnt[((size_t)b * 2 + kind) * kCubes + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
-  const float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[((size_t)b * 2 + kind) * kCubes + c];
+  const int nOld = cubeCnt[tb + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
+  float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
   const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
-  const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points, in stack order
+  const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points: by voxel, then stack order
   float4* in = concat + so + in0;
   float4* out = staged + so + in0;
-  for (int i = threadIdx.x; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
-  __syncthreads();
-  int m, fixed = 0;
-  if (st.workFilter[kind][u]) {
-    // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
-    m = cta_voxel_filter(in, n, kind == 0 ? lineRes : planeRes, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red, &fixed);
+  const float leaf = kind == 0 ? lineRes : planeRes;
+  const int axisBits = kind == 0 ? bitsLine : bitsPlane;
+  const int tid = threadIdx.x;
+  int m, fixed = 0, direct = 0;
+  if (st.workFilter[kind][u] && cubeFix[tb + c] && nOld > 0 && nNew > 0 && axisBits > 0) {
+    // ---------------- merge
+    const VoxLattice L = vox_lattice(c, st.cenW, st.cenH, st.cenD, leaf, axisBits);
+    unsigned* keyNew = kA + so + in0;                       // [nNew] voxel key of every new point
+    int* runStart = reinterpret_cast<int*>(vA + so + in0);  // [runs + 1] first new point of every voxel run
+    int* runPos = reinterpret_cast<int*>(kB + so + in0);    // [runs] position in the old cube (bit 31: that voxel is occupied)
+    int* insBefore = reinterpret_cast<int*>(vB + so + in0); // [runs] inserted runs before this one
+    int* insPos = reinterpret_cast<int*>(in);               // [inserted] old-cube position of every inserted run (concat is free here)
+    for (int t = tid; t < nNew; t += 1024) { const float4 p = sw[ord[t]]; keyNew[t] = vox_key(L, p.x, p.y, p.z); }
+    __syncthreads();
+    const int per = (nNew + 1023) / 1024;
+    const int t0 = min(tid * per, nNew), t1 = min(t0 + per, nNew);
+    int nh = 0;
+    for (int t = t0; t < t1; ++t) nh += (t == 0 || keyNew[t] != keyNew[t - 1]) ? 1 : 0;
+    int r0 = block_exclusive_scan1024(nh, S);
+    const int runs = S.total;
+    for (int t = t0; t < t1; ++t) if (t == 0 || keyNew[t] != keyNew[t - 1]) runStart[r0++] = t;
+    if (tid == 0) runStart[runs] = nNew;
+    __syncthreads();
+    for (int r = tid; r < runs; r += 1024) {
+      const unsigned vk = keyNew[runStart[r]];
+      int lo = 0, hi = nOld;
+      while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        const float4 q = old[mid];
+        if (vox_key(L, q.x, q.y, q.z) < vk) lo = mid + 1; else hi = mid;
+      }
+      int hit = 0;
+      if (lo < nOld) { const float4 q = old[lo]; hit = vox_key(L, q.x, q.y, q.z) == vk; }
+      runPos[r] = lo | (hit ? (int)0x80000000 : 0);
+    }
+    __syncthreads();
+    const int perR = (runs + 1023) / 1024;
+    const int q0 = min(tid * perR, runs), q1 = min(q0 + perR, runs);
+    int ni = 0;
+    for (int r = q0; r < q1; ++r) ni += runPos[r] < 0 ? 0 : 1;
+    int i0 = block_exclusive_scan1024(ni, S);
+    const int inserted = S.total;
+    for (int r = q0; r < q1; ++r) {
+      insBefore[r] = i0;
+      if (runPos[r] >= 0) insPos[i0++] = runPos[r];
+    }
+    __syncthreads();
+    m = nOld + inserted;
+    direct = inserted == 0 ? 1 : 0;
+    float4* dst = direct ? old : out;
+    if (!direct) {
+      // old point i moves up by the number of inserted runs placed at or before it (insPos is ascending)
+      for (int i = tid; i < nOld; i += 1024) {
+        int lo = 0, hi = inserted;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (insPos[mid] <= i) lo = mid + 1; else hi = mid; }
+        dst[i + lo] = old[i];
+      }
+      __syncthreads();
+    }
+    int inside = 1;
+    for (int r = tid; r < runs; r += 1024) {
+      const int pos = runPos[r] & 0x7fffffff;
+      const bool hit = runPos[r] < 0;
+      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+      int cnt = 0;
+      if (hit) { const float4 o = old[pos]; sx = __fadd_rn(sx, o.x); sy = __fadd_rn(sy, o.y); sz = __fadd_rn(sz, o.z); si = __fadd_rn(si, o.w); cnt = 1; }
+      for (int t = runStart[r]; t < runStart[r + 1]; ++t) {
+        const float4 p = sw[ord[t]];
+        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+        ++cnt;
+      }
+      const float nf = (float)cnt;
+      const float4 cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+      if (vox_key(L, cen.x, cen.y, cen.z) != keyNew[runStart[r]]) inside = 0;
+      dst[pos + insBefore[r]] = cen;
+    }
+    fixed = __syncthreads_and(inside);
   } else {
-    for (int i = threadIdx.x; i < n; i += 1024) out[i] = in[i];
-    m = n;
+    if (st.workFilter[kind][u]) {
+      // ---------------- filter
+      for (int i = tid; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
+      __syncthreads();
+      // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
+      m = cta_voxel_filter(in, n, leaf, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red, &fixed);
+    } else {
+      // ---------------- append: back to stack order (a 16-bit key covers every stack index of a scan up to 65 536 points;
+      // larger scans sort on all 32 bits)
+      unsigned* ka = kA + so + in0; unsigned* va = vA + so + in0; unsigned* kb = kB + so + in0; unsigned* vb = vB + so + in0;
+      for (int t = tid; t < nNew; t += 1024) { ka[t] = ord[t]; va[t] = ord[t]; }
+      __syncthreads();
+      const int cur = cta_radix_sort(ka, va, kb, vb, nNew, cap <= 65536 ? 16 : 32, S);
+      const unsigned* vs = cur ? vb : va;
+      for (int i = tid; i < n; i += 1024) out[i] = i < nOld ? old[i] : sw[vs[i - nOld]];
+      m = n;
+    }
   }
-  if (threadIdx.x == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; }
+  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct; }
 }
 
 // lm_place: grid (2, B), block 1024.  New cube tables `dst` from the post-shift tables `src`: a rewritten cube keeps its
@@ -1006,9 +1156,9 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
     st.tabEnd[kind] = te;
   }
 }
-// lm_write_back: grid (kMaxWork, 2, B), block 256: filtered cube -> its slab (in the other pool when the map is re-packed),
-// then the cube's column index is rebuilt from the new content.
-__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const CubeTables T,
+// lm_write_back: grid (kMaxWork, 2, B), block 256: rewritten cube -> its slab (in the other pool when the map is re-packed;
+// nothing to move when lm_refilter patched the slab in place), then the cube's column index is rebuilt from the new content.
+__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const CubeTables Tsrc, const CubeTables T,
                                                       const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap,
                                                       int* __restrict__ tabPool, float4* __restrict__ sorted) {
   __shared__ int s_cells[kCubeCells + 1];
@@ -1019,9 +1169,11 @@ __global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__
   const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int off = T.off[tb + c], slot = T.tab[tb + c];
-  const float4* src = staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
+  const bool direct = st.workDirect[kind][u] != 0;
+  const float4* src = direct ? stream_map(pools, st, b, kind, mapCap) + Tsrc.off[tb + c]
+                             : staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
   float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
-  for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+  if (src != dst) for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
   if (slot < 0 || n == 0) return;
   cta_build_cube_index(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
@@ -1103,6 +1255,7 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
   A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
   A((void**)&lm->nnPos, B * 2 * cap * 5 * sizeof(int));
+  A((void**)&lm->cubeOf, B * 2 * cap * sizeof(int));
   A((void**)&lm->pose, B * 16 * sizeof(double));
   A((void**)&lm->workOf, B * 2 * kCubes * sizeof(short));
   if (e != cudaSuccess) return e;
@@ -1126,7 +1279,7 @@ void lm_destroy(LMDevice* lm) {
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
-    cudaFree(lm->res); cudaFree(lm->nnPos); cudaFree(lm->pose); cudaFree(lm->workOf);
+    cudaFree(lm->res); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
 }
@@ -1151,6 +1304,8 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   const CubeTables T_d{lm->cubeOff[td], lm->cubeCnt[td], lm->cubeCap[td], lm->cubeFix[td], lm->cubeTab[td]};
   const MapPools pools{{lm->mapPts[0], lm->mapPts[1]}};
   const float lineRes = (float)lm->p.mapping_line_resolution, planeRes = (float)lm->p.mapping_plane_resolution;
+  static const bool noMerge = [] { const char* e = getenv("VLOAM_LM_NO_MERGE"); return e && e[0] == '1'; }();   // validation: always re-sort
+  const int bitsLine = noMerge ? 0 : vox_axis_bits(lineRes), bitsPlane = noMerge ? 0 : vox_axis_bits(planeRes);
   VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, T_s, T_d, lm->entryHead, lm->reset_valid ? 1 : 0));
   lm->reset_valid = false;
   if (lm->snap)
@@ -1183,15 +1338,15 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back
   VB_LAUNCH(prof, K_LM_MISC, st, lm_transform_update<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B));
   VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->cubeFix[td],
-                                                                               lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
+                                                                               lm->cubeOf, lineRes, planeRes, bitsLine, bitsPlane, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // the cube-sorted stack indices stay in valA[0 .. n); the per-cube filters use the key/val slabs from offset `cap` on
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], pools, mapCap,
-                                                                                         lm->stackW, cap, lm->valA, lineRes, planeRes, lm->concat, lm->staged,
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
+                                                                                         lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
   lm->ran = true;
   return cudaGetLastError();
