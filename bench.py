@@ -1,10 +1,12 @@
 #!/usr/bin/env python
 """bench.py — scans/sec of the VLOAM per-scan LiDAR hot path on B200 (BASELINE.json metric).
 
-Workload at N = 1 (BASELINE.json configs[1]): scanRegistration + laserOdometry over a synthetic HDL-64
-64 x 2048 range-image stream, `--batch` independent streams driven in lock-step by one handle
-(`--workload sr_lo_lm` adds laserMapping = configs[2]).  One *step* = one scan of every stream through the
-whole path.  Three measurements of the same work:
+Workload at N = 1: BASELINE.json's metric is "scans/sec ... laserOdometry+Mapping", i.e. configs[2]: scan registration,
+laserOdometry and laserMapping (scan-to-submap on a pre-built 1 M-point voxel map, 2 passes x 5 LM iterations = "10 GN
+iters") over a synthetic HDL-64 64 x 2048 range-image stream, `--batch` independent streams driven in lock-step
+(`--workload sr_lo` = configs[1], scanRegistration + laserOdometry only; `--workload vloam` = configs[3], with visual
+odometry feeding the LiDAR prior).  One *step* = one scan of every stream through the whole path.  Three measurements of
+the same work:
 
   value  inputs already resident in HBM (a pool of scans larger than L2), timed with CUDA events on the
          launching stream, barrier + synchronize on both sides, max over ranks;
@@ -142,7 +144,7 @@ class CpuChain:
     """One stream through the oracle in the order of vloam_main_node.cpp:125-180 (CPU arm / cpu_baseline).
     workload: sr_lo | sr_lo_lm | vloam (adds VisualOdometry and feeds its result to laserOdometry as the prior)."""
 
-    def __init__(self, O, workload, map_cubes):
+    def __init__(self, O, workload, map_cubes, lm_iterations=4):
         self.O, self.workload = O, workload
         self.t = {"sr_ms": 0.0, "lo_ms": 0.0, "lm_ms": 0.0, "vo_ms": 0.0, "scans": 0}
         if workload == "vloam":
@@ -156,6 +158,7 @@ class CpuChain:
         else:
             self.pipe = O.Pipeline()
             self.lm = self.pipe.lm
+        self.lm.set_iterations(2, lm_iterations)
         for (kind, cube), pts in map_cubes.items():
             self.lm.set_cube(kind, cube, pts)
 
@@ -201,7 +204,8 @@ def cpu_matches(scan_stream, i):
 
 WORKLOAD_NAME = {
     "sr_lo": ("scanRegistration+laserOdometry", "configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"),
-    "sr_lo_lm": ("scanRegistration+laserOdometry+laserMapping", "configs[2]: laserOdometry + laserMapping scan-to-submap"),
+    "sr_lo_lm": ("scanRegistration+laserOdometry+laserMapping",
+                 "configs[2]: laserOdometry + laserMapping scan-to-submap (1M-pt voxel map, 10 GN iters) on 1xB200, fed by scanRegistration"),
     "vloam": ("visualOdometry(depth+solve)+scanRegistration+laserOdometry(VO prior)+laserMapping",
               "configs[3]: full VLOAM, visual odometry depth association + solve feeding LiDAR odometry and mapping"),
 }
@@ -220,7 +224,7 @@ def run_reference(args, rank):
     do_map = args.workload in ("sr_lo_lm", "vloam")
     seqs, scan_streams = make_base_scans(0, with_streams=True)
     cubes = synth_map_cubes(args.map_points, BENCH_SEED) if do_map else {}
-    pipes = [CpuChain(O, args.workload, cubes) for _ in range(T)]
+    pipes = [CpuChain(O, args.workload, cubes, args.lm_iterations) for _ in range(T)]
     n_steps = args.warmup + args.steps
     mt = {(t % N_BASE, i): cpu_matches(scan_streams[t % N_BASE], i) for t in range(min(T, N_BASE)) for i in range(n_steps)} \
         if args.workload == "vloam" else {}
@@ -242,7 +246,9 @@ def run_reference(args, rank):
         "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME[args.workload][1], "streams": T, "points_per_scan": N_RINGS * N_COLS},
+        "config": {"workload": WORKLOAD_NAME[args.workload][1], "streams": T, "points_per_scan": N_RINGS * N_COLS,
+                   "lo_passes": 2, "lo_iterations_per_pass": 4, "lm_passes": 2, "lm_iterations_per_pass": args.lm_iterations,
+                   "map_points": args.map_points if do_map else 0},
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
                          "sample": f"{T} threads x {args.steps} scans, one stream per thread; per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
                                    f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"},
@@ -305,7 +311,8 @@ def algorithmic_bytes(kernel, c):
         "lm_prepare": 0, "lm_misc": 0,
         "lm_voxel": (c["nLS"] + c["nLF"]) * (16 + 16),
         "lm_index": 0,                                      # only cubes without a column index are (re)indexed: none in steady state
-        "lm_associate": c.get("S", 0) * 96 + c.get("S", 0) * 9 * 8 * 16,
+        "lm_associate": c.get("S", 0) * (16 + 20) + c.get("S", 0) * 9 * 8 * 16,   # query + 5 positions; 3 x 3 columns of ~8 points
+        "lm_fit": c.get("S", 0) * (16 + 20 + 5 * 16 + 72),
         "lm_solve": c.get("S", 0) * 80,
         "lm_insert": c.get("S", 0) * 48,
         "lm_refilter": c.get("Mw", 0) * (16 * 3 + 8 * 4),   # rewritten cubes: slab read, concat written + read, keys/values, staged written
@@ -387,7 +394,7 @@ def run_ours(args, rank, world, local_rank):
         def __init__(self, ctx_, b0, b1):
             self.ctx, self.b0, self.b1, self.nb = ctx_, b0, b1, b1 - b0
             self.lom = V.LidarOdometryMapping(ctx_, batch=self.nb, max_points=cap, map_capacity_points=map_cap,
-                                              detach_VO_LO=0 if do_vo else 1)
+                                              detach_VO_LO=0 if do_vo else 1, lm_max_iterations=args.lm_iterations)
             for (kind, cube), pts in map_cubes.items():      # the same pre-built map under every stream
                 for b in range(self.nb):
                     self.lom.map_set_cube(kind, cube, pts, stream=b)
@@ -574,7 +581,9 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- leg 3: single-stream latency (batch = 1), context only
     lat_ms = None
     if rank == 0:
-        lom1 = V.LidarOdometryMapping(ctx, batch=1, max_points=cap)
+        lom1 = V.LidarOdometryMapping(ctx, batch=1, max_points=cap, map_capacity_points=map_cap, lm_max_iterations=args.lm_iterations)
+        for (kind, cube), pts in map_cubes.items():
+            lom1.map_set_cube(kind, cube, pts)
         one_dev = [dev_pool[k][0:1].contiguous() for k in range(POOL_SCANS)]
         n1 = n_dev[0:1].contiguous()
         with torch.cuda.stream(stream):
@@ -582,6 +591,8 @@ def run_ours(args, rank, world, local_rank):
                 lom1.reset()
                 lom1.scanRegistrationDevice(one_dev[pingpong(i, POOL_SCANS)], n1, 3, cap)
                 lom1.laserOdometryIO(fetch=False)
+                if do_map:
+                    lom1.laserMappingIO(fetch=False)
             for i in range(5):
                 step1(i)
             torch.cuda.synchronize()
@@ -635,7 +646,7 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- CPU baseline: oracle, 1 thread, bounded sample
     from oracle import pyoracle as O
     O.build()
-    pipe = CpuChain(O, args.workload, map_cubes)
+    pipe = CpuChain(O, args.workload, map_cubes, args.lm_iterations)
     n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 20)
     cpu_m = [cpu_matches(scan_streams[0], i) for i in range(n_cpu)] if do_vo else [None] * n_cpu
     t0 = time.perf_counter()
@@ -651,7 +662,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if point else "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
         "config": {"workload": WORKLOAD_NAME[args.workload][1],
-                   "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lm_iterations_per_pass": 4,
+                   "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lo_iterations_per_pass": 4,
+                   "lm_passes": 2, "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0,
                    "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
                    "parallelism": (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
                                    f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}") if point
@@ -687,7 +699,12 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch", type=int, default=0, help="independent streams per GPU (default: 256 for sr_lo, 128 for the mapping workloads)")
-    ap.add_argument("--workload", default="sr_lo", choices=["sr_lo", "sr_lo_lm", "vloam"])
+    ap.add_argument("--workload", default="sr_lo_lm", choices=["sr_lo", "sr_lo_lm", "vloam"],
+                    help="sr_lo_lm (default) = BASELINE.json's metric, laserOdometry+Mapping on a 1 M-point map (configs[2], with the scan "
+                         "registration that feeds it); sr_lo = configs[1]; vloam = configs[3]")
+    ap.add_argument("--lm-iterations", type=int, default=0,
+                    help="LM iterations per laserMapping pass (default: 5 for sr_lo_lm = configs[2]'s '10 GN iters' over the 2 passes; "
+                         "4 = the reference's setting, laser_mapping.cpp:612, for the others)")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
     ap.add_argument("--handles", type=int, default=2, help="split the batch over this many handles / CUDA streams (device leg)")
@@ -696,6 +713,8 @@ def main():
                          "streams and a slice of each stream's correspondences, normal equations summed in-kernel over NVLink")
     ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
+    if args.lm_iterations <= 0:
+        args.lm_iterations = 5 if args.workload == "sr_lo_lm" else 4
     if args.batch <= 0:
         args.batch = 256 if args.workload == "sr_lo" else 128
     rank = int(os.environ.get("RANK", "0"))

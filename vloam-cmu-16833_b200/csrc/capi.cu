@@ -19,7 +19,7 @@ const char* kernel_name(int id) {
   static const char* names[K_COUNT] = {
       "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_pick_features", "sr_less_flat_voxel", "sr_pack",
       "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state", "lo_build_grid", "lo_associate_brute",
-      "lm_prepare", "lm_voxel", "lm_index", "lm_associate", "lm_solve", "lm_insert", "lm_refilter", "lm_place", "lm_misc",
+      "lm_prepare", "lm_voxel", "lm_index", "lm_associate", "lm_fit", "lm_solve", "lm_insert", "lm_refilter", "lm_place", "lm_misc",
       "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }

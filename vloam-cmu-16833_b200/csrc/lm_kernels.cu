@@ -411,9 +411,14 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
                                      float4* __restrict__ sortedOut, int* s_cells, int* s_w) {
   for (int i = threadIdx.x; i <= kCubeCells; i += 256) s_cells[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float4 p = pts[i];
-    atomicAdd(&s_cells[cube_cell_clamped(p.y, minY) * kCubeCellsX + cube_cell_clamped(p.x, minX)], 1);
+  // (four independent loads in flight per thread: the passes over the cube are latency bound otherwise)
+  for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 256; if (i < n) p[u] = pts[i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (i0 + u * 256 < n) atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
   }
   __syncthreads();
   constexpr int per = (kCubeCells + 255) / 256;
@@ -431,10 +436,18 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
   for (int c = c0; c < c1; ++c) { const int t = s_cells[c]; s_cells[c] = run; tab[c] = run; run += t; }
   if (threadIdx.x == 255) tab[kCubeCells] = n;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += 256) {
-    const float4 p = pts[i];
-    const int pos = atomicAdd(&s_cells[cube_cell_clamped(p.y, minY) * kCubeCellsX + cube_cell_clamped(p.x, minX)], 1);
-    sortedOut[pos] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+  for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+    float4 p[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 256; if (i < n) p[u] = pts[i]; }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int i = i0 + u * 256;
+      if (i < n) {
+        const int pos = atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
+        sortedOut[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
+      }
+    }
   }
   __syncthreads();
 }
@@ -570,6 +583,7 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
     int bp[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
+    unsigned wbits = 0x3f7fffffu;   // the largest float below 1.0f (non-negative floats order like their bit patterns)
     if (qi < nq) {
       const float4 po = stk[qi];
       // pointAssociateToMap (:146-155): double transform, rounded to float
@@ -600,15 +614,29 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
               const unsigned gBase = (unsigned)st.validPrefix[kind][e];
               for (int row = max(qy - 1, 0); row <= min(qy + 1, kCubeCellsX - 1); ++row) {
                 const int a = tab[row * kCubeCellsX + x0], en = tab[row * kCubeCellsX + x1 + 1];
-                for (int t = a + gl; t < en; t += kLmGroup) {
-                  const float4 tp = S[off + t];
-                  const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-                  unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
-                  if (key < bk[4]) {
-                    int pos = off + t;
+                // four candidates in flight per lane: the walk is bound by the latency of these (L2) loads
+                for (int t = a + gl; t < en; t += 4 * kLmGroup) {
+                  float4 tp[4];
 #pragma unroll
-                    for (int i = 0; i < 5; ++i)
-                      if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+                  for (int u = 0; u < 4; ++u) if (t + u * kLmGroup < en) tp[u] = S[off + t + u * kLmGroup];
+#pragma unroll
+                  for (int u = 0; u < 4; ++u) {
+                    if (t + u * kLmGroup >= en) break;
+                    // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped,
+                    // :479 / :547, and then every true neighbour is), and none farther than this lane's 5th best.  The
+                    // distance is (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
+                    const float dz = __fsub_rn(sz, tp[u].z);
+                    if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) continue;
+                    const float d = sqdist_f(sx, sy, sz, tp[u].x, tp[u].y, tp[u].z);
+                    if (__float_as_uint(d) > wbits) continue;
+                    unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp[u].w));
+                    if (key < bk[4]) {
+                      int pos = off + t + u * kLmGroup;
+#pragma unroll
+                      for (int i = 0; i < 5; ++i)
+                        if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+                      wbits = min(wbits, (unsigned)(bk[4] >> 32));
+                    }
                   }
                 }
               }
@@ -1173,7 +1201,14 @@ __global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__
   const float4* src = direct ? stream_map(pools, st, b, kind, mapCap) + Tsrc.off[tb + c]
                              : staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
   float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
-  if (src != dst) for (int i = threadIdx.x; i < n; i += 256) dst[i] = src[i];
+  if (src != dst)
+    for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+      float4 p[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256; if (i < n) p[k] = src[i]; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256; if (i < n) dst[i] = p[k]; }
+    }
   if (slot < 0 || n == 0) return;
   cta_build_cube_index(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
@@ -1319,7 +1354,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
     VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
-    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res));
+    VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res));
     {
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.

@@ -365,7 +365,9 @@ __device__ __forceinline__ float grid_safe_radius(const GridView& G, float sx, f
 }
 
 // lo_associate: one 8-lane group per query, grid search.  grid (ceil((kMaxSharp + kMaxFlat) / 32), B), block 256.
-// Same contract as lo_associate_brute.
+// Same contract as lo_associate_brute.  U = candidate points a lane keeps in flight in the plain column walks (the walks
+// are bound by the latency of those loads; more in flight costs registers, i.e. occupancy).
+template <int U>
 __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ hdrCur, const SRHeader* __restrict__ hdrLast,
                                                      const LOState* __restrict__ lo, const float4* __restrict__ sharp,
                                                      const float4* __restrict__ flat, const float4* __restrict__ cornerLast,
@@ -412,11 +414,17 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
     // ---- phase 1: exact nearest neighbour (laser_odometry.cpp:269 / :356)
     unsigned long long best = 0xffffffffffffffffull;
     auto visit1 = [&](int aa, int bb) {
-      for (int t = aa + gl; t < bb; t += kGroup) {
-        const float4 tp = S[t];
-        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-        const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp.w);
-        best = key < best ? key : best;   // order: distance, then original index (the ring bits sit below the index)
+      for (int t = aa + gl; t < bb; t += U * kGroup) {
+        float4 tp[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) if (t + u * kGroup < bb) tp[u] = S[t + u * kGroup];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          if (t + u * kGroup >= bb) break;
+          const float d = sqdist_f(sx, sy, sz, tp[u].x, tp[u].y, tp[u].z);
+          const unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (unsigned)__float_as_int(tp[u].w);
+          best = key < best ? key : best;   // order: distance, then original index (the ring bits sit below the index)
+        }
       }
     };
     // a point at exactly the same distance could still win the index tie-break: the walk only stops on `>`.
@@ -512,7 +520,13 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
         };
         // a run of several columns (shell rows): not ordered as a whole, every point is tested
         auto visit2_run = [&](int aa, int bb) {
-          for (int t = aa + gl; t < bb; t += kGroup) consider(S[t]);
+          for (int t = aa + gl; t < bb; t += U * kGroup) {
+            float4 tp[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (t + u * kGroup < bb) tp[u] = S[t + u * kGroup];
+#pragma unroll
+            for (int u = 0; u < U; ++u) if (t + u * kGroup < bb) consider(tp[u]);
+          }
         };
         // a column can still matter while its bound is below the worst of the needed classes (25 = none found yet)
         group_visit_block_best_first(G, cs, sx, sy, qx, qy, gmask, gshift, gl, visit2, [&]() {
@@ -557,10 +571,10 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
 #define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr, shardRank, shardWorld
 // Two register budgets of the same body: 64 registers (4 CTAs / SM) and <= 40 (6 CTAs / SM); the kernel is latency
 // bound, so which one wins is an occupancy question settled by measurement (VLOAM_LO_ASSOC_OCC=4|5|6|8; measured on B200 at 128 streams: 334 / 314 / 293 us for 4 / 5 / 6, so 6 is the default).
-__global__ void __launch_bounds__(256) lo_associate(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
-__global__ void __launch_bounds__(256, 5) lo_associate_occ5(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
-__global__ void __launch_bounds__(256, 6) lo_associate_occ6(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
-__global__ void __launch_bounds__(256, 8) lo_associate_occ8(VB_LO_ASSOC_ARGS) { lo_associate_body(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 4) lo_associate(VB_LO_ASSOC_ARGS) { lo_associate_body<4>(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 5) lo_associate_occ5(VB_LO_ASSOC_ARGS) { lo_associate_body<2>(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 6) lo_associate_occ6(VB_LO_ASSOC_ARGS) { lo_associate_body<1>(VB_LO_ASSOC_PASS); }
+__global__ void __launch_bounds__(256, 8) lo_associate_occ8(VB_LO_ASSOC_ARGS) { lo_associate_body<1>(VB_LO_ASSOC_PASS); }
 
 
 // ---------------------------------------------------------------------------------------------
