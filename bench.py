@@ -288,6 +288,13 @@ def synth_map_cubes(n_points: int, seed: int):
 
 
 # --------------------------------------------------------------------------------------------- our arm (B200)
+# timing id (vloam_ctx_kernel_name) -> the __global__ functions launched under it (names as ncu prints them)
+NCU_KERNELS = {
+    "lm_associate": ["lm_knn"], "lm_voxel": ["lm_voxel_stack"], "lm_index": ["lm_index_build"], "lm_insert": ["lm_insert_keys"],
+    "lm_place": ["lm_place", "lm_compact_copy", "lm_write_back"], "lm_misc": ["lm_transform_update", "lm_export_pose"],
+}
+
+
 def algorithmic_bytes(kernel, c):
     """Algorithmic HBM bytes of ONE launch of `kernel` over the whole batch (DESIGN.md "Measurement").
     c: dict of batch totals: N (input points), Np (kept points), nLF, nLS, nSharp, nFlat (current scan features),
@@ -633,7 +640,8 @@ def run_ours(args, rank, world, local_rank):
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
             tj = json.load(f)
-        traffic = tj["kernels"][dom]["dram_bytes_per_launch_per_stream"] * (B / H)
+        members = NCU_KERNELS.get(dom, [dom])      # a timing id can cover several launches: average per launch, like `achieved`
+        traffic = sum(tj["kernels"][m_]["dram_bytes_per_launch_per_stream"] for m_ in members) / len(members) * (B / H)
     except Exception:
         traffic = None
     roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -1,7 +1,7 @@
 """Turns the ncu artefacts brought back in gpurun_out/ into the small summaries committed here.
-usage: python profiles/summarize.py LAUNCHES.csv FULL.ncu-rep TAG STREAMS_PER_LAUNCH
-writes profiles/TAG_ncu_launches_summary.md, profiles/TAG_ncu_full_summary.md and profiles/ncu_traffic.json
-(DRAM bytes per launch and per stream of every kernel, read by bench.py for `roofline.traffic`)."""
+usage: python profiles/summarize.py LAUNCHES.csv FULL.ncu-rep TAG STREAMS_PER_LAUNCH [WORKLOAD_DESCRIPTION]
+writes profiles/TAG_ncu_launches_summary.md, profiles/TAG_ncu_full_summary.md and merges the kernels it saw into
+profiles/ncu_traffic.json (DRAM bytes per launch and per stream of every kernel, read by bench.py for `roofline.traffic`)."""
 import collections
 import csv
 import json
@@ -9,6 +9,9 @@ import subprocess
 import sys
 
 launch_csv, rep, tag, streams = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
+what = sys.argv[5] if len(sys.argv) > 5 else "scanRegistration + laserOdometry"
+cmd = sys.argv[6] if len(sys.argv) > 6 else f"bench.py --legs device --batch {streams} --handles 1"
+bench_json = sys.argv[7] if len(sys.argv) > 7 else "profiles/r01_bench_default.json"
 
 
 def base(name):
@@ -34,9 +37,9 @@ for r in rows[1:]:
 tot = sum(v[1] for v in agg.values())
 with open(f"profiles/{tag}_ncu_launches_summary.md", "w") as out:
     out.write(f"# ncu launch list ({tag})\n\n`ncu --metrics gpu__time_duration.sum --clock-control none` over "
-              f"`bench.py --legs device --batch {streams} --handles 1` (scanRegistration + laserOdometry).\n"
+              f"`{cmd}` ({what}).\n"
               "Per-launch times under ncu are cold-cache and serialised; the SHARE is what must agree with the CUDA-event shares in\n"
-              "`profiles/r01_bench_default.json` (`kernels.*.share`).\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
+              f"`{bench_json}` (`kernels.*.share`).\n\n| kernel | launches | total us | share |\n|---|---|---|---|\n")
     for k, (n, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.write(f"| {k} | {n} | {us:.1f} | {us / tot:.3f} |\n")
 
@@ -63,8 +66,8 @@ cols = [("gpu__time_duration.sum", "time us"), ("dram__bytes_read.sum", "dram re
         ("smsp__inst_executed.sum", "warp instr"), ("l1tex__t_sector_hit_rate.pct", "L1 hit %"), ("lts__t_sector_hit_rate.pct", "L2 hit %")]
 traffic = {}
 with open(f"profiles/{tag}_ncu_full_summary.md", "w") as out:
-    out.write(f"# ncu --set full ({tag})\n\nOne scan of `bench.py --legs device --batch {streams} --handles 1` (second scan of the run, so laserOdometry "
-              "is active); one row per launch.\nDRAM bytes are per launch (all streams of the launch).\n\n| kernel | "
+    out.write(f"# ncu --set full ({tag})\n\nOne scan of `{cmd}` ({what}; a steady-state scan); one row per launch.\n"
+              "DRAM bytes are per launch (all streams of the launch).\n\n| kernel | "
               + " | ".join(c[1] for c in cols) + " |\n|---|" + "---|" * len(cols) + "\n")
     for r in rr[2:]:
         name = base(r[idx["Kernel Name"]])
@@ -91,7 +94,15 @@ for k, t in traffic.items():
     t["dram_bytes_per_launch"] = t["dram_bytes"] / t["launches"]
     t["dram_bytes_per_launch_per_stream"] = t["dram_bytes_per_launch"] / streams
     del t["dram_bytes"]
-json.dump({"source": f"profiles/{tag}_ncu_full_summary.md", "streams_per_launch": streams, "kernels": traffic},
-          open("profiles/ncu_traffic.json", "w"), indent=1)
+for t in traffic.values():
+    t["source"] = f"profiles/{tag}_ncu_full_summary.md"
+try:
+    merged = json.load(open("profiles/ncu_traffic.json"))
+except Exception:
+    merged = {"kernels": {}}
+merged.setdefault("kernels", {}).update(traffic)
+merged["source"] = "profiles/*_ncu_full_summary.md (per kernel: `source`)"
+merged.pop("streams_per_launch", None)
+json.dump(merged, open("profiles/ncu_traffic.json", "w"), indent=1)
 print(open(f"profiles/{tag}_ncu_full_summary.md").read())
 print(open(f"profiles/{tag}_ncu_launches_summary.md").read())

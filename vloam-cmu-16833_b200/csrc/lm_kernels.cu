@@ -405,23 +405,24 @@ __device__ __forceinline__ float4 submap_point(const LMState& st, int kind, cons
 __device__ __forceinline__ float cube_min_coord(int idx, int cen) { return (float)((idx - cen) * 50.0 - 25.0); }
 __device__ __forceinline__ int cube_cell(float v, float mn) { return (int)floorf((v - mn) * (1.0f / kCubeCell)); }
 __device__ __forceinline__ int cube_cell_clamped(float v, float mn) { return min(max(cube_cell(v, mn), 0), kCubeCellsX - 1); }
-// One CTA of 256 threads.  pts[0..n): the cube's slab; tab[kCubeCells + 1] (global) receives the column starts; sortedOut[0..n)
-// the column-sorted copy with w = index inside the cube.  s_cells: kCubeCells + 1 ints of shared memory, s_w: 8 ints.
+// One CTA of NT threads (a multiple of 32, <= 1024).  pts[0..n): the cube's slab; tab[kCubeCells + 1] (global) receives the column starts; sortedOut[0..n)
+// the column-sorted copy with w = index inside the cube.  s_cells: kCubeCells + 1 ints of shared memory, s_w: 32 ints.
+template <int NT>
 __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, float minX, float minY, int* __restrict__ tab,
                                      float4* __restrict__ sortedOut, int* s_cells, int* s_w) {
-  for (int i = threadIdx.x; i <= kCubeCells; i += 256) s_cells[i] = 0;
+  for (int i = threadIdx.x; i <= kCubeCells; i += NT) s_cells[i] = 0;
   __syncthreads();
   // (four independent loads in flight per thread: the passes over the cube are latency bound otherwise)
-  for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * NT) {
     float4 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 256; if (i < n) p[u] = pts[i]; }
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; if (i < n) p[u] = pts[i]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + u * 256 < n) atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
+      if (i0 + u * NT < n) atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
   }
   __syncthreads();
-  constexpr int per = (kCubeCells + 255) / 256;
+  constexpr int per = (kCubeCells + NT - 1) / NT;
   const int c0 = min((int)threadIdx.x * per, kCubeCells), c1 = min(c0 + per, kCubeCells);
   int sum = 0;
   for (int c = c0; c < c1; ++c) sum += s_cells[c];
@@ -434,15 +435,15 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
   int run = sc - sum;
   for (int q = 0; q < w; ++q) run += s_w[q];
   for (int c = c0; c < c1; ++c) { const int t = s_cells[c]; s_cells[c] = run; tab[c] = run; run += t; }
-  if (threadIdx.x == 255) tab[kCubeCells] = n;
+  if (threadIdx.x == NT - 1) tab[kCubeCells] = n;
   __syncthreads();
-  for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+  for (int i0 = threadIdx.x; i0 < n; i0 += 4 * NT) {
     float4 p[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) { const int i = i0 + u * 256; if (i < n) p[u] = pts[i]; }
+    for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; if (i < n) p[u] = pts[i]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int i = i0 + u * 256;
+      const int i = i0 + u * NT;
       if (i < n) {
         const int pos = atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
         sortedOut[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
@@ -451,18 +452,19 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
   }
   __syncthreads();
 }
-// lm_index_build: grid (kMaxValid, 2, B), block 256: CTA u indexes the u-th cube of lm_prepare's build list.
-__global__ void __launch_bounds__(256) lm_index_build(const LMState* __restrict__ stAll, const CubeTables T, const MapPools pools,
+// lm_index_build: grid (kMaxValid, 2, B), block kIndexThreads: CTA u indexes the u-th cube of lm_prepare's build list.
+constexpr int kIndexThreads = 512;
+__global__ void __launch_bounds__(kIndexThreads) lm_index_build(const LMState* __restrict__ stAll, const CubeTables T, const MapPools pools,
                                                        int mapCap, int* __restrict__ tabPool, float4* __restrict__ sorted) {
   __shared__ int s_cells[kCubeCells + 1];
-  __shared__ int s_w[8];
+  __shared__ int s_w[32];
   const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (u >= st.buildNum[kind]) return;
   const int c = st.buildList[kind][u];
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int off = T.off[tb + c], n = T.cnt[tb + c], slot = T.tab[tb + c];
-  cta_build_cube_index(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
+  cta_build_cube_index<kIndexThreads>(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
                        cube_min_coord((c / kCubeW) % kCubeH, st.cenH), tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1),
                        sorted + ((size_t)b * 2 + kind) * mapCap + off, s_cells, s_w);
 }
@@ -1184,13 +1186,13 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
     st.tabEnd[kind] = te;
   }
 }
-// lm_write_back: grid (kMaxWork, 2, B), block 256: rewritten cube -> its slab (in the other pool when the map is re-packed;
+// lm_write_back: grid (kMaxWork, 2, B), block kIndexThreads: rewritten cube -> its slab (in the other pool when the map is re-packed;
 // nothing to move when lm_refilter patched the slab in place), then the cube's column index is rebuilt from the new content.
-__global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__ stAll, const CubeTables Tsrc, const CubeTables T,
+__global__ void __launch_bounds__(kIndexThreads) lm_write_back(const LMState* __restrict__ stAll, const CubeTables Tsrc, const CubeTables T,
                                                       const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap,
                                                       int* __restrict__ tabPool, float4* __restrict__ sorted) {
   __shared__ int s_cells[kCubeCells + 1];
-  __shared__ int s_w[8];
+  __shared__ int s_w[32];
   const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (u >= st.workNum[kind] || st.error) return;
@@ -1202,15 +1204,15 @@ __global__ void __launch_bounds__(256) lm_write_back(const LMState* __restrict__
                              : staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
   float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
   if (src != dst)
-    for (int i0 = threadIdx.x; i0 < n; i0 += 1024) {
+    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kIndexThreads) {
       float4 p[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256; if (i < n) p[k] = src[i]; }
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) p[k] = src[i]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int i = i0 + k * 256; if (i < n) dst[i] = p[k]; }
+      for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) dst[i] = p[k]; }
     }
   if (slot < 0 || n == 0) return;
-  cta_build_cube_index(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
+  cta_build_cube_index<kIndexThreads>(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
                        s_cells, s_w);
 }
@@ -1349,7 +1351,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
                                                                               lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // C5: column index of the valid cubes that do not have one yet (new in the sub-map, seeded, or after a re-pack)
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(kMaxValid, 2, B), 256, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(kMaxValid, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
@@ -1381,7 +1383,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), 256, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
   lm->ran = true;
   return cudaGetLastError();

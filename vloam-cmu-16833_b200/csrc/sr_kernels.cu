@@ -96,21 +96,29 @@ __global__ void __launch_bounds__(256) sr_find_ends(const float* __restrict__ xy
   __shared__ int s_first, s_last;
   if (threadIdx.x == 0) { s_first = 0x7fffffff; s_last = -1; }
   __syncthreads();
-  for (int base = 0; base < n; base += 256) {
-    const int i = base + threadIdx.x;
-    bool v = false;
-    if (i < n) v = point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2);
-    if (v) atomicMin(&s_first, i);
+  // 2048 points per step (8 independent loads per thread): a scan can open / close with thousands of no-return points
+  constexpr int kPer = 8;
+  for (int base = 0; base < n; base += 256 * kPer) {
+    int first = 0x7fffffff;
+#pragma unroll
+    for (int u = kPer - 1; u >= 0; --u) {
+      const int i = base + u * 256 + threadIdx.x;
+      if (i < n && point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2)) first = i;
+    }
+    if (first != 0x7fffffff) atomicMin(&s_first, first);
     __syncthreads();
     const bool found = s_first != 0x7fffffff;
     __syncthreads();
     if (found) break;
   }
-  for (int top = n; top > 0; top -= 256) {
-    const int i = top - 1 - (int)threadIdx.x;
-    bool v = false;
-    if (i >= 0) v = point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2);
-    if (v) atomicMax(&s_last, i);
+  for (int top = n; top > 0; top -= 256 * kPer) {
+    int last = -1;
+#pragma unroll
+    for (int u = kPer - 1; u >= 0; --u) {
+      const int i = top - 1 - u * 256 - (int)threadIdx.x;
+      if (i >= 0 && point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2)) last = i;
+    }
+    if (last >= 0) atomicMax(&s_last, last);
     __syncthreads();
     const bool found = s_last >= 0;
     __syncthreads();
