@@ -114,8 +114,10 @@ int vloam_lidar_reset(vloam_lidar* h);
 
 /* LidarOdometryMapping::scanRegistrationIO(cloud)   lidar_odometry_mapping.cpp:73-94
  *   -> ScanRegistration::input   scan_registration.cpp:131-449
- * xyz: host buffer, `batch` slabs of `slab_points` points, each point `stride_floats` floats (3 = packed xyz,
- * 4 = pcl::PointXYZ); n_points[b] = valid points in slab b.  Pinned host memory makes the upload asynchronous. */
+ * xyz: host buffer, `batch` slabs of `slab_points` points, each point `stride_floats` floats starting with x, y, z
+ * (3 = packed xyz, 4 = pcl::PointXYZ or a KITTI .bin record, up to 16 = a sensor_msgs/PointCloud2 payload with
+ * point_step = 4 * stride_floats, taken without the pcl::fromROSMsg copy of vloam_main_node.cpp:148);
+ * n_points[b] = valid points in slab b.  Pinned host memory makes the upload asynchronous. */
 int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points);
 /* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers). */
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats,

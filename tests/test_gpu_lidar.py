@@ -214,3 +214,31 @@ def test_pipelined_host_api_matches_blocking(synth):
         for key in p:
             assert np.array_equal(p[key], q[key]), key
     a.close(); b.close()
+
+
+def test_wire_formats_feed_scan_registration(synth, oracle, tmp_path):
+    """a KITTI .bin record stream (4 floats per point) and a sensor_msgs/PointCloud2 payload with
+    point_step = 32 bytes go into scanRegistrationIO as they are (no pcl::fromROSMsg copy, vloam_main_node.cpp:148) and
+    give the same features as the packed cloud."""
+    import vloam_b200 as V
+    from vloam_b200 import wire
+    sc = synth.ScanStream(17, n_cols=512).scan(0)
+    ref = oracle.scan_registration(sc)
+    n = sc.shape[0]
+    # KITTI .bin: x y z reflectance
+    path = tmp_path / "000000.bin"
+    np.c_[sc, np.full(n, 0.5, np.float32)].astype(np.float32).tofile(str(path))
+    kitti = wire.load_kitti_bin(str(path))
+    # PointCloud2: 32-byte records, x y z at offset 0, intensity at 16, padding elsewhere
+    msg = np.zeros((n, 32), np.uint8)
+    msg[:, 0:12] = sc.copy().view(np.uint8).reshape(n, 12)
+    msg[:, 16:20] = np.full((n, 1), 0.25, np.float32).view(np.uint8)
+    pc2, zero_copy = wire.pointcloud2_xyz(msg.reshape(-1), n, 32, {"x": 0, "y": 4, "z": 8})
+    assert zero_copy and pc2.shape == (n, 8)
+    lom = V.LidarOdometryMapping(batch=1, max_points=n)
+    for cloud in (kitti, pc2, sc):
+        lom.reset()
+        lom.scanRegistrationIO(cloud)
+        _check_sr(lom, ref)
+        lom.laserOdometryIO()
+    lom.close()

@@ -222,14 +222,15 @@ class LidarOdometryMapping:
 
     # -- lidar_odometry_mapping.cpp:73-94
     def scanRegistrationIO(self, laserCloudIn, n_points=None):
-        """laserCloudIn: (batch, n, 3|4) or (n, 3|4) float32 host array (numpy / pinned torch), NaN = no return."""
+        """laserCloudIn: (batch, n, s) or (n, s) float32 host array (numpy / pinned torch), 3 <= s <= 16 floats per point
+        starting with x, y, z (3 = packed, 4 = pcl::PointXYZ / KITTI .bin, more = a PointCloud2 payload); NaN = no return."""
         a = laserCloudIn
         if isinstance(a, np.ndarray):
             a = np.ascontiguousarray(a, dtype=np.float32)
         shape = tuple(a.shape)
         if len(shape) == 2:
             shape = (1,) + shape
-        assert shape[0] == self.batch and shape[2] in (3, 4), shape
+        assert shape[0] == self.batch and 3 <= shape[2] <= 16, shape
         if n_points is None:
             n_points = np.full(self.batch, shape[1], np.int32)
         n_points = np.ascontiguousarray(n_points, np.int32)

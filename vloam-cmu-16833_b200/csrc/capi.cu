@@ -95,7 +95,8 @@ struct vloam_lidar {
   ShardView shard;
   ShardSlot* d_xbuf = nullptr;
   void* ipc_open[kMaxShard] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
-  float* d_in[2] = {nullptr, nullptr};  // [B][cap][4], double-buffered so the next upload overlaps this scan's kernels
+  float* d_in[2] = {nullptr, nullptr};  // [B][cap][in_stride], double-buffered so the next upload overlaps this scan's kernels
+  int in_stride = 4;                    // floats per point the input slabs are sized for (grown on demand, <= kMaxInputStride)
   int* d_n[2] = {nullptr, nullptr};     // [B]
   cudaEvent_t ev_in_ready[2] = {nullptr, nullptr}, ev_in_free[2] = {nullptr, nullptr};
   bool in_used[2] = {false, false};
@@ -387,10 +388,22 @@ static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int
   return VLOAM_OK;
 }
 
+// Records of up to 16 floats (a sensor_msgs/PointCloud2 point_step of 64 bytes) are taken as they are: x, y, z first.
+constexpr int kMaxInputStride = 16;
 int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride, size_t slab_points) {
-  if (!h || !xyz || !n_points || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  if (!h || !xyz || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
   vloam_ctx* c = h->ctx;
   CU(c, cudaSetDevice(c->device));
+  if (stride > h->in_stride) {   // first scan with wider records: re-size both input slabs (rare; synchronises)
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(h->d_in[i]); h->d_in[i] = nullptr;
+      CU(c, dalloc(&h->d_in[i], (size_t)h->B * h->cap * stride));
+      h->in_used[i] = false;
+    }
+    h->in_stride = stride;
+  }
   for (int b = 0; b < h->B; ++b) {
     if (n_points[b] < 0 || (size_t)n_points[b] > slab_points) return fail(c, VLOAM_E_INVALID, "n_points[b] exceeds slab_points");
     if (n_points[b] > h->cap) return fail(c, VLOAM_E_CAPACITY, "scan larger than max_points");
@@ -435,7 +448,7 @@ int vloam_input_consumed(vloam_lidar* h) {
 }
 
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
-  if (!h || !xyz_dev || !n_dev || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  if (!h || !xyz_dev || !n_dev || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
   CU(h->ctx, cudaSetDevice(h->ctx->device));
   return run_scan_registration(h, xyz_dev, n_dev, stride, slab_points);
 }

@@ -559,7 +559,7 @@ int vloam_vo_process_cloud(vloam_vo* h, const float* xyz, const int* n_points, i
   return vo_run_cloud(h, h->d_in, h->d_n, stride, (size_t)h->cap);
 }
 int vloam_vo_process_cloud_device(vloam_vo* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
-  if (!h || !xyz_dev || !n_dev || (stride != 3 && stride != 4)) return VLOAM_E_INVALID;
+  if (!h || !xyz_dev || !n_dev || stride < 3 || stride > 16) return VLOAM_E_INVALID;
   VCU(h->ctx, cudaSetDevice(h->ctx->device));
   return vo_run_cloud(h, xyz_dev, n_dev, stride, slab_points);
 }
