@@ -39,6 +39,16 @@ def build():
         out[f"scan{k}_lo_corr"] = np.array([lo["corner_correspondence"], lo["plane_correspondence"]])
         out[f"scan{k}_lm_pose"] = np.r_[lm["q_w_curr"], lm["t_w_curr"], lm["q_wmap_wodom"], lm["t_wmap_wodom"]]
         out[f"scan{k}_map_points"] = np.array([pipe.lm.map_points(0), pipe.lm.map_points(1)])
+        # the map after this scan: every occupied cube (kind, cube index, points) with the sha1 of its x, y, z bits in order
+        rows, digests = [], []
+        for kind in (0, 1):
+            for cube in range(4851):
+                n = pipe.lm.cube_count(kind, cube)
+                if n:
+                    rows.append((kind, cube, n))
+                    digests.append(np.frombuffer(hashlib.sha1(np.ascontiguousarray(pipe.lm.cube(kind, cube)[:, :3]).tobytes()).digest(), np.uint8))
+        out[f"scan{k}_cubes"] = np.array(rows, np.int32)
+        out[f"scan{k}_cube_sha1"] = np.stack(digests)
     return out
 
 
