@@ -292,6 +292,7 @@ def synth_map_cubes(n_points: int, seed: int):
 NCU_KERNELS = {
     "lm_associate": ["lm_knn"], "lm_voxel": ["lm_voxel_stack"], "lm_index": ["lm_index_build"], "lm_insert": ["lm_insert_keys"],
     "lm_place": ["lm_place", "lm_compact_copy", "lm_write_back"], "lm_misc": ["lm_transform_update", "lm_export_pose"],
+    "lm_refilter": ["lm_refilter_merge", "lm_refilter"],
 }
 
 
@@ -322,7 +323,7 @@ def algorithmic_bytes(kernel, c):
         "lm_fit": c.get("S", 0) * (16 + 20 + 5 * 16 + 72),
         "lm_solve": c.get("S", 0) * 80,
         "lm_insert": c.get("S", 0) * 48,
-        "lm_refilter": c.get("Mw", 0) * (16 * 3 + 8 * 4),   # rewritten cubes: slab read, concat written + read, keys/values, staged written
+        "lm_refilter": c.get("Mw", 0) * (16 + 16) // 2,     # two launches (merge path / sort path): rewritten cubes read, merged cubes written
         "lm_place": c.get("Mw", 0) * (16 * 3 + 16) // 3,    # three launches; write-back: staged read, slab + sorted copy written
     }
     return table.get(kernel, 0)
@@ -706,7 +707,7 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=0, help="independent streams per GPU (default: 256 for sr_lo, 128 for the mapping workloads)")
+    ap.add_argument("--batch", type=int, default=0, help="independent streams per GPU (default: 192 for sr_lo_lm, 256 for sr_lo, 128 for vloam)")
     ap.add_argument("--workload", default="sr_lo_lm", choices=["sr_lo", "sr_lo_lm", "vloam"],
                     help="sr_lo_lm (default) = BASELINE.json's metric, laserOdometry+Mapping on a 1 M-point map (configs[2], with the scan "
                          "registration that feeds it); sr_lo = configs[1]; vloam = configs[3]")
@@ -715,7 +716,9 @@ def main():
                          "4 = the reference's setting, laser_mapping.cpp:612, for the others)")
     ap.add_argument("--cpu-scans", type=int, default=200, help="scans timed for cpu_baseline (1 thread)")
     ap.add_argument("--map-points", type=int, default=1000000, help="size of the pre-built map for --workload sr_lo_lm")
-    ap.add_argument("--handles", type=int, default=2, help="split the batch over this many handles / CUDA streams (device leg)")
+    ap.add_argument("--handles", type=int, default=0,
+                    help="split the batch over this many handles / CUDA streams (device leg); default: 64 streams per handle for "
+                         "sr_lo_lm (3 handles), 2 handles otherwise")
     ap.add_argument("--parallelism", default="stream", choices=["stream", "point"],
                     help="N > 1: stream = independent streams per rank (weak scaling, headline); point = every rank holds all "
                          "streams and a slice of each stream's correspondences, normal equations summed in-kernel over NVLink")
@@ -724,7 +727,9 @@ def main():
     if args.lm_iterations <= 0:
         args.lm_iterations = 5 if args.workload == "sr_lo_lm" else 4
     if args.batch <= 0:
-        args.batch = 256 if args.workload == "sr_lo" else 128
+        args.batch = {"sr_lo": 256, "sr_lo_lm": 192, "vloam": 128}[args.workload]
+    if args.handles <= 0:
+        args.handles = 3 if args.workload == "sr_lo_lm" else 2
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

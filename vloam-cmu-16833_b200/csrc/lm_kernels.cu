@@ -958,17 +958,136 @@ __global__ void lm_transform_update(LMState* __restrict__ stAll, int B) {  // :1
   for (int i = 0; i < 3; ++i) st.t_wmap_wodom[i] = st.parameters[4 + i] - r[i];
 }
 
-// lm_refilter: grid (kMaxWork, 2, B), block 1024.  One work cube per CTA; input = old cube ++ new points.
+// Re-filter of the work list (LM:689-702 for the cubes that can change), one work cube per CTA; input = old cube ++ new points.
 //
-// Three paths (uniform per CTA):
-//   merge   the cube is a fixed point of its filter (one point per voxel, in lattice order) and its new points arrive
-//           sorted by voxel (lm_insert_keys): nothing is sorted.  The new points' voxel runs are located in the old cube
-//           by binary search; a run that hits an occupied voxel replaces that point by the voxel's new centroid
-//           ((0 + old) + new_1 + ... in stack order, exactly the sum pcl::VoxelGrid forms over old ++ new), a run in an
-//           empty voxel is inserted.  No insertion -> the few changed points are patched in the slab itself (workDirect),
-//           else the merged cube is written to `staged`.
-//   filter  any other valid cube: the full voxel filter (sort) over old ++ new.
-//   append  a cube outside the valid list only grows (:639-683), in stack order.
+// Three paths:
+//   merge   (lm_refilter_merge, 256 threads) the cube is a fixed point of its filter (one point per voxel, in lattice
+//           order) and its new points arrive sorted by voxel (lm_insert_keys): nothing is sorted.  The new points' voxel
+//           runs are located in the old cube by binary search; a run that hits an occupied voxel replaces that point by
+//           the voxel's new centroid ((0 + old) + new_1 + ... in stack order, exactly the sum pcl::VoxelGrid forms over
+//           old ++ new), a run in an empty voxel is inserted.  No insertion -> the few changed points are patched in the
+//           slab itself (workDirect), else the merged cube is written to `staged`.
+//   filter  (lm_refilter, 1024 threads) any other valid cube: the full voxel filter (sort) over old ++ new.
+//   append  (lm_refilter) a cube outside the valid list only grows (:639-683), in stack order.
+__device__ __forceinline__ bool refilter_merges(const LMState& st, int kind, int u, int nOld, int fixedPoint, int axisBits) {
+  return st.workFilter[kind][u] && fixedPoint && nOld > 0 && st.workNewN[kind][u] > 0 && axisBits > 0;
+}
+template <int NT>
+__device__ __forceinline__ int block_exclusive_scan_nt(int v, int* s_w /*[NT / 32 + 1]*/) {   // s_w[NT / 32] = block total
+  const int w = threadIdx.x >> 5, l = lane_id();
+  int s = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, s, o); if (l >= o) s += t; }
+  __syncthreads();                 // s_w may still be read from a previous call
+  if (l == 31) s_w[w] = s;
+  __syncthreads();
+  int base = 0, tot = 0;
+#pragma unroll
+  for (int q = 0; q < NT / 32; ++q) { const int x = s_w[q]; if (q < w) base += x; tot += x; }
+  if (threadIdx.x == 0) s_w[NT / 32] = tot;
+  __syncthreads();
+  return base + s - v;
+}
+constexpr int kMergeThreads = 256;
+__global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
+                                                                    const int* __restrict__ cubeCnt, const int* __restrict__ cubeFix,
+                                                                    const MapPools pools, int mapCap, const float4* __restrict__ stackW,
+                                                                    int cap, const unsigned* __restrict__ vAins, float lineRes, float planeRes,
+                                                                    int bitsLine, int bitsPlane, float4* __restrict__ concat,
+                                                                    float4* __restrict__ staged, unsigned* kA, unsigned* vA, unsigned* kB,
+                                                                    unsigned* vB, size_t workCap) {
+  constexpr int NT = kMergeThreads;
+  __shared__ int s_w[NT / 32 + 1];
+  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  LMState& st = stAll[b];
+  if (u >= st.workNum[kind] || st.error) return;
+  const int c = st.workCube[kind][u];
+  const size_t so = ((size_t)b * 2 + kind) * workCap;
+  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+  const int nOld = cubeCnt[tb + c], nNew = st.workNewN[kind][u];
+  const int axisBits = kind == 0 ? bitsLine : bitsPlane;
+  if (!refilter_merges(st, kind, u, nOld, cubeFix[tb + c], axisBits)) return;   // lm_refilter's cube
+  const int in0 = st.workIn0[kind][u];
+  float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
+  const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
+  const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points: by voxel, then stack order
+  float4* out = staged + so + in0;
+  const int tid = threadIdx.x;
+  const VoxLattice L = vox_lattice(c, st.cenW, st.cenH, st.cenD, kind == 0 ? lineRes : planeRes, axisBits);
+  unsigned* keyNew = kA + so + in0;                       // [nNew] voxel key of every new point
+  int* runStart = reinterpret_cast<int*>(vA + so + in0);  // [runs + 1] first new point of every voxel run
+  int* runPos = reinterpret_cast<int*>(kB + so + in0);    // [runs] position in the old cube (bit 31: that voxel is occupied)
+  int* insBefore = reinterpret_cast<int*>(vB + so + in0); // [runs] inserted runs before this one
+  int* insPos = reinterpret_cast<int*>(concat + so + in0);  // [inserted] old-cube position of every inserted run (concat is free here)
+  for (int t = tid; t < nNew; t += NT) { const float4 p = sw[ord[t]]; keyNew[t] = vox_key(L, p.x, p.y, p.z); }
+  __syncthreads();
+  const int per = (nNew + NT - 1) / NT;
+  const int t0 = min(tid * per, nNew), t1 = min(t0 + per, nNew);
+  int nh = 0;
+  for (int t = t0; t < t1; ++t) nh += (t == 0 || keyNew[t] != keyNew[t - 1]) ? 1 : 0;
+  int r0 = block_exclusive_scan_nt<NT>(nh, s_w);
+  const int runs = s_w[NT / 32];
+  for (int t = t0; t < t1; ++t) if (t == 0 || keyNew[t] != keyNew[t - 1]) runStart[r0++] = t;
+  if (tid == 0) runStart[runs] = nNew;
+  __syncthreads();
+  for (int r = tid; r < runs; r += NT) {
+    const unsigned vk = keyNew[runStart[r]];
+    int lo = 0, hi = nOld;
+    while (lo < hi) {
+      const int mid = (lo + hi) >> 1;
+      const float4 q = old[mid];
+      if (vox_key(L, q.x, q.y, q.z) < vk) lo = mid + 1; else hi = mid;
+    }
+    int hit = 0;
+    if (lo < nOld) { const float4 q = old[lo]; hit = vox_key(L, q.x, q.y, q.z) == vk; }
+    runPos[r] = lo | (hit ? (int)0x80000000 : 0);
+  }
+  __syncthreads();
+  const int perR = (runs + NT - 1) / NT;
+  const int q0 = min(tid * perR, runs), q1 = min(q0 + perR, runs);
+  int ni = 0;
+  for (int r = q0; r < q1; ++r) ni += runPos[r] < 0 ? 0 : 1;
+  int i0 = block_exclusive_scan_nt<NT>(ni, s_w);
+  const int inserted = s_w[NT / 32];
+  for (int r = q0; r < q1; ++r) {
+    insBefore[r] = i0;
+    if (runPos[r] >= 0) insPos[i0++] = runPos[r];
+  }
+  __syncthreads();
+  const int m = nOld + inserted;
+  const int direct = inserted == 0 ? 1 : 0;
+  float4* dst = direct ? old : out;
+  if (!direct) {
+    // old point i moves up by the number of inserted runs placed at or before it (insPos is ascending)
+    for (int i = tid; i < nOld; i += NT) {
+      int lo = 0, hi = inserted;
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (insPos[mid] <= i) lo = mid + 1; else hi = mid; }
+      dst[i + lo] = old[i];
+    }
+    __syncthreads();
+  }
+  int inside = 1;
+  for (int r = tid; r < runs; r += NT) {
+    const int pos = runPos[r] & 0x7fffffff;
+    const bool hit = runPos[r] < 0;
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int cnt = 0;
+    if (hit) { const float4 o = old[pos]; sx = __fadd_rn(sx, o.x); sy = __fadd_rn(sy, o.y); sz = __fadd_rn(sz, o.z); si = __fadd_rn(si, o.w); cnt = 1; }
+    for (int t = runStart[r]; t < runStart[r + 1]; ++t) {
+      const float4 p = sw[ord[t]];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+      ++cnt;
+    }
+    const float nf = (float)cnt;
+    const float4 cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+    if (vox_key(L, cen.x, cen.y, cen.z) != keyNew[runStart[r]]) inside = 0;
+    dst[pos + insBefore[r]] = cen;
+  }
+  const int fixed = __syncthreads_and(inside);
+  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct; }
+}
+
+// lm_refilter: grid (kMaxWork, 2, B), block 1024: the filter and append paths.
 __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll, const int* __restrict__ cubeOff, const int* __restrict__ cubeCnt,
                                                      const int* __restrict__ cubeFix, const MapPools pools, int mapCap,
                                                      const float4* __restrict__ stackW,
@@ -985,108 +1104,33 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int in0 = st.workIn0[kind][u];
   const int nOld = cubeCnt[tb + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
-  float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
+  if (refilter_merges(st, kind, u, nOld, cubeFix[tb + c], kind == 0 ? bitsLine : bitsPlane)) return;   // lm_refilter_merge's cube
+  const float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
   const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
   const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points: by voxel, then stack order
   float4* in = concat + so + in0;
   float4* out = staged + so + in0;
   const float leaf = kind == 0 ? lineRes : planeRes;
-  const int axisBits = kind == 0 ? bitsLine : bitsPlane;
   const int tid = threadIdx.x;
-  int m, fixed = 0, direct = 0;
-  if (st.workFilter[kind][u] && cubeFix[tb + c] && nOld > 0 && nNew > 0 && axisBits > 0) {
-    // ---------------- merge
-    const VoxLattice L = vox_lattice(c, st.cenW, st.cenH, st.cenD, leaf, axisBits);
-    unsigned* keyNew = kA + so + in0;                       // [nNew] voxel key of every new point
-    int* runStart = reinterpret_cast<int*>(vA + so + in0);  // [runs + 1] first new point of every voxel run
-    int* runPos = reinterpret_cast<int*>(kB + so + in0);    // [runs] position in the old cube (bit 31: that voxel is occupied)
-    int* insBefore = reinterpret_cast<int*>(vB + so + in0); // [runs] inserted runs before this one
-    int* insPos = reinterpret_cast<int*>(in);               // [inserted] old-cube position of every inserted run (concat is free here)
-    for (int t = tid; t < nNew; t += 1024) { const float4 p = sw[ord[t]]; keyNew[t] = vox_key(L, p.x, p.y, p.z); }
+  int m, fixed = 0;
+  if (st.workFilter[kind][u]) {
+    // ---------------- filter
+    for (int i = tid; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
     __syncthreads();
-    const int per = (nNew + 1023) / 1024;
-    const int t0 = min(tid * per, nNew), t1 = min(t0 + per, nNew);
-    int nh = 0;
-    for (int t = t0; t < t1; ++t) nh += (t == 0 || keyNew[t] != keyNew[t - 1]) ? 1 : 0;
-    int r0 = block_exclusive_scan1024(nh, S);
-    const int runs = S.total;
-    for (int t = t0; t < t1; ++t) if (t == 0 || keyNew[t] != keyNew[t - 1]) runStart[r0++] = t;
-    if (tid == 0) runStart[runs] = nNew;
-    __syncthreads();
-    for (int r = tid; r < runs; r += 1024) {
-      const unsigned vk = keyNew[runStart[r]];
-      int lo = 0, hi = nOld;
-      while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        const float4 q = old[mid];
-        if (vox_key(L, q.x, q.y, q.z) < vk) lo = mid + 1; else hi = mid;
-      }
-      int hit = 0;
-      if (lo < nOld) { const float4 q = old[lo]; hit = vox_key(L, q.x, q.y, q.z) == vk; }
-      runPos[r] = lo | (hit ? (int)0x80000000 : 0);
-    }
-    __syncthreads();
-    const int perR = (runs + 1023) / 1024;
-    const int q0 = min(tid * perR, runs), q1 = min(q0 + perR, runs);
-    int ni = 0;
-    for (int r = q0; r < q1; ++r) ni += runPos[r] < 0 ? 0 : 1;
-    int i0 = block_exclusive_scan1024(ni, S);
-    const int inserted = S.total;
-    for (int r = q0; r < q1; ++r) {
-      insBefore[r] = i0;
-      if (runPos[r] >= 0) insPos[i0++] = runPos[r];
-    }
-    __syncthreads();
-    m = nOld + inserted;
-    direct = inserted == 0 ? 1 : 0;
-    float4* dst = direct ? old : out;
-    if (!direct) {
-      // old point i moves up by the number of inserted runs placed at or before it (insPos is ascending)
-      for (int i = tid; i < nOld; i += 1024) {
-        int lo = 0, hi = inserted;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (insPos[mid] <= i) lo = mid + 1; else hi = mid; }
-        dst[i + lo] = old[i];
-      }
-      __syncthreads();
-    }
-    int inside = 1;
-    for (int r = tid; r < runs; r += 1024) {
-      const int pos = runPos[r] & 0x7fffffff;
-      const bool hit = runPos[r] < 0;
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      int cnt = 0;
-      if (hit) { const float4 o = old[pos]; sx = __fadd_rn(sx, o.x); sy = __fadd_rn(sy, o.y); sz = __fadd_rn(sz, o.z); si = __fadd_rn(si, o.w); cnt = 1; }
-      for (int t = runStart[r]; t < runStart[r + 1]; ++t) {
-        const float4 p = sw[ord[t]];
-        sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
-        ++cnt;
-      }
-      const float nf = (float)cnt;
-      const float4 cen = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
-      if (vox_key(L, cen.x, cen.y, cen.z) != keyNew[runStart[r]]) inside = 0;
-      dst[pos + insBefore[r]] = cen;
-    }
-    fixed = __syncthreads_and(inside);
+    // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
+    m = cta_voxel_filter(in, n, leaf, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red, &fixed);
   } else {
-    if (st.workFilter[kind][u]) {
-      // ---------------- filter
-      for (int i = tid; i < n; i += 1024) in[i] = i < nOld ? old[i] : sw[ord[i - nOld]];
-      __syncthreads();
-      // scratch keys for this cube live at the cube's input offset in the second half of the key arrays
-      m = cta_voxel_filter(in, n, leaf, out, kA + so + in0, vA + so + in0, kB + so + in0, vB + so + in0, S, red, &fixed);
-    } else {
-      // ---------------- append: back to stack order (a 16-bit key covers every stack index of a scan up to 65 536 points;
-      // larger scans sort on all 32 bits)
-      unsigned* ka = kA + so + in0; unsigned* va = vA + so + in0; unsigned* kb = kB + so + in0; unsigned* vb = vB + so + in0;
-      for (int t = tid; t < nNew; t += 1024) { ka[t] = ord[t]; va[t] = ord[t]; }
-      __syncthreads();
-      const int cur = cta_radix_sort(ka, va, kb, vb, nNew, cap <= 65536 ? 16 : 32, S);
-      const unsigned* vs = cur ? vb : va;
-      for (int i = tid; i < n; i += 1024) out[i] = i < nOld ? old[i] : sw[vs[i - nOld]];
-      m = n;
-    }
+    // ---------------- append: back to stack order (a 16-bit key covers every stack index of a scan up to 65 536 points;
+    // larger scans sort on all 32 bits)
+    unsigned* ka = kA + so + in0; unsigned* va = vA + so + in0; unsigned* kb = kB + so + in0; unsigned* vb = vB + so + in0;
+    for (int t = tid; t < nNew; t += 1024) { ka[t] = ord[t]; va[t] = ord[t]; }
+    __syncthreads();
+    const int cur = cta_radix_sort(ka, va, kb, vb, nNew, cap <= 65536 ? 16 : 32, S);
+    const unsigned* vs = cur ? vb : va;
+    for (int i = tid; i < n; i += 1024) out[i] = i < nOld ? old[i] : sw[vs[i - nOld]];
+    m = n;
   }
-  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct; }
+  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = 0; }
 }
 
 // lm_place: grid (2, B), block 1024.  New cube tables `dst` from the post-shift tables `src`: a rewritten cube keeps its
@@ -1377,6 +1421,9 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->cubeFix[td],
                                                                                lm->cubeOf, lineRes, planeRes, bitsLine, bitsPlane, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // the cube-sorted stack indices stay in valA[0 .. n); the per-cube filters use the key/val slabs from offset `cap` on
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter_merge<<<dim3(kMaxWork, 2, B), kMergeThreads, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
+                                                                                         lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
+                                                                                         lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
   VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
                                                                                          lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
