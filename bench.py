@@ -554,31 +554,48 @@ def run_ours(args, rank, world, local_rank):
     lm_info_all = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64) if do_map else None
     map_stats_all = np.concatenate([hd.map_stats() for hd in loms]).astype(np.int64) if do_map else None
     lm_tr = loms[0].lm_trace(1, 0) if do_map else None
-    for g in groups[1:]:
-        g.close()               # the e2e leg below reuses the first context; free the other groups' device memory
-
-    # ---------------- leg 2: host buffers through the public API -> `e2e`
-    g2 = Group(ctx, 0, B)
     if point:
         groups[0].lom.shard_disable()
+    for g in groups:
+        g.close()               # fresh handles for the e2e leg (same inputs, same number of steps -> same final poses)
+
+    # ---------------- leg 2: host buffers through the public API -> `e2e`
+    # The same H handles as the device leg, each uploading its streams' scans from pinned host memory on its own copy
+    # stream (one scan in flight per handle) and reading its poses back.
+    groups2 = []
+    for h in range(H):
+        with torch.cuda.stream(streams[h]):
+            groups2.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
+    g2 = groups2[0]
+    if point:
         D.enable_point_sharding(g2.lom, dist, dev)
+
+    def step_host(i, first):
+        for h in range(H):
+            with torch.cuda.stream(streams[h]):
+                groups2[h].step_host(i, first)
 
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
-            g2.step_host(i, i == 0)
+            step_host(i, i == 0)
         if args.warmup:
-            g2.lom.lo_pose()
+            for g in groups2:
+                g.lom.lo_pose()
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_host0 = time.perf_counter()
         e0.record(stream)
+        for s_ in streams[1:]:
+            s_.wait_event(e0)
         for i in range(args.warmup, args.warmup + args.steps):
-            g2.step_host(i, i == args.warmup)
-        pose_host = g2.lom.lo_pose()          # drain: the last scan's result is read inside the timed region too
+            step_host(i, i == args.warmup)
+        poses_h = [g.lom.lo_pose() for g in groups2]    # drain: the last scan's results are read inside the timed region too
+        join_streams()
         e1.record(stream)
         barrier()
         t_host1 = time.perf_counter()
         ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0)))
+    pose_host = {kk: np.concatenate([p_[kk] for p_ in poses_h]) for kk in poses_h[0]}
     e2e_value = (1 if point else world) * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
     d2h = int(B * 16 * 8)
