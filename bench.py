@@ -673,7 +673,7 @@ def run_ours(args, rank, world, local_rank):
     from oracle import pyoracle as O
     O.build()
     pipe = CpuChain(O, args.workload, map_cubes, args.lm_iterations)
-    n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 20)
+    n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 4)      # ~10-15 s of CPU work either way
     cpu_m = [cpu_matches(scan_streams[0], i) for i in range(n_cpu)] if do_vo else [None] * n_cpu
     t0 = time.perf_counter()
     for i in range(n_cpu):
