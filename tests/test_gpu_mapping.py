@@ -23,11 +23,13 @@ def _same_xyz(a, b, name):
         assert np.max(np.abs(a[:, 3] - b[:, 3])) < 0.14, f"{name}: intensity"
 
 
-def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None):
+def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None, before_scan=None):
     lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=map_capacity, debug_keep_submap=1)
     pipe = oracle.Pipeline()
     worst_t = 0.0
     for k, scan in enumerate(scans):
+        if before_scan is not None:
+            before_scan(k, lom, pipe)
         lom.reset()
         lom.scanRegistrationIO(scan)
         lom.laserOdometryIO()
@@ -82,6 +84,16 @@ def test_laser_mapping_sequence(synth, oracle):
     s = synth.ScanStream(31, n_cols=1024)
     scans = [s.scan(k) for k in range(5)]
     worst = _run_sequence(V, oracle, scans)
+    print("max |t_w_curr - oracle| =", worst)
+
+
+def test_laser_mapping_full_size(synth, oracle):
+    """BASELINE configs[2] shape: full 64 x 2048 scans through scan registration, odometry and mapping (the map is built
+    by the scans themselves); every cube, trace and pose against the oracle after every scan."""
+    import vloam_b200 as V
+    s = synth.ScanStream(33, n_cols=2048)
+    scans = [s.scan(k) for k in range(3)]
+    worst = _run_sequence(V, oracle, scans, map_capacity=1 << 17)
     print("max |t_w_curr - oracle| =", worst)
 
 
@@ -151,6 +163,32 @@ def test_laser_mapping_batched_streams_on_seeded_map(synth, oracle):
             assert (ms[:, 1, 5] < ms[:, 1, 3]).all(), ms[:, 1, :]
             assert (ms[:, :, 4] > 0).all()
     lom.close()
+
+
+def test_laser_mapping_column_table_recycling(synth, oracle, monkeypatch):
+    """The per-cube column tables come from a fixed pool of slots; cubes dropped by grid shifts leak theirs until the pool
+    runs out, then every index is dropped and rebuilt.  With only 14 slots per kind that happens several times in 8
+    scans; map and poses must stay identical to the oracle's."""
+    import vloam_b200 as V
+    monkeypatch.setenv("VLOAM_LM_TAB_SLOTS", "16")
+    s = synth.ScanStream(31, n_cols=1024)
+    scans = [s.scan(k) for k in range(8)]
+    rng = np.random.default_rng(9)
+    cube = 10 + 21 * 10 + 441 * 6            # the cube above the sensor (z in [25, 75)): valid, never reached by the scans
+
+    def reseed(k, lom, pipe):                # replacing a cube's content drops its column index: its table slot leaks
+        if k == 0:
+            return                           # (keep the first scan's empty-map case, laser_mapping.cpp:448)
+        pts = np.c_[rng.uniform(-20, 20, (80, 2)), rng.uniform(30, 70, 80), np.zeros(80)].astype(np.float32)
+        for kind in (0, 1):
+            lom.map_set_cube(kind, cube, pts)
+            pipe.lm.set_cube(kind, cube, pts)
+
+    stats = []
+    _run_sequence(V, oracle, scans, stats_out=stats, before_scan=reseed)
+    st = np.stack(stats)                     # (scan, kind, 10): [9] = table slots handed out
+    assert st[:, :, 9].max() <= 16, st[:, :, 9]
+    assert (np.diff(st[:, 1, 9]) < 0).any(), st[:, 1, 9]      # the slot counter started over at least once
 
 
 def test_laser_mapping_seeded_map_and_cube_shift(synth, oracle):

@@ -52,6 +52,7 @@ struct LMState {
   int compact[2];                       // this scan's write-back re-packs the whole map into the other pool
   int repacks[2];                       // re-packs so far
   int tabEnd[2];                        // column-table slots handed out so far
+  int tabLimit;                         // slots that may be handed out (kTabSlots; smaller only to exercise the recycling in tests)
   int buildNum[2], buildList[2][kMaxValid];   // valid cubes whose column index has to be (re)built before the association
   short entryNext[kMaxValid];           // next valid-list entry naming the same cube (-1: none); heads in LMDevice::entryHead
   int workNum[2];
@@ -343,7 +344,7 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
       }
       st.validPrefix[kind][vn] = acc;
       st.fromMapNum[kind] = acc;
-      s_gc[kind] = st.tabEnd[kind] + need > kTabSlots ? 1 : 0;   // out of table slots: drop every index of this kind, start over
+      s_gc[kind] = st.tabEnd[kind] + need > st.tabLimit ? 1 : 0;   // out of table slots: drop every index of this kind, start over
     }
     st.solved = (st.fromMapNum[0] > 10 && st.fromMapNum[1] > 50) ? 1 : 0;  // :448
     st.trace[0].n_records = st.trace[1].n_records = 0;
@@ -458,15 +459,16 @@ __global__ void __launch_bounds__(kIndexThreads) lm_index_build(const LMState* _
                                                        int mapCap, int* __restrict__ tabPool, float4* __restrict__ sorted) {
   __shared__ int s_cells[kCubeCells + 1];
   __shared__ int s_w[32];
-  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
-  if (u >= st.buildNum[kind]) return;
+  for (int u = blockIdx.x; u < st.buildNum[kind]; u += gridDim.x) {
   const int c = st.buildList[kind][u];
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int off = T.off[tb + c], n = T.cnt[tb + c], slot = T.tab[tb + c];
   cta_build_cube_index<kIndexThreads>(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
                        cube_min_coord((c / kCubeW) % kCubeH, st.cenH), tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1),
                        sorted + ((size_t)b * 2 + kind) * mapCap + off, s_cells, s_w);
+  }
 }
 
 // laserCloudCornerFromMap / SurfFromMap (:422-428) kept for inspection (debug_keep_submap): grid (nblk, 2, B), block 256
@@ -989,6 +991,7 @@ __device__ __forceinline__ int block_exclusive_scan_nt(int v, int* s_w /*[NT / 3
   return base + s - v;
 }
 constexpr int kMergeThreads = 256;
+constexpr int kSortGrid = 16;     // CTAs per stream and kind of the sort-path re-filter (grid-stride over the work list)
 __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __restrict__ stAll, const int* __restrict__ cubeOff,
                                                                     const int* __restrict__ cubeCnt, const int* __restrict__ cubeFix,
                                                                     const MapPools pools, int mapCap, const float4* __restrict__ stackW,
@@ -998,15 +1001,17 @@ __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __re
                                                                     unsigned* vB, size_t workCap) {
   constexpr int NT = kMergeThreads;
   __shared__ int s_w[NT / 32 + 1];
-  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const int kind = blockIdx.y, b = blockIdx.z;
   LMState& st = stAll[b];
-  if (u >= st.workNum[kind] || st.error) return;
+  if (st.error) return;
+  const int nWork = st.workNum[kind];
+  for (int u = blockIdx.x; u < nWork; u += gridDim.x) {   // (a grid of one CTA per possible work cube would be mostly empty CTAs)
   const int c = st.workCube[kind][u];
   const size_t so = ((size_t)b * 2 + kind) * workCap;
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int nOld = cubeCnt[tb + c], nNew = st.workNewN[kind][u];
   const int axisBits = kind == 0 ? bitsLine : bitsPlane;
-  if (!refilter_merges(st, kind, u, nOld, cubeFix[tb + c], axisBits)) return;   // lm_refilter's cube
+  if (!refilter_merges(st, kind, u, nOld, cubeFix[tb + c], axisBits)) continue;   // lm_refilter's cube
   const int in0 = st.workIn0[kind][u];
   float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
   const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
@@ -1085,9 +1090,10 @@ __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __re
   }
   const int fixed = __syncthreads_and(inside);
   if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct; }
+  }
 }
 
-// lm_refilter: grid (kMaxWork, 2, B), block 1024: the filter and append paths.
+// lm_refilter: grid (kSortGrid, 2, B), block 1024: the filter and append paths (rare once the map is in fixed-point form).
 __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll, const int* __restrict__ cubeOff, const int* __restrict__ cubeCnt,
                                                      const int* __restrict__ cubeFix, const MapPools pools, int mapCap,
                                                      const float4* __restrict__ stackW,
@@ -1096,15 +1102,17 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
                                                      unsigned* kB, unsigned* vB, size_t workCap) {
   __shared__ SortSmem S;
   __shared__ float red[6 * 32];
-  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const int kind = blockIdx.y, b = blockIdx.z;
   LMState& st = stAll[b];
-  if (u >= st.workNum[kind] || st.error) return;
+  if (st.error) return;
+  const int nWork = st.workNum[kind];
+  for (int u = blockIdx.x; u < nWork; u += gridDim.x) {
   const int c = st.workCube[kind][u];
   const size_t so = ((size_t)b * 2 + kind) * workCap;
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int in0 = st.workIn0[kind][u];
   const int nOld = cubeCnt[tb + c], nNew = st.workNewN[kind][u], n = nOld + nNew;
-  if (refilter_merges(st, kind, u, nOld, cubeFix[tb + c], kind == 0 ? bitsLine : bitsPlane)) return;   // lm_refilter_merge's cube
+  if (refilter_merges(st, kind, u, nOld, cubeFix[tb + c], kind == 0 ? bitsLine : bitsPlane)) continue;   // lm_refilter_merge's cube
   const float4* old = stream_map(pools, st, b, kind, mapCap) + cubeOff[tb + c];
   const float4* sw = stackW + ((size_t)b * 2 + kind) * cap;
   const unsigned* ord = vAins + so + st.workNew0[kind][u];   // stack indices of this cube's new points: by voxel, then stack order
@@ -1131,6 +1139,8 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
     m = n;
   }
   if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = 0; }
+  __syncthreads();   // shared memory is reused by the next cube
+  }
 }
 
 // lm_place: grid (2, B), block 1024.  New cube tables `dst` from the post-shift tables `src`: a rewritten cube keeps its
@@ -1180,7 +1190,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
       for (int u = 0; u < wn; ++u) {
         const int c = st.workCube[kind][u];
         if (st.workOutN[kind][u] == 0) dst.tab[tb + c] = -1;
-        else if (dst.tab[tb + c] < 0 && te < kTabSlots) dst.tab[tb + c] = te++;
+        else if (dst.tab[tb + c] < 0 && te < st.tabLimit) dst.tab[tb + c] = te++;
       }
       st.tabEnd[kind] = te;
     }
@@ -1226,7 +1236,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
   if (threadIdx.x == 0) {
     st.poolEnd[kind] = S.total; st.compact[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive;
     int te = 0;                        // table slots start over; the rewritten cubes are re-indexed right away
-    for (int u = 0; u < wn && te < kTabSlots; ++u) if (st.workOutN[kind][u] > 0) dst.tab[tb + st.workCube[kind][u]] = te++;
+    for (int u = 0; u < wn && te < st.tabLimit; ++u) if (st.workOutN[kind][u] > 0) dst.tab[tb + st.workCube[kind][u]] = te++;
     st.tabEnd[kind] = te;
   }
 }
@@ -1237,9 +1247,11 @@ __global__ void __launch_bounds__(kIndexThreads) lm_write_back(const LMState* __
                                                       int* __restrict__ tabPool, float4* __restrict__ sorted) {
   __shared__ int s_cells[kCubeCells + 1];
   __shared__ int s_w[32];
-  const int u = blockIdx.x, kind = blockIdx.y, b = blockIdx.z;
+  const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
-  if (u >= st.workNum[kind] || st.error) return;
+  if (st.error) return;
+  const int nWork = st.workNum[kind];
+  for (int u = blockIdx.x; u < nWork; u += gridDim.x) {
   const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const int off = T.off[tb + c], slot = T.tab[tb + c];
@@ -1255,10 +1267,11 @@ __global__ void __launch_bounds__(kIndexThreads) lm_write_back(const LMState* __
 #pragma unroll
       for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) dst[i] = p[k]; }
     }
-  if (slot < 0 || n == 0) return;
+  if (slot < 0 || n == 0) continue;
   cta_build_cube_index<kIndexThreads>(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
                        s_cells, s_w);
+  }
 }
 // lm_compact_copy: grid (128, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
 __global__ void __launch_bounds__(256) lm_compact_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
@@ -1293,7 +1306,7 @@ __global__ void lm_export_pose(LMState* __restrict__ stAll, double* __restrict__
   for (int i = 0; i < 3; ++i) o[11 + i] = s.t_wmap_wodom[i];
   o[14] = s.error; o[15] = s.solved;
 }
-__global__ void lm_init_state(LMState* stAll, int B) {
+__global__ void lm_init_state(LMState* stAll, int B, int tabLimit) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   LMState& s = stAll[b];
@@ -1304,7 +1317,7 @@ __global__ void lm_init_state(LMState* stAll, int B) {
   s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
   s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0;
   s.cur[0] = s.cur[1] = 0; s.compact[0] = s.compact[1] = 0; s.repacks[0] = s.repacks[1] = 0;
-  s.tabEnd[0] = s.tabEnd[1] = 0; s.buildNum[0] = s.buildNum[1] = 0;
+  s.tabEnd[0] = s.tabEnd[1] = 0; s.buildNum[0] = s.buildNum[1] = 0; s.tabLimit = tabLimit;
   s.trace[0].n_records = s.trace[1].n_records = 0;
 }
 
@@ -1340,7 +1353,11 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->pose, B * 16 * sizeof(double));
   A((void**)&lm->workOf, B * 2 * kCubes * sizeof(short));
   if (e != cudaSuccess) return e;
-  VB_LAUNCH(lm->prof, K_LM_MISC, st, lm_init_state<<<(lm->B + 127) / 128, 128, 0, st>>>(lm->st, lm->B));
+  // VLOAM_LM_TAB_SLOTS (tests only): hand out fewer column-table slots so that their recycling runs in a short sequence; the
+  // value must exceed the number of occupied valid cubes
+  int tabLimit = kTabSlots;
+  if (const char* env = getenv("VLOAM_LM_TAB_SLOTS")) { const int v = atoi(env); if (v > 0 && v < kTabSlots) tabLimit = v; }
+  VB_LAUNCH(lm->prof, K_LM_MISC, st, lm_init_state<<<(lm->B + 127) / 128, 128, 0, st>>>(lm->st, lm->B, tabLimit));
   lm->allocated = true;
   return cudaGetLastError();
 }
@@ -1395,7 +1412,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
                                                                               lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // C5: column index of the valid cubes that do not have one yet (new in the sub-map, seeded, or after a re-pack)
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(kMaxValid, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(32, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
@@ -1421,16 +1438,16 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_INSERT, st, lm_insert_keys<<<dim3(2, B), 1024, 0, st>>>(lm->st, lm->stack, cap, lm->stackW, lm->cubeCnt[td], lm->cubeFix[td],
                                                                                lm->cubeOf, lineRes, planeRes, bitsLine, bitsPlane, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // the cube-sorted stack indices stay in valA[0 .. n); the per-cube filters use the key/val slabs from offset `cap` on
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter_merge<<<dim3(kMaxWork, 2, B), kMergeThreads, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter_merge<<<dim3(32, 2, B), kMergeThreads, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
                                                                                          lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
-  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kMaxWork, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
+  VB_LAUNCH(prof, K_LM_REFILTER, st, lm_refilter<<<dim3(kSortGrid, 2, B), 1024, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeCnt[td], lm->cubeFix[td], pools, mapCap,
                                                                                          lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(kMaxWork, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(32, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
   lm->ran = true;
   return cudaGetLastError();
