@@ -1273,7 +1273,7 @@ __global__ void __launch_bounds__(kIndexThreads) lm_write_back(const LMState* __
                        s_cells, s_w);
   }
 }
-// lm_compact_copy: grid (128, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
+// lm_compact_copy: grid (16, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
 __global__ void __launch_bounds__(256) lm_compact_copy(const LMState* __restrict__ stAll, const int* __restrict__ offSrc,
                                                         const int* __restrict__ offDst, const int* __restrict__ cntDst,
                                                         const short* __restrict__ liveListAll, const int* __restrict__ liveNumAll,
@@ -1445,7 +1445,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
                                                                                          lm->stackW, cap, lm->valA, lineRes, planeRes, bitsLine, bitsPlane, lm->concat, lm->staged,
                                                                                          lm->keyA + cap, lm->valA + cap, lm->keyB + cap, lm->valB + cap, lm->workCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(16, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(32, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));

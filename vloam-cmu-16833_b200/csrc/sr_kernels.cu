@@ -84,8 +84,9 @@ __device__ __forceinline__ int ring_of(float x, float y, float z, int n_scans) {
 constexpr double kPi = 3.14159265358979323846;
 
 // ---------------------------------------------------------------------------------------------
-// sr_find_ends: grid (B), block 256.
-__global__ void __launch_bounds__(256) sr_find_ends(const float* __restrict__ xyz, int stride, size_t slab_floats,
+// sr_find_ends: grid (B), block kEndsThreads.
+constexpr int kEndsThreads = 1024;
+__global__ void __launch_bounds__(kEndsThreads) sr_find_ends(const float* __restrict__ xyz, int stride, size_t slab_floats,
                                                      const int* __restrict__ n_points, float min_range,
                                                      SRHeader* __restrict__ hdr) {
   const int b = blockIdx.x;
@@ -96,13 +97,13 @@ __global__ void __launch_bounds__(256) sr_find_ends(const float* __restrict__ xy
   __shared__ int s_first, s_last;
   if (threadIdx.x == 0) { s_first = 0x7fffffff; s_last = -1; }
   __syncthreads();
-  // 2048 points per step (8 independent loads per thread): a scan can open / close with thousands of no-return points
+  // 8192 points per step (8 independent loads per thread): a scan can open / close with thousands of no-return points
   constexpr int kPer = 8;
-  for (int base = 0; base < n; base += 256 * kPer) {
+  for (int base = 0; base < n; base += kEndsThreads * kPer) {
     int first = 0x7fffffff;
 #pragma unroll
     for (int u = kPer - 1; u >= 0; --u) {
-      const int i = base + u * 256 + threadIdx.x;
+      const int i = base + u * kEndsThreads + threadIdx.x;
       if (i < n && point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2)) first = i;
     }
     if (first != 0x7fffffff) atomicMin(&s_first, first);
@@ -111,11 +112,11 @@ __global__ void __launch_bounds__(256) sr_find_ends(const float* __restrict__ xy
     __syncthreads();
     if (found) break;
   }
-  for (int top = n; top > 0; top -= 256 * kPer) {
+  for (int top = n; top > 0; top -= kEndsThreads * kPer) {
     int last = -1;
 #pragma unroll
     for (int u = kPer - 1; u >= 0; --u) {
-      const int i = top - 1 - u * 256 - (int)threadIdx.x;
+      const int i = top - 1 - u * kEndsThreads - (int)threadIdx.x;
       if (i >= 0 && point_valid(p[(size_t)i * stride], p[(size_t)i * stride + 1], p[(size_t)i * stride + 2], thres2)) last = i;
     }
     if (last >= 0) atomicMax(&s_last, last);
@@ -125,8 +126,8 @@ __global__ void __launch_bounds__(256) sr_find_ends(const float* __restrict__ xy
     if (found) break;
   }
   // zero the per-scan counters
-  for (int i = threadIdx.x; i < kMaxRings; i += 256) { h.ringCount[i] = 0; h.ringLessFlat[i] = 0; }
-  for (int i = threadIdx.x; i < kMaxRings * kSectors * 3; i += 256) h.secCount[i] = 0;
+  for (int i = threadIdx.x; i < kMaxRings; i += kEndsThreads) { h.ringCount[i] = 0; h.ringLessFlat[i] = 0; }
+  for (int i = threadIdx.x; i < kMaxRings * kSectors * 3; i += kEndsThreads) h.secCount[i] = 0;
   if (threadIdx.x == 0) {
     h.n_in = n;
     h.halfIdx = 0x7fffffff;
@@ -826,10 +827,11 @@ __global__ void __launch_bounds__(256) sr_less_flat_voxel(SRHeader* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------------
-// sr_pack: grid (kMaxRings + 1, B), block 256.
+// sr_pack: grid (kMaxRings + kPackParts, B), block 256.
 //   blockIdx.x < 64 : copy ring x's down-sampled less-flat points to their packed position
-//   blockIdx.x == 64: pack sharp / less-sharp / flat clouds (ring-major, sector-major, pick order) and
-//                     publish the counts and ring offsets of the packed clouds.
+//   blockIdx.x >= 64: pack sharp / less-sharp / flat clouds (ring-major, sector-major, pick order), one slice of the
+//                     (ring, sector, pick) slots per block; the first of them publishes the counts and ring offsets.
+constexpr int kPackParts = 8;
 __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
                                                 const int* __restrict__ featIdx, const float4* __restrict__ lessFlatStage,
                                                 float4* __restrict__ sharp, int* __restrict__ sharpIdx,
@@ -855,20 +857,37 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
     for (int k = threadIdx.x; k < n; k += 256) dst[k] = src[k];
     return;
   }
-  __shared__ int pre[3][kMaxRings * kSectors + 1];
+  // blocks 64 .. 64 + kPackParts - 1: the picked features, kPackParts slices of the (ring, sector, pick) slots.  Every block
+  // forms the exclusive prefix of the per-sector counts itself (coalesced load + one warp scan per feature kind).
+  constexpr int kSec = kMaxRings * kSectors;        // 384
+  __shared__ int pre[3][kSec + 1];
+  __shared__ int cnt[kSec * 3];
+  const int part = blockIdx.x - kMaxRings;
   const float4* c = cloud + (size_t)b * cap;
-  if (threadIdx.x < 3) {
-    int acc = 0;
-    for (int s = 0; s < kMaxRings * kSectors; ++s) { pre[threadIdx.x][s] = acc; acc += h.secCount[s * 3 + threadIdx.x]; }
-    pre[threadIdx.x][kMaxRings * kSectors] = acc;
+  for (int i = threadIdx.x; i < kSec * 3; i += 256) cnt[i] = h.secCount[i];
+  __syncthreads();
+  if (threadIdx.x < 96) {
+    const int kind = threadIdx.x >> 5, l = threadIdx.x & 31;
+    constexpr int per = kSec / 32;                  // 12 sectors per lane
+    int sum = 0;
+#pragma unroll
+    for (int q = 0; q < per; ++q) sum += cnt[(l * per + q) * 3 + kind];
+    int sc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
+    int run = sc - sum;
+#pragma unroll
+    for (int q = 0; q < per; ++q) { pre[kind][l * per + q] = run; run += cnt[(l * per + q) * 3 + kind]; }
+    if (l == 31) pre[kind][kSec] = run;
   }
   __syncthreads();
   const int* fi = featIdx + (size_t)b * kMaxRings * kSectors * 26;
-  for (int w = threadIdx.x; w < kMaxRings * kSectors * 26; w += 256) {
+  constexpr int kSlots = kSec * 26, kSlice = (kSlots + kPackParts - 1) / kPackParts;
+  for (int w = part * kSlice + threadIdx.x; w < min((part + 1) * kSlice, kSlots); w += 256) {
     const int s = w / 26, k = w % 26;
     int kind, kk;
     if (k < 2) { kind = 0; kk = k; } else if (k < 22) { kind = 1; kk = k - 2; } else { kind = 2; kk = k - 22; }
-    if (kk < h.secCount[s * 3 + kind]) {
+    if (kk < cnt[s * 3 + kind]) {
       const int ind = fi[w];
       const int dst = pre[kind][s] + kk;
       const float4 p = c[ind];
@@ -877,7 +896,7 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
       else { flat[(size_t)b * kMaxFlat + dst] = p; flatIdx[(size_t)b * kMaxFlat + dst] = ind; }
     }
   }
-  if (threadIdx.x <= kMaxRings) {
+  if (part == 0 && threadIdx.x <= kMaxRings) {
     const int r = threadIdx.x;
     h.ringStartLessSharp[r] = pre[1][r * kSectors];  // r == 64 -> total
     int off = 0;
@@ -906,7 +925,7 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
     cudaFuncSetAttribute(sr_less_flat_voxel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<4096>));
     attr_set = true;
   }
-  VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, 256, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
+  VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, kEndsThreads, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
   VB_LAUNCH(prof, K_SR_CLASSIFY, st, sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));
@@ -922,7 +941,7 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
     VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<4096><<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
     VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<4096><<<dim3(4, B), 256, sizeof(VoxelSmem<4096>), st>>>(hdr, cloud, cap, label, lessFlatStage));
   }
-  VB_LAUNCH(prof, K_SR_PACK, st, sr_pack<<<dim3(kMaxRings + 1, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx,
+  VB_LAUNCH(prof, K_SR_PACK, st, sr_pack<<<dim3(kMaxRings + kPackParts, B), 256, 0, st>>>(hdr, cloud, cap, featIdx, lessFlatStage, sharp, sharpIdx,
                                                                               lessSharp, lessSharpIdx, flat, flatIdx, lessFlat));
 }
 
