@@ -1422,7 +1422,9 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
       static const int forced = [] { const char* e = getenv("VLOAM_LM_CLUSTER"); return e ? atoi(e) : 0; }();
-      int cs = forced > 0 ? forced : (B <= 37 ? 4 : B <= 74 ? 2 : 1);
+      // At 64 streams per launch with three launches in flight the GPU is saturated and a single CTA per stream wins
+      // (37.2 k scans/s vs 36.2 k with 2 and 34.6 k with 4 CTAs): clusters only for small batches, where latency counts.
+      int cs = forced > 0 ? forced : (B <= 20 ? 4 : B <= 40 ? 2 : 1);
       cs = cs >= 8 ? kLmClusterMax : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(cs, B); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = st;
