@@ -483,74 +483,139 @@ __global__ void __launch_bounds__(256) lm_snapshot_submap(const LMState* __restr
 
 // ---------------------------------------------------------------------------------------------------------------
 // Small dense kernels of the association (same algorithms as oracle/small_linalg.hpp).
-__device__ void sym_eig3_dev(const double A[9], double evals[3], double evecs[3][3]) {
+// Both are written with compile-time indices only (unrolled loops, conditional swaps instead of index arrays) so that
+// the small matrices live in registers: lm_fit runs them once per thread.
+__device__ __forceinline__ void sym_eig3_dev(const double A[9], double evals[3], double evecs[3][3]) {
   double a[3][3] = {{A[0], A[1], A[2]}, {A[3], A[4], A[5]}, {A[6], A[7], A[8]}};
   double v[3][3] = {{1, 0, 0}, {0, 1, 0}, {0, 0, 1}};
   for (int sweep = 0; sweep < 64; ++sweep) {
     const double off = a[0][1] * a[0][1] + a[0][2] * a[0][2] + a[1][2] * a[1][2];
     const double diag = a[0][0] * a[0][0] + a[1][1] * a[1][1] + a[2][2] * a[2][2];
     if (off <= 1e-300 || off <= 1e-32 * diag) break;
+#pragma unroll
     for (int p = 0; p < 2; ++p)
+#pragma unroll
       for (int q = p + 1; q < 3; ++q) {
         if (a[p][q] == 0.0) continue;
         const double theta = (a[q][q] - a[p][p]) / (2.0 * a[p][q]);
         const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
         const double c = 1.0 / sqrt(t * t + 1.0), s = t * c;
+#pragma unroll
         for (int k = 0; k < 3; ++k) { const double akp = a[k][p], akq = a[k][q]; a[k][p] = c * akp - s * akq; a[k][q] = s * akp + c * akq; }
+#pragma unroll
         for (int k = 0; k < 3; ++k) { const double apk = a[p][k], aqk = a[q][k]; a[p][k] = c * apk - s * aqk; a[q][k] = s * apk + c * aqk; }
+#pragma unroll
         for (int k = 0; k < 3; ++k) { const double vkp = v[k][p], vkq = v[k][q]; v[k][p] = c * vkp - s * vkq; v[k][q] = s * vkp + c * vkq; }
       }
   }
-  int order[3] = {0, 1, 2};
-  for (int i = 0; i < 2; ++i) for (int j = 0; j < 2 - i; ++j) if (a[order[j + 1]][order[j + 1]] < a[order[j]][order[j]]) { const int t = order[j]; order[j] = order[j + 1]; order[j + 1] = t; }
+  // ascending eigenvalues: the bubble sort of oracle/small_linalg.hpp on (value, column) pairs instead of an index array
+  double e[3] = {a[0][0], a[1][1], a[2][2]};
+  double col[3][3];   // col[k][r] = v[r][k]
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) col[k][r] = v[r][k];
+  auto cswap = [&](int i, int j) {   // compile-time i, j after inlining
+    if (e[j] < e[i]) {
+      const double te = e[i]; e[i] = e[j]; e[j] = te;
+#pragma unroll
+      for (int r = 0; r < 3; ++r) { const double tc = col[i][r]; col[i][r] = col[j][r]; col[j][r] = tc; }
+    }
+  };
+  cswap(0, 1); cswap(1, 2); cswap(0, 1);
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
-    evals[k] = a[order[k]][order[k]];
+    evals[k] = e[k];
     double n = 0.0;
-    for (int r = 0; r < 3; ++r) n += v[r][order[k]] * v[r][order[k]];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) n += col[k][r] * col[k][r];
     n = sqrt(n);
-    for (int r = 0; r < 3; ++r) evecs[k][r] = v[r][order[k]] / n;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) evecs[k][r] = col[k][r] / n;
   }
 }
-__device__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5], double x[3]) {
+__device__ __forceinline__ void colpiv_qr_solve_5x3_dev(const double Ain[15], const double bin[5], double x[3]) {
   constexpr int M = 5;
   double A[M][3], b[M];
-  for (int i = 0; i < M; ++i) { b[i] = bin[i]; for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c]; }
+#pragma unroll
+  for (int i = 0; i < M; ++i) {
+    b[i] = bin[i];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) A[i][c] = Ain[i * 3 + c];
+  }
   int perm[3] = {0, 1, 2};
   double maxnorm2 = 0.0;
-  for (int c = 0; c < 3; ++c) { double s = 0; for (int i = 0; i < M; ++i) s += A[i][c] * A[i][c]; maxnorm2 = fmax(maxnorm2, s); }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < M; ++i) s += A[i][c] * A[i][c];
+    maxnorm2 = fmax(maxnorm2, s);
+  }
   const double eps = 2.220446049250313e-16;
   const double thresh = maxnorm2 * (eps / M) * (eps / M);
   int rank = 0;
+  bool active = true;
+#pragma unroll
   for (int k = 0; k < 3; ++k) {
+    if (!active) continue;
     int best = k; double bestn = -1.0;
-    for (int c = k; c < 3; ++c) { double s = 0; for (int i = k; i < M; ++i) s += A[i][c] * A[i][c]; if (s > bestn) { bestn = s; best = c; } }
-    if (bestn <= thresh) break;
-    if (best != k) { for (int i = 0; i < M; ++i) { const double t = A[i][k]; A[i][k] = A[i][best]; A[i][best] = t; } const int t = perm[k]; perm[k] = perm[best]; perm[best] = t; }
+#pragma unroll
+    for (int c = k; c < 3; ++c) {
+      double s = 0;
+#pragma unroll
+      for (int i = k; i < M; ++i) s += A[i][c] * A[i][c];
+      if (s > bestn) { bestn = s; best = c; }
+    }
+    if (bestn <= thresh) { active = false; continue; }
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c)
+      if (best == c) {   // swap columns k and c (compile-time indices)
+#pragma unroll
+        for (int i = 0; i < M; ++i) { const double t = A[i][k]; A[i][k] = A[i][c]; A[i][c] = t; }
+        const int t = perm[k]; perm[k] = perm[c]; perm[c] = t;
+      }
     const double nrm = sqrt(bestn);
     const double alpha = A[k][k] > 0 ? -nrm : nrm;
     double v[M];
-    for (int i = k; i < M; ++i) v[i] = A[i][k];
+#pragma unroll
+    for (int i = 0; i < M; ++i) v[i] = i >= k ? A[i][k] : 0.0;
     v[k] -= alpha;
-    double vn = 0; for (int i = k; i < M; ++i) vn += v[i] * v[i];
+    double vn = 0;
+#pragma unroll
+    for (int i = k; i < M; ++i) vn += v[i] * v[i];
     if (vn > 0) {
+#pragma unroll
       for (int c = k; c < 3; ++c) {
-        double s = 0; for (int i = k; i < M; ++i) s += v[i] * A[i][c];
+        double s = 0;
+#pragma unroll
+        for (int i = k; i < M; ++i) s += v[i] * A[i][c];
         s = 2.0 * s / vn;
+#pragma unroll
         for (int i = k; i < M; ++i) A[i][c] -= s * v[i];
       }
-      double s = 0; for (int i = k; i < M; ++i) s += v[i] * b[i];
+      double s = 0;
+#pragma unroll
+      for (int i = k; i < M; ++i) s += v[i] * b[i];
       s = 2.0 * s / vn;
+#pragma unroll
       for (int i = k; i < M; ++i) b[i] -= s * v[i];
     }
     ++rank;
   }
   double y[3] = {0, 0, 0};
-  for (int k = rank - 1; k >= 0; --k) {
+#pragma unroll
+  for (int k = 2; k >= 0; --k) {
+    if (k >= rank) continue;
     double s = b[k];
-    for (int c = k + 1; c < rank; ++c) s -= A[k][c] * y[c];
+#pragma unroll
+    for (int c = k + 1; c < 3; ++c) if (c < rank) s -= A[k][c] * y[c];
     y[k] = s / A[k][k];
   }
-  for (int k = 0; k < 3; ++k) x[perm[k]] = y[k];
+#pragma unroll
+  for (int k = 0; k < 3; ++k)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) if (perm[k] == j) x[j] = y[k];
 }
 
 // Association (:472-581) in two kernels, so that each runs at its own register budget / occupancy:

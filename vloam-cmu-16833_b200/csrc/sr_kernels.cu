@@ -596,18 +596,8 @@ __device__ int voxel_radix_sort(VoxelSmem<CAP>& S, int m, int bits) {
     unsigned short* pout = S.pos[cur ^ 1];
     for (int d = l; d < 256; d += 32) S.off[w][d] = 0;
     __syncwarp();
-    // (A) per-warp digit totals
-    for (int base = w0; base < w1; base += 32) {
-      const int k = base + l;
-      const bool act = k < w1;
-      const unsigned amask = __ballot_sync(0xffffffffu, act);
-      if (act) {
-        const int d = (kin[k] >> shift) & 255;
-        const unsigned peers = __match_any_sync(amask, d);
-        if (l == __ffs(peers) - 1) S.off[w][d] += __popc(peers);
-      }
-      __syncwarp();
-    }
+    // (A) per-warp digit totals (order is irrelevant here: shared-memory atomics)
+    for (int k = w0 + l; k < w1; k += 32) atomicAdd(&S.off[w][(kin[k] >> shift) & 255], 1);
     __syncthreads();
     // (B) exclusive scan in (digit, warp) order: thread t owns digit t
     {
