@@ -1,0 +1,60 @@
+"""The C++ host mirror of the reference's class API (adapter/host_api.hpp + wire_formats.hpp) on the GPU: the frame loop of
+vloam_main_node.cpp:125-180 written in C++ over KITTI .bin scans must give the poses the Python mirror gets from the same
+library on the same scans (the kernels are deterministic: bit-identical), and the depth PointCloudUtil::queryDepth returns."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "vloam-cmu-16833_b200", "lib", "host_api_check")
+
+
+def test_cpp_host_mirror_matches_python_mirror(synth, tmp_path):
+    import vloam_b200 as V
+    if not os.path.exists(BIN):
+        pytest.skip("host_api_check not built (run __graft_entry__.build())")
+    s = synth.ScanStream(61, n_cols=512)
+    scans, paths = [], []
+    for k in range(3):
+        sc = s.scan(k)
+        sc = sc[np.isfinite(sc).all(1)]                       # KITTI .bin files hold returns only
+        scans.append(sc)
+        p = tmp_path / f"{k:06d}.bin"
+        np.c_[sc, np.zeros(len(sc), np.float32)].astype(np.float32).tofile(str(p))
+        paths.append(str(p))
+    out = subprocess.run([BIN, "run"] + paths, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    frames = [l.split() for l in out.stdout.splitlines() if l.startswith("frame ")]
+    poses = [l.split()[1:] for l in out.stdout.splitlines() if l.startswith("pose ")]
+    assert len(frames) == 3 and len(poses) == 3
+
+    lom = V.LidarOdometryMapping(batch=1, max_points=1 << 17, map_capacity_points=1 << 17)
+    vo = V.VisualOdometry(batch=1, max_points=1 << 17, max_matches=256)
+    vo.setUpPointCloud(*synth.kitti_like_calibration())
+    for k, sc in enumerate(scans):
+        cloud = np.c_[sc, np.zeros(len(sc), np.float32)].astype(np.float32)
+        vo.reset(); lom.reset()
+        vo.processPointCloud(cloud)
+        z = float(vo.queryDepth(np.array([[620.0, 250.0]], np.float32))[0])
+        lom.scanRegistrationIO(cloud)
+        lo = lom.laserOdometryIO()
+        mo = lom.laserMappingIO()
+        f = frames[k]
+        vals = {f[i]: i for i in range(len(f))}
+        assert int(f[vals["n"] + 1]) == len(sc)
+        assert float(f[vals["depth"] + 1]) == pytest.approx(z, rel=1e-7)
+        got_lo_t = np.array([float(v) for v in f[vals["lo_t"] + 1: vals["lo_t"] + 4]])
+        got_lo_q = np.array([float(v) for v in f[vals["lo_q"] + 1: vals["lo_q"] + 5]])
+        got_mo_t = np.array([float(v) for v in f[vals["mo_t"] + 1: vals["mo_t"] + 4]])
+        assert np.array_equal(got_lo_t, lo["t_w_curr"][0]) and np.array_equal(got_lo_q, lo["q_w_curr"][0])
+        assert np.array_equal(got_mo_t, mo["t_w_curr"][0])
+        assert [int(f[vals["corr"] + 1]), int(f[vals["corr"] + 2])] == [int(lo["corner_correspondence"][0]), int(lo["plane_correspondence"][0])]
+        assert int(f[vals["less_flat"] + 1]) == lom.cloud(V.CLOUD_LESS_FLAT).shape[0]
+        assert len(poses[k]) == 12
+    np.testing.assert_allclose(np.array(poses[0], float).reshape(3, 4), np.eye(4)[:3], atol=1e-6)   # first dumped frame = origin
+    assert abs(float(poses[2][3])) + abs(float(poses[2][7])) + abs(float(poses[2][11])) > 0.5          # the sensor moved
+    lom.close(); vo.close()

@@ -85,4 +85,62 @@ class LidarOdometryMapping {
   vloam_lidar_params params_{};
 };
 
+// ROS-free mirror of vloam::VisualOdometry's depth-association / solve half
+// (reference include/visual_odometry/visual_odometry.h:40-121; processImage stays with OpenCV on the caller's side and
+// hands over the matched keypoint pixels).  One instance per sensor; shares the context of a LidarOdometryMapping when
+// given one, so that the scan uploaded by scanRegistrationIO is also VO's cloud (vloam_main_node.cpp:148-166).
+class VisualOdometry {
+ public:
+  explicit VisualOdometry(int max_points = 1 << 18, int max_matches = 2048, int device = 0) : max_matches_(max_matches) {
+    if (vloam_ctx_create(device, &ctx_) != VLOAM_OK) throw std::runtime_error("vloam_ctx_create failed (no CUDA device?)");
+    check(vloam_vo_create(ctx_, 1, max_points, max_matches, &h_));
+  }
+  ~VisualOdometry() {
+    if (h_) vloam_vo_destroy(h_);
+    if (ctx_) vloam_ctx_destroy(ctx_);
+  }
+  VisualOdometry(const VisualOdometry&) = delete;
+  VisualOdometry& operator=(const VisualOdometry&) = delete;
+
+  // visual_odometry.cpp:86-90
+  void reset() { check(vloam_vo_reset(h_)); ++count; }
+  // visual_odometry.cpp:132-155: row-major cam_T_velo (4x4), rect0_T_cam (4x4; the ROS path leaves (3,3) = 0), P_rect0 (3x4)
+  void setUpPointCloud(const float cam_T_velo[16], const float rect0_T_cam[16], const float P_rect0[12]) {
+    check(vloam_vo_set_calibration(h_, cam_T_velo, rect0_T_cam, P_rect0));
+  }
+  // visual_odometry.cpp:157-186: `points` = n records of `stride_floats` floats starting with x, y, z
+  void processPointCloud(const float* points, int n, int stride_floats = 4) {
+    check(vloam_vo_process_cloud(h_, points, &n, stride_floats, (size_t)n));
+  }
+  // visual_odometry.cpp:254-450.  prev_uv / curr_uv: m matched keypoint pixels (cv::KeyPoint::pt of the previous / current
+  // image), init = (angle-axis, t) of cam0_curr_LOT_cam0_prev or nullptr (reset_VO_to_identity).  Fills angles_0to1, t_0to1.
+  void solveNlsAll(const float* prev_uv, const float* curr_uv, int m, const double* init = nullptr, int remove_VO_outlier = 100,
+                   int max_iterations = 100) {
+    if (m > max_matches_) m = max_matches_;
+    double out[8];
+    check(vloam_vo_solve(h_, prev_uv, curr_uv, &m, init, remove_VO_outlier, max_iterations, out));
+    for (int i = 0; i < 3; ++i) { angles_0to1[i] = out[i]; t_0to1[i] = out[3 + i]; }
+    counter32 = (int)out[6]; counter22 = (int)out[7];
+  }
+  // PointCloudUtil::queryDepth (point_cloud_util.cpp:302-407); slot 0 = current frame, 1 = previous
+  float queryDepth(float x, float y, int slot = 0) {
+    const float xy[2] = {x, y};
+    float z = -1.f;
+    check(vloam_vo_query_depth(h_, 0, slot, xy, 1, &z));
+    return z;
+  }
+
+  int count = -1;
+  double angles_0to1[3] = {0, 0, 0}, t_0to1[3] = {0, 0, 0};   // cam0_curr_T_cam0_last as angle-axis + translation
+  int counter32 = 0, counter22 = 0;
+
+ private:
+  void check(int rc) {
+    if (rc != VLOAM_OK) throw std::runtime_error(std::string("vloam_b200: ") + vloam_last_error(ctx_));
+  }
+  vloam_ctx* ctx_ = nullptr;
+  vloam_vo* h_ = nullptr;
+  int max_matches_;
+};
+
 }  // namespace vloam_b200

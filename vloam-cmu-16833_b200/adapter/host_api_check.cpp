@@ -1,17 +1,53 @@
-// Compile/link check of the ROS-free host mirror against libvloam_b200.so (built by __graft_entry__.build()).
+// The ROS-free C++ host mirror (host_api.hpp, wire_formats.hpp) against libvloam_b200.so.
+//   host_api_check                         compile / link / load check (built and run by __graft_entry__.build(); on a CPU-only
+//                                          box the library refuses to create a context: there is no fallback)
+//   host_api_check run A.bin B.bin ...     the frame loop of vloam_main_node.cpp:125-180 over KITTI .bin scans, in C++:
+//                                          LidarOdometryMapping::{reset, scanRegistrationIO, laserOdometryIO, laserMappingIO} and
+//                                          VisualOdometry::{reset, processPointCloud, queryDepth}; prints one line per frame
+//                                          (tests/test_gpu_host_api.py compares them with the Python mirror's results)
 #include <cstdio>
+#include <cstring>
 
 #include "host_api.hpp"
 #include "lidar_odometry_mapping_b200.h"
+#include "visual_odometry_b200.h"
+#include "wire_formats.hpp"
 
-int main() {
+int main(int argc, char** argv) {
   try {
     vloam_b200::LidarOdometryMapping lom(0);
-    lom.params().max_points = 4096;
+    lom.params().max_points = 1 << 17;
+    lom.params().map_capacity_points = 1 << 17;
     lom.init();
+    vloam_b200::VisualOdometry vo(1 << 17, 256, 0);
     std::printf("context created\n");
+    if (argc < 3 || std::strcmp(argv[1], "run") != 0) return 0;
+    // KITTI-like calibration (vloam_b200/synth.py: kitti_like_calibration)
+    const float cam_T_velo[16] = {0, -1, 0, 0, 0, 0, -1, -0.08f, 1, 0, 0, -0.27f, 0, 0, 0, 1};
+    const float rect0_T_cam[16] = {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1};
+    const float P_rect0[12] = {718.856f, 0, 607.1928f, 0, 0, 718.856f, 185.2157f, 0, 0, 0, 1, 0};
+    vo.setUpPointCloud(cam_T_velo, rect0_T_cam, P_rect0);
+    vloam_b200::Cam0StartFrameWriter dump(vloam_b200::Mat4::identity());
+    for (int k = 2; k < argc; ++k) {
+      std::vector<float> xyzi;
+      const int n = vloam_b200::load_kitti_bin(argv[k], xyzi);
+      if (n <= 0) { std::printf("cannot read %s\n", argv[k]); return 3; }
+      vo.reset();
+      lom.reset();
+      vo.processPointCloud(xyzi.data(), n, 4);
+      const float z = vo.queryDepth(620.f, 250.f);
+      lom.scanRegistrationIO(xyzi.data(), n, 4);
+      lom.laserOdometryIO();
+      lom.laserMappingIO();
+      std::printf("frame %d n %d depth %.9g lo_t %.17g %.17g %.17g lo_q %.17g %.17g %.17g %.17g mo_t %.17g %.17g %.17g corr %d %d less_flat %zu\n", k - 2,
+                  n, (double)z, lom.odom.t[0], lom.odom.t[1], lom.odom.t[2], lom.odom.q[0], lom.odom.q[1], lom.odom.q[2], lom.odom.q[3],
+                  lom.mapped.t[0], lom.mapped.t[1], lom.mapped.t[2], lom.corner_correspondence, lom.plane_correspondence,
+                  lom.cloud(VLOAM_CLOUD_LESS_FLAT).size() / 4);
+      std::fputs(("pose " + dump.write(nullptr, k - 2, vloam_b200::Mat4::from_qt(lom.mapped.q.data(), lom.mapped.t.data()))).c_str(), stdout);
+    }
   } catch (const std::exception& e) {
     std::printf("no device: %s\n", e.what());  // expected on a CPU-only box: the library refuses to run, no fallback
+    return argc >= 3 ? 4 : 0;
   }
   return 0;
 }
