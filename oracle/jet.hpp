@@ -34,7 +34,8 @@ template <int N> inline Jet<N> operator*(const Jet<N>& f, const Jet<N>& g) {
 // ceres::Jet division: (f/g)' = (f' - (f/g) g') / g
 template <int N> inline Jet<N> operator/(const Jet<N>& f, const Jet<N>& g) {
   Jet<N> h; const double gi = 1.0 / g.a; const double fg = f.a * gi; h.a = fg;
-  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi; return h;
+  for (int i = 0; i < N; ++i) h.v[i] = (f.v[i] - fg * g.v[i]) * gi;
+  return h;
 }
 template <int N> inline Jet<N> operator*(double s, const Jet<N>& f) { return Jet<N>(s) * f; }
 template <int N> inline Jet<N> operator*(const Jet<N>& f, double s) { return f * Jet<N>(s); }
@@ -48,19 +49,23 @@ template <int N> inline bool operator<=(const Jet<N>& f, const Jet<N>& g) { retu
 
 template <int N> inline Jet<N> jsqrt(const Jet<N>& f) {
   Jet<N> h; h.a = std::sqrt(f.a); const double d = 1.0 / (2.0 * h.a);
-  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * d; return h;
+  for (int i = 0; i < N; ++i) h.v[i] = f.v[i] * d;
+  return h;
 }
 template <int N> inline Jet<N> jsin(const Jet<N>& f) {
   Jet<N> h; h.a = std::sin(f.a); const double c = std::cos(f.a);
-  for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i]; return h;
+  for (int i = 0; i < N; ++i) h.v[i] = c * f.v[i];
+  return h;
 }
 template <int N> inline Jet<N> jcos(const Jet<N>& f) {
   Jet<N> h; h.a = std::cos(f.a); const double s = -std::sin(f.a);
-  for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i]; return h;
+  for (int i = 0; i < N; ++i) h.v[i] = s * f.v[i];
+  return h;
 }
 template <int N> inline Jet<N> jacos(const Jet<N>& f) {
   Jet<N> h; h.a = std::acos(f.a); const double d = -1.0 / std::sqrt(1.0 - f.a * f.a);
-  for (int i = 0; i < N; ++i) h.v[i] = d * f.v[i]; return h;
+  for (int i = 0; i < N; ++i) h.v[i] = d * f.v[i];
+  return h;
 }
 template <int N> inline Jet<N> jabs(const Jet<N>& f) { return f.a < 0.0 ? -f : f; }
 
