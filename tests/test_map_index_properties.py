@@ -1,0 +1,77 @@
+"""CPU check of the exactness argument behind the per-cube column index of laserMapping (lm_knn):
+every map point within 1 m of a query (float32 squared distance < 1, the reference's acceptance test at
+laser_mapping.cpp:479 / :547) lies in the 3 x 3 block of 1.001 m columns around the query in one of the cubes the query's
++-1.001 m box touches.  The index arithmetic is restated here in numpy with the kernel's float32 / double expressions
+(cube_coord, cube_min_coord, cube_cell[_clamped] in lm_kernels.cu); the candidate set it yields is compared with a brute-force
+scan.  Also covers the z-binned refinement (4 m bins inside a column) planned as the next step."""
+import numpy as np
+import pytest
+
+F = np.float32
+CELL_INV = F(1.0) / F(1.001)
+ZBIN_INV = F(1.0) / F(4.0)
+
+
+def cube_coord(v, cen):                      # laser_mapping.cpp:207-216 / 643-652, double arithmetic
+    v = np.asarray(v, np.float64)
+    c = ((v + 25.0) / 50.0).astype(np.int64) + cen          # truncation toward zero like the C cast
+    return np.where(v + 25.0 < 0, c - 1, c)
+
+
+def cube_min(idx, cen):
+    return F((idx - cen) * 50.0 - 25.0)
+
+
+def cell(v, mn):
+    return np.floor((np.asarray(v, F) - F(mn)) * CELL_INV).astype(np.int64)
+
+
+def zbin(z, mnz):
+    return np.clip(np.floor((np.asarray(z, F) - F(mnz)) * ZBIN_INV).astype(np.int64), 0, 12)
+
+
+def sqdist_f(a, b):                          # ((dx*dx + dy*dy) + dz*dz) in float32
+    d = (a.astype(F) - b.astype(F)).astype(F)
+    return ((d[..., 0] * d[..., 0]).astype(F) + (d[..., 1] * d[..., 1]).astype(F)).astype(F) + (d[..., 2] * d[..., 2]).astype(F)
+
+
+@pytest.mark.parametrize("seed,use_zbins", [(0, False), (1, False), (2, True), (3, True)])
+def test_column_block_contains_every_point_within_one_metre(seed, use_zbins):
+    rng = np.random.default_rng(seed)
+    cen = (10, 10, 5)
+    # a dense cloud around a corner where eight cubes meet, so that many queries sit at cube borders
+    corner = np.array([25.0, 25.0, 25.0])
+    pts = (corner + rng.uniform(-6, 6, (60000, 3))).astype(F)
+    # file every point under its cube and its column (and z-bin)
+    ci, cj, ck = (cube_coord(pts[:, a], cen[a]) for a in range(3))
+    mnx = np.array([cube_min(i, cen[0]) for i in ci]); mny = np.array([cube_min(j, cen[1]) for j in cj]); mnz = np.array([cube_min(k, cen[2]) for k in ck])
+    px = np.clip(np.floor((pts[:, 0] - mnx) * CELL_INV).astype(np.int64), 0, 49)
+    py = np.clip(np.floor((pts[:, 1] - mny) * CELL_INV).astype(np.int64), 0, 49)
+    pz = np.clip(np.floor((pts[:, 2] - mnz) * ZBIN_INV).astype(np.int64), 0, 12)
+    index = {}
+    for n, key in enumerate(zip(ci.tolist(), cj.tolist(), ck.tolist(), px.tolist(), py.tolist(), pz.tolist() if use_zbins else [0] * len(pts))):
+        index.setdefault(key, []).append(n)
+    queries = (corner + rng.uniform(-5, 5, (400, 3))).astype(F)
+    queries[:40] = (corner + rng.uniform(-1.2, 1.2, (40, 3))).astype(F)            # right at the corner
+    queries[40:60, 0] = F(25.0)                                                    # exactly on a cube face
+    checked = 0
+    for q in queries:
+        cand = set()
+        r = {}
+        for a, c in enumerate(cen):
+            r[a] = range(int(cube_coord(np.float64(q[a]) - 1.001, c)), int(cube_coord(np.float64(q[a]) + 1.001, c)) + 1)
+        for k in r[2]:
+            for j in r[1]:
+                for i in r[0]:
+                    qx = int(cell(q[0], cube_min(i, cen[0]))); qy = int(cell(q[1], cube_min(j, cen[1])))
+                    mz = cube_min(k, cen[2])
+                    zs = range(int(zbin(q[2] - F(1.001), mz)), int(zbin(q[2] + F(1.001), mz)) + 1) if use_zbins else [0]
+                    for y in range(max(qy - 1, 0), min(qy + 1, 49) + 1):
+                        for x in range(max(qx - 1, 0), min(qx + 1, 49) + 1):
+                            for z in zs:
+                                cand.update(index.get((i, j, k, x, y, z), ()))
+        d = sqdist_f(pts, q[None, :])
+        near = set(np.nonzero(d < F(1.0))[0].tolist())
+        assert near <= cand, (q, len(near - cand))
+        checked += len(near)
+    assert checked > 20000
