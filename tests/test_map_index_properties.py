@@ -75,3 +75,36 @@ def test_column_block_contains_every_point_within_one_metre(seed, use_zbins):
         assert near <= cand, (q, len(near - cand))
         checked += len(near)
     assert checked > 20000
+
+
+def test_lo_grid_safe_radius_bounds_every_unvisited_point():
+    """laserOdometry's column grid (lo_kernels.cu: cell_coord, grid_safe_radius): after the (2k+1)^2 block of columns around
+    the query has been visited, every point filed under another column is farther than the safe radius R_k, in the float32
+    distance the search compares (so stopping at best <= R_k^2 is exact, including the index tie-break)."""
+    rng = np.random.default_rng(7)
+    pts = np.c_[rng.uniform(-60, 60, (40000, 2)), rng.uniform(-3, 8, 40000)].astype(F)
+    minx, miny = F(pts[:, 0].min()), F(pts[:, 1].min())
+    c = F(1.0)
+    inv_c = F(1.0) / c
+    nx = int(np.floor((pts[:, 0].max() - minx) / c)) + 1
+    ny = int(np.floor((pts[:, 1].max() - miny) / c)) + 1
+    ix = np.clip(np.floor((pts[:, 0] - minx) * inv_c).astype(np.int64), 0, nx - 1)
+    iy = np.clip(np.floor((pts[:, 1] - miny) * inv_c).astype(np.int64), 0, ny - 1)
+    queries = np.c_[rng.uniform(-65, 65, (300, 2)), rng.uniform(-3, 8, 300)].astype(F)       # some outside the grid
+    queries[:50, :2] = (np.round(queries[:50, :2]) - (minx % F(1.0))).astype(F)                # near column borders
+    worst = np.inf
+    for q in queries:
+        qx = int(np.floor((q[0] - minx) * inv_c)); qy = int(np.floor((q[1] - miny) * inv_c))
+        d = sqdist_f(pts, q[None, :])
+        for k in range(1, 6):
+            xl = F(q[0] - (minx + F(qx - k) * c)); xr = F((minx + F(qx + k + 1) * c) - q[0])
+            yl = F(q[1] - (miny + F(qy - k) * c)); yr = F((miny + F(qy + k + 1) * c) - q[1])
+            R = F(min(xl, xr, yl, yr) * (F(1.0) - F(1e-5)) - F(1e-4))
+            if R <= 0:
+                continue
+            outside = (np.abs(ix - qx) > k) | (np.abs(iy - qy) > k)
+            if outside.any():
+                m = d[outside].min()
+                assert m > F(R * R), (q, k, m, R)
+                worst = min(worst, float(m) - float(R * R))
+    assert np.isfinite(worst)
