@@ -108,3 +108,50 @@ def test_lo_grid_safe_radius_bounds_every_unvisited_point():
                 assert m > F(R * R), (q, k, m, R)
                 worst = min(worst, float(m) - float(R * R))
     assert np.isfinite(worst)
+
+
+def test_lo_ring_window_interval_equals_the_literal_walks():
+    """lo_associate's ring-window pass (lo_kernels.cu, "phase 2"): the reference walks the ring-major target cloud away from
+    the closest point, forwards until the first point with int(intensity) > id + 2.5 and backwards until the first with
+    int(intensity) < id - 2.5 (laser_odometry.cpp:279-324 / 368-417).  With int(intensity) equal to the point's true ring R
+    or R - 1 (negative relTime), the indices the two walks visit are exactly [lo_j, hi_j) minus the closest point, with
+    lo_j / hi_j from the true ring offsets and the per-ring tables firstFull / lastLow (GridHeader)."""
+    rng = np.random.default_rng(11)
+    R = 64
+    for trial in range(30):
+        counts = rng.integers(0, 40, R)
+        counts[rng.integers(0, R, 6)] = 0                                   # some empty rings
+        ring_start = np.r_[0, np.cumsum(counts)]                            # [R + 1]
+        n = int(ring_start[-1])
+        true_ring = np.repeat(np.arange(R), counts)
+        low = (rng.random(n) < 0.3) & (true_ring > 0)                       # int(intensity) == R - 1 for these
+        rid = true_ring - low.astype(int)
+        first_full = np.full(R + 1, np.iinfo(np.int32).max, np.int64)
+        last_low = np.full(R + 1, -1, np.int64)
+        for j in range(n):
+            r = true_ring[j]
+            if rid[j] == r:
+                first_full[r] = min(first_full[r], j)
+            else:
+                last_low[r] = max(last_low[r], j)
+        rs = np.r_[ring_start, n]                                           # ringStart[64] = ringStart[65] = n
+        for closest in rng.integers(0, n, 60):
+            idc = int(rid[closest])
+            fwd = []
+            for j in range(closest + 1, n):
+                if rid[j] > idc + 2.5:
+                    break
+                fwd.append(j)
+            bwd = []
+            for j in range(closest - 1, -1, -1):
+                if rid[j] < idc - 2.5:
+                    break
+                bwd.append(j)
+            hi_j, lo_j = n, 0
+            if idc + 3 <= R - 1:
+                hi_j = min(first_full[idc + 3], rs[min(idc + 4, R)])
+            if idc - 2 >= 0:
+                lo_j = max(last_low[idc - 2], rs[idc - 2] - 1) + 1
+            want = set(fwd) | set(bwd)
+            got = set(range(int(lo_j), int(hi_j))) - {int(closest)}
+            assert got == want, (trial, closest, idc, sorted(got ^ want)[:5])
