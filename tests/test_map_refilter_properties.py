@@ -90,3 +90,51 @@ def test_lattice_order_is_independent_of_the_bounding_box(oracle):
     yb = oracle.voxel_grid(np.concatenate([a, far]), 0.8)
     core = yb[1:-1]                        # the two far voxels sort first and last
     assert np.array_equal(core.view(np.uint32), ya.view(np.uint32))
+
+
+def _voxel_grid_by_runs(p, leaf):
+    """pcl::VoxelGrid restated over RUNS of consecutive equal voxel keys instead of points (the next step planned for
+    sr_less_flat_voxel): detect runs, order the runs by (key, first index) — a voxel's runs then sit
+    side by side in index order — and chain the float sums through them point by point."""
+    f = np.float32
+    inv = f(1.0) / f(leaf)
+    mn, mx = p[:, :3].min(0), p[:, :3].max(0)
+    minb = np.floor(mn * inv).astype(np.int64)
+    divb = np.floor(mx * inv).astype(np.int64) - minb + 1
+    ijk = (np.floor(p[:, :3] * inv) - minb.astype(f)).astype(np.int64)
+    key = ijk[:, 0] + ijk[:, 1] * divb[0] + ijk[:, 2] * divb[0] * divb[1]
+    starts = np.r_[0, np.nonzero(key[1:] != key[:-1])[0] + 1]
+    ends = np.r_[starts[1:], len(p)]
+    order = np.lexsort((starts, key[starts]))                # runs by (key, first index)
+    out = []
+    i = 0
+    while i < len(order):
+        k = key[starts[order[i]]]
+        s = np.zeros(4, f)
+        cnt = 0
+        while i < len(order) and key[starts[order[i]]] == k:
+            for t in range(starts[order[i]], ends[order[i]]):
+                s = (s + p[t]).astype(f); cnt += 1
+            i += 1
+        out.append((s / f(cnt)).astype(f))
+    return np.stack(out), len(starts)
+
+
+def test_voxel_grid_over_runs_equals_voxel_grid_over_points(oracle, synth):
+    s = synth.ScanStream(77, n_cols=1024)
+    sr = oracle.scan_registration(s.scan(1))
+    cloud, lab = sr.laserCloud, sr.label
+    rings = cloud[:, 3].astype(int)
+    runs = pts = 0
+    for r in range(0, 51, 5):
+        idx = np.nonzero(rings == r)[0]
+        if len(idx) < 20:
+            continue
+        idx = idx[5:-6]
+        idx = idx[lab[idx] <= 0]                             # the ring's less-flat candidates (scan_registration.cpp:424-430)
+        p = np.ascontiguousarray(cloud[idx]).astype(np.float32)
+        ref = oracle.voxel_grid(p, 0.2)
+        got, nr = _voxel_grid_by_runs(p, 0.2)
+        assert got.shape == ref.shape and np.array_equal(got.view(np.uint32), ref.view(np.uint32)), r
+        runs += nr; pts += len(p)
+    assert pts > 3 * runs / 2                                # runs are what make it worthwhile: > 1.5 points per run here
