@@ -1229,7 +1229,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
     dst.tab[tb + c] = src.tab[tb + c];
   }
   // (the other kind's CTA may raise st.error concurrently: one read, shared, keeps the barriers below uniform)
-  if (threadIdx.x == 0) { s_compact = 0; s_nlive = 0; st.compact[kind] = 0; s_err = st.error & 3; }
+  if (threadIdx.x == 0) { s_compact = 0; s_nlive = 0; st.compact[kind] = 0; s_err = st.error; }   // (sticky: an errored stream's map is frozen)
   __syncthreads();
   if (s_err) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }   // the map keeps its pre-insertion state
   const int wn = st.workNum[kind];
