@@ -1,6 +1,7 @@
 """CPU simulation of lo_associate's column-grid search (columns / points visited per query and pass) on a bench scan pair;
 the numbers quoted in DESIGN.md section 10 item 2.  usage: python scripts/simulate_lo_associate.py"""
-import sys; sys.path.insert(0,'/root/repo')
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from oracle import pyoracle as O
 from vloam_b200 import synth
