@@ -79,3 +79,15 @@ def test_bench_helpers():
         assert b.algorithmic_bytes(name, tot) > 0, name
     assert b.algorithmic_bytes("sr_curvature", tot) == 80 * 21                      # 16 B read + 4 + 1 written per kept point
     assert set(b.NCU_KERNELS["lm_place"]) == {"lm_place", "lm_compact_copy", "lm_write_back"}
+
+
+def test_c_ray_caster_reproduces_the_numpy_ray_caster_bit_for_bit(synth):
+    """csrc_host/synth_raycast.c restates Scene.raycast_numpy operation by operation (no FMA, no BLAS): identical bits."""
+    assert synth._raycast_lib() is not None, "lib/libsynth_raycast.so did not build"
+    for seed in (7, 1234, 31):
+        s = synth.ScanStream(seed, n_cols=256)
+        for k in (0, 5, 23):
+            R, t = s.pose(k)
+            dw = synth._mm(s.dirs, np.ascontiguousarray(R.T))
+            a, b = s.scene.raycast(t, dw), s.scene.raycast_numpy(t, dw)
+            assert np.array_equal(a.view(np.uint64), b.view(np.uint64)), (seed, k)

@@ -16,6 +16,10 @@ are dropped by the reference's own `scanID > 50` rule.
 """
 from __future__ import annotations
 
+import ctypes as _C
+import os as _os
+import subprocess as _sp
+
 import numpy as np
 
 N_RINGS = 64
@@ -47,6 +51,35 @@ def _ray_dirs(n_cols: int = N_COLS) -> np.ndarray:
     return d
 
 
+_HERE = _os.path.dirname(_os.path.abspath(__file__))
+RAYCAST_SRC = _os.path.join(_HERE, "csrc_host", "synth_raycast.c")
+RAYCAST_LIB = _os.path.join(_HERE, "lib", "libsynth_raycast.so")
+_raycast = [False, None]     # [probed, library or None]
+
+
+def build_raycast() -> str:
+    """gcc -O2 -ffp-contract=off (no FMA: the numpy code it restates has none) -> lib/libsynth_raycast.so."""
+    _os.makedirs(_os.path.dirname(RAYCAST_LIB), exist_ok=True)
+    if not _os.path.exists(RAYCAST_LIB) or _os.path.getmtime(RAYCAST_LIB) < _os.path.getmtime(RAYCAST_SRC):
+        _sp.check_call(["gcc", "-O2", "-ffp-contract=off", "-fPIC", "-shared", RAYCAST_SRC, "-o", RAYCAST_LIB, "-lm"])
+    return RAYCAST_LIB
+
+
+def _raycast_lib():
+    if not _raycast[0]:
+        _raycast[0] = True
+        if _os.environ.get("VLOAM_SYNTH_NUMPY") != "1":
+            try:
+                L = _C.CDLL(build_raycast())
+                dp = _C.POINTER(_C.c_double)
+                L.synth_raycast.restype = None
+                L.synth_raycast.argtypes = [dp, dp, _C.c_long, dp, dp, _C.c_int, dp, dp, dp, _C.c_int, _C.c_double, dp]
+                _raycast[1] = L
+            except Exception:
+                _raycast[1] = None
+    return _raycast[1]
+
+
 class Scene:
     """Seeded static world: ground plane, boxes (buildings), poles."""
 
@@ -68,7 +101,23 @@ class Scene:
         self.pole_top = GROUND_Z + rng.uniform(3.0, 8.0, n_poles)
 
     def raycast(self, origin: np.ndarray, dirs: np.ndarray) -> np.ndarray:
-        """Range along each ray (inf for no hit). dirs: (M, 3) unit, world frame."""
+        """Range along each ray (inf for no hit). dirs: (M, 3) unit, world frame.  Uses the C restatement
+        (csrc_host/synth_raycast.c, same IEEE operations in the same order: identical bits) when it is built."""
+        L = _raycast_lib()
+        if L is not None:
+            o = np.ascontiguousarray(origin, np.float64)
+            d = np.ascontiguousarray(dirs, np.float64)
+            best = np.empty(d.shape[0], np.float64)
+            dp = _C.POINTER(_C.c_double)
+            arrs = [np.ascontiguousarray(a, np.float64) for a in (self.box_min, self.box_max, self.pole_xy, self.pole_r, self.pole_top)]
+            L.synth_raycast(o.ctypes.data_as(dp), d.ctypes.data_as(dp), d.shape[0], arrs[0].ctypes.data_as(dp), arrs[1].ctypes.data_as(dp),
+                            self.box_min.shape[0], arrs[2].ctypes.data_as(dp), arrs[3].ctypes.data_as(dp), arrs[4].ctypes.data_as(dp),
+                            self.pole_xy.shape[0], GROUND_Z, best.ctypes.data_as(dp))
+            return best
+        return self.raycast_numpy(origin, dirs)
+
+    def raycast_numpy(self, origin: np.ndarray, dirs: np.ndarray) -> np.ndarray:
+        """The reference implementation of raycast (numpy); kept as the fallback and as the checker of the C version."""
         o = origin.astype(np.float64)
         d = dirs
         M = d.shape[0]
@@ -94,8 +143,8 @@ class Scene:
         a = (dxy * dxy).sum(axis=1)
         for p in range(self.pole_xy.shape[0]):
             oc = o[:2] - self.pole_xy[p]
-            bq = dxy @ oc
-            cq = oc @ oc - self.pole_r[p] ** 2
+            bq = dxy[:, 0] * oc[0] + dxy[:, 1] * oc[1]          # (no BLAS: its FMA use differs between CPUs)
+            cq = (oc[0] * oc[0] + oc[1] * oc[1]) - self.pole_r[p] * self.pole_r[p]
             disc = bq * bq - a * cq
             ok = disc > 0
             sq = np.sqrt(np.where(ok, disc, 0.0))
@@ -105,6 +154,16 @@ class Scene:
             hit = ok & (t > 0) & (z <= self.pole_top[p]) & (z >= GROUND_Z)
             best = np.where(hit & (t < best), t, best)
         return best
+
+
+def _mm(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """a @ b for (n, 3) x (3, m) with plain multiplies and adds in a fixed order.  BLAS kernels fuse multiply-adds
+    differently from CPU to CPU; the generator must give the same bits everywhere (tests/golden pins them)."""
+    return (a[:, 0:1] * b[0] + a[:, 1:2] * b[1]) + a[:, 2:3] * b[2]
+
+
+def _mv(a: np.ndarray, v: np.ndarray) -> np.ndarray:
+    return (a[:, 0] * v[0] + a[:, 1] * v[1]) + a[:, 2] * v[2]
 
 
 def _rot_z(yaw: float) -> np.ndarray:
@@ -117,7 +176,7 @@ def _rot_small(roll: float, pitch: float) -> np.ndarray:
     cp, sp = np.cos(pitch), np.sin(pitch)
     rx = np.array([[1, 0, 0], [0, cr, -sr], [0, sr, cr]], dtype=np.float64)
     ry = np.array([[cp, 0, sp], [0, 1, 0], [-sp, 0, cp]], dtype=np.float64)
-    return ry @ rx
+    return _mm(ry, rx)
 
 
 class ScanStream:
@@ -149,10 +208,10 @@ class ScanStream:
                 Rp, tp = self._poses[-1]
                 dt = 0.1
                 jr = np.random.Generator(np.random.Philox(key=[self.seed, 0x9000 + i]))
-                dR = _rot_z(self.yaw_rate * dt) @ _rot_small(jr.normal(0, 2e-3), jr.normal(0, 2e-3))
+                dR = _mm(_rot_z(self.yaw_rate * dt), _rot_small(jr.normal(0, 2e-3), jr.normal(0, 2e-3)))
                 dtv = np.array([self.v * dt, jr.normal(0, 0.01), jr.normal(0, 0.005)])
-                R = Rp @ dR
-                t = tp + Rp @ dtv
+                R = _mm(Rp, dR)
+                t = tp + _mv(Rp, dtv)
             self._poses.append((R, t))
         return self._poses[k]
 
@@ -161,12 +220,12 @@ class ScanStream:
         (the reference's q_last_curr / t_last_curr, laser_odometry.cpp:477-478)."""
         R0, t0 = self.pose(k - 1)
         R1, t1 = self.pose(k)
-        return R0.T @ R1, R0.T @ (t1 - t0)
+        return _mm(np.ascontiguousarray(R0.T), R1), _mv(np.ascontiguousarray(R0.T), t1 - t0)
 
     def scan(self, k: int) -> np.ndarray:
         """float32 (64*n_cols, 3) points in the sensor frame, ring-major; NaN = no return."""
         R, t = self.pose(k)
-        dw = self.dirs @ R.T
+        dw = _mm(self.dirs, np.ascontiguousarray(R.T))
         rng_ = self.scene.raycast(t, dw)
         noise = np.random.Generator(np.random.Philox(key=[self.seed, 0x5CA0 + k])).normal(
             0.0, self.noise_sigma, rng_.shape[0])
