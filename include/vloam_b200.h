@@ -46,7 +46,17 @@ enum {
 enum {
   VLOAM_STREAM_EMPTY = 1,          /* no point survived the NaN / minimum-range filters (the reference would crash) */
   VLOAM_STREAM_RING_OVERFLOW = 2,  /* a ring had more than 4096 points or a sector more than 1024 */
-  VLOAM_STREAM_VOXEL_OVERFLOW = 4  /* pcl::VoxelGrid's "leaf size too small" path was taken (input returned unfiltered) */
+  VLOAM_STREAM_VOXEL_OVERFLOW = 4, /* pcl::VoxelGrid's "leaf size too small" path was taken (input returned unfiltered) */
+  VLOAM_STREAM_CAPACITY = 8        /* a device-resident scan claimed more points than max_points / slab_points: the excess was ignored */
+};
+
+/* per-stream laser-mapping status bits (vloam_get_lm_status); 0 = the scan was mapped and inserted.  The reference's map
+ * grows without bound (std::vector per cube); here it lives in a pool of map_capacity_points per stream and kind. */
+enum {
+  VLOAM_LM_WORKLIST_OVERFLOW = 1,  /* one scan would rewrite more than 200 cubes: its points were not inserted */
+  VLOAM_LM_SCRATCH_OVERFLOW = 2,   /* the re-filter scratch would overflow: the scan's points were not inserted */
+  VLOAM_LM_CORNER_MAP_FULL = 4,    /* map_capacity_points exceeded: the corner map kept its previous content */
+  VLOAM_LM_SURF_MAP_FULL = 8       /* the same for the surf map */
 };
 
 /* cloud selectors for vloam_get_cloud */
@@ -92,7 +102,7 @@ typedef struct vloam_lidar_params {
   double minimum_range;            /*                       scan_registration.cpp:51 */
   double mapping_line_resolution;  /*                       laser_mapping.cpp:95 */
   double mapping_plane_resolution; /*                       laser_mapping.cpp:97 */
-  int mapping_skip_frame;          /*                       laser_odometry.cpp:53 */
+  int mapping_skip_frame;          /* >= 1                  laser_odometry.cpp:53, 618-628 */
   int detach_VO_LO;                /* 1: ignore the VO prior   laser_odometry.cpp:47,223 */
   int lo_outer_passes;             /* 2                     laser_odometry.cpp:211 */
   int lo_max_iterations;           /* 4                     laser_odometry.cpp:460 */
@@ -119,7 +129,9 @@ int vloam_lidar_reset(vloam_lidar* h);
  * point_step = 4 * stride_floats, taken without the pcl::fromROSMsg copy of vloam_main_node.cpp:148);
  * n_points[b] = valid points in slab b.  Pinned host memory makes the upload asynchronous. */
 int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points);
-/* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers). */
+/* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers).  The counts
+ * cannot be checked on the host: a count above min(max_points, slab_points) is clamped and reported per stream as
+ * VLOAM_STREAM_CAPACITY. */
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats,
                                    size_t slab_points);
 /* The device copy of the scan most recently uploaded by vloam_scan_registration ([batch][slab_points][stride] floats and
@@ -156,6 +168,9 @@ int vloam_get_lo_pose(vloam_lidar* h, double* pose_out, int* corr_out);
 int vloam_get_lo_pose_prev(vloam_lidar* h, double* pose_out, int* corr_out);
 /* Overwrite q_last_curr / t_last_curr (the motion prior the next solve starts from), motion[batch][7]. */
 int vloam_set_lo_motion(vloam_lidar* h, const double* motion);
+/* Overwrite the accumulated odometry pose q_w_curr / t_w_curr (laser_odometry.cpp:80-81), pose[batch][7] = q(xyzw) t:
+ * checkpoint / resume of a stream in the middle of a trajectory (the reference can only start at the origin). */
+int vloam_set_lo_pose(vloam_lidar* h, const double* pose);
 
 /* Parity read-out of one outer pass of the last laser odometry solve for one stream:
  * corr[(768 + 1536)][4] = (closestPointInd, minPointInd2, minPointInd3, valid) per query slot (corner queries
@@ -169,15 +184,22 @@ int vloam_get_lo_trace(vloam_lidar* h, int stream, int pass, int* corr, double* 
  * laser_mapping.cpp:720-729); NULL to skip the device->host read. */
 int vloam_laser_mapping(vloam_lidar* h, double* pose_out);
 int vloam_get_lm_pose(vloam_lidar* h, double* pose_out);
+/* status[batch][2] = VLOAM_LM_* bits of the last mapped scan, OR of the bits of every scan since the handle was created.
+ * A set bit never invalidates the poses; it says that stream's map did not take (part of) a scan. */
+int vloam_get_lm_status(vloam_lidar* h, int* status);
 /* Seed / read one 50 m map cube (index i + 21 j + 441 k, laser_mapping.cpp:412) of one stream; kind 0 = corner,
  * 1 = surf.  Used to pre-build the 1 M-point map of the benchmark and by the parity tests.  Seeded points must lie inside
  * the cube (laser_mapping.cpp:643-652 with the stream's current centre offsets), like every point the mapping inserts:
- * VLOAM_E_CAPACITY otherwise, or when map_capacity_points is exceeded. */
+ * VLOAM_E_INVALID otherwise; VLOAM_E_CAPACITY when map_capacity_points is exceeded. */
 int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const float* xyzi, int n);
 int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xyzi_out, int capacity_points, int* n_out);
 /* info[batch][8] = cenWidth, cenHeight, cenDepth, validNum, cornerFromMapNum, surfFromMapNum, cornerStackNum, surfStackNum */
 int vloam_get_lm_info(vloam_lidar* h, int* info);
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
+/* Parity read-out: the queries (indices into laserCloudCornerStack, kind 0, or laserCloudSurfStack, kind 1) that produced a
+ * residual block in outer pass `pass` of the last scan (laser_mapping.cpp:472-581), ascending; n_out receives their number,
+ * at most `capacity` are written. */
+int vloam_get_lm_queries(vloam_lidar* h, int stream, int pass, int kind, int* out, int capacity, int* n_out);
 /* Map storage read-out, stats[batch][2][10] per stream and feature kind (0 corner, 1 surf): points in the map, high-water
  * mark of the slab pool, pool index, non-empty cubes, cubes known to be fixed points of their voxel filter (skipped by
  * the per-scan re-filter of laser_mapping.cpp:689-702 until they receive a point), cubes rewritten by the last scan,

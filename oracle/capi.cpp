@@ -159,6 +159,13 @@ void orc_lo_get_state(void* h, double* pose) {
   pose[14] = lo->corner_correspondence; pose[15] = lo->plane_correspondence;
   pose[16] = lo->frameCount; pose[17] = lo->systemInited;
 }
+void orc_lo_set_skip(void* h, int mapping_skip_frame) { static_cast<LaserOdometry*>(h)->mapping_skip_frame = mapping_skip_frame; }
+// checkpoint / resume hook mirrored by vloam_set_lo_pose: overwrite the accumulated odometry pose
+void orc_lo_set_pose(void* h, const double* q, const double* t) {
+  auto* lo = static_cast<LaserOdometry*>(h);
+  lo->q_w_curr = Quat{q[0], q[1], q[2], q[3]};
+  lo->t_w_curr = Vec3{t[0], t[1], t[2]};
+}
 void orc_lo_set_motion(void* h, const double* q, const double* t) {
   auto* lo = static_cast<LaserOdometry*>(h);
   for (int i = 0; i < 4; ++i) lo->para_q[i] = q[i];
@@ -209,10 +216,16 @@ void orc_lm_set_iterations(void* h, int passes, int lm_iters) {
   lm->num_outer_passes = passes;
   lm->lm_max_iterations = lm_iters;
 }
-void orc_lm_input_from_lo(void* h, void* lo_) {  // lidar_odometry_mapping.cpp:125-136 (skip_frame == false)
+void orc_lm_input_from_lo(void* h, void* lo_) {  // lidar_odometry_mapping.cpp:125-136 with LaserOdometry::output's skip flag
   auto* lm = static_cast<LaserMapping*>(h);
   auto* lo = static_cast<LaserOdometry*>(lo_);
-  lm->input(lo->laserCloudCornerLast, lo->laserCloudSurfLast, lo->laserCloudFullRes, lo->q_w_curr, lo->t_w_curr);
+  lm->input(lo->laserCloudCornerLast, lo->laserCloudSurfLast, lo->laserCloudFullRes, lo->q_w_curr, lo->t_w_curr, lo->skip_frame());
+}
+// pose[8]: the /aft_mapped_to_init pose of the last input() (q xyzw, t), skip_frame
+void orc_lm_published_pose(void* h, double* pose) {
+  auto* lm = static_cast<LaserMapping*>(h);
+  lm->published_pose(pose);
+  pose[7] = lm->skip_frame ? 1.0 : 0.0;
 }
 void orc_lm_input_clouds(void* h, const float* corner, int ncorner, const float* surf, int nsurf, const double* q_odom,
                          const double* t_odom) {
@@ -312,9 +325,10 @@ int orc_pipe_process(void* h, const float* xyz, int n, int stride, int do_mappin
   p->lo.solveLO(sr.laserCloud, sr.cornerPointsSharp, sr.cornerPointsLessSharp, sr.surfPointsFlat, sr.surfPointsLessFlat,
                 nullptr, nullptr);
   double t2 = now_ms();
-  if (do_mapping && !p->lo.skip_frame()) {
-    p->lm.input(p->lo.laserCloudCornerLast, p->lo.laserCloudSurfLast, p->lo.laserCloudFullRes, p->lo.q_w_curr, p->lo.t_w_curr);
-    p->lm.solveMapping();
+  if (do_mapping) {  // lidar_odometry_mapping.cpp:125-140: input() always, solveMapping() unless the frame is skipped
+    const bool skip = p->lo.skip_frame();
+    p->lm.input(p->lo.laserCloudCornerLast, p->lo.laserCloudSurfLast, p->lo.laserCloudFullRes, p->lo.q_w_curr, p->lo.t_w_curr, skip);
+    if (!skip) p->lm.solveMapping();
   }
   double t3 = now_ms();
   p->ms[0] += t1 - t0; p->ms[1] += t2 - t1; p->ms[2] += t3 - t2; p->scans++;

@@ -37,8 +37,9 @@ class LaserMapping {
 
   int laserCloudCenWidth = 10, laserCloudCenHeight = 10, laserCloudCenDepth = 5;
   double parameters[7] = {0, 0, 0, 1, 0, 0, 0};  // q_w_curr (x,y,z,w), t_w_curr
-  Quat q_wmap_wodom, q_wodom_curr;
-  Vec3 t_wmap_wodom, t_wodom_curr;
+  Quat q_wmap_wodom, q_wodom_curr, q_w_curr_highfreq;
+  Vec3 t_wmap_wodom, t_wodom_curr, t_w_curr_highfreq;
+  bool skip_frame = false;
   std::vector<Cloud> laserCloudCornerArray, laserCloudSurfArray;
   int laserCloudValidInd[125], laserCloudSurroundInd[125];
   int laserCloudValidNum = 0, laserCloudSurroundNum = 0;
@@ -68,16 +69,33 @@ class LaserMapping {
   }
 
   void input(const Cloud& cornerLast, const Cloud& surfLast, const Cloud& fullRes, const Quat& q_odom,
-             const Vec3& t_odom) {  // :167-196 with skip_frame == false
-    laserCloudCornerLast = cornerLast;
-    laserCloudSurfLast = surfLast;
-    laserCloudFullRes = fullRes;
-    q_wodom_curr = q_odom;
+             const Vec3& t_odom, bool skip_frame_ = false) {  // :167-196
+    skip_frame = skip_frame_;
+    if (!skip_frame) {  // :175-180
+      laserCloudCornerLast = cornerLast;
+      laserCloudSurfLast = surfLast;
+      laserCloudFullRes = fullRes;
+    }
+    q_wodom_curr = q_odom;  // :182-183
     t_wodom_curr = t_odom;
     Quat q = q_wmap_wodom * q_wodom_curr;
     Vec3 t = rotate(q_wmap_wodom, t_wodom_curr) + t_wmap_wodom;
-    parameters[0] = q.x; parameters[1] = q.y; parameters[2] = q.z; parameters[3] = q.w;
-    parameters[4] = t.x; parameters[5] = t.y; parameters[6] = t.z;
+    if (skip_frame) {  // :186-190: only the high-frequency pose (what publish() sends for such a frame, :742-756)
+      q_w_curr_highfreq = q;
+      t_w_curr_highfreq = t;
+    } else {  // :191-195
+      parameters[0] = q.x; parameters[1] = q.y; parameters[2] = q.z; parameters[3] = q.w;
+      parameters[4] = t.x; parameters[5] = t.y; parameters[6] = t.z;
+    }
+  }
+  // The pose LaserMapping::publish puts into /aft_mapped_to_init for the last input() (:720-756)
+  void published_pose(double out[7]) const {
+    if (skip_frame) {
+      out[0] = q_w_curr_highfreq.x; out[1] = q_w_curr_highfreq.y; out[2] = q_w_curr_highfreq.z; out[3] = q_w_curr_highfreq.w;
+      out[4] = t_w_curr_highfreq.x; out[5] = t_w_curr_highfreq.y; out[6] = t_w_curr_highfreq.z;
+    } else {
+      for (int i = 0; i < 7; ++i) out[i] = parameters[i];
+    }
   }
 
   static int cube_coord(double v, int cen) {  // :207-216 / :643-652

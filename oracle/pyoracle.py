@@ -54,6 +54,9 @@ def lib():
             "orc_lo_solve_clouds": (None, [vp] + [c_fp, C.c_int] * 5 + [c_dp, c_dp]),
             "orc_lo_get_state": (None, [vp, c_dp]),
             "orc_lo_set_motion": (None, [vp, c_dp, c_dp]),
+            "orc_lo_set_pose": (None, [vp, c_dp, c_dp]),
+            "orc_lo_set_skip": (None, [vp, C.c_int]),
+            "orc_lm_published_pose": (None, [vp, c_dp]),
             "orc_lo_trace_passes": (C.c_int, [vp]),
             "orc_lo_trace_sizes": (None, [vp, C.c_int, c_ip]),
             "orc_lo_trace_copy": (None, [vp, C.c_int, c_ip, c_ip, c_dp, c_dp, c_ip]),
@@ -271,6 +274,15 @@ class LaserOdometry:
         t = np.ascontiguousarray(t, np.float64)
         lib().orc_lo_set_motion(self._h, _dp(q), _dp(t))
 
+    def set_pose(self, q, t):
+        """Overwrite q_w_curr / t_w_curr (the accumulated odometry pose)."""
+        q = np.ascontiguousarray(q, np.float64)
+        t = np.ascontiguousarray(t, np.float64)
+        lib().orc_lo_set_pose(self._h, _dp(q), _dp(t))
+
+    def set_mapping_skip_frame(self, n):
+        lib().orc_lo_set_skip(self._h, int(n))
+
     @property
     def state(self):
         s = np.zeros(18)
@@ -325,6 +337,13 @@ class LaserMapping:
         return {"q_w_curr": s[0:4].copy(), "t_w_curr": s[4:7].copy(), "q_wmap_wodom": s[7:11].copy(),
                 "t_wmap_wodom": s[11:14].copy(), "cen": s[14:17].astype(int), "validNum": int(s[17])}
 
+    @property
+    def published_pose(self):
+        """(q_w xyzw, t_w, skipped): the pose LaserMapping::publish sends for the last input (high-frequency pose on a skipped frame)."""
+        s = np.zeros(8)
+        lib().orc_lm_published_pose(self._h, _dp(s))
+        return s[0:4].copy(), s[4:7].copy(), bool(s[7])
+
     def set_cube(self, which, cube, xyzi):
         a = _f32(xyzi).reshape(-1, 4)
         lib().orc_lm_set_cube(self._h, which, cube, _fp(a), a.shape[0])
@@ -355,11 +374,12 @@ class LaserMapping:
 class Pipeline:
     """scanRegistration -> laserOdometry [-> laserMapping] for one stream (CPU baseline)."""
 
-    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8):
+    def __init__(self, n_scans=64, minimum_range=5.0, line_res=0.4, plane_res=0.8, mapping_skip_frame=1):
         L = lib()
         self._h = L.orc_pipe_create(n_scans, float(minimum_range), line_res, plane_res)
         self.lo = LaserOdometry(_borrowed=L.orc_pipe_lo(self._h))
         self.lm = LaserMapping(_borrowed=L.orc_pipe_lm(self._h))
+        self.lo.set_mapping_skip_frame(mapping_skip_frame)
 
     def __del__(self):
         if getattr(self, "_h", None):

@@ -27,7 +27,8 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vloam_b200.h")
 VLOAM_OK = 0
 CLOUD_FULL, CLOUD_SHARP, CLOUD_LESS_SHARP, CLOUD_FLAT, CLOUD_LESS_FLAT, CLOUD_CORNER_LAST, CLOUD_SURF_LAST, \
     CLOUD_CORNER_STACK, CLOUD_SURF_STACK, CLOUD_CORNER_MAP, CLOUD_SURF_MAP = range(11)
-STREAM_EMPTY, STREAM_RING_OVERFLOW, STREAM_VOXEL_OVERFLOW = 1, 2, 4
+STREAM_EMPTY, STREAM_RING_OVERFLOW, STREAM_VOXEL_OVERFLOW, STREAM_CAPACITY = 1, 2, 4, 8
+LM_WORKLIST_OVERFLOW, LM_SCRATCH_OVERFLOW, LM_CORNER_MAP_FULL, LM_SURF_MAP_FULL = 1, 2, 4, 8
 MAX_SHARP, MAX_FLAT = 768, 1536
 
 c_fp = C.POINTER(C.c_float)
@@ -88,6 +89,8 @@ def lib():
             "vloam_get_feature_indices": [vp, C.c_int, C.c_int, c_ip, C.c_int, c_ip],
             "vloam_laser_odometry": [vp, vp, vp, vp], "vloam_laser_odometry_async": [vp, vp],
             "vloam_get_lo_pose": [vp, vp, vp], "vloam_get_lo_pose_prev": [vp, vp, vp], "vloam_set_lo_motion": [vp, c_dp],
+            "vloam_set_lo_pose": [vp, c_dp], "vloam_get_lm_status": [vp, c_ip],
+            "vloam_get_lm_queries": [vp, C.c_int, C.c_int, C.c_int, c_ip, C.c_int, c_ip],
             "vloam_get_lo_trace": [vp, C.c_int, C.c_int, c_ip, c_dp, c_ip, c_dp],
             "vloam_laser_mapping": [vp, vp], "vloam_get_lm_pose": [vp, c_dp],
             "vloam_map_set_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int],
@@ -310,6 +313,11 @@ class LidarOdometryMapping:
         m = np.ascontiguousarray(motion, np.float64).reshape(self.batch, 7)
         self.ctx.check(lib().vloam_set_lo_motion(self._h, m.ctypes.data_as(c_dp)))
 
+    def set_lo_pose(self, pose):
+        """Overwrite q_w_curr / t_w_curr of laser odometry, (batch, 7) = q(xyzw) t (checkpoint / resume)."""
+        m = np.ascontiguousarray(pose, np.float64).reshape(self.batch, 7)
+        self.ctx.check(lib().vloam_set_lo_pose(self._h, m.ctypes.data_as(c_dp)))
+
     # -- lidar_odometry_mapping.cpp:125-154
     def laserMappingIO(self, fetch=True):
         if not fetch:
@@ -401,6 +409,21 @@ class LidarOdometryMapping:
                                                 para.ctypes.data_as(c_dp)))
         return {"iterations": rec[: min(int(info[0]), 8)].copy(), "n_records": int(info[0]), "termination": int(info[1]),
                 "n_corner": int(info[2]), "n_plane": int(info[3]), "para": para}
+
+    def lm_status(self):
+        """(batch, 2) int32: LM_* bits of the last mapped scan, OR of the bits of every scan so far."""
+        st = np.zeros((self.batch, 2), np.int32)
+        self.ctx.check(lib().vloam_get_lm_status(self._h, st.ctypes.data_as(c_ip)))
+        return st
+
+    def lm_queries(self, pass_: int, kind: int, stream: int = 0):
+        """Indices into the down-sampled corner (kind 0) / surf (kind 1) stack that produced a factor in outer pass `pass_`."""
+        n = C.c_int(0)
+        self.ctx.check(lib().vloam_get_lm_queries(self._h, stream, pass_, kind, None, 0, C.byref(n)))
+        out = np.empty(n.value, np.int32)
+        if n.value:
+            self.ctx.check(lib().vloam_get_lm_queries(self._h, stream, pass_, kind, out.ctypes.data_as(c_ip), n.value, C.byref(n)))
+        return out
 
     def map_set_cube(self, kind: int, cube: int, xyzi, stream: int = 0):
         a = np.ascontiguousarray(xyzi, np.float32).reshape(-1, 4)

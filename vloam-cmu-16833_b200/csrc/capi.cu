@@ -146,6 +146,13 @@ int vloam_ctx_create(int device, vloam_ctx** out) {
     return VLOAM_E_CUDA;
   }
   c->stream = c->own_stream;
+  // opt-in shared-memory sizes of the kernels, once per context on its device; a failure here would otherwise surface
+  // later as an opaque launch error
+  if (sr_prepare_device(device) != cudaSuccess || lo_prepare_device(device) != cudaSuccess) {
+    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
+    delete c;
+    return VLOAM_E_CUDA;
+  }
   *out = c;
   return VLOAM_OK;
 }
@@ -324,6 +331,9 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   *out = nullptr;
   if (p->batch < 1 || p->max_points < 64 || (p->scan_line != 16 && p->scan_line != 32 && p->scan_line != 64))
     return fail(c, VLOAM_E_INVALID, "vloam_lidar_create: batch >= 1, max_points >= 64, scan_line in {16,32,64}");
+  if (p->mapping_skip_frame < 1 || p->lo_outer_passes < 0 || p->lo_max_iterations < 0 || p->lm_outer_passes < 0 || p->lm_max_iterations < 0 ||
+      !(p->mapping_line_resolution > 0.0) || !(p->mapping_plane_resolution > 0.0) || !(p->minimum_range >= 0.0))
+    return fail(c, VLOAM_E_INVALID, "vloam_lidar_create: mapping_skip_frame >= 1, pass / iteration counts >= 0, resolutions > 0, minimum_range >= 0");
   CU(c, cudaSetDevice(c->device));
   vloam_lidar* h = new (std::nothrow) vloam_lidar();
   if (!h) return VLOAM_E_NOMEM;
@@ -359,7 +369,8 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
   e = lm_create(&c->prof, c->stream, h->B, h->cap, p, &h->lm);
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, VLOAM_E_CUDA, "vloam_lidar_create: map allocation", e); }
-  CU(c, cudaStreamSynchronize(c->stream));
+  e = cudaStreamSynchronize(c->stream);
+  if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, VLOAM_E_CUDA, "vloam_lidar_create: initialisation", e); }
   *out = h;
   return VLOAM_OK;
 }
@@ -461,8 +472,9 @@ int vloam_input_consumed(vloam_lidar* h) {
 }
 
 int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points) {
-  if (!h || !xyz_dev || !n_dev || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+  if (!h || !xyz_dev || !n_dev || stride < 3 || stride > kMaxInputStride || slab_points == 0) return VLOAM_E_INVALID;
   CU(h->ctx, cudaSetDevice(h->ctx->device));
+  // the counts live in device memory: the kernels clamp them to min(max_points, slab_points) and report VLOAM_STREAM_CAPACITY
   return run_scan_registration(h, xyz_dev, n_dev, stride, slab_points);
 }
 
@@ -610,6 +622,11 @@ static int read_pose(vloam_lidar* h, int par, double* pose_out, int* corr_out) {
   if (!h->pose_valid[par]) return fail(c, VLOAM_E_STATE, "no laser odometry result for that frame yet");
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaEventSynchronize(h->ev_pose[par]));  // waits for that frame's read-back only, not for the whole stream
+  if (h->shard.world > 1) {   // point-sharded: a peer that did not answer inside the solve kernel makes the result invalid
+    int bits = 0;
+    CU(c, cudaMemcpy(&bits, h->shard.error, sizeof(int), cudaMemcpyDeviceToHost));
+    if (bits) return fail(c, VLOAM_E_STATE, "point-sharded solve: a peer rank did not publish its normal equations in time (vloam_shard_status)");
+  }
   for (int b = 0; b < h->B; ++b) {
     if (pose_out) std::memcpy(pose_out + (size_t)b * 14, h->h_pose[par] + (size_t)b * 16, 14 * sizeof(double));
     if (corr_out) { corr_out[b * 2] = (int)h->h_pose[par][b * 16 + 14]; corr_out[b * 2 + 1] = (int)h->h_pose[par][b * 16 + 15]; }
@@ -648,6 +665,16 @@ int vloam_set_lo_motion(vloam_lidar* h, const double* motion) {
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaMemcpyAsync(h->d_prior, motion, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
   launch_lo_set_motion(&c->prof, c->stream, h->d_lo, h->d_prior, h->B);
+  CU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+int vloam_set_lo_pose(vloam_lidar* h, const double* pose) {
+  if (!h || !pose) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaMemcpyAsync(h->d_prior, pose, (size_t)h->B * 7 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  launch_lo_set_pose(&c->prof, c->stream, h->d_lo, h->d_prior, h->B);
   CU(c, cudaStreamSynchronize(c->stream));
   return VLOAM_OK;
 }
@@ -695,7 +722,8 @@ int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const flo
   vloam_ctx* c = h->ctx;
   CU(c, cudaSetDevice(c->device));
   cudaError_t e = lm_set_cube(h->lm, c->stream, stream, kind, cube, xyzi, n);
-  if (e == cudaErrorInvalidValue) return fail(c, VLOAM_E_CAPACITY, "vloam_map_set_cube: map_capacity_points exceeded");
+  if (e == cudaErrorInvalidValue) return fail(c, VLOAM_E_INVALID, "vloam_map_set_cube: a point lies outside the named cube");
+  if (e == cudaErrorMemoryAllocation) return fail(c, VLOAM_E_CAPACITY, "vloam_map_set_cube: map_capacity_points exceeded");
   return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_map_set_cube", e);
 }
 int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* out, int capacity, int* n_out) {
@@ -718,6 +746,20 @@ int vloam_get_map_stats(vloam_lidar* h, int* stats) {
   CU(c, cudaSetDevice(c->device));
   cudaError_t e = lm_get_map_stats(h->lm, c->stream, stats);
   return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_map_stats", e);
+}
+int vloam_get_lm_status(vloam_lidar* h, int* status) {
+  if (!h || !status) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_status(h->lm, c->stream, status);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_status", e);
+}
+int vloam_get_lm_queries(vloam_lidar* h, int stream, int pass, int kind, int* out, int capacity, int* n_out) {
+  if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1 || kind < 0 || kind > 1 || capacity < 0) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_queries(h->lm, c->stream, stream, pass, kind, out, capacity, n_out);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_queries", e);
 }
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para) {
   if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1) return VLOAM_E_INVALID;

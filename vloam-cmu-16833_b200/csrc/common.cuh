@@ -31,6 +31,7 @@ constexpr int kClassifyBlock = 1024;  // points per block in classify / scatter
 constexpr int kStatusEmpty = 1;        // no point survived NaN / range filters
 constexpr int kStatusRingOverflow = 2; // a ring exceeded kRingCap or a sector kSectorCap
 constexpr int kStatusVoxelOverflow = 4;  // PCL's "leaf size too small" path was taken (input returned unfiltered)
+constexpr int kStatusCapacity = 8;     // the scan had more points than the handle's capacity: the excess was ignored
 
 // Per-stream scan-registration bookkeeping, resident on the device.
 struct SRHeader {

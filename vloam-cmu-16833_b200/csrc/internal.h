@@ -53,6 +53,8 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
                               float4* flat, int* flatIdx, float4* lessFlat);
 
+cudaError_t sr_prepare_device(int device);   // per-device function attributes, once per context
+
 // lo_kernels.cu
 void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
 // Grid index over the (corner, surf) target clouds of every stream: [B][2] headers, cell tables and sorted copies.
@@ -71,6 +73,8 @@ void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const
                           const float4* lessFlat, const LOGrid* grid);
 void launch_lo_export(Profiler* prof, cudaStream_t st, const LOState* lo, double* pose, int B);
 void launch_lo_set_motion(Profiler* prof, cudaStream_t st, LOState* lo, const double* motion, int B);
+void launch_lo_set_pose(Profiler* prof, cudaStream_t st, LOState* lo, const double* pose, int B);
+cudaError_t lo_prepare_device(int device);   // per-device function attributes (opt-in shared memory), once per context
 
 // lm_kernels.cu — laser mapping state of a batch of streams
 struct LMDevice;
@@ -86,6 +90,8 @@ cudaError_t lm_get_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int
 cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info);
 cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats);
 cudaError_t lm_get_trace(LMDevice* lm, cudaStream_t st, int stream, int pass, double* records, int* info, double* para);
+cudaError_t lm_get_status(LMDevice* lm, cudaStream_t st, int* status);
+cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out);
 
 }  // namespace vb
 

@@ -30,11 +30,28 @@ namespace vb {
 
 constexpr int kCubeW = 21, kCubeH = 21, kCubeD = 11, kCubes = kCubeW * kCubeH * kCubeD;  // laser_mapping.h:110-114
 constexpr int kMaxValid = 125;                                                           // laser_mapping.h:116
+// LMState::error bits (vloam_get_lm_status)
+constexpr int kLmErrWorkList = 1;   // more than kMaxWork cubes would be rewritten by one scan: the scan's points were not inserted
+constexpr int kLmErrScratch = 2;    // the re-filter scratch would overflow: the scan's points were not inserted
+constexpr int kLmErrCapacity = 4;   // << kind: map_capacity_points exceeded for corner (4) / surf (8): that map keeps its previous content
 constexpr int kMaxWork = 200;   // cubes rewritten per scan: the valid ones plus cubes that received points
 // Column index of a cube (the kd-tree replacement, see lm_associate): 50 x 50 xy-columns of 1.001 m per 50 m cube.
 constexpr float kCubeCell = 1.001f;
 constexpr int kCubeCellsX = 50, kCubeCells = kCubeCellsX * kCubeCellsX;
-constexpr int kTabSlots = 512;   // column tables per stream and kind (>= the 125 valid cubes + the cubes one scan can touch)
+// Inside the cube the points are ordered by 4 m z-layer, then by column (row-major): a query only reads, per z-layer its
+// +-1.001 m interval touches (one or two) and per column row (three), ONE contiguous run covering its three columns.
+constexpr int kZBins = 13;       // 13 x 4 m cover the 50 m cube
+constexpr float kZBin = 4.0f;
+constexpr int kZCells = kZBins * kCubeCells;
+// One index table ("slot") per indexed cube:  int hdr[16]: hdr[z] = first sorted position of z-layer z (z < 13), hdr[13] = n,
+// hdr[14] = mode;  then, mode 0: unsigned short rel[13][2501] = start of every column inside its z-layer (rel[z][2500] = size
+// of the layer);  mode 1 (a cube of more than 65 535 points: 16-bit offsets do not reach): int flat[2501] = column starts of
+// a column-only order, no z-layers.
+constexpr int kTabHdr = 16;
+constexpr int kLayerCells = kCubeCells + 1;
+constexpr int kTabInts = kTabHdr + (kZBins * kLayerCells * 2 + 3) / 4 + 3;   // 16 276 ints = 65 104 bytes, a multiple of 16
+static_assert(kTabInts % 4 == 0 && kTabInts >= kTabHdr + kCubeCells + 1, "slot layout");
+constexpr int kTabSlots = 384;   // index tables per stream and kind (>= the 125 valid cubes + the cubes one scan can touch)
 
 struct LMState {
   double parameters[7];                 // q_w_curr (x,y,z,w), t_w_curr      laser_mapping.cpp:74-83
@@ -60,7 +77,9 @@ struct LMState {
   int workIn0[2][kMaxWork + 1];         // offsets of each work cube's (old ++ new) input inside the concat buffer
   int workOutN[2][kMaxWork], workFixed[2][kMaxWork];
   int workDirect[2][kMaxWork];          // the cube's new content already sits in its slab (patched in place by lm_refilter)
-  int error;
+  int error;                            // this scan's error bits (kLmErr*), cleared by lm_prepare
+  int errorEver;                        // OR of every scan's error bits since the handle was created
+  int applied[2];                       // lm_place committed this scan's rewritten cubes of the kind
   SolveTrace trace[2];
 };
 
@@ -85,7 +104,7 @@ struct LMDevice {
   int* cubeCap[2] = {nullptr, nullptr};
   int* cubeFix[2] = {nullptr, nullptr};
   int* cubeTab[2] = {nullptr, nullptr};   // slot of the cube's column table in tabPool, -1 = no valid index
-  int* tabPool = nullptr;                 // [B][2][kTabSlots][kCubeCells + 1] column starts inside the cube's sorted copy
+  int* tabPool = nullptr;                 // [B][2][kTabSlots][kTabInts] index tables (layout: kTabHdr)
   short* entryHead = nullptr;             // [B][kCubes] first entry of the valid list naming this cube, -1 = not in the sub-map
   float4* mapPts[2] = {nullptr, nullptr}; // two pools [B][2][mapCap]; a stream changes pool only when its map is re-packed
   float4* snap = nullptr;                 // [B][2][mapCap] laserCloud{Corner,Surf}FromMap of the last scan (debug_keep_submap)
@@ -96,6 +115,7 @@ struct LMDevice {
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
   float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
   LMResidual* res = nullptr;              // [B][2][cap]
+  uint8_t* fitType = nullptr;             // [2 passes][B][2][cap] factor type per query and outer pass (vloam_get_lm_queries)
   int* cubeOf = nullptr;                  // [B][2][cap] cube id of every down-sampled scan point (map frame)
   int* nnPos = nullptr;                   // [B][2][cap][5] positions (in `sorted`) of the five nearest map points per query
   double* pose = nullptr;                 // [B][16]
@@ -284,6 +304,7 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
   __shared__ int s_gc[2];
   if (threadIdx.x == 0) {
     if (resetValid) st.validNum = 0;  // LaserMapping::reset (:127-131)
+    st.error = 0;                     // error bits describe one scan (the sticky copy is errorEver)
     // input(), :182-195: q_w_curr = q_wmap_wodom * q_wodom_curr; t_w_curr = q_wmap_wodom * t_wodom_curr + t_wmap_wodom
     for (int i = 0; i < 4; ++i) st.q_wodom[i] = lo[b].q_w[i];
     for (int i = 0; i < 3; ++i) st.t_wodom[i] = lo[b].t_w[i];
@@ -406,12 +427,57 @@ __device__ __forceinline__ float4 submap_point(const LMState& st, int kind, cons
 __device__ __forceinline__ float cube_min_coord(int idx, int cen) { return (float)((idx - cen) * 50.0 - 25.0); }
 __device__ __forceinline__ int cube_cell(float v, float mn) { return (int)floorf((v - mn) * (1.0f / kCubeCell)); }
 __device__ __forceinline__ int cube_cell_clamped(float v, float mn) { return min(max(cube_cell(v, mn), 0), kCubeCellsX - 1); }
-// One CTA of NT threads (a multiple of 32, <= 1024).  pts[0..n): the cube's slab; tab[kCubeCells + 1] (global) receives the column starts; sortedOut[0..n)
-// the column-sorted copy with w = index inside the cube.  s_cells: kCubeCells + 1 ints of shared memory, s_w: 32 ints.
+__device__ __forceinline__ int cube_zbin(float z, float mnz) { return min(max((int)floorf((z - mnz) * (1.0f / kZBin)), 0), kZBins - 1); }
+// One CTA of NT threads (a multiple of 32, <= 1024) builds the index of one cube.  pts[0..n): the cube's slab; tab[kTabInts]
+// (global): the cube's table slot; sortedOut[0..n): the copy ordered by (z-layer, column) with w = index inside the cube.
+// Shared memory (dynamic, kIndexSmemBytes): one 16-bit counter per (z-layer, column) cell, two to a word — first the
+// histogram, then the running position inside the cell, advanced by shared-memory atomics (a half cannot overflow into its
+// neighbour: the whole cube holds at most 65 535 points in this mode) — plus the layer starts.  A larger cube is indexed by
+// column only, with 32-bit counters in the same shared memory (mode 1).
+constexpr int kIndexSmemBytes = ((kZCells + 1) / 2 + kZBins + 3 + 32) * (int)sizeof(int);
 template <int NT>
-__device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, float minX, float minY, int* __restrict__ tab,
-                                     float4* __restrict__ sortedOut, int* s_cells, int* s_w) {
-  for (int i = threadIdx.x; i <= kCubeCells; i += NT) s_cells[i] = 0;
+__device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, float minX, float minY, float minZ, int* __restrict__ tab,
+                                     float4* __restrict__ sortedOut, int* smem) {
+  const int l = lane_id(), w = threadIdx.x >> 5;
+  auto col_of = [&](const float4& p) { return cube_cell_clamped(p.y, minY) * kCubeCellsX + cube_cell_clamped(p.x, minX); };
+  if (n > 65535) {
+    // ---- mode 1: column-only index, 32-bit counters
+    int* s_col = smem;                      // [kCubeCells + 1]
+    int* s_w = smem + kCubeCells + 1;       // [32]
+    int* flat = tab + kTabHdr;
+    for (int i = threadIdx.x; i <= kCubeCells; i += NT) s_col[i] = 0;
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += NT) atomicAdd(&s_col[col_of(pts[i])], 1);
+    __syncthreads();
+    constexpr int per = (kCubeCells + NT - 1) / NT;
+    const int c0 = min((int)threadIdx.x * per, kCubeCells), c1 = min(c0 + per, kCubeCells);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += s_col[c];
+    int sc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
+    if (l == 31) s_w[w] = sc;
+    __syncthreads();
+    int run = sc - sum;
+    for (int q = 0; q < w; ++q) run += s_w[q];
+    for (int c = c0; c < c1; ++c) { const int t = s_col[c]; s_col[c] = run; flat[c] = run; run += t; }
+    if (threadIdx.x == NT - 1) flat[kCubeCells] = n;
+    if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x == 0 ? 0 : threadIdx.x == 14 ? 1 : n;   // one "layer"; mode 1
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += NT) {
+      const float4 p = pts[i];
+      sortedOut[atomicAdd(&s_col[col_of(p)], 1)] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+    }
+    __syncthreads();
+    return;
+  }
+  // ---- mode 0: (z-layer, column) cells, packed 16-bit counters
+  unsigned* s_pack = reinterpret_cast<unsigned*>(smem);            // [(kZCells + 1) / 2]
+  int* s_layer = smem + (kZCells + 1) / 2;                         // [kZBins + 1] layer starts
+  int* s_w = s_layer + kZBins + 3;                                 // [32]
+  unsigned short* rel = reinterpret_cast<unsigned short*>(tab + kTabHdr);
+  auto cell_of = [&](const float4& p) { return cube_zbin(p.z, minZ) * kCubeCells + col_of(p); };
+  for (int i = threadIdx.x; i < (kZCells + 1) / 2; i += NT) s_pack[i] = 0u;
   __syncthreads();
   // (four independent loads in flight per thread: the passes over the cube are latency bound otherwise)
   for (int i0 = threadIdx.x; i0 < n; i0 += 4 * NT) {
@@ -420,24 +486,40 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
     for (int u = 0; u < 4; ++u) { const int i = i0 + u * NT; if (i < n) p[u] = pts[i]; }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (i0 + u * NT < n) atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
+      if (i0 + u * NT < n) { const int c = cell_of(p[u]); atomicAdd(&s_pack[c >> 1], (c & 1) ? 0x10000u : 1u); }
   }
   __syncthreads();
-  constexpr int per = (kCubeCells + NT - 1) / NT;
-  const int c0 = min((int)threadIdx.x * per, kCubeCells), c1 = min(c0 + per, kCubeCells);
+  // exclusive scan over the cells in (z-layer, column) order: a thread owns an even number of consecutive cells, i.e. whole words
+  constexpr int per = (((kZCells + NT - 1) / NT) + 1) & ~1;
+  const int c0 = min((int)threadIdx.x * per, kZCells), c1 = min(c0 + per, kZCells);
+  auto get = [&](int cell) { const unsigned v = s_pack[cell >> 1]; return (int)((cell & 1) ? (v >> 16) : (v & 0xffffu)); };
   int sum = 0;
-  for (int c = c0; c < c1; ++c) sum += s_cells[c];
+  for (int cell = c0; cell < c1; ++cell) sum += get(cell);
   int sc = sum;
-  const int l = lane_id(), w = threadIdx.x >> 5;
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
   if (l == 31) s_w[w] = sc;
   __syncthreads();
-  int run = sc - sum;
-  for (int q = 0; q < w; ++q) run += s_w[q];
-  for (int c = c0; c < c1; ++c) { const int t = s_cells[c]; s_cells[c] = run; tab[c] = run; run += t; }
-  if (threadIdx.x == NT - 1) tab[kCubeCells] = n;
+  int base = sc - sum;
+  for (int q = 0; q < w; ++q) base += s_w[q];
+  {   // the layer starts: position of the first cell of every layer
+    int run = base;
+    for (int cell = c0; cell < c1; ++cell) { if (cell % kCubeCells == 0) s_layer[cell / kCubeCells] = run; run += get(cell); }
+    if (threadIdx.x == 0) s_layer[kZBins] = n;
+  }
   __syncthreads();
+  {   // 16-bit column starts relative to the layer start; the counters start over at zero for the scatter
+    int run = base;
+    for (int cell = c0; cell < c1; ++cell) {
+      const int z = cell / kCubeCells;
+      rel[z * kLayerCells + (cell - z * kCubeCells)] = (unsigned short)(run - s_layer[z]);
+      run += get(cell);
+    }
+    for (int wd = c0 >> 1; wd < (c1 + 1) >> 1; ++wd) s_pack[wd] = 0u;
+    if (threadIdx.x < kZBins) rel[threadIdx.x * kLayerCells + kCubeCells] = (unsigned short)(s_layer[threadIdx.x + 1] - s_layer[threadIdx.x]);
+    if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x <= kZBins ? s_layer[threadIdx.x] : 0;   // hdr[13] = n, hdr[14] = mode 0
+  }
+  __syncthreads();     // (also makes the table written above visible to the whole CTA)
   for (int i0 = threadIdx.x; i0 < n; i0 += 4 * NT) {
     float4 p[4];
 #pragma unroll
@@ -446,28 +528,31 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
     for (int u = 0; u < 4; ++u) {
       const int i = i0 + u * NT;
       if (i < n) {
-        const int pos = atomicAdd(&s_cells[cube_cell_clamped(p[u].y, minY) * kCubeCellsX + cube_cell_clamped(p[u].x, minX)], 1);
-        sortedOut[pos] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
+        const int c = cell_of(p[u]);
+        const int z = c / kCubeCells;
+        const unsigned old = atomicAdd(&s_pack[c >> 1], (c & 1) ? 0x10000u : 1u);
+        const int within = (int)((c & 1) ? (old >> 16) : (old & 0xffffu));
+        sortedOut[s_layer[z] + (int)rel[z * kLayerCells + (c - z * kCubeCells)] + within] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
       }
     }
   }
   __syncthreads();
 }
-// lm_index_build: grid (kMaxValid, 2, B), block kIndexThreads: CTA u indexes the u-th cube of lm_prepare's build list.
+// lm_index_build: grid (32, 2, B), block kIndexThreads: CTAs walk lm_prepare's build list.
 constexpr int kIndexThreads = 512;
-__global__ void __launch_bounds__(kIndexThreads) lm_index_build(const LMState* __restrict__ stAll, const CubeTables T, const MapPools pools,
+__global__ void __launch_bounds__(kIndexThreads, 2) lm_index_build(const LMState* __restrict__ stAll, const CubeTables T, const MapPools pools,
                                                        int mapCap, int* __restrict__ tabPool, float4* __restrict__ sorted) {
-  __shared__ int s_cells[kCubeCells + 1];
-  __shared__ int s_w[32];
+  extern __shared__ int idx_smem[];
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   for (int u = blockIdx.x; u < st.buildNum[kind]; u += gridDim.x) {
-  const int c = st.buildList[kind][u];
-  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
-  const int off = T.off[tb + c], n = T.cnt[tb + c], slot = T.tab[tb + c];
-  cta_build_cube_index<kIndexThreads>(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
-                       cube_min_coord((c / kCubeW) % kCubeH, st.cenH), tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1),
-                       sorted + ((size_t)b * 2 + kind) * mapCap + off, s_cells, s_w);
+    const int c = st.buildList[kind][u];
+    const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+    const int off = T.off[tb + c], n = T.cnt[tb + c], slot = T.tab[tb + c];
+    cta_build_cube_index<kIndexThreads>(stream_map(pools, st, b, kind, mapCap) + off, n, cube_min_coord(c % kCubeW, st.cenW),
+                                        cube_min_coord((c / kCubeW) % kCubeH, st.cenH), cube_min_coord(c / (kCubeW * kCubeH), st.cenD),
+                                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * kTabInts,
+                                        sorted + ((size_t)b * 2 + kind) * mapCap + off, idx_smem);
   }
 }
 
@@ -625,11 +710,15 @@ __device__ __forceinline__ void colpiv_qr_solve_5x3_dev(const double Ain[15], co
 //   lm_fit  one THREAD per point: PCA line test (corner) or least-squares plane fit + 0.2 m check (surf) on the five
 //           neighbours, in double like the reference.  (Done by whole warps this part ran 32 times redundantly.)
 constexpr int kLmGroup = 8;
-// grid (nblk, 2, B), block 256: a CTA takes chunks of 64 points (8 warps x 2 rounds x 4 groups), grid-stride
-__global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
-                                                  const CubeTables T, const short* __restrict__ entryHeadAll,
-                                                  const int* __restrict__ tabPool, const float4* __restrict__ sorted,
-                                                  int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/) {
+// grid (nblk, 2, B), block 256: a CTA takes chunks of 32 points (8 warps x 4 groups), grid-stride.
+// Candidates of a query = per cube its 1.001 m box touches, per z-layer its +-1.001 m interval touches (<= 2), per column
+// row (<= 3): the run of sorted positions covering its three columns — at most six runs, looked up by six lanes at once;
+// then every lane takes one candidate of every run (six independent 16-byte loads in flight) and the rare longer runs are
+// finished in a loop.  On the benchmark map that is ~13 candidates per query instead of the 142 of a z-blind 3 x 3 column block.
+__device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+                                            const CubeTables& T, const short* __restrict__ entryHeadAll,
+                                            const int* __restrict__ tabPool, const float4* __restrict__ sorted,
+                                            int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
@@ -639,7 +728,7 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
   const unsigned gmask = 0xffu << (g * kLmGroup);
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const short* entryHead = entryHeadAll + (size_t)b * kCubes;
-  const int* tabs = tabPool + ((size_t)b * 2 + kind) * kTabSlots * (kCubeCells + 1);
+  const int* tabs = tabPool + ((size_t)b * 2 + kind) * kTabSlots * kTabInts;
   const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
   const int cenW = st.cenW, cenH = st.cenH, cenD = st.cenD;
   const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
@@ -659,6 +748,22 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
       double w[3];
       quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
       const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
+      // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped, :479 / :547,
+      // and then every true neighbour is), and none farther than this lane's 5th best.  The distance is
+      // (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
+      auto consider = [&](const float4 tp, unsigned gBase, int pos) {
+        const float dz = __fsub_rn(sz, tp.z);
+        if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) return;
+        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+        if (__float_as_uint(d) > wbits) return;
+        unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
+        if (key < bk[4]) {
+#pragma unroll
+          for (int i = 0; i < 5; ++i)
+            if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+          wbits = min(wbits, (unsigned)(bk[4] >> 32));
+        }
+      };
       // every cube the 1.001 m box around the query touches (one, unless the query sits at a cube border) ...
       const int ci0 = max(cube_coord((double)sx - 1.001, cenW), 0), ci1 = min(cube_coord((double)sx + 1.001, cenW), kCubeW - 1);
       const int cj0 = max(cube_coord((double)sy - 1.001, cenH), 0), cj1 = min(cube_coord((double)sy + 1.001, cenH), kCubeH - 1);
@@ -671,42 +776,46 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
             if (e < 0) continue;                       // not part of the sub-map (:404-420)
             const int slot = T.tab[tb + c];
             if (slot < 0) continue;                    // empty cube
-            const int* tab = tabs + (size_t)slot * (kCubeCells + 1);
+            const int* tab = tabs + (size_t)slot * kTabInts;
             const int off = T.off[tb + c];
-            const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH);
+            const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH), mnz = cube_min_coord(ck, cenD);
             const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
             const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
-            if (x0 > x1) continue;
+            const int r0 = max(qy - 1, 0), r1 = min(qy + 1, kCubeCellsX - 1);
+            if (x0 > x1 || r0 > r1) continue;
+            // the z-layers the +-1.001 m interval touches (the clamped bin function of the build is monotone, so every point
+            // within 1 m in z lies in one of them); a cube in mode 1 has a single layer
+            const bool flat = tab[14] != 0;
+            const int zb0 = flat ? 0 : cube_zbin(sz - 1.001f, mnz), zb1 = flat ? 0 : cube_zbin(sz + 1.001f, mnz);
+            const int nr = r1 - r0 + 1, nruns = (zb1 - zb0 + 1) * nr;      // <= 2 x 3
+            int ra = 0, re = 0;
+            if (gl < nruns) {
+              const int z = zb0 + gl / nr, row = r0 + gl % nr;
+              if (flat) {
+                ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
+              } else {
+                const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kLayerCells + row * kCubeCellsX;
+                const int L = tab[z];
+                ra = L + (int)rel[x0]; re = L + (int)rel[x1 + 1];
+              }
+            }
             // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
             // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
             for (; e >= 0; e = st.entryNext[e]) {
               const unsigned gBase = (unsigned)st.validPrefix[kind][e];
-              for (int row = max(qy - 1, 0); row <= min(qy + 1, kCubeCellsX - 1); ++row) {
-                const int a = tab[row * kCubeCellsX + x0], en = tab[row * kCubeCellsX + x1 + 1];
-                // four candidates in flight per lane: the walk is bound by the latency of these (L2) loads
-                for (int t = a + gl; t < en; t += 4 * kLmGroup) {
-                  float4 tp[4];
+              // three runs (one z-layer) at a time: three independent candidate loads in flight per lane
+              for (int r3 = 0; r3 < nruns; r3 += 3) {
+                int aa[3], ee[3];
+                float4 tp[3];
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) if (t + u * kLmGroup < en) tp[u] = S[off + t + u * kLmGroup];
+                for (int r = 0; r < 3; ++r) {
+                  aa[r] = __shfl_sync(gmask, ra, r3 + r, kLmGroup) + gl; ee[r] = __shfl_sync(gmask, re, r3 + r, kLmGroup);
+                  if (aa[r] < ee[r]) tp[r] = S[off + aa[r]];
+                }
 #pragma unroll
-                  for (int u = 0; u < 4; ++u) {
-                    if (t + u * kLmGroup >= en) break;
-                    // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped,
-                    // :479 / :547, and then every true neighbour is), and none farther than this lane's 5th best.  The
-                    // distance is (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
-                    const float dz = __fsub_rn(sz, tp[u].z);
-                    if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) continue;
-                    const float d = sqdist_f(sx, sy, sz, tp[u].x, tp[u].y, tp[u].z);
-                    if (__float_as_uint(d) > wbits) continue;
-                    unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp[u].w));
-                    if (key < bk[4]) {
-                      int pos = off + t + u * kLmGroup;
-#pragma unroll
-                      for (int i = 0; i < 5; ++i)
-                        if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
-                      wbits = min(wbits, (unsigned)(bk[4] >> 32));
-                    }
-                  }
+                for (int r = 0; r < 3; ++r) {
+                  if (aa[r] < ee[r]) consider(tp[r], gBase, off + aa[r]);
+                  for (int t = aa[r] + kLmGroup; t < ee[r]; t += kLmGroup) consider(S[off + t], gBase, off + t);   // (rare: a run of more than 8 points)
                 }
               }
             }
@@ -740,10 +849,18 @@ __global__ void __launch_bounds__(256, 4) lm_knn(const LMState* __restrict__ stA
     }
   }
 }
+// Two register budgets of the same body (the kernel is bound by memory latency, so occupancy against spills is settled by
+// measurement: VLOAM_LM_KNN_OCC=3|4).
+#define VB_LM_KNN_ARGS                                                                                                            \
+  const LMState *__restrict__ stAll, const float4 *__restrict__ stack, int cap, const CubeTables T,                              \
+      const short *__restrict__ entryHeadAll, const int *__restrict__ tabPool, const float4 *__restrict__ sorted, int mapCap,    \
+      int *__restrict__ nnPos
+__global__ void __launch_bounds__(256, 4) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos); }
+__global__ void __launch_bounds__(256, 3) lm_knn_occ3(VB_LM_KNN_ARGS) { lm_knn_body(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos); }
 // grid (nblk, 2, B), block 128: one thread per point
 __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
-                                               LMResidual* __restrict__ res) {
+                                               LMResidual* __restrict__ res, uint8_t* __restrict__ fitType /*[B][2][cap] of this pass*/) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
@@ -793,6 +910,7 @@ __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll,
       }
     }
     res[((size_t)b * 2 + kind) * cap + qi] = R;
+    fitType[((size_t)b * 2 + kind) * cap + qi] = (uint8_t)R.type;   // parity read-out: which queries produced a factor in this pass
   }
 }
 
@@ -988,7 +1106,7 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
   if (threadIdx.x == 0) {
     const int* cnt = cubeCnt + ((size_t)b * 2 + kind) * kCubes;
     const int* fix = cubeFix + ((size_t)b * 2 + kind) * kCubes;
-    if (s_nh > kMaxWork) st.error |= 1;
+    if (s_nh > kMaxWork) atomicOr(&st.error, kLmErrWorkList);
     int wn = 0;
     for (int h = 0; h < nh; ++h) {                 // cubes that receive points (distinct by construction)
       const int c = s_headCube[h];
@@ -1000,7 +1118,7 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
       const int c = st.validInd[v];
       if ((s_listed[c >> 5] >> (c & 31)) & 1u) continue;
       if (cnt[c] == 0 || fix[c]) continue;
-      if (wn >= kMaxWork) { st.error |= 1; break; }
+      if (wn >= kMaxWork) { atomicOr(&st.error, kLmErrWorkList); break; }
       s_listed[c >> 5] |= 1u << (c & 31);
       st.workCube[kind][wn] = c; st.workFilter[kind][wn] = 1; st.workNew0[kind][wn] = 0; st.workNewN[kind][wn] = 0; ++wn;
     }
@@ -1008,7 +1126,7 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
     for (int u = 0; u < wn; ++u) { st.workIn0[kind][u] = in0; in0 += cnt[st.workCube[kind][u]] + st.workNewN[kind][u]; }
     st.workIn0[kind][wn] = in0;
     st.workNum[kind] = wn;
-    if ((size_t)in0 + (size_t)cap > workCap) st.error |= 2;
+    if ((size_t)in0 + (size_t)cap > workCap) atomicOr(&st.error, kLmErrScratch);
   }
 }
 __global__ void lm_transform_update(LMState* __restrict__ stAll, int B) {  // :140-144
@@ -1068,7 +1186,7 @@ __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __re
   __shared__ int s_w[NT / 32 + 1];
   const int kind = blockIdx.y, b = blockIdx.z;
   LMState& st = stAll[b];
-  if (st.error) return;
+  if (st.error & (kLmErrWorkList | kLmErrScratch)) return;
   const int nWork = st.workNum[kind];
   for (int u = blockIdx.x; u < nWork; u += gridDim.x) {   // (a grid of one CTA per possible work cube would be mostly empty CTAs)
   const int c = st.workCube[kind][u];
@@ -1169,7 +1287,7 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
   __shared__ float red[6 * 32];
   const int kind = blockIdx.y, b = blockIdx.z;
   LMState& st = stAll[b];
-  if (st.error) return;
+  if (st.error & (kLmErrWorkList | kLmErrScratch)) return;
   const int nWork = st.workNum[kind];
   for (int u = blockIdx.x; u < nWork; u += gridDim.x) {
   const int c = st.workCube[kind][u];
@@ -1228,10 +1346,14 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
     dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
     dst.tab[tb + c] = src.tab[tb + c];
   }
-  // (the other kind's CTA may raise st.error concurrently: one read, shared, keeps the barriers below uniform)
-  if (threadIdx.x == 0) { s_compact = 0; s_nlive = 0; st.compact[kind] = 0; s_err = st.error; }   // (sticky: an errored stream's map is frozen)
+  // Only the bits lm_insert_keys raised (a whole kernel ago) are read here; the capacity bit is per kind and is raised and
+  // acted upon by this CTA alone, so the two kinds' CTAs never see each other's decision half-way.
+  if (threadIdx.x == 0) {
+    s_compact = 0; s_nlive = 0; st.compact[kind] = 0; st.applied[kind] = 0;
+    s_err = st.error & (kLmErrWorkList | kLmErrScratch);
+  }
   __syncthreads();
-  if (s_err) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }   // the map keeps its pre-insertion state
+  if (s_err) { if (threadIdx.x == 0) liveNumAll[b * 2 + kind] = 0; return; }   // nothing was re-filtered: the map keeps its pre-insertion state
   const int wn = st.workNum[kind];
   for (int u = threadIdx.x; u < wn; u += 1024) workOf[st.workCube[kind][u]] = (short)u;
   __syncthreads();
@@ -1248,7 +1370,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
       dst.fix[tb + c] = st.workFilter[kind][u] ? st.workFixed[kind][u] : 0;
     }
     if (!s_compact) {
-      st.poolEnd[kind] = poolEnd;
+      st.poolEnd[kind] = poolEnd; st.applied[kind] = 1;
       // a rewritten cube is re-indexed by lm_write_back: in its old table slot, a new one, or (no slot left) lazily by
       // the next lm_prepare
       int te = st.tabEnd[kind];
@@ -1270,12 +1392,18 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
   block_exclusive_scan1024(sum, S);
   const long long total = S.total;
   __syncthreads();
-  if (total > (long long)mapCap) {   // capacity exceeded: keep the old content (reported through the error bits of the pose export)
+  if (total > (long long)mapCap) {
+    // capacity exceeded: this kind's map keeps its pre-insertion tables (vloam_get_lm_status reports it).  The cubes
+    // lm_refilter_merge patched inside their slab (no insertion: same size, same slab) did change; their filter flag
+    // follows, lm_write_back re-indexes them.
     for (int c = threadIdx.x; c < kCubes; c += 1024) {
-      dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c]; dst.fix[tb + c] = src.fix[tb + c];
+      const int u = workOf[c];
+      const bool direct = u >= 0 && st.workDirect[kind][u];
+      dst.off[tb + c] = src.off[tb + c]; dst.cnt[tb + c] = src.cnt[tb + c]; dst.cap[tb + c] = src.cap[tb + c];
+      dst.fix[tb + c] = direct ? st.workFixed[kind][u] : src.fix[tb + c];
       dst.tab[tb + c] = src.tab[tb + c];
     }
-    if (threadIdx.x == 0) { st.error |= 4; liveNumAll[b * 2 + kind] = 0; }
+    if (threadIdx.x == 0) { atomicOr(&st.error, kLmErrCapacity << kind); liveNumAll[b * 2 + kind] = 0; }
     return;
   }
   const long long spare = ((long long)mapCap - total) / 2;    // half of the free space becomes head-room, half stays for the bump allocator
@@ -1299,7 +1427,7 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    st.poolEnd[kind] = S.total; st.compact[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive;
+    st.poolEnd[kind] = S.total; st.compact[kind] = 1; st.applied[kind] = 1; liveNumAll[b * 2 + kind] = s_nlive;
     int te = 0;                        // table slots start over; the rewritten cubes are re-indexed right away
     for (int u = 0; u < wn && te < st.tabLimit; ++u) if (st.workOutN[kind][u] > 0) dst.tab[tb + st.workCube[kind][u]] = te++;
     st.tabEnd[kind] = te;
@@ -1307,35 +1435,40 @@ __global__ void __launch_bounds__(1024) lm_place(LMState* __restrict__ stAll, co
 }
 // lm_write_back: grid (kMaxWork, 2, B), block kIndexThreads: rewritten cube -> its slab (in the other pool when the map is re-packed;
 // nothing to move when lm_refilter patched the slab in place), then the cube's column index is rebuilt from the new content.
-__global__ void __launch_bounds__(kIndexThreads) lm_write_back(const LMState* __restrict__ stAll, const CubeTables Tsrc, const CubeTables T,
+__global__ void __launch_bounds__(kIndexThreads, 2) lm_write_back(const LMState* __restrict__ stAll, const CubeTables Tsrc, const CubeTables T,
                                                       const MapPools pools, int mapCap, const float4* __restrict__ staged, size_t workCap,
                                                       int* __restrict__ tabPool, float4* __restrict__ sorted) {
-  __shared__ int s_cells[kCubeCells + 1];
-  __shared__ int s_w[32];
+  extern __shared__ int idx_smem[];
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
-  if (st.error) return;
+  if (st.error & (kLmErrWorkList | kLmErrScratch)) return;   // the scan's insertion was abandoned before the re-filter (lm_insert_keys)
+  const bool applied = st.applied[kind] != 0;   // lm_place committed this kind's new tables
   const int nWork = st.workNum[kind];
   for (int u = blockIdx.x; u < nWork; u += gridDim.x) {
-  const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
-  const size_t tb = ((size_t)b * 2 + kind) * kCubes;
-  const int off = T.off[tb + c], slot = T.tab[tb + c];
-  const bool direct = st.workDirect[kind][u] != 0;
-  const float4* src = direct ? stream_map(pools, st, b, kind, mapCap) + Tsrc.off[tb + c]
-                             : staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
-  float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
-  if (src != dst)
-    for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kIndexThreads) {
-      float4 p[4];
+    const int c = st.workCube[kind][u], n = st.workOutN[kind][u];
+    const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+    const bool direct = st.workDirect[kind][u] != 0;
+    // placement failed (the map would not fit its pool even after a re-pack): only the cubes lm_refilter_merge already
+    // patched inside their slab change — same size, same slab — and their index has to follow; everything else keeps
+    // its pre-insertion state
+    if (!applied && !direct) continue;
+    const int off = T.off[tb + c], slot = T.tab[tb + c];
+    const float4* src = direct ? stream_map(pools, st, b, kind, mapCap) + Tsrc.off[tb + c]
+                               : staged + ((size_t)b * 2 + kind) * workCap + st.workIn0[kind][u];
+    float4* dst = ((st.cur[kind] ^ st.compact[kind]) ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap + off;
+    if (src != dst)
+      for (int i0 = threadIdx.x; i0 < n; i0 += 4 * kIndexThreads) {
+        float4 p[4];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) p[k] = src[i]; }
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) p[k] = src[i]; }
 #pragma unroll
-      for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) dst[i] = p[k]; }
-    }
-  if (slot < 0 || n == 0) continue;
-  cta_build_cube_index<kIndexThreads>(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
-                       tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * (kCubeCells + 1), sorted + ((size_t)b * 2 + kind) * mapCap + off,
-                       s_cells, s_w);
+        for (int k = 0; k < 4; ++k) { const int i = i0 + k * kIndexThreads; if (i < n) dst[i] = p[k]; }
+      }
+    if (slot < 0 || n == 0) continue;
+    cta_build_cube_index<kIndexThreads>(src, n, cube_min_coord(c % kCubeW, st.cenW), cube_min_coord((c / kCubeW) % kCubeH, st.cenH),
+                                        cube_min_coord(c / (kCubeW * kCubeH), st.cenD),
+                                        tabPool + (((size_t)b * 2 + kind) * kTabSlots + slot) * kTabInts,
+                                        sorted + ((size_t)b * 2 + kind) * mapCap + off, idx_smem);
   }
 }
 // lm_compact_copy: grid (16, 2, B), block 256: re-pack only — the cubes this scan did not rewrite move to the other pool.
@@ -1369,7 +1502,27 @@ __global__ void lm_export_pose(LMState* __restrict__ stAll, double* __restrict__
   for (int i = 0; i < 7; ++i) o[i] = s.parameters[i];
   for (int i = 0; i < 4; ++i) o[7 + i] = s.q_wmap_wodom[i];
   for (int i = 0; i < 3; ++i) o[11 + i] = s.t_wmap_wodom[i];
+  s.errorEver |= s.error;
   o[14] = s.error; o[15] = s.solved;
+}
+// A frame laserOdometry marks as skipped (laser_odometry.cpp:618-628) only refreshes the high-frequency pose
+// (laser_mapping.cpp:186-190, published at :742-756): q_w_curr_highfreq = q_wmap_wodom * q_wodom_curr,
+// t_w_curr_highfreq = q_wmap_wodom * t_wodom_curr + t_wmap_wodom.  q_w_curr / t_w_curr (st.parameters) and the map stay.
+__global__ void lm_highfreq_pose(LMState* __restrict__ stAll, const LOState* __restrict__ lo, double* __restrict__ pose, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LMState& s = stAll[b];
+  for (int i = 0; i < 4; ++i) s.q_wodom[i] = lo[b].q_w[i];     // :182-183 run for skipped frames too
+  for (int i = 0; i < 3; ++i) s.t_wodom[i] = lo[b].t_w[i];
+  double q[4], t[3];
+  quat_mul(s.q_wmap_wodom, s.q_wodom, q);
+  quat_rotate(s.q_wmap_wodom, s.t_wodom[0], s.t_wodom[1], s.t_wodom[2], t);
+  double* o = pose + (size_t)b * 16;
+  for (int i = 0; i < 4; ++i) o[i] = q[i];
+  for (int i = 0; i < 3; ++i) o[4 + i] = t[i] + s.t_wmap_wodom[i];
+  for (int i = 0; i < 4; ++i) o[7 + i] = s.q_wmap_wodom[i];
+  for (int i = 0; i < 3; ++i) o[11 + i] = s.t_wmap_wodom[i];
+  o[14] = 0.0; o[15] = 0.0;
 }
 __global__ void lm_init_state(LMState* stAll, int B, int tabLimit) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1380,7 +1533,7 @@ __global__ void lm_init_state(LMState* stAll, int B, int tabLimit) {
   for (int i = 0; i < 3; ++i) { s.t_wmap_wodom[i] = 0.0; s.t_wodom[i] = 0.0; }
   s.cenW = 10; s.cenH = 10; s.cenD = 5;                                       // laser_mapping.h:76-78
   s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
-  s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0;
+  s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0; s.errorEver = 0; s.applied[0] = s.applied[1] = 0;
   s.cur[0] = s.cur[1] = 0; s.compact[0] = s.compact[1] = 0; s.repacks[0] = s.repacks[1] = 0;
   s.tabEnd[0] = s.tabEnd[1] = 0; s.buildNum[0] = s.buildNum[1] = 0; s.tabLimit = tabLimit;
   s.trace[0].n_records = s.trace[1].n_records = 0;
@@ -1409,14 +1562,19 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->keyA, B * 2 * lm->workCap * 4); A((void**)&lm->valA, B * 2 * lm->workCap * 4);
   A((void**)&lm->keyB, B * 2 * lm->workCap * 4); A((void**)&lm->valB, B * 2 * lm->workCap * 4);
   A((void**)&lm->concat, B * 2 * lm->workCap * sizeof(float4)); A((void**)&lm->staged, B * 2 * lm->workCap * sizeof(float4));
-  A((void**)&lm->tabPool, B * 2 * (size_t)kTabSlots * (kCubeCells + 1) * sizeof(int));
+  A((void**)&lm->tabPool, B * 2 * (size_t)kTabSlots * kTabInts * sizeof(int));
   A((void**)&lm->entryHead, B * kCubes * sizeof(short));
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
   A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
+  A((void**)&lm->fitType, 2 * B * 2 * cap);
   A((void**)&lm->nnPos, B * 2 * cap * 5 * sizeof(int));
   A((void**)&lm->cubeOf, B * 2 * cap * sizeof(int));
   A((void**)&lm->pose, B * 16 * sizeof(double));
   A((void**)&lm->workOf, B * 2 * kCubes * sizeof(short));
+  if (e != cudaSuccess) return e;
+  // the index builders keep one 16-bit counter per (z-layer, column) cell in shared memory: 65 KB, opt-in (per device)
+  e = cudaFuncSetAttribute(lm_index_build, cudaFuncAttributeMaxDynamicSharedMemorySize, kIndexSmemBytes);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lm_write_back, cudaFuncAttributeMaxDynamicSharedMemorySize, kIndexSmemBytes);
   if (e != cudaSuccess) return e;
   // VLOAM_LM_TAB_SLOTS (tests only): hand out fewer column-table slots so that their recycling runs in a short sequence; the
   // value must exceed the number of occupied valid cubes
@@ -1442,7 +1600,7 @@ void lm_destroy(LMDevice* lm) {
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
-    cudaFree(lm->res); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
+    cudaFree(lm->res); cudaFree(lm->fitType); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
 }
@@ -1457,7 +1615,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   const int B = lm->B, cap = lm->cap, mapCap = lm->mapCap;
   if (skip_frame) {
     // :186-190: a skipped frame only refreshes the high-frequency pose; the map state is untouched
-    VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
+    VB_LAUNCH(prof, K_LM_MISC, st, lm_highfreq_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lo, lm->pose, B));
     return cudaGetLastError();
   }
   // the map = cube slabs in mapPts[LMState::cur] addressed by tables[ts].  lm_prepare writes the shifted tables to
@@ -1477,12 +1635,17 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_VOXEL, st, lm_voxel_stack<<<dim3(2, B), 1024, 0, st>>>(lm->st, hdrCur, cornerLast, surfLast, cap, lineRes, planeRes,
                                                                               lm->stack, lm->keyA, lm->valA, lm->keyB, lm->valB, lm->workCap));
   // C5: column index of the valid cubes that do not have one yet (new in the sub-map, seeded, or after a re-pack)
-  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(32, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_GRID, st, lm_index_build<<<dim3(32, 2, B), kIndexThreads, kIndexSmemBytes, st>>>(lm->st, T_d, pools, mapCap, lm->tabPool, lm->sorted));
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
-    VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
-    VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res));
+    static const int knnOcc = [] { const char* e = getenv("VLOAM_LM_KNN_OCC"); return e ? atoi(e) : 4; }();
+    if (knnOcc == 3)
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_occ3<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
+    else
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
+    VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res,
+                                                                         lm->fitType + (size_t)tp * B * 2 * cap));
     {
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
@@ -1514,10 +1677,16 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_place<<<dim3(2, B), 1024, 0, st>>>(lm->st, T_d, T_s, lm->workOf, lm->liveList, lm->liveNum, mapCap));
   VB_LAUNCH(prof, K_LM_PLACE, st, lm_compact_copy<<<dim3(16, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], lm->cubeOff[ts], lm->cubeCnt[ts], lm->liveList,
                                                                                    lm->liveNum, pools, mapCap));
-  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(32, 2, B), kIndexThreads, 0, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
+  VB_LAUNCH(prof, K_LM_PLACE, st, lm_write_back<<<dim3(32, 2, B), kIndexThreads, kIndexSmemBytes, st>>>(lm->st, T_d, T_s, pools, mapCap, lm->staged, lm->workCap, lm->tabPool, lm->sorted));
   VB_LAUNCH(prof, K_LM_MISC, st, lm_export_pose<<<(B + 127) / 128, 128, 0, st>>>(lm->st, lm->pose, B));
   lm->ran = true;
   return cudaGetLastError();
+}
+
+static cudaError_t lm_fetch_state(LMDevice* lm, cudaStream_t st, int stream, LMState* out) {
+  cudaError_t e = cudaMemcpyAsync(out, lm->st + stream, sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
 }
 
 cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out) {
@@ -1528,14 +1697,41 @@ cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out) {
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
   if (e != cudaSuccess) return e;
   for (int b = 0; b < lm->B; ++b) for (int i = 0; i < 14; ++i) pose_out[(size_t)b * 14 + i] = h[(size_t)b * 16 + i];
-  for (int b = 0; b < lm->B; ++b) if (h[(size_t)b * 16 + 14] != 0.0) return cudaErrorInvalidValue;  // capacity / work-list overflow
+  return cudaSuccess;     // per-stream map errors: lm_get_status
+}
+
+// status[B][2] = error bits of the last mapped scan, OR of the error bits of every scan so far
+cudaError_t lm_get_status(LMDevice* lm, cudaStream_t st, int* status) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  std::vector<LMState> h(lm->B);
+  e = cudaMemcpyAsync(h.data(), lm->st, h.size() * sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  for (int b = 0; b < lm->B; ++b) { status[2 * b] = h[b].error; status[2 * b + 1] = h[b].errorEver | h[b].error; }
   return cudaSuccess;
 }
 
-static cudaError_t lm_fetch_state(LMDevice* lm, cudaStream_t st, int stream, LMState* out) {
-  cudaError_t e = cudaMemcpyAsync(out, lm->st + stream, sizeof(LMState), cudaMemcpyDeviceToHost, st);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  return e;
+// Queries (indices into the down-sampled corner / surf stack) that produced a residual block in outer pass `pass` of the last scan.
+cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  LMState S;
+  e = lm_fetch_state(lm, st, stream, &S);
+  if (e != cudaSuccess) return e;
+  int n = 0;
+  if (lm->ran && S.solved && S.trace[pass].n_records > 0) {
+    std::vector<uint8_t> t((size_t)S.stackNum[kind]);
+    if (!t.empty()) {
+      e = cudaMemcpyAsync(t.data(), lm->fitType + (((size_t)pass * lm->B + stream) * 2 + kind) * lm->cap, t.size(), cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+      if (e != cudaSuccess) return e;
+    }
+    for (size_t i = 0; i < t.size(); ++i)
+      if (t[i]) { if (out && n < capacity) out[n] = (int)i; ++n; }
+  }
+  if (n_out) *n_out = n;
+  return cudaSuccess;
 }
 
 cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out) {
@@ -1584,7 +1780,7 @@ cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int
   }
   // a fresh slab from the pool's bump allocator (a slab the cube may have had is reclaimed by the next re-pack); the
   // content is arbitrary, so the cube is not marked as a fixed point of its voxel filter
-  if ((long long)S.poolEnd[kind] + n > lm->mapCap) return cudaErrorInvalidValue;
+  if ((long long)S.poolEnd[kind] + n > lm->mapCap) return cudaErrorMemoryAllocation;   // map_capacity_points exceeded (capi: VLOAM_E_CAPACITY)
   const size_t tb = ((size_t)stream * 2 + kind) * kCubes + cube;
   const int off = S.poolEnd[kind], zero = 0, none = -1;
   if (n) e = cudaMemcpyAsync(lm->mapPts[S.cur[kind]] + ((size_t)stream * 2 + kind) * lm->mapCap + off, xyzi, (size_t)n * 16, cudaMemcpyHostToDevice, st);

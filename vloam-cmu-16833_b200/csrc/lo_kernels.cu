@@ -735,6 +735,18 @@ void launch_lo_set_motion(Profiler* prof, cudaStream_t st, LOState* lo, const do
   VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, motion, B));
 }
 
+// Checkpoint / resume: overwrite the accumulated odometry pose q_w_curr / t_w_curr (laser_odometry.cpp:80-81) — a stream
+// that starts in the middle of a trajectory.  pose: [B][7] = q(xyzw), t.
+__global__ void lo_set_pose(LOState* lo, const double* __restrict__ pose, int B) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  for (int i = 0; i < 4; ++i) lo[b].q_w[i] = pose[b * 7 + i];
+  for (int i = 0; i < 3; ++i) lo[b].t_w[i] = pose[b * 7 + 4 + i];
+}
+void launch_lo_set_pose(Profiler* prof, cudaStream_t st, LOState* lo, const double* pose, int B) {
+  VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_pose<<<(B + 127) / 128, 128, 0, st>>>(lo, pose, B));
+}
+
 void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B) {
   VB_LAUNCH(prof, K_LO_INIT, st, lo_init_state<<<(B + 127) / 128, 128, 0, st>>>(lo, B));
 }
@@ -745,24 +757,27 @@ static bool lo_use_brute() {
   return v == 1;
 }
 
+constexpr int kLoSolveDynSmem = (kMaxSharp + kMaxFlat) * (4 * (int)sizeof(double) + 1);
+// Opt-in shared-memory sizes are per-device function attributes: set (and checked) once per context, on its device.
+cudaError_t lo_prepare_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCap + 1) * (int)sizeof(int));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lo_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
+  return e;
+}
+
 void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
                           const float4* lessFlat, const LOGrid* g) {
-  static bool attr_set = false;
   const int smem = (kGridCap + 1) * (int)sizeof(int);
-  if (!attr_set) { cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, smem); attr_set = true; }
   VB_LAUNCH(prof, K_LO_BUILD_GRID, st, lo_build_grid<<<dim3(2, B), 1024, smem, st>>>(hdrCur, lessSharp, lessFlat, cap, g->hdr, g->cellStart, g->cursor,
                                                                                   g->sorted[0], g->sorted[1]));
 }
-
-constexpr int kLoSolveDynSmem = (kMaxSharp + kMaxFlat) * (4 * (int)sizeof(double) + 1);
 
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
                     const ShardView* shard) {
   const ShardView sv = shard ? *shard : ShardView();
-  const cudaError_t attr = cudaFuncSetAttribute(lo_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
-  (void)attr;
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
   if (lo_use_brute() && sv.world <= 1)
     VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(

@@ -87,11 +87,15 @@ constexpr double kPi = 3.14159265358979323846;
 // sr_find_ends: grid (B), block kEndsThreads.
 constexpr int kEndsThreads = 1024;
 __global__ void __launch_bounds__(kEndsThreads) sr_find_ends(const float* __restrict__ xyz, int stride, size_t slab_floats,
-                                                     const int* __restrict__ n_points, float min_range,
+                                                     const int* __restrict__ n_points, int cap, float min_range,
                                                      SRHeader* __restrict__ hdr) {
   const int b = blockIdx.x;
   const float* p = xyz + (size_t)b * slab_floats;
-  const int n = n_points[b];
+  // A count beyond the handle's capacity (or the caller's slab) is clamped and reported (kStatusCapacity): the device entry
+  // point cannot validate counts that live in device memory, and every later kernel sizes its loops from h.n_in.
+  const int nmax = (int)min((size_t)cap, slab_floats / (size_t)stride);
+  const int nraw = n_points[b];
+  const int n = min(max(nraw, 0), nmax);
   SRHeader& h = hdr[b];
   const float thres2 = __fmul_rn(min_range, min_range);
   __shared__ int s_first, s_last;
@@ -133,9 +137,10 @@ __global__ void __launch_bounds__(kEndsThreads) sr_find_ends(const float* __rest
     h.halfIdx = 0x7fffffff;
     h.cloudSize = 0;
     h.nSharp = h.nLessSharp = h.nFlat = h.nLessFlat = 0;
+    const int capBit = nraw > nmax ? kStatusCapacity : 0;
     if (s_last < 0) {
       h.firstValid = -1; h.lastValid = -1; h.startOri = 0.f; h.endOri = 0.f;
-      h.status = kStatusEmpty;
+      h.status = kStatusEmpty | capBit;
     } else {
       h.firstValid = s_first; h.lastValid = s_last;
       const float x0 = p[(size_t)s_first * stride], y0 = p[(size_t)s_first * stride + 1];
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kEndsThreads) sr_find_ends(const float* __rest
         endOri = (float)((double)endOri + 2 * kPi);
       }
       h.startOri = startOri; h.endOri = endOri;
-      h.status = 0;
+      h.status = capBit;
     }
   }
 }
@@ -902,6 +907,14 @@ __global__ void __launch_bounds__(256) sr_pack(SRHeader* __restrict__ hdr, const
 }
 
 // ---------------------------------------------------------------------------------------------
+// Opt-in shared-memory sizes are per-device function attributes: set (and checked) once per context, on its device.
+cudaError_t sr_prepare_device(int device) {
+  cudaError_t e = cudaSetDevice(device);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sr_less_flat_voxel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<2048>));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(sr_less_flat_voxel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<4096>));
+  return e;
+}
+
 // host-side launcher (called from capi.cu)
 void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, const float* xyz, int stride, size_t slab_floats,
                               const int* n_points_dev, float min_range, int n_scans, SRHeader* hdr, uint8_t* ring8,
@@ -909,13 +922,7 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
                               float4* lessFlatStage, float4* sharp, int* sharpIdx, float4* lessSharp, int* lessSharpIdx,
                               float4* flat, int* flatIdx, float4* lessFlat) {
   const int nblk = (cap + kClassifyBlock - 1) / kClassifyBlock;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(sr_less_flat_voxel<2048>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<2048>));
-    cudaFuncSetAttribute(sr_less_flat_voxel<4096>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxelSmem<4096>));
-    attr_set = true;
-  }
-  VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, kEndsThreads, 0, st>>>(xyz, stride, slab_floats, n_points_dev, min_range, hdr));
+  VB_LAUNCH(prof, K_SR_FIND_ENDS, st, sr_find_ends<<<B, kEndsThreads, 0, st>>>(xyz, stride, slab_floats, n_points_dev, cap, min_range, hdr));
   VB_LAUNCH(prof, K_SR_CLASSIFY, st, sr_classify<<<dim3(nblk, B), 256, 0, st>>>(xyz, stride, slab_floats, min_range, n_scans, hdr, ring8, cap, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCAN, st, sr_scan<<<B, 64, 0, st>>>(hdr, blockHist, nblk));
   VB_LAUNCH(prof, K_SR_SCATTER, st, sr_scatter<<<dim3(nblk, B), 1024, 0, st>>>(xyz, stride, slab_floats, hdr, ring8, cap, blockHist, nblk, cloud));

@@ -40,11 +40,15 @@ struct VOState {
   SolveTrace trace;
 };
 
+// Counts handed in through device memory (vloam_vo_process_cloud_device, e.g. the lidar handle's input buffer) cannot be
+// validated on the host: every kernel clamps them to this handle's capacity, the excess points are ignored.
+__device__ __forceinline__ int vo_clamped_count(const int* __restrict__ n_points, int b, int nmax) { return min(max(n_points[b], 0), nmax); }
+
 // grid (ceil(cap / 256), B), block 256
 __global__ void __launch_bounds__(256) vo_project(const float* __restrict__ xyz, int stride, size_t slab_floats, const int* __restrict__ n_points,
-                                                   VOCalib C, int cap, float4* __restrict__ uvd, unsigned* __restrict__ key, unsigned* __restrict__ val) {
+                                                   VOCalib C, int cap, int nmax, float4* __restrict__ uvd, unsigned* __restrict__ key, unsigned* __restrict__ val) {
   const int b = blockIdx.y, i = blockIdx.x * 256 + threadIdx.x;
-  const int n = n_points[b];
+  const int n = vo_clamped_count(n_points, b, nmax);
   if (i >= n) return;
   const float* p = xyz + (size_t)b * slab_floats + (size_t)i * stride;
   const float X[4] = {p[0], p[1], p[2], 1.0f};
@@ -68,18 +72,18 @@ __global__ void __launch_bounds__(256) vo_project(const float* __restrict__ xyz,
   val[(size_t)b * cap + i] = (unsigned)i;
 }
 // grid (B), block 1024: stable sort of the point indices by bucket id (result left in kA / vA)
-__global__ void __launch_bounds__(1024) vo_bucket_sort(const int* __restrict__ n_points, int cap, unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB) {
+__global__ void __launch_bounds__(1024) vo_bucket_sort(const int* __restrict__ n_points, int cap, int nmax, unsigned* kA, unsigned* vA, unsigned* kB, unsigned* vB) {
   __shared__ SortSmem S;
   const int b = blockIdx.x;
-  cta_radix_sort(kA + (size_t)b * cap, vA + (size_t)b * cap, kB + (size_t)b * cap, vB + (size_t)b * cap, n_points[b], 16, S);
+  cta_radix_sort(kA + (size_t)b * cap, vA + (size_t)b * cap, kB + (size_t)b * cap, vB + (size_t)b * cap, vo_clamped_count(n_points, b, nmax), 16, S);
 }
 // grid (ceil(kBuckets / 256), B), block 256: one thread folds one bucket in input order
-__global__ void __launch_bounds__(256) vo_bucket_fold(const int* __restrict__ n_points, int cap, const unsigned* __restrict__ key,
+__global__ void __launch_bounds__(256) vo_bucket_fold(const int* __restrict__ n_points, int cap, int nmax, const unsigned* __restrict__ key,
                                                        const unsigned* __restrict__ val, const float4* __restrict__ uvd, float* __restrict__ bx,
                                                        float* __restrict__ by, float* __restrict__ bd, int* __restrict__ bc) {
   const int b = blockIdx.y, bucket = blockIdx.x * 256 + threadIdx.x;
   if (bucket >= kBuckets) return;
-  const int n = n_points[b];
+  const int n = vo_clamped_count(n_points, b, nmax);
   const unsigned* k = key + (size_t)b * cap;
   const unsigned* v = val + (size_t)b * cap;
   int lo = 0, hi = n;  // first position with key >= bucket
@@ -536,10 +540,11 @@ static int vo_run_cloud(vloam_vo* h, const float* xyz_dev, const int* n_dev, int
   const int s = h->slot();
   cudaStream_t st = c->stream;
   (void)cudaGetLastError();   // a stale, unrelated error must not be blamed on the launches below
+  const int nmax = (int)(slab_points < (size_t)h->cap ? slab_points : (size_t)h->cap);   // counts are clamped to this in every kernel
   VB_LAUNCH(&c->prof, K_VO_PROJECT, st, vo_project<<<dim3(h->cap / 256, h->B), 256, 0, st>>>(xyz_dev, stride, slab_points * (size_t)stride, n_dev, h->calib, h->cap,
-                                                                                           h->d_uvd, h->kA, h->vA));
-  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_sort<<<h->B, 1024, 0, st>>>(n_dev, h->cap, h->kA, h->vA, h->kB, h->vB));
-  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_fold<<<dim3((kBuckets + 255) / 256, h->B), 256, 0, st>>>(n_dev, h->cap, h->kA, h->vA, h->d_uvd, h->bx[s], h->by[s],
+                                                                                           nmax, h->d_uvd, h->kA, h->vA));
+  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_sort<<<h->B, 1024, 0, st>>>(n_dev, h->cap, nmax, h->kA, h->vA, h->kB, h->vB));
+  VB_LAUNCH(&c->prof, K_VO_BUCKET, st, vo_bucket_fold<<<dim3((kBuckets + 255) / 256, h->B), 256, 0, st>>>(n_dev, h->cap, nmax, h->kA, h->vA, h->d_uvd, h->bx[s], h->by[s],
                                                                                                         h->bd[s], h->bc[s]));
   VCU(c, cudaGetLastError());
   return VLOAM_OK;
