@@ -35,14 +35,20 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 N_RINGS, N_COLS = 64, 2048
-POOL_SCANS = 4          # consecutive scans per base sequence, visited ping-pong 0 1 2 3 2 1 0 ...
-N_BASE = 4              # distinct base sequences, tiled across the batch
+TRAJ_SCANS = 64         # consecutive scans of every base sequence: a forward drive of 32..96 m (5..15 m/s at 10 Hz); a run of up
+                        # to 64 steps never replays a scan, a longer one drives the same road back (63, 62, ...) and forth
+N_BASE = 4              # distinct base sequences per rank, tiled across the batch
 BENCH_SEED = 1234
 
 
 def pingpong(i: int, n: int) -> int:
     p = i % (2 * n - 2)
     return p if p < n else 2 * n - 2 - p
+
+
+def scan_index(i: int) -> int:
+    """Trajectory scan visited at step i (0, 1, ..., 63, 62, ...)."""
+    return pingpong(i, TRAJ_SCANS)
 
 
 def load_peaks():
@@ -129,14 +135,16 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons), "source": "nvidia-smi"}
 
 
-def make_base_scans(rank: int, with_streams: bool = False):
-    """N_BASE sequences x POOL_SCANS scans, float32 (n, 3), NaN = no return."""
+def make_base_scans(rank: int, needed, world: int = 1, batch: int = N_BASE, with_streams: bool = False):
+    """N_BASE sequences of this rank; seqs[i][k] = scan k (float32 (n, 3), NaN = no return) for every k in `needed`."""
+    from vloam_b200 import dist as D
     from vloam_b200 import synth
     seqs, streams = [], []
+    first = D.shard_streams(world * batch, world, rank)[0] if batch > 0 else 0     # this rank's first global stream
     for i in range(N_BASE):
-        s = synth.ScanStream(BENCH_SEED + 16 * rank + i, n_cols=N_COLS)
+        s = synth.ScanStream(D.stream_seed(BENCH_SEED, first + i, N_BASE) if world > 1 else BENCH_SEED + i, n_cols=N_COLS)
         streams.append(s)
-        seqs.append([s.scan(k) for k in range(POOL_SCANS)])
+        seqs.append({k: s.scan(k) for k in needed})
     return (seqs, streams) if with_streams else seqs
 
 
@@ -191,13 +199,17 @@ class CpuChain:
     def timings(self):
         return dict(self.t)
 
+    def lm_iterations(self):
+        """LM iterations the oracle ran in each outer pass of the last mapped scan (iteration records minus the initial one)."""
+        return [int(t["iterations"].shape[0]) - 1 for t in self.lm.trace()]
+
 
 def cpu_matches(scan_stream, i):
     """(prev_uv, curr_uv) for replay step i of one base sequence (None for the first frame)."""
     from vloam_b200 import synth
     if i == 0:
         return None
-    kp, k = pingpong(i - 1, POOL_SCANS), pingpong(i, POOL_SCANS)
+    kp, k = scan_index(i - 1), scan_index(i)
     pu, cu, _ = synth.make_matches(scan_stream, max(kp, k), n_matches=800)
     return (pu, cu) if k > kp else (cu, pu)
 
@@ -212,9 +224,22 @@ WORKLOAD_NAME = {
 
 
 # --------------------------------------------------------------------------------------------- reference arm (CPU)
+def config_dict(args, streams_per_gpu, handles, world, do_map, extra=None):
+    """The `config` object both arms print (same keys, same values for the same command line)."""
+    c = {"workload": WORKLOAD_NAME[args.workload][1], "streams_per_gpu": streams_per_gpu, "handles": handles,
+         "points_per_scan": N_RINGS * N_COLS, "lo_passes": 2, "lo_iterations_per_pass": 4, "lm_passes": 2,
+         "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0,
+         "trajectory": f"{N_BASE} seeded base sequences x {TRAJ_SCANS} consecutive scans (forward drive, no replay within {TRAJ_SCANS} steps), "
+                       "tiled across the streams"}
+    if extra:
+        c.update(extra)
+    return c
+
+
 def run_reference(args, rank):
     """The reference's CPU path (oracle port: the reference needs ROS/PCL/Ceres/Eigen, none installed) on all host
-    threads: one independent stream per thread; a step = one scan on every thread."""
+    threads: one independent stream per thread; a step = one scan on every thread.  Same trajectory, same pre-built map,
+    same iteration limits as the B200 arm."""
     if rank != 0:
         return
     from oracle import pyoracle as O
@@ -222,15 +247,16 @@ def run_reference(args, rank):
     O.build()
     T = max(1, len(os.sched_getaffinity(0)))
     do_map = args.workload in ("sr_lo_lm", "vloam")
-    seqs, scan_streams = make_base_scans(0, with_streams=True)
+    n_steps = args.warmup + args.steps
+    needed = sorted({scan_index(i) for i in range(n_steps)})
+    seqs, scan_streams = make_base_scans(0, needed, with_streams=True)
     cubes = synth_map_cubes(args.map_points, BENCH_SEED) if do_map else {}
     pipes = [CpuChain(O, args.workload, cubes, args.lm_iterations) for _ in range(T)]
-    n_steps = args.warmup + args.steps
     mt = {(t % N_BASE, i): cpu_matches(scan_streams[t % N_BASE], i) for t in range(min(T, N_BASE)) for i in range(n_steps)} \
         if args.workload == "vloam" else {}
 
     def one(t, i):
-        pipes[t].process(seqs[t % N_BASE][pingpong(i, POOL_SCANS)], mt.get((t % N_BASE, i)))
+        pipes[t].process(seqs[t % N_BASE][scan_index(i)], mt.get((t % N_BASE, i)))
 
     with ThreadPoolExecutor(T) as ex:
         for i in range(args.warmup):
@@ -241,17 +267,18 @@ def run_reference(args, rank):
         dt = time.perf_counter() - t0
     value = T * args.steps / dt
     tm = pipes[0].timings()
+    its = pipes[0].lm_iterations() if do_map else None
     line = {
         "impl": "reference", "metric": "scans/sec (HDL-64, 64x2048 pts) " + WORKLOAD_NAME[args.workload][0],
         "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": "synthetic",
-        "config": {"workload": WORKLOAD_NAME[args.workload][1], "streams": T, "points_per_scan": N_RINGS * N_COLS,
-                   "lo_passes": 2, "lo_iterations_per_pass": 4, "lm_passes": 2, "lm_iterations_per_pass": args.lm_iterations,
-                   "map_points": args.map_points if do_map else 0},
+        "config": config_dict(args, args.batch, args.handles, 1, do_map),
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
-                         "sample": f"{T} threads x {args.steps} scans, one stream per thread; per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
-                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"},
+                         "sample": f"{T} threads x {args.steps} scans, one stream per thread (the GPU arm's streams_per_gpu streams are a batch "
+                                   f"dimension this CPU path does not have); per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
+                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"
+                                   + (f"; LM iterations executed in the last scan's passes: {its}" if its else "")},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -259,32 +286,8 @@ def run_reference(args, rank):
 
 
 def synth_map_cubes(n_points: int, seed: int):
-    """A synthetic pre-built map for configs[2]: n_points surf points (one per 0.8 m voxel —
-    the map's own resolution — jittered inside the voxel, on the ground plane and on stacked horizontal layers, so the
-    map keeps its size under the reference's per-scan re-filter) plus 10 % as many corner points (vertical poles), inside
-    the 5 x 5 x 3 cube window around the origin.  Returns {(kind, cube_index): (n, 4) float32}."""
-    rng = np.random.default_rng(seed)
-    k = np.arange(-155, 155)
-    per_layer = k.size * k.size
-    layers = max(1, int(np.ceil(n_points / per_layer)))
-    pts = []
-    for l in range(layers):
-        gx, gy = np.meshgrid((k + 0.5) * 0.8, (k + 0.5) * 0.8)
-        z = -1.73 + 7.0 * l
-        p = np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, z)] + rng.uniform(-0.3, 0.3, (gx.size, 3)) * [1, 1, 0.02]
-        pts.append(p)
-    surf = np.concatenate(pts)[:n_points].astype(np.float32)
-    ncor = max(1000, n_points // 10)
-    cx, cy = rng.uniform(-120, 120, ncor // 20), rng.uniform(-120, 120, ncor // 20)
-    corner = np.c_[np.repeat(cx, 20), np.repeat(cy, 20), np.tile(np.arange(20) * 0.4 - 1.7, ncor // 20)].astype(np.float32)
-    out = {}
-    for kind, cloud in ((0, corner), (1, surf)):
-        ci = (np.floor((cloud[:, 0] + 25.0) / 50.0).astype(int) + 10) + 21 * (np.floor((cloud[:, 1] + 25.0) / 50.0).astype(int) + 10) \
-            + 441 * (np.floor((cloud[:, 2] + 25.0) / 50.0).astype(int) + 5)
-        for c in np.unique(ci):
-            sel = cloud[ci == c]
-            out[(kind, int(c))] = np.c_[sel, np.zeros(len(sel), np.float32)].astype(np.float32)
-    return out
+    from vloam_b200 import synth
+    return synth.map_cubes(n_points, seed)
 
 
 # --------------------------------------------------------------------------------------------- our arm (B200)
@@ -319,7 +322,9 @@ def algorithmic_bytes(kernel, c):
         "lm_prepare": 0, "lm_misc": 0,
         "lm_voxel": (c["nLS"] + c["nLF"]) * (16 + 16),
         "lm_index": 0,                                      # only cubes without a column index are (re)indexed: none in steady state
-        "lm_associate": c.get("S", 0) * (16 + 20) + c.get("S", 0) * 9 * 8 * 16,   # query + 5 positions; 3 x 3 columns of ~8 points
+        # per query: the point (16 B), five positions out (20 B), <= 6 run look-ups (2 x 2 B each + a layer start) and the
+        # candidates of its runs (16 B each; count measured by the statistics pass, ~13 on the benchmark map)
+        "lm_associate": c.get("S", 0) * (16 + 20 + 6 * 8 + c.get("cand", 13.0) * 16),
         "lm_fit": c.get("S", 0) * (16 + 20 + 5 * 16 + 72),
         "lm_solve": c.get("S", 0) * 80,
         "lm_insert": c.get("S", 0) * 48,
@@ -329,61 +334,97 @@ def algorithmic_bytes(kernel, c):
     return table.get(kernel, 0)
 
 
+def bind_near_gpu(local_rank: int):
+    """Best effort: run this process (and so first-touch its pinned host buffers) on the CPUs of the GPU's NUMA node.
+    Returns a short description for the JSON line."""
+    try:
+        import torch
+        bus = torch.cuda.get_device_properties(local_rank).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(local_rank), "pci_domain_id", 0)
+        devid = torch.cuda.get_device_properties(local_rank).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{devid:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return "numa node unknown"
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return f"gpu on numa node {node}, none of its cpus allowed"
+        os.sched_setaffinity(0, allowed)
+        return f"bound to {len(allowed)} cpus of numa node {node}"
+    except Exception as e:          # sysfs not visible in the container, ...
+        return f"not bound ({type(e).__name__})"
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import vloam_b200 as V
+    from vloam_b200 import dist as D
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device — the B200 path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa = bind_near_gpu(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        if not os.environ.get("VLOAM_KEEP_NCCL_DEBUG"):
-            os.environ["NCCL_DEBUG"] = "WARN"      # NCCL's version banner goes to stdout, which carries exactly one JSON line
+        # NCCL's own log lines (version banner, the `nranks` evidence at NCCL_DEBUG=INFO) go to stderr: stdout carries exactly
+        # one JSON line
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
     do_vo = args.workload == "vloam"
     do_map = args.workload in ("sr_lo_lm", "vloam")
     cap = N_RINGS * N_COLS
     point = args.parallelism == "point" and world > 1
+    n_total = args.warmup + 2 * args.steps + 2           # timed leg + per-kernel timing pass + statistics pass
+    needed = sorted({scan_index(i) for i in range(n_total)})
     # point-sharded: every rank replays the SAME streams (rank-independent seeds) and owns a slice of their correspondences
-    seqs, scan_streams = make_base_scans(0 if point else rank, with_streams=True)
+    t_gen = time.perf_counter()
+    seqs, scan_streams = make_base_scans(0 if point else rank, needed, 1 if point else world, B, with_streams=True)
+    t_gen = time.perf_counter() - t_gen
 
-    # pools: POOL_SCANS tensors of [B, cap, 3]; stream b replays base sequence b % N_BASE
-    host_pool, dev_pool = [], []
-    for k in range(POOL_SCANS):
-        h = torch.empty((B, cap, 3), dtype=torch.float32).pin_memory()
-        hv = h.numpy()
-        for b in range(B):
-            hv[b] = seqs[b % N_BASE][k]
-        host_pool.append(h)
-        dev_pool.append(h.to(dev, non_blocking=True))
+    # Scan pools.  Host: the N_BASE x len(needed) distinct scans once, pinned; a stream's scan is uploaded from the base
+    # sequence it replays (one host buffer per stream, vloam_scan_registration_ptrs).  Device: [B, cap, 3] per trajectory
+    # step (stream b replays base sequence b % N_BASE), gathered on the device from the uploaded base scans.
+    slot_of = {k: j for j, k in enumerate(needed)}
+    host_base = torch.empty((N_BASE, len(needed), cap, 3), dtype=torch.float32).pin_memory()
+    hb = host_base.numpy()
+    for i in range(N_BASE):
+        for k in needed:
+            hb[i, slot_of[k]] = seqs[i][k]
+    dev_base = host_base.to(dev, non_blocking=True)
+    sel = torch.arange(B, device=dev) % N_BASE
+    dev_pool = {k: dev_base[sel, slot_of[k]].contiguous() for k in needed}
     n_host = np.full(B, cap, np.int32)
     n_dev = torch.from_numpy(n_host).to(dev)
-    pool_bytes = POOL_SCANS * B * cap * 12
+    pool_bytes = len(needed) * B * cap * 12
+    base_ptr = host_base.data_ptr()
+    host_ptrs = {k: np.array([base_ptr + (((b % N_BASE) * len(needed) + slot_of[k]) * cap * 12) for b in range(B)], np.uint64) for k in needed}
 
-    # configs[3]: matched keypoint pixels for every (previous scan -> current scan) pair the ping-pong replay visits
+    # configs[3]: matched keypoint pixels for every (previous scan -> current scan) pair the run visits
     M = 1024
     match_host, match_dev, velo_T_cam0, calib = {}, {}, None, None
     if do_vo:
         from vloam_b200 import synth
         calib = synth.kitti_like_calibration()
         velo_T_cam0 = np.linalg.inv(calib[0].astype(np.float64))
-        base = {}
-        for s_i, sst in enumerate(scan_streams):
-            for k in range(1, POOL_SCANS):
-                pu, cu, _ = synth.make_matches(sst, k, n_matches=800)
-                base[(s_i, k - 1, k)] = (pu, cu)
-                base[(s_i, k, k - 1)] = (cu, pu)       # the replay also runs backwards in time
-        for (kp, k) in {(kp, k) for (_, kp, k) in base}:
+        pairs = sorted({(scan_index(i - 1), scan_index(i)) for i in range(1, n_total)})
+        for (kp, k) in pairs:
             hp = torch.zeros((B, M, 2), dtype=torch.float32).pin_memory()
             hc = torch.zeros((B, M, 2), dtype=torch.float32).pin_memory()
             hn = torch.zeros((B,), dtype=torch.int32).pin_memory()
+            per_base = []
+            for sst in scan_streams:
+                pu, cu, _ = synth.make_matches(sst, max(kp, k), n_matches=800)
+                per_base.append((pu, cu) if k > kp else (cu, pu))      # a long run also drives backwards in time
             for b in range(B):
-                pu, cu = base[(b % N_BASE, kp, k)]
+                pu, cu = per_base[b % N_BASE]
                 hp[b, :len(pu)] = torch.from_numpy(pu); hc[b, :len(cu)] = torch.from_numpy(cu); hn[b] = len(pu)
             match_host[(kp, k)] = (hp, hc, hn)
             match_dev[(kp, k)] = (hp.to(dev), hc.to(dev), hn.to(dev))
@@ -424,12 +465,12 @@ def run_ours(args, rank, world, local_rank):
                 self.vo.exportLOPrior(velo_T_cam0, self.prior)
 
         def step_dev(self, i):
-            k = pingpong(i, POOL_SCANS)
+            k = scan_index(i)
             sl = slice(self.b0, self.b1)
             self.lom.reset()
             self.lom.scanRegistrationDevice(dev_pool[k][sl], n_dev[sl], 3, cap)
             if do_vo:
-                pu, cu, nm = match_dev[(pingpong(i - 1, POOL_SCANS), k)] if i > 0 else (None, None, None)
+                pu, cu, nm = match_dev[(scan_index(i - 1), k)] if i > 0 else (None, None, None)
                 self._vo(i, dev_pool[k][sl], n_dev[sl], 3, cap, None if pu is None else pu[sl], None if cu is None else cu[sl],
                          None if nm is None else nm[sl])
             self.lom.laserOdometryIO(prior=self.prior, fetch=False)
@@ -440,14 +481,14 @@ def run_ours(args, rank, world, local_rank):
         def step_host(self, i, first):
             """One scan in flight: enqueue scan i (pinned host -> device upload on the copy stream + kernels), then read
             scan i-1's poses (device -> host) while scan i runs, so uploads overlap compute."""
-            k = pingpong(i, POOL_SCANS)
+            k = scan_index(i)
             sl = slice(self.b0, self.b1)
             self.lom.reset()
-            self.lom.scanRegistrationIO(host_pool[k][sl], n_host[sl])
+            self.lom.scanRegistrationPtrs(host_ptrs[k][sl], n_host[sl], 3, keep=host_base)
             if do_vo:
                 xyz, n, stride, slab = self.lom.input_device()          # the cloud is uploaded once and read twice
                 if i > 0:
-                    hp, hc, hn = match_host[(pingpong(i - 1, POOL_SCANS), k)]
+                    hp, hc, hn = match_host[(scan_index(i - 1), k)]
                     self.uv[0].copy_(hp[sl], non_blocking=True); self.uv[1].copy_(hc[sl], non_blocking=True)
                     self.nm.copy_(hn[sl], non_blocking=True)
                 self._vo(i, xyz, n, stride, slab, self.uv[0], self.uv[1], self.nm)
@@ -469,10 +510,17 @@ def run_ours(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    from vloam_b200 import dist as D
-
     def max_over_ranks(ms):
         return D.max_over_ranks(ms, dist, dev)
+
+    def all_ranks(x):
+        """[x of rank 0, x of rank 1, ...] (floats)."""
+        if dist is None:
+            return [float(x)]
+        t = torch.tensor([float(x)], dtype=torch.float64, device=dev)
+        out = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(out, t)
+        return [float(o.item()) for o in out]
 
     try:
         gpu_uuid = "GPU-" + str(torch.cuda.get_device_properties(local_rank).uuid)
@@ -492,7 +540,6 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(streams[h]):
             groups.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
     loms = [g.lom for g in groups]
-    from vloam_b200 import dist as D
     if point:
         D.enable_point_sharding(groups[0].lom, dist, dev)
 
@@ -509,11 +556,15 @@ def run_ours(args, rank, world, local_rank):
             ev.record(s_)
             stream.wait_event(ev)
 
+    def counters():
+        return np.concatenate([hd.lm_counters() for hd in loms]) if do_map else None
+
     with torch.cuda.stream(stream):
         for i in range(args.warmup):
             step_dev(i)
         barrier()
         launches0 = sum(c_.launch_count for c_ in ctxs)
+        cnt0 = counters()
         if rank == 0:
             sampler.start()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -525,11 +576,15 @@ def run_ours(args, rank, world, local_rank):
         join_streams()
         e1.record(stream)
         barrier()
-        ms_dev = max_over_ranks(e0.elapsed_time(e1))
+        ms_rank = e0.elapsed_time(e1)
+        ms_ranks = all_ranks(ms_rank)
+        ms_dev = max(ms_ranks)
         clocks = sampler.stop() if rank == 0 else None
         launches = sum(c_.launch_count for c_ in ctxs) - launches0
+        cnt1 = counters()
         counts = np.concatenate([hd.feature_counts() for hd in loms]).astype(np.int64)
         pose_dev = {kk: np.concatenate([hd.lo_pose()[kk] for hd in loms]) for kk in loms[0].lo_pose()}
+        lm_status = np.concatenate([hd.lm_status() for hd in loms]) if do_map else np.zeros((B, 2), np.int32)
         # per-kernel durations: the same steps again with a CUDA-event pair around every launch; with H > 1 the groups
         # are run one after the other here so that the per-kernel times are not inflated by overlap
         for c_ in ctxs:
@@ -544,11 +599,27 @@ def run_ours(args, rank, world, local_rank):
                 a = ktimes.get(kname, (0.0, 0))
                 ktimes[kname] = (a[0] + ms_k, a[1] + n_k)
             c_.enable_timing(False)
-    value = (1 if point else world) * B * args.steps / (ms_dev * 1e-3)
+        # statistics pass (untimed): candidate points the 5-NN search tests per query
+        knn = None
+        if do_map:
+            for hd in loms:
+                hd.set_debug_stats(True)
+            c_a = counters()
+            for i in range(args.warmup + 2 * args.steps, args.warmup + 2 * args.steps + 2):
+                step_dev(i)
+            barrier()
+            c_b = counters()
+            for hd in loms:
+                hd.set_debug_stats(False)
+            dq, dc = float((c_b[:, 16] - c_a[:, 16]).sum()), float((c_b[:, 17] - c_a[:, 17]).sum())
+            knn = {"queries": dq, "candidates": dc, "candidates_per_query": dc / max(dq, 1.0)}
+    # whole-job units / max-over-ranks time (helpers shared with the CPU test tests/test_dist_gloo.py)
+    value = (B * args.steps / (ms_dev * 1e-3)) if point else D.aggregate_throughput(B * args.steps, ms_rank, dist, dev)
 
     if args.legs == "device":
         if rank == 0:
             print(json.dumps({"value": value, "ms_per_step": ms_dev / args.steps, "gpu_launches": int(launches), "legs": "device",
+                              "knn": knn,
                               "kernels": {k: {"avg_us": 1e3 * v[0] / v[1], "launches": v[1]} for k, v in ktimes.items()}}), flush=True)
         return
     lm_info_all = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64) if do_map else None
@@ -594,7 +665,9 @@ def run_ours(args, rank, world, local_rank):
         e1.record(stream)
         barrier()
         t_host1 = time.perf_counter()
-        ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0)))
+        ms_e2e_rank = max(e0.elapsed_time(e1), 1e3 * (t_host1 - t_host0))
+        ms_e2e_ranks = all_ranks(ms_e2e_rank)
+        ms_e2e = max(ms_e2e_ranks)
     pose_host = {kk: np.concatenate([p_[kk] for p_ in poses_h]) for kk in poses_h[0]}
     e2e_value = (1 if point else world) * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
@@ -603,18 +676,38 @@ def run_ours(args, rank, world, local_rank):
     # same inputs, same number of steps -> both legs must end on identical poses
     same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
 
+    # The host -> device ceiling of this box for exactly these uploads (every rank at once, nothing else running): B copies
+    # of one 1.57 MB scan from the pinned pool per step.  e2e cannot beat it; it is printed beside e2e.
+    with torch.cuda.stream(stream):
+        sink = torch.empty((B, cap, 3), dtype=torch.float32, device=dev)
+        reps = 6
+        barrier()
+        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a_.record(stream)
+        for r in range(reps):
+            k = needed[r % len(needed)]
+            for b in range(B):
+                sink[b].copy_(host_base[b % N_BASE, slot_of[k]], non_blocking=True)
+        b_.record(stream)
+        barrier()
+        h2d_ms = max(all_ranks(a_.elapsed_time(b_) / reps))
+        del sink
+    h2d_ceiling_gbs = B * cap * 12 / (h2d_ms * 1e-3) / 1e9             # per GPU, all ranks copying at once
+    h2d_ceiling_scans = (1 if point else world) * B / (h2d_ms * 1e-3)
+
     # ---------------- leg 3: single-stream latency (batch = 1), context only
     lat_ms = None
     if rank == 0:
         lom1 = V.LidarOdometryMapping(ctx, batch=1, max_points=cap, map_capacity_points=map_cap, lm_max_iterations=args.lm_iterations)
         for (kind, cube), pts in map_cubes.items():
             lom1.map_set_cube(kind, cube, pts)
-        one_dev = [dev_pool[k][0:1].contiguous() for k in range(POOL_SCANS)]
         n1 = n_dev[0:1].contiguous()
+        n_lat = 40
+        lat_scan = (lambda i: needed[pingpong(i, len(needed))]) if len(needed) > 1 else (lambda i: needed[0])   # stays inside the pool
         with torch.cuda.stream(stream):
             def step1(i):
                 lom1.reset()
-                lom1.scanRegistrationDevice(one_dev[pingpong(i, POOL_SCANS)], n1, 3, cap)
+                lom1.scanRegistrationDevice(dev_pool[lat_scan(i)][0:1], n1, 3, cap)
                 lom1.laserOdometryIO(fetch=False)
                 if do_map:
                     lom1.laserMappingIO(fetch=False)
@@ -623,17 +716,17 @@ def run_ours(args, rank, world, local_rank):
             torch.cuda.synchronize()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             a.record(stream)
-            for i in range(5, 45):
+            for i in range(5, 5 + n_lat):
                 step1(i)
             b_.record(stream)
             torch.cuda.synchronize()
-            lat_ms = a.elapsed_time(b_) / 40
+            lat_ms = a.elapsed_time(b_) / n_lat
         lom1.close()
 
     if rank != 0:
         return
 
-    # ---------------- roofline of the dominant kernel
+    # ---------------- per-kernel table and the roofline of the dominant kernel
     peaks, peak_kind = load_peaks()
     tot = {"N": int(B * cap), "Np": int(counts[:, 0].sum()), "nSharp": int(counts[:, 1].sum()), "nLS": int(counts[:, 2].sum()),
            "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
@@ -643,64 +736,105 @@ def run_ours(args, rank, world, local_rank):
         tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
         tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
         tot["Mw"] = int(map_stats_all[:, :, 8].sum())
+        tot["cand"] = knn["candidates_per_query"] if knn else 0.0
     kern = {}
     for name, (ms, cnt) in ktimes.items():
-        by = algorithmic_bytes(name, tot) // H          # one launch covers one handle's B/H streams
+        by = int(algorithmic_bytes(name, tot)) // H          # one launch covers one handle's B/H streams
         kern[name] = {"ms_total": ms, "launches": cnt, "avg_us": 1e3 * ms / cnt, "share": None,
                       "alg_bytes_per_launch": by, "gbs": (by / (ms / cnt * 1e-3) / 1e9) if ms > 0 else None}
     ksum = sum(v["ms_total"] for v in kern.values()) or 1.0
     for v in kern.values():
         v["share"] = v["ms_total"] / ksum
     dom = max(kern, key=lambda k: kern[k]["ms_total"])
-    # DRAM traffic of the same kernel from the committed ncu --set full capture (profiles/ncu_traffic.json, per launch
-    # and per stream there; scaled to this run's streams per launch)
-    traffic = None
+    # measured DRAM traffic / issue utilisation of the same kernels from the committed ncu --set full capture
+    # (profiles/ncu_traffic.json: per launch and per stream there; scaled to this run's streams per launch)
+    tj = {}
     try:
         with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as f:
-            tj = json.load(f)
-        members = NCU_KERNELS.get(dom, [dom])      # a timing id can cover several launches: average per launch, like `achieved`
-        traffic = sum(tj["kernels"][m_]["dram_bytes_per_launch_per_stream"] for m_ in members) / len(members) * (B / H)
+            tj = json.load(f)["kernels"]
     except Exception:
-        traffic = None
+        tj = {}
+
+    def ncu_of(timing_id):
+        members = [m_ for m_ in NCU_KERNELS.get(timing_id, [timing_id]) if m_ in tj]
+        if not members:
+            return None, None
+        tr_ = sum(tj[m_]["dram_bytes_per_launch_per_stream"] for m_ in members) / len(members) * (B / H)
+        ia = [tj[m_].get("issue_active_pct") for m_ in members if tj[m_].get("issue_active_pct") is not None]
+        return tr_, (sum(ia) / len(ia) if ia else None)
+    traffic, issue_active = ncu_of(dom)
+    dur_s = kern[dom]["ms_total"] / kern[dom]["launches"] * 1e-3
     roof = {"kernel": dom, "bound": "hbm", "achieved": kern[dom]["gbs"], "peak": peaks["hbm_gbs"], "unit": "GB/s",
             "frac": (kern[dom]["gbs"] or 0.0) / peaks["hbm_gbs"], "traffic": traffic, "peak_source": peak_kind,
             "alg_bytes_per_launch": kern[dom]["alg_bytes_per_launch"],
-            "note": "achieved = algorithmic bytes per launch / CUDA-event duration; traffic = ncu dram read+write bytes per launch "
-                    "(profiles/ncu_traffic.json, from profiles/r01_ncu_full_summary.md)"}
+            "dram_gbs_from_ncu_traffic": (traffic / dur_s / 1e9) if traffic else None,
+            "dram_frac_from_ncu_traffic": (traffic / dur_s / 1e9 / peaks["hbm_gbs"]) if traffic else None,
+            "issue_active_pct_ncu": issue_active,
+            "note": "achieved = algorithmic bytes per launch (DESIGN.md section 6) / CUDA-event duration; traffic = ncu dram read+write bytes "
+                    "per launch (profiles/ncu_traffic.json).  The irregular searches (lm_associate, lo_associate) are served from L1/L2 and "
+                    "bound by instruction issue, not by HBM: for them read issue_active_pct_ncu and candidates_per_query, not frac."}
+    named = {}
+    for nm_ in ("sr_curvature", "lo_solve", "lm_solve", "lm_accumulate", "lo_accumulate"):      # the kernels the north star names
+        if nm_ in kern and kern[nm_]["gbs"] is not None:
+            t_, ia_ = ncu_of(nm_)
+            named[nm_] = {"gbs": kern[nm_]["gbs"], "frac": kern[nm_]["gbs"] / peaks["hbm_gbs"], "avg_us": kern[nm_]["avg_us"],
+                          "share": kern[nm_]["share"], "ncu_dram_bytes_per_launch": t_}
     curv = kern.get("sr_curvature")
 
-    # ---------------- CPU baseline: oracle, 1 thread, bounded sample
+    # ---------------- CPU baseline: oracle, 1 thread, bounded sample of the same trajectory
     from oracle import pyoracle as O
     O.build()
     pipe = CpuChain(O, args.workload, map_cubes, args.lm_iterations)
     n_cpu = args.cpu_scans if not do_map else max(4, args.cpu_scans // 4)      # ~10-15 s of CPU work either way
+    n_cpu = min(n_cpu, n_total)
     cpu_m = [cpu_matches(scan_streams[0], i) for i in range(n_cpu)] if do_vo else [None] * n_cpu
     t0 = time.perf_counter()
     for i in range(n_cpu):
-        pipe.process(seqs[0][pingpong(i, POOL_SCANS)], cpu_m[i])
+        pipe.process(seqs[0][scan_index(i)], cpu_m[i])
     cpu_dt = time.perf_counter() - t0
     tm = pipe.timings()
     cpu_value = n_cpu / cpu_dt
+
+    lm_work = None
+    if do_map:
+        d = (cnt1 - cnt0).astype(np.float64)
+        scans_t = max(d[:, 0].sum(), 1.0)
+        per = lambda col: float(d[:, col].sum() / scans_t)       # noqa: E731  (mean per scan and stream over the timed region)
+        lm_work = {
+            "scans_mapped": int(d[:, 0].sum()), "scans_solved": int(d[:, 1].sum()),
+            "lm_iterations_executed_per_pass": [per(2), per(3)], "lm_iterations_limit_per_pass": args.lm_iterations,
+            "cubes_entering_window_indexed_per_scan": [per(4), per(5)], "cubes_rewritten_per_scan": [per(6), per(7)],
+            "cubes_merged_per_scan": per(8), "of_which_patched_in_place": per(9), "cubes_fully_refiltered_per_scan": per(10),
+            "cubes_appended_per_scan": per(11), "voxels_inserted_per_scan": per(12), "repacks": int(d[:, 13].sum()),
+            "knn_queries_per_scan_per_pass": per(14), "residual_blocks_last_pass_per_scan": per(15),
+            "knn_candidates_per_query": knn["candidates_per_query"] if knn else None,
+            "streams_with_map_errors": int((lm_status[:, 1] != 0).sum()),
+        }
 
     line = {
         "metric": "scans/sec (HDL-64, 64x2048 pts) " + WORKLOAD_NAME[args.workload][0],
         "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if point else "weak", "vs_baseline": None,
-        "dtype": "f32 points / f64 solve", "data": f"synthetic ({N_BASE} seeded base sequences x {POOL_SCANS} scans tiled across the batch)",
-        "config": {"workload": WORKLOAD_NAME[args.workload][1],
-                   "streams_per_gpu": B, "handles": H, "points_per_scan": cap, "lo_passes": 2, "lo_iterations_per_pass": 4,
-                   "lm_passes": 2, "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0,
-                   "l2_policy": f"inputs larger than L2: pool of {POOL_SCANS} x {B} scans = {pool_bytes/1e6:.0f} MB rotated every step",
-                   "parallelism": (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
-                                   f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}") if point
-                                  else f"stream-sharded x{world} (no data-path collective)"},
+        "dtype": "f32 points / f64 solve",
+        "data": f"synthetic ({N_BASE} seeded base sequences x {TRAJ_SCANS}-scan forward trajectories tiled across the batch; generated in {t_gen:.1f} s)",
+        "config": config_dict(args, B, args.handles, world, do_map, {
+            "l2_policy": f"inputs larger than L2: a different [{B}, {cap}, 3] slab of the {pool_bytes/1e9:.1f} GB scan pool every step",
+            "parallelism": (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
+                            f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}") if point
+                           else f"stream-sharded x{world} (no data-path collective)"}),
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same},
+                "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same,
+                "h2d_gbs_per_gpu": h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
+                "h2d_ceiling_gbs_per_gpu": h2d_ceiling_gbs, "h2d_ceiling_scans_per_s": h2d_ceiling_scans,
+                "ms_per_step_per_rank": [m_ / args.steps for m_ in ms_e2e_ranks], "host_numa": numa},
+        "ms_per_step_per_rank": [m_ / args.steps for m_ in ms_ranks],
         "gpu_launches": int(launches),
         "roofline": roof,
+        "north_star_kernels": named,
         "kernels": {k: {kk: (round(vv, 4) if isinstance(vv, float) else vv) for kk, vv in v.items()} for k, v in kern.items()},
         "curvature_kernel": None if curv is None else {"gbs": curv["gbs"], "frac": curv["gbs"] / peaks["hbm_gbs"]},
         "single_stream_latency_ms": lat_ms,
+        "laser_mapping_work": lm_work,
         "map": None if not do_map else {
             "points_per_stream": float(map_stats_all[:, :, 0].sum() / B), "cubes_per_stream": float(map_stats_all[:, :, 3].sum() / B),
             "cubes_rewritten_last_scan_per_stream": float(map_stats_all[:, :, 5].sum() / B),
@@ -712,7 +846,8 @@ def run_ours(args, rank, world, local_rank):
                     "(the reference filters them again and gets the same cloud back)"},
         "cpu_baseline": {"value": cpu_value, "unit": "scans/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} scans of one stream, 1 thread: SR {tm['sr_ms']/n_cpu:.1f} ms + LO {tm['lo_ms']/n_cpu:.1f} ms"
-                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"},
+                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"
+                                   + (f"; LM iterations executed in the last scan's passes: {pipe.lm_iterations()}" if do_map else "")},
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)

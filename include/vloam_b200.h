@@ -129,6 +129,9 @@ int vloam_lidar_reset(vloam_lidar* h);
  * point_step = 4 * stride_floats, taken without the pcl::fromROSMsg copy of vloam_main_node.cpp:148);
  * n_points[b] = valid points in slab b.  Pinned host memory makes the upload asynchronous. */
 int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points);
+/* Same with one host buffer per stream (xyz_ptrs[batch]: every sensor's driver owns its own message buffer; nothing is
+ * gathered on the host).  n_points[b] <= max_points. */
+int vloam_scan_registration_ptrs(vloam_lidar* h, const float* const* xyz_ptrs, const int* n_points, int stride_floats);
 /* Same with the scans already resident in device memory (xyz_dev and n_points_dev are device pointers).  The counts
  * cannot be checked on the host: a count above min(max_points, slab_points) is clamped and reported per stream as
  * VLOAM_STREAM_CAPACITY. */
@@ -196,6 +199,16 @@ int vloam_map_get_cube(vloam_lidar* h, int stream, int kind, int cube, float* xy
 /* info[batch][8] = cenWidth, cenHeight, cenDepth, validNum, cornerFromMapNum, surfFromMapNum, cornerStackNum, surfStackNum */
 int vloam_get_lm_info(vloam_lidar* h, int* info);
 int vloam_get_lm_trace(vloam_lidar* h, int stream, int pass, double* records, int* info, double* para);
+/* Work counters of laser mapping, cumulative since the handle was created (the benchmark reports their per-scan means; they
+ * replace the reference's ROS_INFO statistics).  counters[batch][18]:
+ *   0 scans mapped, 1 scans whose map passed the gate of laser_mapping.cpp:448, 2 / 3 Levenberg-Marquardt iterations run in
+ *   outer pass 0 / 1, 4 / 5 corner / surf cubes that had to be indexed on entering the 5 x 5 x 3 window, 6 / 7 corner / surf cubes
+ *   rewritten, 8 cubes re-filtered by merging (9: of those, patched inside their slab), 10 cubes re-filtered by a full voxel
+ *   sort, 11 cubes outside the window that only grew, 12 voxels inserted by merges, 13 re-packs of a map pool, 14 down-sampled
+ *   scan points (k-NN queries per pass), 15 residual blocks of the last pass; 16 / 17 k-NN queries / candidate points tested
+ *   while vloam_lidar_set_debug_stats is on. */
+int vloam_get_lm_counters(vloam_lidar* h, long long* counters);
+int vloam_lidar_set_debug_stats(vloam_lidar* h, int on);
 /* Parity read-out: the queries (indices into laserCloudCornerStack, kind 0, or laserCloudSurfStack, kind 1) that produced a
  * residual block in outer pass `pass` of the last scan (laser_mapping.cpp:472-581), ascending; n_out receives their number,
  * at most `capacity` are written. */

@@ -15,7 +15,7 @@ bench_json = sys.argv[7] if len(sys.argv) > 7 else "profiles/r01_bench_default.j
 
 
 def base(name):
-    return name.split("(")[0].replace("void ", "").replace("vb::", "").split("<")[0].replace("_occ6", "").replace("_occ5", "").replace("_occ8", "")
+    return name.split("(")[0].replace("void ", "").replace("vb::", "").split("<")[0].replace("_occ6", "").replace("_occ5", "").replace("_occ8", "").replace("_occ3", "")
 
 
 # ---- launch list: per-kernel time share (cold-cache, serialised: compare shares, not absolutes)
@@ -87,12 +87,18 @@ with open(f"profiles/{tag}_ncu_full_summary.md", "w") as out:
                 cells.append(f"{v:.1f}")
         out.write(f"| {name} | " + " | ".join(cells) + " |\n")
         rd, wr = val(r, "dram__bytes_read.sum") or 0.0, val(r, "dram__bytes_write.sum") or 0.0
-        t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0})
+        t = traffic.setdefault(name, {"launches": 0, "dram_bytes": 0.0, "issue": 0.0, "time_us": 0.0})
         t["launches"] += 1
         t["dram_bytes"] += rd + wr
+        t["issue"] += val(r, "smsp__issue_active.avg.pct_of_peak_sustained_active") or 0.0
+        tu = val(r, "gpu__time_duration.sum") or 0.0
+        t["time_us"] += tu / 1000.0 if units[idx["gpu__time_duration.sum"]].startswith("n") else tu
 for k, t in traffic.items():
     t["dram_bytes_per_launch"] = t["dram_bytes"] / t["launches"]
     t["dram_bytes_per_launch_per_stream"] = t["dram_bytes_per_launch"] / streams
+    t["issue_active_pct"] = t.pop("issue") / t["launches"]
+    t["ncu_time_us_per_launch"] = t.pop("time_us") / t["launches"]
+    t["streams_per_launch"] = streams
     del t["dram_bytes"]
 for t in traffic.values():
     t["source"] = f"profiles/{tag}_ncu_full_summary.md"

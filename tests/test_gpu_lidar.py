@@ -266,3 +266,66 @@ def test_other_sensors_ring_formulas(synth, oracle, scan_line):
         if k > 0:
             _check_lo(lom, olo, pose)
     lom.close()
+
+
+@pytest.mark.parametrize("seed0", [0, 25, 50, 75])
+def test_seed_sweep_scan_registration_and_odometry(synth, oracle, seed0):
+    """seeds 0..99 x 2 consecutive scans (64 x 1024) — curvature, labels, every feature index set and
+    every cloud bit-exact, laser-odometry correspondences identical and poses within 1e-4 on the second scan.  Five streams
+    per handle, so the sweep also covers the batched layout."""
+    import vloam_b200 as V
+    B, cols = 5, 1024
+    cap = 64 * cols
+    lom = V.LidarOdometryMapping(batch=B, max_points=cap)
+    for base in range(seed0, seed0 + 25, B):
+        streams = [synth.ScanStream(base + b, n_cols=cols) for b in range(B)]
+        olos = [oracle.LaserOdometry() for _ in range(B)]
+        for k in range(2):
+            buf = np.stack([st.scan(k) for st in streams])
+            lom.reset()
+            lom.scanRegistrationIO(buf)
+            refs = [oracle.scan_registration(buf[b]) for b in range(B)]
+            for b in range(B):
+                _check_sr(lom, refs[b], b)
+            pose = lom.laserOdometryIO()
+            for b in range(B):
+                olos[b].solve(refs[b])
+                if k > 0:
+                    _check_lo(lom, olos[b], pose, b)
+        lom.init()      # the next group of seeds starts from a fresh handle, like its fresh oracles
+    lom.close()
+
+
+def test_device_resident_count_beyond_capacity_is_clamped_and_reported(synth):
+    """vloam_scan_registration_device cannot validate counts that live in device memory: a count above the handle
+    capacity must be clamped inside the kernels and reported per stream, not overrun the buffers."""
+    import torch
+    import vloam_b200 as V
+    cols = 256
+    cap = 64 * cols
+    sc = synth.ScanStream(12, n_cols=cols).scan(0)
+    big = np.concatenate([sc, sc, sc])                             # 3 x capacity points in the caller's buffer
+    lom = V.LidarOdometryMapping(batch=2, max_points=cap)
+    xyz = torch.from_numpy(np.stack([big, big])).cuda()
+    n = torch.tensor([cap, 3 * cap], dtype=torch.int32).cuda()    # stream 1 claims three times the capacity
+    torch.cuda.synchronize()
+    lom.reset()
+    lom.scanRegistrationDevice(xyz, n, 3, 3 * cap)
+    st = lom.stream_status()
+    assert st[0] == 0 and st[1] == V.STREAM_CAPACITY, st
+    c = lom.feature_counts()
+    assert list(c[0]) == list(c[1])                                # the clamped stream saw exactly the first `cap` points
+    lom.laserOdometryIO()
+    lom.close()
+    # the VO handle rounds its capacity differently from the lidar handle: a larger count is clamped, not overrun
+    vo = V.VisualOdometry(batch=1, max_points=cap, max_matches=64)
+    vo.setUpPointCloud(*synth.kitti_like_calibration())
+    vo.reset()
+    vo.processPointCloudDevice(xyz[1:], n[1:], 3, 3 * cap)
+    ref = V.VisualOdometry(batch=1, max_points=cap, max_matches=64)
+    ref.setUpPointCloud(*synth.kitti_like_calibration())
+    ref.reset()
+    ref.processPointCloud(sc)
+    for a, b in zip(vo.buckets(0), ref.buckets(0)):
+        assert np.array_equal(a, b)
+    vo.close(); ref.close()

@@ -48,6 +48,9 @@ def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stat
         for p, t in enumerate(otr):
             g = lom.lm_trace(p)
             assert (g["n_corner"], g["n_plane"]) == (len(t["corner"]), len(t["plane"])), (k, p)
+            # the same queries produced the factors (laser_mapping.cpp:472-581), not just the same number of them
+            assert np.array_equal(lom.lm_queries(p, 0), t["corner"].ravel()), (k, p, "corner queries")
+            assert np.array_equal(lom.lm_queries(p, 1), t["plane"].ravel()), (k, p, "surf queries")
             assert g["termination"] == t["termination"]
             n = t["iterations"].shape[0]
             assert g["n_records"] == n
@@ -73,6 +76,7 @@ def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stat
         for kind in (0, 1):      # storage bookkeeping: the tables account for exactly the oracle's map
             assert ms[kind, 0] == sum(pipe.lm.cube_count(kind, c) for c in range(4851))
             assert ms[kind, 0] <= ms[kind, 7] <= ms[kind, 1] <= map_capacity
+        assert not lom.lm_status()[0].any()
         if stats_out is not None:
             stats_out.append(ms.copy())
     lom.close()
@@ -191,31 +195,265 @@ def test_laser_mapping_column_table_recycling(synth, oracle, monkeypatch):
     assert (np.diff(st[:, 1, 9]) < 0).any(), st[:, 1, 9]      # the slot counter started over at least once
 
 
-def test_laser_mapping_seeded_map_and_cube_shift(synth, oracle):
-    """Map cubes seeded through vloam_map_set_cube; a large odometry offset forces the rolling grid to shift."""
+def _cube_of(p, cen=(10, 10, 5)):
+    c = np.floor((np.asarray(p, np.float64) + 25.0) / 50.0).astype(int) + np.asarray(cen)
+    return c[..., 0] + 21 * c[..., 1] + 441 * c[..., 2]
+
+
+def _compare_all_cubes(lom, olm, tag, stream=0):
+    """Every cube of both kinds: identical content (so also: dropped by the same shifts)."""
+    ms = lom.map_stats()[stream]
+    occupied = 0
+    for kind in (0, 1):
+        total = 0
+        for cube in range(4851):
+            n_or = olm.cube_count(kind, cube)
+            total += n_or
+            if n_or:
+                _same_xyz(lom.map_get_cube(kind, cube, stream=stream), olm.cube(kind, cube), f"{tag} cube {cube} kind {kind}")
+                occupied += 1
+        assert ms[kind, 0] == total, (tag, kind, ms[kind, 0], total)      # ... and nothing else anywhere
+    return occupied
+
+
+def test_laser_mapping_cube_grid_shift_all_directions(synth, oracle):
+    """laser_mapping.cpp:218-402: jumps of the odometry pose (vloam_set_lo_pose on both sides, before laserMapping) drive the
+    centre cube out of [3, W-3) in +x, +y, -x / +z, -y / -z (single and double steps) and back; the rolling grid must shift
+    by the same steps, seeded far-away cubes must survive at their shifted index or be dropped exactly like the oracle's,
+    and around the jump targets a seeded ground lattice + poles makes the solve run on the shifted tables."""
     import vloam_b200 as V
     s = synth.ScanStream(32, n_cols=512)
-    scans = [s.scan(k) for k in range(3)]
+    scans = [s.scan(k) for k in range(6)]
     lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=1 << 18, debug_keep_submap=1)
     pipe = oracle.Pipeline()
-    # seed one far-away cube in both maps: it must survive the grid shift at its shifted index or be dropped identically
     rng = np.random.default_rng(0)
-    seed = np.c_[rng.uniform(280, 320, (500, 2)), rng.uniform(-2, 2, 500), rng.uniform(0, 50, 500)].astype(np.float32)
-    cube = (10 + 6) + 21 * (10 + 6) + 441 * 5
-    lom.map_set_cube(1, cube, seed)
-    pipe.lm.set_cube(1, cube, seed)
-    assert np.array_equal(lom.map_get_cube(1, cube), seed)
+    seeded = {}
+
+    def seed(kind, pts):
+        pts = np.c_[pts, np.zeros(len(pts))].astype(np.float32)
+        ci = _cube_of(pts[:, :3])
+        for c in np.unique(ci):
+            seeded[(kind, int(c))] = pts[ci == c]
+    # far cubes that only exist to be carried around / dropped by the shifts (at the grid's border planes too)
+    seed(1, np.c_[rng.uniform(280, 320, (500, 2)), rng.uniform(-2, 2, 500)])
+    seed(1, np.c_[rng.uniform(-520, -480, 300), rng.uniform(-20, 20, 300), rng.uniform(-2, 2, 300)])      # i = 0: dropped by a shift towards -x
+    seed(0, np.c_[rng.uniform(480, 520, 300), rng.uniform(-20, 20, 300), rng.uniform(-2, 2, 300)])        # i = 20
+    seed(1, np.c_[rng.uniform(-20, 20, (300, 2)), rng.uniform(230, 270, 300)])                             # k = 10
+    seed(0, np.c_[rng.uniform(-20, 20, 300), rng.uniform(-520, -480, 300), rng.uniform(-2, 2, 300)])      # j = 0
+    # a ground lattice and poles around the jump targets, so that the gate of :448 passes and the solve runs there
+    for cx, cy in ((400.0, 0.0), (400.0, 400.0), (-400.0, 400.0)):
+        g = np.arange(-70.0, 70.0, 0.8)
+        gx, gy = np.meshgrid(g + cx, g + cy)
+        seed(1, np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, -1.73)] + rng.uniform(-0.2, 0.2, (gx.size, 3)) * [1, 1, 0.02])
+        px, py = rng.uniform(cx - 60, cx + 60, 30), rng.uniform(cy - 60, cy + 60, 30)
+        seed(0, np.c_[np.repeat(px, 12), np.repeat(py, 12), np.tile(np.arange(12) * 0.4 - 1.5, 30)])
+    for (kind, cube), pts in seeded.items():
+        lom.map_set_cube(kind, cube, pts)
+        pipe.lm.set_cube(kind, cube, pts)
+    jumps = [None, (400.0, 0.0, 0.0), (400.0, 400.0, 0.0), (-400.0, 400.0, 130.0), (-400.0, -400.0, -130.0), (0.0, 0.0, 0.0)]
+    expect_cen = [(10, 10, 5), (9, 10, 5), (9, 9, 5), (11, 9, 4), (11, 11, 6), (11, 11, 6)]
+    solved = 0
     for k, scan in enumerate(scans):
-        # shift both odometries by 400 m in x so that centerCubeI >= laserCloudWidth - 3 (laser_mapping.cpp:249)
-        sc = scan
-        lom.reset(); lom.scanRegistrationIO(sc); lom.laserOdometryIO()
-        assert pipe.process(sc, do_mapping=False) == 0
-        if k == 0:
-            off = np.array([[0, 0, 0, 1, 400.0, 0, 0]])
-        lom_pose = lom.lo_pose()
+        lom.reset(); lom.scanRegistrationIO(scan)
+        lp = lom.laserOdometryIO()
+        assert pipe.process(scan, do_mapping=False) == 0
+        if jumps[k] is not None:
+            pose = np.r_[lp["q_w_curr"][0], np.asarray(jumps[k])]      # the jump target is absolute: identical on both sides
+            lom.set_lo_pose(pose[None])
+            pipe.lo.set_pose(pose[:4], pose[4:])
         mp = lom.laserMappingIO()
+        n_before = pipe.lm.map_points(1)
         pipe.lm.reset(); pipe.lm.input_from_lo(pipe.lo); pipe.lm.solve()
         ost = pipe.lm.state
-        assert list(lom.lm_info()[0][:3]) == list(ost["cen"])
-        assert np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])) < POSE_TOL_M
+        info = lom.lm_info()[0]
+        assert tuple(ost["cen"]) == expect_cen[k], (k, ost["cen"])        # the oracle really shifted (the test's premise)
+        if k == 1:   # ... and the shift towards -x dropped the seeded i = 0 plane (300 points) on its way
+            assert pipe.lm.map_points(1) <= n_before + pipe.lm.cloud(1).shape[0] - 300
+        assert list(info[:4]) == list(ost["cen"]) + [ost["validNum"]], (k, info, ost)
+        _same_xyz(lom.cloud(V.CLOUD_CORNER_MAP), pipe.lm.cloud(2), f"scan {k} corner from map")
+        _same_xyz(lom.cloud(V.CLOUD_SURF_MAP), pipe.lm.cloud(3), f"scan {k} surf from map")
+        for p, t in enumerate(pipe.lm.trace()):
+            g = lom.lm_trace(p)
+            assert (g["n_corner"], g["n_plane"]) == (len(t["corner"]), len(t["plane"])), (k, p)
+            assert np.array_equal(lom.lm_queries(p, 1), t["plane"].ravel())
+            np.testing.assert_allclose(g["iterations"][: t["iterations"].shape[0], 0], t["iterations"][:, 0], rtol=1e-8, atol=1e-12)
+            solved += 1
+        assert np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])) < POSE_TOL_M, k
+        assert _quat_angle(mp["q_w_curr"][0], ost["q_w_curr"]) < POSE_TOL_RAD
+        assert _compare_all_cubes(lom, pipe.lm, f"scan {k}") > 0
+    assert solved >= 4          # the solve ran on shifted tables, not only the insertion
+    lom.close()
+
+
+def test_laser_mapping_bench_configuration(synth, oracle):
+    """The configuration bench.py times (BASELINE configs[2]): full-size scans on the pre-built 1 M-point map, 2 passes x 5 LM
+    iterations, several streams in one handle — poses, solver traces, query sets and every cube of the map against one
+    oracle pipeline per stream, after every scan."""
+    import vloam_b200 as V
+    B, n_scans = 2, 4
+    cubes = synth.map_cubes(1_000_000, 1234)
+    streams = [synth.ScanStream(1234 + b, n_cols=2048) for b in range(B)]
+    cap = 64 * 2048
+    lom = V.LidarOdometryMapping(batch=B, max_points=cap, map_capacity_points=1 << 21, lm_max_iterations=5)
+    pipes = [oracle.Pipeline() for _ in range(B)]
+    for b in range(B):
+        pipes[b].lm.set_iterations(2, 5)
+        for (kind, cube), pts in cubes.items():
+            lom.map_set_cube(kind, cube, pts, stream=b)
+            pipes[b].lm.set_cube(kind, cube, pts)
+    its = []
+    for k in range(n_scans):
+        buf = np.stack([st.scan(k) for st in streams])
+        lom.reset(); lom.scanRegistrationIO(buf); lom.laserOdometryIO()
+        mp = lom.laserMappingIO()
+        assert not lom.lm_status().any()
+        for b in range(B):
+            assert pipes[b].process(buf[b], do_mapping=True) == 0
+            ost = pipes[b].lm.state
+            assert np.max(np.abs(mp["t_w_curr"][b] - ost["t_w_curr"])) < POSE_TOL_M, (k, b)
+            assert _quat_angle(mp["q_w_curr"][b], ost["q_w_curr"]) < POSE_TOL_RAD
+            otr = pipes[b].lm.trace()
+            assert len(otr) == 2
+            for p, t in enumerate(otr):
+                g = lom.lm_trace(p, b)
+                assert np.array_equal(lom.lm_queries(p, 0, b), t["corner"].ravel()), (k, b, p)
+                assert np.array_equal(lom.lm_queries(p, 1, b), t["plane"].ravel()), (k, b, p)
+                n = t["iterations"].shape[0]
+                assert g["n_records"] == n and g["termination"] == t["termination"]
+                np.testing.assert_allclose(g["iterations"][:n, 0], t["iterations"][:, 0], rtol=1e-8, atol=1e-12)
+                np.testing.assert_array_equal(g["iterations"][:n, 5:7], t["iterations"][:, 5:7])
+                assert len(t["plane"]) > 1000
+                its.append(n - 1)
+            assert _compare_all_cubes(lom, pipes[b].lm, f"scan {k} stream {b}", stream=b) >= 50
+    print("LM iterations executed per pass (oracle == CUDA):", its)
+    lom.close()
+
+
+def test_laser_mapping_long_forward_sequence(synth, oracle):
+    """60 consecutive scans of a forward trajectory (no replay; ~65 m of travel: the window moves to new cubes, voxels are
+    inserted, slabs grow and the map is re-packed): pose within 1e-4 m / 1e-4 rad after EVERY scan, every cube of the map
+    identical every 10 scans and at the end."""
+    import vloam_b200 as V
+    s = synth.ScanStream(34, n_cols=512)
+    n_scans = 60
+    lom = V.LidarOdometryMapping(batch=1, max_points=64 * 512, map_capacity_points=1 << 17)
+    pipe = oracle.Pipeline()
+    worst = 0.0
+    cens = set()
+    for k in range(n_scans):
+        scan = s.scan(k)
+        lom.reset(); lom.scanRegistrationIO(scan); lom.laserOdometryIO()
+        mp = lom.laserMappingIO()
+        assert pipe.process(scan, do_mapping=True) == 0
+        ost = pipe.lm.state
+        dt = float(np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])))
+        worst = max(worst, dt)
+        assert dt < POSE_TOL_M, (k, dt)
+        assert _quat_angle(mp["q_w_curr"][0], ost["q_w_curr"]) < POSE_TOL_RAD, k
+        for p, t in enumerate(pipe.lm.trace()):
+            g = lom.lm_trace(p)
+            assert (g["n_corner"], g["n_plane"], g["termination"]) == (len(t["corner"]), len(t["plane"]), t["termination"]), (k, p)
+        cens.add(tuple(ost["cen"]) + (int(_cube_of(ost["t_w_curr"], ost["cen"])),))
+        if k % 10 == 9 or k == n_scans - 1:
+            _compare_all_cubes(lom, pipe.lm, f"scan {k}")
+        assert not lom.lm_status()[0].any()
+    assert np.linalg.norm(pipe.lm.state["t_w_curr"]) > 30.0        # the trajectory really went somewhere
+    assert len(cens) >= 2                                          # ... into another centre cube
+    print("max |t_w_curr - oracle| over", n_scans, "scans =", worst)
+    lom.close()
+
+
+def test_laser_mapping_skip_frame(synth, oracle):
+    """mapping_skip_frame = 2 (laser_odometry.cpp:618-628, laser_mapping.cpp:175-195, 742-756): every second frame only
+    refreshes the high-frequency pose q_wmap_wodom * q_wodom_curr; the map and q_w_curr are untouched by it."""
+    import vloam_b200 as V
+    s = synth.ScanStream(35, n_cols=512)
+    lom = V.LidarOdometryMapping(batch=1, max_points=64 * 512, map_capacity_points=1 << 17, mapping_skip_frame=2)
+    pipe = oracle.Pipeline(mapping_skip_frame=2)
+    skipped = 0
+    for k in range(7):
+        scan = s.scan(k)
+        lom.reset(); lom.scanRegistrationIO(scan); lom.laserOdometryIO()
+        before = lom.map_stats()[0, :, 0].copy()
+        mp = lom.laserMappingIO()
+        assert pipe.process(scan, do_mapping=True) == 0
+        q, t, skip = pipe.lm.published_pose
+        skipped += skip
+        assert np.max(np.abs(mp["t_w_curr"][0] - t)) < POSE_TOL_M, (k, skip)
+        assert _quat_angle(mp["q_w_curr"][0], q) < POSE_TOL_RAD, (k, skip)
+        ost = pipe.lm.state
+        assert np.max(np.abs(mp["t_wmap_wodom"][0] - ost["t_wmap_wodom"])) < POSE_TOL_M
+        if skip:
+            assert np.array_equal(lom.map_stats()[0, :, 0], before)       # a skipped frame inserts nothing
+        _compare_all_cubes(lom, pipe.lm, f"scan {k}")
+    assert skipped == 4          # frameCount is 1, 3, 5, 7 after the odometry of scans 0, 2, 4, 6: those frames are skipped
+    lom.close()
+    with pytest.raises(V.VloamError):
+        V.LidarOdometryMapping(batch=1, max_points=4096, mapping_skip_frame=0)
+
+
+def test_laser_mapping_capacity_overflow_is_per_kind_and_recoverable(synth, oracle):
+    """A map pool too small for the surf map: that kind keeps its pre-insertion content and reports VLOAM_LM_SURF_MAP_FULL
+    for the scan; the corner map still takes the scan, nothing is corrupted (every cube stays readable and indexed: the next
+    scans keep solving), and the bit clears once a scan fits again."""
+    import vloam_b200 as V
+    s = synth.ScanStream(31, n_cols=1024)
+    lom = V.LidarOdometryMapping(batch=1, max_points=64 * 1024, map_capacity_points=6000)
+    full_seen = False
+    for k in range(6):
+        scan = s.scan(k)
+        lom.reset(); lom.scanRegistrationIO(scan); lom.laserOdometryIO()
+        st0 = lom.map_stats()[0].copy()
+        mp = lom.laserMappingIO()
+        status = lom.lm_status()[0]
+        st1 = lom.map_stats()[0]
+        assert np.isfinite(mp["t_w_curr"]).all()
+        if status[0] & V.LM_SURF_MAP_FULL:
+            full_seen = True
+            assert st1[1, 0] == st0[1, 0]                      # the surf map kept its point count ...
+            assert not (status[0] & V.LM_CORNER_MAP_FULL)
+            assert st1[0, 0] >= st0[0, 0]                      # ... while the corner map took the scan
+        for kind in (0, 1):                                     # tables stay consistent: counts add up, slabs inside the pool
+            assert st1[kind, 0] <= st1[kind, 7] <= 6000
+            if k == 5:      # every cube is still readable and the counts add up
+                assert sum(lom.map_get_cube(kind, c).shape[0] for c in range(4851)) == st1[kind, 0]
+        assert status[1] & status[0] == status[0]              # the sticky word accumulates the per-scan word
+    assert full_seen, "the test's map capacity did not overflow: lower it"
+    g = lom.lm_trace(1)
+    assert g["n_plane"] > 100                                  # still solving against the (frozen) surf map
+    lom.close()
+
+
+def test_laser_mapping_large_cube_uses_flat_index(synth, oracle):
+    """A cube of more than 65 535 points cannot use 16-bit z-layer offsets: its index falls back to column-only order with
+    32-bit starts.  Results must not change: a dense seeded ground cube (70 k points), full parity with the oracle."""
+    import vloam_b200 as V
+    s = synth.ScanStream(36, n_cols=512)
+    lom = V.LidarOdometryMapping(batch=1, max_points=64 * 512, map_capacity_points=1 << 18)
+    pipe = oracle.Pipeline()
+    rng = np.random.default_rng(3)
+    g = np.arange(-24.9, 24.9, 0.186)
+    gx, gy = np.meshgrid(g, g)
+    surf = np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, -1.73) + rng.uniform(-0.02, 0.02, gx.size), np.zeros(gx.size)].astype(np.float32)
+    assert surf.shape[0] > 65535
+    px, py = rng.uniform(-24, 24, 40), rng.uniform(-24, 24, 40)
+    corner = np.c_[np.repeat(px, 12), np.repeat(py, 12), np.tile(np.arange(12) * 0.4 - 1.5, 40), np.zeros(480)].astype(np.float32)
+    c0 = int(_cube_of(np.zeros(3)))
+    for kind, pts in ((0, corner), (1, surf)):
+        lom.map_set_cube(kind, c0, pts)
+        pipe.lm.set_cube(kind, c0, pts)
+    for k in range(3):
+        scan = s.scan(k)
+        lom.reset(); lom.scanRegistrationIO(scan); lom.laserOdometryIO()
+        mp = lom.laserMappingIO()
+        assert pipe.process(scan, do_mapping=True) == 0
+        ost = pipe.lm.state
+        assert np.max(np.abs(mp["t_w_curr"][0] - ost["t_w_curr"])) < POSE_TOL_M, k
+        for p, t in enumerate(pipe.lm.trace()):
+            g_ = lom.lm_trace(p)
+            assert np.array_equal(lom.lm_queries(p, 1), t["plane"].ravel()), (k, p)
+            assert np.array_equal(lom.lm_queries(p, 0), t["corner"].ravel()), (k, p)
+            if k == 0:
+                assert g_["n_plane"] > 200      # the first scan matches against the dense cube (still > 65 535 points: flat index)
+        _compare_all_cubes(lom, pipe.lm, f"scan {k}")
     lom.close()

@@ -50,6 +50,10 @@ def test_vo_depth_buckets_query_and_solve(synth, oracle, rect33):
         tg, to = vo.trace(), ovo.trace()
         np.testing.assert_allclose(tg["iterations"][0, 0], to[0, 0], rtol=1e-10)      # initial cost
         assert tg["n_records"] == to.shape[0]
+        nk = min(8, to.shape[0])                                                      # the library keeps the first 8 records
+        np.testing.assert_allclose(tg["iterations"][:nk, 0], to[:nk, 0], rtol=1e-8)   # cost after every kept iteration
+        np.testing.assert_array_equal(tg["iterations"][:nk, 5:7], to[:nk, 5:7])       # step valid / successful
+        np.testing.assert_allclose(tg["iterations"][:nk, 4], to[:nk, 4], rtol=1e-6)   # trust-region radius
         np.testing.assert_allclose(gs["angles_0to1"][0], os_["angles_0to1"], atol=1e-6)
         np.testing.assert_allclose(gs["t_0to1"][0], os_["t_0to1"], atol=1e-5)
         # and the estimate is a sensible camera motion (about 1 m forward along z)

@@ -297,3 +297,83 @@ def test_laser_mapping_runs_and_refines(oracle, scans_small):
     assert pipe.lm.map_points(0) > 100 and pipe.lm.map_points(1) > 1000
     tr = pipe.lm.trace()
     assert len(tr) == 2 and tr[0]["iterations"][0, 0] >= tr[-1]["iterations"][-1, 0]   # cost does not increase
+
+
+def test_oracle_grid_shift_equals_array_shift(oracle):
+    """laser_mapping.cpp:218-402 moves 21 x 21 x 11 cloud pointers one plane per while-iteration and clears the plane that
+    wraps around.  Independent model: a (k, j, i) integer array shifted with slice assignment.  Every cube holds one
+    point whose intensity is its original index, so the oracle's array after the shift can be read back as that integer array."""
+    W, H, D = 21, 21, 11
+    rng = np.random.default_rng(11)
+    cases = [(400.0, 0.0, 0.0), (-400.0, 0.0, 0.0), (0.0, 460.0, 0.0), (0.0, -460.0, 0.0), (0.0, 0.0, 130.0), (0.0, 0.0, -180.0),
+             (600.0, -520.0, 140.0), (24.9, -24.9, 0.0), (140.0, 140.0, 0.0)]
+    for tx, ty, tz in cases:
+        lm = oracle.LaserMapping()
+        ids = np.arange(W * H * D).reshape(D, H, W)           # ids[k, j, i] = i + 21 j + 441 k
+        occupied = rng.random(ids.shape) < 0.5
+        for c in ids[occupied]:
+            i, j, k = c % W, (c // W) % H, c // (W * H)
+            p = np.array([[(i - 10) * 50.0, (j - 10) * 50.0, (k - 5) * 50.0, float(c)]], np.float32)   # the cube's own centre
+            lm.set_cube(1, int(c), p)
+        lm.input_clouds(np.zeros((0, 4), np.float32), np.zeros((0, 4), np.float32), [0, 0, 0, 1.0], [tx, ty, tz])
+        lm.solve()
+        # model
+        model = np.where(occupied, ids, -1)
+        cen = [10, 10, 5]
+        def coord(v, c):
+            r = int((v + 25.0) / 50.0) + c
+            return r - 1 if v + 25.0 < 0 else r
+        cc = [coord(tx, 10), coord(ty, 10), coord(tz, 5)]
+        for axis, n in ((2, W), (1, H), (0, D)):              # numpy axis of i, j, k
+            a = 2 - axis
+            while cc[a] < 3:
+                model = np.roll(model, 1, axis=axis)
+                sl = [slice(None)] * 3; sl[axis] = 0
+                model[tuple(sl)] = -1
+                cc[a] += 1; cen[a] += 1
+            while cc[a] >= n - 3:
+                model = np.roll(model, -1, axis=axis)
+                sl = [slice(None)] * 3; sl[axis] = n - 1
+                model[tuple(sl)] = -1
+                cc[a] -= 1; cen[a] -= 1
+        assert list(lm.state["cen"]) == cen, (tx, ty, tz)
+        got = np.full(ids.shape, -1)
+        for c in range(W * H * D):
+            n = lm.cube_count(1, c)
+            assert n <= 1
+            if n:
+                got[c // (W * H), (c // W) % H, c % W] = int(lm.cube(1, c)[0, 3])
+        assert np.array_equal(got, model), (tx, ty, tz)
+
+
+def test_oracle_skip_frame_publishes_high_frequency_pose(oracle, scans_small):
+    """mapping_skip_frame = 2: LaserOdometry::output flags frames with frameCount % 2 != 0 (laser_odometry.cpp:618-628); for
+    those LaserMapping::input only forms q_wmap_wodom * q_wodom_curr (laser_mapping.cpp:186-190) and solveMapping is not
+    run (lidar_odometry_mapping.cpp:134-135): the map must not change and the published pose must be that composition."""
+    scans, _ = scans_small
+    pipe = oracle.Pipeline(mapping_skip_frame=2)
+
+    def qmul(a, b):
+        ax, ay, az, aw = a; bx, by, bz, bw = b
+        return np.array([aw * bx + ax * bw + ay * bz - az * by, aw * by + ay * bw + az * bx - ax * bz,
+                         aw * bz + az * bw + ax * by - ay * bx, aw * bw - ax * bx - ay * by - az * bz])
+
+    def qrot(q, v):
+        u = q[:3]
+        return v + 2.0 * np.cross(u, np.cross(u, v) + q[3] * v)
+    flags = []
+    for k, sc in enumerate(scans):
+        before = (pipe.lm.map_points(0), pipe.lm.map_points(1))
+        st_before = pipe.lm.state
+        assert pipe.process(sc, do_mapping=True) == 0
+        q, t, skip = pipe.lm.published_pose
+        flags.append(skip)
+        lo, st = pipe.lo.state, pipe.lm.state
+        if skip:
+            assert (pipe.lm.map_points(0), pipe.lm.map_points(1)) == before
+            np.testing.assert_array_equal(st["q_w_curr"], st_before["q_w_curr"])      # q_w_curr itself is not touched
+            np.testing.assert_allclose(q, qmul(st["q_wmap_wodom"], lo["q_w_curr"]), atol=1e-14)
+            np.testing.assert_allclose(t, qrot(st["q_wmap_wodom"], lo["t_w_curr"]) + st["t_wmap_wodom"], atol=1e-12)
+        else:
+            np.testing.assert_array_equal(np.r_[q, t], np.r_[st["q_w_curr"], st["t_w_curr"]])
+    assert flags == [True, False, True, False]

@@ -78,6 +78,7 @@ def lib():
             "vloam_lidar_create": [vp, C.POINTER(LidarParams), pp], "vloam_lidar_destroy": [vp], "vloam_lidar_reset": [vp],
             "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
+            "vloam_scan_registration_ptrs": [vp, vp, vp, C.c_int],
             "vloam_get_input_device": [vp, pp, pp, c_ip, C.POINTER(C.c_size_t)], "vloam_input_consumed": [vp],
             "vloam_shard_buffer": [vp, pp, C.POINTER(C.c_size_t)], "vloam_shard_ipc_handle": [vp, C.c_char_p],
             "vloam_shard_open_ipc": [vp, C.c_int, C.c_int, C.c_char_p], "vloam_shard_enable": [vp, C.c_int, C.c_int, pp],
@@ -91,6 +92,7 @@ def lib():
             "vloam_get_lo_pose": [vp, vp, vp], "vloam_get_lo_pose_prev": [vp, vp, vp], "vloam_set_lo_motion": [vp, c_dp],
             "vloam_set_lo_pose": [vp, c_dp], "vloam_get_lm_status": [vp, c_ip],
             "vloam_get_lm_queries": [vp, C.c_int, C.c_int, C.c_int, c_ip, C.c_int, c_ip],
+            "vloam_get_lm_counters": [vp, C.POINTER(C.c_longlong)], "vloam_lidar_set_debug_stats": [vp, C.c_int],
             "vloam_get_lo_trace": [vp, C.c_int, C.c_int, c_ip, c_dp, c_ip, c_dp],
             "vloam_laser_mapping": [vp, vp], "vloam_get_lm_pose": [vp, c_dp],
             "vloam_map_set_cube": [vp, C.c_int, C.c_int, C.c_int, c_fp, C.c_int],
@@ -239,6 +241,15 @@ class LidarOdometryMapping:
         n_points = np.ascontiguousarray(n_points, np.int32)
         self._keep = (a, n_points)  # keep host buffers alive until the async upload has been consumed
         self.ctx.check(lib().vloam_scan_registration(self._h, _ptr(a), _ptr(n_points), shape[2], shape[1]))
+
+    def scanRegistrationPtrs(self, ptrs, n_points, stride: int, keep=None):
+        """One host buffer per stream: ptrs = (batch,) uint64 array of host addresses (pinned memory uploads asynchronously);
+        `keep` = whatever owns those buffers (kept alive until the next call)."""
+        p = np.ascontiguousarray(ptrs, np.uint64)
+        n = np.ascontiguousarray(n_points, np.int32)
+        assert p.shape == (self.batch,) and n.shape == (self.batch,)
+        self._keep = (p, n, keep)
+        self.ctx.check(lib().vloam_scan_registration_ptrs(self._h, _ptr(p), _ptr(n), stride))
 
     def scanRegistrationDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int):
         """Scans already resident in HBM (torch CUDA tensors or raw device addresses)."""
@@ -415,6 +426,19 @@ class LidarOdometryMapping:
         st = np.zeros((self.batch, 2), np.int32)
         self.ctx.check(lib().vloam_get_lm_status(self._h, st.ctypes.data_as(c_ip)))
         return st
+
+    LM_COUNTERS = ("scans", "solved", "lm_iterations_pass0", "lm_iterations_pass1", "cubes_indexed_corner", "cubes_indexed_surf",
+                   "cubes_rewritten_corner", "cubes_rewritten_surf", "cubes_merged", "cubes_merged_in_place", "cubes_filtered",
+                   "cubes_appended", "voxels_inserted", "repacks", "queries", "factors_last_pass", "knn_queries", "knn_candidates")
+
+    def lm_counters(self):
+        """(batch, 18) int64 cumulative laser-mapping work counters (names: LM_COUNTERS)."""
+        c = np.zeros((self.batch, 18), np.int64)
+        self.ctx.check(lib().vloam_get_lm_counters(self._h, c.ctypes.data_as(C.POINTER(C.c_longlong))))
+        return c
+
+    def set_debug_stats(self, on: bool = True):
+        self.ctx.check(lib().vloam_lidar_set_debug_stats(self._h, int(on)))
 
     def lm_queries(self, pass_: int, kind: int, stream: int = 0):
         """Indices into the down-sampled corner (kind 0) / surf (kind 1) stack that produced a factor in outer pass `pass_`."""

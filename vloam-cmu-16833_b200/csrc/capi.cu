@@ -401,8 +401,12 @@ static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int
 
 // Records of up to 16 floats (a sensor_msgs/PointCloud2 point_step of 64 bytes) are taken as they are: x, y, z first.
 constexpr int kMaxInputStride = 16;
-int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride, size_t slab_points) {
-  if (!h || !xyz || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+}  // extern "C"
+
+// Upload one scan per stream on the copy stream and run scan registration on it.  src(b) = host address of stream b's points;
+// contiguous != nullptr: the slabs are `slab_points` apart in one buffer (one DMA for the whole batch when they line up).
+template <typename Src>
+static int upload_and_register(vloam_lidar* h, Src src, const float* contiguous, const int* n_points, int stride, size_t slab_points) {
   vloam_ctx* c = h->ctx;
   CU(c, cudaSetDevice(c->device));
   if (stride > h->in_stride) {   // first scan with wider records: re-size both input slabs (rare; synchronises)
@@ -425,19 +429,19 @@ int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_point
   if (h->in_used[slot]) CU(c, cudaStreamWaitEvent(c->copy_stream, h->ev_in_free[slot], 0));
   // one DMA for the whole batch when the slabs line up (same count everywhere): a copy per stream costs a few
   // microseconds of set-up each, which shows at PCIe rate (1.5 MB slabs take ~30 us)
-  bool same = true;
+  bool same = contiguous != nullptr;
   for (int b = 1; b < h->B; ++b) same = same && n_points[b] == n_points[0];
   if (same && n_points[0] > 0 && h->B > 1) {
     const size_t row = (size_t)n_points[0] * stride * sizeof(float);
     if (slab_points == (size_t)h->cap && (size_t)n_points[0] == slab_points)
-      CU(c, cudaMemcpyAsync(h->d_in[slot], xyz, row * h->B, cudaMemcpyHostToDevice, c->copy_stream));
+      CU(c, cudaMemcpyAsync(h->d_in[slot], contiguous, row * h->B, cudaMemcpyHostToDevice, c->copy_stream));
     else
-      CU(c, cudaMemcpy2DAsync(h->d_in[slot], (size_t)h->cap * stride * sizeof(float), xyz, slab_points * stride * sizeof(float), row,
+      CU(c, cudaMemcpy2DAsync(h->d_in[slot], (size_t)h->cap * stride * sizeof(float), contiguous, slab_points * stride * sizeof(float), row,
                               (size_t)h->B, cudaMemcpyHostToDevice, c->copy_stream));
   } else {
     for (int b = 0; b < h->B; ++b)
       if (n_points[b])
-        CU(c, cudaMemcpyAsync(h->d_in[slot] + (size_t)b * h->cap * stride, xyz + (size_t)b * slab_points * stride,
+        CU(c, cudaMemcpyAsync(h->d_in[slot] + (size_t)b * h->cap * stride, src(b),
                               (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
   }
   CU(c, cudaMemcpyAsync(h->d_n[slot], n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
@@ -450,6 +454,19 @@ int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_point
   h->last_stride = stride;
   h->host_scans++;
   return VLOAM_OK;
+}
+
+extern "C" {
+
+int vloam_scan_registration(vloam_lidar* h, const float* xyz, const int* n_points, int stride, size_t slab_points) {
+  if (!h || !xyz || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+  return upload_and_register(h, [&](int b) { return xyz + (size_t)b * slab_points * stride; }, xyz, n_points, stride, slab_points);
+}
+
+int vloam_scan_registration_ptrs(vloam_lidar* h, const float* const* xyz_ptrs, const int* n_points, int stride) {
+  if (!h || !xyz_ptrs || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+  for (int b = 0; b < h->B; ++b) if (n_points[b] > 0 && !xyz_ptrs[b]) return VLOAM_E_INVALID;
+  return upload_and_register(h, [&](int b) { return xyz_ptrs[b]; }, nullptr, n_points, stride, (size_t)h->cap);
 }
 
 int vloam_get_input_device(vloam_lidar* h, const float** xyz_dev, const int** n_dev, int* stride_floats, size_t* slab_points) {
@@ -753,6 +770,18 @@ int vloam_get_lm_status(vloam_lidar* h, int* status) {
   CU(c, cudaSetDevice(c->device));
   cudaError_t e = lm_get_status(h->lm, c->stream, status);
   return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_status", e);
+}
+int vloam_get_lm_counters(vloam_lidar* h, long long* counters) {
+  if (!h || !counters) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  cudaError_t e = lm_get_counters(h->lm, c->stream, counters);
+  return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_counters", e);
+}
+int vloam_lidar_set_debug_stats(vloam_lidar* h, int on) {
+  if (!h) return VLOAM_E_INVALID;
+  lm_set_debug_stats(h->lm, on != 0);
+  return VLOAM_OK;
 }
 int vloam_get_lm_queries(vloam_lidar* h, int stream, int pass, int kind, int* out, int capacity, int* n_out) {
   if (!h || stream < 0 || stream >= h->B || pass < 0 || pass > 1 || kind < 0 || kind > 1 || capacity < 0) return VLOAM_E_INVALID;

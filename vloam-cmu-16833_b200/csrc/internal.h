@@ -91,6 +91,8 @@ cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info);
 cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats);
 cudaError_t lm_get_trace(LMDevice* lm, cudaStream_t st, int stream, int pass, double* records, int* info, double* para);
 cudaError_t lm_get_status(LMDevice* lm, cudaStream_t st, int* status);
+cudaError_t lm_get_counters(LMDevice* lm, cudaStream_t st, long long* counters);
+void lm_set_debug_stats(LMDevice* lm, bool on);
 cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out);
 
 }  // namespace vb

@@ -30,6 +30,9 @@ namespace vb {
 
 constexpr int kCubeW = 21, kCubeH = 21, kCubeD = 11, kCubes = kCubeW * kCubeH * kCubeD;  // laser_mapping.h:110-114
 constexpr int kMaxValid = 125;                                                           // laser_mapping.h:116
+// LMState::counters
+enum { kCntScans = 0, kCntSolved, kCntIters0, kCntIters1, kCntIndexedCorner, kCntIndexedSurf, kCntWorkCorner, kCntWorkSurf, kCntMerged,
+       kCntMergedInPlace, kCntFiltered, kCntAppended, kCntVoxelsInserted, kCntRepacks, kCntQueries, kCntFactors };
 // LMState::error bits (vloam_get_lm_status)
 constexpr int kLmErrWorkList = 1;   // more than kMaxWork cubes would be rewritten by one scan: the scan's points were not inserted
 constexpr int kLmErrScratch = 2;    // the re-filter scratch would overflow: the scan's points were not inserted
@@ -80,6 +83,9 @@ struct LMState {
   int error;                            // this scan's error bits (kLmErr*), cleared by lm_prepare
   int errorEver;                        // OR of every scan's error bits since the handle was created
   int applied[2];                       // lm_place committed this scan's rewritten cubes of the kind
+  // cumulative work counters since the handle was created (vloam_get_lm_counters; bench.py reports their per-scan means)
+  int counters[16];
+  unsigned long long knnQueries, knnCandidates;   // filled only while debug statistics are on (vloam_lidar_set_debug_stats)
   SolveTrace trace[2];
 };
 
@@ -94,7 +100,7 @@ struct LMDevice {
   int B = 0, cap = 0, mapCap = 0;
   vloam_lidar_params p{};
   Profiler* prof = nullptr;
-  bool allocated = false, reset_valid = true, ran = false;
+  bool allocated = false, reset_valid = true, ran = false, debugStats = false;
   int curTab = 0;                  // the map = cube slabs in mapPts[LMState::cur] addressed by the tables [curTab]
   LMState* st = nullptr;
   // Cube tables [B][2][kCubes]: a cube is the slab [off, off + cap) of its pool holding cnt points; fix = the cube is a
@@ -388,6 +394,8 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
       }
     st.tabEnd[kind] = te;
     st.buildNum[kind] = nb;
+    st.counters[kCntIndexedCorner + kind] += nb;
+    if (kind == 0) { st.counters[kCntScans]++; st.counters[kCntSolved] += st.solved; }
   }
 }
 
@@ -715,12 +723,14 @@ constexpr int kLmGroup = 8;
 // row (<= 3): the run of sorted positions covering its three columns — at most six runs, looked up by six lanes at once;
 // then every lane takes one candidate of every run (six independent 16-byte loads in flight) and the rare longer runs are
 // finished in a loop.  On the benchmark map that is ~13 candidates per query instead of the 142 of a z-blind 3 x 3 column block.
+template <bool STATS>
 __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                             const CubeTables& T, const short* __restrict__ entryHeadAll,
                                             const int* __restrict__ tabPool, const float4* __restrict__ sorted,
-                                            int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/) {
+                                            int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/, LMState* statsOut) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
+  unsigned nCand = 0, nQuer = 0;      // debug statistics (only accumulated into global memory when statsOut != nullptr)
   if (!st.solved) return;
   const int nq = st.stackNum[kind];
   const int lane = lane_id(), warp = threadIdx.x >> 5;
@@ -803,6 +813,7 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
             // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
             for (; e >= 0; e = st.entryNext[e]) {
               const unsigned gBase = (unsigned)st.validPrefix[kind][e];
+              if (STATS && gl < nruns) nCand += (unsigned)(re - ra);
               // three runs (one z-layer) at a time: three independent candidate loads in flight per lane
               for (int r3 = 0; r3 < nruns; r3 += 3) {
                 int aa[3], ee[3];
@@ -840,6 +851,7 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
       myPos[rr] = wp;
       if (rr == 4) fifth = m;
     }
+    if (STATS && qi < nq && gl == 0) ++nQuer;
     if (qi < nq && gl < 5) {
       const bool ok = fifth != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(fifth >> 32)) < 1.0;  // :479 / :547
       int v = -1;
@@ -848,15 +860,20 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
       outPos[(size_t)qi * 5 + gl] = ok ? v : -1;
     }
   }
+  if (STATS && statsOut != nullptr) {
+    nCand = __reduce_add_sync(0xffffffffu, nCand); nQuer = __reduce_add_sync(0xffffffffu, nQuer);
+    if (lane == 0 && nQuer) { atomicAdd(&statsOut[b].knnCandidates, (unsigned long long)nCand); atomicAdd(&statsOut[b].knnQueries, (unsigned long long)nQuer); }
+  }
 }
 // Two register budgets of the same body (the kernel is bound by memory latency, so occupancy against spills is settled by
 // measurement: VLOAM_LM_KNN_OCC=3|4).
 #define VB_LM_KNN_ARGS                                                                                                            \
   const LMState *__restrict__ stAll, const float4 *__restrict__ stack, int cap, const CubeTables T,                              \
       const short *__restrict__ entryHeadAll, const int *__restrict__ tabPool, const float4 *__restrict__ sorted, int mapCap,    \
-      int *__restrict__ nnPos
-__global__ void __launch_bounds__(256, 4) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos); }
-__global__ void __launch_bounds__(256, 3) lm_knn_occ3(VB_LM_KNN_ARGS) { lm_knn_body(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos); }
+      int *__restrict__ nnPos, LMState *statsOut
+__global__ void __launch_bounds__(256, 4) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
+__global__ void __launch_bounds__(256, 3) lm_knn_occ3(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
+__global__ void __launch_bounds__(256, 3) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
 // grid (nblk, 2, B), block 128: one thread per point
 __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
@@ -922,7 +939,7 @@ __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll,
 // bit-identical state and no broadcast is needed; only rank 0 writes results.
 constexpr int kLmClusterMax = 8;     // cluster size is a launch attribute (1, 2, 4 or 8): see lm_run
 __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
-                                                                                    int cap, int pass, int max_iterations) {
+                                                                                    int cap, int pass, int max_iterations, int lastPass) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
   __shared__ LMShared S;
@@ -981,7 +998,11 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
     __syncthreads();
   };
   lm_solve_block(S, tr, max_iterations, false, evaluate);
-  if (rank == 0 && threadIdx.x == 0) for (int i = 0; i < 7; ++i) st.parameters[i] = S.x[i];
+  if (rank == 0 && threadIdx.x == 0) {
+    for (int i = 0; i < 7; ++i) st.parameters[i] = S.x[i];
+    st.counters[pass == 0 ? kCntIters0 : kCntIters1] += tr->n_records - 1;       // evaluations after the initial one = LM iterations run
+    if (lastPass) st.counters[kCntFactors] += tr->n_corner + tr->n_plane;
+  }
   cluster.sync();                      // nobody leaves while a peer may still read its partial sums
 }
 
@@ -1126,6 +1147,8 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
     for (int u = 0; u < wn; ++u) { st.workIn0[kind][u] = in0; in0 += cnt[st.workCube[kind][u]] + st.workNewN[kind][u]; }
     st.workIn0[kind][wn] = in0;
     st.workNum[kind] = wn;
+    st.counters[kCntWorkCorner + kind] += wn;
+    atomicAdd(&st.counters[kCntQueries], n);
     if ((size_t)in0 + (size_t)cap > workCap) atomicOr(&st.error, kLmErrScratch);
   }
 }
@@ -1272,7 +1295,10 @@ __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __re
     dst[pos + insBefore[r]] = cen;
   }
   const int fixed = __syncthreads_and(inside);
-  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct; }
+  if (tid == 0) {
+    st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = direct;
+    atomicAdd(&st.counters[kCntMerged], 1); atomicAdd(&st.counters[kCntMergedInPlace], direct); atomicAdd(&st.counters[kCntVoxelsInserted], inserted);
+  }
   }
 }
 
@@ -1321,7 +1347,10 @@ __global__ void __launch_bounds__(1024) lm_refilter(LMState* __restrict__ stAll,
     for (int i = tid; i < n; i += 1024) out[i] = i < nOld ? old[i] : sw[vs[i - nOld]];
     m = n;
   }
-  if (tid == 0) { st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = 0; }
+  if (tid == 0) {
+    st.workOutN[kind][u] = m; st.workFixed[kind][u] = fixed; st.workDirect[kind][u] = 0;
+    atomicAdd(&st.counters[st.workFilter[kind][u] ? kCntFiltered : kCntAppended], 1);
+  }
   __syncthreads();   // shared memory is reused by the next cube
   }
 }
@@ -1497,7 +1526,7 @@ __global__ void lm_export_pose(LMState* __restrict__ stAll, double* __restrict__
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
   LMState& s = stAll[b];
-  for (int kind = 0; kind < 2; ++kind) if (s.compact[kind]) { s.cur[kind] ^= 1; s.compact[kind] = 0; s.repacks[kind]++; }
+  for (int kind = 0; kind < 2; ++kind) if (s.compact[kind]) { s.cur[kind] ^= 1; s.compact[kind] = 0; s.repacks[kind]++; s.counters[kCntRepacks]++; }
   double* o = pose + (size_t)b * 16;
   for (int i = 0; i < 7; ++i) o[i] = s.parameters[i];
   for (int i = 0; i < 4; ++i) o[7 + i] = s.q_wmap_wodom[i];
@@ -1534,6 +1563,8 @@ __global__ void lm_init_state(LMState* stAll, int B, int tabLimit) {
   s.cenW = 10; s.cenH = 10; s.cenD = 5;                                       // laser_mapping.h:76-78
   s.validNum = 0; s.fromMapNum[0] = s.fromMapNum[1] = 0; s.stackNum[0] = s.stackNum[1] = 0; s.solved = 0;
   s.poolEnd[0] = s.poolEnd[1] = 0; s.workNum[0] = s.workNum[1] = 0; s.error = 0; s.errorEver = 0; s.applied[0] = s.applied[1] = 0;
+  for (int i = 0; i < 16; ++i) s.counters[i] = 0;
+  s.knnQueries = 0ull; s.knnCandidates = 0ull;
   s.cur[0] = s.cur[1] = 0; s.compact[0] = s.compact[1] = 0; s.repacks[0] = s.repacks[1] = 0;
   s.tabEnd[0] = s.tabEnd[1] = 0; s.buildNum[0] = s.buildNum[1] = 0; s.tabLimit = tabLimit;
   s.trace[0].n_records = s.trace[1].n_records = 0;
@@ -1640,10 +1671,12 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
     static const int knnOcc = [] { const char* e = getenv("VLOAM_LM_KNN_OCC"); return e ? atoi(e) : 4; }();
-    if (knnOcc == 3)
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_occ3<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
+    if (lm->debugStats)
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_stats<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, lm->st));
+    else if (knnOcc == 3)
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_occ3<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
     else
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos));
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
     VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res,
                                                                          lm->fitType + (size_t)tp * B * 2 * cap));
     {
@@ -1660,7 +1693,8 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve, lm->st, (const LMResidual*)lm->res, cap, tp, lm->p.lm_max_iterations));
+      VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve, lm->st, (const LMResidual*)lm->res, cap, tp, lm->p.lm_max_iterations,
+                                                                 pass == lm->p.lm_outer_passes - 1 ? 1 : 0));
     }
   }
   // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back
@@ -1711,6 +1745,23 @@ cudaError_t lm_get_status(LMDevice* lm, cudaStream_t st, int* status) {
   for (int b = 0; b < lm->B; ++b) { status[2 * b] = h[b].error; status[2 * b + 1] = h[b].errorEver | h[b].error; }
   return cudaSuccess;
 }
+
+// counters[B][18]: LMState::counters (16, cumulative) + the k-NN debug statistics (queries, candidates; low 31 bits of the per-stream
+// totals are enough for the benchmark's short statistics pass)
+cudaError_t lm_get_counters(LMDevice* lm, cudaStream_t st, long long* counters) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  std::vector<LMState> h(lm->B);
+  e = cudaMemcpyAsync(h.data(), lm->st, h.size() * sizeof(LMState), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  for (int b = 0; b < lm->B; ++b) {
+    for (int i = 0; i < 16; ++i) counters[(size_t)b * 18 + i] = h[b].counters[i];
+    counters[(size_t)b * 18 + 16] = (long long)h[b].knnQueries; counters[(size_t)b * 18 + 17] = (long long)h[b].knnCandidates;
+  }
+  return cudaSuccess;
+}
+void lm_set_debug_stats(LMDevice* lm, bool on) { if (lm) lm->debugStats = on; }
 
 // Queries (indices into the down-sampled corner / surf stack) that produced a residual block in outer pass `pass` of the last scan.
 cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out) {

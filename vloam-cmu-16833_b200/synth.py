@@ -242,6 +242,36 @@ def make_scans(seed: int, n_scans: int, n_cols: int = N_COLS) -> tuple[list[np.n
     return [s.scan(k) for k in range(n_scans)], s
 
 
+# ------------------------------------------------------------------------------------------------ pre-built map (BASELINE configs[2])
+def map_cubes(n_points: int, seed: int):
+    """A synthetic pre-built map for configs[2]: n_points surf points (one per 0.8 m voxel —
+    the map's own resolution — jittered inside the voxel, on the ground plane and on stacked horizontal layers, so the
+    map keeps its size under the reference's per-scan re-filter) plus 10 % as many corner points (vertical poles), inside
+    the 5 x 5 x 3 cube window around the origin.  Returns {(kind, cube_index): (n, 4) float32}."""
+    rng = np.random.default_rng(seed)
+    k = np.arange(-155, 155)
+    per_layer = k.size * k.size
+    layers = max(1, int(np.ceil(n_points / per_layer)))
+    pts = []
+    for l in range(layers):
+        gx, gy = np.meshgrid((k + 0.5) * 0.8, (k + 0.5) * 0.8)
+        z = -1.73 + 7.0 * l
+        p = np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, z)] + rng.uniform(-0.3, 0.3, (gx.size, 3)) * [1, 1, 0.02]
+        pts.append(p)
+    surf = np.concatenate(pts)[:n_points].astype(np.float32)
+    ncor = max(1000, n_points // 10)
+    cx, cy = rng.uniform(-120, 120, ncor // 20), rng.uniform(-120, 120, ncor // 20)
+    corner = np.c_[np.repeat(cx, 20), np.repeat(cy, 20), np.tile(np.arange(20) * 0.4 - 1.7, ncor // 20)].astype(np.float32)
+    out = {}
+    for kind, cloud in ((0, corner), (1, surf)):
+        ci = (np.floor((cloud[:, 0] + 25.0) / 50.0).astype(int) + 10) + 21 * (np.floor((cloud[:, 1] + 25.0) / 50.0).astype(int) + 10) \
+            + 441 * (np.floor((cloud[:, 2] + 25.0) / 50.0).astype(int) + 5)
+        for c in np.unique(ci):
+            sel = cloud[ci == c]
+            out[(kind, int(c))] = np.c_[sel, np.zeros(len(sel), np.float32)].astype(np.float32)
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ visual odometry inputs
 def kitti_like_calibration():
     """cam_T_velo (4x4), rect0_T_cam (4x4), P_rect0 (3x4): KITTI-like camera 0."""
