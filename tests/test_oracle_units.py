@@ -7,6 +7,8 @@ auto-diff (dual number) Jacobians of the literal functors vs finite differences 
 CUDA kernels use, the Levenberg-Marquardt loop vs scipy.optimize.least_squares, and scan-to-scan odometry vs the
 generator's ground-truth motion.
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -377,3 +379,31 @@ def test_oracle_skip_frame_publishes_high_frequency_pose(oracle, scans_small):
         else:
             np.testing.assert_array_equal(np.r_[q, t], np.r_[st["q_w_curr"], st["t_w_curr"]])
     assert flags == [True, False, True, False]
+
+
+def test_device_atan2f_is_the_c_librarys_atan2f(tmp_path, synth):
+    """The CUDA scan registration computes azimuths with csrc/fdlibm_atan2f.h (the fdlibm algorithm glibc <= 2.40 ships) so
+    that relTime, intensity and the 2 pi unwrapping decisions of scan_registration.cpp:166-262 carry the bits of the
+    platform the reference runs on.  Host build of the same header vs the C library's atan2f: tens of millions of random
+    arguments, the special values, and the (y, x) of a synthetic scan."""
+    import ctypes as C
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so = str(tmp_path / "fdlibm_check.so")
+    subprocess.check_call(["g++", "-O2", "-ffp-contract=off", "-shared", "-fPIC", os.path.join(root, "tests", "native", "fdlibm_check.cpp"), "-o", so])
+    L = C.CDLL(so)
+    L.fd_mismatches.restype = C.c_long
+    L.fd_mismatches.argtypes = [C.c_long, C.c_uint, C.c_float]
+    L.fd_same.argtypes = [C.c_float, C.c_float]
+    for seed, scale in ((1, 80.0), (2, 1.0), (3, 1e-3), (4, 1e6)):
+        assert L.fd_mismatches(8_000_000, seed, scale) == 0, (seed, scale)
+    inf, nan = float("inf"), float("nan")
+    for y in (0.0, -0.0, 1.0, -1.0, inf, -inf, nan, 1e-40, 3e38, 0.4375, 0.6875, 1.1875, 2.4375, 2.0 ** 26, 2.0 ** -30):
+        for x in (0.0, -0.0, 1.0, -1.0, inf, -inf, nan, 1e-40, -1e-40, 3e38, -3e38, 2.0 ** -70, 2.0 ** 70):
+            assert L.fd_same(y, x), (y, x)
+    sc = synth.ScanStream(3, n_cols=512).scan(0)
+    sc = sc[np.isfinite(sc[:, 0])]
+    L.fd_atan2f.restype = C.c_float
+    L.fd_atan2f.argtypes = [C.c_float, C.c_float]
+    for x, y in sc[::5, :2]:
+        assert L.fd_same(float(y), float(x)), (y, x)

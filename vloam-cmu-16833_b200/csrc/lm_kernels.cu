@@ -47,12 +47,11 @@ constexpr int kZBins = 13;       // 13 x 4 m cover the 50 m cube
 constexpr float kZBin = 4.0f;
 constexpr int kZCells = kZBins * kCubeCells;
 // One index table ("slot") per indexed cube:  int hdr[16]: hdr[z] = first sorted position of z-layer z (z < 13), hdr[13] = n,
-// hdr[14] = mode;  then, mode 0: unsigned short rel[13][2501] = start of every column inside its z-layer (rel[z][2500] = size
-// of the layer);  mode 1 (a cube of more than 65 535 points: 16-bit offsets do not reach): int flat[2501] = column starts of
-// a column-only order, no z-layers.
+// hdr[14] = mode;  then, mode 0: unsigned short rel[13][2500] = start of every column inside its z-layer (the end of a layer's
+// last column is the next layer's start);  mode 1 (a cube of more than 65 535 points: 16-bit offsets do not reach):
+// int flat[2501] = column starts of a column-only order, no z-layers.
 constexpr int kTabHdr = 16;
-constexpr int kLayerCells = kCubeCells + 1;
-constexpr int kTabInts = kTabHdr + (kZBins * kLayerCells * 2 + 3) / 4 + 3;   // 16 276 ints = 65 104 bytes, a multiple of 16
+constexpr int kTabInts = kTabHdr + (kZCells + 1) / 2 + 2;   // 16 268 ints = 65 072 bytes, a multiple of 16
 static_assert(kTabInts % 4 == 0 && kTabInts >= kTabHdr + kCubeCells + 1, "slot layout");
 constexpr int kTabSlots = 384;   // index tables per stream and kind (>= the 125 valid cubes + the cubes one scan can touch)
 
@@ -483,7 +482,6 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
   unsigned* s_pack = reinterpret_cast<unsigned*>(smem);            // [(kZCells + 1) / 2]
   int* s_layer = smem + (kZCells + 1) / 2;                         // [kZBins + 1] layer starts
   int* s_w = s_layer + kZBins + 3;                                 // [32]
-  unsigned short* rel = reinterpret_cast<unsigned short*>(tab + kTabHdr);
   auto cell_of = [&](const float4& p) { return cube_zbin(p.z, minZ) * kCubeCells + col_of(p); };
   for (int i = threadIdx.x; i < (kZCells + 1) / 2; i += NT) s_pack[i] = 0u;
   __syncthreads();
@@ -516,18 +514,27 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
     if (threadIdx.x == 0) s_layer[kZBins] = n;
   }
   __syncthreads();
-  {   // 16-bit column starts relative to the layer start; the counters start over at zero for the scatter
+  {   // every counter becomes the 16-bit start of its column relative to the layer start: that IS the table
     int run = base;
+    unsigned word = 0u;
     for (int cell = c0; cell < c1; ++cell) {
-      const int z = cell / kCubeCells;
-      rel[z * kLayerCells + (cell - z * kCubeCells)] = (unsigned short)(run - s_layer[z]);
-      run += get(cell);
+      const int cnt = get(cell);
+      const unsigned r = (unsigned)(run - s_layer[cell / kCubeCells]);
+      if (cell & 1) s_pack[cell >> 1] = word | (r << 16); else word = r;
+      run += cnt;
     }
-    for (int wd = c0 >> 1; wd < (c1 + 1) >> 1; ++wd) s_pack[wd] = 0u;
-    if (threadIdx.x < kZBins) rel[threadIdx.x * kLayerCells + kCubeCells] = (unsigned short)(s_layer[threadIdx.x + 1] - s_layer[threadIdx.x]);
+    if ((c1 & 1) && c1 > c0) s_pack[c1 >> 1] = word;     // (never: c0 and c1 are even)
     if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x <= kZBins ? s_layer[threadIdx.x] : 0;   // hdr[13] = n, hdr[14] = mode 0
   }
-  __syncthreads();     // (also makes the table written above visible to the whole CTA)
+  __syncthreads();
+  // the table goes to global memory as it sits in shared memory: coalesced 32-bit words
+  {
+    unsigned* relw = reinterpret_cast<unsigned*>(tab + kTabHdr);
+    for (int i = threadIdx.x; i < (kZCells + 1) / 2; i += NT) relw[i] = s_pack[i];
+  }
+  __syncthreads();
+  // scatter: the same counters now run from the column's start; the atomic returns a point's position inside its layer
+  // (start + points of the column placed so far <= size of the layer <= 65 535: a half never carries into its neighbour)
   for (int i0 = threadIdx.x; i0 < n; i0 += 4 * NT) {
     float4 p[4];
 #pragma unroll
@@ -537,10 +544,9 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
       const int i = i0 + u * NT;
       if (i < n) {
         const int c = cell_of(p[u]);
-        const int z = c / kCubeCells;
         const unsigned old = atomicAdd(&s_pack[c >> 1], (c & 1) ? 0x10000u : 1u);
         const int within = (int)((c & 1) ? (old >> 16) : (old & 0xffffu));
-        sortedOut[s_layer[z] + (int)rel[z * kLayerCells + (c - z * kCubeCells)] + within] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
+        sortedOut[s_layer[c / kCubeCells] + within] = make_float4(p[u].x, p[u].y, p[u].z, __int_as_float(i));
       }
     }
   }
@@ -804,9 +810,10 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
               if (flat) {
                 ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
               } else {
-                const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kLayerCells + row * kCubeCellsX;
+                const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells + row * kCubeCellsX;
                 const int L = tab[z];
-                ra = L + (int)rel[x0]; re = L + (int)rel[x1 + 1];
+                ra = L + (int)rel[x0];
+                re = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[x1 + 1];   // a layer ends where the next begins
               }
             }
             // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a

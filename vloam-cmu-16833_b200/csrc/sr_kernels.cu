@@ -13,6 +13,8 @@
 //   sr_less_flat_voxel :424-439  per ring: less-flat gather + pcl::VoxelGrid(0.2) restated in shared memory
 //   sr_pack                    ring-major packing of the four feature clouds
 //
+// Azimuths go through vb_fdlibm::atan2f_fd (fdlibm_atan2f.h): the C library's atan2f bit for bit, so relTime / intensity and the
+// 2*pi unwrapping decisions are the reference's.
 // Bit-level decisions (ring id, curvature, thresholds, voxel keys) use explicit
 // round-to-nearest intrinsics so nvcc cannot contract them into FMAs: the CPU
 // reference is built without FMA (CMakeLists.txt:5-6) and the index sets depend on it.
@@ -21,6 +23,7 @@
 #include <cuda_pipeline.h>
 
 #include "common.cuh"
+#include "fdlibm_atan2f.h"
 #include "internal.h"
 
 namespace vb {
@@ -146,8 +149,8 @@ __global__ void __launch_bounds__(kEndsThreads) sr_find_ends(const float* __rest
       const float x0 = p[(size_t)s_first * stride], y0 = p[(size_t)s_first * stride + 1];
       const float x1 = p[(size_t)s_last * stride], y1 = p[(size_t)s_last * stride + 1];
       // :166-176
-      float startOri = -atan2f(y0, x0);
-      float endOri = (float)((double)(-atan2f(y1, x1)) + 2 * kPi);
+      float startOri = -vb_fdlibm::atan2f_fd(y0, x0);
+      float endOri = (float)((double)(-vb_fdlibm::atan2f_fd(y1, x1)) + 2 * kPi);
       if ((double)(__fsub_rn(endOri, startOri)) > 3 * kPi) {
         endOri = (float)((double)endOri - 2 * kPi);
       } else if ((double)(__fsub_rn(endOri, startOri)) < kPi) {
@@ -210,7 +213,7 @@ __global__ void __launch_bounds__(256) sr_classify(const float* __restrict__ xyz
       if (point_valid(x, y, z, thres2)) ring = ring_of(x, y, z, n_scans);
       if (ring >= 0) {
         // :234-250, the not-yet-halfPassed branch: is this the point that flips halfPassed?
-        float ori = -atan2f(y, x);
+        float ori = -vb_fdlibm::atan2f_fd(y, x);
         if ((double)ori < (double)startOri - kPi / 2) ori = (float)((double)ori + 2 * kPi);
         else if ((double)ori > (double)startOri + kPi * 3 / 2) ori = (float)((double)ori - 2 * kPi);
         if ((double)__fsub_rn(ori, startOri) > kPi) myHalf = min(myHalf, i);
@@ -297,7 +300,7 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
     const float* p = xyz + (size_t)b * slab_floats + (size_t)i * stride;
     const float x = p[0], y = p[1], z = p[2];
     const float startOri = h.startOri, endOri = h.endOri;
-    float ori = -atan2f(y, x);
+    float ori = -vb_fdlibm::atan2f_fd(y, x);
     if (i <= h.halfIdx) {  // :235-250
       if ((double)ori < (double)startOri - kPi / 2) ori = (float)((double)ori + 2 * kPi);
       else if ((double)ori > (double)startOri + kPi * 3 / 2) ori = (float)((double)ori - 2 * kPi);
