@@ -20,7 +20,7 @@ def _same_xyz(a, b, name):
     assert a.shape == b.shape, f"{name}: {a.shape} vs {b.shape}"
     if a.shape[0]:
         assert np.array_equal(_bits(a[:, :3]), _bits(b[:, :3])), f"{name}: xyz not bit-identical"
-        assert np.max(np.abs(a[:, 3] - b[:, 3])) < 0.14, f"{name}: intensity"
+        assert np.array_equal(_bits(a[:, 3]), _bits(b[:, 3])), f"{name}: intensity not bit-identical"
 
 
 def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None, before_scan=None):
