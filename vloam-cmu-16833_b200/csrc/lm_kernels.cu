@@ -122,7 +122,7 @@ struct LMDevice {
   LMResidual* res = nullptr;              // [B][2][cap]
   uint8_t* fitType = nullptr;             // [2 passes][B][2][cap] factor type per query and outer pass (vloam_get_lm_queries)
   int* cubeOf = nullptr;                  // [B][2][cap] cube id of every down-sampled scan point (map frame)
-  int* nnPos = nullptr;                   // [B][2][cap][5] positions (in `sorted`) of the five nearest map points per query
+  int* nnPos = nullptr;                   // [B][2][5][cap] positions (in `sorted`) of the five nearest map points per query
   double* pose = nullptr;                 // [B][16]
   short* workOf = nullptr;                // [B][2][kCubes]
   short* liveList = nullptr;              // [B][2][kCubes] cubes a re-pack has to move
@@ -495,35 +495,56 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
       if (i0 + u * NT < n) { const int c = cell_of(p[u]); atomicAdd(&s_pack[c >> 1], (c & 1) ? 0x10000u : 1u); }
   }
   __syncthreads();
-  // exclusive scan over the cells in (z-layer, column) order: a thread owns an even number of consecutive cells, i.e. whole words
-  constexpr int per = (((kZCells + NT - 1) / NT) + 1) & ~1;
-  const int c0 = min((int)threadIdx.x * per, kZCells), c1 = min(c0 + per, kZCells);
-  auto get = [&](int cell) { const unsigned v = s_pack[cell >> 1]; return (int)((cell & 1) ? (v >> 16) : (v & 0xffffu)); };
-  int sum = 0;
-  for (int cell = c0; cell < c1; ++cell) sum += get(cell);
-  int sc = sum;
+  // Exclusive scan over the cells in (z-layer, column) order, a warp per contiguous range of words and a lane per word of a
+  // 32-word row (consecutive lanes -> consecutive banks; a thread walking its own run of words would hit one bank 32 ways).
+  constexpr int kWords = (kZCells + 1) / 2, kWarps = NT / 32;
+  constexpr int kRows = (kWords + 32 * kWarps - 1) / (32 * kWarps);      // rows of 32 words per warp
+  const int w0 = w * kRows * 32;
+  auto warp_scan = [&](int v) {           // inclusive
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
-  if (l == 31) s_w[w] = sc;
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (l >= o) v += t; }
+    return v;
+  };
+  {
+    int sum = 0;
+    for (int r = 0; r < kRows; ++r) {
+      const int j = w0 + r * 32 + l;
+      if (j < kWords) { const unsigned v = s_pack[j]; sum += (int)(v & 0xffffu) + (int)(v >> 16); }
+    }
+    sum = __reduce_add_sync(0xffffffffu, sum);
+    if (l == 0) s_w[w] = sum;
+  }
   __syncthreads();
-  int base = sc - sum;
+  int base = 0;
   for (int q = 0; q < w; ++q) base += s_w[q];
-  {   // the layer starts: position of the first cell of every layer
-    int run = base;
-    for (int cell = c0; cell < c1; ++cell) { if (cell % kCubeCells == 0) s_layer[cell / kCubeCells] = run; run += get(cell); }
+  // pass 1: the layer starts (layer z begins at cell z * 2500: the low half of word z * 1250)
+  {
+    int carry = base;
+    for (int r = 0; r < kRows; ++r) {
+      const int j = w0 + r * 32 + l;
+      const unsigned v = j < kWords ? s_pack[j] : 0u;
+      const int cnt = (int)(v & 0xffffu) + (int)(v >> 16);
+      const int incl = warp_scan(cnt);
+      if (j < kWords && j % (kCubeCells / 2) == 0) s_layer[j / (kCubeCells / 2)] = carry + incl - cnt;
+      carry += __shfl_sync(0xffffffffu, incl, 31);
+    }
     if (threadIdx.x == 0) s_layer[kZBins] = n;
   }
   __syncthreads();
-  {   // every counter becomes the 16-bit start of its column relative to the layer start: that IS the table
-    int run = base;
-    unsigned word = 0u;
-    for (int cell = c0; cell < c1; ++cell) {
-      const int cnt = get(cell);
-      const unsigned r = (unsigned)(run - s_layer[cell / kCubeCells]);
-      if (cell & 1) s_pack[cell >> 1] = word | (r << 16); else word = r;
-      run += cnt;
+  // pass 2: every counter becomes the 16-bit start of its column relative to its layer's start: that IS the table
+  {
+    int carry = base;
+    for (int r = 0; r < kRows; ++r) {
+      const int j = w0 + r * 32 + l;
+      const unsigned v = j < kWords ? s_pack[j] : 0u;
+      const int lo = (int)(v & 0xffffu), cnt = lo + (int)(v >> 16);
+      const int incl = warp_scan(cnt);
+      if (j < kWords) {
+        const int start = carry + incl - cnt - s_layer[(2 * j) / kCubeCells];     // both cells of a word lie in one layer (2500 is even)
+        s_pack[j] = (unsigned)start | ((unsigned)(start + lo) << 16);
+      }
+      carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if ((c1 & 1) && c1 > c0) s_pack[c1 >> 1] = word;     // (never: c0 and c1 are even)
     if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x <= kZBins ? s_layer[threadIdx.x] : 0;   // hdr[13] = n, hdr[14] = mode 0
   }
   __syncthreads();
@@ -723,25 +744,23 @@ __device__ __forceinline__ void colpiv_qr_solve_5x3_dev(const double Ain[15], co
 //           sorted top-5, the group merges them; writes the five positions (or -1: fifth neighbour not within 1 m).
 //   lm_fit  one THREAD per point: PCA line test (corner) or least-squares plane fit + 0.2 m check (surf) on the five
 //           neighbours, in double like the reference.  (Done by whole warps this part ran 32 times redundantly.)
-constexpr int kLmGroup = 8;
-// grid (nblk, 2, B), block 256: a CTA takes chunks of 32 points (8 warps x 4 groups), grid-stride.
-// Candidates of a query = per cube its 1.001 m box touches, per z-layer its +-1.001 m interval touches (<= 2), per column
-// row (<= 3): the run of sorted positions covering its three columns — at most six runs, looked up by six lanes at once;
-// then every lane takes one candidate of every run (six independent 16-byte loads in flight) and the rare longer runs are
-// finished in a loop.  On the benchmark map that is ~13 candidates per query instead of the 142 of a z-blind 3 x 3 column block.
+// lm_knn: grid (kKnnGrid, 2, B), block 128: one THREAD per down-sampled scan point, grid-stride.
+// Candidates of a query = per cube its 1.001 m box touches (one, unless the query sits at a cube border), per z-layer its
+// +-1.001 m interval touches (<= 2), per column row (<= 3): the run of sorted positions covering its three columns.  On
+// the benchmark map that is ~25 candidates per query instead of the 142 of a z-blind 3 x 3 column block, so the search is a
+// short serial scan: a thread per query needs no cross-lane merge at all.  (Round 1 and the first z-layered version used
+// an 8-lane group per query: ncu counted ~390 warp instructions per query, two thirds of them the per-query set-up,
+// shuffles and the five-round group merge, each executed by all 8 lanes.)
+constexpr int kKnnGrid = 48, kKnnThreads = 128;
 template <bool STATS>
 __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                             const CubeTables& T, const short* __restrict__ entryHeadAll,
                                             const int* __restrict__ tabPool, const float4* __restrict__ sorted,
-                                            int mapCap, int* __restrict__ nnPos /*[B][2][cap][5]*/, LMState* statsOut) {
+                                            int mapCap, int* __restrict__ nnPos /*[B][2][5][cap]*/, LMState* statsOut) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
-  unsigned nCand = 0, nQuer = 0;      // debug statistics (only accumulated into global memory when statsOut != nullptr)
   if (!st.solved) return;
   const int nq = st.stackNum[kind];
-  const int lane = lane_id(), warp = threadIdx.x >> 5;
-  const int g = lane / kLmGroup, gl = lane % kLmGroup;
-  const unsigned gmask = 0xffu << (g * kLmGroup);
   const size_t tb = ((size_t)b * 2 + kind) * kCubes;
   const short* entryHead = entryHeadAll + (size_t)b * kCubes;
   const int* tabs = tabPool + ((size_t)b * 2 + kind) * kTabSlots * kTabInts;
@@ -751,136 +770,103 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
   int* outPos = nnPos + ((size_t)b * 2 + kind) * cap * 5;
   const double qq[4] = {st.parameters[0], st.parameters[1], st.parameters[2], st.parameters[3]};
   const double t0 = st.parameters[4], t1 = st.parameters[5], t2 = st.parameters[6];
-  for (int base = (blockIdx.x * 8 + warp) * 4; base < nq; base += gridDim.x * 32) {
-    const int qi = base + g;
+  unsigned nCand = 0, nQuer = 0;      // debug statistics (only accumulated into global memory when STATS)
+  for (int qi = blockIdx.x * kKnnThreads + threadIdx.x; qi < nq; qi += gridDim.x * kKnnThreads) {
     unsigned long long bk[5];
     int bp[5];
 #pragma unroll
     for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
     unsigned wbits = 0x3f7fffffu;   // the largest float below 1.0f (non-negative floats order like their bit patterns)
-    if (qi < nq) {
-      const float4 po = stk[qi];
-      // pointAssociateToMap (:146-155): double transform, rounded to float
-      double w[3];
-      quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
-      const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
-      // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped, :479 / :547,
-      // and then every true neighbour is), and none farther than this lane's 5th best.  The distance is
-      // (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
-      auto consider = [&](const float4 tp, unsigned gBase, int pos) {
-        const float dz = __fsub_rn(sz, tp.z);
-        if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) return;
-        const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
-        if (__float_as_uint(d) > wbits) return;
-        unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
-        if (key < bk[4]) {
+    const float4 po = stk[qi];
+    // pointAssociateToMap (:146-155): double transform, rounded to float
+    double w[3];
+    quat_rotate(qq, (double)po.x, (double)po.y, (double)po.z, w);
+    const float sx = (float)(w[0] + t0), sy = (float)(w[1] + t1), sz = (float)(w[2] + t2);
+    // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped, :479 / :547,
+    // and then every true neighbour is), and none farther than the current 5th best.  The distance is
+    // (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
+    auto consider = [&](const float4 tp, unsigned gBase, int pos) {
+      const float dz = __fsub_rn(sz, tp.z);
+      if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) return;
+      const float d = sqdist_f(sx, sy, sz, tp.x, tp.y, tp.z);
+      if (__float_as_uint(d) > wbits) return;
+      unsigned long long key = ((unsigned long long)__float_as_uint(d) << 32) | (gBase + (unsigned)__float_as_int(tp.w));
+      if (key < bk[4]) {
 #pragma unroll
-          for (int i = 0; i < 5; ++i)
-            if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
-          wbits = min(wbits, (unsigned)(bk[4] >> 32));
-        }
-      };
-      // every cube the 1.001 m box around the query touches (one, unless the query sits at a cube border) ...
-      const int ci0 = max(cube_coord((double)sx - 1.001, cenW), 0), ci1 = min(cube_coord((double)sx + 1.001, cenW), kCubeW - 1);
-      const int cj0 = max(cube_coord((double)sy - 1.001, cenH), 0), cj1 = min(cube_coord((double)sy + 1.001, cenH), kCubeH - 1);
-      const int ck0 = max(cube_coord((double)sz - 1.001, cenD), 0), ck1 = min(cube_coord((double)sz + 1.001, cenD), kCubeD - 1);
-      for (int ck = ck0; ck <= ck1; ++ck)
-        for (int cj = cj0; cj <= cj1; ++cj)
-          for (int ci = ci0; ci <= ci1; ++ci) {
-            const int c = ci + kCubeW * cj + kCubeW * kCubeH * ck;
-            int e = entryHead[c];
-            if (e < 0) continue;                       // not part of the sub-map (:404-420)
-            const int slot = T.tab[tb + c];
-            if (slot < 0) continue;                    // empty cube
-            const int* tab = tabs + (size_t)slot * kTabInts;
-            const int off = T.off[tb + c];
-            const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH), mnz = cube_min_coord(ck, cenD);
-            const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
-            const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
-            const int r0 = max(qy - 1, 0), r1 = min(qy + 1, kCubeCellsX - 1);
-            if (x0 > x1 || r0 > r1) continue;
-            // the z-layers the +-1.001 m interval touches (the clamped bin function of the build is monotone, so every point
-            // within 1 m in z lies in one of them); a cube in mode 1 has a single layer
-            const bool flat = tab[14] != 0;
-            const int zb0 = flat ? 0 : cube_zbin(sz - 1.001f, mnz), zb1 = flat ? 0 : cube_zbin(sz + 1.001f, mnz);
-            const int nr = r1 - r0 + 1, nruns = (zb1 - zb0 + 1) * nr;      // <= 2 x 3
-            int ra = 0, re = 0;
-            if (gl < nruns) {
-              const int z = zb0 + gl / nr, row = r0 + gl % nr;
-              if (flat) {
-                ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
-              } else {
-                const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells + row * kCubeCellsX;
-                const int L = tab[z];
-                ra = L + (int)rel[x0];
-                re = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[x1 + 1];   // a layer ends where the next begins
-              }
-            }
-            // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
-            // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
-            for (; e >= 0; e = st.entryNext[e]) {
-              const unsigned gBase = (unsigned)st.validPrefix[kind][e];
-              if (STATS && gl < nruns) nCand += (unsigned)(re - ra);
-              // three runs (one z-layer) at a time: three independent candidate loads in flight per lane
-              for (int r3 = 0; r3 < nruns; r3 += 3) {
-                int aa[3], ee[3];
-                float4 tp[3];
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                  aa[r] = __shfl_sync(gmask, ra, r3 + r, kLmGroup) + gl; ee[r] = __shfl_sync(gmask, re, r3 + r, kLmGroup);
-                  if (aa[r] < ee[r]) tp[r] = S[off + aa[r]];
+        for (int i = 0; i < 5; ++i)
+          if (key < bk[i]) { const unsigned long long tk = bk[i]; bk[i] = key; key = tk; const int tq = bp[i]; bp[i] = pos; pos = tq; }
+        wbits = min(wbits, (unsigned)(bk[4] >> 32));
+      }
+    };
+    // Every cube the 1.001 m box around the query touches.  A superset is harmless (a cube that holds nothing near the query
+    // contributes empty or far-away runs), so the cube range is computed in float with a margin that dominates the rounding:
+    // floor((v + 25) / 50) + cen, the cube coordinate of laser_mapping.cpp:643-652 for in-range values.
+    const int ci0 = max((int)floorf((sx + 23.995f) * 0.02f) + cenW, 0), ci1 = min((int)floorf((sx + 26.005f) * 0.02f) + cenW, kCubeW - 1);
+    const int cj0 = max((int)floorf((sy + 23.995f) * 0.02f) + cenH, 0), cj1 = min((int)floorf((sy + 26.005f) * 0.02f) + cenH, kCubeH - 1);
+    const int ck0 = max((int)floorf((sz + 23.995f) * 0.02f) + cenD, 0), ck1 = min((int)floorf((sz + 26.005f) * 0.02f) + cenD, kCubeD - 1);
+    for (int ck = ck0; ck <= ck1; ++ck)
+      for (int cj = cj0; cj <= cj1; ++cj)
+        for (int ci = ci0; ci <= ci1; ++ci) {
+          const int c = ci + kCubeW * cj + kCubeW * kCubeH * ck;
+          int e = entryHead[c];
+          if (e < 0) continue;                       // not part of the sub-map (:404-420)
+          const int slot = T.tab[tb + c];
+          if (slot < 0) continue;                    // empty cube
+          const int* tab = tabs + (size_t)slot * kTabInts;
+          const int off = T.off[tb + c];
+          const float mnx = cube_min_coord(ci, cenW), mny = cube_min_coord(cj, cenH), mnz = cube_min_coord(ck, cenD);
+          const int qx = cube_cell(sx, mnx), qy = cube_cell(sy, mny);
+          const int x0 = max(qx - 1, 0), x1 = min(qx + 1, kCubeCellsX - 1);
+          const int r0 = max(qy - 1, 0), r1 = min(qy + 1, kCubeCellsX - 1);
+          if (x0 > x1 || r0 > r1) continue;
+          // the z-layers the +-1.001 m interval touches (the clamped bin function of the build is monotone, so every point
+          // within 1 m in z lies in one of them); a cube in mode 1 has a single layer
+          const bool flat = tab[14] != 0;
+          const int zb0 = flat ? 0 : cube_zbin(sz - 1.001f, mnz), zb1 = flat ? 0 : cube_zbin(sz + 1.001f, mnz);
+          // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
+          // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
+          for (; e >= 0; e = st.entryNext[e]) {
+            const unsigned gBase = (unsigned)st.validPrefix[kind][e];
+            for (int z = zb0; z <= zb1; ++z) {
+              const int L = flat ? 0 : tab[z];
+              const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells;
+              for (int row = r0; row <= r1; ++row) {
+                int ra, re;
+                if (flat) {
+                  ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
+                } else {
+                  ra = L + (int)rel[row * kCubeCellsX + x0];
+                  re = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[row * kCubeCellsX + x1 + 1];   // a layer ends where the next begins
                 }
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                  if (aa[r] < ee[r]) consider(tp[r], gBase, off + aa[r]);
-                  for (int t = aa[r] + kLmGroup; t < ee[r]; t += kLmGroup) consider(S[off + t], gBase, off + t);   // (rare: a run of more than 8 points)
+                if (STATS) nCand += (unsigned)(re - ra);
+                // two candidates in flight
+                int t = ra;
+                for (; t + 1 < re; t += 2) {
+                  const float4 p0 = S[off + t], p1 = S[off + t + 1];
+                  consider(p0, gBase, off + t);
+                  consider(p1, gBase, off + t + 1);
                 }
+                if (t < re) consider(S[off + t], gBase, off + t);
               }
             }
           }
-    }
-    // group merge: five rounds of "smallest head wins" (keys are unique: the low word is the sub-map index)
-    int head = 0, myPos[5];
-    unsigned long long fifth = 0xffffffffffffffffull;
+        }
+    if (STATS) ++nQuer;
+    const bool ok = bk[4] != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(bk[4] >> 32)) < 1.0;  // :479 / :547
 #pragma unroll
-    for (int rr = 0; rr < 5; ++rr) {
-      unsigned long long mine = 0xffffffffffffffffull;
-      int minePos = -1;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) if (i == head) { mine = bk[i]; minePos = bp[i]; }
-      unsigned long long m = mine;
-#pragma unroll
-      for (int o = kLmGroup / 2; o > 0; o >>= 1) { const unsigned long long t = __shfl_xor_sync(gmask, m, o); m = t < m ? t : m; }
-      const bool won = mine == m && m != 0xffffffffffffffffull;
-      const unsigned win = __ballot_sync(gmask, won) & gmask;
-      int wp = -1;
-      if (win) { wp = __shfl_sync(gmask, minePos, __ffs(win) - 1); if (won) head++; }
-      myPos[rr] = wp;
-      if (rr == 4) fifth = m;
-    }
-    if (STATS && qi < nq && gl == 0) ++nQuer;
-    if (qi < nq && gl < 5) {
-      const bool ok = fifth != 0xffffffffffffffffull && (double)__uint_as_float((unsigned)(fifth >> 32)) < 1.0;  // :479 / :547
-      int v = -1;
-#pragma unroll
-      for (int i = 0; i < 5; ++i) if (i == gl) v = myPos[i];
-      outPos[(size_t)qi * 5 + gl] = ok ? v : -1;
-    }
+    for (int i = 0; i < 5; ++i) outPos[(size_t)i * cap + qi] = ok ? bp[i] : -1;
   }
   if (STATS && statsOut != nullptr) {
-    nCand = __reduce_add_sync(0xffffffffu, nCand); nQuer = __reduce_add_sync(0xffffffffu, nQuer);
-    if (lane == 0 && nQuer) { atomicAdd(&statsOut[b].knnCandidates, (unsigned long long)nCand); atomicAdd(&statsOut[b].knnQueries, (unsigned long long)nQuer); }
+    nCand = __reduce_add_sync(__activemask(), nCand); nQuer = __reduce_add_sync(__activemask(), nQuer);
+    if (lane_id() == 0 && nQuer) { atomicAdd(&statsOut[b].knnCandidates, (unsigned long long)nCand); atomicAdd(&statsOut[b].knnQueries, (unsigned long long)nQuer); }
   }
 }
-// Two register budgets of the same body (the kernel is bound by memory latency, so occupancy against spills is settled by
-// measurement: VLOAM_LM_KNN_OCC=3|4).
 #define VB_LM_KNN_ARGS                                                                                                            \
   const LMState *__restrict__ stAll, const float4 *__restrict__ stack, int cap, const CubeTables T,                              \
       const short *__restrict__ entryHeadAll, const int *__restrict__ tabPool, const float4 *__restrict__ sorted, int mapCap,    \
       int *__restrict__ nnPos, LMState *statsOut
-__global__ void __launch_bounds__(256, 4) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
-__global__ void __launch_bounds__(256, 3) lm_knn_occ3(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
-__global__ void __launch_bounds__(256, 3) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
+__global__ void __launch_bounds__(kKnnThreads) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
+__global__ void __launch_bounds__(kKnnThreads) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
 // grid (nblk, 2, B), block 128: one thread per point
 __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
@@ -900,7 +886,7 @@ __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll,
     for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
     int pos[5];
 #pragma unroll
-    for (int j = 0; j < 5; ++j) pos[j] = inPos[(size_t)qi * 5 + j];
+    for (int j = 0; j < 5; ++j) pos[j] = inPos[(size_t)j * cap + qi];
     if (pos[4] >= 0) {
       double P[5][3];
 #pragma unroll
@@ -1677,13 +1663,10 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
-    static const int knnOcc = [] { const char* e = getenv("VLOAM_LM_KNN_OCC"); return e ? atoi(e) : 4; }();
     if (lm->debugStats)
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_stats<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, lm->st));
-    else if (knnOcc == 3)
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_occ3<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_stats<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, lm->st));
     else
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(128, 2, B), 256, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
     VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res,
                                                                          lm->fitType + (size_t)tp * B * 2 * cap));
     {
