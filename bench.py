@@ -228,7 +228,7 @@ def config_dict(args, streams_per_gpu, handles, world, do_map, extra=None):
     """The `config` object both arms print (same keys, same values for the same command line)."""
     c = {"workload": WORKLOAD_NAME[args.workload][1], "streams_per_gpu": streams_per_gpu, "handles": handles,
          "points_per_scan": N_RINGS * N_COLS, "lo_passes": 2, "lo_iterations_per_pass": 4, "lm_passes": 2,
-         "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0,
+         "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0, "solver_mode": args.solver_mode,
          "trajectory": f"{N_BASE} seeded base sequences x {TRAJ_SCANS} consecutive scans (forward drive, no replay within {TRAJ_SCANS} steps), "
                        "tiled across the streams"}
     if extra:
@@ -443,7 +443,8 @@ def run_ours(args, rank, world, local_rank):
         def __init__(self, ctx_, b0, b1):
             self.ctx, self.b0, self.b1, self.nb = ctx_, b0, b1, b1 - b0
             self.lom = V.LidarOdometryMapping(ctx_, batch=self.nb, max_points=cap, map_capacity_points=map_cap,
-                                              detach_VO_LO=0 if do_vo else 1, lm_max_iterations=args.lm_iterations)
+                                              detach_VO_LO=0 if do_vo else 1, lm_max_iterations=args.lm_iterations,
+                                              solver_mode=args.solver_mode)
             for (kind, cube), pts in map_cubes.items():      # the same pre-built map under every stream
                 for b in range(self.nb):
                     self.lom.map_set_cube(kind, cube, pts, stream=b)
@@ -874,6 +875,8 @@ def main():
     ap.add_argument("--parallelism", default="stream", choices=["stream", "point"],
                     help="N > 1: stream = independent streams per rank (weak scaling, headline); point = every rank holds all "
                          "streams and a slice of each stream's correspondences, normal equations summed in-kernel over NVLink")
+    ap.add_argument("--solver-mode", type=int, default=0, choices=[0, 1, 2],
+                    help="vloam_lidar_params::solver_mode: 0 = by batch size, 1 = one CTA (cluster) per stream, 2 = wide accumulate + step launches")
     ap.add_argument("--legs", default="all", choices=["all", "device"], help="device: only the HBM-resident timed leg (for ncu runs)")
     args = ap.parse_args()
     if args.lm_iterations <= 0:

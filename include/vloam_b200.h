@@ -111,6 +111,9 @@ typedef struct vloam_lidar_params {
   int map_capacity_points;         /* capacity of the rolling map per stream and per feature kind */
   int debug_keep_submap;           /* 1: keep a copy of laserCloudCornerFromMap / SurfFromMap (laser_mapping.cpp:422-428) of the
                                       last scan for vloam_get_cloud(VLOAM_CLOUD_*_MAP); costs one sub-map copy per scan */
+  int solver_mode;                 /* how ceres::Solve is laid out on the GPU: 0 = by batch size, 1 = one CTA (or cluster) per stream,
+                                      whole solve in one launch (small batches: fewest launches), 2 = wide: one launch over all
+                                      residual blocks of all streams per Levenberg-Marquardt evaluation + a warp-per-stream step */
 } vloam_lidar_params;
 
 /* Fills the reference's KITTI HDL-64 launch-file values. */
@@ -236,6 +239,15 @@ int vloam_shard_open_ipc(vloam_lidar* h, int rank, int world, const unsigned cha
 int vloam_shard_enable(vloam_lidar* h, int rank, int world, void* const* peer_ptrs);
 int vloam_shard_disable(vloam_lidar* h);
 int vloam_shard_status(vloam_lidar* h, int* error_bits);
+/* The same split with the exchange done by NCCL, as BASELINE configs[4] words it: every Levenberg-Marquardt evaluation of laser
+ * odometry AND laser mapping is one wide accumulate launch (tiles x streams, 28-double partial normal equations per tile),
+ * an ncclAllReduce of the partials over the ranks, and a warp-per-stream step kernel; each rank associates and accumulates
+ * its slice of the queries.  The library resolves NCCL at run time from the process (torch's libnccl) or VLOAM_NCCL_LIB.
+ *   vloam_shard_nccl_unique_id : rank 0 creates the 128-byte ncclUniqueId, the caller broadcasts it (any transport)
+ *   vloam_shard_nccl_init      : collective over the group; afterwards every laser odometry / mapping call is collective too */
+int vloam_shard_nccl_unique_id(unsigned char* id128);
+int vloam_shard_nccl_init(vloam_lidar* h, int rank, int world, const unsigned char* id128);
+int vloam_shard_nccl_destroy(vloam_lidar* h);
 
 /* ------------------------------------------------------------------ visual odometry (depth association + residuals)
  * VisualOdometry::setUpPointCloud   visual_odometry.cpp:132-155: cam_T_velo[16], rect0_T_cam[16], P_rect0[12], row-major float */

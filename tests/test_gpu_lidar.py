@@ -81,11 +81,13 @@ def _check_lo(lom, olo, pose, stream=0, require_identical_sets=True):
     return float(np.max(np.abs(pose["t_last_curr"][stream] - st["t_last_curr"])))
 
 
-def test_scan_registration_and_odometry_full_size(scans_full, oracle):
-    """BASELINE configs[1] shape: 64 x 2048 scans, scanRegistration + laserOdometry, one stream."""
+@pytest.mark.parametrize("solver_mode", [1, 2])
+def test_scan_registration_and_odometry_full_size(scans_full, oracle, solver_mode):
+    """BASELINE configs[1] shape: 64 x 2048 scans, scanRegistration + laserOdometry, one stream; both layouts of the solve
+    (vloam_lidar_params::solver_mode)."""
     import vloam_b200 as V
     scans, _ = scans_full
-    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0])
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], solver_mode=solver_mode)
     olo = oracle.LaserOdometry()
     worst = 0.0
     for k, scan in enumerate(scans):

@@ -23,8 +23,11 @@ def _same_xyz(a, b, name):
         assert np.array_equal(_bits(a[:, 3]), _bits(b[:, 3])), f"{name}: intensity not bit-identical"
 
 
-def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None, before_scan=None):
-    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=map_capacity, debug_keep_submap=1)
+def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stats_out=None, before_scan=None, solver_mode=0, nccl=False):
+    lom = V.LidarOdometryMapping(batch=1, max_points=scans[0].shape[0], map_capacity_points=map_capacity, debug_keep_submap=1,
+                                 solver_mode=solver_mode)
+    if nccl:
+        lom.shard_nccl_init(0, 1, V.shard_nccl_unique_id())
     pipe = oracle.Pipeline()
     worst_t = 0.0
     for k, scan in enumerate(scans):
@@ -83,12 +86,25 @@ def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stat
     return worst_t
 
 
-def test_laser_mapping_sequence(synth, oracle):
+@pytest.mark.parametrize("solver_mode", [1, 2])
+def test_laser_mapping_sequence(synth, oracle, solver_mode):
+    """solver_mode 1: the whole ceres::Solve of a pass in one launch, a CTA (cluster) per stream; 2: one wide accumulate launch
+    per Levenberg-Marquardt evaluation + a warp-per-stream step (gn_split.cuh).  Same traces, same poses, same map."""
     import vloam_b200 as V
     s = synth.ScanStream(31, n_cols=1024)
     scans = [s.scan(k) for k in range(5)]
-    worst = _run_sequence(V, oracle, scans)
+    worst = _run_sequence(V, oracle, scans, solver_mode=solver_mode)
     print("max |t_w_curr - oracle| =", worst)
+
+
+def test_laser_mapping_sequence_nccl_exchange_single_rank(synth, oracle):
+    """The point-sharded layout of BASELINE configs[4] with a group of one rank: wide accumulate, ncclAllReduce of the partial
+    normal equations (the identity here), step — odometry and mapping.  Exercises the run-time NCCL binding and the
+    collective path on one GPU; the multi-GPU run is scripts/run_point_sharded.sh."""
+    import vloam_b200 as V
+    s = synth.ScanStream(31, n_cols=1024)
+    scans = [s.scan(k) for k in range(4)]
+    _run_sequence(V, oracle, scans, nccl=True)
 
 
 def test_laser_mapping_full_size(synth, oracle):

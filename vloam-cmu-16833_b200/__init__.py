@@ -45,7 +45,7 @@ class LidarParams(C.Structure):
                 ("mapping_line_resolution", C.c_double), ("mapping_plane_resolution", C.c_double),
                 ("mapping_skip_frame", C.c_int), ("detach_VO_LO", C.c_int), ("lo_outer_passes", C.c_int),
                 ("lo_max_iterations", C.c_int), ("lm_outer_passes", C.c_int), ("lm_max_iterations", C.c_int),
-                ("map_capacity_points", C.c_int), ("debug_keep_submap", C.c_int)]
+                ("map_capacity_points", C.c_int), ("debug_keep_submap", C.c_int), ("solver_mode", C.c_int)]
 
 
 def build(verbose: bool = False) -> str:
@@ -83,6 +83,8 @@ def lib():
             "vloam_shard_buffer": [vp, pp, C.POINTER(C.c_size_t)], "vloam_shard_ipc_handle": [vp, C.c_char_p],
             "vloam_shard_open_ipc": [vp, C.c_int, C.c_int, C.c_char_p], "vloam_shard_enable": [vp, C.c_int, C.c_int, pp],
             "vloam_shard_disable": [vp], "vloam_shard_status": [vp, c_ip],
+            "vloam_shard_nccl_unique_id": [C.c_char_p], "vloam_shard_nccl_init": [vp, C.c_int, C.c_int, C.c_char_p],
+            "vloam_shard_nccl_destroy": [vp],
             "vloam_get_stream_status": [vp, c_ip], "vloam_get_feature_counts": [vp, c_ip],
             "vloam_get_cloud": [vp, C.c_int, C.c_int, c_fp, C.c_int, c_ip],
             "vloam_get_curvature": [vp, C.c_int, c_fp, C.c_int, c_ip],
@@ -124,6 +126,15 @@ def lib():
         L.vloam_ctx_launch_count.argtypes = [vp]
         _lib = L
     return _lib
+
+
+def shard_nccl_unique_id() -> bytes:
+    """A fresh 128-byte ncclUniqueId (rank 0 creates it, the caller broadcasts it)."""
+    buf = C.create_string_buffer(128)
+    rc = lib().vloam_shard_nccl_unique_id(buf)
+    if rc != VLOAM_OK:
+        raise VloamError(f"vloam_shard_nccl_unique_id failed with {rc}: no libnccl in the process?")
+    return buf.raw
 
 
 def exported_symbols_in_header() -> list[str]:
@@ -285,6 +296,14 @@ class LidarOdometryMapping:
     def shard_enable(self, rank: int, world: int, peer_ptrs):
         arr = (C.c_void_p * world)(*[C.c_void_p(int(p)) for p in peer_ptrs])
         self.ctx.check(lib().vloam_shard_enable(self._h, rank, world, arr))
+
+    def shard_nccl_init(self, rank: int, world: int, unique_id: bytes):
+        """Point-sharded streams with the exchange done by ncclAllReduce (collective over the group)."""
+        assert len(unique_id) == 128
+        self.ctx.check(lib().vloam_shard_nccl_init(self._h, rank, world, unique_id))
+
+    def shard_nccl_destroy(self):
+        self.ctx.check(lib().vloam_shard_nccl_destroy(self._h))
 
     def shard_disable(self):
         self.ctx.check(lib().vloam_shard_disable(self._h))

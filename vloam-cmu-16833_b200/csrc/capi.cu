@@ -1,6 +1,9 @@
 // vloam_b200 — C-ABI implementation (include/vloam_b200.h): handles, device buffers, launch sequencing.
 // No torch types, no CPU fallback: every entry point either runs the CUDA path or returns an error code.
+#include <dlfcn.h>
+
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -8,6 +11,7 @@
 
 #include "../../include/vloam_b200.h"
 #include "common.cuh"
+#include "gn_split.cuh"
 #include "internal.h"
 
 using namespace vb;
@@ -20,6 +24,7 @@ const char* kernel_name(int id) {
       "sr_find_ends", "sr_classify", "sr_scan", "sr_scatter", "sr_curvature", "sr_pick_features", "sr_less_flat_voxel", "sr_pack",
       "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state", "lo_build_grid", "lo_associate_brute",
       "lm_prepare", "lm_voxel", "lm_index", "lm_associate", "lm_fit", "lm_solve", "lm_insert", "lm_refilter", "lm_place", "lm_misc",
+      "lo_accumulate", "lo_step", "lm_accumulate", "lm_step",
       "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
@@ -54,6 +59,53 @@ void Profiler::clear() { for (int i = 0; i < K_COUNT; ++i) { ms[i] = 0; cnt[i] =
 Profiler::~Profiler() {
   collect();
   for (cudaEvent_t e : pool) cudaEventDestroy(e);
+}
+}  // namespace vb
+
+// ---------------------------------------------------------------------------------------------------------------
+// NCCL binding (BASELINE configs[4]: "NCCL allreduce of 6x6 J'J per GN iteration").  The library does not link NCCL: the
+// four entry points it needs are resolved at run time from the libnccl the process already carries (torch's) or from
+// VLOAM_NCCL_LIB.  Only the point-sharded mode uses it; everything else runs without NCCL present.
+struct NcclId { char internal[128]; };      // ncclUniqueId
+namespace {
+struct NcclApi {
+  void* lib = nullptr;
+  int (*GetUniqueId)(void*) = nullptr;
+  int (*CommInitRank)(void**, int, /* ncclUniqueId by value: 128 bytes */ NcclId, int) = nullptr;
+  int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+  int (*CommDestroy)(void*) = nullptr;
+  const char* (*GetErrorString)(int) = nullptr;
+};
+NcclApi* nccl_api() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    const char* names[] = {getenv("VLOAM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      if (!n || !*n) continue;
+      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.lib) break;
+    }
+    if (api.lib) {
+      api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));
+      api.CommInitRank = reinterpret_cast<int (*)(void**, int, NcclId, int)>(dlsym(api.lib, "ncclCommInitRank"));
+      api.AllReduce = reinterpret_cast<int (*)(const void*, void*, size_t, int, int, void*, cudaStream_t)>(dlsym(api.lib, "ncclAllReduce"));
+      api.CommDestroy = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclCommDestroy"));
+      api.GetErrorString = reinterpret_cast<const char* (*)(int)>(dlsym(api.lib, "ncclGetErrorString"));
+      if (!api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.CommDestroy) api.lib = nullptr;
+    }
+  }
+  return api.lib ? &api : nullptr;
+}
+}  // namespace
+
+namespace vb {
+// The exchange step of the wide solve for point-sharded streams: sum the partial normal equations (or the correspondence
+// counts) over the ranks, in place, on the solve's stream.  ncclFloat64 = 8, ncclSum = 0.
+void gn_allreduce_partials(void* ncclComm, double* partial, size_t count, cudaStream_t st) {
+  NcclApi* api = nccl_api();
+  if (api && ncclComm) api->AllReduce(partial, partial, count, 8, 0, ncclComm, st);
 }
 }  // namespace vb
 
@@ -95,6 +147,7 @@ struct vloam_lidar {
   ShardView shard;
   ShardSlot* d_xbuf = nullptr;
   void* ipc_open[kMaxShard] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  void* nccl = nullptr;      // ncclComm_t of the point-sharded group (vloam_shard_nccl_init)
   float* d_in[2] = {nullptr, nullptr};  // [B][cap][in_stride], double-buffered so the next upload overlaps this scan's kernels
   int in_stride = 4;                    // floats per point the input slabs are sized for (grown on demand, <= kMaxInputStride)
   int* d_n[2] = {nullptr, nullptr};     // [B]
@@ -211,6 +264,7 @@ int vloam_lidar_params_default(vloam_lidar_params* p) {
   p->lm_max_iterations = 4;
   p->map_capacity_points = 1 << 21;
   p->debug_keep_submap = 0;
+  p->solver_mode = 0;
   return VLOAM_OK;
 }
 
@@ -230,7 +284,9 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
   cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart); cudaFree(h->grid.cursor);
+  cudaFree(h->grid.gnRec); cudaFree(h->grid.gnState); cudaFree(h->grid.gnPartial); cudaFree(h->grid.gnCounts);
   for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); }
+  if (h->nccl) { if (NcclApi* api = nccl_api()) api->CommDestroy(h->nccl); h->nccl = nullptr; }
   if (h->lm) lm_destroy(h->lm);
   for (int r = 0; r < kMaxShard; ++r) if (h->ipc_open[r]) cudaIpcCloseMemHandle(h->ipc_open[r]);
   cudaFree(h->d_xbuf); cudaFree(h->shard.seq); cudaFree(h->shard.error);
@@ -326,13 +382,54 @@ int vloam_shard_status(vloam_lidar* h, int* error_bits) {
   return VLOAM_OK;
 }
 
+int vloam_shard_nccl_unique_id(unsigned char* id128) {
+  if (!id128) return VLOAM_E_INVALID;
+  NcclApi* api = nccl_api();
+  if (!api) return VLOAM_E_STATE;
+  NcclId id;
+  if (api->GetUniqueId(&id) != 0) return VLOAM_E_CUDA;
+  std::memcpy(id128, id.internal, 128);
+  return VLOAM_OK;
+}
+
+int vloam_shard_nccl_init(vloam_lidar* h, int rank, int world, const unsigned char* id128) {
+  if (!h || !id128 || world < 1 || world > kMaxShard || rank < 0 || rank >= world) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  NcclApi* api = nccl_api();
+  if (!api) return fail(c, VLOAM_E_STATE, "vloam_shard_nccl_init: no libnccl in the process (set VLOAM_NCCL_LIB)");
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h->nccl) { api->CommDestroy(h->nccl); h->nccl = nullptr; }
+  NcclId id;
+  std::memcpy(id.internal, id128, 128);
+  const int r = api->CommInitRank(&h->nccl, world, id, rank);
+  if (r != 0) { h->nccl = nullptr; return fail(c, VLOAM_E_CUDA, api->GetErrorString ? api->GetErrorString(r) : "ncclCommInitRank failed"); }
+  h->shard.rank = rank; h->shard.world = world;       // lo_associate / lm_knn deal the queries to the ranks
+  h->grid.ncclComm = h->nccl;
+  lm_set_nccl(h->lm, h->nccl, rank, world);
+  return VLOAM_OK;
+}
+
+int vloam_shard_nccl_destroy(vloam_lidar* h) {
+  if (!h) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  CU(c, cudaStreamSynchronize(c->stream));
+  NcclApi* api = nccl_api();
+  if (h->nccl && api) api->CommDestroy(h->nccl);
+  h->nccl = nullptr; h->grid.ncclComm = nullptr;
+  lm_set_nccl(h->lm, nullptr, 0, 1);
+  h->shard.rank = 0; h->shard.world = 1;
+  return VLOAM_OK;
+}
+
 int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** out) {
   if (!c || !p || !out) return VLOAM_E_INVALID;
   *out = nullptr;
   if (p->batch < 1 || p->max_points < 64 || (p->scan_line != 16 && p->scan_line != 32 && p->scan_line != 64))
     return fail(c, VLOAM_E_INVALID, "vloam_lidar_create: batch >= 1, max_points >= 64, scan_line in {16,32,64}");
   if (p->mapping_skip_frame < 1 || p->lo_outer_passes < 0 || p->lo_max_iterations < 0 || p->lm_outer_passes < 0 || p->lm_max_iterations < 0 ||
-      !(p->mapping_line_resolution > 0.0) || !(p->mapping_plane_resolution > 0.0) || !(p->minimum_range >= 0.0))
+      p->solver_mode < 0 || p->solver_mode > 2 || !(p->mapping_line_resolution > 0.0) || !(p->mapping_plane_resolution > 0.0) || !(p->minimum_range >= 0.0))
     return fail(c, VLOAM_E_INVALID, "vloam_lidar_create: mapping_skip_frame >= 1, pass / iteration counts >= 0, resolutions > 0, minimum_range >= 0");
   CU(c, cudaSetDevice(c->device));
   vloam_lidar* h = new (std::nothrow) vloam_lidar();
@@ -365,6 +462,8 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   A(dalloc(&h->grid.hdr, B * 2)); A(dalloc(&h->grid.cellStart, B * 2 * (kGridCap + 1))); A(dalloc(&h->grid.cursor, B * 2 * (kGridCap + 1)));
   A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp));
   A(dalloc(&h->grid.sorted[1], B * cap));
+  A(dalloc(&h->grid.gnRec, B * (kMaxSharp + kMaxFlat))); A(dalloc(&h->grid.gnState, B)); A(dalloc(&h->grid.gnPartial, B * kGnTiles * 28));
+  A(dalloc(&h->grid.gnCounts, B * 2));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);
   e = lm_create(&c->prof, c->stream, h->B, h->cap, p, &h->lm);
@@ -610,7 +709,8 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
     for (int pass = 0; pass < passes; ++pass) {
       launch_lo_pass(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
                      h->d_lessSharp[last], h->d_lessFlat[last], &h->grid, h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
-                     h->p.lo_max_iterations, pass == passes - 1, prior, h->shard.world > 1 ? &h->shard : nullptr);
+                     h->p.lo_max_iterations, pass == passes - 1, prior, h->shard.world > 1 ? &h->shard : nullptr, h->p.solver_mode);   // (with an NCCL communicator
+                                                                                       // the pass takes the wide solve and sums there)
     }
   }
   // laser_odometry.cpp:511-526: the current less-sharp / less-flat clouds become "last" and are indexed for the next scan

@@ -209,14 +209,17 @@ static __device__ __forceinline__ bool chol_solve6(const double Hu[21], const do
 }
 
 // Trust-region LM state kept in shared memory by the solve kernels (Ceres 2.0 defaults, oracle/ceres_lm.hpp).
-struct LMShared {
+struct LMCore {
   double x[7], cand[7];
   double H[21], g[6], cost;     // at x, unscaled
   double scale[6], diagonal[6];
   double radius, decrease_factor, model_cost_change, x_norm, gmax;
   int reuse_diagonal, iteration, done, termination, invalid_run;
   int euclid;  // 1: x = [angle-axis(3), t(3)] with plain addition (visual odometry); 0: x = [q(4), t(3)] on the quaternion manifold
-  double red[28];
+  double red[28];               // (J'J, J'r, cost) of the latest evaluation
+};
+// ... plus the block-reduction scratch of the one-CTA-per-problem kernels
+struct LMShared : LMCore {
   double scratch[32 * 28];
 };
 
@@ -235,7 +238,7 @@ __device__ __forceinline__ void lm_record(SolveTrace* tr, double cost, double ca
 
 // Thread 0: given (H, g, cost) at x, compute the next LM step and candidate; handles invalid steps by shrinking the
 // radius (each invalid step is one iteration).  Returns with S.done set, or with S.cand ready for evaluation.
-static __device__ void lm_prepare_step(LMShared& S, SolveTrace* tr, int max_iterations) {
+static __device__ void lm_prepare_step(LMCore& S, SolveTrace* tr, int max_iterations) {
   while (true) {
     if (S.iteration >= max_iterations) { S.done = 1; S.termination = TERM_NO_CONVERGENCE; return; }
     if (S.gmax <= 1e-10) { S.done = 1; S.termination = TERM_GRADIENT; return; }
@@ -285,7 +288,7 @@ static __device__ void lm_prepare_step(LMShared& S, SolveTrace* tr, int max_iter
 }
 
 // Thread 0: red[] holds (H, g, cost) evaluated at S.cand.  Accept / reject, update the trust region.
-static __device__ void lm_finish_step(LMShared& S, SolveTrace* tr) {
+static __device__ void lm_finish_step(LMCore& S, SolveTrace* tr) {
   const double cand_cost = S.red[27];
   double step_norm = 0.0;
   for (int i = 0; i < 7; ++i) step_norm += (S.x[i] - S.cand[i]) * (S.x[i] - S.cand[i]);
@@ -325,7 +328,7 @@ static __device__ void lm_finish_step(LMShared& S, SolveTrace* tr) {
 }
 
 // Thread 0: red[] holds (H, g, cost) at the initial x (iteration 0).
-static __device__ void lm_begin(LMShared& S, SolveTrace* tr, const double x0[7]) {
+static __device__ void lm_begin(LMCore& S, SolveTrace* tr, const double x0[7]) {
   for (int i = 0; i < 7; ++i) S.x[i] = x0[i];
   double xn = 0.0;
   for (int i = 0; i < 7; ++i) xn += x0[i] * x0[i];

@@ -1,0 +1,53 @@
+// vloam_b200 — the ceres::Solve of one outer pass as a sequence of WIDE launches: every Levenberg-Marquardt
+// evaluation is one gn_accumulate launch over all residual blocks of all streams (grid = tiles x streams, every SM busy,
+// 28-double partial normal equations per tile) followed by one gn_step launch (a warp per stream: fixed-order sum of the
+// tile partials, 6 x 6 Cholesky and the Ceres trust-region bookkeeping of gn_solver.cuh).  Between the two sits the one
+// real exchange step of the path: with the residuals of a stream split across GPUs (BASELINE configs[4]) the partials are
+// all-reduced there (ncclAllReduce, see capi.cu).  The one-CTA-per-stream kernels (lo_solve, lm_solve) remain for small
+// batches, where launch count matters more than width.
+#pragma once
+#include "common.cuh"
+#include "gn_solver.cuh"
+
+namespace vb {
+
+struct Profiler;
+
+// Residual record shared by laser odometry and laser mapping.
+struct GNResidual {
+  double v[7];   // edge: a(3), b(3); plane: n(3), d0
+  float px, py, pz;
+  int type;      // 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneFactor / LidarPlaneNormFactor: r = n . (q p + t) + d0)
+};
+
+constexpr int kGnTiles = 8;          // CTAs per stream of gn_accumulate
+constexpr int kGnThreads = 256;
+
+struct GNState {                     // per stream, lives in global memory between the launches of one solve
+  LMCore core;
+  double evalX[7];                   // the point the next gn_accumulate evaluates at (x0, then the LM candidates)
+  int active;                        // the stream has a problem to solve in this pass
+  int pad;
+};
+
+// A per-stream field inside an array of per-stream structs: base + b * stride bytes.
+struct Strided {
+  const void* base; size_t stride;
+  template <typename T> __device__ __forceinline__ const T* at(int b) const { return reinterpret_cast<const T*>(static_cast<const char*>(base) + (size_t)b * stride); }
+  template <typename T> __device__ __forceinline__ T* at_mut(int b) const { return reinterpret_cast<T*>(const_cast<char*>(static_cast<const char*>(base)) + (size_t)b * stride); }
+};
+
+struct GNProblemView {
+  const GNResidual* rec[2];          // up to two record arrays per stream (laser mapping: corner / surf queries)
+  size_t recStride[2];               // records per stream in each array
+  Strided count[2];                  // int: live records of each array (count[i].base == nullptr: fixedCount[i])
+  int fixedCount[2];
+  Strided active;                    // int flag (nullptr: always active)
+  Strided x;                         // double[7]: the parameters (read at the start, written back at the end)
+  Strided trace;                     // SolveTrace
+};
+
+void launch_gn_solve(Profiler* prof, cudaStream_t st, int B, const GNProblemView& pv, GNState* gs, double* partial /*[B][kGnTiles][28]*/,
+                     int max_iterations, int kidAccumulate, int kidStep, void* ncclComm /*or nullptr*/);
+
+}  // namespace vb

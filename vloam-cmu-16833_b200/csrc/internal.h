@@ -16,6 +16,7 @@ enum KernelId {
   K_SR_FIND_ENDS = 0, K_SR_CLASSIFY, K_SR_SCAN, K_SR_SCATTER, K_SR_CURVATURE, K_SR_PICK, K_SR_VOXEL, K_SR_PACK,
   K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT, K_LO_BUILD_GRID, K_LO_ASSOCIATE_BRUTE,
   K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_FIT, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_PLACE, K_LM_MISC,
+  K_LO_ACCUMULATE, K_LO_STEP, K_LM_ACCUMULATE, K_LM_STEP,
   K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC,
   K_COUNT
 };
@@ -58,7 +59,15 @@ cudaError_t sr_prepare_device(int device);   // per-device function attributes, 
 // lo_kernels.cu
 void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
 // Grid index over the (corner, surf) target clouds of every stream: [B][2] headers, cell tables and sorted copies.
+struct GNState;
+struct GNResidual;
 struct LOGrid {
+  // wide solve (gn_split.cuh): residual records [B][kMaxSharp + kMaxFlat], per-stream state, tile partials, rank-summed counts
+  GNResidual* gnRec = nullptr;
+  GNState* gnState = nullptr;
+  double* gnPartial = nullptr;
+  double* gnCounts = nullptr;
+  void* ncclComm = nullptr;    // point-sharded streams: partial normal equations all-reduced across ranks
   GridHeader* hdr = nullptr;   // [B][2]
   int* cellStart = nullptr;    // [B][2][kGridCap + 1]
   int* cursor = nullptr;       // [B][2][kGridCap + 1] scatter cursors (scratch)
@@ -67,7 +76,7 @@ struct LOGrid {
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* grid, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
-                    const ShardView* shard = nullptr);
+                    const ShardView* shard = nullptr, int solverMode = 0);
 // kd-tree rebuild of laser_odometry.cpp:525-526: index the current scan's less-sharp / less-flat clouds.
 void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
                           const float4* lessFlat, const LOGrid* grid);
@@ -93,6 +102,7 @@ cudaError_t lm_get_trace(LMDevice* lm, cudaStream_t st, int stream, int pass, do
 cudaError_t lm_get_status(LMDevice* lm, cudaStream_t st, int* status);
 cudaError_t lm_get_counters(LMDevice* lm, cudaStream_t st, long long* counters);
 void lm_set_debug_stats(LMDevice* lm, bool on);
+void lm_set_nccl(LMDevice* lm, void* comm, int rank, int world);
 cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out);
 
 }  // namespace vb

@@ -24,6 +24,7 @@
 #include "common.cuh"
 #include "cta_sort.cuh"
 #include "gn_solver.cuh"
+#include "gn_split.cuh"
 #include "internal.h"
 
 namespace vb {
@@ -88,12 +89,9 @@ struct LMState {
   SolveTrace trace[2];
 };
 
-// Residual record produced by lm_associate for one down-sampled scan point.
-struct LMResidual {
-  double v[7];   // edge: a(3), b(3); plane: n(3), d
-  float px, py, pz;
-  int type;      // 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneNormFactor)
-};
+// Residual record produced by lm_fit for one down-sampled scan point: v = edge a(3), b(3) / plane n(3), d; p = the point;
+// type 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneNormFactor).  The record of gn_split.cuh.
+using LMResidual = GNResidual;
 
 struct LMDevice {
   int B = 0, cap = 0, mapCap = 0;
@@ -120,6 +118,10 @@ struct LMDevice {
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
   float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
   LMResidual* res = nullptr;              // [B][2][cap]
+  GNState* gnState = nullptr;             // [B] wide solve (gn_split.cuh): per-stream trust-region state between launches
+  double* gnPartial = nullptr;            // [B][kGnTiles][28] partial normal equations of one evaluation
+  void* ncclComm = nullptr;               // point-sharded streams: the partials are all-reduced across ranks (capi.cu)
+  int shardRank = 0, shardWorld = 1;      // ... and the queries are dealt round-robin to the ranks
   uint8_t* fitType = nullptr;             // [2 passes][B][2][cap] factor type per query and outer pass (vloam_get_lm_queries)
   int* cubeOf = nullptr;                  // [B][2][cap] cube id of every down-sampled scan point (map frame)
   int* nnPos = nullptr;                   // [B][2][5][cap] positions (in `sorted`) of the five nearest map points per query
@@ -756,7 +758,8 @@ template <bool STATS>
 __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                             const CubeTables& T, const short* __restrict__ entryHeadAll,
                                             const int* __restrict__ tabPool, const float4* __restrict__ sorted,
-                                            int mapCap, int* __restrict__ nnPos /*[B][2][5][cap]*/, LMState* statsOut) {
+                                            int mapCap, int* __restrict__ nnPos /*[B][2][5][cap]*/, LMState* statsOut, int shardRank,
+                                            int shardWorld) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
@@ -777,6 +780,11 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
 #pragma unroll
     for (int i = 0; i < 5; ++i) { bk[i] = 0xffffffffffffffffull; bp[i] = -1; }
     unsigned wbits = 0x3f7fffffu;   // the largest float below 1.0f (non-negative floats order like their bit patterns)
+    if (shardWorld > 1 && qi % shardWorld != shardRank) {     // point-sharded: another rank's query (no factor on this rank)
+#pragma unroll
+      for (int i = 0; i < 5; ++i) outPos[(size_t)i * cap + qi] = -1;
+      continue;
+    }
     const float4 po = stk[qi];
     // pointAssociateToMap (:146-155): double transform, rounded to float
     double w[3];
@@ -823,30 +831,42 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
           // within 1 m in z lies in one of them); a cube in mode 1 has a single layer
           const bool flat = tab[14] != 0;
           const int zb0 = flat ? 0 : cube_zbin(sz - 1.001f, mnz), zb1 = flat ? 0 : cube_zbin(sz + 1.001f, mnz);
+          // the bounds of all (<= 2 x 3) runs first: independent loads, one memory latency for the lot
+          int ra[6], rn[6];
+#pragma unroll
+          for (int zi = 0; zi < 2; ++zi) {
+            const int z = zb0 + zi;
+            const bool zok = z <= zb1;
+            const int L = (zok && !flat) ? tab[z] : 0;
+            const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells;
+#pragma unroll
+            for (int ri = 0; ri < 3; ++ri) {
+              const int row = r0 + ri;
+              int a = 0, en = 0;
+              if (zok && row <= r1) {
+                if (flat) {
+                  a = tab[kTabHdr + row * kCubeCellsX + x0]; en = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
+                } else {
+                  a = L + (int)rel[row * kCubeCellsX + x0];
+                  en = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[row * kCubeCellsX + x1 + 1];   // a layer ends where the next begins
+                }
+              }
+              ra[zi * 3 + ri] = off + a; rn[zi * 3 + ri] = en - a;
+            }
+          }
           // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
           // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
           for (; e >= 0; e = st.entryNext[e]) {
             const unsigned gBase = (unsigned)st.validPrefix[kind][e];
-            for (int z = zb0; z <= zb1; ++z) {
-              const int L = flat ? 0 : tab[z];
-              const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells;
-              for (int row = r0; row <= r1; ++row) {
-                int ra, re;
-                if (flat) {
-                  ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
-                } else {
-                  ra = L + (int)rel[row * kCubeCellsX + x0];
-                  re = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[row * kCubeCellsX + x1 + 1];   // a layer ends where the next begins
-                }
-                if (STATS) nCand += (unsigned)(re - ra);
-                // two candidates in flight
-                int t = ra;
-                for (; t + 1 < re; t += 2) {
-                  const float4 p0 = S[off + t], p1 = S[off + t + 1];
-                  consider(p0, gBase, off + t);
-                  consider(p1, gBase, off + t + 1);
-                }
-                if (t < re) consider(S[off + t], gBase, off + t);
+#pragma unroll
+            for (int r = 0; r < 6; ++r) {
+              if (STATS) nCand += (unsigned)rn[r];
+              for (int t = 0; t < rn[r]; t += 4) {          // four candidates in flight
+                float4 p[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (t + u < rn[r]) p[u] = S[ra[r] + t + u];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) if (t + u < rn[r]) consider(p[u], gBase, ra[r] + t + u);
               }
             }
           }
@@ -864,16 +884,20 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
 #define VB_LM_KNN_ARGS                                                                                                            \
   const LMState *__restrict__ stAll, const float4 *__restrict__ stack, int cap, const CubeTables T,                              \
       const short *__restrict__ entryHeadAll, const int *__restrict__ tabPool, const float4 *__restrict__ sorted, int mapCap,    \
-      int *__restrict__ nnPos, LMState *statsOut
-__global__ void __launch_bounds__(kKnnThreads) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
-__global__ void __launch_bounds__(kKnnThreads) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut); }
+      int *__restrict__ nnPos, LMState *statsOut, int shardRank, int shardWorld
+// Two register budgets of the same body (bound by memory latency: occupancy against spills is settled by measurement,
+// VLOAM_LM_KNN_OCC=4|6; measured on B200: see DESIGN.md).
+__global__ void __launch_bounds__(kKnnThreads, 6) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }
+__global__ void __launch_bounds__(kKnnThreads, 4) lm_knn_occ4(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }
+__global__ void __launch_bounds__(kKnnThreads) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }
 // grid (nblk, 2, B), block 128: one thread per point
-__global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
+__global__ void __launch_bounds__(128) lm_fit(LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
-                                               LMResidual* __restrict__ res, uint8_t* __restrict__ fitType /*[B][2][cap] of this pass*/) {
+                                               LMResidual* __restrict__ res, uint8_t* __restrict__ fitType /*[B][2][cap] of this pass*/, int pass) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
+  int nFactors = 0;
   const int nq = st.stackNum[kind];
   const float4* S = sorted + ((size_t)b * 2 + kind) * mapCap;
   const float4* stk = stack + ((size_t)b * 2 + kind) * cap;
@@ -921,7 +945,11 @@ __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll,
     }
     res[((size_t)b * 2 + kind) * cap + qi] = R;
     fitType[((size_t)b * 2 + kind) * cap + qi] = (uint8_t)R.type;   // parity read-out: which queries produced a factor in this pass
+    nFactors += R.type != 0;
   }
+  // residual blocks of the pass (:517 / :581), for the trace and the wide solve: one atomic per warp
+  nFactors = __reduce_add_sync(0xffffffffu, nFactors);
+  if (lane_id() == 0 && nFactors) atomicAdd(kind == 0 ? &stAll[b].trace[pass].n_corner : &stAll[b].trace[pass].n_plane, nFactors);
 }
 
 // lm_solve: one outer pass of :458-626 (the association was just done by lm_associate).  grid (kLmCluster, B), block 256,
@@ -930,7 +958,8 @@ __global__ void __launch_bounds__(128) lm_fit(const LMState* __restrict__ stAll,
 // CTA reduces its share to 28 doubles, and the partial sums are exchanged through distributed shared memory.  Every CTA
 // adds them in rank order and runs the (cheap, deterministic) trust-region bookkeeping itself, so all of them hold
 // bit-identical state and no broadcast is needed; only rank 0 writes results.
-constexpr int kLmClusterMax = 8;     // cluster size is a launch attribute (1, 2, 4 or 8): see lm_run
+constexpr int kLmClusterMax = 8;
+constexpr int kGnSplitMinBatch = 1 << 30;   // batch size from which the wide solve (gn_split.cuh) is the default: set by measurement     // cluster size is a launch attribute (1, 2, 4 or 8): see lm_run
 __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
                                                                                     int cap, int pass, int max_iterations, int lastPass) {
   namespace cg = cooperative_groups;
@@ -997,6 +1026,17 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
     if (lastPass) st.counters[kCntFactors] += tr->n_corner + tr->n_plane;
   }
   cluster.sync();                      // nobody leaves while a peer may still read its partial sums
+}
+
+// Wide solve (gn_split.cuh): book-keeping after the last gn_step of a pass.
+__global__ void lm_gn_finish(LMState* __restrict__ stAll, int B, int pass, int lastPass) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LMState& st = stAll[b];
+  if (!st.solved) return;
+  const SolveTrace& tr = st.trace[pass];
+  st.counters[pass == 0 ? kCntIters0 : kCntIters1] += tr.n_records - 1;
+  if (lastPass) st.counters[kCntFactors] += tr.n_corner + tr.n_plane;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1591,6 +1631,7 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
   A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
   A((void**)&lm->fitType, 2 * B * 2 * cap);
+  A((void**)&lm->gnState, B * sizeof(GNState)); A((void**)&lm->gnPartial, B * kGnTiles * 28 * sizeof(double));
   A((void**)&lm->nnPos, B * 2 * cap * 5 * sizeof(int));
   A((void**)&lm->cubeOf, B * 2 * cap * sizeof(int));
   A((void**)&lm->pose, B * 16 * sizeof(double));
@@ -1624,7 +1665,7 @@ void lm_destroy(LMDevice* lm) {
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
-    cudaFree(lm->res); cudaFree(lm->fitType); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
+    cudaFree(lm->res); cudaFree(lm->fitType); cudaFree(lm->gnState); cudaFree(lm->gnPartial); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
 }
@@ -1663,18 +1704,31 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   // C6-C9: outer passes of association + LM
   for (int pass = 0; pass < lm->p.lm_outer_passes; ++pass) {
     const int tp = pass < 2 ? pass : 1;
+    static const int knnOcc = [] { const char* e = getenv("VLOAM_LM_KNN_OCC"); return e ? atoi(e) : 6; }();
     if (lm->debugStats)
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_stats<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, lm->st));
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_stats<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, lm->st, lm->shardRank, lm->shardWorld));
+    else if (knnOcc == 4)
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn_occ4<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr, lm->shardRank, lm->shardWorld));
     else
-      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr));
+      VB_LAUNCH(prof, K_LM_ASSOCIATE, st, lm_knn<<<dim3(kKnnGrid, 2, B), kKnnThreads, 0, st>>>(lm->st, lm->stack, cap, T_d, lm->entryHead, lm->tabPool, lm->sorted, mapCap, lm->nnPos, nullptr, lm->shardRank, lm->shardWorld));
     VB_LAUNCH(prof, K_LM_FIT, st, lm_fit<<<dim3(64, 2, B), 128, 0, st>>>(lm->st, lm->stack, cap, lm->sorted, mapCap, lm->nnPos, lm->res,
-                                                                         lm->fitType + (size_t)tp * B * 2 * cap));
-    {
+                                                                         lm->fitType + (size_t)tp * B * 2 * cap, tp));
+    const bool split = lm->ncclComm != nullptr || lm->p.solver_mode == 2 || (lm->p.solver_mode == 0 && B >= kGnSplitMinBatch);   // vloam_lidar_params::solver_mode
+    if (split) {
+      // wide solve: one launch over all residual blocks of all streams per evaluation + a warp-per-stream step
+      GNProblemView pv{};
+      pv.rec[0] = lm->res; pv.rec[1] = lm->res + cap;            // corner / surf records of stream b at b * 2 * cap
+      pv.recStride[0] = pv.recStride[1] = (size_t)2 * cap;
+      pv.count[0] = Strided{&lm->st[0].stackNum[0], sizeof(LMState)}; pv.count[1] = Strided{&lm->st[0].stackNum[1], sizeof(LMState)};
+      pv.active = Strided{&lm->st[0].solved, sizeof(LMState)};
+      pv.x = Strided{&lm->st[0].parameters[0], sizeof(LMState)};
+      pv.trace = Strided{&lm->st[0].trace[tp], sizeof(LMState)};
+      launch_gn_solve(prof, st, B, pv, lm->gnState, lm->gnPartial, lm->p.lm_max_iterations, K_LM_ACCUMULATE, K_LM_STEP, lm->ncclComm);
+      VB_LAUNCH(prof, K_LM_STEP, st, lm_gn_finish<<<(B + 127) / 128, 128, 0, st>>>(lm->st, B, tp, pass == lm->p.lm_outer_passes - 1 ? 1 : 0));
+    } else {
       // one cluster per stream.  Measured on B200 at 16 streams per launch (two launches in flight): 132 / 92 / 73 / 98 us
       // for 1 / 2 / 4 / 8 CTAs per cluster — 8 costs more in barriers and remote reads than it gains.
       static const int forced = [] { const char* e = getenv("VLOAM_LM_CLUSTER"); return e ? atoi(e) : 0; }();
-      // At 64 streams per launch with three launches in flight the GPU is saturated and a single CTA per stream wins
-      // (37.2 k scans/s vs 36.2 k with 2 and 34.6 k with 4 CTAs): clusters only for small batches, where latency counts.
       int cs = forced > 0 ? forced : (B <= 20 ? 4 : B <= 40 ? 2 : 1);
       cs = cs >= 8 ? kLmClusterMax : cs >= 4 ? 4 : cs >= 2 ? 2 : 1;
       cudaLaunchConfig_t cfg = {};
@@ -1752,6 +1806,7 @@ cudaError_t lm_get_counters(LMDevice* lm, cudaStream_t st, long long* counters) 
   return cudaSuccess;
 }
 void lm_set_debug_stats(LMDevice* lm, bool on) { if (lm) lm->debugStats = on; }
+void lm_set_nccl(LMDevice* lm, void* comm, int rank, int world) { if (lm) { lm->ncclComm = comm; lm->shardRank = rank; lm->shardWorld = world > 0 ? world : 1; } }
 
 // Queries (indices into the down-sampled corner / surf stack) that produced a residual block in outer pass `pass` of the last scan.
 cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, int kind, int* out, int capacity, int* n_out) {

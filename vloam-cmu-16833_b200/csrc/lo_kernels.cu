@@ -17,6 +17,7 @@
 
 #include "common.cuh"
 #include "gn_solver.cuh"
+#include "gn_split.cuh"
 #include "internal.h"
 
 namespace vb {
@@ -697,6 +698,88 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Wide solve (gn_split.cuh).  lo_stage_residuals: grid (B), block 256 — the per-correspondence geometry of lidarFactor.hpp:14-106
+// as residual records (what lo_solve stages in shared memory), plus the correspondence counts (:348, :441).
+__global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __restrict__ hdrCur, LOState* __restrict__ lo,
+                                                           const float4* __restrict__ sharp, const float4* __restrict__ flat,
+                                                           const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
+                                                           int cap, const int4* __restrict__ corr, int pass, GNResidual* __restrict__ recAll,
+                                                           double* __restrict__ counts /*[B][2] or nullptr*/) {
+  constexpr int kSlots = kMaxSharp + kMaxFlat;
+  const int b = blockIdx.x;
+  LOState& st = lo[b];
+  const int4* cr = corr + (size_t)b * kSlots;
+  const float4* sh = sharp + (size_t)b * kMaxSharp;
+  const float4* fl = flat + (size_t)b * kMaxFlat;
+  const float4* CL = cornerLast + (size_t)b * kMaxLessSharp;
+  const float4* SL = surfLast + (size_t)b * cap;
+  GNResidual* rec = recAll + (size_t)b * kSlots;
+  const int nSharp = hdrCur[b].nSharp, nFlat = hdrCur[b].nFlat;
+  __shared__ int s_nc, s_np;
+  if (threadIdx.x == 0) { s_nc = 0; s_np = 0; }
+  __syncthreads();
+  int nc = 0, np = 0;
+  for (int s = threadIdx.x; s < kSlots; s += blockDim.x) {
+    const bool isCorner = s < kMaxSharp;
+    const int qi = isCorner ? s : s - kMaxSharp;
+    GNResidual R;
+    R.type = 0; R.px = R.py = R.pz = 0.f;
+#pragma unroll
+    for (int i = 0; i < 7; ++i) R.v[i] = 0.0;
+    if (qi < (isCorner ? nSharp : nFlat)) {
+      const int4 c = cr[s];
+      if (c.w) {
+        const float4 p = isCorner ? sh[qi] : fl[qi];
+        R.px = p.x; R.py = p.y; R.pz = p.z;
+        if (isCorner) {
+          const float4 A = CL[c.x], Bp = CL[c.y];
+          R.v[0] = A.x; R.v[1] = A.y; R.v[2] = A.z; R.v[3] = Bp.x; R.v[4] = Bp.y; R.v[5] = Bp.z;
+          R.type = 1; nc++;
+        } else {
+          const float4 Jp = SL[c.x], Lp = SL[c.y], Mp = SL[c.z];
+          // ljm_norm = normalize((j - l) x (j - m))  (lidarFactor.hpp:68-69)
+          const double ax = (double)Jp.x - (double)Lp.x, ay = (double)Jp.y - (double)Lp.y, az = (double)Jp.z - (double)Lp.z;
+          const double bx = (double)Jp.x - (double)Mp.x, by = (double)Jp.y - (double)Mp.y, bz = (double)Jp.z - (double)Mp.z;
+          double n[3] = {ay * bz - az * by, az * bx - ax * bz, ax * by - ay * bx};
+          const double z2 = n[0] * n[0] + n[1] * n[1] + n[2] * n[2];
+          if (z2 > 0.0) { const double nn = sqrt(z2); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
+          R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2];
+          R.v[3] = -(n[0] * (double)Jp.x + n[1] * (double)Jp.y + n[2] * (double)Jp.z);
+          R.type = 2; np++;
+        }
+      }
+    }
+    rec[s] = R;
+  }
+  nc = __reduce_add_sync(0xffffffffu, nc);
+  np = __reduce_add_sync(0xffffffffu, np);
+  if (lane_id() == 0) { atomicAdd(&s_nc, nc); atomicAdd(&s_np, np); }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (counts) { counts[2 * b] = (double)s_nc; counts[2 * b + 1] = (double)s_np; }    // summed across ranks before lo_gn_finish reads them
+    else { st.corner_correspondence = s_nc; st.plane_correspondence = s_np; st.trace[pass].n_corner = s_nc; st.trace[pass].n_plane = s_np; }
+  }
+}
+// after the last gn_step of a pass: the (rank-summed) counts and the pose integration of :477-478
+__global__ void lo_gn_finish(LOState* __restrict__ lo, int B, int pass, int integrate, const double* __restrict__ counts) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  LOState& st = lo[b];
+  if (counts) {
+    st.corner_correspondence = (int)counts[2 * b]; st.plane_correspondence = (int)counts[2 * b + 1];
+    st.trace[pass].n_corner = st.corner_correspondence; st.trace[pass].n_plane = st.plane_correspondence;
+  }
+  if (integrate) {
+    double rt[3];
+    quat_rotate(st.q_w, st.para_t[0], st.para_t[1], st.para_t[2], rt);
+    st.t_w[0] += rt[0]; st.t_w[1] += rt[1]; st.t_w[2] += rt[2];
+    double qn[4];
+    quat_mul(st.q_w, st.para_q, qn);
+    for (int i = 0; i < 4; ++i) st.q_w[i] = qn[i];
+  }
+}
+
 __global__ void lo_init_state(LOState* lo, int B) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= B) return;
@@ -758,6 +841,8 @@ static bool lo_use_brute() {
 }
 
 constexpr int kLoSolveDynSmem = (kMaxSharp + kMaxFlat) * (4 * (int)sizeof(double) + 1);
+constexpr int kLoSplitMinBatch = 1 << 30;   // batch size from which the wide solve is the default: set by measurement
+void gn_allreduce_partials(void* ncclComm, double* partial, size_t count, cudaStream_t st);   // capi.cu
 // Opt-in shared-memory sizes are per-device function attributes: set (and checked) once per context, on its device.
 cudaError_t lo_prepare_device(int device) {
   cudaError_t e = cudaSetDevice(device);
@@ -776,7 +861,7 @@ void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
-                    const ShardView* shard) {
+                    const ShardView* shard, int solverMode) {
   const ShardView sv = shard ? *shard : ShardView();
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
   if (lo_use_brute() && sv.world <= 1)
@@ -802,6 +887,22 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
                                               g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
+  }
+  // vloam_lidar_params::solver_mode (0 = by batch size); the NCCL exchange needs the wide layout, the in-kernel peer exchange the narrow one
+  const bool split = g->gnState != nullptr && (g->ncclComm != nullptr || (sv.world <= 1 && (solverMode == 2 || (solverMode == 0 && B >= kLoSplitMinBatch))));
+  if (split) {
+    // wide solve (gn_split.cuh): residual records once per pass, then one launch over all streams per LM evaluation
+    double* counts = g->ncclComm ? g->gnCounts : nullptr;
+    VB_LAUNCH(prof, K_LO_STEP, st, lo_stage_residuals<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, g->gnRec, counts));
+    if (counts) gn_allreduce_partials(g->ncclComm, counts, (size_t)B * 2, st);
+    GNProblemView pv{};
+    pv.rec[0] = g->gnRec; pv.rec[1] = nullptr;
+    pv.recStride[0] = kMaxSharp + kMaxFlat; pv.fixedCount[0] = kMaxSharp + kMaxFlat;
+    pv.x = Strided{&lo[0].para_q[0], sizeof(LOState)};
+    pv.trace = Strided{&lo[0].trace[pass], sizeof(LOState)};
+    launch_gn_solve(prof, st, B, pv, g->gnState, g->gnPartial, max_iterations, K_LO_ACCUMULATE, K_LO_STEP, g->ncclComm);
+    VB_LAUNCH(prof, K_LO_STEP, st, lo_gn_finish<<<(B + 127) / 128, 128, 0, st>>>(lo, B, pass, integrate, counts));
+    return;
   }
   VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
                                                                max_iterations, integrate, sv));
