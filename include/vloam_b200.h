@@ -274,6 +274,20 @@ int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, cons
 int vloam_vo_solve_device_async(vloam_vo* h, const float* prev_uv_dev, const float* curr_uv_dev, const int* n_matches_dev,
                                 const double* init_dev, int remove_VO_outlier, int max_iterations);
 int vloam_vo_get_result(vloam_vo* h, double* out /* [batch][8] as vloam_vo_solve */);
+/* ImageUtil::matchDescriptors   image_util.cpp:214-296, in the configuration VisualOdometry selects (visual_odometry.cpp:34-37):
+ * cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) over 32-byte binary descriptors (cv::ORB) and the ratio test
+ * `m[0].distance < ratio * m[1].distance` (ratio = 0.8, :277).  desc_query / desc_train: [batch][max_matches][32] bytes
+ * (rows of the cv::Mat the extractor returns), n_query / n_train [batch] rows in use; kp_query / kp_train: NULL, or
+ * [batch][max_matches][2] = cv::KeyPoint::pt of the same rows.  matches_out[batch][max_matches][3] = (queryIdx, trainIdx,
+ * distance) of the accepted matches in query order, n_matches_out[batch].  Host buffers. */
+int vloam_vo_match_descriptors(vloam_vo* h, const uint8_t* desc_query, const int* n_query, const uint8_t* desc_train, const int* n_train,
+                               const float* kp_query, const float* kp_train, double ratio, int* matches_out, int* n_matches_out);
+/* Parity read-out: knn[batch][max_matches][4] = (trainIdx of the nearest, of the second nearest, their distances) per query row:
+ * the knn_matches of image_util.cpp:263 before the ratio test (-1: fewer than two train descriptors). */
+int vloam_vo_get_knn(vloam_vo* h, int* knn);
+/* The matched pixel pairs of that call (when keypoints were given) stay on the device in solveNlsAll's layout
+ * ([batch][max_matches][2] each, counts [batch]): pass them to vloam_vo_solve_device_async. */
+int vloam_vo_get_match_buffers(vloam_vo* h, const float** query_uv_dev, const float** train_uv_dev, const int** n_matches_dev);
 /* VO result -> LO prior, on the device: cam0_curr_T_cam0_last (visual_odometry.cpp:426-430) ->
  * velo_last_VOT_velo_curr = velo_T_cam0 * cam0_curr_T_cam0_last^-1 * velo_T_cam0^-1 (VloamTF::VO2VeloAndBase, vloam_tf.cpp:59-63),
  * written as [batch][7] = q(x y z w) t to prior_dev, the layout vloam_laser_odometry_async reads (laser_odometry.cpp:225-232).

@@ -1,0 +1,79 @@
+"""Descriptor matching of the visual-odometry front end — the one row whose parity is PINNED by
+the reference's own dependency: tests/golden/vo_frontend_cv2.npz was produced by OpenCV (cv2) with the calls of
+image_util.cpp:13-26, 176-204, 228-283 (tests/golden/make_golden_vo_frontend.py)."""
+import os
+
+import numpy as np
+import pytest
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vo_frontend_cv2.npz")
+PAIRS = (0, 1, 2)
+
+
+@pytest.fixture(scope="module")
+def golden():
+    return np.load(GOLDEN)
+
+
+def test_numpy_restatement_matches_opencv(golden):
+    from oracle import vo_frontend as F
+    for p in PAIRS:
+        d0, d1 = golden[f"pair{p}_desc0"], golden[f"pair{p}_desc1"]
+        idx, dist = F.knn2(d0, d1)
+        assert np.array_equal(idx, golden[f"pair{p}_knn_idx"][:, 1:]), f"pair {p}: 2-NN train indices (ties included)"
+        assert np.array_equal(golden[f"pair{p}_knn_idx"][:, 0], np.arange(d0.shape[0]))
+        assert np.array_equal(dist.astype(np.float32), golden[f"pair{p}_knn_dist"]), f"pair {p}: distances"
+        assert np.array_equal(F.match_descriptors(d0, d1), golden[f"pair{p}_matches"]), f"pair {p}: ratio-tested matches"
+    assert (golden["pair2_knn_dist"][:, 0] == golden["pair2_knn_dist"][:, 1]).mean() > 0.9      # the tie fixture really ties
+
+
+def test_opencv_still_reproduces_the_golden_vectors(golden):
+    """If cv2 is importable, the committed vectors are what it produces today (guards against a stale fixture)."""
+    cv2 = pytest.importorskip("cv2")
+    for p in PAIRS:
+        d0, d1 = golden[f"pair{p}_desc0"], golden[f"pair{p}_desc1"]
+        knn = cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False).knnMatch(d0, d1, 2)
+        got = np.array([[m[0].queryIdx, m[0].trainIdx, m[1].trainIdx] for m in knn], np.int32)
+        assert np.array_equal(got, golden[f"pair{p}_knn_idx"])
+        good = np.array([[m[0].queryIdx, m[0].trainIdx, int(m[0].distance)] for m in knn if m[0].distance < 0.8 * m[1].distance], np.int32).reshape(-1, 3)
+        assert np.array_equal(good, golden[f"pair{p}_matches"])
+
+
+@pytest.mark.gpu
+def test_cuda_matcher_hits_the_opencv_vectors(golden):
+    """vo_bf_match (TMA-staged train descriptors, popcount 2-NN, ratio test, ordered compaction) == cv2, bit for bit: the raw
+    2-NN table with its tie-breaks, the accepted matches, and the matched pixel pairs left on the device for solveNlsAll.
+    All three pairs as one batch of three streams."""
+    import torch
+    import vloam_b200 as V
+    vo = V.VisualOdometry(batch=3, max_points=1024, max_matches=1024)
+    d0 = [golden[f"pair{p}_desc0"] for p in PAIRS]
+    d1 = [golden[f"pair{p}_desc1"] for p in PAIRS]
+    k0 = [golden[f"pair{p}_kp0"] for p in PAIRS]
+    k1 = [golden[f"pair{p}_kp1"] for p in PAIRS]
+    res = vo.matchDescriptors(d0, d1, k0, k1, ratio=0.8)
+    qa, ta, na = vo.match_buffers()
+    for p in PAIRS:
+        g_idx, g_dist = golden[f"pair{p}_knn_idx"], golden[f"pair{p}_knn_dist"]
+        assert np.array_equal(res[p]["knn"][:, :2], g_idx[:, 1:]), f"pair {p}: 2-NN indices"
+        assert np.array_equal(res[p]["knn"][:, 2:].astype(np.float32), g_dist), f"pair {p}: 2-NN distances"
+        assert np.array_equal(res[p]["matches"], golden[f"pair{p}_matches"]), f"pair {p}: matches"
+    # the device-resident pixel pairs feed solveNlsAll without a host round trip
+    nm = np.array([len(golden[f"pair{p}_matches"]) for p in PAIRS])
+    assert nm[0] > 100
+    import ctypes
+    buf = np.zeros((3, 1024, 2), np.float32)
+    torch.cuda.synchronize()
+    for addr, kps, col in ((qa, k0, 0), (ta, k1, 1)):
+        rc = torch.cuda.cudart().cudaMemcpy(buf.ctypes.data, addr, buf.nbytes, 2)      # cudaMemcpyDeviceToHost
+        assert int(rc) == 0
+        for p in PAIRS:
+            m = golden[f"pair{p}_matches"]
+            assert np.array_equal(buf[p, : len(m)], kps[p][m[:, col]]), f"pair {p}: matched pixels ({'query' if col == 0 else 'train'})"
+    # degenerate sizes: an empty query set, a train set with a single descriptor (no second neighbour -> no match)
+    one = vo.matchDescriptors([d0[0][:0], d0[1], d0[2][:5]], [d1[0], d1[1][:1], d1[2][:2]])
+    assert one[0]["matches"].shape == (0, 3) and one[1]["matches"].shape == (0, 3)
+    assert np.array_equal(one[1]["knn"][:, 1], np.full(len(d0[1]), -1))
+    from oracle import vo_frontend as F
+    assert np.array_equal(one[2]["matches"], F.match_descriptors(d0[2][:5], d1[2][:2]))
+    vo.close()

@@ -110,6 +110,8 @@ def lib():
             "vloam_vo_solve_device_async": [vp, vp, vp, vp, vp, C.c_int, C.c_int], "vloam_vo_get_result": [vp, c_dp],
             "vloam_vo_export_lo_prior": [vp, c_dp, vp],
             "vloam_vo_get_trace": [vp, C.c_int, c_dp, c_ip, c_dp],
+            "vloam_vo_match_descriptors": [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp], "vloam_vo_get_knn": [vp, vp],
+            "vloam_vo_get_match_buffers": [vp, pp, pp, pp],
             "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
         }
         for name, args in sig.items():
@@ -569,6 +571,41 @@ class VisualOdometry:
                                             self.max_num_iterations, out.ctypes.data_as(c_dp)))
         return {"angles_0to1": out[:, 0:3].copy(), "t_0to1": out[:, 3:6].copy(), "counter32": out[:, 6].astype(int),
                 "counter22": out[:, 7].astype(int)}
+
+    # -- image_util.cpp:214-296 (BF + NORM_HAMMING + KNN + ratio test: the configuration of visual_odometry.cpp:34-37)
+    def matchDescriptors(self, desc_query, desc_train, kp_query=None, kp_train=None, ratio: float = 0.8):
+        """desc_*: per stream an (n, 32) uint8 array (the cv::Mat of cv::ORB), or one array for batch 1; kp_*: matching (n, 2)
+        float32 keypoint pixels or None.  Returns per stream the accepted (queryIdx, trainIdx, distance) rows in query order
+        and the raw 2-NN table (idx0, idx1, d0, d1) per query row."""
+        if isinstance(desc_query, np.ndarray):
+            desc_query, desc_train = [desc_query], [desc_train]
+            kp_query, kp_train = (None if kp_query is None else [kp_query]), (None if kp_train is None else [kp_train])
+        B, M = self.batch, self.max_matches
+        assert len(desc_query) == B and len(desc_train) == B
+        dq = np.zeros((B, M, 32), np.uint8); dt = np.zeros((B, M, 32), np.uint8)
+        nq = np.zeros(B, np.int32); nt = np.zeros(B, np.int32)
+        kq = kt = None
+        if kp_query is not None:
+            kq = np.zeros((B, M, 2), np.float32); kt = np.zeros((B, M, 2), np.float32)
+        for b in range(B):
+            a, t = np.ascontiguousarray(desc_query[b], np.uint8).reshape(-1, 32), np.ascontiguousarray(desc_train[b], np.uint8).reshape(-1, 32)
+            nq[b], nt[b] = a.shape[0], t.shape[0]
+            dq[b, :nq[b]] = a; dt[b, :nt[b]] = t
+            if kq is not None:
+                kq[b, :nq[b]] = kp_query[b]; kt[b, :nt[b]] = kp_train[b]
+        m = np.zeros((B, M, 3), np.int32)
+        nm = np.zeros(B, np.int32)
+        self.ctx.check(lib().vloam_vo_match_descriptors(self._h, _ptr(dq), _ptr(nq), _ptr(dt), _ptr(nt), _ptr(kq), _ptr(kt), float(ratio),
+                                                        _ptr(m), _ptr(nm)))
+        knn = np.zeros((B, M, 4), np.int32)
+        self.ctx.check(lib().vloam_vo_get_knn(self._h, _ptr(knn)))
+        return [{"matches": m[b, :nm[b]].copy(), "knn": knn[b, :nq[b]].copy()} for b in range(B)]
+
+    def match_buffers(self):
+        """(query_uv, train_uv, n_matches) device addresses of the last matchDescriptors call with keypoints."""
+        a, b, n = C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self.ctx.check(lib().vloam_vo_get_match_buffers(self._h, C.byref(a), C.byref(b), C.byref(n)))
+        return a.value, b.value, n.value
 
     def solveNlsAllDevice(self, prev_uv_dev, curr_uv_dev, n_matches_dev, init_dev=None):
         """solveNlsAll on device-resident matches ((batch, max_matches, 2) float32, (batch,) int32); asynchronous."""

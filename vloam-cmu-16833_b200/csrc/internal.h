@@ -17,7 +17,7 @@ enum KernelId {
   K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT, K_LO_BUILD_GRID, K_LO_ASSOCIATE_BRUTE,
   K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_FIT, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_PLACE, K_LM_MISC,
   K_LO_ACCUMULATE, K_LO_STEP, K_LM_ACCUMULATE, K_LM_STEP,
-  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC,
+  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC, K_VO_MATCH,
   K_COUNT
 };
 const char* kernel_name(int id);

@@ -831,42 +831,30 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
           // within 1 m in z lies in one of them); a cube in mode 1 has a single layer
           const bool flat = tab[14] != 0;
           const int zb0 = flat ? 0 : cube_zbin(sz - 1.001f, mnz), zb1 = flat ? 0 : cube_zbin(sz + 1.001f, mnz);
-          // the bounds of all (<= 2 x 3) runs first: independent loads, one memory latency for the lot
-          int ra[6], rn[6];
-#pragma unroll
-          for (int zi = 0; zi < 2; ++zi) {
-            const int z = zb0 + zi;
-            const bool zok = z <= zb1;
-            const int L = (zok && !flat) ? tab[z] : 0;
-            const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells;
-#pragma unroll
-            for (int ri = 0; ri < 3; ++ri) {
-              const int row = r0 + ri;
-              int a = 0, en = 0;
-              if (zok && row <= r1) {
-                if (flat) {
-                  a = tab[kTabHdr + row * kCubeCellsX + x0]; en = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
-                } else {
-                  a = L + (int)rel[row * kCubeCellsX + x0];
-                  en = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[row * kCubeCellsX + x1 + 1];   // a layer ends where the next begins
-                }
-              }
-              ra[zi * 3 + ri] = off + a; rn[zi * 3 + ri] = en - a;
-            }
-          }
           // ... once per entry of the valid list naming it: the sub-map index (the tie-break of the k-NN order) of a
           // point = offset of that entry's copy of the cube in laserCloud*FromMap + index inside the cube
           for (; e >= 0; e = st.entryNext[e]) {
             const unsigned gBase = (unsigned)st.validPrefix[kind][e];
-#pragma unroll
-            for (int r = 0; r < 6; ++r) {
-              if (STATS) nCand += (unsigned)rn[r];
-              for (int t = 0; t < rn[r]; t += 4) {          // four candidates in flight
-                float4 p[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (t + u < rn[r]) p[u] = S[ra[r] + t + u];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) if (t + u < rn[r]) consider(p[u], gBase, ra[r] + t + u);
+            for (int z = zb0; z <= zb1; ++z) {
+              const int L = flat ? 0 : tab[z];
+              const unsigned short* rel = reinterpret_cast<const unsigned short*>(tab + kTabHdr) + z * kCubeCells;
+              for (int row = r0; row <= r1; ++row) {
+                int ra, re;
+                if (flat) {
+                  ra = tab[kTabHdr + row * kCubeCellsX + x0]; re = tab[kTabHdr + row * kCubeCellsX + x1 + 1];
+                } else {
+                  ra = L + (int)rel[row * kCubeCellsX + x0];
+                  re = (row == kCubeCellsX - 1 && x1 == kCubeCellsX - 1) ? tab[z + 1] : L + (int)rel[row * kCubeCellsX + x1 + 1];   // a layer ends where the next begins
+                }
+                if (STATS) nCand += (unsigned)(re - ra);
+                // two candidates in flight
+                int t = ra;
+                for (; t + 1 < re; t += 2) {
+                  const float4 p0 = S[off + t], p1 = S[off + t + 1];
+                  consider(p0, gBase, off + t);
+                  consider(p1, gBase, off + t + 1);
+                }
+                if (t < re) consider(S[off + t], gBase, off + t);
               }
             }
           }
@@ -885,8 +873,9 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
   const LMState *__restrict__ stAll, const float4 *__restrict__ stack, int cap, const CubeTables T,                              \
       const short *__restrict__ entryHeadAll, const int *__restrict__ tabPool, const float4 *__restrict__ sorted, int mapCap,    \
       int *__restrict__ nnPos, LMState *statsOut, int shardRank, int shardWorld
-// Two register budgets of the same body (bound by memory latency: occupancy against spills is settled by measurement,
-// VLOAM_LM_KNN_OCC=4|6; measured on B200: see DESIGN.md).
+// Measured on B200 (64 streams per launch): this body, runs walked one after the other with two candidates in flight, 80
+// registers: 127 us; all run bounds loaded up front + four candidates in flight: 161 us at 80 registers (spills), 147 us at 126.
+// The occ4 variant stays selectable (VLOAM_LM_KNN_OCC=4).
 __global__ void __launch_bounds__(kKnnThreads, 6) lm_knn(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }
 __global__ void __launch_bounds__(kKnnThreads, 4) lm_knn_occ4(VB_LM_KNN_ARGS) { lm_knn_body<false>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }
 __global__ void __launch_bounds__(kKnnThreads) lm_knn_stats(VB_LM_KNN_ARGS) { lm_knn_body<true>(stAll, stack, cap, T, entryHeadAll, tabPool, sorted, mapCap, nnPos, statsOut, shardRank, shardWorld); }

@@ -10,6 +10,9 @@
 //                     distance weights
 //   vo_build_residuals VisualOdometry::solveNlsAll (visual_odometry.cpp:283-416): integer-truncated pixels (Q7), flow gate,
 //                     depth lookup, back-projection through P_rect0 (float column-pivoted Householder 3x3)
+//   vo_bf_match       ImageUtil::matchDescriptors (image_util.cpp:214-296) in the configuration visual_odometry.cpp:34-37 selects:
+//                     brute-force Hamming 2-NN over 256-bit ORB descriptors + the 0.8 ratio test; the train descriptors are
+//                     staged in shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier)
 //   vo_solve          CostFunctor32 / CostFunctor22 (ceres_cost_function.h:54-96, 147-185) with analytic Jacobians of
 //                     ceres::AngleAxisRotatePoint + ceres::Solve (<= 100 iterations, Huber 0.1, no manifold) in one launch
 #include <cstring>
@@ -21,6 +24,7 @@
 #include "cta_sort.cuh"
 #include "gn_solver.cuh"
 #include "internal.h"
+#include "tma_bulk.cuh"
 
 namespace vb {
 
@@ -453,6 +457,88 @@ __global__ void vo_export_prior(const VOState* __restrict__ st, VOFrame A, int B
   out[4] = V.t[0]; out[5] = V.t[1]; out[6] = V.t[2];
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// vo_bf_match: grid (B), block kMatchThreads, dynamic shared memory kMatchChunk * 32 bytes + an mbarrier.
+// cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, k = 2) + `m[0].distance < ratio * m[1].distance`
+// (image_util.cpp:263-283), for binary descriptors of 32 bytes (ORB, cv::ORB::create()).
+//   * a thread owns a query descriptor (8 words in registers) and scans the train descriptors, which the CTA stages
+//     in shared memory chunk by chunk with one TMA bulk copy per chunk (all threads then read the same descriptor:
+//     a shared-memory broadcast); Hamming distance = 8 x popc(xor);
+//   * OpenCV keeps the k best in insertion order — a candidate enters only if strictly closer than the current k-th and
+//     stays behind equal distances — i.e. the two smallest (distance, train index) pairs;
+//   * accepted matches are compacted in query order (the order of knn_matches), like the push_back loop of :275-281.
+constexpr int kMatchThreads = 1024, kMatchChunk = 1024;          // 32 KB of descriptors per chunk
+__global__ void __launch_bounds__(kMatchThreads) vo_bf_match(const uint8_t* __restrict__ descQ, const int* __restrict__ nQ,
+                                                              const uint8_t* __restrict__ descT, const int* __restrict__ nT, int maxK,
+                                                              const float* __restrict__ kpQ, const float* __restrict__ kpT, double ratio,
+                                                              int* __restrict__ matches /*[B][maxK][3]*/, int* __restrict__ nMatches,
+                                                              float* __restrict__ uvQ, float* __restrict__ uvT /*[B][maxK][2]*/,
+                                                              int4* __restrict__ knn /*[B][maxK]: idx0, idx1, d0, d1*/) {
+  extern __shared__ __align__(128) unsigned char match_smem[];
+  uint4* sT = reinterpret_cast<uint4*>(match_smem);                                         // [kMatchChunk][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(match_smem + (size_t)kMatchChunk * 32);
+  __shared__ int s_wsum[kMatchThreads / 32];
+  __shared__ int s_base;
+  const int b = blockIdx.x;
+  const int nq = min(max(nQ[b], 0), maxK), nt = min(max(nT[b], 0), maxK);
+  const uint4* gQ = reinterpret_cast<const uint4*>(descQ + (size_t)b * maxK * 32);
+  const unsigned char* gT = descT + (size_t)b * maxK * 32;
+  if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_fence_init(); s_base = 0; }
+  __syncthreads();
+  unsigned phase = 0;
+  for (int q0 = 0; q0 < nq; q0 += kMatchThreads) {          // (one round unless a frame has more than 1024 keypoints)
+    const int q = q0 + threadIdx.x;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (q < nq) { a0 = gQ[2 * q]; a1 = gQ[2 * q + 1]; }
+    int d0 = 0x7fffffff, d1 = 0x7fffffff, i0 = -1, i1 = -1;      // best and second best (distance, train index)
+    for (int t0 = 0; t0 < nt; t0 += kMatchChunk) {
+      const int m = min(kMatchChunk, nt - t0);
+      if (threadIdx.x == 0) {
+        fence_proxy_async();                                 // the previous chunk was read through the generic proxy
+        mbar_arrive_expect_tx(mbar, (unsigned)m * 32u);
+        bulk_g2s(sT, gT + (size_t)t0 * 32, (unsigned)m * 32u, mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+      if (q < nq) {
+        for (int t = 0; t < m; ++t) {
+          const uint4 b0 = sT[2 * t], b1 = sT[2 * t + 1];
+          const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                        __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+          if (d < d1) {                                      // strictly closer than the current second best
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = t0 + t; } else { d1 = d; i1 = t0 + t; }
+          }
+        }
+      }
+      __syncthreads();                                       // everyone is done with the chunk before it is refilled
+    }
+    // ratio test in double, as `float < double * float` evaluates (:277); fewer than two train descriptors: no second
+    // neighbour to test against (the reference would index past the end), no match
+    if (q < nq) knn[(size_t)b * maxK + q] = make_int4(i0, i1, i0 >= 0 ? d0 : -1, i1 >= 0 ? d1 : -1);
+    const bool ok = q < nq && i1 >= 0 && (double)(float)d0 < ratio * (double)(float)d1;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int w = threadIdx.x >> 5, l = lane_id();
+    if (l == 0) s_wsum[w] = __popc(bal);
+    __syncthreads();
+    int before = s_base;
+    for (int i = 0; i < w; ++i) before += s_wsum[i];
+    if (ok) {
+      const int o = before + __popc(bal & ((1u << l) - 1u));
+      int* mo = matches + ((size_t)b * maxK + o) * 3;
+      mo[0] = q; mo[1] = i0; mo[2] = d0;
+      if (kpQ && kpT) {
+        const size_t oq = ((size_t)b * maxK + q) * 2, ot = ((size_t)b * maxK + i0) * 2, oo = ((size_t)b * maxK + o) * 2;
+        uvQ[oo] = kpQ[oq]; uvQ[oo + 1] = kpQ[oq + 1];
+        uvT[oo] = kpT[ot]; uvT[oo + 1] = kpT[ot + 1];
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int i = 0; i < kMatchThreads / 32; ++i) tot += s_wsum[i]; s_base += tot; }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nMatches[b] = s_base;
+}
+
 struct vloam_vo {
   vloam_ctx* ctx = nullptr;
   int B = 0, cap = 0, maxM = 0;
@@ -467,6 +553,9 @@ struct vloam_vo {
   VOResidual* d_res = nullptr;
   VOState* d_st = nullptr;
   float* d_q = nullptr; float* d_qo = nullptr;  // query scratch
+  // descriptor matching: query / train descriptors [B][maxM][32], keypoints [B][maxM][2], counts, match list [B][maxM][3]
+  uint8_t* d_desc[2] = {nullptr, nullptr}; float* d_kp[2] = {nullptr, nullptr}; int* d_nkp[2] = {nullptr, nullptr};
+  int* d_matches = nullptr; int* d_nmatch = nullptr; float* d_muv[2] = {nullptr, nullptr}; int4* d_knn = nullptr;
   int qcap = 0;
   int slot() const { return (int)(count % 2); }
 };
@@ -489,6 +578,8 @@ int vloam_vo_destroy(vloam_vo* h) {
   for (int i = 0; i < 2; ++i) { cudaFree(h->bx[i]); cudaFree(h->by[i]); cudaFree(h->bd[i]); cudaFree(h->bc[i]); }
   cudaFree(h->d_prev); cudaFree(h->d_curr); cudaFree(h->d_nm); cudaFree(h->d_init); cudaFree(h->d_res); cudaFree(h->d_st);
   cudaFree(h->d_q); cudaFree(h->d_qo);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->d_desc[i]); cudaFree(h->d_kp[i]); cudaFree(h->d_nkp[i]); cudaFree(h->d_muv[i]); }
+  cudaFree(h->d_matches); cudaFree(h->d_nmatch); cudaFree(h->d_knn);
   delete h;
   return VLOAM_OK;
 }
@@ -513,6 +604,12 @@ int vloam_vo_create(vloam_ctx* c, int batch, int max_points, int max_matches, vl
   A((void**)&h->d_init, B * 6 * sizeof(double)); A((void**)&h->d_res, B * M * sizeof(VOResidual)); A((void**)&h->d_st, B * sizeof(VOState));
   h->qcap = 4096;
   A((void**)&h->d_q, h->qcap * 2 * sizeof(float)); A((void**)&h->d_qo, h->qcap * sizeof(float));
+  for (int i = 0; i < 2; ++i) {
+    A((void**)&h->d_desc[i], B * M * 32); A((void**)&h->d_kp[i], B * M * 2 * sizeof(float)); A((void**)&h->d_nkp[i], B * sizeof(int));
+    A((void**)&h->d_muv[i], B * M * 2 * sizeof(float));
+  }
+  A((void**)&h->d_matches, B * M * 3 * sizeof(int)); A((void**)&h->d_nmatch, B * sizeof(int)); A((void**)&h->d_knn, B * M * sizeof(int4));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(vo_bf_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchChunk * 32 + 16);
   if (e != cudaSuccess) { vloam_vo_destroy(h); return vfail(c, VLOAM_E_CUDA, "vloam_vo_create: allocation", e); }
   *out = h;
   return VLOAM_OK;
@@ -681,6 +778,53 @@ int vloam_vo_get_residuals(vloam_vo* h, int stream, int* type, double* obs) {
     if (type) type[i] = r[i].type;
     if (obs) for (int k = 0; k < 5; ++k) obs[(size_t)i * 5 + k] = r[i].obs[k];
   }
+  return VLOAM_OK;
+}
+
+// ImageUtil::matchDescriptors (image_util.cpp:214-296): BF + NORM_HAMMING + knnMatch(k = 2) + ratio test
+int vloam_vo_match_descriptors(vloam_vo* h, const uint8_t* desc_query, const int* n_query, const uint8_t* desc_train, const int* n_train,
+                               const float* kp_query, const float* kp_train, double ratio, int* matches_out, int* n_matches_out) {
+  if (!h || !desc_query || !n_query || !desc_train || !n_train || (kp_query == nullptr) != (kp_train == nullptr)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  const size_t B = h->B, M = h->maxM;
+  for (int b = 0; b < h->B; ++b)
+    if (n_query[b] < 0 || n_train[b] < 0 || n_query[b] > h->maxM || n_train[b] > h->maxM) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_match_descriptors: more keypoints than max_matches");
+  cudaStream_t st = c->stream;
+  VCU(c, cudaMemcpyAsync(h->d_desc[0], desc_query, B * M * 32, cudaMemcpyHostToDevice, st));
+  VCU(c, cudaMemcpyAsync(h->d_desc[1], desc_train, B * M * 32, cudaMemcpyHostToDevice, st));
+  VCU(c, cudaMemcpyAsync(h->d_nkp[0], n_query, B * sizeof(int), cudaMemcpyHostToDevice, st));
+  VCU(c, cudaMemcpyAsync(h->d_nkp[1], n_train, B * sizeof(int), cudaMemcpyHostToDevice, st));
+  if (kp_query) {
+    VCU(c, cudaMemcpyAsync(h->d_kp[0], kp_query, B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    VCU(c, cudaMemcpyAsync(h->d_kp[1], kp_train, B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+  }
+  (void)cudaGetLastError();
+  VB_LAUNCH(&c->prof, K_VO_MATCH, st, vo_bf_match<<<h->B, kMatchThreads, kMatchChunk * 32 + 16, st>>>(
+                                          h->d_desc[0], h->d_nkp[0], h->d_desc[1], h->d_nkp[1], h->maxM, kp_query ? h->d_kp[0] : nullptr,
+                                          kp_query ? h->d_kp[1] : nullptr, ratio, h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
+  VCU(c, cudaGetLastError());
+  if (matches_out) VCU(c, cudaMemcpyAsync(matches_out, h->d_matches, B * M * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_matches_out) VCU(c, cudaMemcpyAsync(n_matches_out, h->d_nmatch, B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VCU(c, cudaStreamSynchronize(st));
+  return VLOAM_OK;
+}
+// Parity read-out of the last vloam_vo_match_descriptors call: knn[batch][max_matches][4] = (trainIdx of the nearest, of the second
+// nearest, their Hamming distances) per query row, i.e. the knn_matches of image_util.cpp:263 before the ratio test.
+int vloam_vo_get_knn(vloam_vo* h, int* knn) {
+  if (!h || !knn) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  VCU(c, cudaMemcpyAsync(knn, h->d_knn, (size_t)h->B * h->maxM * sizeof(int4), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+// The matched pixel pairs of the last vloam_vo_match_descriptors call with keypoints, in solveNlsAll's layout: feed them to
+// vloam_vo_solve_device_async(h, query_uv_dev, train_uv_dev, n_matches_dev, ...) (query = previous frame, train = current frame,
+// visual_odometry.cpp:118-119).
+int vloam_vo_get_match_buffers(vloam_vo* h, const float** query_uv_dev, const float** train_uv_dev, const int** n_matches_dev) {
+  if (!h || !query_uv_dev || !train_uv_dev || !n_matches_dev) return VLOAM_E_INVALID;
+  *query_uv_dev = h->d_muv[0]; *train_uv_dev = h->d_muv[1]; *n_matches_dev = h->d_nmatch;
   return VLOAM_OK;
 }
 
