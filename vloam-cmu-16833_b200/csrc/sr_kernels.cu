@@ -20,11 +20,10 @@
 // reference is built without FMA (CMakeLists.txt:5-6) and the index sets depend on it.
 #include <math_constants.h>
 
-#include <cuda_pipeline.h>
-
 #include "common.cuh"
 #include "fdlibm_atan2f.h"
 #include "internal.h"
+#include "tma_bulk.cuh"
 
 namespace vb {
 
@@ -317,12 +316,15 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
 
 // ---------------------------------------------------------------------------------------------
 // sr_curvature: grid (ceil(tiles / tilesPerCta), B), block 256; a CTA walks `tilesPerCta` consecutive 1024-point tiles
-// with a two-stage cp.async pipeline (tile k+1 streams into shared memory while tile k is computed), so loads stay in
-// flight for the whole life of the CTA.  Every thread produces 4 consecutive curvatures from 14 points held in
-// registers.  21 B of HBM traffic per point (16 read + 4 + 1 written); the shared-memory tile is padded by one float4
-// every 8 so the stride-4 register fill is bank-conflict free.
+// through a two-stage pipeline: tile k+1 streams into shared memory while tile k is computed, so loads stay in flight for
+// the whole life of the CTA.  The tile is moved by the TMA unit: 130 bulk copies of one 128-byte row (8 points) each,
+// issued by 130 threads, completion counted in bytes on one mbarrier per stage — instead of 1034 per-thread 16-byte
+// cp.async with their address arithmetic and bounds tests (round 1).  Rows land at a 144-byte stride (one float4 of padding
+// every 8) so the stride-4 register fill below is bank-conflict free.  Every thread produces 4 consecutive curvatures from
+// 14 points held in registers.  21 B of HBM traffic per point (16 read + 4 + 1 written).
 __device__ __forceinline__ int curv_pad(int e) { return e + (e >> 3); }
 constexpr int kCurvTile = 1024;
+constexpr int kCurvElems = kCurvTile + 10, kCurvRows = (kCurvElems + 7) / 8;     // 1034 points with the halo = 129 rows + 2 points
 constexpr int kCurvTileSmem = kCurvTile + 10 + (kCurvTile + 10) / 8 + 1;
 __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
                                                      int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag,
@@ -334,20 +336,36 @@ __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__
   if (first >= last) return;
   const float4* c = cloud + (size_t)b * cap;
   __shared__ __align__(16) float4 tile[2][kCurvTileSmem];
-  auto issue = [&](int tileIdx, int buf) {   // tile[buf][pad(e)] <- cloud[tileIdx * 1024 - 5 + e]
-    const int base = tileIdx * kCurvTile;
-    for (int e = threadIdx.x; e < kCurvTile + 10; e += 256) {
-      const int g = base - 5 + e;
-      if (g >= 0 && g < size) __pipeline_memcpy_async(&tile[buf][curv_pad(e)], c + g, sizeof(float4));
-      else tile[buf][curv_pad(e)] = make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ __align__(8) uint64_t mbar[2];
+  if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+  __syncthreads();
+  auto issue = [&](int tileIdx, int buf) {   // tile[buf][pad(e)] <- cloud[tileIdx * 1024 - 5 + e], zero outside the cloud
+    const int base = tileIdx * kCurvTile - 5;
+    const int lo = max(0, -base), hi = min(kCurvElems, size - base);      // tile elements [lo, hi) exist
+    if (threadIdx.x == 0) {
+      // bytes the bulk copies will deliver: the rows that lie entirely inside [lo, hi)
+      const int rlo = (lo + 7) >> 3, rfull = hi >> 3;                     // full rows: rlo <= r < min(rfull, 129)
+      int pts = max(min(rfull, kCurvRows - 1) - rlo, 0) * 8;
+      if (hi == kCurvElems && lo <= 8 * (kCurvRows - 1)) pts += kCurvElems - 8 * (kCurvRows - 1);   // the 2-point tail row
+      mbar_arrive_expect_tx(&mbar[buf], (unsigned)pts * 16u);
     }
-    __pipeline_commit();
+    for (int r = threadIdx.x; r < kCurvRows; r += 256) {
+      const int e0 = 8 * r, e1 = min(e0 + 8, kCurvElems);
+      if (e0 >= lo && e1 <= hi) {
+        fence_proxy_async();        // this buffer was last read with ordinary loads (two iterations ago)
+        bulk_g2s(&tile[buf][curv_pad(e0)], c + base + e0, (unsigned)(e1 - e0) * 16u, &mbar[buf]);
+      } else {                      // a row that sticks out of the cloud (first / last tile only)
+        for (int e = e0; e < e1; ++e) tile[buf][curv_pad(e)] = (e >= lo && e < hi) ? c[base + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
   };
+  unsigned phase[2] = {0u, 0u};
   issue(first, 0);
   for (int tix = first; tix < last; ++tix) {
     const int buf = (tix - first) & 1;
-    if (tix + 1 < last) { issue(tix + 1, buf ^ 1); __pipeline_wait_prior(1); }
-    else __pipeline_wait_prior(0);
+    if (tix + 1 < last) issue(tix + 1, buf ^ 1);
+    mbar_wait(&mbar[buf], phase[buf]);
+    phase[buf] ^= 1u;
     __syncthreads();
     const int i0 = tix * kCurvTile + 4 * threadIdx.x;
     if (i0 < size) {
