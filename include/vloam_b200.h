@@ -147,6 +147,17 @@ int vloam_scan_registration_device(vloam_lidar* h, const float* xyz_dev, const i
 int vloam_get_input_device(vloam_lidar* h, const float** xyz_dev, const int** n_points_dev, int* stride_floats, size_t* slab_points);
 int vloam_input_consumed(vloam_lidar* h);
 
+/* One frame of the caller's loop in one call: LidarOdometryMapping::reset, scanRegistrationIO, laserOdometryIO and laserMappingIO
+ * (vloam_main_node.cpp:134,165-167) for the given scans; results are read with vloam_get_lo_pose / vloam_get_lm_pose as usual.
+ * use_graph != 0: the ~40 kernel launches of a frame are captured into a CUDA graph the first time a (buffer parity, odometry
+ * initialised, mapping skipped) combination occurs and replayed afterwards — one launch per frame, which is what the latency of
+ * a single stream is made of.  prior_dev: NULL or the device array vloam_laser_odometry_async takes.  The device variant copies the
+ * scans into the handle's own input slot first (a graph replays fixed addresses). */
+int vloam_lidar_process(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points,
+                        const double* prior_dev, int use_graph);
+int vloam_lidar_process_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats, size_t slab_points,
+                               const double* prior_dev, int use_graph);
+
 /* status[batch]: VLOAM_STREAM_* bits of the last scan registration. */
 int vloam_get_stream_status(vloam_lidar* h, int* status);
 /* counts[batch][5]: sizes of laserCloud, sharp, lessSharp, flat, lessFlat   (ScanRegistration::output :501-512) */
@@ -288,6 +299,8 @@ int vloam_vo_get_knn(vloam_vo* h, int* knn);
 /* The matched pixel pairs of that call (when keypoints were given) stay on the device in solveNlsAll's layout
  * ([batch][max_matches][2] each, counts [batch]): pass them to vloam_vo_solve_device_async. */
 int vloam_vo_get_match_buffers(vloam_vo* h, const float** query_uv_dev, const float** train_uv_dev, const int** n_matches_dev);
+/* ... and their host copy (parity read-out), query_uv / train_uv [batch][max_matches][2]. */
+int vloam_vo_get_match_uv(vloam_vo* h, float* query_uv, float* train_uv);
 /* VO result -> LO prior, on the device: cam0_curr_T_cam0_last (visual_odometry.cpp:426-430) ->
  * velo_last_VOT_velo_curr = velo_T_cam0 * cam0_curr_T_cam0_last^-1 * velo_T_cam0^-1 (VloamTF::VO2VeloAndBase, vloam_tf.cpp:59-63),
  * written as [batch][7] = q(x y z w) t to prior_dev, the layout vloam_laser_odometry_async reads (laser_odometry.cpp:225-232).

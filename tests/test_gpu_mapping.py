@@ -473,3 +473,42 @@ def test_laser_mapping_large_cube_uses_flat_index(synth, oracle):
                 assert g_["n_plane"] > 200      # the first scan matches against the dense cube (still > 65 535 points: flat index)
         _compare_all_cubes(lom, pipe.lm, f"scan {k}")
     lom.close()
+
+
+@pytest.mark.parametrize("batch", [1, 3])
+def test_one_call_per_frame_with_cuda_graph_replay_matches_stage_calls(synth, batch):
+    """vloam_lidar_process (reset + scanRegistrationIO + laserOdometryIO + laserMappingIO in one call, the frame's launch
+    sequence replayed as a CUDA graph from the fourth frame on) must leave exactly the state the three stage calls leave:
+    identical poses (bit for bit — same kernels, same order) and identical maps, host-buffer and device-buffer variants."""
+    import torch
+    import vloam_b200 as V
+    streams = [synth.ScanStream(60 + b, n_cols=512) for b in range(batch)]
+    cap = 64 * 512
+    mk = lambda: V.LidarOdometryMapping(batch=batch, max_points=cap, map_capacity_points=1 << 17)   # noqa: E731
+    ref, g_host, g_dev, nog = mk(), mk(), mk(), mk()
+    n_dev = torch.full((batch,), cap, dtype=torch.int32, device="cuda")
+    for k in range(8):
+        buf = np.stack([s.scan(k) for s in streams])
+        ref.reset(); ref.scanRegistrationIO(buf); lo_ref = ref.laserOdometryIO(); lm_ref = ref.laserMappingIO()
+        g_host.process(buf, use_graph=True)
+        xyz = torch.from_numpy(buf).cuda()
+        torch.cuda.synchronize()
+        g_dev.processDevice(xyz, n_dev, 3, cap, use_graph=True)
+        nog.processDevice(xyz, n_dev, 3, cap, use_graph=False)
+        for name, h in (("graph/host", g_host), ("graph/device", g_dev), ("direct/device", nog)):
+            lo, lm = h.lo_pose(), h.lm_pose()
+            for key in lo_ref:
+                assert np.array_equal(lo[key], lo_ref[key]), (k, name, key)
+            for key in lm_ref:
+                assert np.array_equal(lm[key], lm_ref[key]), (k, name, key)
+            assert np.array_equal(h.map_stats()[:, :, 0], ref.map_stats()[:, :, 0]), (k, name)
+    # the maps themselves
+    for kind in (0, 1):
+        for cube in range(4851):
+            a = ref.map_get_cube(kind, cube)
+            if a.shape[0]:
+                for h in (g_host, g_dev):
+                    assert np.array_equal(a.view(np.uint32), h.map_get_cube(kind, cube).view(np.uint32)), (kind, cube)
+    assert g_host.ctx.launch_count > 0
+    for h in (ref, g_host, g_dev, nog):
+        h.close()

@@ -79,6 +79,8 @@ def lib():
             "vloam_scan_registration": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_device": [vp, vp, vp, C.c_int, C.c_size_t],
             "vloam_scan_registration_ptrs": [vp, vp, vp, C.c_int],
+            "vloam_lidar_process": [vp, vp, vp, C.c_int, C.c_size_t, vp, C.c_int],
+            "vloam_lidar_process_device": [vp, vp, vp, C.c_int, C.c_size_t, vp, C.c_int],
             "vloam_get_input_device": [vp, pp, pp, c_ip, C.POINTER(C.c_size_t)], "vloam_input_consumed": [vp],
             "vloam_shard_buffer": [vp, pp, C.POINTER(C.c_size_t)], "vloam_shard_ipc_handle": [vp, C.c_char_p],
             "vloam_shard_open_ipc": [vp, C.c_int, C.c_int, C.c_char_p], "vloam_shard_enable": [vp, C.c_int, C.c_int, pp],
@@ -111,7 +113,7 @@ def lib():
             "vloam_vo_export_lo_prior": [vp, c_dp, vp],
             "vloam_vo_get_trace": [vp, C.c_int, c_dp, c_ip, c_dp],
             "vloam_vo_match_descriptors": [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp], "vloam_vo_get_knn": [vp, vp],
-            "vloam_vo_get_match_buffers": [vp, pp, pp, pp],
+            "vloam_vo_get_match_buffers": [vp, pp, pp, pp], "vloam_vo_get_match_uv": [vp, vp, vp],
             "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
         }
         for name, args in sig.items():
@@ -263,6 +265,33 @@ class LidarOdometryMapping:
         assert p.shape == (self.batch,) and n.shape == (self.batch,)
         self._keep = (p, n, keep)
         self.ctx.check(lib().vloam_scan_registration_ptrs(self._h, _ptr(p), _ptr(n), stride))
+
+    def process(self, laserCloudIn, n_points=None, prior_dev=None, use_graph=True):
+        """reset + scanRegistrationIO + laserOdometryIO + laserMappingIO in one call (asynchronous; read the poses with
+        lo_pose() / lm_pose()).  use_graph: replay the frame's launch sequence as one CUDA graph."""
+        a = laserCloudIn
+        if isinstance(a, np.ndarray):
+            a = np.ascontiguousarray(a, dtype=np.float32)
+        shape = tuple(a.shape)
+        if len(shape) == 2:
+            shape = (1,) + shape
+        assert shape[0] == self.batch and 3 <= shape[2] <= 16, shape
+        if n_points is None:
+            n_points = np.full(self.batch, shape[1], np.int32)
+        n_points = np.ascontiguousarray(n_points, np.int32)
+        self._keep = (a, n_points)
+        self.ctx.check(lib().vloam_lidar_process(self._h, _ptr(a), _ptr(n_points), shape[2], shape[1], _ptr(prior_dev), int(use_graph)))
+
+    def processDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int, prior_dev=None, use_graph=True):
+        self._keep = (xyz_dev, n_points_dev)
+        self.ctx.check(lib().vloam_lidar_process_device(self._h, _ptr(xyz_dev), _ptr(n_points_dev), stride, slab_points, _ptr(prior_dev),
+                                                        int(use_graph)))
+
+    def lm_pose(self):
+        pose = np.zeros((self.batch, 14))
+        self.ctx.check(lib().vloam_get_lm_pose(self._h, pose.ctypes.data_as(c_dp)))
+        return {"q_w_curr": pose[:, 0:4].copy(), "t_w_curr": pose[:, 4:7].copy(), "q_wmap_wodom": pose[:, 7:11].copy(),
+                "t_wmap_wodom": pose[:, 11:14].copy()}
 
     def scanRegistrationDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int):
         """Scans already resident in HBM (torch CUDA tensors or raw device addresses)."""
@@ -606,6 +635,13 @@ class VisualOdometry:
         a, b, n = C.c_void_p(), C.c_void_p(), C.c_void_p()
         self.ctx.check(lib().vloam_vo_get_match_buffers(self._h, C.byref(a), C.byref(b), C.byref(n)))
         return a.value, b.value, n.value
+
+    def match_uv(self):
+        """Host copies of the matched (query, train) pixel pairs, (batch, max_matches, 2) each."""
+        q = np.zeros((self.batch, self.max_matches, 2), np.float32)
+        t = np.zeros_like(q)
+        self.ctx.check(lib().vloam_vo_get_match_uv(self._h, _ptr(q), _ptr(t)))
+        return q, t
 
     def solveNlsAllDevice(self, prev_uv_dev, curr_uv_dev, n_matches_dev, init_dev=None):
         """solveNlsAll on device-resident matches ((batch, max_matches, 2) float32, (batch,) int32); asynchronous."""

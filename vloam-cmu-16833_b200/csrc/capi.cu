@@ -179,6 +179,11 @@ struct vloam_lidar {
   LOGrid grid;
   // laser mapping
   LMDevice* lm = nullptr;
+  // CUDA graphs of one frame's launch sequence (vloam_lidar_process): [buffer parity][odometry initialised][mapping skipped]
+  cudaGraphExec_t graph[2][2][2] = {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}};
+  bool capturing = false;
+  long long graph_launches[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};   // kernel launches one replay stands for (bench.py's gpu_launches)
+  const double* graph_prior[2][2][2] = {{{nullptr, nullptr}, {nullptr, nullptr}}, {{nullptr, nullptr}, {nullptr, nullptr}}};
   int cur() const { return (int)(frame & 1); }
 };
 
@@ -286,6 +291,7 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart); cudaFree(h->grid.cursor);
   cudaFree(h->grid.gnRec); cudaFree(h->grid.gnState); cudaFree(h->grid.gnPartial); cudaFree(h->grid.gnCounts);
   for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); }
+  for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) if (h->graph[a][b][k]) cudaGraphExecDestroy(h->graph[a][b][k]);
   if (h->nccl) { if (NcclApi* api = nccl_api()) api->CommDestroy(h->nccl); h->nccl = nullptr; }
   if (h->lm) lm_destroy(h->lm);
   for (int r = 0; r < kMaxShard; ++r) if (h->ipc_open[r]) cudaIpcCloseMemHandle(h->ipc_open[r]);
@@ -502,10 +508,11 @@ static int run_scan_registration(vloam_lidar* h, const float* xyz_dev, const int
 constexpr int kMaxInputStride = 16;
 }  // extern "C"
 
-// Upload one scan per stream on the copy stream and run scan registration on it.  src(b) = host address of stream b's points;
-// contiguous != nullptr: the slabs are `slab_points` apart in one buffer (one DMA for the whole batch when they line up).
+// Upload one scan per stream on the copy stream into the next input slot; the main stream waits for it.  src(b) = host
+// address of stream b's points; contiguous != nullptr: the slabs are `slab_points` apart in one buffer (one DMA for the whole
+// batch when they line up).
 template <typename Src>
-static int upload_and_register(vloam_lidar* h, Src src, const float* contiguous, const int* n_points, int stride, size_t slab_points) {
+static int upload_only(vloam_lidar* h, Src src, const float* contiguous, const int* n_points, int stride, size_t slab_points) {
   vloam_ctx* c = h->ctx;
   CU(c, cudaSetDevice(c->device));
   if (stride > h->in_stride) {   // first scan with wider records: re-size both input slabs (rare; synchronises)
@@ -546,7 +553,16 @@ static int upload_and_register(vloam_lidar* h, Src src, const float* contiguous,
   CU(c, cudaMemcpyAsync(h->d_n[slot], n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
   CU(c, cudaEventRecord(h->ev_in_ready[slot], c->copy_stream));
   CU(c, cudaStreamWaitEvent(c->stream, h->ev_in_ready[slot], 0));
-  int r = run_scan_registration(h, h->d_in[slot], h->d_n[slot], stride, (size_t)h->cap);
+  return VLOAM_OK;
+}
+// ... and run scan registration on it
+template <typename Src>
+static int upload_and_register(vloam_lidar* h, Src src, const float* contiguous, const int* n_points, int stride, size_t slab_points) {
+  vloam_ctx* c = h->ctx;
+  const int slot = (int)(h->host_scans & 1);
+  int r = upload_only(h, src, contiguous, n_points, stride, slab_points);
+  if (r) return r;
+  r = run_scan_registration(h, h->d_in[slot], h->d_n[slot], stride, (size_t)h->cap);
   if (r) return r;
   CU(c, cudaEventRecord(h->ev_in_free[slot], c->stream));
   h->in_used[slot] = true;
@@ -720,7 +736,7 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
   {  // asynchronous read-back of the poses into the pinned buffer of this frame's parity
     const int par = (int)(h->frame & 1);
     CU(c, cudaMemcpyAsync(h->h_pose[par], h->d_pose, (size_t)h->B * 16 * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaEventRecord(h->ev_pose[par], c->stream));
+    if (!h->capturing) CU(c, cudaEventRecord(h->ev_pose[par], c->stream));   // (a captured frame records it after the graph launch)
     h->pose_valid[par] = true;
   }
   h->lo_done_for_frame = true;
@@ -834,6 +850,101 @@ int vloam_get_lm_pose(vloam_lidar* h, double* pose_out) {
   cudaError_t e = lm_get_pose(h->lm, c->stream, pose_out);
   return e == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "vloam_get_lm_pose", e);
 }
+
+// ------------------------------------------------------------------------------------------------ one frame in one call
+// The LiDAR part of vloam_main_node.cpp:125-180 — reset, scanRegistrationIO, laserOdometryIO, laserMappingIO — for the scan
+// already sitting in input slot `slot`.  With use_graph the ~40 launches are captured into a CUDA graph the first time a
+// (buffer parity, odometry initialised, mapping skipped) combination occurs and replayed afterwards: one launch per frame.
+static int process_frame(vloam_lidar* h, int slot, int stride, const double* prior_dev, int use_graph) {
+  vloam_ctx* c = h->ctx;
+  const bool inited = h->frame + 1 >= 1;                       // LaserOdometry::systemInited for the frame about to run
+  const bool skip = ((h->lo_frames + 1) % h->p.mapping_skip_frame) != 0;
+  const int par = (int)((h->frame + 1) & 1);
+  const bool graphable = use_graph && !c->prof.enabled && h->shard.world <= 1 && lm_graph_safe(h->lm) && par == slot;
+  auto run_direct = [&]() -> int {
+    vloam_lidar_reset(h);
+    int r = run_scan_registration(h, h->d_in[slot], h->d_n[slot], stride, (size_t)h->cap);
+    if (r) return r;
+    r = run_laser_odometry(h, prior_dev);
+    if (r) return r;
+    return vloam_laser_mapping(h, nullptr);
+  };
+  if (!graphable) return run_direct();
+  cudaGraphExec_t& g = h->graph[par][inited ? 1 : 0][skip ? 1 : 0];
+  if (g && h->graph_prior[par][inited ? 1 : 0][skip ? 1 : 0] != prior_dev) { cudaGraphExecDestroy(g); g = nullptr; }   // another prior buffer: capture again
+  if (!g) {
+    cudaError_t e = lm_ensure_alloc(h->lm, c->stream);         // no allocation inside a capture
+    if (e != cudaSuccess) return fail(c, VLOAM_E_CUDA, "vloam_lidar_process: map allocation", e);
+    CU(c, cudaStreamSynchronize(c->stream));
+    const long long launches0 = c->prof.launches;
+    CU(c, cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+    h->capturing = true;
+    const int r = run_direct();                                // records the launches, advances the host-side frame state
+    h->capturing = false;
+    cudaGraph_t graph = nullptr;
+    const cudaError_t ce = cudaStreamEndCapture(c->stream, &graph);
+    if (r) { if (graph) cudaGraphDestroy(graph); return r; }
+    if (ce != cudaSuccess) return fail(c, VLOAM_E_CUDA, "vloam_lidar_process: stream capture", ce);
+    const cudaError_t ie = cudaGraphInstantiate(&g, graph, 0);
+    cudaGraphDestroy(graph);
+    if (ie != cudaSuccess) { g = nullptr; return fail(c, VLOAM_E_CUDA, "vloam_lidar_process: graph instantiation", ie); }
+    h->graph_prior[par][inited ? 1 : 0][skip ? 1 : 0] = prior_dev;
+    h->graph_launches[par][inited ? 1 : 0][skip ? 1 : 0] = c->prof.launches - launches0;
+  } else {
+    // replay: the host-side state the three stages leave behind
+    vloam_lidar_reset(h);
+    h->frame++;
+    h->pose_valid[par] = true;
+    h->lo_done_for_frame = true;
+    h->lo_frames++;
+    lm_note_run(h->lm, skip);
+    c->prof.launches += h->graph_launches[par][inited ? 1 : 0][skip ? 1 : 0];
+  }
+  CU(c, cudaGraphLaunch(g, c->stream));
+  CU(c, cudaEventRecord(h->ev_pose[par], c->stream));          // the frame's poses are in the pinned buffer once the graph has run
+  return VLOAM_OK;
+}
+
+int vloam_lidar_process(vloam_lidar* h, const float* xyz, const int* n_points, int stride, size_t slab_points, const double* prior_dev,
+                        int use_graph) {
+  if (!h || !xyz || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  // the upload is the front half of vloam_scan_registration; the kernels then run from the slot (directly or as a graph)
+  h->host_scans = h->frame + 1;                                 // input slot parity == frame parity on this path
+  const int slot = (int)(h->host_scans & 1);
+  const int r = upload_only(h, [&](int b) { return xyz + (size_t)b * slab_points * stride; }, xyz, n_points, stride, slab_points);
+  if (r) return r;
+  const int r2 = process_frame(h, slot, stride, h->p.detach_VO_LO ? nullptr : prior_dev, use_graph);
+  if (r2) return r2;
+  CU(c, cudaEventRecord(h->ev_in_free[slot], c->stream));
+  h->in_used[slot] = true; h->last_stride = stride; h->host_scans++;
+  return VLOAM_OK;
+}
+
+int vloam_lidar_process_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points, const double* prior_dev,
+                               int use_graph) {
+  if (!h || !xyz_dev || !n_dev || stride < 3 || stride > kMaxInputStride || slab_points == 0) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  CU(c, cudaSetDevice(c->device));
+  if (!use_graph) {
+    vloam_lidar_reset(h);
+    int r = run_scan_registration(h, xyz_dev, n_dev, stride, slab_points);
+    if (r) return r;
+    r = run_laser_odometry(h, h->p.detach_VO_LO ? nullptr : prior_dev);
+    if (r) return r;
+    return vloam_laser_mapping(h, nullptr);
+  }
+  // a graph replays fixed addresses: the scan is first copied (device to device) into the handle's input slot
+  if (stride > h->in_stride) return fail(c, VLOAM_E_INVALID, "vloam_lidar_process_device with graphs: stride above the handle's input stride (4)");
+  const int slot = (int)((h->frame + 1) & 1);
+  const size_t rowBytes = (slab_points < (size_t)h->cap ? slab_points : (size_t)h->cap) * stride * sizeof(float);
+  CU(c, cudaMemcpy2DAsync(h->d_in[slot], (size_t)h->cap * stride * sizeof(float), xyz_dev, slab_points * stride * sizeof(float), rowBytes, (size_t)h->B,
+                          cudaMemcpyDeviceToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(h->d_n[slot], n_dev, (size_t)h->B * sizeof(int), cudaMemcpyDeviceToDevice, c->stream));
+  h->host_scans = h->frame + 2; h->last_stride = stride;
+  return process_frame(h, slot, stride, h->p.detach_VO_LO ? nullptr : prior_dev, use_graph);
+}
+
 int vloam_map_set_cube(vloam_lidar* h, int stream, int kind, int cube, const float* xyzi, int n) {
   if (!h || stream < 0 || stream >= h->B || kind < 0 || kind > 1 || cube < 0 || cube >= 4851 || n < 0 || (n && !xyzi)) return VLOAM_E_INVALID;
   vloam_ctx* c = h->ctx;

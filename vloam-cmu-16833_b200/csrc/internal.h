@@ -90,6 +90,9 @@ struct LMDevice;
 cudaError_t lm_create(Profiler* prof, cudaStream_t st, int B, int cap, const vloam_lidar_params* p, LMDevice** out);
 void lm_destroy(LMDevice* lm);
 void lm_reset(LMDevice* lm);
+cudaError_t lm_ensure_alloc(LMDevice* lm, cudaStream_t st);
+void lm_note_run(LMDevice* lm, bool skip_frame);
+bool lm_graph_safe(const LMDevice* lm);
 cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const float4* cornerLast, const float4* surfLast,
                    const LOState* lo, bool skip_frame);
 cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out);

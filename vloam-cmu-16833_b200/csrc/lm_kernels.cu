@@ -1659,6 +1659,11 @@ void lm_destroy(LMDevice* lm) {
   delete lm;
 }
 void lm_reset(LMDevice* lm) { if (lm) lm->reset_valid = true; }
+// CUDA-graph replay (capi.cu): the device buffers must exist before a capture starts, and a replayed lm_run leaves the same
+// host-side flags behind as a launched one.
+cudaError_t lm_ensure_alloc(LMDevice* lm, cudaStream_t st) { return lm_alloc(lm, st); }
+void lm_note_run(LMDevice* lm, bool skip_frame) { if (lm && !skip_frame) { lm->reset_valid = false; lm->ran = true; } }
+bool lm_graph_safe(const LMDevice* lm) { return lm && !lm->debugStats && lm->snap == nullptr && lm->ncclComm == nullptr; }
 
 cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const float4* cornerLast, const float4* surfLast,
                    const LOState* lo, bool skip_frame) {

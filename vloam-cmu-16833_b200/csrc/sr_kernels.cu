@@ -20,6 +20,10 @@
 // reference is built without FMA (CMakeLists.txt:5-6) and the index sets depend on it.
 #include <math_constants.h>
 
+#include <cstdlib>
+
+#include <cuda_pipeline.h>
+
 #include "common.cuh"
 #include "fdlibm_atan2f.h"
 #include "internal.h"
@@ -317,18 +321,25 @@ __global__ void __launch_bounds__(1024) sr_scatter(const float* __restrict__ xyz
 // ---------------------------------------------------------------------------------------------
 // sr_curvature: grid (ceil(tiles / tilesPerCta), B), block 256; a CTA walks `tilesPerCta` consecutive 1024-point tiles
 // through a two-stage pipeline: tile k+1 streams into shared memory while tile k is computed, so loads stay in flight for
-// the whole life of the CTA.  The tile is moved by the TMA unit: 130 bulk copies of one 128-byte row (8 points) each,
-// issued by 130 threads, completion counted in bytes on one mbarrier per stage — instead of 1034 per-thread 16-byte
-// cp.async with their address arithmetic and bounds tests (round 1).  Rows land at a 144-byte stride (one float4 of padding
-// every 8) so the stride-4 register fill below is bank-conflict free.  Every thread produces 4 consecutive curvatures from
-// 14 points held in registers.  21 B of HBM traffic per point (16 read + 4 + 1 written).
+// the whole life of the CTA.  Every thread produces 4 consecutive curvatures from 14 points held in registers; rows of 8
+// points sit at a 144-byte stride in shared memory (one float4 of padding every 8) so that stride-4 register fill is
+// bank-conflict free.  21 B of HBM traffic per point (16 read + 4 + 1 written).
+//
+// Two ways of moving a tile, same arithmetic (template parameter TMA):
+//   false (default)  per-thread 16-byte cp.async (LDGSTS), 4 per thread and tile, no bounds tests on interior tiles;
+//   true             the TMA unit: one cp.async.bulk per 128-byte row (the padding forbids longer runs), 130 per tile, issued
+//                    by one warp in a uniform loop, completion counted in bytes on an mbarrier per stage.
+// Measured on B200, 64 streams per launch: LDGSTS 36.1 us (3.7 TB/s, 57 % of the measured HBM peak), TMA rows 42.4 us —
+// 130 small bulk copies per 16 KB tile cost more than they save, so LDGSTS stays the default (VLOAM_SR_CURV_TMA=1 selects
+// the other).
 __device__ __forceinline__ int curv_pad(int e) { return e + (e >> 3); }
 constexpr int kCurvTile = 1024;
 constexpr int kCurvElems = kCurvTile + 10, kCurvRows = (kCurvElems + 7) / 8;     // 1034 points with the halo = 129 rows + 2 points
 constexpr int kCurvTileSmem = kCurvTile + 10 + (kCurvTile + 10) / 8 + 1;
-__global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
-                                                     int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag,
-                                                     int tilesPerCta) {
+template <bool TMA>
+__device__ __forceinline__ void sr_curvature_body(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud,
+                                                  int cap, float* __restrict__ curv, uint8_t* __restrict__ gapflag,
+                                                  int tilesPerCta) {
   const int b = blockIdx.y;
   const int size = hdr[b].cloudSize;
   const int ntiles = (size + kCurvTile - 1) / kCurvTile;
@@ -337,35 +348,57 @@ __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__
   const float4* c = cloud + (size_t)b * cap;
   __shared__ __align__(16) float4 tile[2][kCurvTileSmem];
   __shared__ __align__(8) uint64_t mbar[2];
-  if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
-  __syncthreads();
+  if (TMA) {
+    if (threadIdx.x == 0) { mbar_init(&mbar[0], 1); mbar_init(&mbar[1], 1); mbar_fence_init(); }
+    __syncthreads();
+  }
   auto issue = [&](int tileIdx, int buf) {   // tile[buf][pad(e)] <- cloud[tileIdx * 1024 - 5 + e], zero outside the cloud
     const int base = tileIdx * kCurvTile - 5;
     const int lo = max(0, -base), hi = min(kCurvElems, size - base);      // tile elements [lo, hi) exist
-    if (threadIdx.x == 0) {
-      // bytes the bulk copies will deliver: the rows that lie entirely inside [lo, hi)
-      const int rlo = (lo + 7) >> 3, rfull = hi >> 3;                     // full rows: rlo <= r < min(rfull, 129)
-      int pts = max(min(rfull, kCurvRows - 1) - rlo, 0) * 8;
-      if (hi == kCurvElems && lo <= 8 * (kCurvRows - 1)) pts += kCurvElems - 8 * (kCurvRows - 1);   // the 2-point tail row
-      mbar_arrive_expect_tx(&mbar[buf], (unsigned)pts * 16u);
-    }
-    for (int r = threadIdx.x; r < kCurvRows; r += 256) {
-      const int e0 = 8 * r, e1 = min(e0 + 8, kCurvElems);
-      if (e0 >= lo && e1 <= hi) {
-        fence_proxy_async();        // this buffer was last read with ordinary loads (two iterations ago)
-        bulk_g2s(&tile[buf][curv_pad(e0)], c + base + e0, (unsigned)(e1 - e0) * 16u, &mbar[buf]);
-      } else {                      // a row that sticks out of the cloud (first / last tile only)
-        for (int e = e0; e < e1; ++e) tile[buf][curv_pad(e)] = (e >= lo && e < hi) ? c[base + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (TMA) {
+      if (threadIdx.x == 0) {
+        // bytes the bulk copies will deliver: the rows that lie entirely inside [lo, hi)
+        const int rlo = (lo + 7) >> 3, rfull = hi >> 3;                   // full rows: rlo <= r < min(rfull, 129)
+        int pts = max(min(rfull, kCurvRows - 1) - rlo, 0) * 8;
+        if (hi == kCurvElems && lo <= 8 * (kCurvRows - 1)) pts += kCurvElems - 8 * (kCurvRows - 1);   // the 2-point tail row
+        mbar_arrive_expect_tx(&mbar[buf], (unsigned)pts * 16u);
       }
+      if (threadIdx.x < 32) {       // one warp issues the copies: the instruction is warp-uniform (UBLKCP takes uniform registers)
+        fence_proxy_async();        // this buffer was last read with ordinary loads (two iterations ago)
+        for (int r = 0; r < kCurvRows; ++r) {
+          const int e0 = 8 * r, e1 = min(e0 + 8, kCurvElems);
+          if (e0 >= lo && e1 <= hi) {
+            if (threadIdx.x == 0) bulk_g2s(&tile[buf][curv_pad(e0)], c + base + e0, (unsigned)(e1 - e0) * 16u, &mbar[buf]);
+          } else if ((int)threadIdx.x < e1 - e0) {   // a row that sticks out of the cloud (first / last tile only)
+            const int e = e0 + threadIdx.x;
+            tile[buf][curv_pad(e)] = (e >= lo && e < hi) ? c[base + e] : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
+      }
+    } else {
+      if (lo == 0 && hi == kCurvElems) {      // interior tile: no bounds tests
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { const int e = k * 256 + threadIdx.x; __pipeline_memcpy_async(&tile[buf][curv_pad(e)], c + base + e, sizeof(float4)); }
+        if (threadIdx.x < 10) { const int e = kCurvTile + threadIdx.x; __pipeline_memcpy_async(&tile[buf][curv_pad(e)], c + base + e, sizeof(float4)); }
+      } else {
+        for (int e = threadIdx.x; e < kCurvElems; e += 256) {
+          if (e >= lo && e < hi) __pipeline_memcpy_async(&tile[buf][curv_pad(e)], c + base + e, sizeof(float4));
+          else tile[buf][curv_pad(e)] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+      }
+      __pipeline_commit();
     }
   };
-  unsigned phase[2] = {0u, 0u};
+  unsigned phase0 = 0u, phase1 = 0u;
   issue(first, 0);
   for (int tix = first; tix < last; ++tix) {
     const int buf = (tix - first) & 1;
     if (tix + 1 < last) issue(tix + 1, buf ^ 1);
-    mbar_wait(&mbar[buf], phase[buf]);
-    phase[buf] ^= 1u;
+    if (TMA) {
+      if (buf == 0) { mbar_wait(&mbar[0], phase0); phase0 ^= 1u; } else { mbar_wait(&mbar[1], phase1); phase1 ^= 1u; }
+    } else {
+      if (tix + 1 < last) __pipeline_wait_prior(1); else __pipeline_wait_prior(0);
+    }
     __syncthreads();
     const int i0 = tix * kCurvTile + 4 * threadIdx.x;
     if (i0 < size) {
@@ -402,6 +435,14 @@ __global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__
     }
     __syncthreads();   // everyone is done with tile[buf] before the next iteration refills it
   }
+}
+__global__ void __launch_bounds__(256) sr_curvature(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
+                                                     float* __restrict__ curv, uint8_t* __restrict__ gapflag, int tilesPerCta) {
+  sr_curvature_body<false>(hdr, cloud, cap, curv, gapflag, tilesPerCta);
+}
+__global__ void __launch_bounds__(256) sr_curvature_tma(const SRHeader* __restrict__ hdr, const float4* __restrict__ cloud, int cap,
+                                                         float* __restrict__ curv, uint8_t* __restrict__ gapflag, int tilesPerCta) {
+  sr_curvature_body<true>(hdr, cloud, cap, curv, gapflag, tilesPerCta);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -951,7 +992,9 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
     // tiles per CTA: long pipelines when the batch alone fills the machine, one tile per CTA for small batches
     const int tiles = (cap + kCurvTile - 1) / kCurvTile;
     const int per = (size_t)B * tiles >= 4096 ? 4 : 1;
-    VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
+    static const bool useTma = [] { const char* e = getenv("VLOAM_SR_CURV_TMA"); return e && e[0] == '1'; }();
+    if (useTma) VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature_tma<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
+    else VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
   }
   VB_LAUNCH(prof, K_SR_PICK, st, sr_pick_features<2048><<<dim3(kMaxRings / 4, B), 128, 0, st>>>(hdr, curv, gapflag, cap, label, featIdx));
   VB_LAUNCH(prof, K_SR_VOXEL, st, sr_less_flat_voxel<2048><<<dim3(kMaxRings, B), 256, sizeof(VoxelSmem<2048>), st>>>(hdr, cloud, cap, label, lessFlatStage));

@@ -809,6 +809,17 @@ int vloam_vo_match_descriptors(vloam_vo* h, const uint8_t* desc_query, const int
   VCU(c, cudaStreamSynchronize(st));
   return VLOAM_OK;
 }
+// Host copy of the matched pixel pairs (the arrays vloam_vo_get_match_buffers names): query_uv / train_uv [batch][max_matches][2].
+int vloam_vo_get_match_uv(vloam_vo* h, float* query_uv, float* train_uv) {
+  if (!h || !query_uv || !train_uv) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  const size_t bytes = (size_t)h->B * h->maxM * 2 * sizeof(float);
+  VCU(c, cudaMemcpyAsync(query_uv, h->d_muv[0], bytes, cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaMemcpyAsync(train_uv, h->d_muv[1], bytes, cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
 // Parity read-out of the last vloam_vo_match_descriptors call: knn[batch][max_matches][4] = (trainIdx of the nearest, of the second
 // nearest, their Hamming distances) per query row, i.e. the knn_matches of image_util.cpp:263 before the ratio test.
 int vloam_vo_get_knn(vloam_vo* h, int* knn) {
