@@ -155,6 +155,8 @@ int vloam_input_consumed(vloam_lidar* h);
  * scans into the handle's own input slot first (a graph replays fixed addresses). */
 int vloam_lidar_process(vloam_lidar* h, const float* xyz, const int* n_points, int stride_floats, size_t slab_points,
                         const double* prior_dev, int use_graph);
+int vloam_lidar_process_ptrs(vloam_lidar* h, const float* const* xyz_ptrs, const int* n_points, int stride_floats, const double* prior_dev,
+                             int use_graph);
 int vloam_lidar_process_device(vloam_lidar* h, const float* xyz_dev, const int* n_points_dev, int stride_floats, size_t slab_points,
                                const double* prior_dev, int use_graph);
 

@@ -81,6 +81,7 @@ def lib():
             "vloam_scan_registration_ptrs": [vp, vp, vp, C.c_int],
             "vloam_lidar_process": [vp, vp, vp, C.c_int, C.c_size_t, vp, C.c_int],
             "vloam_lidar_process_device": [vp, vp, vp, C.c_int, C.c_size_t, vp, C.c_int],
+            "vloam_lidar_process_ptrs": [vp, vp, vp, C.c_int, vp, C.c_int],
             "vloam_get_input_device": [vp, pp, pp, c_ip, C.POINTER(C.c_size_t)], "vloam_input_consumed": [vp],
             "vloam_shard_buffer": [vp, pp, C.POINTER(C.c_size_t)], "vloam_shard_ipc_handle": [vp, C.c_char_p],
             "vloam_shard_open_ipc": [vp, C.c_int, C.c_int, C.c_char_p], "vloam_shard_enable": [vp, C.c_int, C.c_int, pp],
@@ -281,6 +282,13 @@ class LidarOdometryMapping:
         n_points = np.ascontiguousarray(n_points, np.int32)
         self._keep = (a, n_points)
         self.ctx.check(lib().vloam_lidar_process(self._h, _ptr(a), _ptr(n_points), shape[2], shape[1], _ptr(prior_dev), int(use_graph)))
+
+    def processPtrs(self, ptrs, n_points, stride: int, prior_dev=None, use_graph=True, keep=None):
+        """process() with one host buffer per stream (see scanRegistrationPtrs)."""
+        p = np.ascontiguousarray(ptrs, np.uint64)
+        n = np.ascontiguousarray(n_points, np.int32)
+        self._keep = (p, n, keep)
+        self.ctx.check(lib().vloam_lidar_process_ptrs(self._h, _ptr(p), _ptr(n), stride, _ptr(prior_dev), int(use_graph)))
 
     def processDevice(self, xyz_dev, n_points_dev, stride: int, slab_points: int, prior_dev=None, use_graph=True):
         self._keep = (xyz_dev, n_points_dev)

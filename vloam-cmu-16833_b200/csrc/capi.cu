@@ -921,6 +921,21 @@ int vloam_lidar_process(vloam_lidar* h, const float* xyz, const int* n_points, i
   return VLOAM_OK;
 }
 
+int vloam_lidar_process_ptrs(vloam_lidar* h, const float* const* xyz_ptrs, const int* n_points, int stride, const double* prior_dev, int use_graph) {
+  if (!h || !xyz_ptrs || !n_points || stride < 3 || stride > kMaxInputStride) return VLOAM_E_INVALID;
+  for (int b = 0; b < h->B; ++b) if (n_points[b] > 0 && !xyz_ptrs[b]) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  h->host_scans = h->frame + 1;
+  const int slot = (int)(h->host_scans & 1);
+  const int r = upload_only(h, [&](int b) { return xyz_ptrs[b]; }, nullptr, n_points, stride, (size_t)h->cap);
+  if (r) return r;
+  const int r2 = process_frame(h, slot, stride, h->p.detach_VO_LO ? nullptr : prior_dev, use_graph);
+  if (r2) return r2;
+  CU(c, cudaEventRecord(h->ev_in_free[slot], c->stream));
+  h->in_used[slot] = true; h->last_stride = stride; h->host_scans++;
+  return VLOAM_OK;
+}
+
 int vloam_lidar_process_device(vloam_lidar* h, const float* xyz_dev, const int* n_dev, int stride, size_t slab_points, const double* prior_dev,
                                int use_graph) {
   if (!h || !xyz_dev || !n_dev || stride < 3 || stride > kMaxInputStride || slab_points == 0) return VLOAM_E_INVALID;
