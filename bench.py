@@ -694,10 +694,14 @@ def run_ours(args, rank, world, local_rank):
         barrier()
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_.record(stream)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(stream)
         for r in range(reps):
             k = needed[r % len(needed)]
-            for b in range(B):
-                sink[b].copy_(host_base[b % N_BASE, slot_of[k]], non_blocking=True)
+            for b in range(B):      # two upload queues, like the library's copy streams
+                with torch.cuda.stream(side if b & 1 else stream):
+                    sink[b].copy_(host_base[b % N_BASE, slot_of[k]], non_blocking=True)
+        stream.wait_stream(side)
         b_.record(stream)
         barrier()
         h2d_ms = max(all_ranks(a_.elapsed_time(b_) / reps))

@@ -199,7 +199,9 @@ int vloam_ctx_create(int device, vloam_ctx** out) {
   if (!c) return VLOAM_E_NOMEM;
   c->device = device;
   if (cudaSetDevice(device) != cudaSuccess || cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess ||
-      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess) {
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->ev_copy2, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return VLOAM_E_CUDA;
   }
@@ -207,7 +209,7 @@ int vloam_ctx_create(int device, vloam_ctx** out) {
   // opt-in shared-memory sizes of the kernels, once per context on its device; a failure here would otherwise surface
   // later as an opaque launch error
   if (sr_prepare_device(device) != cudaSuccess || lo_prepare_device(device) != cudaSuccess) {
-    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream);
+    cudaStreamDestroy(c->own_stream); cudaStreamDestroy(c->copy_stream); cudaStreamDestroy(c->copy_stream2);
     delete c;
     return VLOAM_E_CUDA;
   }
@@ -219,6 +221,8 @@ int vloam_ctx_destroy(vloam_ctx* c) {
   cudaSetDevice(c->device);
   if (c->own_stream) cudaStreamDestroy(c->own_stream);
   if (c->copy_stream) cudaStreamDestroy(c->copy_stream);
+  if (c->copy_stream2) cudaStreamDestroy(c->copy_stream2);
+  if (c->ev_copy2) cudaEventDestroy(c->ev_copy2);
   delete c;
   return VLOAM_OK;
 }
@@ -545,10 +549,14 @@ static int upload_only(vloam_lidar* h, Src src, const float* contiguous, const i
       CU(c, cudaMemcpy2DAsync(h->d_in[slot], (size_t)h->cap * stride * sizeof(float), contiguous, slab_points * stride * sizeof(float), row,
                               (size_t)h->B, cudaMemcpyHostToDevice, c->copy_stream));
   } else {
+    // one copy per stream, alternating between two upload queues (the second one joins the first before the ready event)
+    if (h->in_used[slot]) CU(c, cudaStreamWaitEvent(c->copy_stream2, h->ev_in_free[slot], 0));
     for (int b = 0; b < h->B; ++b)
       if (n_points[b])
         CU(c, cudaMemcpyAsync(h->d_in[slot] + (size_t)b * h->cap * stride, src(b),
-                              (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+                              (size_t)n_points[b] * stride * sizeof(float), cudaMemcpyHostToDevice, (b & 1) ? c->copy_stream2 : c->copy_stream));
+    CU(c, cudaEventRecord(c->ev_copy2, c->copy_stream2));
+    CU(c, cudaStreamWaitEvent(c->copy_stream, c->ev_copy2, 0));
   }
   CU(c, cudaMemcpyAsync(h->d_n[slot], n_points, h->B * sizeof(int), cudaMemcpyHostToDevice, c->copy_stream));
   CU(c, cudaEventRecord(h->ev_in_ready[slot], c->copy_stream));
