@@ -114,6 +114,9 @@ typedef struct vloam_lidar_params {
   int solver_mode;                 /* how ceres::Solve is laid out on the GPU: 0 = by batch size, 1 = one CTA (or cluster) per stream,
                                       whole solve in one launch (small batches: fewest launches), 2 = wide: one launch over all
                                       residual blocks of all streams per Levenberg-Marquardt evaluation + a warp-per-stream step */
+  int distortion;                  /* laser_odometry.h:90 DISTORTION (a compile-time constant of the reference, false as shipped): 1 = every
+                                      feature is interpolated inside the sweep, s = frac(intensity) / 0.1, pose applied as
+                                      Identity.slerp(s, q_last_curr), s * t_last_curr (laser_odometry.cpp:149-167, lidarFactor.hpp:28-35) */
 } vloam_lidar_params;
 
 /* Fills the reference's KITTI HDL-64 launch-file values. */

@@ -159,6 +159,7 @@ void orc_lo_get_state(void* h, double* pose) {
   pose[14] = lo->corner_correspondence; pose[15] = lo->plane_correspondence;
   pose[16] = lo->frameCount; pose[17] = lo->systemInited;
 }
+void orc_lo_set_distortion(void* h, int on) { static_cast<LaserOdometry*>(h)->DISTORTION = on != 0; }
 void orc_lo_set_skip(void* h, int mapping_skip_frame) { static_cast<LaserOdometry*>(h)->mapping_skip_frame = mapping_skip_frame; }
 // checkpoint / resume hook mirrored by vloam_set_lo_pose: overwrite the accumulated odometry pose
 void orc_lo_set_pose(void* h, const double* q, const double* t) {

@@ -24,7 +24,7 @@ struct LOPassTrace {
 class LaserOdometry {
  public:
   // laser_odometry.h:90-95
-  static constexpr bool DISTORTION = false;
+  bool DISTORTION = false;   // laser_odometry.h:90 (a compile-time constant of the reference, false as shipped; a run-time switch here)
   static constexpr double SCAN_PERIOD = 0.1;
   static constexpr double DISTANCE_SQ_THRESHOLD = 25;
   static constexpr double NEARBY_SCAN = 2.5;
@@ -46,11 +46,21 @@ class LaserOdometry {
 
   void init() { *this = LaserOdometry(); }
 
-  // TransformToStart :149-167 with DISTORTION == false (s = 1)
+  // interpolation ratio of a point inside the sweep, :152-156 / :329-335 / :425-431
+  double ratio(const PointXYZI& pi) const {
+    if (DISTORTION) return (pi.intensity - int(pi.intensity)) / SCAN_PERIOD;   // float - int -> float, / double
+    return 1.0;
+  }
+  // TransformToStart :149-167
   void TransformToStart(const PointXYZI& pi, PointXYZI* po) const {
-    double s = 1.0;
-    // Identity().slerp(1, q_last_curr) == +-q_last_curr (same rotation); t_point_last = s * t
+    const double s = ratio(pi);
+    // q_point_last = Identity().slerp(s, q_last_curr) (Eigen::QuaternionBase::slerp, restated in lidar_factors.hpp); with
+    // s == 1 that is +-q_last_curr up to rounding — the shipped configuration, kept on its exact short path
     Quat q{para_q[0], para_q[1], para_q[2], para_q[3]};
+    if (DISTORTION) {
+      const Q4<double> qs = slerp_from_identity(s, Q4<double>{para_q[3], para_q[0], para_q[1], para_q[2]});
+      q = Quat{qs.x, qs.y, qs.z, qs.w};
+    }
     Vec3 point{pi.x, pi.y, pi.z};
     Vec3 un_point = rotate(q, point) + s * Vec3{para_t[0], para_t[1], para_t[2]};
     po->x = static_cast<float>(un_point.x);
@@ -116,7 +126,7 @@ class LaserOdometry {
                               laserCloudCornerLast[closestPointInd].z};
             f.last_point_b = {laserCloudCornerLast[minPointInd2].x, laserCloudCornerLast[minPointInd2].y,
                               laserCloudCornerLast[minPointInd2].z};
-            f.s = 1.0;
+            f.s = ratio(cornerPointsSharp[i]);   // :329-335
             owned.push_back(new AutoDiffBlock43<LidarEdgeFunctor, 3>(f));
             tr.corner.push_back(i); tr.corner.push_back(closestPointInd); tr.corner.push_back(minPointInd2);
             corner_correspondence++;
@@ -158,7 +168,7 @@ class LaserOdometry {
                      laserCloudSurfLast[minPointInd2].z};
               Vec3 cc{laserCloudSurfLast[minPointInd3].x, laserCloudSurfLast[minPointInd3].y,
                       laserCloudSurfLast[minPointInd3].z};
-              owned.push_back(new AutoDiffBlock43<LidarPlaneFunctor, 1>(LidarPlaneFunctor(c, a, b, cc, 1.0)));
+              owned.push_back(new AutoDiffBlock43<LidarPlaneFunctor, 1>(LidarPlaneFunctor(c, a, b, cc, ratio(surfPointsFlat[i]))));
               tr.plane.push_back(i); tr.plane.push_back(closestPointInd);
               tr.plane.push_back(minPointInd2); tr.plane.push_back(minPointInd3);
               plane_correspondence++;

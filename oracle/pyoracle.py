@@ -56,6 +56,7 @@ def lib():
             "orc_lo_set_motion": (None, [vp, c_dp, c_dp]),
             "orc_lo_set_pose": (None, [vp, c_dp, c_dp]),
             "orc_lo_set_skip": (None, [vp, C.c_int]),
+            "orc_lo_set_distortion": (None, [vp, C.c_int]),
             "orc_lm_published_pose": (None, [vp, c_dp]),
             "orc_lo_trace_passes": (C.c_int, [vp]),
             "orc_lo_trace_sizes": (None, [vp, C.c_int, c_ip]),
@@ -279,6 +280,10 @@ class LaserOdometry:
         q = np.ascontiguousarray(q, np.float64)
         t = np.ascontiguousarray(t, np.float64)
         lib().orc_lo_set_pose(self._h, _dp(q), _dp(t))
+
+    def set_distortion(self, on=True):
+        """laser_odometry.h:90 DISTORTION (a compile-time constant of the reference, false as shipped)."""
+        lib().orc_lo_set_distortion(self._h, int(on))
 
     def set_mapping_skip_frame(self, n):
         lib().orc_lo_set_skip(self._h, int(n))

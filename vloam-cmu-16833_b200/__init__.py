@@ -45,7 +45,7 @@ class LidarParams(C.Structure):
                 ("mapping_line_resolution", C.c_double), ("mapping_plane_resolution", C.c_double),
                 ("mapping_skip_frame", C.c_int), ("detach_VO_LO", C.c_int), ("lo_outer_passes", C.c_int),
                 ("lo_max_iterations", C.c_int), ("lm_outer_passes", C.c_int), ("lm_max_iterations", C.c_int),
-                ("map_capacity_points", C.c_int), ("debug_keep_submap", C.c_int), ("solver_mode", C.c_int)]
+                ("map_capacity_points", C.c_int), ("debug_keep_submap", C.c_int), ("solver_mode", C.c_int), ("distortion", C.c_int)]
 
 
 def build(verbose: bool = False) -> str:

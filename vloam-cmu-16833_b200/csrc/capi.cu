@@ -274,6 +274,7 @@ int vloam_lidar_params_default(vloam_lidar_params* p) {
   p->map_capacity_points = 1 << 21;
   p->debug_keep_submap = 0;
   p->solver_mode = 0;
+  p->distortion = 0;                   // laser_odometry.h:90
   return VLOAM_OK;
 }
 
@@ -733,7 +734,7 @@ static int run_laser_odometry(vloam_lidar* h, const double* prior_dev) {
     for (int pass = 0; pass < passes; ++pass) {
       launch_lo_pass(&c->prof, c->stream, h->B, h->cap, h->d_hdr[cur], h->d_hdr[last], h->d_lo, h->d_sharp, h->d_flat,
                      h->d_lessSharp[last], h->d_lessFlat[last], &h->grid, h->d_corr[pass < 2 ? pass : 1], pass < 2 ? pass : 1,
-                     h->p.lo_max_iterations, pass == passes - 1, prior, h->shard.world > 1 ? &h->shard : nullptr, h->p.solver_mode);   // (with an NCCL communicator
+                     h->p.lo_max_iterations, pass == passes - 1, prior, h->shard.world > 1 ? &h->shard : nullptr, h->p.solver_mode, h->p.distortion != 0);   // (with an NCCL communicator
                                                                                        // the pass takes the wide solve and sums there)
     }
   }

@@ -1,6 +1,8 @@
 // vloam_b200 — wide Gauss-Newton / Levenberg-Marquardt solve (see gn_split.cuh).
 #include "gn_split.cuh"
 
+#include "gn_jet.cuh"
+
 #include "internal.h"
 
 namespace vb {
@@ -19,6 +21,7 @@ __global__ void gn_begin(const GNProblemView pv, GNState* __restrict__ gs, int B
 // gn_accumulate: grid (kGnTiles, B), block 256.  One evaluation of (J'J, J'r, cost) at evalX over every residual block of
 // the stream: analytic Jacobians per block, warp-shuffle + block reduction to 28 doubles per tile.  The summation order
 // is fixed (thread-strided, warp tree, warp order, then tile order in gn_step): results are reproducible run to run.
+template <bool SLERP>   // SLERP: the records may carry a motion-distortion ratio (types 3 / 4); a separate instance keeps the registers of the shipped one low
 __global__ void __launch_bounds__(kGnThreads) gn_accumulate(const GNProblemView pv, const GNState* __restrict__ gs, double* __restrict__ partial) {
   __shared__ double s_red[28];
   __shared__ double s_scratch[32 * 28];
@@ -40,12 +43,14 @@ __global__ void __launch_bounds__(kGnThreads) gn_accumulate(const GNProblemView 
       const int type = R.type;
       if (type == 0) continue;
       const float4 p = make_float4(R.px, R.py, R.pz, 0.f);
-      if (type == 1) {
+      // type 1 / 2: the shipped configuration (interpolation ratio s == 1, closed-form Jacobians); 3 / 4: the same blocks with
+      // a per-point ratio (DISTORTION == true) through Eigen's slerp, by dual numbers
+      if (type == 1 || type == 3) {
         const double pa[3] = {R.v[0], R.v[1], R.v[2]}, pb[3] = {R.v[3], R.v[4], R.v[5]};
-        edge_block(q, t, p, pa, pb, acc);
+        if (!SLERP || type == 1) edge_block(q, t, p, pa, pb, acc); else edge_block_slerp(q, t, p, pa, pb, R.v[6], acc);
       } else {
         const double nn[3] = {R.v[0], R.v[1], R.v[2]};
-        plane_block(q, t, p, nn, R.v[3], acc);
+        if (!SLERP || type == 2) plane_block(q, t, p, nn, R.v[3], acc); else plane_block_slerp(q, t, p, nn, R.v[3], R.v[4], acc);
       }
     }
   }
@@ -100,7 +105,8 @@ void launch_gn_solve(Profiler* prof, cudaStream_t st, int B, const GNProblemView
   // evaluation 0 at x0, then one evaluation per LM iteration: a stream that is done (converged, failed or out of
   // iterations) is skipped by both kernels, so the late launches cost a few microseconds each
   for (int phase = 0; phase <= max_iterations; ++phase) {
-    VB_LAUNCH(prof, kidAccumulate, st, gn_accumulate<<<dim3(kGnTiles, B), kGnThreads, 0, st>>>(pv, gs, partial));
+    if (pv.slerp) VB_LAUNCH(prof, kidAccumulate, st, gn_accumulate<true><<<dim3(kGnTiles, B), kGnThreads, 0, st>>>(pv, gs, partial));
+    else VB_LAUNCH(prof, kidAccumulate, st, gn_accumulate<false><<<dim3(kGnTiles, B), kGnThreads, 0, st>>>(pv, gs, partial));
     if (ncclComm) gn_allreduce_partials(ncclComm, partial, (size_t)B * kGnTiles * 28, st);
     VB_LAUNCH(prof, kidStep, st, gn_step<<<(B + 3) / 4, 128, 0, st>>>(pv, gs, partial, B, phase, max_iterations));
   }

@@ -17,7 +17,8 @@ struct Profiler;
 struct GNResidual {
   double v[7];   // edge: a(3), b(3); plane: n(3), d0
   float px, py, pz;
-  int type;      // 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneFactor / LidarPlaneNormFactor: r = n . (q p + t) + d0)
+  int type;      // 0 none, 1 edge (LidarEdgeFactor), 2 plane (LidarPlaneFactor / LidarPlaneNormFactor: r = n . (q p + t) + d0);
+                 // 3 / 4: edge / plane with the motion-distortion ratio s in v[6] / v[4] (laser_odometry.h:90 DISTORTION)
 };
 
 constexpr int kGnTiles = 8;          // CTAs per stream of gn_accumulate
@@ -45,6 +46,7 @@ struct GNProblemView {
   Strided active;                    // int flag (nullptr: always active)
   Strided x;                         // double[7]: the parameters (read at the start, written back at the end)
   Strided trace;                     // SolveTrace
+  int slerp;                         // the records may be of type 3 / 4 (motion-distortion ratio)
 };
 
 void launch_gn_solve(Profiler* prof, cudaStream_t st, int B, const GNProblemView& pv, GNState* gs, double* partial /*[B][kGnTiles][28]*/,

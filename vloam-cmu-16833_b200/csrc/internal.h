@@ -76,7 +76,7 @@ struct LOGrid {
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* grid, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
-                    const ShardView* shard = nullptr, int solverMode = 0);
+                    const ShardView* shard = nullptr, int solverMode = 0, bool distortion = false);
 // kd-tree rebuild of laser_odometry.cpp:525-526: index the current scan's less-sharp / less-flat clouds.
 void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const float4* lessSharp,
                           const float4* lessFlat, const LOGrid* grid);

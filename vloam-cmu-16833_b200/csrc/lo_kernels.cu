@@ -28,6 +28,17 @@ __device__ __forceinline__ int decode_order(unsigned long long k, int nT) {
   return (o & 0x80000000u) ? nT - (int)(o & 0x7fffffffu) : (int)o;
 }
 
+// Eigen::Quaterniond::Identity().slerp(s, q) (laser_odometry.cpp:159), q and the result as (x, y, z, w).
+__device__ __forceinline__ void slerp_from_identity(double s, const double q[4], double out[4]) {
+  const double one = 1.0 - 2.220446049250313e-16;
+  const double d = q[3], absD = fabs(d);
+  double scale0, scale1;
+  if (absD >= one) { scale0 = 1.0 - s; scale1 = s; }
+  else { const double theta = acos(absD), sinTheta = sin(theta); scale0 = sin((1.0 - s) * theta) / sinTheta; scale1 = sin(s * theta) / sinTheta; }
+  if (d < 0.0) scale1 = -scale1;
+  out[0] = scale1 * q[0]; out[1] = scale1 * q[1]; out[2] = scale1 * q[2]; out[3] = scale0 + scale1 * q[3];
+}
+
 // The reference walks the ring-major target cloud away from `closest` in both directions, classifying every point
 // by int(intensity) and stopping at the first point more than NEARBY_SCAN = 2.5 rings away (laser_odometry.cpp:
 // 279-324 / 368-417).  Literal restatement, 32 points per step: a later candidate replaces the incumbent only if
@@ -375,7 +386,7 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
                                                      const float4* __restrict__ surfLast, int cap,
                                                      const GridHeader* __restrict__ ghdr, const int* __restrict__ cellStartAll,
                                                      const float4* __restrict__ sortedC, const float4* __restrict__ sortedS,
-                                                     int4* __restrict__ corr, int shardRank, int shardWorld) {
+                                                     int4* __restrict__ corr, int shardRank, int shardWorld, int distortion) {
   const int b = blockIdx.y;
   const int lane = lane_id(), g = lane / kGroup, gl = lane % kGroup, gshift = g * kGroup;
   const unsigned gmask = 0xffu << gshift;
@@ -402,12 +413,20 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
     GridView G;
     G.minx = GH.minx; G.miny = GH.miny; G.c = GH.c; G.inv_c = GH.inv_c; G.nx = GH.nx; G.ny = GH.ny;
     const float4 p = isCorner ? sharp[(size_t)b * kMaxSharp + qi] : flat[(size_t)b * kMaxFlat + qi];
-    // TransformToStart, DISTORTION == false: un = q_last_curr * p + t_last_curr, rounded to float (:158-165)
+    // TransformToStart (:149-167): un = Identity.slerp(s, q_last_curr) * p + s * t_last_curr, rounded to float; s == 1 (the
+    // shipped DISTORTION == false) keeps its exact short path
     double un[3];
-    quat_rotate(lo[b].para_q, (double)p.x, (double)p.y, (double)p.z, un);
-    const float sx = (float)(un[0] + lo[b].para_t[0]);
-    const float sy = (float)(un[1] + lo[b].para_t[1]);
-    const float sz = (float)(un[2] + lo[b].para_t[2]);
+    float sx, sy, sz;
+    if (distortion) {
+      const double s = (double)__fsub_rn(p.w, (float)(int)p.w) / 0.1;
+      double qs[4];
+      slerp_from_identity(s, lo[b].para_q, qs);
+      quat_rotate(qs, (double)p.x, (double)p.y, (double)p.z, un);
+      sx = (float)(un[0] + s * lo[b].para_t[0]); sy = (float)(un[1] + s * lo[b].para_t[1]); sz = (float)(un[2] + s * lo[b].para_t[2]);
+    } else {
+      quat_rotate(lo[b].para_q, (double)p.x, (double)p.y, (double)p.z, un);
+      sx = (float)(un[0] + lo[b].para_t[0]); sy = (float)(un[1] + lo[b].para_t[1]); sz = (float)(un[2] + lo[b].para_t[2]);
+    }
     const float4* T = isCorner ? cornerLast + (size_t)b * kMaxLessSharp : surfLast + (size_t)b * cap;
     const float4* S = isCorner ? sortedC + (size_t)b * kMaxLessSharp : sortedS + (size_t)b * cap;
     const int* cs = cellStartAll + (size_t)(b * 2 + which) * (kGridCap + 1);
@@ -568,8 +587,8 @@ __device__ __forceinline__ void lo_associate_body(const SRHeader* __restrict__ h
       const float4 *__restrict__ sharp, const float4 *__restrict__ flat, const float4 *__restrict__ cornerLast,                  \
       const float4 *__restrict__ surfLast, int cap, const GridHeader *__restrict__ ghdr, const int *__restrict__ cellStartAll,   \
       const float4 *__restrict__ sortedC, const float4 *__restrict__ sortedS, int4 *__restrict__ corr, int shardRank,          \
-      int shardWorld
-#define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr, shardRank, shardWorld
+      int shardWorld, int distortion
+#define VB_LO_ASSOC_PASS hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, ghdr, cellStartAll, sortedC, sortedS, corr, shardRank, shardWorld, distortion
 // Two register budgets of the same body: 64 registers (4 CTAs / SM) and <= 40 (6 CTAs / SM); the kernel is latency
 // bound, so which one wins is an occupancy question settled by measurement (VLOAM_LO_ASSOC_OCC=4|5|6|8; measured on B200 at 128 streams: 334 / 314 / 293 us for 4 / 5 / 6, so 6 is the default).
 __global__ void __launch_bounds__(256, 4) lo_associate(VB_LO_ASSOC_ARGS) { lo_associate_body<4>(VB_LO_ASSOC_PASS); }
@@ -705,7 +724,7 @@ __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __rest
                                                            const float4* __restrict__ sharp, const float4* __restrict__ flat,
                                                            const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
                                                            int cap, const int4* __restrict__ corr, int pass, GNResidual* __restrict__ recAll,
-                                                           double* __restrict__ counts /*[B][2] or nullptr*/) {
+                                                           double* __restrict__ counts /*[B][2] or nullptr*/, int distortion) {
   constexpr int kSlots = kMaxSharp + kMaxFlat;
   const int b = blockIdx.x;
   LOState& st = lo[b];
@@ -732,10 +751,11 @@ __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __rest
       if (c.w) {
         const float4 p = isCorner ? sh[qi] : fl[qi];
         R.px = p.x; R.py = p.y; R.pz = p.z;
+        const double s = distortion ? (double)__fsub_rn(p.w, (float)(int)p.w) / 0.1 : 1.0;    // :329-335 / :425-431
         if (isCorner) {
           const float4 A = CL[c.x], Bp = CL[c.y];
           R.v[0] = A.x; R.v[1] = A.y; R.v[2] = A.z; R.v[3] = Bp.x; R.v[4] = Bp.y; R.v[5] = Bp.z;
-          R.type = 1; nc++;
+          R.v[6] = s; R.type = distortion ? 3 : 1; nc++;
         } else {
           const float4 Jp = SL[c.x], Lp = SL[c.y], Mp = SL[c.z];
           // ljm_norm = normalize((j - l) x (j - m))  (lidarFactor.hpp:68-69)
@@ -746,7 +766,7 @@ __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __rest
           if (z2 > 0.0) { const double nn = sqrt(z2); n[0] /= nn; n[1] /= nn; n[2] /= nn; }
           R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2];
           R.v[3] = -(n[0] * (double)Jp.x + n[1] * (double)Jp.y + n[2] * (double)Jp.z);
-          R.type = 2; np++;
+          R.v[4] = s; R.type = distortion ? 4 : 2; np++;
         }
       }
     }
@@ -861,10 +881,10 @@ void launch_lo_build_grid(Profiler* prof, cudaStream_t st, int B, int cap, const
 void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHeader* hdrCur, const SRHeader* hdrLast, LOState* lo,
                     const float4* sharp, const float4* flat, const float4* cornerLast, const float4* surfLast,
                     const LOGrid* g, int4* corr, int pass, int max_iterations, int integrate, const double* prior,
-                    const ShardView* shard, int solverMode) {
+                    const ShardView* shard, int solverMode, bool distortion) {
   const ShardView sv = shard ? *shard : ShardView();
   if (prior) VB_LAUNCH(prof, K_LO_SET_MOTION, st, lo_set_motion<<<(B + 127) / 128, 128, 0, st>>>(lo, prior, B));
-  if (lo_use_brute() && sv.world <= 1)
+  if (lo_use_brute() && sv.world <= 1 && !distortion)
     VB_LAUNCH(prof, K_LO_ASSOCIATE_BRUTE, st, lo_associate_brute<<<dim3((kMaxSharp + kMaxFlat + 7) / 8, B), 256, 0, st>>>(
                                                   hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, corr));
   else
@@ -874,32 +894,34 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
     if (occ >= 8)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ8<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world, distortion ? 1 : 0));
     else if (occ >= 6)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ6<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world, distortion ? 1 : 0));
     else if (occ == 5)
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate_occ5<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world, distortion ? 1 : 0));
     else
       VB_LAUNCH(prof, K_LO_ASSOCIATE, st, lo_associate<<<grid, 256, 0, st>>>(
                                               hdrCur, hdrLast, lo, sharp, flat, cornerLast, surfLast, cap, g->hdr, g->cellStart,
-                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world));
+                                              g->sorted[0], g->sorted[1], corr, sv.rank, sv.world, distortion ? 1 : 0));
   }
   // vloam_lidar_params::solver_mode (0 = by batch size); the NCCL exchange needs the wide layout, the in-kernel peer exchange the narrow one
-  const bool split = g->gnState != nullptr && (g->ncclComm != nullptr || (sv.world <= 1 && (solverMode == 2 || (solverMode == 0 && B >= kLoSplitMinBatch))));
+  // (the motion-distortion blocks exist in the wide layout only)
+  const bool split = g->gnState != nullptr && (g->ncclComm != nullptr || distortion || (sv.world <= 1 && (solverMode == 2 || (solverMode == 0 && B >= kLoSplitMinBatch))));
   if (split) {
     // wide solve (gn_split.cuh): residual records once per pass, then one launch over all streams per LM evaluation
     double* counts = g->ncclComm ? g->gnCounts : nullptr;
-    VB_LAUNCH(prof, K_LO_STEP, st, lo_stage_residuals<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, g->gnRec, counts));
+    VB_LAUNCH(prof, K_LO_STEP, st, lo_stage_residuals<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, g->gnRec, counts, distortion ? 1 : 0));
     if (counts) gn_allreduce_partials(g->ncclComm, counts, (size_t)B * 2, st);
     GNProblemView pv{};
     pv.rec[0] = g->gnRec; pv.rec[1] = nullptr;
     pv.recStride[0] = kMaxSharp + kMaxFlat; pv.fixedCount[0] = kMaxSharp + kMaxFlat;
     pv.x = Strided{&lo[0].para_q[0], sizeof(LOState)};
     pv.trace = Strided{&lo[0].trace[pass], sizeof(LOState)};
+    pv.slerp = distortion ? 1 : 0;
     launch_gn_solve(prof, st, B, pv, g->gnState, g->gnPartial, max_iterations, K_LO_ACCUMULATE, K_LO_STEP, g->ncclComm);
     VB_LAUNCH(prof, K_LO_STEP, st, lo_gn_finish<<<(B + 127) / 128, 128, 0, st>>>(lo, B, pass, integrate, counts));
     return;
