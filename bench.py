@@ -381,7 +381,8 @@ def run_ours(args, rank, world, local_rank):
     do_vo = args.workload == "vloam"
     do_map = args.workload in ("sr_lo_lm", "vloam")
     cap = N_RINGS * N_COLS
-    point = args.parallelism == "point" and world > 1
+    point = args.parallelism in ("point", "point-peer") and world > 1
+    point_nccl = args.parallelism == "point"
     n_total = args.warmup + 2 * args.steps + 2           # timed leg + per-kernel timing pass + statistics pass
     needed = sorted({scan_index(i) for i in range(n_total)})
     # point-sharded: every rank replays the SAME streams (rank-independent seeds) and owns a slice of their correspondences
@@ -550,8 +551,19 @@ def run_ours(args, rank, world, local_rank):
         with torch.cuda.stream(streams[h]):
             groups.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
     loms = [g.lom for g in groups]
+    def enable_sharding(lom_):
+        if point_nccl:
+            D.enable_point_sharding_nccl(lom_, dist, dev)
+        else:
+            D.enable_point_sharding(lom_, dist, dev)
+
+    def disable_sharding(lom_):
+        if point_nccl:
+            lom_.shard_nccl_destroy()
+        else:
+            lom_.shard_disable()
     if point:
-        D.enable_point_sharding(groups[0].lom, dist, dev)
+        enable_sharding(groups[0].lom)
 
     def step_dev(i, serial=False):
         for h in range(H):
@@ -636,7 +648,7 @@ def run_ours(args, rank, world, local_rank):
     map_stats_all = np.concatenate([hd.map_stats() for hd in loms]).astype(np.int64) if do_map else None
     lm_tr = loms[0].lm_trace(1, 0) if do_map else None
     if point:
-        groups[0].lom.shard_disable()
+        disable_sharding(groups[0].lom)
     for g in groups:
         g.close()               # fresh handles for the e2e leg (same inputs, same number of steps -> same final poses)
 
@@ -649,7 +661,7 @@ def run_ours(args, rank, world, local_rank):
             groups2.append(Group(ctxs[h], bounds[h], bounds[h + 1]))
     g2 = groups2[0]
     if point:
-        D.enable_point_sharding(g2.lom, dist, dev)
+        enable_sharding(g2.lom)
 
     def step_host(i, first):
         for h in range(H):
@@ -682,7 +694,7 @@ def run_ours(args, rank, world, local_rank):
     e2e_value = (1 if point else world) * B * args.steps / (ms_e2e * 1e-3)
     h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
     d2h = int(B * 16 * 8)
-    shard_err = g2.lom.shard_status() if point else 0
+    shard_err = g2.lom.shard_status() if (point and not point_nccl) else 0
     # same inputs, same number of steps -> both legs must end on identical poses
     same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
 
@@ -841,8 +853,11 @@ def run_ours(args, rank, world, local_rank):
         "data": f"synthetic ({N_BASE} seeded base sequences x {TRAJ_SCANS}-scan forward trajectories tiled across the batch; generated in {t_gen:.1f} s)",
         "config": config_dict(args, B, args.handles, world, do_map, {
             "l2_policy": f"inputs larger than L2: a different [{B}, {cap}, 3] slab of the {pool_bytes/1e9:.1f} GB scan pool every step",
-            "parallelism": (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
-                            f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}") if point
+            "parallelism": ((f"point-sharded x{world}: replicated scans, queries split across ranks, partial normal equations (28 doubles per "
+                             f"tile, {8 * 28 * 8} bytes per stream and evaluation) all-reduced by NCCL between the accumulate and step launches of "
+                             f"laser odometry and laser mapping") if point_nccl else
+                            (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
+                             f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}")) if point
                            else f"stream-sharded x{world} (no data-path collective)"}),
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same,
@@ -893,9 +908,11 @@ def main():
     ap.add_argument("--handles", type=int, default=0,
                     help="split the batch over this many handles / CUDA streams (device leg); default: 64 streams per handle for "
                          "sr_lo_lm (3 handles), 2 handles otherwise")
-    ap.add_argument("--parallelism", default="stream", choices=["stream", "point"],
-                    help="N > 1: stream = independent streams per rank (weak scaling, headline); point = every rank holds all "
-                         "streams and a slice of each stream's correspondences, normal equations summed in-kernel over NVLink")
+    ap.add_argument("--parallelism", default="stream", choices=["stream", "point", "point-peer"],
+                    help="N > 1: stream = independent streams per rank (weak scaling, headline); point = BASELINE configs[4] as worded: "
+                         "every rank holds all streams and a slice of each stream's queries, the partial normal equations of every "
+                         "Levenberg-Marquardt evaluation (odometry and mapping) are summed by ncclAllReduce; point-peer = the same "
+                         "split for laser odometry with the sum formed inside the solve kernel through NVLink peer memory")
     ap.add_argument("--solver-mode", type=int, default=0, choices=[0, 1, 2],
                     help="vloam_lidar_params::solver_mode: 0 = by batch size, 1 = one CTA (cluster) per stream, 2 = wide accumulate + step launches")
     ap.add_argument("--graphs", type=int, default=0, choices=[0, 1],

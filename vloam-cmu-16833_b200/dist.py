@@ -86,3 +86,18 @@ def enable_point_sharding(lom, dist, device=None):
     handles = gather_ipc_handles(lom.shard_ipc_handle(), dist, device)
     lom.shard_open_ipc(rank, world, handles)
     dist.barrier()          # nobody starts exchanging before every rank has mapped and cleared its slots
+
+
+def enable_point_sharding_nccl(lom, dist, device=None):
+    """The same split with the exchange done by ncclAllReduce between a wide accumulate launch and the step launch
+    (BASELINE configs[4] as worded; include/vloam_b200.h vloam_shard_nccl_*).  Rank 0 creates the ncclUniqueId, everybody
+    receives it through the job's process group, then the library builds its own communicator (collective)."""
+    import torch
+    from . import shard_nccl_unique_id
+    rank, world = dist.get_rank(), dist.get_world_size()
+    t = torch.zeros(128, dtype=torch.uint8, device=device)
+    if rank == 0:
+        t.copy_(torch.tensor(list(shard_nccl_unique_id()), dtype=torch.uint8))
+    dist.broadcast(t, src=0)
+    lom.shard_nccl_init(rank, world, bytes(t.cpu().numpy().tobytes()))
+    dist.barrier()
