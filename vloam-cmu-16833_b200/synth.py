@@ -243,24 +243,27 @@ def make_scans(seed: int, n_scans: int, n_cols: int = N_COLS) -> tuple[list[np.n
 
 
 # ------------------------------------------------------------------------------------------------ pre-built map (BASELINE configs[2])
-def map_cubes(n_points: int, seed: int):
+def map_cubes(n_points: int, seed: int, x_range=(-100.0, 250.0), y_half=124.0):
     """A synthetic pre-built map for configs[2]: n_points surf points (one per 0.8 m voxel —
     the map's own resolution — jittered inside the voxel, on the ground plane and on stacked horizontal layers, so the
-    map keeps its size under the reference's per-scan re-filter) plus 10 % as many corner points (vertical poles), inside
-    the 5 x 5 x 3 cube window around the origin.  Returns {(kind, cube_index): (n, 4) float32}."""
+    map keeps its size under the reference's per-scan re-filter) plus 10 % as many corner points (vertical poles).  The map
+    is a corridor along +x, the direction the synthetic vehicles drive: it fills the 5 x 5 x 3 cube window around the origin
+    and reaches 125 m beyond it, so that the cubes entering the window when a vehicle crosses a cube border hold map points
+    (they have to be indexed on entry).  Returns {(kind, cube_index): (n, 4) float32}."""
     rng = np.random.default_rng(seed)
-    k = np.arange(-155, 155)
-    per_layer = k.size * k.size
+    kx = np.arange(int(np.floor(x_range[0] / 0.8)), int(np.ceil(x_range[1] / 0.8)))
+    ky = np.arange(-int(y_half / 0.8), int(y_half / 0.8))
+    per_layer = kx.size * ky.size
     layers = max(1, int(np.ceil(n_points / per_layer)))
     pts = []
     for l in range(layers):
-        gx, gy = np.meshgrid((k + 0.5) * 0.8, (k + 0.5) * 0.8)
+        gx, gy = np.meshgrid((kx + 0.5) * 0.8, (ky + 0.5) * 0.8)
         z = -1.73 + 7.0 * l
         p = np.c_[gx.ravel(), gy.ravel(), np.full(gx.size, z)] + rng.uniform(-0.3, 0.3, (gx.size, 3)) * [1, 1, 0.02]
         pts.append(p)
     surf = np.concatenate(pts)[:n_points].astype(np.float32)
     ncor = max(1000, n_points // 10)
-    cx, cy = rng.uniform(-120, 120, ncor // 20), rng.uniform(-120, 120, ncor // 20)
+    cx, cy = rng.uniform(x_range[0] + 4.0, x_range[1] - 4.0, ncor // 20), rng.uniform(-y_half + 4.0, y_half - 4.0, ncor // 20)
     corner = np.c_[np.repeat(cx, 20), np.repeat(cy, 20), np.tile(np.arange(20) * 0.4 - 1.7, ncor // 20)].astype(np.float32)
     out = {}
     for kind, cloud in ((0, corner), (1, surf)):
