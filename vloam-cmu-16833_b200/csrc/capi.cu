@@ -764,7 +764,7 @@ static int read_pose(vloam_lidar* h, int par, double* pose_out, int* corr_out) {
   if (!h->pose_valid[par]) return fail(c, VLOAM_E_STATE, "no laser odometry result for that frame yet");
   CU(c, cudaSetDevice(c->device));
   CU(c, cudaEventSynchronize(h->ev_pose[par]));  // waits for that frame's read-back only, not for the whole stream
-  if (h->shard.world > 1) {   // point-sharded: a peer that did not answer inside the solve kernel makes the result invalid
+  if (h->shard.world > 1 && h->shard.error != nullptr && h->nccl == nullptr) {   // peer-memory exchange: a peer that did not answer inside the solve kernel makes the result invalid
     int bits = 0;
     CU(c, cudaMemcpy(&bits, h->shard.error, sizeof(int), cudaMemcpyDeviceToHost));
     if (bits) return fail(c, VLOAM_E_STATE, "point-sharded solve: a peer rank did not publish its normal equations in time (vloam_shard_status)");
