@@ -294,7 +294,7 @@ int vloam_lidar_destroy(vloam_lidar* h) {
   cudaFree(h->d_lessFlatStage); cudaFree(h->d_sharp); cudaFree(h->d_sharpIdx); cudaFree(h->d_lessSharpIdx);
   cudaFree(h->d_flat); cudaFree(h->d_flatIdx); cudaFree(h->d_lo); cudaFree(h->d_prior); cudaFree(h->d_pose);
   cudaFree(h->grid.hdr); cudaFree(h->grid.cellStart); cudaFree(h->grid.cursor);
-  cudaFree(h->grid.gnRec); cudaFree(h->grid.gnState); cudaFree(h->grid.gnPartial); cudaFree(h->grid.gnCounts);
+  cudaFree(h->grid.gnRecV); cudaFree(h->grid.gnRecP); cudaFree(h->grid.gnState); cudaFree(h->grid.gnPartial); cudaFree(h->grid.gnCounts);
   for (int i = 0; i < 2; ++i) { cudaFree(h->grid.sorted[i]); }
   for (int a = 0; a < 2; ++a) for (int b = 0; b < 2; ++b) for (int k = 0; k < 2; ++k) if (h->graph[a][b][k]) cudaGraphExecDestroy(h->graph[a][b][k]);
   if (h->nccl) { if (NcclApi* api = nccl_api()) api->CommDestroy(h->nccl); h->nccl = nullptr; }
@@ -473,7 +473,7 @@ int vloam_lidar_create(vloam_ctx* c, const vloam_lidar_params* p, vloam_lidar** 
   A(dalloc(&h->grid.hdr, B * 2)); A(dalloc(&h->grid.cellStart, B * 2 * (kGridCap + 1))); A(dalloc(&h->grid.cursor, B * 2 * (kGridCap + 1)));
   A(dalloc(&h->grid.sorted[0], B * kMaxLessSharp));
   A(dalloc(&h->grid.sorted[1], B * cap));
-  A(dalloc(&h->grid.gnRec, B * (kMaxSharp + kMaxFlat))); A(dalloc(&h->grid.gnState, B)); A(dalloc(&h->grid.gnPartial, B * kGnTiles * 28));
+  A(dalloc(&h->grid.gnRecV, B * 7 * (kMaxSharp + kMaxFlat))); A(dalloc(&h->grid.gnRecP, B * (kMaxSharp + kMaxFlat))); A(dalloc(&h->grid.gnState, B)); A(dalloc(&h->grid.gnPartial, B * kGnTiles * 28));
   A(dalloc(&h->grid.gnCounts, B * 2));
   if (e != cudaSuccess) { vloam_lidar_destroy(h); return fail(c, e == cudaErrorMemoryAllocation ? VLOAM_E_NOMEM : VLOAM_E_CUDA, "vloam_lidar_create: allocation", e); }
   launch_lo_init(&c->prof, c->stream, h->d_lo, h->B);

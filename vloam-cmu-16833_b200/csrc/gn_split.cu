@@ -33,24 +33,24 @@ __global__ void __launch_bounds__(kGnThreads) gn_accumulate(const GNProblemView 
   for (int k = 0; k < 28; ++k) acc[k] = 0.0;
   const double q[4] = {G.evalX[0], G.evalX[1], G.evalX[2], G.evalX[3]};
   const double t[3] = {G.evalX[4], G.evalX[5], G.evalX[6]};
-#pragma unroll
-  for (int a = 0; a < 2; ++a) {
-    if (pv.rec[a] == nullptr) continue;
+  for (int a = 0; a < pv.blocksPerStream; ++a) {
     const int n = pv.count[a].base ? *pv.count[a].at<int>(b) : pv.fixedCount[a];
-    const GNResidual* rc = pv.rec[a] + (size_t)b * pv.recStride[a];
+    const size_t block = (size_t)b * pv.blocksPerStream + a;
+    const float4* P = pv.rec.p + block * (size_t)pv.rec.n;
+    const double* V = pv.rec.v + block * 7 * (size_t)pv.rec.n;
+    const size_t pl = (size_t)pv.rec.n;
     for (int i = blockIdx.x * kGnThreads + threadIdx.x; i < n; i += kGnTiles * kGnThreads) {
-      const GNResidual& R = rc[i];
-      const int type = R.type;
+      const float4 p = P[i];
+      const int type = gn_type(p);
       if (type == 0) continue;
-      const float4 p = make_float4(R.px, R.py, R.pz, 0.f);
       // type 1 / 2: the shipped configuration (interpolation ratio s == 1, closed-form Jacobians); 3 / 4: the same blocks with
       // a per-point ratio (DISTORTION == true) through Eigen's slerp, by dual numbers
       if (type == 1 || type == 3) {
-        const double pa[3] = {R.v[0], R.v[1], R.v[2]}, pb[3] = {R.v[3], R.v[4], R.v[5]};
-        if (!SLERP || type == 1) edge_block(q, t, p, pa, pb, acc); else edge_block_slerp(q, t, p, pa, pb, R.v[6], acc);
+        const double pa[3] = {V[i], V[pl + i], V[2 * pl + i]}, pb[3] = {V[3 * pl + i], V[4 * pl + i], V[5 * pl + i]};
+        if (!SLERP || type == 1) edge_block(q, t, p, pa, pb, acc); else edge_block_slerp(q, t, p, pa, pb, V[6 * pl + i], acc);
       } else {
-        const double nn[3] = {R.v[0], R.v[1], R.v[2]};
-        if (!SLERP || type == 2) plane_block(q, t, p, nn, R.v[3], acc); else plane_block_slerp(q, t, p, nn, R.v[3], R.v[4], acc);
+        const double nn[3] = {V[i], V[pl + i], V[2 * pl + i]};
+        if (!SLERP || type == 2) plane_block(q, t, p, nn, V[3 * pl + i], acc); else plane_block_slerp(q, t, p, nn, V[3 * pl + i], V[4 * pl + i], acc);
       }
     }
   }

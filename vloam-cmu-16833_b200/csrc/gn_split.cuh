@@ -21,6 +21,22 @@ struct GNResidual {
                  // 3 / 4: edge / plane with the motion-distortion ratio s in v[6] / v[4] (laser_odometry.h:90 DISTORTION)
 };
 
+// Storage of the records: structure of arrays, so that consecutive threads read consecutive addresses — seven planes of
+// doubles and one float4 (point + type) per record.  Block `k` (a stream, or a stream's corner / surf half) holds `n` slots:
+// v[(k * 7 + plane) * n + i], p[k * n + i].  (Round 1 kept 72-byte records: every 8-byte load of a warp touched 32 sectors.)
+struct GNRecArray {
+  double* v;
+  float4* p;
+  int n;
+};
+__device__ __forceinline__ void gn_store(const GNRecArray& A, size_t block, int i, const GNResidual& R) {
+  double* v = A.v + block * 7 * (size_t)A.n + i;
+#pragma unroll
+  for (int k = 0; k < 7; ++k) v[(size_t)k * A.n] = R.v[k];
+  A.p[block * (size_t)A.n + i] = make_float4(R.px, R.py, R.pz, __int_as_float(R.type));
+}
+__device__ __forceinline__ int gn_type(const float4& p) { return __float_as_int(p.w); }
+
 constexpr int kGnTiles = 8;          // CTAs per stream of gn_accumulate
 constexpr int kGnThreads = 256;
 
@@ -39,8 +55,8 @@ struct Strided {
 };
 
 struct GNProblemView {
-  const GNResidual* rec[2];          // up to two record arrays per stream (laser mapping: corner / surf queries)
-  size_t recStride[2];               // records per stream in each array
+  GNRecArray rec;                    // the records; stream b owns the blocks b * blocksPerStream + (0 .. blocksPerStream - 1)
+  int blocksPerStream;               // 1 (laser odometry) or 2 (laser mapping: corner / surf queries)
   Strided count[2];                  // int: live records of each array (count[i].base == nullptr: fixedCount[i])
   int fixedCount[2];
   Strided active;                    // int flag (nullptr: always active)

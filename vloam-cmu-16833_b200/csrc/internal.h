@@ -60,10 +60,10 @@ cudaError_t sr_prepare_device(int device);   // per-device function attributes, 
 void launch_lo_init(Profiler* prof, cudaStream_t st, LOState* lo, int B);
 // Grid index over the (corner, surf) target clouds of every stream: [B][2] headers, cell tables and sorted copies.
 struct GNState;
-struct GNResidual;
 struct LOGrid {
   // wide solve (gn_split.cuh): residual records [B][kMaxSharp + kMaxFlat], per-stream state, tile partials, rank-summed counts
-  GNResidual* gnRec = nullptr;
+  double* gnRecV = nullptr;    // [B][7][kMaxSharp + kMaxFlat]
+  float4* gnRecP = nullptr;    // [B][kMaxSharp + kMaxFlat]
   GNState* gnState = nullptr;
   double* gnPartial = nullptr;
   double* gnCounts = nullptr;

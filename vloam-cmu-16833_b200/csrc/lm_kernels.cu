@@ -117,7 +117,7 @@ struct LMDevice {
   float4* concat = nullptr;               // [B][2][workCap] refilter inputs (old ++ new per work cube)
   float4* staged = nullptr;               // [B][2][workCap] refilter outputs
   float4* sorted = nullptr;               // [B][2][mapCap] column-sorted copy of every indexed cube at its slab's offset, w = index in the cube
-  LMResidual* res = nullptr;              // [B][2][cap]
+  GNRecArray res{nullptr, nullptr, 0};    // [B][2] blocks of cap records (gn_split.cuh): residual blocks of the current pass
   GNState* gnState = nullptr;             // [B] wide solve (gn_split.cuh): per-stream trust-region state between launches
   double* gnPartial = nullptr;            // [B][kGnTiles][28] partial normal equations of one evaluation
   void* ncclComm = nullptr;               // point-sharded streams: the partials are all-reduced across ranks (capi.cu)
@@ -497,59 +497,38 @@ __device__ void cta_build_cube_index(const float4* __restrict__ pts, int n, floa
       if (i0 + u * NT < n) { const int c = cell_of(p[u]); atomicAdd(&s_pack[c >> 1], (c & 1) ? 0x10000u : 1u); }
   }
   __syncthreads();
-  // Exclusive scan over the cells in (z-layer, column) order, a warp per contiguous range of words and a lane per word of a
-  // 32-word row (consecutive lanes -> consecutive banks; a thread walking its own run of words would hit one bank 32 ways).
-  constexpr int kWords = (kZCells + 1) / 2, kWarps = NT / 32;
-  constexpr int kRows = (kWords + 32 * kWarps - 1) / (32 * kWarps);      // rows of 32 words per warp
-  const int w0 = w * kRows * 32;
-  auto warp_scan = [&](int v) {           // inclusive
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, v, o); if (l >= o) v += t; }
-    return v;
-  };
-  {
-    int sum = 0;
+  // Column starts relative to the layer start = an exclusive scan inside every z-layer: one warp per layer (13 of the
+  // warps), a lane per word of a 32-word row (consecutive lanes -> consecutive banks), one pass.  The layer totals fall out
+  // of the same pass; their prefix gives the layer starts the scatter and the table header need.
+  constexpr int kLayerWords = kCubeCells / 2;                      // 1250 words of two 16-bit counters per layer
+  constexpr int kRows = (kLayerWords + 31) / 32;
+  static_assert(NT / 32 >= kZBins, "one warp per z-layer");
+  if (w < kZBins) {
+    const int w0 = w * kLayerWords;
+    int carry = 0;
     for (int r = 0; r < kRows; ++r) {
-      const int j = w0 + r * 32 + l;
-      if (j < kWords) { const unsigned v = s_pack[j]; sum += (int)(v & 0xffffu) + (int)(v >> 16); }
-    }
-    sum = __reduce_add_sync(0xffffffffu, sum);
-    if (l == 0) s_w[w] = sum;
-  }
-  __syncthreads();
-  int base = 0;
-  for (int q = 0; q < w; ++q) base += s_w[q];
-  // pass 1: the layer starts (layer z begins at cell z * 2500: the low half of word z * 1250)
-  {
-    int carry = base;
-    for (int r = 0; r < kRows; ++r) {
-      const int j = w0 + r * 32 + l;
-      const unsigned v = j < kWords ? s_pack[j] : 0u;
-      const int cnt = (int)(v & 0xffffu) + (int)(v >> 16);
-      const int incl = warp_scan(cnt);
-      if (j < kWords && j % (kCubeCells / 2) == 0) s_layer[j / (kCubeCells / 2)] = carry + incl - cnt;
-      carry += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (threadIdx.x == 0) s_layer[kZBins] = n;
-  }
-  __syncthreads();
-  // pass 2: every counter becomes the 16-bit start of its column relative to its layer's start: that IS the table
-  {
-    int carry = base;
-    for (int r = 0; r < kRows; ++r) {
-      const int j = w0 + r * 32 + l;
-      const unsigned v = j < kWords ? s_pack[j] : 0u;
+      const int jj = r * 32 + l;
+      const unsigned v = jj < kLayerWords ? s_pack[w0 + jj] : 0u;
       const int lo = (int)(v & 0xffffu), cnt = lo + (int)(v >> 16);
-      const int incl = warp_scan(cnt);
-      if (j < kWords) {
-        const int start = carry + incl - cnt - s_layer[(2 * j) / kCubeCells];     // both cells of a word lie in one layer (2500 is even)
-        s_pack[j] = (unsigned)start | ((unsigned)(start + lo) << 16);
+      int incl = cnt;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += t; }
+      if (jj < kLayerWords) {
+        const int start = carry + incl - cnt;                      // both cells of a word lie in one layer (2500 is even)
+        s_pack[w0 + jj] = (unsigned)start | ((unsigned)(start + lo) << 16);
       }
       carry += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x <= kZBins ? s_layer[threadIdx.x] : 0;   // hdr[13] = n, hdr[14] = mode 0
+    if (l == 0) s_w[w] = carry;                                    // points in layer w
   }
   __syncthreads();
+  if (threadIdx.x == 0) {
+    int run = 0;
+    for (int z = 0; z < kZBins; ++z) { s_layer[z] = run; run += s_w[z]; }
+    s_layer[kZBins] = run;                                         // == n
+  }
+  __syncthreads();
+  if (threadIdx.x < kTabHdr) tab[threadIdx.x] = threadIdx.x <= kZBins ? s_layer[threadIdx.x] : 0;   // hdr[13] = n, hdr[14] = mode 0
   // the table goes to global memory as it sits in shared memory: coalesced 32-bit words
   {
     unsigned* relw = reinterpret_cast<unsigned*>(tab + kTabHdr);
@@ -882,7 +861,7 @@ __global__ void __launch_bounds__(kKnnThreads) lm_knn_stats(VB_LM_KNN_ARGS) { lm
 // grid (nblk, 2, B), block 128: one thread per point
 __global__ void __launch_bounds__(128) lm_fit(LMState* __restrict__ stAll, const float4* __restrict__ stack, int cap,
                                                const float4* __restrict__ sorted, int mapCap, const int* __restrict__ nnPos,
-                                               LMResidual* __restrict__ res, uint8_t* __restrict__ fitType /*[B][2][cap] of this pass*/, int pass) {
+                                               const GNRecArray res, uint8_t* __restrict__ fitType /*[B][2][cap] of this pass*/, int pass) {
   const int kind = blockIdx.y, b = blockIdx.z;
   const LMState& st = stAll[b];
   if (!st.solved) return;
@@ -932,7 +911,7 @@ __global__ void __launch_bounds__(128) lm_fit(LMState* __restrict__ stAll, const
         if (ok) { R.type = 2; R.v[0] = n[0]; R.v[1] = n[1]; R.v[2] = n[2]; R.v[3] = d; }
       }
     }
-    res[((size_t)b * 2 + kind) * cap + qi] = R;
+    gn_store(res, (size_t)b * 2 + kind, qi, R);
     fitType[((size_t)b * 2 + kind) * cap + qi] = (uint8_t)R.type;   // parity read-out: which queries produced a factor in this pass
     nFactors += R.type != 0;
   }
@@ -949,7 +928,7 @@ __global__ void __launch_bounds__(128) lm_fit(LMState* __restrict__ stAll, const
 // bit-identical state and no broadcast is needed; only rank 0 writes results.
 constexpr int kLmClusterMax = 8;
 constexpr int kGnSplitMinBatch = 1 << 30;   // batch size from which the wide solve (gn_split.cuh) is the default: set by measurement     // cluster size is a launch attribute (1, 2, 4 or 8): see lm_run
-__global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const LMResidual* __restrict__ res,
+__device__ __forceinline__ void lm_solve_body(LMState* __restrict__ stAll, const GNRecArray res,
                                                                                     int cap, int pass, int max_iterations, int lastPass) {
   namespace cg = cooperative_groups;
   cg::cluster_group cluster = cg::this_cluster();
@@ -962,16 +941,19 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
   LMState& st = stAll[b];
   if (!st.solved) return;              // uniform over the cluster
   SolveTrace* tr = rank == 0 ? &st.trace[pass] : &s_trace;
-  const LMResidual* rc = res + ((size_t)b * 2 + 0) * cap;
-  const LMResidual* rs = res + ((size_t)b * 2 + 1) * cap;
+  const size_t pl = (size_t)res.n;
+  const float4* Pc = res.p + ((size_t)b * 2 + 0) * pl;
+  const float4* Ps = res.p + ((size_t)b * 2 + 1) * pl;
+  const double* Vc = res.v + ((size_t)b * 2 + 0) * 7 * pl;
+  const double* Vs = res.v + ((size_t)b * 2 + 1) * 7 * pl;
   const int nc = st.stackNum[0], ns = st.stackNum[1];
   if (threadIdx.x < 2) s_cnt[threadIdx.x] = 0;
   if (threadIdx.x == 0) for (int i = 0; i < 7; ++i) S.x[i] = st.parameters[i];
   __syncthreads();
   if (rank == 0) {
     int a = 0, c = 0;
-    for (int i = threadIdx.x; i < nc; i += blockDim.x) a += rc[i].type == 1;
-    for (int i = threadIdx.x; i < ns; i += blockDim.x) c += rs[i].type == 2;
+    for (int i = threadIdx.x; i < nc; i += blockDim.x) a += gn_type(Pc[i]) == 1;
+    for (int i = threadIdx.x; i < ns; i += blockDim.x) c += gn_type(Ps[i]) == 2;
     a = __reduce_add_sync(0xffffffffu, a); c = __reduce_add_sync(0xffffffffu, c);
     if (lane_id() == 0) { atomicAdd(&s_cnt[0], a); atomicAdd(&s_cnt[1], c); }
     __syncthreads();
@@ -986,16 +968,16 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
     const double q[4] = {x[0], x[1], x[2], x[3]};
     const double t[3] = {x[4], x[5], x[6]};
     for (int i = first; i < nc; i += stride) {
-      const LMResidual& R = rc[i];
-      if (R.type != 1) continue;
-      const double a[3] = {R.v[0], R.v[1], R.v[2]}, bb[3] = {R.v[3], R.v[4], R.v[5]};
-      edge_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), a, bb, acc);
+      const float4 p = Pc[i];
+      if (gn_type(p) != 1) continue;
+      const double a[3] = {Vc[i], Vc[pl + i], Vc[2 * pl + i]}, bb[3] = {Vc[3 * pl + i], Vc[4 * pl + i], Vc[5 * pl + i]};
+      edge_block(q, t, p, a, bb, acc);
     }
     for (int i = first; i < ns; i += stride) {
-      const LMResidual& R = rs[i];
-      if (R.type != 2) continue;
-      const double n[3] = {R.v[0], R.v[1], R.v[2]};
-      plane_block(q, t, make_float4(R.px, R.py, R.pz, 0.f), n, R.v[3], acc);
+      const float4 p = Ps[i];
+      if (gn_type(p) != 2) continue;
+      const double n[3] = {Vs[i], Vs[pl + i], Vs[2 * pl + i]};
+      plane_block(q, t, p, n, Vs[3 * pl + i], acc);
     }
     block_reduce28(acc, S.red, S.scratch);
     if (threadIdx.x < 28) s_part[gen][threadIdx.x] = S.red[threadIdx.x];
@@ -1015,6 +997,15 @@ __global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, con
     if (lastPass) st.counters[kCntFactors] += tr->n_corner + tr->n_plane;
   }
   cluster.sync();                      // nobody leaves while a peer may still read its partial sums
+}
+
+// Two register budgets: 226 registers (one CTA per SM) and <= 128 (two per SM, some spilling); chosen by measurement
+// (VLOAM_LM_SOLVE_REGS=128), DESIGN.md section 5.
+__global__ void __launch_bounds__(256) lm_solve(LMState* __restrict__ stAll, const GNRecArray res, int cap, int pass, int max_iterations, int lastPass) {
+  lm_solve_body(stAll, res, cap, pass, max_iterations, lastPass);
+}
+__global__ void __launch_bounds__(256, 2) lm_solve_r128(LMState* __restrict__ stAll, const GNRecArray res, int cap, int pass, int max_iterations, int lastPass) {
+  lm_solve_body(stAll, res, cap, pass, max_iterations, lastPass);
 }
 
 // Wide solve (gn_split.cuh): book-keeping after the last gn_step of a pass.
@@ -1618,7 +1609,8 @@ static cudaError_t lm_alloc(LMDevice* lm, cudaStream_t st) {
   A((void**)&lm->tabPool, B * 2 * (size_t)kTabSlots * kTabInts * sizeof(int));
   A((void**)&lm->entryHead, B * kCubes * sizeof(short));
   A((void**)&lm->sorted, B * 2 * mapCap * sizeof(float4));
-  A((void**)&lm->res, B * 2 * cap * sizeof(LMResidual));
+  A((void**)&lm->res.v, B * 2 * 7 * cap * sizeof(double)); A((void**)&lm->res.p, B * 2 * cap * sizeof(float4));
+  lm->res.n = (int)cap;
   A((void**)&lm->fitType, 2 * B * 2 * cap);
   A((void**)&lm->gnState, B * sizeof(GNState)); A((void**)&lm->gnPartial, B * kGnTiles * 28 * sizeof(double));
   A((void**)&lm->nnPos, B * 2 * cap * 5 * sizeof(int));
@@ -1654,7 +1646,7 @@ void lm_destroy(LMDevice* lm) {
     cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
-    cudaFree(lm->res); cudaFree(lm->fitType); cudaFree(lm->gnState); cudaFree(lm->gnPartial); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
+    cudaFree(lm->res.v); cudaFree(lm->res.p); cudaFree(lm->fitType); cudaFree(lm->gnState); cudaFree(lm->gnPartial); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
   }
   delete lm;
 }
@@ -1711,8 +1703,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
     if (split) {
       // wide solve: one launch over all residual blocks of all streams per evaluation + a warp-per-stream step
       GNProblemView pv{};
-      pv.rec[0] = lm->res; pv.rec[1] = lm->res + cap;            // corner / surf records of stream b at b * 2 * cap
-      pv.recStride[0] = pv.recStride[1] = (size_t)2 * cap;
+      pv.rec = lm->res; pv.blocksPerStream = 2;                  // corner / surf records of stream b: blocks 2 b, 2 b + 1
       pv.count[0] = Strided{&lm->st[0].stackNum[0], sizeof(LMState)}; pv.count[1] = Strided{&lm->st[0].stackNum[1], sizeof(LMState)};
       pv.active = Strided{&lm->st[0].solved, sizeof(LMState)};
       pv.x = Strided{&lm->st[0].parameters[0], sizeof(LMState)};
@@ -1731,8 +1722,13 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve, lm->st, (const LMResidual*)lm->res, cap, tp, lm->p.lm_max_iterations,
-                                                                 pass == lm->p.lm_outer_passes - 1 ? 1 : 0));
+      static const bool regs128 = [] { const char* e = getenv("VLOAM_LM_SOLVE_REGS"); return e && atoi(e) == 128; }();
+      if (regs128)
+        VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve_r128, lm->st, lm->res, cap, tp, lm->p.lm_max_iterations,
+                                                                   pass == lm->p.lm_outer_passes - 1 ? 1 : 0));
+      else
+        VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve, lm->st, lm->res, cap, tp, lm->p.lm_max_iterations,
+                                                                   pass == lm->p.lm_outer_passes - 1 ? 1 : 0));
     }
   }
   // C10-C12: transformUpdate, insertion, re-filter of the cubes that can change, write-back

@@ -723,7 +723,7 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
 __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __restrict__ hdrCur, LOState* __restrict__ lo,
                                                            const float4* __restrict__ sharp, const float4* __restrict__ flat,
                                                            const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
-                                                           int cap, const int4* __restrict__ corr, int pass, GNResidual* __restrict__ recAll,
+                                                           int cap, const int4* __restrict__ corr, int pass, const GNRecArray recAll,
                                                            double* __restrict__ counts /*[B][2] or nullptr*/, int distortion) {
   constexpr int kSlots = kMaxSharp + kMaxFlat;
   const int b = blockIdx.x;
@@ -733,7 +733,6 @@ __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __rest
   const float4* fl = flat + (size_t)b * kMaxFlat;
   const float4* CL = cornerLast + (size_t)b * kMaxLessSharp;
   const float4* SL = surfLast + (size_t)b * cap;
-  GNResidual* rec = recAll + (size_t)b * kSlots;
   const int nSharp = hdrCur[b].nSharp, nFlat = hdrCur[b].nFlat;
   __shared__ int s_nc, s_np;
   if (threadIdx.x == 0) { s_nc = 0; s_np = 0; }
@@ -770,7 +769,7 @@ __global__ void __launch_bounds__(256) lo_stage_residuals(const SRHeader* __rest
         }
       }
     }
-    rec[s] = R;
+    gn_store(recAll, (size_t)b, s, R);
   }
   nc = __reduce_add_sync(0xffffffffu, nc);
   np = __reduce_add_sync(0xffffffffu, np);
@@ -914,11 +913,11 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
   if (split) {
     // wide solve (gn_split.cuh): residual records once per pass, then one launch over all streams per LM evaluation
     double* counts = g->ncclComm ? g->gnCounts : nullptr;
-    VB_LAUNCH(prof, K_LO_STEP, st, lo_stage_residuals<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, g->gnRec, counts, distortion ? 1 : 0));
+    VB_LAUNCH(prof, K_LO_STEP, st, lo_stage_residuals<<<B, 256, 0, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, GNRecArray{g->gnRecV, g->gnRecP, kMaxSharp + kMaxFlat}, counts, distortion ? 1 : 0));
     if (counts) gn_allreduce_partials(g->ncclComm, counts, (size_t)B * 2, st);
     GNProblemView pv{};
-    pv.rec[0] = g->gnRec; pv.rec[1] = nullptr;
-    pv.recStride[0] = kMaxSharp + kMaxFlat; pv.fixedCount[0] = kMaxSharp + kMaxFlat;
+    pv.rec = GNRecArray{g->gnRecV, g->gnRecP, kMaxSharp + kMaxFlat}; pv.blocksPerStream = 1;
+    pv.fixedCount[0] = kMaxSharp + kMaxFlat;
     pv.x = Strided{&lo[0].para_q[0], sizeof(LOState)};
     pv.trace = Strided{&lo[0].trace[pass], sizeof(LOState)};
     pv.slerp = distortion ? 1 : 0;
