@@ -628,6 +628,7 @@ struct VoxelSmem {
   unsigned key[2][CAP];
   unsigned short pos[2][CAP];
   int lf[CAP];           // cloud indices of the less-flat candidates (ring order)
+  unsigned short runStart[CAP + 2];   // first candidate of every run of equal voxel keys, in ring order; [runs] = m
   int off[8][256];       // per-warp digit offsets
   int scan[256 + 1];
   float red[6 * 8];
@@ -777,93 +778,54 @@ __device__ __forceinline__ void voxel_ring(VoxelSmem<CAP>& S, SRHeader* __restri
     const int i0 = (int)__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)minb[0]);
     const int i1 = (int)__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)minb[1]);
     const int i2 = (int)__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)minb[2]);
-    S.key[0][k] = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
-    S.pos[0][k] = (unsigned short)k;
+    S.key[1][k] = (unsigned)(i0 + i1 * mul1 + i2 * mul2);     // per-point keys (scratch: the sort's second buffer)
   }
   __syncthreads();
+  // ---- runs of equal keys along the ring.  Consecutive points of a ring mostly stay in one 0.2 m voxel for a few
+  // steps and a voxel is rarely entered twice, so sorting RUNS (about a third as many as points) is enough: a voxel's runs
+  // end up side by side in ring order (stable sort) and the ordered float sum is chained through them point by point —
+  // the same additions in the same order as over the individually sorted points.
+  int nr;
+  {
+    const int per = (m + 255) / 256;
+    const int k0 = min((int)threadIdx.x * per, m), k1 = min(k0 + per, m);
+    int cnt = 0;
+    for (int k = k0; k < k1; ++k) cnt += (k == 0 || S.key[1][k] != S.key[1][k - 1]) ? 1 : 0;
+    int r = block_exclusive_scan(cnt, S.scan);
+    for (int k = k0; k < k1; ++k)
+      if (k == 0 || S.key[1][k] != S.key[1][k - 1]) { S.runStart[r] = (unsigned short)k; S.key[0][r] = S.key[1][k]; S.pos[0][r] = (unsigned short)r; ++r; }
+    nr = S.scan[256];
+    if (threadIdx.x == 0) S.runStart[nr] = (unsigned short)m;
+    __syncthreads();
+  }
   // keys are < divb[0]*divb[1]*divb[2]; if that product does not fit 32 bits fall back to all 32 key bits
   int bits = 32;
   if ((long long)divb[0] * divb[1] * divb[2] <= 0xffffffffLL) bits = maxKey ? 32 - __clz(maxKey) : 1;
-  const int cur = voxel_radix_sort<CAP>(S, m, bits);
+  const int cur = voxel_radix_sort<CAP>(S, nr, bits);
   const unsigned* keys = S.key[cur];
-  const unsigned short* pos = S.pos[cur];
-  // segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n).
-  // A warp takes 32 consecutive sorted entries at a time: every lane loads its own point (independent loads, one
-  // latency per window instead of one per point), then each head lane adds the points of its voxel strictly left to
-  // right, fetching them from the following lanes (this window or the next, which is already in registers) by shuffle.
-  const int w = threadIdx.x >> 5, l = lane_id();
-  const int nwin = (m + 31) >> 5;                     // <= CAP / 32 <= 128
-  for (int v = w; v < nwin; v += 8) {
-    const int q = v * 32 + l;
-    const bool head = q < m && (q == 0 || keys[q] != keys[q - 1]);
-    const unsigned hm = __ballot_sync(0xffffffffu, head);
-    if (l == 0) S.scan[v] = __popc(hm);
-  }
-  __syncthreads();
-  if (w == 0) {   // exclusive prefix of the per-window head counts
-    int carry = 0;
-    for (int base = 0; base < nwin; base += 32) {
-      const int x = base + l < nwin ? S.scan[base + l] : 0;
-      int sc = x;
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, sc, o); if (l >= o) sc += t; }
-      if (base + l < nwin) S.scan[base + l] = carry + sc - x;
-      carry += __shfl_sync(0xffffffffu, sc, 31);
-    }
-    if (l == 0) S.scan[256] = carry;
-  }
-  __syncthreads();
+  const unsigned short* rid = S.pos[cur];
+  // ---- one output per voxel = per head among the sorted runs; thread t owns a contiguous range of sorted runs
   {
-    const int perw = (nwin + 7) / 8;
-    const int v0 = min(w * perw, nwin), v1 = min(v0 + perw, nwin);
-    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1;
-    unsigned k0 = 0, bnd0 = 0xffffffffu, hd0 = 0, bnd1, hd1;
-    auto load_window = [&](int u, float4& p, unsigned& k, unsigned& bnd, unsigned& hd) {
-      const int q = u * 32 + l;
-      const bool ok = q < m;
-      k = ok ? keys[q] : 0u;
-      const bool head = ok && (q == 0 || keys[q - 1] != k);
-      p = ok ? c[S.lf[pos[q]]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      hd = __ballot_sync(0xffffffffu, head);
-      bnd = hd | ~__ballot_sync(0xffffffffu, ok);       // a run ends at the next head or at the end of the data
-    };
-    if (v0 < v1) load_window(v0, p0, k0, bnd0, hd0);
-    for (int v = v0; v < v1; ++v) {
-      unsigned k1;
-      load_window(v + 1, p1, k1, bnd1, hd1);
-      const bool head = (hd0 >> l) & 1u;
-      // run length of the voxel starting at this lane, seen through the 64-entry window pair
-      const unsigned long long B = (unsigned long long)bnd0 | ((unsigned long long)bnd1 << 32);
-      const unsigned long long rest = l == 63 ? 0ull : (B >> (l + 1));
-      const bool open = rest == 0ull;                    // no boundary in sight: the run leaves the window pair
-      int len = head ? (open ? 64 - l : (int)__ffsll((long long)rest)) : 0;
-      const int maxlen = __reduce_max_sync(0xffffffffu, len);
+    const int per = (nr + 255) / 256;
+    const int q0 = min((int)threadIdx.x * per, nr), q1 = min(q0 + per, nr);
+    int nh = 0;
+    for (int q = q0; q < q1; ++q) nh += (q == 0 || keys[q] != keys[q - 1]) ? 1 : 0;
+    int opos = block_exclusive_scan(nh, S.scan);
+    for (int q = q0; q < q1; ++q) {
+      if (!(q == 0 || keys[q] != keys[q - 1])) continue;
+      const unsigned vox = keys[q];
       float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      sx = __fadd_rn(sx, p0.x); sy = __fadd_rn(sy, p0.y); sz = __fadd_rn(sz, p0.z); si = __fadd_rn(si, p0.w);
-      for (int j = 1; j < maxlen; ++j) {
-        // entry l + j lives in lane (l + j) & 31 of this window (if l + j < 32) or of the next one; lane s is asked
-        // for its current-window point by reader s - j and for its next-window point by reader s + 32 - j, never both
-        const bool cur = l >= j;
-        const int src = (l + j) & 31;
-        const float gx = __shfl_sync(0xffffffffu, cur ? p0.x : p1.x, src);
-        const float gy = __shfl_sync(0xffffffffu, cur ? p0.y : p1.y, src);
-        const float gz = __shfl_sync(0xffffffffu, cur ? p0.z : p1.z, src);
-        const float gi = __shfl_sync(0xffffffffu, cur ? p0.w : p1.w, src);
-        if (j < len) { sx = __fadd_rn(sx, gx); sy = __fadd_rn(sy, gy); sz = __fadd_rn(sz, gz); si = __fadd_rn(si, gi); }
-      }
-      if (head) {
-        if (open) {   // rare: more than 64 - l points of one voxel; finish from memory
-          for (int qq = v * 32 + 64; qq < m && keys[qq] == k0; ++qq) {
-            const float4 pp = c[S.lf[pos[qq]]];
-            sx = __fadd_rn(sx, pp.x); sy = __fadd_rn(sy, pp.y); sz = __fadd_rn(sz, pp.z); si = __fadd_rn(si, pp.w);
-            ++len;
-          }
+      int cnt = 0;
+      for (int qq = q; qq < nr && keys[qq] == vox; ++qq) {        // the voxel's runs, in ring order
+        const int r = rid[qq];
+        for (int t = S.runStart[r]; t < S.runStart[r + 1]; ++t) {  // the run's points, in ring order
+          const float4 pp = c[S.lf[t]];
+          sx = __fadd_rn(sx, pp.x); sy = __fadd_rn(sy, pp.y); sz = __fadd_rn(sz, pp.z); si = __fadd_rn(si, pp.w);
+          ++cnt;
         }
-        const float nf = (float)len;
-        stage[S.scan[v] + __popc(hd0 & ((1u << l) - 1u))] =
-            make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
       }
-      p0 = p1; k0 = k1; bnd0 = bnd1; hd0 = hd1;
+      const float nf = (float)cnt;
+      stage[opos++] = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
     }
   }
   const int outBase = S.scan[256];
