@@ -71,7 +71,10 @@ enum {
   VLOAM_CLOUD_CORNER_STACK = 7,/* laserCloudCornerStack laser_mapping.cpp:432-435 */
   VLOAM_CLOUD_SURF_STACK = 8,  /* laserCloudSurfStack   laser_mapping.cpp:437-440 */
   VLOAM_CLOUD_CORNER_MAP = 9,  /* laserCloudCornerFromMap laser_mapping.cpp:422-428 */
-  VLOAM_CLOUD_SURF_MAP = 10    /* laserCloudSurfFromMap */
+  VLOAM_CLOUD_SURF_MAP = 10,   /* laserCloudSurfFromMap */
+  VLOAM_CLOUD_MAP = 11,        /* /laser_cloud_map: every cube's corner then surf points, laser_mapping.cpp:778-790 */
+  VLOAM_CLOUD_FULL_REGISTERED = 12 /* /velodyne_cloud_registered: laserCloudFullRes through pointAssociateToMap with the
+                                      current mapping pose, laser_mapping.cpp:797-805 */
 };
 
 /* ------------------------------------------------------------------ context */

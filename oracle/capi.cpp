@@ -264,19 +264,24 @@ long long orc_lm_map_points(void* h, int which) {
   for (const Cloud& c : (which == 0 ? lm->laserCloudCornerArray : lm->laserCloudSurfArray)) n += (long long)c.size();
   return n;
 }
-// which: 0 corner stack, 1 surf stack, 2 corner-from-map, 3 surf-from-map
-int orc_lm_cloud_count(void* h, int which) {
-  auto* lm = static_cast<LaserMapping*>(h);
-  const Cloud* c = which == 0 ? &lm->laserCloudCornerStack : which == 1 ? &lm->laserCloudSurfStack
-                   : which == 2 ? &lm->laserCloudCornerFromMap : &lm->laserCloudSurfFromMap;
-  return (int)c->size();
+// which: 0 corner stack, 1 surf stack, 2 corner-from-map, 3 surf-from-map, 4 laserCloudFullRes (in the map frame once
+// orc_lm_publish_registered has run for the frame), 5 the /laser_cloud_map concatenation
+static Cloud lm_cloud_of(LaserMapping* lm, int which) {
+  switch (which) {
+    case 0: return lm->laserCloudCornerStack;
+    case 1: return lm->laserCloudSurfStack;
+    case 2: return lm->laserCloudCornerFromMap;
+    case 3: return lm->laserCloudSurfFromMap;
+    case 4: return lm->laserCloudFullRes;
+    default: return lm->map_cloud();
+  }
 }
+int orc_lm_cloud_count(void* h, int which) { return (int)lm_cloud_of(static_cast<LaserMapping*>(h), which).size(); }
 void orc_lm_cloud_copy(void* h, int which, float* out) {
-  auto* lm = static_cast<LaserMapping*>(h);
-  const Cloud* c = which == 0 ? &lm->laserCloudCornerStack : which == 1 ? &lm->laserCloudSurfStack
-                   : which == 2 ? &lm->laserCloudCornerFromMap : &lm->laserCloudSurfFromMap;
-  if (!c->empty()) std::memcpy(out, c->data(), sizeof(PointXYZI) * c->size());
+  const Cloud c = lm_cloud_of(static_cast<LaserMapping*>(h), which);
+  if (!c.empty()) std::memcpy(out, c.data(), sizeof(PointXYZI) * c.size());
 }
+void orc_lm_publish_registered(void* h) { static_cast<LaserMapping*>(h)->publish_registered(); }
 int orc_lm_trace_passes(void* h) { return (int)static_cast<LaserMapping*>(h)->trace.size(); }
 void orc_lm_trace_sizes(void* h, int pass, int* sizes) {
   const LMPassTrace& t = static_cast<LaserMapping*>(h)->trace[pass];

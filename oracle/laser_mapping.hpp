@@ -88,6 +88,21 @@ class LaserMapping {
       parameters[4] = t.x; parameters[5] = t.y; parameters[6] = t.z;
     }
   }
+  // The cloud part of LaserMapping::publish.  :797-801 moves laserCloudFullRes into the map frame IN PLACE (the object's own
+  // deep copy, :175-180) before it goes out on /velodyne_cloud_registered — so a skipped frame, which keeps the previous
+  // copy, transforms it a second time; restated literally.  Call once per frame, like publish().
+  void publish_registered() {
+    for (PointXYZI& p : laserCloudFullRes) pointAssociateToMap(p, &p);
+  }
+  // /laser_cloud_map (:778-785): every cube, corner points then surf points
+  Cloud map_cloud() const {
+    Cloud all;
+    for (int i = 0; i < laserCloudNum; ++i) {
+      all.insert(all.end(), laserCloudCornerArray[i].begin(), laserCloudCornerArray[i].end());
+      all.insert(all.end(), laserCloudSurfArray[i].begin(), laserCloudSurfArray[i].end());
+    }
+    return all;
+  }
   // The pose LaserMapping::publish puts into /aft_mapped_to_init for the last input() (:720-756)
   void published_pose(double out[7]) const {
     if (skip_frame) {

@@ -23,8 +23,8 @@ c_ip = C.POINTER(C.c_int)
 
 def build(force: bool = False) -> str:
     """Compile the C++ restatement (g++ only).  Safe to call repeatedly."""
-    if force or not os.path.exists(_LIB_PATH):
-        subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
+    # make is incremental: a no-op when the library is newer than every source, a rebuild when a header changed
+    subprocess.check_call(["make", "-C", _HERE] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return _LIB_PATH
 
 
@@ -77,6 +77,7 @@ def lib():
             "orc_lm_map_points": (C.c_longlong, [vp, C.c_int]),
             "orc_lm_cloud_count": (C.c_int, [vp, C.c_int]),
             "orc_lm_cloud_copy": (None, [vp, C.c_int, c_fp]),
+            "orc_lm_publish_registered": (None, [vp]),
             "orc_lm_trace_passes": (C.c_int, [vp]),
             "orc_lm_trace_sizes": (None, [vp, C.c_int, c_ip]),
             "orc_lm_trace_copy": (None, [vp, C.c_int, c_ip, c_ip, c_dp, c_dp, c_ip]),
@@ -370,6 +371,16 @@ class LaserMapping:
         a = np.empty((n, 4), np.float32)
         lib().orc_lm_cloud_copy(self._h, which, _fp(a))
         return a
+
+    def publish_registered(self):
+        """LaserMapping::publish's /velodyne_cloud_registered (laser_mapping.cpp:797-805): moves laserCloudFullRes into the
+        map frame in place (once per frame) and returns it."""
+        lib().orc_lm_publish_registered(self._h)
+        return self.cloud(4)
+
+    def map_cloud(self):
+        """/laser_cloud_map (laser_mapping.cpp:778-790): every cube's corner then surf points."""
+        return self.cloud(5)
 
     def trace(self):
         L = lib()

@@ -25,7 +25,7 @@ static pcl::PointCloud<pcl::PointXYZ> load(const char* path) {   // packed float
 static void set_params() {
   auto& p = ros::stub::params();
   p["loam_verbose_level"] = 0; p["scan_line"] = 64; p["minimum_range"] = 5.0; p["mapping_skip_frame"] = 1; p["detach_VO_LO"] = 1;
-  p["mapping_line_resolution"] = 0.4; p["mapping_plane_resolution"] = 0.8;
+  p["mapping_line_resolution"] = 0.4; p["mapping_plane_resolution"] = 0.8; p["map_pub_number"] = 2;
 }
 
 int main(int argc, char** argv) {

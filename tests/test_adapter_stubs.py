@@ -60,3 +60,6 @@ def test_adapters_run_the_callers_frame_loop(tmp_path, synth):
     published = {l.split()[1]: int(l.split()[2]) for l in out.splitlines() if l.startswith("published")}
     for t in ("/laser_odom_to_init", "/laser_odom_path", "/aft_mapped_to_init", "/aft_mapped_path", "/laser_cloud_sharp"):
         assert published[t] == 6, (t, published)        # three frames through the façade + three through the stage classes
+    assert published["/velodyne_cloud_registered"] == 6                  # laser_mapping.cpp:797-805: every frame
+    assert published["/laser_cloud_map"] == 2                            # :778: frameCount % map_pub_number (= 2) == 0, once per run of 3
+    assert published["/laser_cloud_surround"] == 0                       # advertised, never published (the reference does neither)

@@ -75,6 +75,16 @@ def _run_sequence(V, oracle, scans, check_cubes=True, map_capacity=1 << 18, stat
                         _same_xyz(lom.map_get_cube(kind, cube), pipe.lm.cube(kind, cube), f"scan {k} cube {cube} kind {kind}")
                         occupied += n_or > 0
             assert occupied > 0
+        if check_cubes:
+            # what LaserMapping::publish sends: /laser_cloud_map (every cube, corner then surf, laser_mapping.cpp:778-790) bit
+            # for bit; /velodyne_cloud_registered (:797-805) through the device's own mapping pose, which agrees with the
+            # oracle's to ~1e-8, so the float-rounded coordinates may differ in the last place
+            _same_xyz(lom.cloud(V.CLOUD_MAP), pipe.lm.map_cloud(), f"scan {k} /laser_cloud_map")
+            reg, oreg = lom.cloud(V.CLOUD_FULL_REGISTERED), pipe.lm.publish_registered()
+            assert reg.shape == oreg.shape and reg.shape[0] > 1000
+            assert np.array_equal(_bits(reg[:, 3]), _bits(oreg[:, 3]))
+            np.testing.assert_allclose(reg[:, :3], oreg[:, :3], atol=3e-5, rtol=0)
+            assert np.mean(_bits(reg[:, :3]) == _bits(oreg[:, :3])) > 0.99
         ms = lom.map_stats()[0]
         for kind in (0, 1):      # storage bookkeeping: the tables account for exactly the oracle's map
             assert ms[kind, 0] == sum(pipe.lm.cube_count(kind, c) for c in range(4851))

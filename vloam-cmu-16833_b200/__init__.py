@@ -26,7 +26,7 @@ HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "vloam_b200.h")
 
 VLOAM_OK = 0
 CLOUD_FULL, CLOUD_SHARP, CLOUD_LESS_SHARP, CLOUD_FLAT, CLOUD_LESS_FLAT, CLOUD_CORNER_LAST, CLOUD_SURF_LAST, \
-    CLOUD_CORNER_STACK, CLOUD_SURF_STACK, CLOUD_CORNER_MAP, CLOUD_SURF_MAP = range(11)
+    CLOUD_CORNER_STACK, CLOUD_SURF_STACK, CLOUD_CORNER_MAP, CLOUD_SURF_MAP, CLOUD_MAP, CLOUD_FULL_REGISTERED = range(13)
 STREAM_EMPTY, STREAM_RING_OVERFLOW, STREAM_VOXEL_OVERFLOW, STREAM_CAPACITY = 1, 2, 4, 8
 LM_WORKLIST_OVERFLOW, LM_SCRATCH_OVERFLOW, LM_CORNER_MAP_FULL, LM_SURF_MAP_FULL = 1, 2, 4, 8
 MAX_SHARP, MAX_FLAT = 768, 1536

@@ -61,7 +61,13 @@ class LidarOdometryMapping {
     for (int i = 0; i < 4; ++i) { mapped.q[i] = p[i]; wmap_wodom.q[i] = p[7 + i]; }
     for (int i = 0; i < 3; ++i) { mapped.t[i] = p[4 + i]; wmap_wodom.t[i] = p[11 + i]; }
   }
-  // ScanRegistration::output / LaserOdometry::output clouds as XYZI records
+  // per-stream status of the last laserMappingIO (VLOAM_LM_* bits; 0 = the scan was mapped and inserted)
+  int mappingStatus() {
+    int st = 0;
+    check(vloam_get_lm_status(h_, &st));
+    return st;
+  }
+  // ScanRegistration::output / LaserOdometry::output / LaserMapping::publish clouds as XYZI records
   std::vector<float> cloud(int which) {
     int n = 0;
     check(vloam_get_cloud(h_, 0, which, nullptr, 0, &n));

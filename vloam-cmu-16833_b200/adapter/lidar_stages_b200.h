@@ -17,6 +17,9 @@
 #include <pcl_conversions/pcl_conversions.h>
 #include <ros/ros.h>
 #include <sensor_msgs/PointCloud2.h>
+#if __has_include(<tf/transform_broadcaster.h>)
+#include <tf/transform_broadcaster.h>
+#endif
 #include <vloam_tf/vloam_tf.h>
 
 #if __has_include(<eigen3/Eigen/Dense>)
@@ -197,6 +200,8 @@ class LaserMapping {
     if (!ros::param::get("loam_verbose_level", verbose_level)) ROS_BREAK();
     if (!ros::param::get("mapping_line_resolution", p.mapping_line_resolution)) ROS_BREAK();
     if (!ros::param::get("mapping_plane_resolution", p.mapping_plane_resolution)) ROS_BREAK();
+    if (!ros::param::get("map_pub_number", map_pub_number)) ROS_BREAK();   // :123-124
+    if (!ros::param::get("mapping_skip_frame", mapping_skip_frame)) mapping_skip_frame = 1;
     pubLaserCloudSurround = nh.advertise<sensor_msgs::PointCloud2>("/laser_cloud_surround", 100);
     pubLaserCloudMap = nh.advertise<sensor_msgs::PointCloud2>("/laser_cloud_map", 100);
     pubLaserCloudFullRes = nh.advertise<sensor_msgs::PointCloud2>("/velodyne_cloud_registered", 100);
@@ -213,7 +218,15 @@ class LaserMapping {
   // there from frameCount % mapping_skip_frame exactly like LaserOdometry::output did.
   void input(const pcl::PointCloud<PointType>::Ptr&, const pcl::PointCloud<PointType>::Ptr&, const pcl::PointCloud<PointType>::Ptr&,
              const Eigen::Quaterniond&, const Eigen::Vector3d&, const bool& skip_frame_) { skip_frame = skip_frame_; }
-  void solveMapping() { core->laserMappingIO(); solved = true; }   // :198-708
+  void solveMapping() {   // :198-708
+    core->laserMappingIO();
+    solved = true;
+    ++frameCount;           // :707
+    // the reference's map grows without bound; this one lives in a pool of vloam_lidar_params::map_capacity_points
+    const int st = core->mappingStatus();
+    if (st & (VLOAM_LM_CORNER_MAP_FULL | VLOAM_LM_SURF_MAP_FULL))
+      ROS_WARN("laser mapping: the map pool is full (status 0x%x) - this scan was not inserted; raise map_capacity_points", st);
+  }
   void publish() {   // :710-814
     if (!solved) core->laserMappingIO();      // a skipped frame: only the high-frequency pose is refreshed (:186-190, 742-756)
     solved = false;
@@ -230,6 +243,20 @@ class LaserMapping {
     laserAfterMappedPath.header.frame_id = "map";
     laserAfterMappedPath.poses.push_back(laserAfterMappedPose);
     pubLaserAfterMappedPath.publish(laserAfterMappedPath);
+#if __has_include(<tf/transform_broadcaster.h>)
+    {   // :767-776 map -> aft_mapped
+      static tf::TransformBroadcaster br;
+      tf::Transform transform;
+      transform.setOrigin(tf::Vector3(m.t[0], m.t[1], m.t[2]));
+      transform.setRotation(tf::Quaternion(m.q[0], m.q[1], m.q[2], m.q[3]));
+      br.sendTransform(tf::StampedTransform(transform, odomAftMapped.header.stamp, "map", "aft_mapped"));
+    }
+#endif
+    if ((frameCount * mapping_skip_frame) % map_pub_number == 0)   // :778-790: the whole map, every cube's corner then surf points
+      b200_detail::publish_cloud(pubLaserCloudMap, *core, VLOAM_CLOUD_MAP, "velo_origin");
+    // :792-805 the full-resolution scan in the map frame.  (On a skipped frame the reference transforms its already
+    // transformed copy a second time, :175-180 + :797-801; here the scan is always taken in the sensor frame.)
+    b200_detail::publish_cloud(pubLaserCloudFullRes, *core, VLOAM_CLOUD_FULL_REGISTERED, "map");
   }
   void output() {}
 
@@ -239,6 +266,7 @@ class LaserMapping {
   ros::NodeHandle nh;
   int verbose_level = 0;
   bool skip_frame = false, solved = false;
+  int frameCount = 0, map_pub_number = 20, mapping_skip_frame = 1;
   nav_msgs::Path laserAfterMappedPath;
   ros::Publisher pubLaserCloudSurround, pubLaserCloudMap, pubLaserCloudFullRes, pubOdomAftMapped, pubLaserAfterMappedPath;
 };

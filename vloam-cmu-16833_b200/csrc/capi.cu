@@ -665,6 +665,15 @@ int vloam_get_cloud(vloam_lidar* h, int stream, int which, float* out, int capac
   vloam_ctx* c = h->ctx;
   if (h->frame < 0) return fail(c, VLOAM_E_STATE, "no scan registered yet");
   CU(c, cudaSetDevice(c->device));
+  if (which == VLOAM_CLOUD_MAP)
+    return lm_get_map_cloud(h->lm, c->stream, stream, out, capacity, n_out) == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "lm_get_map_cloud");
+  if (which == VLOAM_CLOUD_FULL_REGISTERED) {
+    std::vector<SRHeader> hd0;
+    int r0 = fetch_headers(h, &hd0, h->cur());
+    if (r0) return r0;
+    return lm_get_registered(h->lm, c->stream, stream, h->d_cloud[h->cur()] + (size_t)stream * h->cap, hd0[stream].cloudSize, out, capacity, n_out) == cudaSuccess
+               ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "lm_get_registered");
+  }
   if (which >= VLOAM_CLOUD_CORNER_STACK) return lm_get_cloud(h->lm, c->stream, stream, which, out, capacity, n_out) == cudaSuccess ? VLOAM_OK : fail(c, VLOAM_E_CUDA, "lm_get_cloud");
   std::vector<SRHeader> hd;
   // CORNER_LAST / SURF_LAST are the current scan's less-sharp / less-flat clouds once laser odometry has run

@@ -98,6 +98,8 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
 cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out);
 cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out);
 cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, const float* xyzi, int n);
+cudaError_t lm_get_registered(LMDevice* lm, cudaStream_t st, int stream, const float4* cloud, int n, float* out, int capacity, int* n_out);
+cudaError_t lm_get_map_cloud(LMDevice* lm, cudaStream_t st, int stream, float* out, int capacity, int* n_out);
 cudaError_t lm_get_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, float* out, int capacity, int* n_out);
 cudaError_t lm_get_info(LMDevice* lm, cudaStream_t st, int* info);
 cudaError_t lm_get_map_stats(LMDevice* lm, cudaStream_t st, int* stats);

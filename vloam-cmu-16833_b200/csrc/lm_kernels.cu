@@ -111,6 +111,9 @@ struct LMDevice {
   short* entryHead = nullptr;             // [B][kCubes] first entry of the valid list naming this cube, -1 = not in the sub-map
   float4* mapPts[2] = {nullptr, nullptr}; // two pools [B][2][mapCap]; a stream changes pool only when its map is re-packed
   float4* snap = nullptr;                 // [B][2][mapCap] laserCloud{Corner,Surf}FromMap of the last scan (debug_keep_submap)
+  float4* pubBuf = nullptr;               // staging for the clouds LaserMapping::publish sends (allocated on first use)
+  int* pubCount = nullptr;
+  size_t pubCap = 0;
   float4* stack = nullptr;                // [B][2][cap]  down-sampled scan (laserCloudCornerStack / SurfStack)
   float4* stackW = nullptr;               // [B][2][cap]  the same points in the map frame (pointAssociateToMap)
   unsigned* keyA = nullptr; unsigned* valA = nullptr; unsigned* keyB = nullptr; unsigned* valB = nullptr;  // [B][2][workCap]
@@ -1643,7 +1646,7 @@ void lm_destroy(LMDevice* lm) {
   if (lm->allocated) {
     cudaFree(lm->st);
     for (int i = 0; i < 2; ++i) { cudaFree(lm->cubeOff[i]); cudaFree(lm->cubeCnt[i]); cudaFree(lm->cubeCap[i]); cudaFree(lm->cubeFix[i]); cudaFree(lm->cubeTab[i]); cudaFree(lm->mapPts[i]); }
-    cudaFree(lm->snap); cudaFree(lm->liveList); cudaFree(lm->liveNum);
+    cudaFree(lm->snap); cudaFree(lm->pubBuf); cudaFree(lm->pubCount); cudaFree(lm->liveList); cudaFree(lm->liveNum);
     cudaFree(lm->stack); cudaFree(lm->stackW); cudaFree(lm->keyA); cudaFree(lm->valA); cudaFree(lm->keyB); cudaFree(lm->valB);
     cudaFree(lm->concat); cudaFree(lm->staged); cudaFree(lm->tabPool); cudaFree(lm->entryHead); cudaFree(lm->sorted);
     cudaFree(lm->res.v); cudaFree(lm->res.p); cudaFree(lm->fitType); cudaFree(lm->gnState); cudaFree(lm->gnPartial); cudaFree(lm->nnPos); cudaFree(lm->cubeOf); cudaFree(lm->pose); cudaFree(lm->workOf);
@@ -1818,6 +1821,89 @@ cudaError_t lm_get_queries(LMDevice* lm, cudaStream_t st, int stream, int pass, 
   }
   if (n_out) *n_out = n;
   return cudaSuccess;
+}
+
+// ---------------------------------------------------------------------------- the clouds LaserMapping::publish sends
+// lm_register_cloud: /velodyne_cloud_registered (laser_mapping.cpp:797-805) — the full-resolution scan moved into the map
+// frame by pointAssociateToMap with the mapping pose.
+__global__ void __launch_bounds__(256) lm_register_cloud(const LMState* __restrict__ stAll, int b, const float4* __restrict__ cloud,
+                                                          int n, float4* __restrict__ out) {
+  const LMState& st = stAll[b];
+  const double q[4] = {st.parameters[0], st.parameters[1], st.parameters[2], st.parameters[3]};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = cloud[i];
+    double w[3];
+    quat_rotate(q, (double)p.x, (double)p.y, (double)p.z, w);
+    out[i] = make_float4((float)(w[0] + st.parameters[4]), (float)(w[1] + st.parameters[5]), (float)(w[2] + st.parameters[6]), p.w);
+  }
+}
+// lm_gather_map: /laser_cloud_map (laser_mapping.cpp:778-790) — for every cube in index order its corner points, then its
+// surf points.  Every CTA scans the 4851 cube sizes (cheap) and copies its share of the cubes.
+constexpr int kGatherThreads = 256;
+__global__ void __launch_bounds__(kGatherThreads) lm_gather_map(const LMState* __restrict__ stAll, int b, const int* __restrict__ cubeOff,
+                                                                 const int* __restrict__ cubeCnt, const MapPools pools, int mapCap,
+                                                                 float4* __restrict__ out, int* __restrict__ total) {
+  __shared__ int s_start[kCubes + 1];
+  __shared__ int s_w[kGatherThreads / 32 + 1];
+  const LMState& st = stAll[b];
+  const int* cnt0 = cubeCnt + ((size_t)b * 2 + 0) * kCubes;
+  const int* cnt1 = cubeCnt + ((size_t)b * 2 + 1) * kCubes;
+  constexpr int kPer = (kCubes + kGatherThreads - 1) / kGatherThreads;
+  int sum = 0;
+  for (int k = 0; k < kPer; ++k) { const int c = threadIdx.x * kPer + k; if (c < kCubes) sum += cnt0[c] + cnt1[c]; }
+  int run = block_exclusive_scan_nt<kGatherThreads>(sum, s_w);
+  for (int k = 0; k < kPer; ++k) { const int c = threadIdx.x * kPer + k; if (c < kCubes) { s_start[c] = run; run += cnt0[c] + cnt1[c]; } }
+  if (threadIdx.x == 0) { s_start[kCubes] = s_w[kGatherThreads / 32]; if (blockIdx.x == 0) *total = s_w[kGatherThreads / 32]; }
+  __syncthreads();
+  for (int c = blockIdx.x; c < kCubes; c += gridDim.x) {
+    const int n0 = cnt0[c], n = s_start[c + 1] - s_start[c];
+    if (n == 0) continue;
+    const float4* src0 = stream_map(pools, st, b, 0, mapCap) + cubeOff[((size_t)b * 2 + 0) * kCubes + c];
+    const float4* src1 = stream_map(pools, st, b, 1, mapCap) + cubeOff[((size_t)b * 2 + 1) * kCubes + c];
+    float4* dst = out + s_start[c];
+    for (int i = threadIdx.x; i < n; i += kGatherThreads) dst[i] = i < n0 ? src0[i] : src1[i - n0];
+  }
+}
+static cudaError_t lm_publish_scratch(LMDevice* lm, size_t points) {
+  if (lm->pubCap >= points) return cudaSuccess;
+  cudaFree(lm->pubBuf);
+  lm->pubBuf = nullptr; lm->pubCap = 0;
+  cudaError_t e = cudaMalloc((void**)&lm->pubBuf, points * sizeof(float4));
+  if (e == cudaSuccess && !lm->pubCount) e = cudaMalloc((void**)&lm->pubCount, sizeof(int));
+  if (e == cudaSuccess) lm->pubCap = points;
+  return e;
+}
+cudaError_t lm_get_registered(LMDevice* lm, cudaStream_t st, int stream, const float4* cloud, int n, float* out, int capacity, int* n_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  if (n_out) *n_out = n;
+  const int m = n < capacity ? n : capacity;
+  if (m <= 0 || !out) return cudaSuccess;
+  e = lm_publish_scratch(lm, (size_t)lm->cap);
+  if (e != cudaSuccess) return e;
+  lm_register_cloud<<<(m + 255) / 256, 256, 0, st>>>(lm->st, stream, cloud, m, lm->pubBuf);
+  e = cudaMemcpyAsync(out, lm->pubBuf, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+cudaError_t lm_get_map_cloud(LMDevice* lm, cudaStream_t st, int stream, float* out, int capacity, int* n_out) {
+  cudaError_t e = lm_alloc(lm, st);
+  if (e != cudaSuccess) return e;
+  e = lm_publish_scratch(lm, (size_t)2 * lm->mapCap);
+  if (e != cudaSuccess) return e;
+  MapPools pools{{lm->mapPts[0], lm->mapPts[1]}};
+  lm_gather_map<<<148, kGatherThreads, 0, st>>>(lm->st, stream, lm->cubeOff[lm->curTab], lm->cubeCnt[lm->curTab], pools, lm->mapCap, lm->pubBuf, lm->pubCount);
+  int n = 0;
+  e = cudaMemcpyAsync(&n, lm->pubCount, sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e != cudaSuccess) return e;
+  if (n_out) *n_out = n;
+  const int m = n < capacity ? n : capacity;
+  if (m > 0 && out) {
+    e = cudaMemcpyAsync(out, lm->pubBuf, (size_t)m * 16, cudaMemcpyDeviceToHost, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  }
+  return e;
 }
 
 cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out) {
