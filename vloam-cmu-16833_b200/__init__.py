@@ -133,8 +133,27 @@ def lib():
     return _lib
 
 
+def _prefer_bundled_nccl() -> None:
+    """The library binds NCCL at run time.  When the interpreter has a pip-installed NCCL (the copy PyTorch loads), name it in
+    VLOAM_NCCL_LIB so both end up on the same libnccl.so.2 whichever is loaded first; a system copy loaded first would
+    otherwise satisfy PyTorch's dependency by soname and may be too old for it."""
+    if os.environ.get("VLOAM_NCCL_LIB"):
+        return
+    import importlib.util
+    try:
+        spec = importlib.util.find_spec("nvidia.nccl")
+    except (ImportError, ValueError):
+        spec = None
+    for d in (spec.submodule_search_locations if spec else []):
+        cand = os.path.join(d, "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            os.environ["VLOAM_NCCL_LIB"] = cand
+            return
+
+
 def shard_nccl_unique_id() -> bytes:
     """A fresh 128-byte ncclUniqueId (rank 0 creates it, the caller broadcasts it)."""
+    _prefer_bundled_nccl()
     buf = C.create_string_buffer(128)
     rc = lib().vloam_shard_nccl_unique_id(buf)
     if rc != VLOAM_OK:
@@ -339,6 +358,7 @@ class LidarOdometryMapping:
     def shard_nccl_init(self, rank: int, world: int, unique_id: bytes):
         """Point-sharded streams with the exchange done by ncclAllReduce (collective over the group)."""
         assert len(unique_id) == 128
+        _prefer_bundled_nccl()
         self.ctx.check(lib().vloam_shard_nccl_init(self._h, rank, world, unique_id))
 
     def shard_nccl_destroy(self):

@@ -81,11 +81,15 @@ NcclApi* nccl_api() {
   static bool tried = false;
   if (!tried) {
     tried = true;
+    // 1. the libnccl the process already carries (a framework loaded earlier), 2. VLOAM_NCCL_LIB, 3. the system's.
+    // A process that loads a framework with its own NCCL *later* must point VLOAM_NCCL_LIB at that copy: the dynamic loader
+    // resolves the framework's dependency by soname to whichever libnccl.so.2 came first (the Python mirror does this).
+    api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
     const char* names[] = {getenv("VLOAM_NCCL_LIB"), "libnccl.so.2", "libnccl.so"};
     for (const char* n : names) {
-      if (!n || !*n) continue;
-      api.lib = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
       if (api.lib) break;
+      if (!n || !*n) continue;
+      api.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL);
     }
     if (api.lib) {
       api.GetUniqueId = reinterpret_cast<int (*)(void*)>(dlsym(api.lib, "ncclGetUniqueId"));

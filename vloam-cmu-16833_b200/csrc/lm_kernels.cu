@@ -204,10 +204,13 @@ __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf
   const unsigned* keys = cur ? kB : kA;
   const unsigned* vals = cur ? vB : vA;
   // Segment heads -> centroid of (x, y, z, intensity), summed in ascending input order, divided by float(n).
-  // A warp takes 32 consecutive sorted entries at a time: every lane loads its own point (independent gathers, one
-  // latency per window instead of one per point), then each head lane adds the points of its voxel strictly left to
-  // right, fetching them from the following lanes (this window or the next, already in registers) by shuffle.
+  // Pass 1: heads per 32-entry window -> exclusive prefix; pass 2: the sorted position of every voxel's first entry;
+  // pass 3: one THREAD per voxel adds its run strictly left to right (the float sum is order-dependent, so a voxel is a
+  // serial chain, but the chains of 32 neighbouring voxels run side by side in a warp).  The first version walked the
+  // windows with a head lane pulling its run out of the other lanes by shuffle: every window then costs as many rounds as
+  // its longest run with a quarter of the lanes working — 53 % of the kernel's instructions (ncu, profiles/r02h).
   unsigned* winHeads = cur ? kA : kB;                 // the sort's spare key buffer: heads per window -> exclusive prefix
+  unsigned* headPos = cur ? vA : vB;                  // the sort's spare value buffer: first sorted position of every voxel
   const int nwin = (n + 31) >> 5;
   for (int v = w; v < nwin; v += 32) {
     const int q = v * 32 + l;
@@ -226,62 +229,33 @@ __device__ int cta_voxel_filter(const float4* __restrict__ in, int n, float leaf
   }
   const int total = S.total;
   __syncthreads();
+  for (int v = w; v < nwin; v += 32) {
+    const int q = v * 32 + l;
+    const bool head = q < n && (q == 0 || keys[q] != keys[q - 1]);
+    const unsigned hm = __ballot_sync(0xffffffffu, head);
+    if (head) headPos[(int)winHeads[v] + __popc(hm & ((1u << l) - 1u))] = (unsigned)q;
+  }
+  __syncthreads();
   int inside = 1;
-  {
-    const int perw = (nwin + 31) / 32;
-    const int v0 = min(w * perw, nwin), v1 = min(v0 + perw, nwin);
-    float4 p0 = make_float4(0.f, 0.f, 0.f, 0.f), p1;
-    unsigned k0 = 0, bnd0 = 0xffffffffu, hd0 = 0, bnd1, hd1;
-    auto load_window = [&](int u, float4& p, unsigned& k, unsigned& bnd, unsigned& hd) {
-      const int q = u * 32 + l;
-      const bool ok = q < n;
-      k = ok ? keys[q] : 0u;
-      const bool head = ok && (q == 0 || keys[q - 1] != k);
-      p = ok ? in[vals[q]] : make_float4(0.f, 0.f, 0.f, 0.f);
-      hd = __ballot_sync(0xffffffffu, head);
-      bnd = hd | ~__ballot_sync(0xffffffffu, ok);       // a run ends at the next head or at the end of the data
-    };
-    if (v0 < v1) load_window(v0, p0, k0, bnd0, hd0);
-    for (int v = v0; v < v1; ++v) {
-      unsigned k1;
-      load_window(v + 1, p1, k1, bnd1, hd1);
-      const bool head = (hd0 >> l) & 1u;
-      // run length of the voxel starting at this lane, seen through the 64-entry window pair
-      const unsigned long long Bm = (unsigned long long)bnd0 | ((unsigned long long)bnd1 << 32);
-      const unsigned long long rest = Bm >> (l + 1);
-      const bool open = rest == 0ull;                    // no boundary in sight: the run leaves the window pair
-      int len = head ? (open ? 64 - l : (int)__ffsll((long long)rest)) : 0;
-      const int maxlen = __reduce_max_sync(0xffffffffu, len);
-      float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
-      sx = __fadd_rn(sx, p0.x); sy = __fadd_rn(sy, p0.y); sz = __fadd_rn(sz, p0.z); si = __fadd_rn(si, p0.w);
-      for (int j = 1; j < maxlen; ++j) {
-        // entry l + j lives in lane (l + j) & 31 of this window (if l + j < 32) or of the next one; lane s is asked
-        // for its current-window point by reader s - j and for its next-window point by reader s + 32 - j, never both
-        const bool curw = l >= j;
-        const int src = (l + j) & 31;
-        const float gx = __shfl_sync(0xffffffffu, curw ? p0.x : p1.x, src);
-        const float gy = __shfl_sync(0xffffffffu, curw ? p0.y : p1.y, src);
-        const float gz = __shfl_sync(0xffffffffu, curw ? p0.z : p1.z, src);
-        const float gi = __shfl_sync(0xffffffffu, curw ? p0.w : p1.w, src);
-        if (j < len) { sx = __fadd_rn(sx, gx); sy = __fadd_rn(sy, gy); sz = __fadd_rn(sz, gz); si = __fadd_rn(si, gi); }
-      }
-      if (head) {
-        if (open) {   // rare: more than 64 - l points of one voxel; finish from memory
-          for (int qq = v * 32 + 64; qq < n && keys[qq] == k0; ++qq) {
-            const float4 pp = in[vals[qq]];
-            sx = __fadd_rn(sx, pp.x); sy = __fadd_rn(sy, pp.y); sz = __fadd_rn(sz, pp.z); si = __fadd_rn(si, pp.w);
-            ++len;
-          }
-        }
-        const float nf = (float)len;
-        const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
-        // the voxel's lattice coordinates are those of its first member, this lane's own point
-        if (floorf(__fmul_rn(c.x, inv)) != floorf(__fmul_rn(p0.x, inv)) || floorf(__fmul_rn(c.y, inv)) != floorf(__fmul_rn(p0.y, inv)) ||
-            floorf(__fmul_rn(c.z, inv)) != floorf(__fmul_rn(p0.z, inv))) inside = 0;
-        out[(int)winHeads[v] + __popc(hd0 & ((1u << l) - 1u))] = c;
-      }
-      p0 = p1; k0 = k1; bnd0 = bnd1; hd0 = hd1;
+  for (int v = threadIdx.x; v < total; v += 1024) {
+    const int q0 = (int)headPos[v], q1 = v + 1 < total ? (int)headPos[v + 1] : n;
+    const float4 first = in[vals[q0]];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    sx = __fadd_rn(sx, first.x); sy = __fadd_rn(sy, first.y); sz = __fadd_rn(sz, first.z); si = __fadd_rn(si, first.w);
+    for (int q = q0 + 1; q < q1; q += 4) {             // four gathers in flight, added in order
+      float4 pp[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (q + u < q1) pp[u] = in[vals[q + u]];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (q + u < q1) { sx = __fadd_rn(sx, pp[u].x); sy = __fadd_rn(sy, pp[u].y); sz = __fadd_rn(sz, pp[u].z); si = __fadd_rn(si, pp[u].w); }
     }
+    const float nf = (float)(q1 - q0);
+    const float4 c = make_float4(__fdiv_rn(sx, nf), __fdiv_rn(sy, nf), __fdiv_rn(sz, nf), __fdiv_rn(si, nf));
+    // the voxel's lattice coordinates are those of its first member
+    if (floorf(__fmul_rn(c.x, inv)) != floorf(__fmul_rn(first.x, inv)) || floorf(__fmul_rn(c.y, inv)) != floorf(__fmul_rn(first.y, inv)) ||
+        floorf(__fmul_rn(c.z, inv)) != floorf(__fmul_rn(first.z, inv))) inside = 0;
+    out[v] = c;
   }
   *fixedPoint = __syncthreads_and(inside);
   return total;
@@ -300,18 +274,25 @@ __device__ __forceinline__ float4* stream_map(const MapPools& pools, const LMSta
   return (st.cur[kind] ? pools.p[1] : pools.p[0]) + ((size_t)b * 2 + kind) * mapCap;
 }
 
-// lm_prepare: grid (B), block 256.  Table ping-pong: reads tables `src`, writes the shifted tables to `dst`.
+// lm_prepare: grid (B), block kPrepThreads.  Table ping-pong: reads tables `src`, writes the shifted tables to `dst`.
 // Also: the valid-cube list, the cube -> valid-entry lists the association walks, and column-table slots for the valid
 // cubes that have no usable column index yet (built next by lm_index_build).
-__global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, const LOState* __restrict__ lo,
-                                                   const CubeTables src, const CubeTables dst, short* __restrict__ entryHeadAll,
-                                                   int resetValid) {
+// The kernel is a chain of short dependent steps on one stream's tables, i.e. latency: the table copy runs 1024 wide, the
+// per-valid-cube look-ups are fetched by one thread per (kind, entry) into shared memory, and only the two order-dependent
+// loops (prefix of the sub-map, slot hand-out) stay serial — on shared memory.  (The first version did the look-ups in the
+// serial loops: ~300 dependent global loads, two thirds of the kernel's 67 us.)
+constexpr int kPrepThreads = 1024;
+__global__ void __launch_bounds__(kPrepThreads) lm_prepare(LMState* __restrict__ stAll, const LOState* __restrict__ lo,
+                                                            const CubeTables src, const CubeTables dst, short* __restrict__ entryHeadAll,
+                                                            int resetValid) {
   const int b = blockIdx.x;
   LMState& st = stAll[b];
   short* entryHead = entryHeadAll + (size_t)b * kCubes;
   __shared__ int sh[3];
   __shared__ int center[3];
-  __shared__ int s_gc[2];
+  __shared__ int s_gc[2], s_vn, s_dup, s_total[2];
+  __shared__ int s_vind[kMaxValid], s_cnt[2][kMaxValid], s_tab[2][kMaxValid];
+  __shared__ unsigned char s_head[kMaxValid];
   if (threadIdx.x == 0) {
     if (resetValid) st.validNum = 0;  // LaserMapping::reset (:127-131)
     st.error = 0;                     // error bits describe one scan (the sticky copy is errorEver)
@@ -335,12 +316,27 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
     while (cK >= kCubeD - 3) { cK--; st.cenD--; sK--; }
     sh[0] = sI; sh[1] = sJ; sh[2] = sK;
     center[0] = cI; center[1] = cJ; center[2] = cK;
+    // :404-420 valid cubes in the reference's loop order
+    int vn = st.validNum;
+    const int vn0 = vn;
+    for (int i = cI - 2; i <= cI + 2; i++)
+      for (int j = cJ - 2; j <= cJ + 2; j++)
+        for (int k = cK - 1; k <= cK + 1; k++)
+          if (i >= 0 && i < kCubeW && j >= 0 && j < kCubeH && k >= 0 && k < kCubeD && vn < kMaxValid)
+            st.validInd[vn++] = i + kCubeW * j + kCubeW * kCubeH * k;
+    st.validNum = vn;
+    s_vn = vn;
+    for (int v = 0; v < vn; ++v) s_vind[v] = st.validInd[v];
+    // cube -> entries of the valid list naming it, ascending.  One entry per cube unless the caller skipped reset()
+    // (the list then keeps growing and names cubes twice); only that case needs the chained insertion below.
+    for (int v = 0; v < vn; ++v) { st.entryNext[v] = -1; s_head[v] = 1; }
+    s_dup = vn0 > 0 ? 1 : 0;
   }
   __syncthreads();
   const int sI = sh[0], sJ = sh[1], sK = sh[2];
   for (int kind = 0; kind < 2; ++kind) {
     const size_t tb = ((size_t)b * 2 + kind) * kCubes;
-    for (int c = threadIdx.x; c < kCubes; c += 256) {
+    for (int c = threadIdx.x; c < kCubes; c += kPrepThreads) {
       const int i = c % kCubeW, j = (c / kCubeW) % kCubeH, k = c / (kCubeW * kCubeH);
       const int si = i - sI, sj = j - sJ, sk = k - sK;  // new[i] = old[i - shift]; wrapped planes are cleared
       int o = 0, n = 0, cp = 0, fx = 0, tbs = -1;        // (a cleared cube's slab and table slot are reclaimed later)
@@ -351,55 +347,64 @@ __global__ void __launch_bounds__(256) lm_prepare(LMState* __restrict__ stAll, c
       dst.off[tb + c] = o; dst.cnt[tb + c] = n; dst.cap[tb + c] = cp; dst.fix[tb + c] = fx; dst.tab[tb + c] = n > 0 ? tbs : -1;
     }
   }
-  for (int c = threadIdx.x; c < kCubes; c += 256) entryHead[c] = -1;
+  for (int c = threadIdx.x; c < kCubes; c += kPrepThreads) entryHead[c] = -1;
   __syncthreads();
+  const int vn = s_vn;
   if (threadIdx.x == 0) {
-    // :404-420 valid cubes in the reference's loop order
-    const int cI = center[0], cJ = center[1], cK = center[2];
-    int vn = st.validNum;
-    for (int i = cI - 2; i <= cI + 2; i++)
-      for (int j = cJ - 2; j <= cJ + 2; j++)
-        for (int k = cK - 1; k <= cK + 1; k++)
-          if (i >= 0 && i < kCubeW && j >= 0 && j < kCubeH && k >= 0 && k < kCubeD && vn < kMaxValid)
-            st.validInd[vn++] = i + kCubeW * j + kCubeW * kCubeH * k;
-    st.validNum = vn;
-    // cube -> entries of the valid list naming it (one entry unless the caller skipped reset()), ascending
-    for (int v = vn - 1; v >= 0; --v) { const int c = st.validInd[v]; st.entryNext[v] = entryHead[c]; entryHead[c] = (short)v; }
-    for (int kind = 0; kind < 2; ++kind) {
-      const size_t tb = ((size_t)b * 2 + kind) * kCubes;
-      int acc = 0, need = 0;
-      for (int v = 0; v < vn; ++v) {
-        const int c = st.validInd[v];
-        st.validPrefix[kind][v] = acc; acc += dst.cnt[tb + c];
-        if (entryHead[c] == v && dst.cnt[tb + c] > 0 && dst.tab[tb + c] < 0) ++need;
-      }
-      st.validPrefix[kind][vn] = acc;
-      st.fromMapNum[kind] = acc;
-      s_gc[kind] = st.tabEnd[kind] + need > st.tabLimit ? 1 : 0;   // out of table slots: drop every index of this kind, start over
+    if (s_dup) {   // duplicates possible: literal chained insertion (head = the smallest entry naming the cube)
+      for (int v = vn - 1; v >= 0; --v) { const int c = s_vind[v]; st.entryNext[v] = entryHead[c]; entryHead[c] = (short)v; }
+      for (int v = 0; v < vn; ++v) s_head[v] = entryHead[s_vind[v]] == v ? 1 : 0;
+    } else {
+      for (int v = 0; v < vn; ++v) entryHead[s_vind[v]] = (short)v;
     }
-    st.solved = (st.fromMapNum[0] > 10 && st.fromMapNum[1] > 50) ? 1 : 0;  // :448
-    st.trace[0].n_records = st.trace[1].n_records = 0;
-    st.trace[0].n_corner = st.trace[0].n_plane = st.trace[1].n_corner = st.trace[1].n_plane = 0;
+  }
+  // the shifted tables' rows of the valid cubes, one thread per (kind, entry)
+  if (threadIdx.x < 2 * kMaxValid) {
+    const int kind = threadIdx.x / kMaxValid, v = threadIdx.x % kMaxValid;
+    if (v < vn) {
+      const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+      s_cnt[kind][v] = dst.cnt[tb + s_vind[v]];
+      s_tab[kind][v] = dst.tab[tb + s_vind[v]];
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2) {
+    const int kind = threadIdx.x;
+    int acc = 0, need = 0;
+    for (int v = 0; v < vn; ++v) {
+      st.validPrefix[kind][v] = acc; acc += s_cnt[kind][v];
+      if (s_head[v] && s_cnt[kind][v] > 0 && s_tab[kind][v] < 0) ++need;
+    }
+    st.validPrefix[kind][vn] = acc;
+    st.fromMapNum[kind] = acc;
+    s_gc[kind] = st.tabEnd[kind] + need > st.tabLimit ? 1 : 0;   // out of table slots: drop every index of this kind, start over
+    s_total[kind] = acc;
   }
   __syncthreads();
   for (int kind = 0; kind < 2; ++kind)
-    if (s_gc[kind]) for (int c = threadIdx.x; c < kCubes; c += 256) dst.tab[((size_t)b * 2 + kind) * kCubes + c] = -1;
+    if (s_gc[kind]) for (int c = threadIdx.x; c < kCubes; c += kPrepThreads) dst.tab[((size_t)b * 2 + kind) * kCubes + c] = -1;
   __syncthreads();
   if (threadIdx.x < 2) {
     const int kind = threadIdx.x;
     const size_t tb = ((size_t)b * 2 + kind) * kCubes;
+    const int solved = (s_total[0] > 10 && s_total[1] > 50) ? 1 : 0;  // :448
     int te = s_gc[kind] ? 0 : st.tabEnd[kind], nb = 0;
-    if (st.solved)
-      for (int v = 0; v < st.validNum; ++v) {
-        const int c = st.validInd[v];
-        if (entryHead[c] != v || dst.cnt[tb + c] == 0 || dst.tab[tb + c] >= 0) continue;
+    if (solved)
+      for (int v = 0; v < vn; ++v) {
+        if (!s_head[v] || s_cnt[kind][v] == 0 || (!s_gc[kind] && s_tab[kind][v] >= 0)) continue;
+        const int c = s_vind[v];
         dst.tab[tb + c] = te++;               // <= kMaxValid new slots after a reset of the slot counter: always fits
         st.buildList[kind][nb++] = c;
       }
     st.tabEnd[kind] = te;
     st.buildNum[kind] = nb;
     st.counters[kCntIndexedCorner + kind] += nb;
-    if (kind == 0) { st.counters[kCntScans]++; st.counters[kCntSolved] += st.solved; }
+    if (kind == 0) {
+      st.solved = solved;
+      st.trace[0].n_records = st.trace[1].n_records = 0;
+      st.trace[0].n_corner = st.trace[0].n_plane = st.trace[1].n_corner = st.trace[1].n_plane = 0;
+      st.counters[kCntScans]++; st.counters[kCntSolved] += solved;
+    }
   }
 }
 
@@ -775,6 +780,9 @@ __device__ __forceinline__ void lm_knn_body(const LMState* __restrict__ stAll, c
     // Only a candidate closer than 1 m can matter (a query whose 5th neighbour is not within 1 m is dropped, :479 / :547,
     // and then every true neighbour is), and none farther than the current 5th best.  The distance is
     // (dx^2 + dy^2) + dz^2 in float: never below dz^2, so the z term alone prunes first.
+    // (Tried and rejected: noting passing candidates in a per-thread shared-memory list and forming the top-5 at the end of
+    // the query, to keep the ~45-instruction insertion out of the candidate loop: 185 us instead of 122 — without the
+    // shrinking threshold far more candidates reach the distance computation and the list.)
     auto consider = [&](const float4 tp, unsigned gBase, int pos) {
       const float dz = __fsub_rn(sz, tp.z);
       if (__float_as_uint(__fmul_rn(dz, dz)) > wbits) return;
@@ -1139,28 +1147,42 @@ __global__ void __launch_bounds__(1024) lm_insert_keys(LMState* __restrict__ stA
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (ka[mid] <= c) lo = mid + 1; else hi = mid; }
     s_headEnd[h] = lo;
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
+  // the table rows the serial list build below needs, fetched side by side (it used to read them one dependent global load
+  // at a time: a quarter of the kernel)
+  __shared__ int s_headCnt[kMaxWork], s_validCube[kMaxValid], s_validCnt[kMaxValid];
+  __shared__ unsigned char s_validOpen[kMaxValid];
+  {
     const int* cnt = cubeCnt + ((size_t)b * 2 + kind) * kCubes;
     const int* fix = cubeFix + ((size_t)b * 2 + kind) * kCubes;
+    for (int h = threadIdx.x; h < nh; h += 1024) s_headCnt[h] = cnt[s_headCube[h]];
+    for (int v = threadIdx.x; v < st.validNum; v += 1024) {
+      const int c = st.validInd[v];
+      const int n0 = cnt[c];
+      s_validCube[v] = c; s_validCnt[v] = n0; s_validOpen[v] = (n0 != 0 && !fix[c]) ? 1 : 0;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
     if (s_nh > kMaxWork) atomicOr(&st.error, kLmErrWorkList);
-    int wn = 0;
+    const int vnum = st.validNum;
+    int wn = 0, in0 = 0;
     for (int h = 0; h < nh; ++h) {                 // cubes that receive points (distinct by construction)
       const int c = s_headCube[h];
       s_listed[c >> 5] |= 1u << (c & 31);
+      const int nNew = s_headEnd[h] - s_headStart[h];
       st.workCube[kind][wn] = c; st.workFilter[kind][wn] = (s_validBits[c >> 5] >> (c & 31)) & 1u;
-      st.workNew0[kind][wn] = s_headStart[h]; st.workNewN[kind][wn] = s_headEnd[h] - s_headStart[h]; ++wn;
+      st.workNew0[kind][wn] = s_headStart[h]; st.workNewN[kind][wn] = nNew;
+      st.workIn0[kind][wn] = in0; in0 += s_headCnt[h] + nNew; ++wn;
     }
-    for (int v = 0; v < st.validNum; ++v) {        // valid cubes whose filter result is not known to be a fixed point
-      const int c = st.validInd[v];
+    for (int v = 0; v < vnum; ++v) {               // valid cubes whose filter result is not known to be a fixed point
+      if (!s_validOpen[v]) continue;
+      const int c = s_validCube[v];
       if ((s_listed[c >> 5] >> (c & 31)) & 1u) continue;
-      if (cnt[c] == 0 || fix[c]) continue;
       if (wn >= kMaxWork) { atomicOr(&st.error, kLmErrWorkList); break; }
       s_listed[c >> 5] |= 1u << (c & 31);
-      st.workCube[kind][wn] = c; st.workFilter[kind][wn] = 1; st.workNew0[kind][wn] = 0; st.workNewN[kind][wn] = 0; ++wn;
+      st.workCube[kind][wn] = c; st.workFilter[kind][wn] = 1; st.workNew0[kind][wn] = 0; st.workNewN[kind][wn] = 0;
+      st.workIn0[kind][wn] = in0; in0 += s_validCnt[v]; ++wn;
     }
-    int in0 = 0;
-    for (int u = 0; u < wn; ++u) { st.workIn0[kind][u] = in0; in0 += cnt[st.workCube[kind][u]] + st.workNewN[kind][u]; }
     st.workIn0[kind][wn] = in0;
     st.workNum[kind] = wn;
     st.counters[kCntWorkCorner + kind] += wn;
@@ -1286,9 +1308,11 @@ __global__ void __launch_bounds__(kMergeThreads) lm_refilter_merge(LMState* __re
   float4* dst = direct ? old : out;
   if (!direct) {
     // old point i moves up by the number of inserted runs placed at or before it (insPos is ascending)
+    // (a thread's i only grows, so its count is carried along instead of searched for every point: the searches were 39 %
+    // of the kernel's instructions)
+    int lo = 0;
     for (int i = tid; i < nOld; i += NT) {
-      int lo = 0, hi = inserted;
-      while (lo < hi) { const int mid = (lo + hi) >> 1; if (insPos[mid] <= i) lo = mid + 1; else hi = mid; }
+      while (lo < inserted && insPos[lo] <= i) ++lo;
       dst[i + lo] = old[i];
     }
     __syncthreads();
@@ -1681,7 +1705,7 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
   const float lineRes = (float)lm->p.mapping_line_resolution, planeRes = (float)lm->p.mapping_plane_resolution;
   static const bool noMerge = [] { const char* e = getenv("VLOAM_LM_NO_MERGE"); return e && e[0] == '1'; }();   // validation: always re-sort
   const int bitsLine = noMerge ? 0 : vox_axis_bits(lineRes), bitsPlane = noMerge ? 0 : vox_axis_bits(planeRes);
-  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, 256, 0, st>>>(lm->st, lo, T_s, T_d, lm->entryHead, lm->reset_valid ? 1 : 0));
+  VB_LAUNCH(prof, K_LM_PREPARE, st, lm_prepare<<<B, kPrepThreads, 0, st>>>(lm->st, lo, T_s, T_d, lm->entryHead, lm->reset_valid ? 1 : 0));
   lm->reset_valid = false;
   if (lm->snap)
     VB_LAUNCH(prof, K_LM_MISC, st, lm_snapshot_submap<<<dim3(256, 2, B), 256, 0, st>>>(lm->st, lm->cubeOff[td], pools, mapCap, lm->snap));

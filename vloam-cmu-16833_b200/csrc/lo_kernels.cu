@@ -265,16 +265,24 @@ __global__ void __launch_bounds__(1024) lo_build_grid(const SRHeader* __restrict
   // order (arbitrary inside a pair), so the ring-window pass of the search can jump to its rings instead of reading the
   // whole column.  The cloud is ring-major, so a ring pair is a contiguous index range; w carries the original index
   // (tie-breaks, result), the true ring and int(intensity), the "scan id" of the reference's window tests (:275, :285 ...).
+  // A ring pair rarely holds more than 1024 points, so a pair is one step of the CTA followed by a barrier: the load of the
+  // NEXT pair's point is issued before the barrier of the current one, so that a pair does not pay a full memory latency
+  // (measured: 78 -> 76 us per 64-stream launch; the 32 barriers and the shared-memory atomics are what remains).
+  auto place = [&](const float4 p, int j, int pr, int jm) {
+    const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
+    const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
+    const int pos = atomicAdd(&cells[iy * nx + ix], 1);
+    S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, j >= jm ? 2 * pr + 1 : 2 * pr, (int)p.w)));
+  };
+  float4 pn = make_float4(0.f, 0.f, 0.f, 0.f);
+  { const int j = s_ringStart[0] + tid; if (j < s_ringStart[2]) pn = T[j]; }
   for (int pr = 0; pr < kMaxRings / 2; ++pr) {
     const int j0 = s_ringStart[2 * pr], jm = s_ringStart[2 * pr + 1], j1 = s_ringStart[2 * pr + 2];
+    const float4 pc = pn;
+    if (pr + 1 < kMaxRings / 2) { const int j = j1 + tid; if (j < s_ringStart[2 * pr + 4]) pn = T[j]; }
     if (j1 <= j0) continue;                     // uniform: empty pair
-    for (int j = j0 + tid; j < j1; j += 1024) {
-      const float4 p = T[j];
-      const int ix = min(max(cell_coord(p.x, minx, inv_c), 0), nx - 1);
-      const int iy = min(max(cell_coord(p.y, miny, inv_c), 0), ny - 1);
-      const int pos = atomicAdd(&cells[iy * nx + ix], 1);
-      S[pos] = make_float4(p.x, p.y, p.z, __int_as_float(pack_index_ring(j, j >= jm ? 2 * pr + 1 : 2 * pr, (int)p.w)));
-    }
+    if (j0 + tid < j1) place(pc, j0 + tid, pr, jm);
+    for (int j = j0 + tid + 1024; j < j1; j += 1024) place(T[j], j, pr, jm);
     __syncthreads();
   }
   for (int j = s_ringStart[kMaxRings] + tid; j < n; j += 1024) {   // points past the last ring offset (foreign clouds only)
@@ -599,7 +607,7 @@ __global__ void __launch_bounds__(256, 8) lo_associate_occ8(VB_LO_ASSOC_ARGS) { 
 
 // ---------------------------------------------------------------------------------------------
 // lo_solve: grid (B), block 256.  One CTA solves one stream's pass.
-__global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdrCur, LOState* __restrict__ lo,
+__device__ __forceinline__ void lo_solve_body(const SRHeader* __restrict__ hdrCur, LOState* __restrict__ lo,
                                                  const float4* __restrict__ sharp, const float4* __restrict__ flat,
                                                  const float4* __restrict__ cornerLast, const float4* __restrict__ surfLast,
                                                  int cap, const int4* __restrict__ corr, int pass, int max_iterations,
@@ -715,6 +723,19 @@ __global__ void __launch_bounds__(256) lo_solve(const SRHeader* __restrict__ hdr
       for (int i = 0; i < 4; ++i) st.q_w[i] = qn[i];
     }
   }
+}
+
+#define VB_LO_SOLVE_ARGS                                                                                                       \
+  const SRHeader *__restrict__ hdrCur, LOState *__restrict__ lo, const float4 *__restrict__ sharp, const float4 *__restrict__ flat, \
+      const float4 *__restrict__ cornerLast, const float4 *__restrict__ surfLast, int cap, const int4 *__restrict__ corr, int pass, \
+      int max_iterations, int integrate, const ShardView sv
+// Two register budgets (as lm_solve): 212 registers, one CTA per SM, or <= 128 with two per SM (VLOAM_LO_SOLVE_REGS=128):
+// while a solve runs, the registers it leaves free decide how much of the other handles' kernels its SM can take.
+__global__ void __launch_bounds__(256) lo_solve(VB_LO_SOLVE_ARGS) {
+  lo_solve_body(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, max_iterations, integrate, sv);
+}
+__global__ void __launch_bounds__(256, 2) lo_solve_r128(VB_LO_SOLVE_ARGS) {
+  lo_solve_body(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass, max_iterations, integrate, sv);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -867,6 +888,7 @@ cudaError_t lo_prepare_device(int device) {
   cudaError_t e = cudaSetDevice(device);
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lo_build_grid, cudaFuncAttributeMaxDynamicSharedMemorySize, (kGridCap + 1) * (int)sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(lo_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(lo_solve_r128, cudaFuncAttributeMaxDynamicSharedMemorySize, kLoSolveDynSmem);
   return e;
 }
 
@@ -925,8 +947,13 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
     VB_LAUNCH(prof, K_LO_STEP, st, lo_gn_finish<<<(B + 127) / 128, 128, 0, st>>>(lo, B, pass, integrate, counts));
     return;
   }
-  VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
-                                                               max_iterations, integrate, sv));
+  static const bool regs128 = [] { const char* e = getenv("VLOAM_LO_SOLVE_REGS"); return e && atoi(e) == 128; }();
+  if (regs128)
+    VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve_r128<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
+                                                                      max_iterations, integrate, sv));
+  else
+    VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
+                                                                 max_iterations, integrate, sv));
 }
 
 }  // namespace vb
