@@ -71,3 +71,39 @@ def test_unanswered_peer_is_reported_not_hung(synth):
     a.ctx.synchronize()
     assert a.shard_status() != 0
     b.close(); a.close()        # a owns the context b borrows
+
+
+def _two_gpus():
+    import torch
+    return torch.cuda.is_available() and torch.cuda.device_count() >= 2
+
+
+@pytest.mark.parametrize("mode", ["peer", "nccl"])
+def test_point_sharded_two_processes(tmp_path, mode):
+    """The same split across two PROCESSES on two GPUs (torchrun): `peer` maps the other rank's exchange slots through CUDA IPC
+    and sums inside the running solve kernel over NVLink; `nccl` all-reduces the tile partials of the wide solve (odometry and
+    mapping).  Both ranks must end on bit-identical poses, equal to an unsharded handle's up to summation order."""
+    import os
+    import subprocess
+    import sys
+    if not _two_gpus():
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29531" if mode == "peer" else "29532", os.path.join(root, "tests", "workers", "shard_two_process.py"),
+           "--mode", mode, "--out", str(tmp_path)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-3000:]
+    r0, r1 = np.load(tmp_path / "rank0.npz"), np.load(tmp_path / "rank1.npz")
+    assert int(r0["shard_status"]) == 0 and int(r1["shard_status"]) == 0
+    for k in range(4):
+        for key in ("q_last_curr", "t_last_curr", "q_w_curr", "t_w_curr"):
+            a, b, ref = r0[f"lo_{key}_{k}"], r1[f"lo_{key}_{k}"], r0[f"ref_lo_{key}_{k}"]
+            assert np.array_equal(a, b), f"scan {k}: ranks disagree on {key}"
+            np.testing.assert_allclose(a, ref, atol=1e-9, err_msg=f"scan {k}: {key}")
+        for key in ("corner_correspondence", "plane_correspondence"):
+            assert np.array_equal(r0[f"lo_{key}_{k}"], r0[f"ref_lo_{key}_{k}"])
+        if mode == "nccl":
+            assert np.array_equal(r0[f"lm_q_{k}"], r1[f"lm_q_{k}"]) and np.array_equal(r0[f"lm_t_{k}"], r1[f"lm_t_{k}"])
+            np.testing.assert_allclose(r0[f"lm_t_{k}"], r0[f"ref_lm_t_{k}"], atol=1e-6)
+            np.testing.assert_allclose(np.abs(r0[f"lm_q_{k}"]), np.abs(r0[f"ref_lm_q_{k}"]), atol=1e-6)
