@@ -698,8 +698,9 @@ def run_ours(args, rank, world, local_rank):
     # same inputs, same number of steps -> both legs must end on identical poses
     same = bool(np.array_equal(pose_dev["t_w_curr"], pose_host["t_w_curr"]))
 
-    # The host -> device ceiling of this box for exactly these uploads (every rank at once, nothing else running): B copies
-    # of one 1.57 MB scan from the pinned pool per step.  e2e cannot beat it; it is printed beside e2e.
+    # The host -> device ceiling of this box for these uploads (every rank at once, nothing else running): first as B separate
+    # copies of one 1.57 MB scan from the pinned pool per step (one cudaMemcpyAsync per stream, what round 2 started with),
+    # then as contiguous copies of the same bytes.  e2e cannot beat the second; it is printed beside e2e.
     with torch.cuda.stream(stream):
         sink = torch.empty((B, cap, 3), dtype=torch.float32, device=dev)
         reps = 6
@@ -716,10 +717,26 @@ def run_ours(args, rank, world, local_rank):
         stream.wait_stream(side)
         b_.record(stream)
         barrier()
+        h2d_percopy_ms = max(all_ranks(a_.elapsed_time(b_) / reps))
+        # ... and as large contiguous copies of the same number of bytes: what the link delivers at best, and what the
+        # library's batched upload (cudaMemcpyBatchAsync) is measured to reach with one buffer per stream
+        flat_host, flat_dev = host_base.view(-1), sink.view(-1)
+        chunk = min(flat_host.numel(), flat_dev.numel())
+        barrier()
+        a_.record(stream)
+        for r in range(reps):
+            done_ = 0
+            while done_ < flat_dev.numel():
+                m_ = min(chunk, flat_dev.numel() - done_)
+                flat_dev[done_:done_ + m_].copy_(flat_host[:m_], non_blocking=True)
+                done_ += m_
+        b_.record(stream)
+        barrier()
         h2d_ms = max(all_ranks(a_.elapsed_time(b_) / reps))
         del sink
     h2d_ceiling_gbs = B * cap * 12 / (h2d_ms * 1e-3) / 1e9             # per GPU, all ranks copying at once
     h2d_ceiling_scans = (1 if point else world) * B / (h2d_ms * 1e-3)
+    h2d_percopy_gbs = B * cap * 12 / (h2d_percopy_ms * 1e-3) / 1e9
 
     # ---------------- leg 3: single-stream latency (batch = 1), context only
     lat_ms, lat = None, None
@@ -863,8 +880,11 @@ def run_ours(args, rank, world, local_rank):
                 "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same,
                 "h2d_gbs_per_gpu": h2d / (ms_e2e / args.steps * 1e-3) / 1e9,
                 "h2d_ceiling_gbs_per_gpu": h2d_ceiling_gbs, "h2d_ceiling_scans_per_s": h2d_ceiling_scans,
+                "h2d_one_memcpy_per_stream_gbs_per_gpu": h2d_percopy_gbs,
+                "upload": "one pinned host buffer per stream, all streams of a handle in one cudaMemcpyBatchAsync",
                 "ms_per_step_per_rank": [m_ / args.steps for m_ in ms_e2e_ranks], "host_numa": numa},
         "ms_per_step_per_rank": [m_ / args.steps for m_ in ms_ranks],
+        "exchange": exchange_report(args, world, do_map) if point else None,
         "gpu_launches": int(launches),
         "roofline": roof,
         "north_star_kernels": named,
@@ -888,6 +908,27 @@ def run_ours(args, rank, world, local_rank):
         "clocks": clocks,
     }
     print(json.dumps(line), flush=True)
+
+
+def exchange_report(args, world, do_map):
+    """Point-sharded layouts: what crosses NVLink per scan and stream.  One Levenberg-Marquardt evaluation exchanges the partial
+    normal equations (21 upper J'J + 6 J'r + cost = 28 doubles); a pass runs at most max_iterations + 1 evaluations."""
+    lo_eval = 2 * (4 + 1)
+    lm_eval = 2 * (args.lm_iterations + 1) if do_map else 0
+    if args.parallelism == "point":
+        payload = 8 * 28 * 8                                  # kGnTiles tile partials per stream, summed after the all-reduce
+        n_coll = lo_eval + lm_eval + 2                        # + the correspondence counts of the two odometry passes
+        return {"mechanism": "ncclAllReduce between the accumulate and step launches (laser odometry and laser mapping)",
+                "payload_bytes_per_stream_per_evaluation": payload, "collectives_per_scan_max": n_coll,
+                "payload_bytes_per_stream_per_scan_max": (lo_eval + lm_eval) * payload + 2 * 16,
+                "nvlink_bytes_per_rank_per_stream_per_scan_max": int(2 * (world - 1) / world * ((lo_eval + lm_eval) * payload + 2 * 16)),
+                "note": "ring all-reduce volume 2(N-1)/N x payload per rank; every collective carries all streams of the handle"}
+    payload = 28 * 8 + 8                                      # one partial + its sequence number per stream
+    return {"mechanism": "peer-memory loads inside the running solve kernel (laser odometry only)",
+            "payload_bytes_per_stream_per_evaluation": payload, "collectives_per_scan_max": 0,
+            "payload_bytes_per_stream_per_scan_max": lo_eval * payload,
+            "nvlink_bytes_per_rank_per_stream_per_scan_max": (world - 1) * lo_eval * payload,
+            "note": "every rank reads the other ranks' slots: (N-1) x payload per evaluation"}
 
 
 def main():

@@ -212,6 +212,35 @@ def test_pipelined_host_api_matches_blocking(synth):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("pinned", [True, False])
+def test_one_host_buffer_per_stream_upload(synth, pinned):
+    """vloam_scan_registration_ptrs: pinned buffers go to the driver as one batched copy (cudaMemcpyBatchAsync), pageable ones
+    as one cudaMemcpyAsync each; ragged counts; every stream's cloud and pose equal the slab upload's."""
+    import torch
+    import vloam_b200 as V
+    B, n_cols = 5, 256
+    streams = [synth.ScanStream(300 + i, n_cols=n_cols) for i in range(B)]
+    cap = 64 * n_cols
+    a = V.LidarOdometryMapping(batch=B, max_points=cap)
+    b = V.LidarOdometryMapping(batch=B, max_points=cap)
+    n = np.array([cap, cap - 700, cap, 0, cap - 64], np.int32)        # ragged, one empty stream
+    for k in range(3):
+        scans = np.stack([st.scan(k) for st in streams]).astype(np.float32)
+        bufs = [torch.from_numpy(scans[i].copy()) for i in range(B)]
+        if pinned:
+            bufs = [t.pin_memory() for t in bufs]
+        ptrs = np.array([t.data_ptr() for t in bufs], np.uint64)
+        a.reset(); a.scanRegistrationIO(scans, n_points=n); pa = a.laserOdometryIO()
+        b.reset(); b.scanRegistrationPtrs(ptrs, n, 3, keep=bufs); pb = b.laserOdometryIO()
+        for i in range(B):
+            if n[i]:
+                assert np.array_equal(a.cloud(V.CLOUD_FULL, stream=i), b.cloud(V.CLOUD_FULL, stream=i)), (k, i)
+        assert np.array_equal(a.stream_status(), b.stream_status())
+        for key in pa:
+            assert np.array_equal(pa[key], pb[key]), (k, key)
+    a.close(); b.close()
+
+
 def test_wire_formats_feed_scan_registration(synth, oracle, tmp_path):
     """a KITTI .bin record stream (4 floats per point) and a sensor_msgs/PointCloud2 payload with
     point_step = 32 bytes go into scanRegistrationIO as they are (no pcl::fromROSMsg copy, vloam_main_node.cpp:148) and

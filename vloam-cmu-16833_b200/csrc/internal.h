@@ -119,6 +119,7 @@ struct vloam_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   cudaStream_t copy_stream = nullptr;  // host->device uploads overlap the previous scan's kernels
+  bool batch_copy_unsupported = false;  // cudaMemcpyBatchAsync refused once: keep to per-stream copies
   cudaStream_t copy_stream2 = nullptr; // second upload queue: per-stream copies alternate between the two, so the DMA set-up of one
                                        // copy hides behind the transfer of another (a batch is up to a few hundred 1.5 MB copies)
   cudaEvent_t ev_copy2 = nullptr;
