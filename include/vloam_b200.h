@@ -293,6 +293,19 @@ int vloam_vo_solve(vloam_vo* h, const float* prev_uv, const float* curr_uv, cons
 int vloam_vo_solve_device_async(vloam_vo* h, const float* prev_uv_dev, const float* curr_uv_dev, const int* n_matches_dev,
                                 const double* init_dev, int remove_VO_outlier, int max_iterations);
 int vloam_vo_get_result(vloam_vo* h, double* out /* [batch][8] as vloam_vo_solve */);
+/* ImageUtil::detKeypoints with DetectorType::ShiTomasi   image_util.cpp:11-37 (the detector visual_odometry.cpp:34 selects):
+ * cv::goodFeaturesToTrack(img, max_corners = 1024, quality_level = 0.03, min_distance = 7.5, Mat(), blockSize = 5, false, 0.04)
+ * = the minimum-eigenvalue response of cv::cornerMinEigenVal(img, 5, 3), thresholded at quality_level * max, its 3 x 3 local
+ * maxima sorted by response, and the greedy pass that keeps a corner when no kept corner is closer than min_distance.
+ * images: host, [batch][height][width] bytes (8-bit grey, the cv::Mat rows packed).  corners_xy[batch][max_corners][2] =
+ * cv::Point2f (x, y) of the corners in OpenCV's order, n_corners[batch]; both may be NULL (results stay on the device:
+ * vloam_vo_get_corner_buffers).  The block size is the reference's 5.  VLOAM_E_CAPACITY: an image whose response has more
+ * local maxima than a quarter of its pixels (large plateaus of exactly equal response). */
+int vloam_vo_detect_corners(vloam_vo* h, const uint8_t* images, int height, int width, int max_corners, double quality_level,
+                            double min_distance, float* corners_xy, int* n_corners);
+/* The response map of the last detection (cv::cornerMinEigenVal), stream `stream`, row-major height x width floats. */
+int vloam_vo_get_corner_response(vloam_vo* h, int stream, float* out, size_t capacity_pixels);
+int vloam_vo_get_corner_buffers(vloam_vo* h, const float** corners_xy_dev, const int** n_corners_dev);
 /* ImageUtil::matchDescriptors   image_util.cpp:214-296, in the configuration VisualOdometry selects (visual_odometry.cpp:34-37):
  * cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) over 32-byte binary descriptors (cv::ORB) and the ratio test
  * `m[0].distance < ratio * m[1].distance` (ratio = 0.8, :277).  desc_query / desc_train: [batch][max_matches][32] bytes

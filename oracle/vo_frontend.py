@@ -1,9 +1,13 @@
-"""ORACLE — TEST INFRASTRUCTURE ONLY.  numpy restatement of the descriptor matching of the reference's visual odometry
-front end (/root/reference/src/visual_odometry/src/image_util.cpp:214-296 in the configuration visual_odometry.cpp:34-37
-selects: cv::BFMatcher(NORM_HAMMING), knnMatch k = 2, ratio test 0.8).
+"""ORACLE — TEST INFRASTRUCTURE ONLY.  numpy restatement of two stages of the reference's visual odometry front end
+(/root/reference/src/visual_odometry/src/image_util.cpp in the configuration visual_odometry.cpp:34-37 selects):
+  * key-point detection, image_util.cpp:5-37: cv::goodFeaturesToTrack(img, 1024, 0.03, 7.5, Mat(), 5, false, 0.04), i.e. the
+    Shi-Tomasi minimum-eigenvalue response (cv::cornerMinEigenVal) + threshold / 3x3 local maxima / sort / greedy spacing;
+  * descriptor matching, image_util.cpp:214-296: cv::BFMatcher(NORM_HAMMING), knnMatch k = 2, ratio test 0.8.
 
-PARITY PINNED: tests/golden/vo_frontend_cv2.npz holds the outputs of OpenCV itself (the reference's dependency, cv2 4.13)
-for the same calls; tests/test_vo_frontend.py checks this restatement against them bit for bit.
+PARITY PINNED: tests/golden/vo_frontend_cv2.npz and tests/golden/vo_detect_cv2.npz hold the outputs of OpenCV itself (the
+reference's dependency, cv2 4.13) for the same calls; tests/test_vo_frontend.py checks this restatement against them: matches
+and corner lists bit for bit, the response map bit for bit on > 99.99 % of the pixels (the rest differ in the last place:
+OpenCV's box filter keeps running double-precision sums per thread stripe, whose rounding depends on the stripe layout).
 """
 import numpy as np
 
@@ -40,3 +44,107 @@ def match_descriptors(d0, d1, ratio=0.8):
         if idx[q, 1] >= 0 and float(np.float32(dist[q, 0])) < ratio * float(np.float32(dist[q, 1])):
             out.append((q, int(idx[q, 0]), int(dist[q, 0])))
     return np.array(out, np.int32).reshape(-1, 3)
+
+
+# ------------------------------------------------------------------------------------------------ key-point detection
+def _fma(a, b, c):
+    """float32 fused multiply-add (the product of two float32 is exact in float64; one rounding to float64 before the final
+    rounding to float32 — adequate for the magnitudes here and checked against OpenCV's output)."""
+    return (np.float64(a) * np.float64(b) + np.float64(c)).astype(np.float32)
+
+
+def _reflect101(i, n):
+    """cv::BORDER_REFLECT_101 index map for i in [-n + 1, 2n - 2]."""
+    i = np.abs(i)
+    return np.where(i >= n, 2 * (n - 1) - i, i)
+
+
+def min_eigen_response(img, block=5):
+    """cv::cornerMinEigenVal(img, block, 3) for an 8-bit image (imgproc corner.cpp: cornerEigenValsVecs + calcMinEigenVal), with
+    the operation order of OpenCV 4.13's vectorised code path (what cv2 runs on AVX2 / AVX-512 hosts):
+      scale = 1 / (2^(3-1) * block * 255); Sobel kernels with the scale folded into the smoothing taps (s, 2s, s);
+      Dx = fma(s, r[y-1] + r[y+1], 2s * r[y])          with r = I[x+1] - I[x-1]   (exact)
+      Dy = row[y+1] - row[y-1]                         with row = fma(s, I[x+1], fma(2s, I[x], s * I[x-1])) — except in the last
+           W mod 32 columns, which OpenCV's scalar tail loop computes without fused operations;
+      (Dx^2, Dx Dy, Dy^2) box-summed over block x block in double precision (rows, then columns), rounded to float;
+      response = (a + c) - sqrt((a - c)^2 + b^2) with a = Sxx / 2, b = Sxy, c = Syy / 2, plain float operations."""
+    img = np.ascontiguousarray(img, np.uint8)
+    H, W = img.shape
+    sc = 1.0 / (4 * block * 255.0)
+    s1 = np.float32(sc)
+    s2 = np.float32(2) * s1
+    p = np.pad(img.astype(np.float32), 1, mode="reflect")
+    r = p[:, 2:] - p[:, :-2]
+    Dx = _fma(s1, r[:-2] + r[2:], (s2 * r[1:-1]).astype(np.float32))
+    c0, c1, c2 = p[:, :-2], p[:, 1:-1], p[:, 2:]
+    rows = _fma(s1, c2, _fma(s2, c1, (s1 * c0).astype(np.float32)))
+    tail = W - W % 32
+    if tail < W:
+        rows[:, tail:] = (((s1 * c0[:, tail:]).astype(np.float32) + (s2 * c1[:, tail:]).astype(np.float32)).astype(np.float32)
+                          + (s1 * c2[:, tail:]).astype(np.float32)).astype(np.float32)
+    Dy = (rows[2:] - rows[:-2]).astype(np.float32)
+    cov = np.stack([Dx * Dx, Dx * Dy, Dy * Dy], -1).astype(np.float32)
+    h = block // 2
+    pc = np.pad(cov.astype(np.float64), ((h, h), (h, h), (0, 0)), mode="reflect")
+    rs = np.zeros((H + 2 * h, W, 3))
+    for dx in range(block):
+        rs += pc[:, dx:dx + W]
+    acc = np.zeros((H, W, 3))
+    for dy in range(block):
+        acc += rs[dy:dy + H]
+    box = acc.astype(np.float32)
+    a = box[..., 0] * np.float32(0.5)
+    b = box[..., 1]
+    c = box[..., 2] * np.float32(0.5)
+    t = (a - c).astype(np.float32)
+    return ((a + c).astype(np.float32) - np.sqrt(((t * t).astype(np.float32) + (b * b).astype(np.float32)).astype(np.float32))).astype(np.float32)
+
+
+def select_corners(eig, max_corners=1024, quality=0.03, min_distance=7.5):
+    """The rest of cv::goodFeaturesToTrack (imgproc featureselect.cpp) on a response map: threshold at quality * max (to zero),
+    3 x 3 local maxima (value equal to its dilation) away from the one-pixel border, std::sort with greaterThanPtr — value
+    descending, equal values by descending address —, then the greedy pass that keeps a corner when no kept corner lies
+    closer than min_distance, stopped at max_corners.  Returns (n, 2) float32 (x, y)."""
+    eig = np.ascontiguousarray(eig, np.float32)
+    H, W = eig.shape
+    thr = np.float32(np.float64(eig.max()) * quality)
+    e = np.where(eig > thr, eig, np.float32(0))
+    pe = np.pad(e, 1, mode="constant", constant_values=-np.inf)
+    dil = np.max(np.stack([pe[dy:dy + H, dx:dx + W] for dy in range(3) for dx in range(3)]), 0)
+    m = (e != 0) & (e == dil)
+    m[0, :] = m[-1, :] = False
+    m[:, 0] = m[:, -1] = False
+    ys, xs = np.nonzero(m)
+    vals = e[ys, xs]
+    ofs = ys * W + xs
+    order = np.lexsort((-ofs, -vals.astype(np.float64)))
+    cell = int(np.rint(min_distance))                      # cvRound: half to even
+    md2 = min_distance * min_distance
+    gw, gh = (W + cell - 1) // cell, (H + cell - 1) // cell
+    grid = {}
+    out = []
+    for k in order:
+        y, x = int(ys[k]), int(xs[k])
+        xc, yc = x // cell, y // cell
+        good = True
+        for yy in range(max(0, yc - 1), min(gh - 1, yc + 1) + 1):
+            for xx in range(max(0, xc - 1), min(gw - 1, xc + 1) + 1):
+                for (px, py) in grid.get((yy, xx), ()):
+                    if (x - px) * (x - px) + (y - py) * (y - py) < md2:
+                        good = False
+                        break
+                if not good:
+                    break
+            if not good:
+                break
+        if good:
+            grid.setdefault((yc, xc), []).append((x, y))
+            out.append((x, y))
+            if len(out) == max_corners:
+                break
+    return np.array(out, np.float32).reshape(-1, 2)
+
+
+def good_features_to_track(img, max_corners=1024, quality=0.03, min_distance=7.5, block=5):
+    """ImageUtil::detKeypoints with DetectorType::ShiTomasi (image_util.cpp:11-37): corner coordinates (x, y) in pick order."""
+    return select_corners(min_eigen_response(img, block), max_corners, quality, min_distance)

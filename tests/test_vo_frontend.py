@@ -39,6 +39,51 @@ def test_opencv_still_reproduces_the_golden_vectors(golden):
         assert np.array_equal(good, golden[f"pair{p}_matches"])
 
 
+DETECT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vo_detect_cv2.npz")
+IMAGES = ("kitti", "small", "shapes")
+
+
+@pytest.fixture(scope="module")
+def detect_golden():
+    return np.load(DETECT)
+
+
+def _ulp_distance(a, b):
+    ia, ib = a.view(np.int32).astype(np.int64), b.view(np.int32).astype(np.int64)
+    return np.abs(ia - ib)
+
+
+def test_numpy_detection_matches_opencv(detect_golden):
+    """Shi-Tomasi detection (image_util.cpp:11-37) against cv2's own outputs: the response map bit for bit on > 99.99 % of the
+    pixels and within one unit in the last place elsewhere (module docstring of oracle/vo_frontend.py), the selected corners —
+    coordinates AND order — exactly; and the selection stage alone exactly, fed with cv2's response map."""
+    from oracle import vo_frontend as F
+    g = detect_golden
+    for name in IMAGES:
+        img = g[f"{name}_image"]
+        resp = F.min_eigen_response(img)
+        ref = g[f"{name}_response"] if name == "small" else g[f"{name}_response_rows"]
+        got = resp if name == "small" else resp[::8]
+        assert got.shape == ref.shape
+        ulp = _ulp_distance(got, ref)
+        assert (ulp == 0).mean() > 0.9999, (name, (ulp == 0).mean())
+        big = np.abs(ref) > 1e-3 * float(g[f"{name}_response_max"])      # (tiny responses are differences of nearly equal sums)
+        assert ulp[big].max() <= 1, (name, ulp[big].max())
+        assert np.float32(resp.max()) == g[f"{name}_response_max"]
+        corners = F.select_corners(resp)
+        assert np.array_equal(corners, g[f"{name}_corners"]), name
+    assert np.array_equal(F.select_corners(g["small_response"]), g["small_corners"])
+    assert len(g["shapes_corners"]) < 1024          # the quality threshold and the spacing decide here, not the cap
+
+
+def test_opencv_still_reproduces_the_detection_vectors(detect_golden):
+    cv2 = pytest.importorskip("cv2")
+    g = detect_golden
+    for name in IMAGES:
+        c = cv2.goodFeaturesToTrack(g[f"{name}_image"], 1024, 0.03, 7.5, None, blockSize=5, useHarrisDetector=False, k=0.04).reshape(-1, 2)
+        assert np.array_equal(c, g[f"{name}_corners"]), name
+
+
 @pytest.mark.gpu
 def test_cuda_matcher_hits_the_opencv_vectors(golden):
     """vo_bf_match (TMA-staged train descriptors, popcount 2-NN, ratio test, ordered compaction) == cv2, bit for bit: the raw
@@ -73,3 +118,27 @@ def test_cuda_matcher_hits_the_opencv_vectors(golden):
     from oracle import vo_frontend as F
     assert np.array_equal(one[2]["matches"], F.match_descriptors(d0[2][:5], d1[2][:2]))
     vo.close()
+
+
+@pytest.mark.gpu
+def test_cuda_detector_hits_the_opencv_vectors(detect_golden):
+    """vo_min_eigen / vo_corner_candidates / vo_select_corners == the numpy restatement bit for bit (response map included), and
+    == cv2.goodFeaturesToTrack on the committed images: the same corners in the same order."""
+    import vloam_b200 as V
+    from oracle import vo_frontend as F
+    g = detect_golden
+    for name in IMAGES:
+        img = g[f"{name}_image"]
+        vo = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+        flipped = np.ascontiguousarray(img[::-1, ::-1])                # second stream: another image of the same size
+        got = vo.detKeypoints(np.stack([img, flipped]))
+        for b, im in enumerate((img, flipped)):
+            resp = F.min_eigen_response(im)
+            assert np.array_equal(vo.corner_response(b).view(np.uint32), resp.view(np.uint32)), (name, b, "response map")
+            assert np.array_equal(got[b], F.select_corners(resp)), (name, b, "corners")
+        assert np.array_equal(got[0], g[f"{name}_corners"]), (name, "cv2 corners")
+        # other parameters: fewer corners, wider spacing (the greedy pass decides more), a flat image (no corner at all)
+        few = vo.detKeypoints(np.stack([img, np.full_like(img, 77)]), max_corners=100, quality_level=0.1, min_distance=20.0)
+        assert np.array_equal(few[0], F.good_features_to_track(img, 100, 0.1, 20.0))
+        assert few[1].shape == (0, 2)
+        vo.close()

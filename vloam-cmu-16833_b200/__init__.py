@@ -115,6 +115,8 @@ def lib():
             "vloam_vo_get_trace": [vp, C.c_int, c_dp, c_ip, c_dp],
             "vloam_vo_match_descriptors": [vp, vp, vp, vp, vp, vp, vp, C.c_double, vp, vp], "vloam_vo_get_knn": [vp, vp],
             "vloam_vo_get_match_buffers": [vp, pp, pp, pp], "vloam_vo_get_match_uv": [vp, vp, vp],
+            "vloam_vo_detect_corners": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp],
+            "vloam_vo_get_corner_response": [vp, C.c_int, vp, C.c_size_t], "vloam_vo_get_corner_buffers": [vp, pp, pp],
             "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
         }
         for name, args in sig.items():
@@ -657,6 +659,27 @@ class VisualOdometry:
         knn = np.zeros((B, M, 4), np.int32)
         self.ctx.check(lib().vloam_vo_get_knn(self._h, _ptr(knn)))
         return [{"matches": m[b, :nm[b]].copy(), "knn": knn[b, :nq[b]].copy()} for b in range(B)]
+
+    def detKeypoints(self, images, max_corners: int = 1024, quality_level: float = 0.03, min_distance: float = 7.5):
+        """ImageUtil::detKeypoints with DetectorType::ShiTomasi (image_util.cpp:11-37): images = (batch, H, W) or (H, W) uint8;
+        returns per stream the (n, 2) float32 corner coordinates (x, y) in cv::goodFeaturesToTrack's order."""
+        a = np.ascontiguousarray(images, np.uint8)
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape[0] == self.batch, a.shape
+        out = np.zeros((self.batch, max_corners, 2), np.float32)
+        n = np.zeros(self.batch, np.int32)
+        self.ctx.check(lib().vloam_vo_detect_corners(self._h, _ptr(a), a.shape[1], a.shape[2], max_corners, float(quality_level),
+                                                     float(min_distance), _ptr(out), _ptr(n)))
+        self._det_shape = a.shape[1:]
+        return [out[b, :n[b]].copy() for b in range(self.batch)]
+
+    def corner_response(self, stream: int = 0):
+        """cv::cornerMinEigenVal map of the last detKeypoints call, (H, W) float32."""
+        H, W = self._det_shape
+        r = np.zeros((H, W), np.float32)
+        self.ctx.check(lib().vloam_vo_get_corner_response(self._h, stream, _ptr(r), H * W))
+        return r
 
     def match_buffers(self):
         """(query_uv, train_uv, n_matches) device addresses of the last matchDescriptors call with keypoints."""

@@ -17,7 +17,7 @@ enum KernelId {
   K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT, K_LO_BUILD_GRID, K_LO_ASSOCIATE_BRUTE,
   K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_FIT, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_PLACE, K_LM_MISC,
   K_LO_ACCUMULATE, K_LO_STEP, K_LM_ACCUMULATE, K_LM_STEP,
-  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC, K_VO_MATCH,
+  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC, K_VO_MATCH, K_VO_DETECT,
   K_COUNT
 };
 const char* kernel_name(int id);
@@ -98,6 +98,17 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
 cudaError_t lm_get_pose(LMDevice* lm, cudaStream_t st, double* pose_out);
 cudaError_t lm_get_cloud(LMDevice* lm, cudaStream_t st, int stream, int which, float* out, int capacity, int* n_out);
 cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, const float* xyzi, int n);
+// vo_detect.cu: Shi-Tomasi key-point detection (image_util.cpp:11-37)
+struct VODetect;
+cudaError_t vo_detect_run(VODetect** d, Profiler* prof, cudaStream_t st, int B, const uint8_t* images, int H, int W, int maxCorners,
+                          double quality, double minDistance, int* status_out);
+cudaError_t vo_detect_read(VODetect* d, cudaStream_t st, float* corners, int* n);
+cudaError_t vo_detect_response(VODetect* d, cudaStream_t st, int stream, float* out, size_t pixels);
+const float* vo_detect_corners_device(const VODetect* d);
+const int* vo_detect_counts_device(const VODetect* d);
+int vo_detect_height(const VODetect* d);
+int vo_detect_width(const VODetect* d);
+void vo_detect_destroy(VODetect* d);
 cudaError_t lm_get_registered(LMDevice* lm, cudaStream_t st, int stream, const float4* cloud, int n, float* out, int capacity, int* n_out);
 cudaError_t lm_get_map_cloud(LMDevice* lm, cudaStream_t st, int stream, float* out, int capacity, int* n_out);
 cudaError_t lm_get_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int cube, float* out, int capacity, int* n_out);

@@ -1,0 +1,332 @@
+// vloam_b200 — key-point detection of the visual-odometry front end on the device:
+//   ImageUtil::detKeypoints with DetectorType::ShiTomasi (/root/reference/src/visual_odometry/src/image_util.cpp:11-37)
+//   = cv::goodFeaturesToTrack(img, 1024, 0.03, 7.5, Mat(), 5, false, 0.04).
+// OpenCV's algorithm (imgproc corner.cpp / featureselect.cpp), restated in oracle/vo_frontend.py and pinned there against cv2:
+//   vo_min_eigen         cornerMinEigenVal: 3 x 3 Sobel derivatives (scale folded into the smoothing taps), the products
+//                        (Dx^2, Dx Dy, Dy^2), a 5 x 5 box sum in double precision (rows, then columns), the smaller eigenvalue;
+//                        per-image maximum on the way out
+//   vo_corner_candidates threshold at quality * max, 3 x 3 local maxima away from the border -> unordered candidate list
+//   vo_select_corners    sort by (value descending, address descending), then the greedy spacing pass.  The reference walks
+//                        the sorted list serially ("keep a corner if no kept corner is closer than min_distance"); the same set
+//                        comes out of rounds in which every undecided candidate looks at the earlier candidates within the
+//                        radius: any of them kept -> dropped; all of them dropped -> kept; otherwise wait.  The earliest
+//                        undecided candidate is always decided, a round decides thousands at once.
+// Every float operation that OpenCV's vectorised path fuses or does not fuse is written with the explicit intrinsic, so the
+// response map carries the oracle's bits.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <vector>
+
+#include "../../include/vloam_b200.h"
+#include "common.cuh"
+#include "cta_sort.cuh"
+#include "internal.h"
+
+namespace vb {
+
+struct VODetect {
+  int B = 0, H = 0, W = 0, capCand = 0, cells = 0, maxCorners = 0;
+  uint8_t* img = nullptr;        // [B][H][W]
+  float* eig = nullptr;          // [B][H][W]
+  unsigned* maxBits = nullptr;   // [B] bits of the largest (positive) response
+  int* nCand = nullptr;          // [B]
+  unsigned *kA = nullptr, *vA = nullptr, *kB = nullptr, *vB = nullptr;   // [B][capCand] sort buffers
+  uint8_t* state = nullptr;      // [B][capCand] 0 undecided, 1 kept, 2 dropped
+  int* cellStart = nullptr;      // [B][cells + 1]
+  int* cellFill = nullptr;       // [B][cells]
+  int* cellItems = nullptr;      // [B][capCand] ranks, grouped by cell
+  float* corners = nullptr;      // [B][maxCorners][2]
+  int* nCorners = nullptr;       // [B]
+  int* status = nullptr;         // [B] 1 = candidate list overflowed
+};
+
+namespace {
+
+__device__ __forceinline__ int reflect101(int i, int n) {
+  if (n == 1) return 0;
+  while (i < 0 || i >= n) i = i < 0 ? -i : 2 * (n - 1) - i;
+  return i;
+}
+
+constexpr int kTileW = 64, kTileH = 16, kHalo = 2;                 // 5 x 5 box
+constexpr int kCovW = kTileW + 2 * kHalo, kCovH = kTileH + 2 * kHalo;
+
+// grid (ceil(W / 64), ceil(H / 16), B), block 256
+__global__ void __launch_bounds__(256) vo_min_eigen(const uint8_t* __restrict__ imgAll, int H, int W, float* __restrict__ eigAll,
+                                                    unsigned* __restrict__ maxBits) {
+  __shared__ float cov[3][kCovH][kCovW];
+  __shared__ double rs[3][kCovH][kTileW];
+  const int b = blockIdx.z;
+  const uint8_t* img = imgAll + (size_t)b * H * W;
+  const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
+  const float s1 = (float)(1.0 / (4.0 * 5.0 * 255.0));            // 1 / (2^(ksize-1) * block * 255), corner.cpp
+  const float s2 = __fmul_rn(2.0f, s1);
+  const int tail = W - W % 32;                                     // OpenCV's scalar tail columns: no fused operations
+  for (int e = threadIdx.x; e < kCovH * kCovW; e += 256) {
+    const int j = e / kCovW, i = e % kCovW;
+    const int y = reflect101(y0 - kHalo + j, H), x = reflect101(x0 - kHalo + i, W);   // the box filter's border: the product at the mirrored pixel
+    const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H), xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+    const float a00 = img[(size_t)ym * W + xm], a01 = img[(size_t)ym * W + x], a02 = img[(size_t)ym * W + xp];
+    const float a10 = img[(size_t)y * W + xm], a12 = img[(size_t)y * W + xp];
+    const float a20 = img[(size_t)yp * W + xm], a21 = img[(size_t)yp * W + x], a22 = img[(size_t)yp * W + xp];
+    // Dx: derivative (-1, 0, 1) along x (exact), smoothing (s, 2s, s) along y as fma(s, r[y-1] + r[y+1], 2s * r[y])
+    const float r0 = __fsub_rn(a02, a00), r1 = __fsub_rn(a12, a10), r2 = __fsub_rn(a22, a20);
+    const float dx = __fmaf_rn(s1, __fadd_rn(r0, r2), __fmul_rn(s2, r1));
+    // Dy: smoothing along x per row, then the difference of the rows below and above
+    float rowm, rowp;
+    if (x < tail) {
+      rowm = __fmaf_rn(s1, a02, __fmaf_rn(s2, a01, __fmul_rn(s1, a00)));
+      rowp = __fmaf_rn(s1, a22, __fmaf_rn(s2, a21, __fmul_rn(s1, a20)));
+    } else {
+      rowm = __fadd_rn(__fadd_rn(__fmul_rn(s1, a00), __fmul_rn(s2, a01)), __fmul_rn(s1, a02));
+      rowp = __fadd_rn(__fadd_rn(__fmul_rn(s1, a20), __fmul_rn(s2, a21)), __fmul_rn(s1, a22));
+    }
+    const float dy = __fsub_rn(rowp, rowm);
+    cov[0][j][i] = __fmul_rn(dx, dx); cov[1][j][i] = __fmul_rn(dx, dy); cov[2][j][i] = __fmul_rn(dy, dy);
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < 3 * kCovH * kTileW; e += 256) {
+    const int ch = e / (kCovH * kTileW), j = (e / kTileW) % kCovH, i = e % kTileW;
+    double s = (double)cov[ch][j][i];
+#pragma unroll
+    for (int d = 1; d < 5; ++d) s = __dadd_rn(s, (double)cov[ch][j][i + d]);
+    rs[ch][j][i] = s;
+  }
+  __syncthreads();
+  float vmax = 0.f;
+  for (int e = threadIdx.x; e < kTileH * kTileW; e += 256) {
+    const int j = e / kTileW, i = e % kTileW;
+    const int y = y0 + j, x = x0 + i;
+    if (y >= H || x >= W) continue;
+    float box[3];
+#pragma unroll
+    for (int ch = 0; ch < 3; ++ch) {
+      double s = rs[ch][j][i];
+#pragma unroll
+      for (int d = 1; d < 5; ++d) s = __dadd_rn(s, rs[ch][j + d][i]);
+      box[ch] = __double2float_rn(s);
+    }
+    // calcMinEigenVal: a = Sxx / 2, b = Sxy, c = Syy / 2; (a + c) - sqrt((a - c)^2 + b^2)
+    const float a = __fmul_rn(box[0], 0.5f), bb = box[1], c = __fmul_rn(box[2], 0.5f);
+    const float t = __fsub_rn(a, c);
+    const float v = __fsub_rn(__fadd_rn(a, c), __fsqrt_rn(__fadd_rn(__fmul_rn(t, t), __fmul_rn(bb, bb))));
+    eigAll[(size_t)b * H * W + (size_t)y * W + x] = v;
+    vmax = fmaxf(vmax, v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
+  if (lane_id() == 0 && vmax > 0.f) atomicMax(&maxBits[b], __float_as_uint(vmax));   // positive floats order like their bits
+}
+
+// grid (ceil(W / 32), ceil(H / 8), B), block (32, 8): threshold (to zero) + "equal to its 3 x 3 dilation", border excluded
+__global__ void __launch_bounds__(256) vo_corner_candidates(const float* __restrict__ eigAll, int H, int W, const unsigned* __restrict__ maxBits,
+                                                            double quality, int capCand, unsigned* __restrict__ keyOfs, unsigned* __restrict__ valBits,
+                                                            int* __restrict__ nCand, int* __restrict__ status) {
+  const int b = blockIdx.z;
+  const float* eig = eigAll + (size_t)b * H * W;
+  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const float thr = (float)((double)__uint_as_float(maxBits[b]) * quality);      // threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO)
+  bool cand = false;
+  float v = 0.f;
+  if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+    const float raw = eig[(size_t)y * W + x];
+    v = raw > thr ? raw : 0.f;
+    if (v != 0.f) {
+      cand = true;
+#pragma unroll
+      for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+        for (int dx = -1; dx <= 1; ++dx) {
+          const float n = eig[(size_t)(y + dy) * W + (x + dx)];
+          if ((n > thr ? n : 0.f) > v) cand = false;
+        }
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, cand);
+  if (m == 0u) return;
+  int base = 0;
+  if (threadIdx.x == __ffs(m) - 1) base = atomicAdd(&nCand[b], __popc(m));
+  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
+  if (cand) {
+    const int pos = base + __popc(m & ((1u << threadIdx.x) - 1u));
+    if (pos < capCand) {
+      // ascending sort of the complements = descending value, then descending address (greaterThanPtr, featureselect.cpp)
+      keyOfs[(size_t)b * capCand + pos] = (unsigned)(H * W - 1 - (y * W + x));
+      valBits[(size_t)b * capCand + pos] = ~__float_as_uint(v);
+    } else {
+      status[b] = 1;
+    }
+  }
+}
+
+// grid (B), block 1024, dynamic shared memory = sizeof(SortSmem)
+__global__ void __launch_bounds__(1024) vo_select_corners(int H, int W, int capCand, int cells, int gw, int gh, int cell, float minDist2,
+                                                          int maxCorners, const int* __restrict__ nCand, unsigned* kAall, unsigned* vAall,
+                                                          unsigned* kBall, unsigned* vBall, uint8_t* __restrict__ stateAll, int* __restrict__ cellStartAll,
+                                                          int* __restrict__ cellFillAll, int* __restrict__ cellItemsAll, float* __restrict__ cornersAll,
+                                                          int* __restrict__ nCorners) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int n = min(nCand[b], capCand);
+  unsigned* kA = kAall + (size_t)b * capCand; unsigned* vA = vAall + (size_t)b * capCand;
+  unsigned* kB = kBall + (size_t)b * capCand; unsigned* vB = vBall + (size_t)b * capCand;
+  volatile uint8_t* state = stateAll + (size_t)b * capCand;
+  int* cellStart = cellStartAll + (size_t)b * (cells + 1);
+  int* cellFill = cellFillAll + (size_t)b * cells;
+  int* cellItems = cellItemsAll + (size_t)b * capCand;
+  float* corners = cornersAll + (size_t)b * maxCorners * 2;
+  if (n == 0) { if (tid == 0) nCorners[b] = 0; return; }
+  // ---- order: address descending (unique, makes the unordered candidate list canonical), then value descending (stable)
+  int bitsOfs = 1;
+  while ((1ll << bitsOfs) < (long long)H * W) ++bitsOfs;
+  int cur = cta_radix_sort(kA, vA, kB, vB, n, bitsOfs, S);                       // (key = address', value = response')
+  unsigned* k1 = cur ? kB : kA; unsigned* v1 = cur ? vB : vA;
+  unsigned* k2 = cur ? kA : kB; unsigned* v2 = cur ? vA : vB;
+  __syncthreads();
+  cur = cta_radix_sort(v1, k1, v2, k2, n, 32, S);                                // (key = response', value = address')
+  const unsigned* ofsSorted = cur ? k2 : k1;                                      // rank -> complemented address
+  __syncthreads();
+  // ---- candidates grouped by 'cell' x 'cell' pixel cells (featureselect.cpp's grid; cell >= min_distance)
+  for (int c = tid; c <= cells; c += 1024) { cellStart[c] = 0; if (c < cells) cellFill[c] = 0; }
+  __syncthreads();
+  auto cell_of = [&](int r, int& x, int& y) {
+    const int ofs = H * W - 1 - (int)ofsSorted[r];
+    y = ofs / W; x = ofs - y * W;
+    return (y / cell) * gw + (x / cell);
+  };
+  for (int r = tid; r < n; r += 1024) { int x, y; atomicAdd(&cellStart[cell_of(r, x, y)], 1); state[r] = 0; }
+  __syncthreads();
+  {  // exclusive scan of the cell counts, a contiguous chunk per thread
+    const int per = (cells + 1023) / 1024;
+    const int c0 = min(tid * per, cells), c1 = min(c0 + per, cells);
+    int sum = 0;
+    for (int c = c0; c < c1; ++c) sum += cellStart[c];
+    int run = block_exclusive_scan1024(sum, S);
+    for (int c = c0; c < c1; ++c) { const int t = cellStart[c]; cellStart[c] = run; run += t; }
+    if (tid == 0) cellStart[cells] = n;
+  }
+  __syncthreads();
+  for (int r = tid; r < n; r += 1024) { int x, y; const int c = cell_of(r, x, y); cellItems[cellStart[c] + atomicAdd(&cellFill[c], 1)] = r; }
+  __syncthreads();
+  // ---- the greedy spacing pass as rounds (see the file header)
+  for (int round = 0; round < n + 1; ++round) {
+    int undecided = 0;
+    for (int r = tid; r < n; r += 1024) {
+      if (state[r] != 0) continue;
+      int x, y;
+      cell_of(r, x, y);
+      const int xc = x / cell, yc = y / cell;
+      bool dropped = false, wait = false;
+      for (int yy = max(yc - 1, 0); yy <= min(yc + 1, gh - 1) && !dropped; ++yy)
+        for (int xx = max(xc - 1, 0); xx <= min(xc + 1, gw - 1) && !dropped; ++xx) {
+          const int c = yy * gw + xx;
+          for (int t = cellStart[c]; t < cellStart[c + 1]; ++t) {
+            const int q = cellItems[t];
+            if (q >= r) continue;                                  // only earlier candidates can have been kept before this one
+            int qx, qy;
+            cell_of(q, qx, qy);
+            const float dx = (float)(x - qx), dy = (float)(y - qy);
+            if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < minDist2)) continue;
+            const uint8_t sq = state[q];
+            if (sq == 1) { dropped = true; break; }
+            if (sq == 0) wait = true;
+          }
+        }
+      if (dropped) state[r] = 2;
+      else if (!wait) state[r] = 1;
+      else undecided = 1;
+    }
+    if (!__syncthreads_or(undecided)) break;
+  }
+  // ---- the first maxCorners kept candidates, in rank order
+  {
+    const int per = (n + 1023) / 1024;
+    const int r0 = min(tid * per, n), r1 = min(r0 + per, n);
+    int cnt = 0;
+    for (int r = r0; r < r1; ++r) cnt += state[r] == 1 ? 1 : 0;
+    int pos = block_exclusive_scan1024(cnt, S);
+    const int total = S.total;
+    for (int r = r0; r < r1 && pos < maxCorners; ++r)
+      if (state[r] == 1) { int x, y; cell_of(r, x, y); corners[2 * pos] = (float)x; corners[2 * pos + 1] = (float)y; ++pos; }
+    if (tid == 0) nCorners[b] = min(total, maxCorners);
+  }
+}
+
+}  // namespace
+
+void vo_detect_destroy(VODetect* d) {
+  if (!d) return;
+  cudaFree(d->img); cudaFree(d->eig); cudaFree(d->maxBits); cudaFree(d->nCand); cudaFree(d->kA); cudaFree(d->vA); cudaFree(d->kB); cudaFree(d->vB);
+  cudaFree(d->state); cudaFree(d->cellStart); cudaFree(d->cellFill); cudaFree(d->cellItems); cudaFree(d->corners); cudaFree(d->nCorners); cudaFree(d->status);
+  delete d;
+}
+
+static cudaError_t vo_detect_alloc(VODetect** pd, int B, int H, int W, int cell, int maxCorners) {
+  VODetect* d = *pd;
+  const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
+  if (d && d->B == B && d->H == H && d->W == W && d->cells == gw * gh && d->maxCorners == maxCorners) return cudaSuccess;
+  vo_detect_destroy(d);
+  *pd = d = new VODetect();
+  d->B = B; d->H = H; d->W = W; d->cells = gw * gh; d->maxCorners = maxCorners;
+  d->capCand = (H * W + 3) / 4 + 32;      // 3 x 3 local maxima of distinct values cannot be denser; plateaus of equal values can (reported)
+  cudaError_t e = cudaSuccess;
+  auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 4); };
+  const size_t px = (size_t)B * H * W, nc = (size_t)B * d->capCand;
+  A((void**)&d->img, px); A((void**)&d->eig, px * sizeof(float)); A((void**)&d->maxBits, B * sizeof(unsigned)); A((void**)&d->nCand, B * sizeof(int));
+  A((void**)&d->kA, nc * 4); A((void**)&d->vA, nc * 4); A((void**)&d->kB, nc * 4); A((void**)&d->vB, nc * 4); A((void**)&d->state, nc);
+  A((void**)&d->cellStart, (size_t)B * (d->cells + 1) * sizeof(int)); A((void**)&d->cellFill, (size_t)B * d->cells * sizeof(int));
+  A((void**)&d->cellItems, nc * sizeof(int)); A((void**)&d->corners, (size_t)B * maxCorners * 2 * sizeof(float));
+  A((void**)&d->nCorners, B * sizeof(int)); A((void**)&d->status, B * sizeof(int));
+  if (e == cudaSuccess) e = cudaFuncSetAttribute(vo_select_corners, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  return e;
+}
+
+// images: host [B][H][W] (8-bit).  Results stay on the device until read with vo_detect_read.
+cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B, const uint8_t* images, int H, int W, int maxCorners,
+                          double quality, double minDistance, int* status_out) {
+  const int cell = (int)nearbyint(minDistance) > 0 ? (int)nearbyint(minDistance) : 1;     // cvRound (half to even)
+  cudaError_t e = vo_detect_alloc(pd, B, H, W, cell, maxCorners);
+  if (e != cudaSuccess) return e;
+  VODetect* d = *pd;
+  const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
+  e = cudaMemcpyAsync(d->img, images, (size_t)B * H * W, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->maxBits, 0, B * sizeof(unsigned), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->nCand, 0, B * sizeof(int), st);
+  if (e == cudaSuccess) e = cudaMemsetAsync(d->status, 0, B * sizeof(int), st);
+  if (e != cudaSuccess) return e;
+  VB_LAUNCH(prof, K_VO_DETECT, st, vo_min_eigen<<<dim3((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B), 256, 0, st>>>(d->img, H, W, d->eig, d->maxBits));
+  VB_LAUNCH(prof, K_VO_DETECT, st, vo_corner_candidates<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st>>>(d->eig, H, W, d->maxBits, quality, d->capCand, d->kA, d->vA, d->nCand, d->status));
+  VB_LAUNCH(prof, K_VO_DETECT, st, vo_select_corners<<<B, 1024, sizeof(SortSmem), st>>>(H, W, d->capCand, d->cells, gw, gh, cell, (float)(minDistance * minDistance), maxCorners,
+                                                                                      d->nCand, d->kA, d->vA, d->kB, d->vB, d->state, d->cellStart, d->cellFill,
+                                                                                      d->cellItems, d->corners, d->nCorners));
+  e = cudaGetLastError();
+  if (e != cudaSuccess) return e;
+  std::vector<int> stt(B);
+  e = cudaMemcpyAsync(stt.data(), d->status, B * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  if (e == cudaSuccess && status_out) { *status_out = 0; for (int b = 0; b < B; ++b) *status_out |= stt[b]; }
+  return e;
+}
+
+cudaError_t vo_detect_read(VODetect* d, cudaStream_t st, float* corners, int* n) {
+  cudaError_t e = cudaMemcpyAsync(corners, d->corners, (size_t)d->B * d->maxCorners * 2 * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(n, d->nCorners, d->B * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
+cudaError_t vo_detect_response(VODetect* d, cudaStream_t st, int stream, float* out, size_t pixels) {
+  const size_t px = (size_t)d->H * d->W;
+  cudaError_t e = cudaMemcpyAsync(out, d->eig + (size_t)stream * px, (pixels < px ? pixels : px) * sizeof(float), cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  return e;
+}
+
+const float* vo_detect_corners_device(const VODetect* d) { return d->corners; }
+const int* vo_detect_counts_device(const VODetect* d) { return d->nCorners; }
+int vo_detect_height(const VODetect* d) { return d->H; }
+int vo_detect_width(const VODetect* d) { return d->W; }
+
+}  // namespace vb

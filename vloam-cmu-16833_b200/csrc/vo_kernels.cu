@@ -557,6 +557,7 @@ struct vloam_vo {
   uint8_t* d_desc[2] = {nullptr, nullptr}; float* d_kp[2] = {nullptr, nullptr}; int* d_nkp[2] = {nullptr, nullptr};
   int* d_matches = nullptr; int* d_nmatch = nullptr; float* d_muv[2] = {nullptr, nullptr}; int4* d_knn = nullptr;
   int qcap = 0;
+  vb::VODetect* det = nullptr;   // key-point detection (vo_detect.cu), created by the first vloam_vo_detect_corners
   int slot() const { return (int)(count % 2); }
 };
 
@@ -580,6 +581,7 @@ int vloam_vo_destroy(vloam_vo* h) {
   cudaFree(h->d_q); cudaFree(h->d_qo);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_desc[i]); cudaFree(h->d_kp[i]); cudaFree(h->d_nkp[i]); cudaFree(h->d_muv[i]); }
   cudaFree(h->d_matches); cudaFree(h->d_nmatch); cudaFree(h->d_knn);
+  vb::vo_detect_destroy(h->det);
   delete h;
   return VLOAM_OK;
 }
@@ -836,6 +838,34 @@ int vloam_vo_get_knn(vloam_vo* h, int* knn) {
 int vloam_vo_get_match_buffers(vloam_vo* h, const float** query_uv_dev, const float** train_uv_dev, const int** n_matches_dev) {
   if (!h || !query_uv_dev || !train_uv_dev || !n_matches_dev) return VLOAM_E_INVALID;
   *query_uv_dev = h->d_muv[0]; *train_uv_dev = h->d_muv[1]; *n_matches_dev = h->d_nmatch;
+  return VLOAM_OK;
+}
+
+int vloam_vo_detect_corners(vloam_vo* h, const uint8_t* images, int height, int width, int max_corners, double quality_level,
+                            double min_distance, float* corners_xy, int* n_corners) {
+  if (!h || !images || height < 3 || width < 3 || max_corners < 1 || !(quality_level > 0.0) || !(min_distance >= 1.0)) return VLOAM_E_INVALID;
+  if ((long long)height * width > (1ll << 28)) return VLOAM_E_CAPACITY;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  int status = 0;
+  VCU(c, vb::vo_detect_run(&h->det, &c->prof, c->stream, h->B, images, height, width, max_corners, quality_level, min_distance, &status));
+  if (corners_xy && n_corners) VCU(c, vb::vo_detect_read(h->det, c->stream, corners_xy, n_corners));
+  if (status) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_detect_corners: more local maxima than a quarter of the pixels (plateaus of equal response)");
+  return VLOAM_OK;
+}
+
+int vloam_vo_get_corner_response(vloam_vo* h, int stream, float* out, size_t capacity_pixels) {
+  if (!h || !out || stream < 0 || stream >= h->B) return VLOAM_E_INVALID;
+  if (!h->det) return vfail(h->ctx, VLOAM_E_STATE, "vloam_vo_get_corner_response before vloam_vo_detect_corners");
+  VCU(h->ctx, cudaSetDevice(h->ctx->device));
+  VCU(h->ctx, vb::vo_detect_response(h->det, h->ctx->stream, stream, out, capacity_pixels));
+  return VLOAM_OK;
+}
+
+int vloam_vo_get_corner_buffers(vloam_vo* h, const float** corners_xy_dev, const int** n_corners_dev) {
+  if (!h || !corners_xy_dev || !n_corners_dev) return VLOAM_E_INVALID;
+  if (!h->det) return vfail(h->ctx, VLOAM_E_STATE, "vloam_vo_get_corner_buffers before vloam_vo_detect_corners");
+  *corners_xy_dev = vb::vo_detect_corners_device(h->det); *n_corners_dev = vb::vo_detect_counts_device(h->det);
   return VLOAM_OK;
 }
 
