@@ -57,4 +57,21 @@ def test_cpp_host_mirror_matches_python_mirror(synth, tmp_path):
         assert len(poses[k]) == 12
     np.testing.assert_allclose(np.array(poses[0], float).reshape(3, 4), np.eye(4)[:3], atol=1e-6)   # first dumped frame = origin
     assert abs(float(poses[2][3])) + abs(float(poses[2][7])) + abs(float(poses[2][11])) > 0.5          # the sensor moved
+    # the front-end calls of the mirror on the same deterministic inputs
+    from oracle import vo_frontend as F
+    y, x = np.mgrid[0:120, 0:200]
+    img = ((x * 3 + y * 5 + (((x // 9) + (y // 7)) % 2) * 110) % 256).astype(np.uint8)
+    want = F.good_features_to_track(img)
+    line = [l.split() for l in out.stdout.splitlines() if l.startswith("corners ")][0]
+    assert int(line[1]) == len(want) and len(want) > 20
+    assert np.array_equal(np.array(line[2:], np.float32), want.ravel()[:12])
+    i0 = np.arange(40 * 32)
+    d0 = ((i0 * 37 + (i0 // 32) * 11) % 251).astype(np.uint8).reshape(40, 32)
+    i1 = np.arange(50 * 32)
+    j = i1 % (40 * 32)
+    d1 = (((j * 37 + (j // 32) * 11) % 251) ^ np.where((i1 // 32) % 3 == 0, 1, 0)).astype(np.uint8).reshape(50, 32)
+    wm = F.match_descriptors(d0, d1)
+    line = [l.split() for l in out.stdout.splitlines() if l.startswith("matches ")][0]
+    assert int(line[1]) == len(wm)
+    assert [int(v) for v in line[2:]] == wm.ravel()[:9].tolist()
     lom.close(); vo.close()

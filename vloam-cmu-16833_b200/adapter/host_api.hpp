@@ -6,6 +6,7 @@
 // is a thin wrapper around this class.
 #pragma once
 #include <array>
+#include <algorithm>
 #include <stdexcept>
 #include <string>
 #include <vector>
@@ -127,6 +128,29 @@ class VisualOdometry {
     check(vloam_vo_solve(h_, prev_uv, curr_uv, &m, init, remove_VO_outlier, max_iterations, out));
     for (int i = 0; i < 3; ++i) { angles_0to1[i] = out[i]; t_0to1[i] = out[3 + i]; }
     counter32 = (int)out[6]; counter22 = (int)out[7];
+  }
+  // ImageUtil::detKeypoints, DetectorType::ShiTomasi (image_util.cpp:11-37): 8-bit grey image, rows packed -> (x, y) pairs in
+  // cv::goodFeaturesToTrack's order (the adapter wraps them into cv::KeyPoint with size = 5 like :29-35)
+  std::vector<float> detKeypoints(const uint8_t* image, int height, int width, int max_corners = 1024, double quality_level = 0.03,
+                                  double min_distance = 7.5) {
+    std::vector<float> xy((size_t)max_corners * 2);
+    int n = 0;
+    check(vloam_vo_detect_corners(h_, image, height, width, max_corners, quality_level, min_distance, xy.data(), &n));
+    xy.resize((size_t)n * 2);
+    return xy;
+  }
+  // ImageUtil::matchDescriptors (image_util.cpp:214-296, BF + NORM_HAMMING + kNN + 0.8 ratio test): rows of the ORB descriptor
+  // matrices (32 bytes each) -> (queryIdx, trainIdx, distance) triples in query order
+  std::vector<int> matchDescriptors(const uint8_t* desc_query, int n_query, const uint8_t* desc_train, int n_train, double ratio = 0.8) {
+    std::vector<uint8_t> q((size_t)max_matches_ * 32, 0), t((size_t)max_matches_ * 32, 0);
+    n_query = n_query < max_matches_ ? n_query : max_matches_; n_train = n_train < max_matches_ ? n_train : max_matches_;
+    std::copy(desc_query, desc_query + (size_t)n_query * 32, q.begin());
+    std::copy(desc_train, desc_train + (size_t)n_train * 32, t.begin());
+    std::vector<int> m((size_t)max_matches_ * 3);
+    int nm = 0;
+    check(vloam_vo_match_descriptors(h_, q.data(), &n_query, t.data(), &n_train, nullptr, nullptr, ratio, m.data(), &nm));
+    m.resize((size_t)nm * 3);
+    return m;
   }
   // PointCloudUtil::queryDepth (point_cloud_util.cpp:302-407); slot 0 = current frame, 1 = previous
   float queryDepth(float x, float y, int slot = 0) {

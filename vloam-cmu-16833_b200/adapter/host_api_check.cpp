@@ -45,6 +45,23 @@ int main(int argc, char** argv) {
                   lom.cloud(VLOAM_CLOUD_LESS_FLAT).size() / 4);
       std::fputs(("pose " + dump.write(nullptr, k - 2, vloam_b200::Mat4::from_qt(lom.mapped.q.data(), lom.mapped.t.data()))).c_str(), stdout);
     }
+    {  // ImageUtil::detKeypoints / matchDescriptors through the mirror, on a deterministic checkerboard-with-ramp image
+      const int H = 120, W = 200;
+      std::vector<uint8_t> img((size_t)H * W);
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) img[(size_t)y * W + x] = (uint8_t)((x * 3 + y * 5 + (((x / 9) + (y / 7)) % 2) * 110) % 256);
+      const std::vector<float> xy = vo.detKeypoints(img.data(), H, W);
+      std::printf("corners %zu", xy.size() / 2);
+      for (size_t i = 0; i < xy.size() && i < 12; ++i) std::printf(" %g", (double)xy[i]);
+      std::printf("\n");
+      std::vector<uint8_t> d0(40 * 32), d1(50 * 32);
+      for (size_t i = 0; i < d0.size(); ++i) d0[i] = (uint8_t)((i * 37 + (i / 32) * 11) % 251);
+      for (size_t i = 0; i < d1.size(); ++i) d1[i] = (uint8_t)(((i % (40 * 32)) * 37 + ((i % (40 * 32)) / 32) * 11) % 251 ^ ((i / 32) % 3 == 0 ? 1 : 0));
+      const std::vector<int> m = vo.matchDescriptors(d0.data(), 40, d1.data(), 50);
+      std::printf("matches %zu", m.size() / 3);
+      for (size_t i = 0; i < m.size() && i < 9; ++i) std::printf(" %d", m[i]);
+      std::printf("\n");
+    }
   } catch (const std::exception& e) {
     std::printf("no device: %s\n", e.what());  // expected on a CPU-only box: the library refuses to run, no fallback
     return argc >= 3 ? 4 : 0;

@@ -1,8 +1,8 @@
 // Drop-in replacement for include/visual_odometry/visual_odometry.h of YukunXia/VLOAM-CMU-16833: the same class name,
 // namespace, public methods and the public members the caller reads (cam0_curr_T_cam0_last, vloam_main_node.cpp:160), so
-// src/vloam_main/src/vloam_main_node.cpp compiles unchanged.  The OpenCV front-end (processImage: Shi-Tomasi / ORB /
-// matching through the reference's own ImageUtil) stays on the host; the LiDAR depth association, residual construction
-// and solve run through libvloam_b200.so.  Only built where ROS + PCL + OpenCV exist.
+// src/vloam_main/src/vloam_main_node.cpp compiles unchanged.  Of the image front end (processImage) the Shi-Tomasi detection
+// and the descriptor matching run on the device, ORB description stays with OpenCV; the LiDAR depth association, residual
+// construction and solve run through libvloam_b200.so.  Only built where ROS + PCL + OpenCV exist.
 #pragma once
 #if __has_include(<ros/ros.h>) && __has_include(<pcl/point_cloud.h>) && __has_include(<opencv2/opencv.hpp>)
 #include <pcl/point_cloud.h>
@@ -36,6 +36,7 @@ class VisualOdometry {
     if (!ros::param::get("CLAHE", CLAHE)) ROS_BREAK();
     if (!ros::param::get("visualize_optical_flow", visualize_optical_flow)) ROS_BREAK();
     if (!ros::param::get("optical_flow_match", optical_flow_match)) ROS_BREAK();
+    ros::param::get("vo_frontend_on_device", frontend_on_device);
     count = -1;
     images.resize(2); keypoints.resize(2); descriptors.resize(2); keypoints_2f.resize(2);
     if (CLAHE) clahe = cv::createCLAHE(2.0, cv::Size(8, 8));
@@ -47,12 +48,32 @@ class VisualOdometry {
 
   void reset() { ++count; i = count % 2; impl->reset(); }                                                      // :86-90
 
-  void processImage(const cv::Mat& img00) {                                                                    // :92-130, unchanged: stock OpenCV
+  // :92-130.  Detection (Shi-Tomasi, image_util.cpp:11-37) and matching (BF + Hamming + ratio test, :214-296) run on the device
+  // when `vo_frontend_on_device` is set (new, optional parameter, default true) and the inputs have the shapes the reference
+  // produces (8-bit grey image, 32-byte ORB rows); ORB description (:162-212) and the optical-flow branch stay with OpenCV.
+  void processImage(const cv::Mat& img00) {
     if (CLAHE) clahe->apply(img00, images[i]); else images[i] = img00;
-    keypoints[i] = image_util.detKeypoints(images[i]);
+    if (frontend_on_device && images[i].type() == CV_8UC1 && images[i].isContinuous()) {
+      const std::vector<float> xy = impl->detKeypoints(images[i].data, images[i].rows, images[i].cols);
+      keypoints[i].clear();
+      for (size_t k = 0; k + 1 < xy.size(); k += 2) {            // image_util.cpp:29-35
+        cv::KeyPoint kp;
+        kp.pt = cv::Point2f(xy[k], xy[k + 1]);
+        kp.size = 5;
+        keypoints[i].push_back(kp);
+      }
+    } else {
+      keypoints[i] = image_util.detKeypoints(images[i]);
+    }
     if (!optical_flow_match) descriptors[i] = image_util.descKeypoints(keypoints[i], images[i]);
     if (count > 0) {
-      if (!optical_flow_match) matches = image_util.matchDescriptors(descriptors[1 - i], descriptors[i]);
+      const cv::Mat &dq = descriptors[1 - i], &dt = descriptors[i];
+      if (!optical_flow_match && frontend_on_device && dq.type() == CV_8UC1 && dt.type() == CV_8UC1 && dq.cols == 32 && dt.cols == 32 &&
+          dq.isContinuous() && dt.isContinuous()) {
+        const std::vector<int> m = impl->matchDescriptors(dq.data, dq.rows, dt.data, dt.rows);
+        matches.clear();
+        for (size_t k = 0; k + 2 < m.size(); k += 3) matches.emplace_back(m[k], m[k + 1], (float)m[k + 2]);   // cv::DMatch(queryIdx, trainIdx, distance)
+      } else if (!optical_flow_match) matches = image_util.matchDescriptors(dq, dt);
       else std::tie(keypoints_2f[1 - i], keypoints_2f[i], optical_flow_status) = image_util.calculateOpticalFlow(images[1 - i], images[i], keypoints[i]);
     }
   }
@@ -140,6 +161,7 @@ class VisualOdometry {
   ros::NodeHandle nh;
   int verbose_level = 0, remove_VO_outlier = 100;
   bool reset_VO_to_identity = false, keypoint_NMS = false, CLAHE = false, visualize_optical_flow = false, optical_flow_match = false;
+  bool frontend_on_device = true;
   cv::Ptr<cv::CLAHE> clahe;
   nav_msgs::Odometry visualOdometry;
   nav_msgs::Path visualPath;
