@@ -520,6 +520,7 @@ __device__ void pick_ring(const float* __restrict__ cv, uint8_t* picked, const u
       c[m] = 0.f;
       if (pos <= ep) { c[m] = cv[pos]; if (!picked[pos - rs]) alive |= 1u << m; }
     }
+    __syncwarp();   // the reads of `picked` above are ordered before the writes of suppress() below (racecheck: write-after-read)
     // mark `ind` and its suppressed neighbours picked (:351-376 / :396-420); every lane updates its alive mask
     auto suppress = [&](int ind) {
       // lanes 0..4: forward steps 1..5 = pairs (ind+l, ind+l+1); lanes 5..9: backward steps = pairs (ind-m-1, ind-m)
