@@ -46,6 +46,9 @@ def pingpong(i: int, n: int) -> int:
     return p if p < n else 2 * n - 2 - p
 
 
+BENCH_YAW_RATE_MAX = 0.01      # rad/s: the 64-scan drives stay on the scene's road (synth.ScanStream)
+
+
 def scan_index(i: int) -> int:
     """Trajectory scan visited at step i (0, 1, ..., 63, 62, ...)."""
     return pingpong(i, TRAJ_SCANS)
@@ -142,7 +145,8 @@ def make_base_scans(rank: int, needed, world: int = 1, batch: int = N_BASE, with
     seqs, streams = [], []
     first = D.shard_streams(world * batch, world, rank)[0] if batch > 0 else 0     # this rank's first global stream
     for i in range(N_BASE):
-        s = synth.ScanStream(D.stream_seed(BENCH_SEED, first + i, N_BASE) if world > 1 else BENCH_SEED + i, n_cols=N_COLS)
+        s = synth.ScanStream(D.stream_seed(BENCH_SEED, first + i, N_BASE) if world > 1 else BENCH_SEED + i, n_cols=N_COLS,
+                             yaw_rate_max=BENCH_YAW_RATE_MAX, on_road=True)
         streams.append(s)
         seqs.append({k: s.scan(k) for k in needed})
     return (seqs, streams) if with_streams else seqs
@@ -621,6 +625,18 @@ def run_ours(args, rank, world, local_rank):
                 a = ktimes.get(kname, (0.0, 0))
                 ktimes[kname] = (a[0] + ms_k, a[1] + n_k)
             c_.enable_timing(False)
+        # the byte model must describe the SAME scans the durations come from: once more over those scans (ping-pong index),
+        # reading the point / feature counts after every step (a read-back per step would disturb the timing pass itself)
+        counts_sum, lm_info_sum, n_k_steps = None, None, 0
+        for i in range(args.warmup + args.steps, args.warmup + 2 * args.steps):
+            step_dev(i)
+            c_i = np.concatenate([hd.feature_counts() for hd in loms]).astype(np.int64)
+            counts_sum = c_i if counts_sum is None else counts_sum + c_i
+            if do_map:
+                l_i = np.concatenate([hd.lm_info() for hd in loms]).astype(np.int64)
+                lm_info_sum = l_i if lm_info_sum is None else lm_info_sum + l_i
+            n_k_steps += 1
+        barrier()
         # statistics pass (untimed): candidate points the 5-NN search tests per query
         knn = None
         if do_map:
@@ -779,11 +795,12 @@ def run_ours(args, rank, world, local_rank):
 
     # ---------------- per-kernel table and the roofline of the dominant kernel
     peaks, peak_kind = load_peaks()
-    tot = {"N": int(B * cap), "Np": int(counts[:, 0].sum()), "nSharp": int(counts[:, 1].sum()), "nLS": int(counts[:, 2].sum()),
-           "nFlat": int(counts[:, 3].sum()), "nLF": int(counts[:, 4].sum())}
+    cm = counts_sum / max(n_k_steps, 1)                          # mean per scan over the per-kernel timing pass
+    tot = {"N": int(B * cap), "Np": int(cm[:, 0].sum()), "nSharp": int(cm[:, 1].sum()), "nLS": int(cm[:, 2].sum()),
+           "nFlat": int(cm[:, 3].sum()), "nLF": int(cm[:, 4].sum())}
     tot["nLSlast"], tot["nLFlast"] = tot["nLS"], tot["nLF"]
     if do_map:
-        info = lm_info_all
+        info = lm_info_sum / max(n_k_steps, 1)
         tot["M"] = int(info[:, 4].sum() + info[:, 5].sum())
         tot["S"] = int(info[:, 6].sum() + info[:, 7].sum())
         tot["Mw"] = int(map_stats_all[:, :, 8].sum())

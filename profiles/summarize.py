@@ -9,9 +9,9 @@ import subprocess
 import sys
 
 launch_csv, rep, tag, streams = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
-what = sys.argv[5] if len(sys.argv) > 5 else "scanRegistration + laserOdometry"
-cmd = sys.argv[6] if len(sys.argv) > 6 else f"bench.py --legs device --batch {streams} --handles 1"
-bench_json = sys.argv[7] if len(sys.argv) > 7 else "profiles/r01_bench_default.json"
+what = sys.argv[5] if len(sys.argv) > 5 else "scanRegistration + laserOdometry + laserMapping on the 1 M-point corridor map, forward trajectory"
+cmd = sys.argv[6] if len(sys.argv) > 6 else f"bench.py --workload sr_lo_lm --legs device --batch {streams} --handles 1 --steps 3 --warmup 4"
+bench_json = sys.argv[7] if len(sys.argv) > 7 else "profiles/r02_bench_default.json"
 
 
 def base(name):

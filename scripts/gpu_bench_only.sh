@@ -1,0 +1,14 @@
+#!/bin/bash
+mkdir -p gpurun_out
+tag=${1:-bench}
+shift
+timeout 600 python bench.py "$@" > gpurun_out/${tag}_bench.json 2> gpurun_out/${tag}_bench.err
+tail -2 gpurun_out/${tag}_bench.err
+TAG=$tag python - <<'PY'
+import json, os
+d = json.loads(open(f"gpurun_out/{os.environ['TAG']}_bench.json").read().strip().splitlines()[-1])
+e = d["e2e"]
+print("value", round(d["value"]), "e2e", round(e["value"]), "h2d", round(e["h2d_gbs_per_gpu"], 1), "ceiling", round(e["h2d_ceiling_gbs_per_gpu"], 1), "lat", d["single_stream_latency_ms"], "cpu", d["cpu_baseline"]["value"])
+print({k: round(v["avg_us"], 1) for k, v in d["kernels"].items()})
+print(d["north_star_kernels"]["sr_curvature"])
+PY

@@ -317,8 +317,9 @@ def test_laser_mapping_bench_configuration(synth, oracle):
     oracle pipeline per stream, after every scan."""
     import vloam_b200 as V
     B, n_scans = 2, 4
-    cubes = synth.map_cubes(1_000_000, 1234)
-    streams = [synth.ScanStream(1234 + b, n_cols=2048) for b in range(B)]
+    import bench
+    cubes = synth.map_cubes(1_000_000, bench.BENCH_SEED)
+    streams = [synth.ScanStream(bench.BENCH_SEED + b, n_cols=2048, yaw_rate_max=bench.BENCH_YAW_RATE_MAX, on_road=True) for b in range(B)]
     cap = 64 * 2048
     lom = V.LidarOdometryMapping(batch=B, max_points=cap, map_capacity_points=1 << 21, lm_max_iterations=5)
     pipes = [oracle.Pipeline() for _ in range(B)]
