@@ -556,11 +556,9 @@ class LidarOdometryMapping:
 
 
 class VisualOdometry:
-    """Mirror of the in-scope part of vloam::VisualOdometry (depth association + residuals + solve) for `batch` streams.
-
-    The OpenCV front-end (processImage: detect / describe / match) stays on the host and is out of scope; its output,
-    the matched keypoint pixels, is the input of solveNlsAll.
-    """
+    """Mirror of the in-scope part of vloam::VisualOdometry for `batch` streams: of processImage the Shi-Tomasi detection
+    (detKeypoints) and the descriptor matching (matchDescriptors) — ORB description stays with OpenCV on the host —, then
+    depth association, residual construction and the solve (processPointCloud, solveNlsAll)."""
 
     def __init__(self, ctx: Context | None = None, batch: int = 1, max_points: int = 131072, max_matches: int = 1024,
                  remove_VO_outlier: int = 100, max_num_iterations: int = 100):

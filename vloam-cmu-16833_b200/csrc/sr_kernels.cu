@@ -954,7 +954,8 @@ void launch_scan_registration(Profiler* prof, cudaStream_t st, int B, int cap, c
   {
     // tiles per CTA: long pipelines when the batch alone fills the machine, one tile per CTA for small batches
     const int tiles = (cap + kCurvTile - 1) / kCurvTile;
-    const int per = (size_t)B * tiles >= 4096 ? 4 : 1;
+    static const int perEnv = [] { const char* e = getenv("VLOAM_SR_CURV_TILES"); return e ? atoi(e) : 0; }();
+    const int per = perEnv > 0 ? perEnv : ((size_t)B * tiles >= 4096 ? 4 : 1);
     static const bool useTma = [] { const char* e = getenv("VLOAM_SR_CURV_TMA"); return e && e[0] == '1'; }();
     if (useTma) VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature_tma<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
     else VB_LAUNCH(prof, K_SR_CURVATURE, st, sr_curvature<<<dim3((tiles + per - 1) / per, B), 256, 0, st>>>(hdr, cloud, cap, curv, gapflag, per));
