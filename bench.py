@@ -233,8 +233,22 @@ def config_dict(args, streams_per_gpu, handles, world, do_map, extra=None):
     c = {"workload": WORKLOAD_NAME[args.workload][1], "streams_per_gpu": streams_per_gpu, "handles": handles,
          "points_per_scan": N_RINGS * N_COLS, "lo_passes": 2, "lo_iterations_per_pass": 4, "lm_passes": 2,
          "lm_iterations_per_pass": args.lm_iterations, "map_points": args.map_points if do_map else 0, "solver_mode": args.solver_mode, "cuda_graphs": args.graphs,
-         "trajectory": f"{N_BASE} seeded base sequences x {TRAJ_SCANS} consecutive scans (forward drive, no replay within {TRAJ_SCANS} steps), "
+         "trajectory": f"{N_BASE} seeded base sequences x {TRAJ_SCANS} consecutive scans (forward drive along the scene's road, full-size scans throughout, no replay within {TRAJ_SCANS} steps), "
                        "tiled across the streams"}
+    cap = N_RINGS * N_COLS
+    # (both arms print these two as well: they describe the B200 arm's run of this configuration — the timed steps read a different
+    # slab of the device-resident scan pool each, which exceeds the 126 MB L2 from 84 streams on)
+    c["l2_policy"] = (f"inputs larger than L2: a different [{streams_per_gpu}, {cap}, 3] slab ({streams_per_gpu * cap * 12 / 1e6:.0f} MB) of the "
+                      "device-resident scan pool every step")
+    if args.parallelism == "point":
+        c["parallelism"] = (f"point-sharded x{world}: replicated scans, queries split across ranks, partial normal equations (28 doubles per tile, "
+                            f"{8 * 28 * 8} bytes per stream and evaluation) all-reduced by NCCL between the accumulate and step launches of laser "
+                            "odometry and laser mapping")
+    elif args.parallelism == "point-peer":
+        c["parallelism"] = (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations summed inside "
+                            "the solve kernel over NVLink peer memory")
+    else:
+        c["parallelism"] = f"stream-sharded x{world} (no data-path collective)"
     if extra:
         c.update(extra)
     return c
@@ -277,7 +291,7 @@ def run_reference(args, rank):
         "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve", "data": "synthetic",
-        "config": config_dict(args, args.batch, args.handles, 1, do_map),
+        "config": config_dict(args, args.batch, args.handles, max(1, args.gpus), do_map),
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
                          "sample": f"{T} threads x {args.steps} scans, one stream per thread (the GPU arm's streams_per_gpu streams are a batch "
                                    f"dimension this CPU path does not have); per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
@@ -885,14 +899,8 @@ def run_ours(args, rank, world, local_rank):
         "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "strong" if point else "weak", "vs_baseline": None,
         "dtype": "f32 points / f64 solve",
         "data": f"synthetic ({N_BASE} seeded base sequences x {TRAJ_SCANS}-scan forward trajectories tiled across the batch; generated in {t_gen:.1f} s)",
-        "config": config_dict(args, B, args.handles, world, do_map, {
-            "l2_policy": f"inputs larger than L2: a different [{B}, {cap}, 3] slab of the {pool_bytes/1e9:.1f} GB scan pool every step",
-            "parallelism": ((f"point-sharded x{world}: replicated scans, queries split across ranks, partial normal equations (28 doubles per "
-                             f"tile, {8 * 28 * 8} bytes per stream and evaluation) all-reduced by NCCL between the accumulate and step launches of "
-                             f"laser odometry and laser mapping") if point_nccl else
-                            (f"point-sharded x{world}: replicated scans, correspondences split across ranks, 28-double normal equations "
-                             f"summed inside the solve kernel over NVLink peer memory, shard_status={shard_err}")) if point
-                           else f"stream-sharded x{world} (no data-path collective)"}),
+        "config": config_dict(args, B, args.handles, world, do_map),
+        "scan_pool_gb": pool_bytes / 1e9, "shard_status": int(shard_err),
         "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": ms_e2e / args.steps, "poses_identical_to_device_leg": same,
                 "h2d_gbs_per_gpu": h2d / (ms_e2e / args.steps * 1e-3) / 1e9,

@@ -1749,7 +1749,10 @@ cudaError_t lm_run(LMDevice* lm, cudaStream_t st, const SRHeader* hdrCur, const 
       at[0].id = cudaLaunchAttributeClusterDimension;
       at[0].val.clusterDim.x = cs; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
       cfg.attrs = at; cfg.numAttrs = 1;
-      static const bool regs128 = [] { const char* e = getenv("VLOAM_LM_SOLVE_REGS"); return e && atoi(e) == 128; }();
+      // register budget: from 32 streams per launch on, the SMs a solve occupies are wanted by the other handles' kernels, and the
+      // 128-register variant leaves room for them (measured: kernel 3 % slower, step 2 % faster); VLOAM_LM_SOLVE_REGS=128|256 forces one
+      static const int regsEnv = [] { const char* e = getenv("VLOAM_LM_SOLVE_REGS"); return e ? atoi(e) : 0; }();
+      const bool regs128 = regsEnv == 128 || (regsEnv == 0 && B >= 32);
       if (regs128)
         VB_LAUNCH(prof, K_LM_SOLVE, st, cudaLaunchKernelEx(&cfg, lm_solve_r128, lm->st, lm->res, cap, tp, lm->p.lm_max_iterations,
                                                                    pass == lm->p.lm_outer_passes - 1 ? 1 : 0));

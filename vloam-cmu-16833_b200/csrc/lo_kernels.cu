@@ -947,7 +947,8 @@ void launch_lo_pass(Profiler* prof, cudaStream_t st, int B, int cap, const SRHea
     VB_LAUNCH(prof, K_LO_STEP, st, lo_gn_finish<<<(B + 127) / 128, 128, 0, st>>>(lo, B, pass, integrate, counts));
     return;
   }
-  static const bool regs128 = [] { const char* e = getenv("VLOAM_LO_SOLVE_REGS"); return e && atoi(e) == 128; }();
+  static const int regsEnv = [] { const char* e = getenv("VLOAM_LO_SOLVE_REGS"); return e ? atoi(e) : 0; }();
+  const bool regs128 = regsEnv == 128;     // measured: no gain for the step at any batch size (41.65 k vs 41.68 k scans/s), so only on request
   if (regs128)
     VB_LAUNCH(prof, K_LO_SOLVE, st, lo_solve_r128<<<B, 256, kLoSolveDynSmem, st>>>(hdrCur, lo, sharp, flat, cornerLast, surfLast, cap, corr, pass,
                                                                       max_iterations, integrate, sv));
