@@ -195,6 +195,38 @@ def test_laser_mapping_batched_streams_on_seeded_map(synth, oracle):
     lom.close()
 
 
+def test_laser_mapping_32_streams_per_launch(synth, oracle):
+    """From 32 streams per launch on the mapping solve runs in its 128-register variant (lm_solve_r128, two CTAs per SM) — the
+    one the benchmark's 64-stream handles use: 32 different streams against 32 oracle pipelines, poses, traces and query sets
+    after every scan."""
+    import vloam_b200 as V
+    B = 32
+    streams = [synth.ScanStream(500 + b, n_cols=256) for b in range(B)]
+    lom = V.LidarOdometryMapping(batch=B, max_points=64 * 256, map_capacity_points=1 << 16)
+    pipes = [oracle.Pipeline() for _ in range(B)]
+    solved = 0
+    for k in range(4):
+        buf = np.stack([s.scan(k) for s in streams])
+        lom.reset(); lom.scanRegistrationIO(buf); lom.laserOdometryIO()
+        mp = lom.laserMappingIO()
+        assert not lom.lm_status().any()
+        for b in range(B):
+            assert pipes[b].process(buf[b], do_mapping=True) == 0
+            ost = pipes[b].lm.state
+            assert np.max(np.abs(mp["t_w_curr"][b] - ost["t_w_curr"])) < POSE_TOL_M, (k, b)
+            assert _quat_angle(mp["q_w_curr"][b], ost["q_w_curr"]) < POSE_TOL_RAD
+            for p, t in enumerate(pipes[b].lm.trace()):
+                g = lom.lm_trace(p, b)
+                assert np.array_equal(lom.lm_queries(p, 0, b), t["corner"].ravel()) and np.array_equal(lom.lm_queries(p, 1, b), t["plane"].ravel())
+                n = t["iterations"].shape[0]
+                assert g["n_records"] == n and g["termination"] == t["termination"]
+                np.testing.assert_allclose(g["iterations"][:n, 0], t["iterations"][:, 0], rtol=1e-8, atol=1e-12)
+                np.testing.assert_allclose(g["para"], t["para"], atol=1e-8)
+                solved += 1
+    assert solved >= 3 * 2 * B
+    lom.close()
+
+
 def test_laser_mapping_column_table_recycling(synth, oracle, monkeypatch):
     """The per-cube column tables come from a fixed pool of slots; cubes dropped by grid shifts leak theirs until the pool
     runs out, then every index is dropped and rebuilt.  With only 14 slots per kind that happens several times in 8
