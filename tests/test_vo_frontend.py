@@ -76,6 +76,52 @@ def test_numpy_detection_matches_opencv(detect_golden):
     assert len(g["shapes_corners"]) < 1024          # the quality threshold and the spacing decide here, not the cap
 
 
+def test_corner_selection_against_a_literal_greedy_pass():
+    """select_corners (grid of cvRound(min_distance) cells, as OpenCV) against the definition it implements: walk the local maxima
+    by (response descending, address descending) and keep one when no kept corner is closer than min_distance — on response
+    maps with many exactly equal values (the tie-break matters) and for spacings on both sides of the cell size."""
+    from oracle import vo_frontend as F
+    rng = np.random.default_rng(11)
+    for min_distance, quant in ((7.5, 12), (3.0, 5), (12.4, 0)):
+        eig = rng.random((90, 140)).astype(np.float32)
+        if quant:
+            eig = (np.floor(eig * quant) / quant).astype(np.float32)          # few distinct levels: plateaus and ties
+        got = F.select_corners(eig, max_corners=300, quality=0.2, min_distance=min_distance)
+        H, W = eig.shape
+        thr = np.float32(np.float64(eig.max()) * 0.2)
+        e = np.where(eig > thr, eig, np.float32(0))
+        cand = []
+        for y in range(1, H - 1):
+            for x in range(1, W - 1):
+                v = e[y, x]
+                if v != 0 and v == e[y - 1:y + 2, x - 1:x + 2].max():
+                    cand.append((-float(v), -(y * W + x), x, y))
+        cand.sort()
+        cell = int(np.rint(min_distance))
+        kept = []
+        for _, _, x, y in cand:
+            # OpenCV only looks into the 3 x 3 cells around the candidate: for min_distance <= cell that is every corner in range
+            near = [(px, py) for px, py in kept if abs(px // cell - x // cell) <= 1 and abs(py // cell - y // cell) <= 1]
+            if all((x - px) ** 2 + (y - py) ** 2 >= min_distance * min_distance for px, py in near):
+                kept.append((x, y))
+                if len(kept) == 300:
+                    break
+        assert np.array_equal(got, np.array(kept, np.float32).reshape(-1, 2)), min_distance
+        assert len(kept) > 20
+
+
+def test_response_restatement_against_opencv_across_image_sizes():
+    """If cv2 is importable: the restated operation order (fused Sobel taps, the scalar tail of width mod 32 columns, double box
+    sums) holds for narrow, odd and large images, not only for the committed ones."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import vo_frontend as F
+    rng = np.random.default_rng(9)
+    for H, W in ((40, 20), (33, 50), (64, 64), (100, 95), (37, 129), (480, 752)):
+        img = cv2.GaussianBlur((rng.random((H, W)) * 255).astype(np.uint8), (0, 0), 1.5)
+        ulp = _ulp_distance(F.min_eigen_response(img), cv2.cornerMinEigenVal(img, 5, ksize=3))
+        assert (ulp == 0).mean() > 0.9999 and ulp.max() <= 4, ((H, W), (ulp == 0).mean(), ulp.max())
+
+
 def test_opencv_still_reproduces_the_detection_vectors(detect_golden):
     cv2 = pytest.importorskip("cv2")
     g = detect_golden
