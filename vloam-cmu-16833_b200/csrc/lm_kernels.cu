@@ -289,7 +289,6 @@ __global__ void __launch_bounds__(kPrepThreads) lm_prepare(LMState* __restrict__
   LMState& st = stAll[b];
   short* entryHead = entryHeadAll + (size_t)b * kCubes;
   __shared__ int sh[3];
-  __shared__ int center[3];
   __shared__ int s_gc[2], s_vn, s_dup, s_total[2];
   __shared__ int s_vind[kMaxValid], s_cnt[2][kMaxValid], s_tab[2][kMaxValid];
   __shared__ unsigned char s_head[kMaxValid];
@@ -315,7 +314,6 @@ __global__ void __launch_bounds__(kPrepThreads) lm_prepare(LMState* __restrict__
     while (cK < 3) { cK++; st.cenD++; sK++; }
     while (cK >= kCubeD - 3) { cK--; st.cenD--; sK--; }
     sh[0] = sI; sh[1] = sJ; sh[2] = sK;
-    center[0] = cI; center[1] = cJ; center[2] = cK;
     // :404-420 valid cubes in the reference's loop order
     int vn = st.validNum;
     const int vn0 = vn;

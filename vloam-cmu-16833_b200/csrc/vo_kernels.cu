@@ -28,7 +28,7 @@
 
 namespace vb {
 
-constexpr int kImgW = 1242, kImgH = 375, kBucket = 5;      // point_cloud_util.h:26,41-42
+constexpr int kBucket = 5;                                  // point_cloud_util.h:26,41-42: IMG_WIDTH 1242, IMG_HEIGHT 375
 constexpr int kBW = 249, kBH = 75, kBuckets = kBW * kBH;   // ceil(1242 / 5), ceil(375 / 5)
 
 struct VOCalib { float cam_T_velo[16], rect0_T_cam[16], P_rect0[12]; };
