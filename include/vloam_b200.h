@@ -306,6 +306,33 @@ int vloam_vo_detect_corners(vloam_vo* h, const uint8_t* images, int height, int 
 /* The response map of the last detection (cv::cornerMinEigenVal), stream `stream`, row-major height x width floats. */
 int vloam_vo_get_corner_response(vloam_vo* h, int stream, float* out, size_t capacity_pixels);
 int vloam_vo_get_corner_buffers(vloam_vo* h, const float** corners_xy_dev, const int** n_corners_dev);
+/* ImageUtil::descKeypoints with DescriptorType::ORB   image_util.cpp:162-212 (the descriptor visual_odometry.cpp:35 selects):
+ * cv::ORB::create()->compute(img, keypoints, descriptors) on key points of octave 0 and the default angle -1, which is what
+ * detKeypoints builds from its corners (image_util.cpp:29-35).  ORB (a) drops the key points whose rounded position is not in
+ * [31, cols - 31) x [31, rows - 31) and rewrites the caller's vector to the survivors, in order; (b) blurs the image (7 x 7,
+ * sigma 2; float taps, OpenCV's rounding sequence) and (c) evaluates its 256 learned intensity comparisons around each survivor.
+ * images: host [batch][height][width] bytes, or NULL = the images of the last vloam_vo_detect_corners (still on the device).
+ * keypoints_xy / n_keypoints: host [batch][max_matches][2] = cv::KeyPoint::pt and [batch], or both NULL = the corners of the last
+ * detection (on the device; its max_corners must not exceed max_matches).  Outputs (each may be NULL; the results also stay on
+ * the device as keypoints[i] / descriptors[i] of the processImage chain): kept_xy[batch][max_matches][2] the surviving key
+ * points, kept_index[batch][max_matches] their positions in the input list, descriptors[batch][max_matches][32] the rows of
+ * the cv::Mat, n_kept[batch]. */
+int vloam_vo_describe_orb(vloam_vo* h, const uint8_t* images, int height, int width, const float* keypoints_xy, const int* n_keypoints,
+                          float* kept_xy, int* kept_index, uint8_t* descriptors, int* n_kept);
+/* VisualOdometry::processImage   visual_odometry.cpp:92-130 with the reference's selections (visual_odometry.cpp:34-37: ShiTomasi,
+ * ORB, BF matcher, kNN selector): keypoints[i] = detKeypoints(img), descriptors[i] = descKeypoints(keypoints[i], img) and, from
+ * the second frame on (count > 0), matches = matchDescriptors(descriptors[1 - i], descriptors[i]) — one upload of the images,
+ * everything else on the device; the matched pixel pairs land in the buffers vloam_vo_get_match_buffers names, in solveNlsAll's
+ * layout.  Call vloam_vo_reset first (visual_odometry.cpp:86-90), as the reference's frame loop does.  images: host
+ * [batch][height][width] bytes; n_keypoints / n_matches [batch]: optional host read-outs (NULL, NULL = no synchronisation
+ * after the launches; the first frame reports 0 matches).  max_matches must be >= 1024 (the detector's maxCorners). */
+int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int width, int* n_keypoints, int* n_matches);
+/* keypoints[slot] / descriptors[slot] of that chain (slot 0 = current frame, 1 = previous frame): keypoints_xy
+ * [batch][max_matches][2], descriptors [batch][max_matches][32], n_keypoints[batch]; each may be NULL. */
+int vloam_vo_get_frame_features(vloam_vo* h, int slot, float* keypoints_xy, uint8_t* descriptors, int* n_keypoints);
+/* The match list of the last vloam_vo_process_image / vloam_vo_match_descriptors: matches[batch][max_matches][3] =
+ * (queryIdx, trainIdx, distance), n_matches[batch]. */
+int vloam_vo_get_matches(vloam_vo* h, int* matches, int* n_matches);
 /* ImageUtil::matchDescriptors   image_util.cpp:214-296, in the configuration VisualOdometry selects (visual_odometry.cpp:34-37):
  * cv::BFMatcher(NORM_HAMMING).knnMatch(query, train, 2) over 32-byte binary descriptors (cv::ORB) and the ratio test
  * `m[0].distance < ratio * m[1].distance` (ratio = 0.8, :277).  desc_query / desc_train: [batch][max_matches][32] bytes

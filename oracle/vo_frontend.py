@@ -148,3 +148,85 @@ def select_corners(eig, max_corners=1024, quality=0.03, min_distance=7.5):
 def good_features_to_track(img, max_corners=1024, quality=0.03, min_distance=7.5, block=5):
     """ImageUtil::detKeypoints with DetectorType::ShiTomasi (image_util.cpp:11-37): corner coordinates (x, y) in pick order."""
     return select_corners(min_eigen_response(img, block), max_corners, quality, min_distance)
+
+
+# ------------------------------------------------------------------ ORB description (image_util.cpp:162-212)
+ORB_EDGE = 31                                             # cv::ORB::create(): edgeThreshold 31, patchSize 31, WTA_K 2, first level 0
+def _gauss7_taps():
+    """cv::getGaussianKernel(7, 2, CV_32F): exp(-x^2 / (2 sigma^2)) in double, normalised in double, stored as float."""
+    x = np.arange(7, dtype=np.float64) - 3.0
+    k = np.exp(-(x * x) / 8.0)
+    return (k / k.sum()).astype(np.float32)
+
+
+def _mad(a, b, c):
+    return (a * np.float32(b) + c).astype(np.float32)
+
+
+def gaussian_blur_7x7(img):
+    """The blur inside cv::ORB::compute: GaussianBlur(level, level, Size(7, 7), 2, 2, BORDER_REFLECT_101) on a SUB-MATRIX of the
+    pyramid buffer.  For a sub-matrix OpenCV skips its 8-bit fixed-point Gaussian and calls sepFilter2D with the float taps:
+    rows first (uchar -> float, taps in order 0..6), then columns (centre tap, then the three symmetric pairs
+    tap_k * (row[+k] + row[-k])), one cvRound to 8 bits.  The rounding sequence below is that of cv2 4.13's AVX2 build, found
+    by experiment and pinned by tests/test_vo_frontend.py against cv2.sepFilter2D / cv2.ORB on many image widths: the
+    vectorised loops fuse multiply-adds, the scalar tails do not — rows: columns x < 32 * (w // 32) fused, the rest unfused;
+    columns: x < 4 * (w // 4) fused, the last w % 4 unfused."""
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape
+    k = _gauss7_taps()
+    p = np.pad(img, 3, mode="reflect").astype(np.float32)            # BORDER_REFLECT_101
+    wv = 32 * (w // 32)
+    rows = np.empty((h + 6, w), np.float32)
+    for lo, hi, op in ((0, wv, _fma), (wv, w, _mad)):
+        if hi > lo:
+            acc = (p[:, lo:hi] * k[0]).astype(np.float32)
+            for t in range(1, 7):
+                acc = op(p[:, lo + t:hi + t], k[t], acc)
+            rows[:, lo:hi] = acc
+    out = np.empty((h, w), np.float32)
+    wc = 4 * (w // 4)
+    for lo, hi, op in ((0, wc, _fma), (wc, w, _mad)):
+        if hi > lo:
+            acc = (rows[3:3 + h, lo:hi] * k[3]).astype(np.float32)
+            for t in (1, 2, 3):
+                acc = op((rows[3 + t:3 + t + h, lo:hi] + rows[3 - t:3 - t + h, lo:hi]).astype(np.float32), k[3 + t], acc)
+            out[:, lo:hi] = acc
+    return np.clip(np.rint(out), 0, 255).astype(np.uint8)
+
+
+def orb_steered_pattern(angle_deg=-1.0):
+    """The 512 sample offsets of computeOrbDescriptors for a key point of angle `angle_deg` (cv::KeyPoint's default -1: the
+    reference builds its key points from corners, image_util.cpp:29-35, so ORB never estimates an orientation): the learned
+    pattern rotated in float and rounded (cvRound).  For -1 degree every offset rounds back to the table entry."""
+    try:
+        from .orb_pattern import ORB_PATTERN
+    except ImportError:           # run as a plain module from inside oracle/
+        from orb_pattern import ORB_PATTERN
+    pat = np.array(ORB_PATTERN, np.float32).reshape(-1, 2)            # (512, 2) x, y
+    ang = np.float32(angle_deg) * np.float32(np.pi / 180.0)
+    a, b = np.float32(np.cos(np.float64(ang))), np.float32(np.sin(np.float64(ang)))
+    x = pat[:, 0] * a - pat[:, 1] * b
+    y = pat[:, 0] * b + pat[:, 1] * a
+    return np.rint(x).astype(np.int32), np.rint(y).astype(np.int32)
+
+
+def orb_describe(img, keypoints_xy):
+    """ImageUtil::descKeypoints with DescriptorType::ORB (image_util.cpp:162-212): cv::ORB::create()->compute(img, keypoints,
+    descriptors) on key points of octave 0 and angle -1.  Returns (kept, descriptors): the indices of the key points ORB keeps
+    (KeyPointsFilter::runByImageBorder with the edge threshold, on the rounded position: 31 <= cvRound(x) < cols - 31 and
+    31 <= cvRound(y) < rows - 31; the reference's key-point vector is rewritten to these, in order) and their 32-byte descriptors: bit i of byte j is
+    blurred(c + a) < blurred(c + b) for pair 8 j + i, c = (cvRound(x), cvRound(y))."""
+    img = np.asarray(img, np.uint8)
+    h, w = img.shape
+    kp = np.asarray(keypoints_xy, np.float32).reshape(-1, 2)
+    rx, ry = np.rint(kp[:, 0]).astype(np.int64), np.rint(kp[:, 1]).astype(np.int64)      # Rect_<int>::contains(Point(pt)): cvRound
+    keep = (rx >= ORB_EDGE) & (rx < w - ORB_EDGE) & (ry >= ORB_EDGE) & (ry < h - ORB_EDGE)
+    kept = np.nonzero(keep)[0].astype(np.int32)
+    if len(kept) == 0 or w <= 2 * ORB_EDGE or h <= 2 * ORB_EDGE:
+        return np.zeros(0, np.int32), np.zeros((0, 32), np.uint8)
+    blur = gaussian_blur_7x7(img)
+    cx, cy = rx[kept], ry[kept]
+    ox, oy = orb_steered_pattern()
+    v = blur[cy[:, None] + oy[None, :], cx[:, None] + ox[None, :]]     # (n, 512)
+    bits = (v[:, 0::2] < v[:, 1::2]).astype(np.uint8)                 # (n, 256)
+    return kept, np.packbits(bits, axis=1, bitorder="little")

@@ -74,4 +74,20 @@ def test_cpp_host_mirror_matches_python_mirror(synth, tmp_path):
     line = [l.split() for l in out.stdout.splitlines() if l.startswith("matches ")][0]
     assert int(line[1]) == len(wm)
     assert [int(v) for v in line[2:]] == wm.ravel()[:9].tolist()
+
+    def checksum(values):
+        s = 0
+        for v in values:
+            s = (s * 31 + int(v)) & 0xFFFFFFFF
+        return s
+    kept, desc = F.orb_describe(img, want)
+    line = [l.split() for l in out.stdout.splitlines() if l.startswith("described ")][0]
+    assert int(line[1]) == len(kept) and len(kept) > 5 and int(line[3]) == checksum(desc.ravel())
+    img2 = np.roll(img, -3, axis=1)
+    c2 = F.good_features_to_track(img2)
+    kept2, desc2 = F.orb_describe(img2, c2)
+    wm = F.match_descriptors(desc, desc2)
+    line = [l.split() for l in out.stdout.splitlines() if l.startswith("chain ")][0]
+    assert [int(v) for v in line[1:5]] == [len(kept), 0, len(kept2), len(wm)]
+    assert int(line[6]) == checksum(wm.ravel() & 0xFFFFFFFF)
     lom.close(); vo.close()

@@ -188,3 +188,171 @@ def test_cuda_detector_hits_the_opencv_vectors(detect_golden):
         assert np.array_equal(few[0], F.good_features_to_track(img, 100, 0.1, 20.0))
         assert few[1].shape == (0, 2)
         vo.close()
+
+
+# ------------------------------------------------------------------------------------------------ ORB description, processImage
+ORB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "vo_orb_cv2.npz")
+VIEWS = ("kitti", "small", "shapes", "kitti_w1087", "kitti_next")
+
+
+def _views(g):
+    """The images of the ORB fixture, rebuilt from the committed detection images (tests/golden/make_golden_vo_orb.py views())."""
+    k = g["kitti_image"]
+    nxt = np.roll(k, (-2, 5), axis=(0, 1)).astype(np.int32)
+    yy, xx = np.mgrid[0:k.shape[0], 0:k.shape[1]]
+    nxt = np.clip(nxt + ((xx * 7 + yy * 13) % 5) - 2, 0, 255).astype(np.uint8)
+    return {"kitti": k, "small": g["small_image"], "shapes": g["shapes_image"], "kitti_w1087": np.ascontiguousarray(k[:300, 40:1127]),
+            "kitti_next": nxt}
+
+
+@pytest.fixture(scope="module")
+def orb_golden():
+    return np.load(ORB)
+
+
+def test_numpy_orb_description_matches_opencv(detect_golden, orb_golden):
+    """ImageUtil::descKeypoints (image_util.cpp:162-212) against cv2.ORB's own outputs: which key points survive ORB's border
+    filter (indices, order) and every descriptor byte — on the detector's corners and on key points chosen to sit on the filter's
+    band, at exact halves (cvRound) and outside the image; the detection + description + matching chain of processImage too."""
+    from oracle import vo_frontend as F
+    g = orb_golden
+    feats = {}
+    for name, img in _views(detect_golden).items():
+        corners = F.good_features_to_track(img)
+        assert np.array_equal(corners, g[f"{name}_corners"]), (name, "corners")
+        kept, desc = F.orb_describe(img, corners)
+        assert np.array_equal(kept, g[f"{name}_kept_index"]) and np.array_equal(desc, g[f"{name}_desc"]), name
+        feats[name] = desc
+        kept, desc = F.orb_describe(img, g[f"{name}_extra"])
+        assert np.array_equal(kept, g[f"{name}_extra_kept_index"]) and np.array_equal(desc, g[f"{name}_extra_desc"]), (name, "extra")
+        assert 0 < len(kept) < len(g[f"{name}_extra"])
+    assert np.array_equal(F.match_descriptors(feats["kitti"], feats["kitti_next"]), g["chain_matches"])
+    assert len(g["chain_matches"]) > 500
+    # degenerate inputs: no key point, every key point filtered, an image too small to hold any
+    img = detect_golden["small_image"]
+    for kp in (np.zeros((0, 2), np.float32), np.array([[3.0, 3.0], [630.0, 100.0]], np.float32)):
+        kept, desc = F.orb_describe(img, kp)
+        assert kept.shape == (0,) and desc.shape == (0, 32)
+    assert F.orb_describe(img[:62, :300], np.array([[31.0, 31.0]], np.float32))[0].shape == (0,)
+    assert F.orb_describe(img[:63, :300], np.array([[31.0, 31.0]], np.float32))[0].shape == (1,)
+
+
+def test_orb_pattern_is_steering_invariant_at_minus_one_degree():
+    """The key points carry cv::KeyPoint's default angle -1: the rotated pattern rounds back to the table (so the table is what
+    the probing script recovers, and what the kernel indexes without rotating)."""
+    from oracle import vo_frontend as F
+    from oracle.orb_pattern import ORB_PATTERN
+    x, y = F.orb_steered_pattern(-1.0)
+    p = np.array(ORB_PATTERN, np.int32).reshape(-1, 2)
+    assert np.array_equal(x, p[:, 0]) and np.array_equal(y, p[:, 1])
+    assert np.abs(p).max() == 13                      # the reach vo_orb_describe's 33 x 33 patch is sized for
+    x5, y5 = F.orb_steered_pattern(5.0)
+    assert not (np.array_equal(x5, p[:, 0]) and np.array_equal(y5, p[:, 1]))
+
+
+def test_orb_blur_and_description_against_opencv_across_image_sizes():
+    """The float rounding sequence of the blur (fused vector body, unfused scalar tails; oracle/vo_frontend.py gaussian_blur_7x7)
+    against cv2.sepFilter2D with cv2's own taps, and the whole description against cv2.ORB, on random images whose widths put
+    sampled pixels into the row pass's scalar tail."""
+    cv2 = pytest.importorskip("cv2")
+    from oracle import vo_frontend as F
+    taps = cv2.getGaussianKernel(7, 2, cv2.CV_32F).ravel()
+    assert np.array_equal(taps, F._gauss7_taps())
+    rng = np.random.default_rng(5)
+    orb = cv2.ORB_create()
+    for t in range(10):
+        h, w = int(rng.integers(70, 420)), (32 * int(rng.integers(3, 30)) + 31 if t < 4 else int(rng.integers(70, 1300)))
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        if t % 2:
+            img = cv2.GaussianBlur(img, (0, 0), 2.0)             # smooth content: many near-ties in the 256 comparisons
+        assert np.array_equal(F.gaussian_blur_7x7(img), cv2.sepFilter2D(img, cv2.CV_8U, taps, taps, borderType=cv2.BORDER_REFLECT_101)), (h, w)
+        kp = np.stack([rng.random(1500) * (w + 4) - 2, rng.random(1500) * (h + 4) - 2], 1).astype(np.float32)
+        k2, d = orb.compute(img, [cv2.KeyPoint(float(x), float(y), 5.0) for x, y in kp])
+        kept, desc = F.orb_describe(img, kp)
+        assert np.array_equal(np.array([k.pt for k in k2], np.float32).reshape(-1, 2), kp[kept]), (h, w)
+        assert np.array_equal(d, desc), (h, w)
+
+
+def test_opencv_still_reproduces_the_orb_vectors(detect_golden, orb_golden):
+    cv2 = pytest.importorskip("cv2")
+    g = orb_golden
+    for name, img in _views(detect_golden).items():
+        for key in ("corners", "extra"):
+            pts = g[f"{name}_{key}"]
+            kept, d = cv2.ORB_create().compute(img, [cv2.KeyPoint(float(x), float(y), 5.0) for x, y in pts])
+            idx = g[f"{name}_kept_index" if key == "corners" else f"{name}_extra_kept_index"]
+            assert np.array_equal(np.array([k.pt for k in kept], np.float32).reshape(-1, 2), pts[idx]), (name, key)
+            assert np.array_equal(d, g[f"{name}_desc" if key == "corners" else f"{name}_extra_desc"]), (name, key)
+
+
+@pytest.mark.gpu
+def test_cuda_orb_description_hits_the_opencv_vectors(detect_golden, orb_golden):
+    """vo_orb_describe == cv2.ORB on the committed vectors (surviving key points, their order, every descriptor byte), on the
+    detector's corners taken from the device and on host key points; second stream: the flipped image against the restatement."""
+    import vloam_b200 as V
+    from oracle import vo_frontend as F
+    g = orb_golden
+    for name, img in _views(detect_golden).items():
+        vo = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+        flipped = np.ascontiguousarray(img[::-1, ::-1])
+        pair = np.stack([img, flipped])
+        corners = vo.detKeypoints(pair)
+        assert np.array_equal(corners[0], g[f"{name}_corners"]), name
+        res = vo.descKeypoints()                                     # corners and images still on the device
+        assert np.array_equal(res[0]["index"], g[f"{name}_kept_index"]), name
+        assert np.array_equal(res[0]["descriptors"], g[f"{name}_desc"]), name
+        assert np.array_equal(res[0]["keypoints"], corners[0][g[f"{name}_kept_index"]]), name
+        kept, desc = F.orb_describe(flipped, corners[1])
+        assert np.array_equal(res[1]["index"], kept) and np.array_equal(res[1]["descriptors"], desc), (name, "flipped")
+        # host key points and host images
+        ex = g[f"{name}_extra"]
+        res = vo.descKeypoints([ex, ex[::-1]], pair)
+        assert np.array_equal(res[0]["index"], g[f"{name}_extra_kept_index"]) and np.array_equal(res[0]["descriptors"], g[f"{name}_extra_desc"]), (name, "extra")
+        kept, desc = F.orb_describe(flipped, ex[::-1])
+        assert np.array_equal(res[1]["index"], kept) and np.array_equal(res[1]["descriptors"], desc), (name, "extra, flipped")
+        # degenerate: no key point / every key point filtered
+        res = vo.descKeypoints([np.zeros((0, 2), np.float32), np.array([[3.0, 3.0], [5.0, 100.0]], np.float32)], pair)
+        assert res[0]["descriptors"].shape == (0, 32) and res[1]["descriptors"].shape == (0, 32)
+        vo.close()
+
+
+@pytest.mark.gpu
+def test_cuda_process_image_chain_hits_the_opencv_vectors(detect_golden, orb_golden):
+    """VisualOdometry::processImage over two frames, everything on the device after the image upload: the features of both frames,
+    the ratio-tested matches and the matched pixel pairs handed to solveNlsAll equal cv2's."""
+    import vloam_b200 as V
+    from oracle import vo_frontend as F
+    g = orb_golden
+    v = _views(detect_golden)
+    a, b = v["kitti"], v["kitti_next"]
+    vo = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+    frames = (np.stack([a, b[::-1].copy()]), np.stack([b, a[::-1].copy()]))       # stream 1: other images, the other way round
+    vo.reset()
+    r0 = vo.processImage(frames[0])
+    assert r0["n_keypoints"][0] == len(g["kitti_desc"]) and np.array_equal(r0["n_matches"], [0, 0])
+    vo.reset()
+    r1 = vo.processImage(frames[1])
+    assert r1["n_keypoints"][0] == len(g["kitti_next_desc"]) and r1["n_matches"][0] == len(g["chain_matches"])
+    cur, prev = vo.frame_features(0), vo.frame_features(1)
+    assert np.array_equal(prev[0]["descriptors"], g["kitti_desc"]) and np.array_equal(cur[0]["descriptors"], g["kitti_next_desc"])
+    assert np.array_equal(prev[0]["keypoints"], g["kitti_corners"][g["kitti_kept_index"]])
+    m = vo.matches()
+    assert np.array_equal(m[0], g["chain_matches"])
+    uq, ut = vo.match_uv()
+    assert np.array_equal(uq[0, :len(m[0])], prev[0]["keypoints"][m[0][:, 0]]) and np.array_equal(ut[0, :len(m[0])], cur[0]["keypoints"][m[0][:, 1]])
+    # stream 1 against the restatement
+    feats = []
+    for img in (frames[0][1], frames[1][1]):
+        c = F.good_features_to_track(img)
+        kept, desc = F.orb_describe(img, c)
+        feats.append((c[kept], desc))
+    assert np.array_equal(prev[1]["keypoints"], feats[0][0]) and np.array_equal(prev[1]["descriptors"], feats[0][1])
+    assert np.array_equal(cur[1]["keypoints"], feats[1][0]) and np.array_equal(cur[1]["descriptors"], feats[1][1])
+    assert np.array_equal(m[1], F.match_descriptors(feats[0][1], feats[1][1]))
+    # a third frame: the slots swap again (query = frame 2's features)
+    vo.reset()
+    r2 = vo.processImage(frames[0])
+    assert np.array_equal(vo.frame_features(1)[0]["descriptors"], g["kitti_next_desc"])
+    assert np.array_equal(vo.matches()[0], F.match_descriptors(g["kitti_next_desc"], g["kitti_desc"]))
+    assert r2["n_matches"][0] == len(vo.matches()[0])
+    vo.close()

@@ -118,6 +118,9 @@ def lib():
             "vloam_vo_detect_corners": [vp, vp, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, vp, vp],
             "vloam_vo_get_corner_response": [vp, C.c_int, vp, C.c_size_t], "vloam_vo_get_corner_buffers": [vp, pp, pp],
             "vloam_vo_get_residuals": [vp, C.c_int, c_ip, c_dp],
+            "vloam_vo_describe_orb": [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp],
+            "vloam_vo_process_image": [vp, vp, C.c_int, C.c_int, vp, vp],
+            "vloam_vo_get_frame_features": [vp, C.c_int, vp, vp, vp], "vloam_vo_get_matches": [vp, vp, vp],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -556,9 +559,9 @@ class LidarOdometryMapping:
 
 
 class VisualOdometry:
-    """Mirror of the in-scope part of vloam::VisualOdometry for `batch` streams: of processImage the Shi-Tomasi detection
-    (detKeypoints) and the descriptor matching (matchDescriptors) — ORB description stays with OpenCV on the host —, then
-    depth association, residual construction and the solve (processPointCloud, solveNlsAll)."""
+    """Mirror of the in-scope part of vloam::VisualOdometry for `batch` streams: processImage (Shi-Tomasi detection, ORB
+    description, descriptor matching: detKeypoints / descKeypoints / matchDescriptors), then depth association, residual
+    construction and the solve (processPointCloud, solveNlsAll)."""
 
     def __init__(self, ctx: Context | None = None, batch: int = 1, max_points: int = 131072, max_matches: int = 1024,
                  remove_VO_outlier: int = 100, max_num_iterations: int = 100):
@@ -671,6 +674,69 @@ class VisualOdometry:
                                                      float(min_distance), _ptr(out), _ptr(n)))
         self._det_shape = a.shape[1:]
         return [out[b, :n[b]].copy() for b in range(self.batch)]
+
+    # -- image_util.cpp:162-212 (DescriptorType::ORB)
+    def descKeypoints(self, keypoints=None, images=None):
+        """ImageUtil::descKeypoints with DescriptorType::ORB: keypoints = per stream an (n, 2) float32 array of cv::KeyPoint::pt
+        (one array for batch 1), or None = the corners of the last detKeypoints call (still on the device); images = (batch, H, W)
+        or (H, W) uint8, or None = the images of that call.  Returns per stream {"keypoints": the key points ORB keeps (the
+        reference's vector after the call), "index": their positions in the input list, "descriptors": (n, 32) uint8}."""
+        B, M = self.batch, self.max_matches
+        kp = n = img = None
+        H = W = 0
+        if keypoints is not None:
+            if isinstance(keypoints, np.ndarray) and keypoints.ndim == 2:
+                keypoints = [keypoints]
+            assert len(keypoints) == B
+            kp = np.zeros((B, M, 2), np.float32)
+            n = np.zeros(B, np.int32)
+            for b in range(B):
+                a = np.ascontiguousarray(keypoints[b], np.float32).reshape(-1, 2)
+                n[b] = a.shape[0]
+                kp[b, :min(n[b], M)] = a[:M]
+        if images is not None:
+            img = np.ascontiguousarray(images, np.uint8)
+            if img.ndim == 2:
+                img = img[None]
+            assert img.shape[0] == B
+            H, W = img.shape[1:]
+        kxy = np.zeros((B, M, 2), np.float32)
+        kidx = np.zeros((B, M), np.int32)
+        desc = np.zeros((B, M, 32), np.uint8)
+        nk = np.zeros(B, np.int32)
+        self.ctx.check(lib().vloam_vo_describe_orb(self._h, _ptr(img), H, W, _ptr(kp), _ptr(n), _ptr(kxy), _ptr(kidx), _ptr(desc), _ptr(nk)))
+        return [{"keypoints": kxy[b, :nk[b]].copy(), "index": kidx[b, :nk[b]].copy(), "descriptors": desc[b, :nk[b]].copy()} for b in range(B)]
+
+    # -- visual_odometry.cpp:92-130
+    def processImage(self, images, fetch: bool = True):
+        """VisualOdometry::processImage: detection, description and (from the second frame on) matching against the previous
+        frame on the device; call reset() first, like the reference's frame loop.  fetch: return per stream
+        {"n_keypoints", "n_matches"}; the features and matches are read with frame_features() / matches()."""
+        a = np.ascontiguousarray(images, np.uint8)
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape[0] == self.batch, a.shape
+        nk = np.zeros(self.batch, np.int32) if fetch else None
+        nm = np.zeros(self.batch, np.int32) if fetch else None
+        self.ctx.check(lib().vloam_vo_process_image(self._h, _ptr(a), a.shape[1], a.shape[2], _ptr(nk), _ptr(nm)))
+        self._det_shape = a.shape[1:]
+        return {"n_keypoints": nk, "n_matches": nm} if fetch else None
+
+    def frame_features(self, slot: int = 0):
+        """keypoints[slot] / descriptors[slot] of the processImage chain (0 = current frame, 1 = previous), per stream."""
+        B, M = self.batch, self.max_matches
+        kxy = np.zeros((B, M, 2), np.float32)
+        desc = np.zeros((B, M, 32), np.uint8)
+        nk = np.zeros(B, np.int32)
+        self.ctx.check(lib().vloam_vo_get_frame_features(self._h, slot, _ptr(kxy), _ptr(desc), _ptr(nk)))
+        return [{"keypoints": kxy[b, :nk[b]].copy(), "descriptors": desc[b, :nk[b]].copy()} for b in range(B)]
+
+    def matches(self):
+        """The (queryIdx, trainIdx, distance) rows of the last processImage / matchDescriptors call, per stream."""
+        m = np.zeros((self.batch, self.max_matches, 3), np.int32)
+        nm = np.zeros(self.batch, np.int32)
+        self.ctx.check(lib().vloam_vo_get_matches(self._h, _ptr(m), _ptr(nm)))
+        return [m[b, :nm[b]].copy() for b in range(self.batch)]
 
     def corner_response(self, stream: int = 0):
         """cv::cornerMinEigenVal map of the last detKeypoints call, (H, W) float32."""

@@ -93,8 +93,8 @@ class LidarOdometryMapping {
 };
 
 // ROS-free mirror of vloam::VisualOdometry's depth-association / solve half
-// (reference include/visual_odometry/visual_odometry.h:40-121; processImage stays with OpenCV on the caller's side and
-// hands over the matched keypoint pixels).  One instance per sensor; shares the context of a LidarOdometryMapping when
+// (reference include/visual_odometry/visual_odometry.h:40-121) and of processImage in the reference's configuration
+// (Shi-Tomasi + ORB + BF / kNN: detKeypoints, descKeypoints, matchDescriptors, or the whole chain in one call).  One instance per sensor; shares the context of a LidarOdometryMapping when
 // given one, so that the scan uploaded by scanRegistrationIO is also VO's cloud (vloam_main_node.cpp:148-166).
 class VisualOdometry {
  public:
@@ -151,6 +151,43 @@ class VisualOdometry {
     check(vloam_vo_match_descriptors(h_, q.data(), &n_query, t.data(), &n_train, nullptr, nullptr, ratio, m.data(), &nm));
     m.resize((size_t)nm * 3);
     return m;
+  }
+  // ImageUtil::descKeypoints, DescriptorType::ORB (image_util.cpp:162-212): n key points (x, y) on an 8-bit grey image -> the key
+  // points cv::ORB keeps (the reference's vector after the call) and their 32-byte descriptor rows
+  struct Features {
+    std::vector<float> keypoints_xy;      // 2 floats per key point
+    std::vector<uint8_t> descriptors;     // 32 bytes per key point (the rows of the cv::Mat)
+    int size() const { return (int)(keypoints_xy.size() / 2); }
+  };
+  Features descKeypoints(const uint8_t* image, int height, int width, const float* keypoints_xy, int n) {
+    n = n < max_matches_ ? n : max_matches_;
+    std::vector<float> in((size_t)max_matches_ * 2, 0.f);
+    std::copy(keypoints_xy, keypoints_xy + (size_t)n * 2, in.begin());
+    Features f;
+    f.keypoints_xy.resize((size_t)max_matches_ * 2); f.descriptors.resize((size_t)max_matches_ * 32);
+    int kept = 0;
+    check(vloam_vo_describe_orb(h_, image, height, width, in.data(), &n, f.keypoints_xy.data(), nullptr, f.descriptors.data(), &kept));
+    f.keypoints_xy.resize((size_t)kept * 2); f.descriptors.resize((size_t)kept * 32);
+    return f;
+  }
+  // VisualOdometry::processImage (visual_odometry.cpp:92-130) with ShiTomasi + ORB + BF / kNN: one image upload, detection,
+  // description and (after the first frame) matching on the device.  Call reset() first.  Returns keypoints[i], descriptors[i]
+  // and `matches` = (queryIdx into the previous frame's key points, trainIdx into this frame's, distance) triples.
+  struct Frame {
+    Features features;
+    std::vector<int> matches;
+  };
+  Frame processImage(const uint8_t* image, int height, int width) {
+    Frame fr;
+    int nk = 0, nm = 0;
+    check(vloam_vo_process_image(h_, image, height, width, &nk, &nm));
+    fr.features.keypoints_xy.resize((size_t)max_matches_ * 2); fr.features.descriptors.resize((size_t)max_matches_ * 32);
+    check(vloam_vo_get_frame_features(h_, 0, fr.features.keypoints_xy.data(), fr.features.descriptors.data(), &nk));
+    fr.features.keypoints_xy.resize((size_t)nk * 2); fr.features.descriptors.resize((size_t)nk * 32);
+    fr.matches.resize((size_t)max_matches_ * 3);
+    check(vloam_vo_get_matches(h_, fr.matches.data(), &nm));
+    fr.matches.resize((size_t)nm * 3);
+    return fr;
   }
   // PointCloudUtil::queryDepth (point_cloud_util.cpp:302-407); slot 0 = current frame, 1 = previous
   float queryDepth(float x, float y, int slot = 0) {

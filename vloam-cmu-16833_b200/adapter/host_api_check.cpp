@@ -19,7 +19,7 @@ int main(int argc, char** argv) {
     lom.params().max_points = 1 << 17;
     lom.params().map_capacity_points = 1 << 17;
     lom.init();
-    vloam_b200::VisualOdometry vo(1 << 17, 256, 0);
+    vloam_b200::VisualOdometry vo(1 << 17, 1024, 0);
     std::printf("context created\n");
     if (argc < 3 || std::strcmp(argv[1], "run") != 0) return 0;
     // KITTI-like calibration (vloam_b200/synth.py: kitti_like_calibration)
@@ -61,6 +61,21 @@ int main(int argc, char** argv) {
       std::printf("matches %zu", m.size() / 3);
       for (size_t i = 0; i < m.size() && i < 9; ++i) std::printf(" %d", m[i]);
       std::printf("\n");
+      // ImageUtil::descKeypoints (ORB) on those corners, then VisualOdometry::processImage over two frames (the second one moved by 3 px)
+      const vloam_b200::VisualOdometry::Features f = vo.descKeypoints(img.data(), H, W, xy.data(), (int)(xy.size() / 2));
+      unsigned sum = 0;
+      for (size_t i = 0; i < f.descriptors.size(); ++i) sum = sum * 31u + f.descriptors[i];
+      std::printf("described %d checksum %u\n", f.size(), sum);
+      std::vector<uint8_t> img2((size_t)H * W);
+      for (int y = 0; y < H; ++y)
+        for (int x = 0; x < W; ++x) img2[(size_t)y * W + x] = img[(size_t)y * W + (x + 3) % W];
+      vo.reset();
+      const vloam_b200::VisualOdometry::Frame f0 = vo.processImage(img.data(), H, W);
+      vo.reset();
+      const vloam_b200::VisualOdometry::Frame f1 = vo.processImage(img2.data(), H, W);
+      unsigned msum = 0;
+      for (size_t i = 0; i < f1.matches.size(); ++i) msum = msum * 31u + (unsigned)f1.matches[i];
+      std::printf("chain %d %zu %d %zu checksum %u\n", f0.features.size(), f0.matches.size() / 3, f1.features.size(), f1.matches.size() / 3, msum);
     }
   } catch (const std::exception& e) {
     std::printf("no device: %s\n", e.what());  // expected on a CPU-only box: the library refuses to run, no fallback

@@ -1,8 +1,7 @@
 // Drop-in replacement for include/visual_odometry/visual_odometry.h of YukunXia/VLOAM-CMU-16833: the same class name,
 // namespace, public methods and the public members the caller reads (cam0_curr_T_cam0_last, vloam_main_node.cpp:160), so
-// src/vloam_main/src/vloam_main_node.cpp compiles unchanged.  Of the image front end (processImage) the Shi-Tomasi detection
-// and the descriptor matching run on the device, ORB description stays with OpenCV; the LiDAR depth association, residual
-// construction and solve run through libvloam_b200.so.  Only built where ROS + PCL + OpenCV exist.
+// src/vloam_main/src/vloam_main_node.cpp compiles unchanged.  The image front end (processImage: Shi-Tomasi detection, ORB
+// description, descriptor matching), the LiDAR depth association, residual construction and solve run through libvloam_b200.so.  Only built where ROS + PCL + OpenCV exist.
 #pragma once
 #if __has_include(<ros/ros.h>) && __has_include(<pcl/point_cloud.h>) && __has_include(<opencv2/opencv.hpp>)
 #include <pcl/point_cloud.h>
@@ -48,12 +47,36 @@ class VisualOdometry {
 
   void reset() { ++count; i = count % 2; impl->reset(); }                                                      // :86-90
 
-  // :92-130.  Detection (Shi-Tomasi, image_util.cpp:11-37) and matching (BF + Hamming + ratio test, :214-296) run on the device
-  // when `vo_frontend_on_device` is set (new, optional parameter, default true) and the inputs have the shapes the reference
-  // produces (8-bit grey image, 32-byte ORB rows); ORB description (:162-212) and the optical-flow branch stay with OpenCV.
+  // :92-130.  With `vo_frontend_on_device` (new, optional parameter, default true), an 8-bit grey image and the descriptor
+  // branch (optical_flow_match false) the whole chain — detection (image_util.cpp:11-37), ORB description (:162-212), matching
+  // (:214-296) — is one device call whose results are mirrored into keypoints[i] / descriptors[i] / matches (after a frame that
+  // OpenCV processed the device holds no previous descriptors: that one frame is matched from the host copies).
   void processImage(const cv::Mat& img00) {
     if (CLAHE) clahe->apply(img00, images[i]); else images[i] = img00;
-    if (frontend_on_device && images[i].type() == CV_8UC1 && images[i].isContinuous()) {
+    const bool on_device = frontend_on_device && images[i].type() == CV_8UC1 && images[i].isContinuous();
+    if (on_device && !optical_flow_match && images[i].rows >= 3 && images[i].cols >= 3) {
+      const vloam_b200::VisualOdometry::Frame fr = impl->processImage(images[i].data, images[i].rows, images[i].cols);
+      const int n = fr.features.size();
+      keypoints[i].clear();
+      for (int k = 0; k < n; ++k) {                               // image_util.cpp:29-35, filtered by cv::ORB (:204)
+        cv::KeyPoint kp;
+        kp.pt = cv::Point2f(fr.features.keypoints_xy[2 * k], fr.features.keypoints_xy[2 * k + 1]);
+        kp.size = 5;
+        keypoints[i].push_back(kp);
+      }
+      descriptors[i] = n ? cv::Mat(n, 32, CV_8UC1, const_cast<uint8_t*>(fr.features.descriptors.data())).clone() : cv::Mat();
+      std::vector<int> m = fr.matches;
+      const cv::Mat& dq = descriptors[1 - i];
+      if (count > 0 && !device_prev)
+        m = (n && dq.type() == CV_8UC1 && dq.cols == 32 && dq.isContinuous()) ? impl->matchDescriptors(dq.data, dq.rows, descriptors[i].data, n)
+                                                                              : std::vector<int>();
+      matches.clear();
+      for (size_t k = 0; k + 2 < m.size(); k += 3) matches.emplace_back(m[k], m[k + 1], (float)m[k + 2]);       // cv::DMatch(queryIdx, trainIdx, distance)
+      device_prev = true;
+      return;
+    }
+    device_prev = false;
+    if (on_device) {
       const std::vector<float> xy = impl->detKeypoints(images[i].data, images[i].rows, images[i].cols);
       keypoints[i].clear();
       for (size_t k = 0; k + 1 < xy.size(); k += 2) {            // image_util.cpp:29-35
@@ -161,7 +184,7 @@ class VisualOdometry {
   ros::NodeHandle nh;
   int verbose_level = 0, remove_VO_outlier = 100;
   bool reset_VO_to_identity = false, keypoint_NMS = false, CLAHE = false, visualize_optical_flow = false, optical_flow_match = false;
-  bool frontend_on_device = true;
+  bool frontend_on_device = true, device_prev = false;
   cv::Ptr<cv::CLAHE> clahe;
   nav_msgs::Odometry visualOdometry;
   nav_msgs::Path visualPath;

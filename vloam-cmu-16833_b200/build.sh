@@ -6,8 +6,8 @@ mkdir -p lib
 NVCC=${NVCC:-/usr/local/cuda/bin/nvcc}
 FLAGS="-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC -Xptxas -v"
 OBJS=""
-HDRS="csrc/common.cuh csrc/internal.h csrc/gn_solver.cuh csrc/cta_sort.cuh csrc/gn_split.cuh csrc/gn_jet.cuh csrc/tma_bulk.cuh csrc/fdlibm_atan2f.h ../include/vloam_b200.h"
-for f in sr_kernels lo_kernels lm_kernels vo_kernels vo_detect gn_split capi; do
+HDRS="csrc/common.cuh csrc/internal.h csrc/gn_solver.cuh csrc/cta_sort.cuh csrc/gn_split.cuh csrc/gn_jet.cuh csrc/tma_bulk.cuh csrc/fdlibm_atan2f.h csrc/orb_pattern.inc ../include/vloam_b200.h"
+for f in sr_kernels lo_kernels lm_kernels vo_kernels vo_detect vo_orb gn_split capi; do
   stale=0
   [ -f lib/$f.o ] || stale=1
   for d in csrc/$f.cu $HDRS; do [ "$d" -nt lib/$f.o ] && stale=1; done

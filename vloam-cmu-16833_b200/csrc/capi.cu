@@ -25,7 +25,7 @@ const char* kernel_name(int id) {
       "lo_set_motion", "lo_associate", "lo_solve", "lo_export_pose", "lo_init_state", "lo_build_grid", "lo_associate_brute",
       "lm_prepare", "lm_voxel", "lm_index", "lm_associate", "lm_fit", "lm_solve", "lm_insert", "lm_refilter", "lm_place", "lm_misc",
       "lo_accumulate", "lo_step", "lm_accumulate", "lm_step",
-      "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc", "vo_bf_match", "vo_detect"};
+      "vo_project", "vo_bucket", "vo_query", "vo_solve", "vo_misc", "vo_bf_match", "vo_detect", "vo_orb_describe"};
   return (id >= 0 && id < K_COUNT) ? names[id] : "?";
 }
 cudaEvent_t Profiler::get() {

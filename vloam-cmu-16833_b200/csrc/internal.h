@@ -17,7 +17,7 @@ enum KernelId {
   K_LO_SET_MOTION, K_LO_ASSOCIATE, K_LO_SOLVE, K_LO_EXPORT, K_LO_INIT, K_LO_BUILD_GRID, K_LO_ASSOCIATE_BRUTE,
   K_LM_PREPARE, K_LM_VOXEL, K_LM_GRID, K_LM_ASSOCIATE, K_LM_FIT, K_LM_SOLVE, K_LM_INSERT, K_LM_REFILTER, K_LM_PLACE, K_LM_MISC,
   K_LO_ACCUMULATE, K_LO_STEP, K_LM_ACCUMULATE, K_LM_STEP,
-  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC, K_VO_MATCH, K_VO_DETECT,
+  K_VO_PROJECT, K_VO_BUCKET, K_VO_QUERY, K_VO_SOLVE, K_VO_MISC, K_VO_MATCH, K_VO_DETECT, K_VO_DESCRIBE,
   K_COUNT
 };
 const char* kernel_name(int id);
@@ -108,6 +108,11 @@ const float* vo_detect_corners_device(const VODetect* d);
 const int* vo_detect_counts_device(const VODetect* d);
 int vo_detect_height(const VODetect* d);
 int vo_detect_width(const VODetect* d);
+const uint8_t* vo_detect_image_device(const VODetect* d);
+int vo_detect_max_corners(const VODetect* d);
+// vo_orb.cu: ORB description of given key points (image_util.cpp:162-212)
+void launch_vo_orb_describe(Profiler* prof, cudaStream_t st, int B, const uint8_t* img, int H, int W, const float* kp, const int* nKp,
+                            int kpStride, int maxK, float* keptXY, int* keptIdx, uint8_t* desc, int* nKept);
 void vo_detect_destroy(VODetect* d);
 cudaError_t lm_get_registered(LMDevice* lm, cudaStream_t st, int stream, const float4* cloud, int n, float* out, int capacity, int* n_out);
 cudaError_t lm_get_map_cloud(LMDevice* lm, cudaStream_t st, int stream, float* out, int capacity, int* n_out);

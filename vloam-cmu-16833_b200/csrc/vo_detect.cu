@@ -328,5 +328,7 @@ const float* vo_detect_corners_device(const VODetect* d) { return d->corners; }
 const int* vo_detect_counts_device(const VODetect* d) { return d->nCorners; }
 int vo_detect_height(const VODetect* d) { return d->H; }
 int vo_detect_width(const VODetect* d) { return d->W; }
+const uint8_t* vo_detect_image_device(const VODetect* d) { return d->img; }
+int vo_detect_max_corners(const VODetect* d) { return d->maxCorners; }
 
 }  // namespace vb

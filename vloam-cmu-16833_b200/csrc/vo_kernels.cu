@@ -556,6 +556,10 @@ struct vloam_vo {
   // descriptor matching: query / train descriptors [B][maxM][32], keypoints [B][maxM][2], counts, match list [B][maxM][3]
   uint8_t* d_desc[2] = {nullptr, nullptr}; float* d_kp[2] = {nullptr, nullptr}; int* d_nkp[2] = {nullptr, nullptr};
   int* d_matches = nullptr; int* d_nmatch = nullptr; float* d_muv[2] = {nullptr, nullptr}; int4* d_knn = nullptr;
+  // ORB description / processImage: per ping-pong slot the key points ORB kept, their descriptors and counts (same layouts),
+  // the index each kept key point had in the list given to ORB; upload buffers for host images / key points
+  uint8_t* d_fdesc[2] = {nullptr, nullptr}; float* d_fkp[2] = {nullptr, nullptr}; int* d_fn[2] = {nullptr, nullptr}; int* d_fidx = nullptr;
+  uint8_t* d_orbimg = nullptr; size_t orbimg_bytes = 0; float* d_orbkp = nullptr; int* d_orbn = nullptr;
   int qcap = 0;
   vb::VODetect* det = nullptr;   // key-point detection (vo_detect.cu), created by the first vloam_vo_detect_corners
   int slot() const { return (int)(count % 2); }
@@ -581,6 +585,8 @@ int vloam_vo_destroy(vloam_vo* h) {
   cudaFree(h->d_q); cudaFree(h->d_qo);
   for (int i = 0; i < 2; ++i) { cudaFree(h->d_desc[i]); cudaFree(h->d_kp[i]); cudaFree(h->d_nkp[i]); cudaFree(h->d_muv[i]); }
   cudaFree(h->d_matches); cudaFree(h->d_nmatch); cudaFree(h->d_knn);
+  for (int i = 0; i < 2; ++i) { cudaFree(h->d_fdesc[i]); cudaFree(h->d_fkp[i]); cudaFree(h->d_fn[i]); }
+  cudaFree(h->d_fidx); cudaFree(h->d_orbimg); cudaFree(h->d_orbkp); cudaFree(h->d_orbn);
   vb::vo_detect_destroy(h->det);
   delete h;
   return VLOAM_OK;
@@ -609,7 +615,9 @@ int vloam_vo_create(vloam_ctx* c, int batch, int max_points, int max_matches, vl
   for (int i = 0; i < 2; ++i) {
     A((void**)&h->d_desc[i], B * M * 32); A((void**)&h->d_kp[i], B * M * 2 * sizeof(float)); A((void**)&h->d_nkp[i], B * sizeof(int));
     A((void**)&h->d_muv[i], B * M * 2 * sizeof(float));
+    A((void**)&h->d_fdesc[i], B * M * 32); A((void**)&h->d_fkp[i], B * M * 2 * sizeof(float)); A((void**)&h->d_fn[i], B * sizeof(int));
   }
+  A((void**)&h->d_fidx, B * M * sizeof(int)); A((void**)&h->d_orbkp, B * M * 2 * sizeof(float)); A((void**)&h->d_orbn, B * sizeof(int));
   A((void**)&h->d_matches, B * M * 3 * sizeof(int)); A((void**)&h->d_nmatch, B * sizeof(int)); A((void**)&h->d_knn, B * M * sizeof(int4));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(vo_bf_match, cudaFuncAttributeMaxDynamicSharedMemorySize, kMatchChunk * 32 + 16);
   if (e != cudaSuccess) { vloam_vo_destroy(h); return vfail(c, VLOAM_E_CUDA, "vloam_vo_create: allocation", e); }
@@ -866,6 +874,118 @@ int vloam_vo_get_corner_buffers(vloam_vo* h, const float** corners_xy_dev, const
   if (!h || !corners_xy_dev || !n_corners_dev) return VLOAM_E_INVALID;
   if (!h->det) return vfail(h->ctx, VLOAM_E_STATE, "vloam_vo_get_corner_buffers before vloam_vo_detect_corners");
   *corners_xy_dev = vb::vo_detect_corners_device(h->det); *n_corners_dev = vb::vo_detect_counts_device(h->det);
+  return VLOAM_OK;
+}
+
+// ImageUtil::descKeypoints with DescriptorType::ORB (image_util.cpp:162-212): cv::ORB::create()->compute on key points of angle -1
+namespace {
+// Enqueues the description of `kp_dev` ([B][kp_stride][2], counts n_dev) on `img_dev` into the handle's slot `fs`.
+int vo_enqueue_describe(vloam_vo* h, const uint8_t* img_dev, int height, int width, const float* kp_dev, const int* n_dev, int kp_stride, int fs) {
+  vloam_ctx* c = h->ctx;
+  vb::launch_vo_orb_describe(&c->prof, c->stream, h->B, img_dev, height, width, kp_dev, n_dev, kp_stride, h->maxM, h->d_fkp[fs], h->d_fidx,
+                             h->d_fdesc[fs], h->d_fn[fs]);
+  VCU(c, cudaGetLastError());
+  return VLOAM_OK;
+}
+int vo_feature_slot(const vloam_vo* h) { return h->count < 0 ? 0 : h->slot(); }
+}  // namespace
+
+int vloam_vo_describe_orb(vloam_vo* h, const uint8_t* images, int height, int width, const float* keypoints_xy, const int* n_keypoints,
+                          float* kept_xy, int* kept_index, uint8_t* descriptors, int* n_kept) {
+  if (!h || (keypoints_xy == nullptr) != (n_keypoints == nullptr)) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  const size_t B = h->B, M = h->maxM;
+  const uint8_t* img_dev = nullptr;
+  if (images) {
+    if (height < 1 || width < 1 || (long long)height * width > (1ll << 28)) return VLOAM_E_INVALID;
+    const size_t bytes = B * (size_t)height * width;
+    if (bytes > h->orbimg_bytes) {
+      VCU(c, cudaStreamSynchronize(st));
+      cudaFree(h->d_orbimg); h->d_orbimg = nullptr; h->orbimg_bytes = 0;
+      VCU(c, cudaMalloc((void**)&h->d_orbimg, bytes));
+      h->orbimg_bytes = bytes;
+    }
+    VCU(c, cudaMemcpyAsync(h->d_orbimg, images, bytes, cudaMemcpyHostToDevice, st));
+    img_dev = h->d_orbimg;
+  } else {
+    if (!h->det) return vfail(c, VLOAM_E_STATE, "vloam_vo_describe_orb: images == NULL needs a previous vloam_vo_detect_corners");
+    img_dev = vb::vo_detect_image_device(h->det); height = vb::vo_detect_height(h->det); width = vb::vo_detect_width(h->det);
+  }
+  const float* kp_dev = nullptr; const int* n_dev = nullptr; int stride = 0;
+  if (keypoints_xy) {
+    for (int b = 0; b < h->B; ++b) if (n_keypoints[b] < 0 || n_keypoints[b] > h->maxM) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_describe_orb: more keypoints than max_matches");
+    VCU(c, cudaMemcpyAsync(h->d_orbkp, keypoints_xy, B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
+    VCU(c, cudaMemcpyAsync(h->d_orbn, n_keypoints, B * sizeof(int), cudaMemcpyHostToDevice, st));
+    kp_dev = h->d_orbkp; n_dev = h->d_orbn; stride = h->maxM;
+  } else {
+    if (!h->det) return vfail(c, VLOAM_E_STATE, "vloam_vo_describe_orb: keypoints == NULL needs a previous vloam_vo_detect_corners");
+    kp_dev = vb::vo_detect_corners_device(h->det); n_dev = vb::vo_detect_counts_device(h->det); stride = vb::vo_detect_max_corners(h->det);
+    if (stride > h->maxM) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_describe_orb: the detection's max_corners exceeds max_matches");
+  }
+  const int fs = vo_feature_slot(h);
+  if (int rc = vo_enqueue_describe(h, img_dev, height, width, kp_dev, n_dev, stride, fs)) return rc;
+  if (kept_xy) VCU(c, cudaMemcpyAsync(kept_xy, h->d_fkp[fs], B * M * 2 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (kept_index) VCU(c, cudaMemcpyAsync(kept_index, h->d_fidx, B * M * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (descriptors) VCU(c, cudaMemcpyAsync(descriptors, h->d_fdesc[fs], B * M * 32, cudaMemcpyDeviceToHost, st));
+  if (n_kept) VCU(c, cudaMemcpyAsync(n_kept, h->d_fn[fs], B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  VCU(c, cudaStreamSynchronize(st));
+  return VLOAM_OK;
+}
+
+// VisualOdometry::processImage (visual_odometry.cpp:92-130) with the reference's selections (ShiTomasi + ORB + BF / kNN 0.8):
+// images -> keypoints[i], descriptors[i] -> (count > 0) matches of descriptors[1 - i] (query, previous frame) in descriptors[i] (train).
+int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int width, int* n_keypoints, int* n_matches) {
+  if (!h || !images || height < 3 || width < 3) return VLOAM_E_INVALID;
+  if ((long long)height * width > (1ll << 28)) return VLOAM_E_CAPACITY;
+  vloam_ctx* c = h->ctx;
+  if (h->count < 0) return vfail(c, VLOAM_E_STATE, "vloam_vo_process_image before vloam_vo_reset");
+  if (h->maxM < 1024) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_process_image: max_matches must hold the detector's 1024 corners");
+  VCU(c, cudaSetDevice(c->device));
+  cudaStream_t st = c->stream;
+  int status = 0;
+  VCU(c, vb::vo_detect_run(&h->det, &c->prof, st, h->B, images, height, width, 1024, 0.03, 7.5, &status));      // image_util.cpp:13-26
+  if (status) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_process_image: more local maxima than a quarter of the pixels (plateaus of equal response)");
+  const int i = h->slot();
+  if (int rc = vo_enqueue_describe(h, vb::vo_detect_image_device(h->det), height, width, vb::vo_detect_corners_device(h->det),
+                                   vb::vo_detect_counts_device(h->det), 1024, i)) return rc;
+  if (h->count > 0) {
+    VB_LAUNCH(&c->prof, K_VO_MATCH, st, vo_bf_match<<<h->B, kMatchThreads, kMatchChunk * 32 + 16, st>>>(
+                                            h->d_fdesc[1 - i], h->d_fn[1 - i], h->d_fdesc[i], h->d_fn[i], h->maxM, h->d_fkp[1 - i], h->d_fkp[i], 0.8,
+                                            h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
+    VCU(c, cudaGetLastError());
+  } else {
+    VCU(c, cudaMemsetAsync(h->d_nmatch, 0, h->B * sizeof(int), st));
+  }
+  if (n_keypoints) VCU(c, cudaMemcpyAsync(n_keypoints, h->d_fn[i], h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_matches) VCU(c, cudaMemcpyAsync(n_matches, h->d_nmatch, h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (n_keypoints || n_matches) VCU(c, cudaStreamSynchronize(st));
+  return VLOAM_OK;
+}
+
+// keypoints[slot] / descriptors[slot] of the processImage chain (slot 0 = current frame, 1 = previous frame), host copies.
+int vloam_vo_get_frame_features(vloam_vo* h, int slot, float* keypoints_xy, uint8_t* descriptors, int* n_keypoints) {
+  if (!h || slot < 0 || slot > 1) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  const int fs = slot == 0 ? vo_feature_slot(h) : 1 - vo_feature_slot(h);
+  const size_t B = h->B, M = h->maxM;
+  if (keypoints_xy) VCU(c, cudaMemcpyAsync(keypoints_xy, h->d_fkp[fs], B * M * 2 * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  if (descriptors) VCU(c, cudaMemcpyAsync(descriptors, h->d_fdesc[fs], B * M * 32, cudaMemcpyDeviceToHost, c->stream));
+  if (n_keypoints) VCU(c, cudaMemcpyAsync(n_keypoints, h->d_fn[fs], B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
+  return VLOAM_OK;
+}
+
+// The match list of the last vloam_vo_match_descriptors / vloam_vo_process_image: matches[batch][max_matches][3], n_matches[batch].
+int vloam_vo_get_matches(vloam_vo* h, int* matches, int* n_matches) {
+  if (!h || !matches || !n_matches) return VLOAM_E_INVALID;
+  vloam_ctx* c = h->ctx;
+  VCU(c, cudaSetDevice(c->device));
+  VCU(c, cudaMemcpyAsync(matches, h->d_matches, (size_t)h->B * h->maxM * 3 * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaMemcpyAsync(n_matches, h->d_nmatch, h->B * sizeof(int), cudaMemcpyDeviceToHost, c->stream));
+  VCU(c, cudaStreamSynchronize(c->stream));
   return VLOAM_OK;
 }
 
