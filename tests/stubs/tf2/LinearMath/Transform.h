@@ -6,6 +6,7 @@ class Vector3 {
  public:
   Vector3(double x = 0, double y = 0, double z = 0) : v_{x, y, z} {}
   double x() const { return v_[0]; } double y() const { return v_[1]; } double z() const { return v_[2]; }
+  double getX() const { return v_[0]; } double getY() const { return v_[1]; } double getZ() const { return v_[2]; }
   Vector3 operator+(const Vector3& o) const { return {v_[0] + o.v_[0], v_[1] + o.v_[1], v_[2] + o.v_[2]}; }
   Vector3 operator-() const { return {-v_[0], -v_[1], -v_[2]}; }
  private:
@@ -16,6 +17,17 @@ class Quaternion {
   Quaternion(double x = 0, double y = 0, double z = 0, double w = 1) : q_{x, y, z, w} {}
   double x() const { return q_[0]; } double y() const { return q_[1]; } double z() const { return q_[2]; } double w() const { return q_[3]; }
   Quaternion inverse() const { return {-q_[0], -q_[1], -q_[2], q_[3]}; }
+  void setRotation(const Vector3& axis, double angle) {        // tf2::Quaternion::setRotation: the axis is normalised by its length
+    const double d = std::sqrt(axis.x() * axis.x() + axis.y() * axis.y() + axis.z() * axis.z()), s = std::sin(angle * 0.5) / d;
+    q_[0] = axis.x() * s; q_[1] = axis.y() * s; q_[2] = axis.z() * s; q_[3] = std::cos(angle * 0.5);
+  }
+  double getAngle() const { return 2.0 * std::acos(q_[3]); }
+  Vector3 getAxis() const {
+    const double s2 = 1.0 - q_[3] * q_[3];
+    if (s2 < 1e-14) return Vector3(1.0, 0.0, 0.0);
+    const double s = 1.0 / std::sqrt(s2);
+    return Vector3(q_[0] * s, q_[1] * s, q_[2] * s);
+  }
   Quaternion operator*(const Quaternion& b) const {
     return {q_[3] * b.q_[0] + q_[0] * b.q_[3] + q_[1] * b.q_[2] - q_[2] * b.q_[1], q_[3] * b.q_[1] + q_[1] * b.q_[3] + q_[2] * b.q_[0] - q_[0] * b.q_[2],
             q_[3] * b.q_[2] + q_[2] * b.q_[3] + q_[0] * b.q_[1] - q_[1] * b.q_[0], q_[3] * b.q_[3] - q_[0] * b.q_[0] - q_[1] * b.q_[1] - q_[2] * b.q_[2]};

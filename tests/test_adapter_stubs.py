@@ -63,3 +63,87 @@ def test_adapters_run_the_callers_frame_loop(tmp_path, synth):
     assert published["/velodyne_cloud_registered"] == 6                  # laser_mapping.cpp:797-805: every frame
     assert published["/laser_cloud_map"] == 2                            # :778: frameCount % map_pub_number (= 2) == 0, once per run of 3
     assert published["/laser_cloud_surround"] == 0                       # advertised, never published (the reference does neither)
+
+
+# ------------------------------------------------------------------------------------------------ vloam::VisualOdometry
+def _build_vo(tmp_path):
+    import vloam_b200
+    vloam_b200.build()
+    exe = str(tmp_path / "vo_adapter_frame_loop")
+    subprocess.check_call(["g++", "-std=c++17", "-O1", "-I", os.path.join(ROOT, "tests", "stubs"), os.path.join(ROOT, "tests", "native", "vo_adapter_frame_loop.cpp"),
+                           "-o", exe, "-L" + LIB, "-lvloam_b200", "-Wl,-rpath," + LIB, "-L/usr/local/cuda/lib64", "-lcudart"])
+    return exe
+
+
+def test_vo_adapter_compiles_and_links_against_stub_ros_and_opencv(tmp_path):
+    """adapter/visual_odometry_b200.h (same class name, methods and public members as the reference's visual_odometry.h:40-121)
+    compiles against the stub ROS / PCL / OpenCV headers; its constructor advertises the reference's topic (visual_odometry.cpp:7)."""
+    exe = _build_vo(tmp_path)
+    out = subprocess.run([exe, "compile-only"], capture_output=True, text=True, check=True).stdout
+    assert [l.split()[1] for l in out.splitlines() if l.startswith("topic")] == ["/point_cloud_follow_VO"]
+
+
+@pytest.mark.gpu
+def test_vo_adapter_runs_the_callers_frame_loop(tmp_path, synth):
+    """vloam::VisualOdometry (the adapter) through three frames of vloam_main_node.cpp:134-166 — processImage as one device chain
+    (the stub ImageUtil would abort if the adapter fell back to OpenCV) — against the Python mirror: the same key points,
+    descriptors and matches in the members the caller reads, and the same solved motion, bit for bit."""
+    import vloam_b200 as V
+    exe = _build_vo(tmp_path)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "vo_detect_cv2.npz"))
+    base = g["kitti_image"]
+    imgs = [base, np.ascontiguousarray(np.roll(base, (-2, 5), axis=(0, 1))), np.ascontiguousarray(np.roll(base, (-3, 9), axis=(0, 1)))]
+    H, W = base.shape
+    s = synth.ScanStream(83, n_cols=512)
+    cam_T_velo, rect0, P = synth.kitti_like_calibration()
+    calib = str(tmp_path / "calib.txt")
+    with open(calib, "w") as f:
+        f.write(" ".join(repr(float(v)) for v in np.r_[cam_T_velo.ravel(), rect0[:3, :3].ravel(), P.ravel()]))
+    args, scans = [], []
+    for k, im in enumerate(imgs):
+        fi, fs = str(tmp_path / f"img{k}.bin"), str(tmp_path / f"scan{k}.bin")
+        im.tofile(fi)
+        sc = s.scan(k)
+        sc = sc[np.isfinite(sc).all(1)].astype(np.float32)
+        sc.tofile(fs)
+        scans.append(sc)
+        args += [fi, fs]
+    out = subprocess.run([exe, "run", str(H), str(W), calib] + args, capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    rows = [l.split() for l in out.stdout.splitlines() if l.startswith("vo ")]
+    assert len(rows) == 3
+
+    def checksum(values):
+        s_ = 0
+        for v in values:
+            s_ = (s_ * 31 + int(v)) & 0xFFFFFFFF
+        return s_
+    vo = V.VisualOdometry(batch=1, max_points=1 << 18, max_matches=2048)           # the C++ mirror's defaults
+    rect_q8 = rect0.copy()
+    rect_q8[3, 3] = 0.0                                                            # the ROS path leaves (3, 3) = 0 (SURVEY Q8), and so does the adapter
+    prev = None
+    for k, im in enumerate(imgs):
+        vo.reset()
+        r = vo.processImage(im)
+        vo.setUpPointCloud(cam_T_velo, rect_q8, P)
+        vo.processPointCloud(np.c_[scans[k], np.ones(len(scans[k]), np.float32)])   # pcl::PointXYZ: 16-byte records
+        cur = vo.frame_features(0)[0]
+        m = vo.matches()[0]
+        row = rows[k]
+        val = {row[i]: i for i in range(len(row))}
+        assert int(row[val["keypoints"] + 1]) == len(cur["keypoints"]) == int(row[val["rows"] + 1]) and len(cur["keypoints"]) > 500
+        assert int(row[val["desc"] + 1]) == checksum(cur["descriptors"].ravel())
+        assert int(row[val["matches"] + 1]) == len(m)
+        assert int(row[val["msum"] + 1]) == checksum(m[:, :2].ravel())
+        motion = np.array([float(v) for v in row[val["motion"] + 1: val["motion"] + 7]])
+        if k == 0:
+            assert len(m) == 0 and not motion.any()
+        else:
+            assert len(m) > 300
+            res = vo.solveNlsAll(prev["keypoints"][m[:, 0]], cur["keypoints"][m[:, 1]])
+            assert np.array_equal(motion, np.r_[res["angles_0to1"][0], res["t_0to1"][0]]), (k, motion)
+            assert res["counter32"][0] + res["counter22"][0] > 50
+        prev = cur
+    published = {l.split()[1]: int(l.split()[2]) for l in out.stdout.splitlines() if l.startswith("published")}
+    assert published == {"/point_cloud_follow_VO": 3, "/visual_odom_to_init": 3, "/visual_odom_path": 3}
+    vo.close()

@@ -4,6 +4,9 @@
 // description, descriptor matching), the LiDAR depth association, residual construction and solve run through libvloam_b200.so.  Only built where ROS + PCL + OpenCV exist.
 #pragma once
 #if __has_include(<ros/ros.h>) && __has_include(<pcl/point_cloud.h>) && __has_include(<opencv2/opencv.hpp>)
+#include <geometry_msgs/PoseStamped.h>
+#include <nav_msgs/Odometry.h>
+#include <nav_msgs/Path.h>
 #include <pcl/point_cloud.h>
 #include <pcl/point_types.h>
 #include <ros/ros.h>
