@@ -51,25 +51,25 @@ __device__ __forceinline__ int reflect101(int i, int n) {
 
 constexpr int kTileW = 64, kTileH = 16, kHalo = 2;                 // 5 x 5 box
 constexpr int kCovW = kTileW + 2 * kHalo, kCovH = kTileH + 2 * kHalo;
+constexpr int kRawW = kCovW + 2, kRawH = kCovH + 2;                // + the 3 x 3 Sobel reach
 
 // grid (ceil(W / 64), ceil(H / 16), B), block 256
 __global__ void __launch_bounds__(256) vo_min_eigen(const uint8_t* __restrict__ imgAll, int H, int W, float* __restrict__ eigAll,
                                                     unsigned* __restrict__ maxBits) {
-  __shared__ float cov[3][kCovH][kCovW];
-  __shared__ double rs[3][kCovH][kTileW];
+  __shared__ __align__(16) float cov[3][kCovH][kCovW];
+  __shared__ __align__(16) double rs[3][kCovH][kTileW];
+  __shared__ float s_max[8];
+  float (*raw)[kRawW] = reinterpret_cast<float (*)[kRawW]>(&rs[0][0][0]);      // the staged pixels live in rs until the row sums overwrite them
   const int b = blockIdx.z;
   const uint8_t* img = imgAll + (size_t)b * H * W;
   const int x0 = blockIdx.x * kTileW, y0 = blockIdx.y * kTileH;
   const float s1 = (float)(1.0 / (4.0 * 5.0 * 255.0));            // 1 / (2^(ksize-1) * block * 255), corner.cpp
   const float s2 = __fmul_rn(2.0f, s1);
   const int tail = W - W % 32;                                     // OpenCV's scalar tail columns: no fused operations
-  for (int e = threadIdx.x; e < kCovH * kCovW; e += 256) {
-    const int j = e / kCovW, i = e % kCovW;
-    const int y = reflect101(y0 - kHalo + j, H), x = reflect101(x0 - kHalo + i, W);   // the box filter's border: the product at the mirrored pixel
-    const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H), xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
-    const float a00 = img[(size_t)ym * W + xm], a01 = img[(size_t)ym * W + x], a02 = img[(size_t)ym * W + xp];
-    const float a10 = img[(size_t)y * W + xm], a12 = img[(size_t)y * W + xp];
-    const float a20 = img[(size_t)yp * W + xm], a21 = img[(size_t)yp * W + x], a22 = img[(size_t)yp * W + xp];
+  // the tile + halo of the three products.  A CTA whose 22 x 70 pixel footprint lies inside the image stages it in shared memory
+  // once (as float) and differentiates from there; a border CTA mirrors every access (BORDER_REFLECT_101 of the box filter applied to
+  // the product at the mirrored pixel, and of the Sobel filter around it)
+  auto products = [&](int j, int i, int x, float a00, float a01, float a02, float a10, float a12, float a20, float a21, float a22) {
     // Dx: derivative (-1, 0, 1) along x (exact), smoothing (s, 2s, s) along y as fma(s, r[y-1] + r[y+1], 2s * r[y])
     const float r0 = __fsub_rn(a02, a00), r1 = __fsub_rn(a12, a10), r2 = __fsub_rn(a22, a20);
     const float dx = __fmaf_rn(s1, __fadd_rn(r0, r2), __fmul_rn(s2, r1));
@@ -84,14 +84,44 @@ __global__ void __launch_bounds__(256) vo_min_eigen(const uint8_t* __restrict__ 
     }
     const float dy = __fsub_rn(rowp, rowm);
     cov[0][j][i] = __fmul_rn(dx, dx); cov[1][j][i] = __fmul_rn(dx, dy); cov[2][j][i] = __fmul_rn(dy, dy);
+  };
+  const bool interior = x0 - kHalo - 1 >= 0 && x0 - kHalo - 1 + kRawW <= W && y0 - kHalo - 1 >= 0 && y0 - kHalo - 1 + kRawH <= H;   // (CTA-uniform)
+  if (interior) {
+    const uint8_t* src = img + (size_t)(y0 - kHalo - 1) * W + (x0 - kHalo - 1);
+    for (int e = threadIdx.x; e < kRawH * kRawW; e += 256) {
+      const int j = e / kRawW, i = e - j * kRawW;
+      raw[j][i] = (float)src[(size_t)j * W + i];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < kCovH * kCovW; e += 256) {
+      const int j = e / kCovW, i = e - j * kCovW;
+      products(j, i, x0 - kHalo + i, raw[j][i], raw[j][i + 1], raw[j][i + 2], raw[j + 1][i], raw[j + 1][i + 2], raw[j + 2][i], raw[j + 2][i + 1], raw[j + 2][i + 2]);
+    }
+  } else {
+    for (int e = threadIdx.x; e < kCovH * kCovW; e += 256) {
+      const int j = e / kCovW, i = e % kCovW;
+      const int y = reflect101(y0 - kHalo + j, H), x = reflect101(x0 - kHalo + i, W);   // the box filter's border: the product at the mirrored pixel
+      const int ym = reflect101(y - 1, H), yp = reflect101(y + 1, H), xm = reflect101(x - 1, W), xp = reflect101(x + 1, W);
+      products(j, i, x, img[(size_t)ym * W + xm], img[(size_t)ym * W + x], img[(size_t)ym * W + xp], img[(size_t)y * W + xm], img[(size_t)y * W + xp],
+               img[(size_t)yp * W + xm], img[(size_t)yp * W + x], img[(size_t)yp * W + xp]);
+    }
   }
   __syncthreads();
-  for (int e = threadIdx.x; e < 3 * kCovH * kTileW; e += 256) {
-    const int ch = e / (kCovH * kTileW), j = (e / kTileW) % kCovH, i = e % kTileW;
-    double s = (double)cov[ch][j][i];
+  // 5-tap row sums in double, left to right; a thread produces four neighbouring sums from eight products (two 16-byte loads)
+  for (int e = threadIdx.x; e < 3 * kCovH * (kTileW / 4); e += 256) {
+    const int ch = e / (kCovH * (kTileW / 4)), rem = e - ch * (kCovH * (kTileW / 4)), j = rem / (kTileW / 4), i = (rem - j * (kTileW / 4)) * 4;
+    const float4 lo = *reinterpret_cast<const float4*>(&cov[ch][j][i]), hi = *reinterpret_cast<const float4*>(&cov[ch][j][i + 4]);
+    const double c[8] = {(double)lo.x, (double)lo.y, (double)lo.z, (double)lo.w, (double)hi.x, (double)hi.y, (double)hi.z, (double)hi.w};
+    double out[4];
 #pragma unroll
-    for (int d = 1; d < 5; ++d) s = __dadd_rn(s, (double)cov[ch][j][i + d]);
-    rs[ch][j][i] = s;
+    for (int o = 0; o < 4; ++o) {
+      double t = c[o];
+#pragma unroll
+      for (int d = 1; d < 5; ++d) t = __dadd_rn(t, c[o + d]);
+      out[o] = t;
+    }
+    *reinterpret_cast<double2*>(&rs[ch][j][i]) = make_double2(out[0], out[1]);
+    *reinterpret_cast<double2*>(&rs[ch][j][i + 2]) = make_double2(out[2], out[3]);
   }
   __syncthreads();
   float vmax = 0.f;
@@ -116,52 +146,82 @@ __global__ void __launch_bounds__(256) vo_min_eigen(const uint8_t* __restrict__ 
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(0xffffffffu, vmax, o));
-  if (lane_id() == 0 && vmax > 0.f) atomicMax(&maxBits[b], __float_as_uint(vmax));   // positive floats order like their bits
+  if (lane_id() == 0) s_max[threadIdx.x >> 5] = vmax;
+  __syncthreads();
+  if (threadIdx.x == 0) {                                                             // one atomic per CTA on the stream's maximum
+#pragma unroll
+    for (int i = 1; i < 8; ++i) vmax = fmaxf(vmax, s_max[i]);
+    if (vmax > 0.f) atomicMax(&maxBits[b], __float_as_uint(vmax));                    // positive floats order like their bits
+  }
 }
 
-// grid (ceil(W / 32), ceil(H / 8), B), block (32, 8): threshold (to zero) + "equal to its 3 x 3 dilation", border excluded
+// grid (ceil(W / 32), ceil(H / 64), B), block (32, 8): threshold (to zero) + "equal to its 3 x 3 dilation", border excluded.
+// A thread tests eight pixels of its column (rows y0 + ty + 8 j); the CTA reserves room for all its candidates with ONE atomic on
+// the stream's counter (a counter per stream takes ~10^4 appends per frame: one atomic per warp serialised on that address and
+// was two thirds of this kernel's time) and writes them in a CTA-local order — any order will do, vo_select_corners sorts by address.
+constexpr int kCandRows = 8;
 __global__ void __launch_bounds__(256) vo_corner_candidates(const float* __restrict__ eigAll, int H, int W, const unsigned* __restrict__ maxBits,
                                                             double quality, int capCand, unsigned* __restrict__ keyOfs, unsigned* __restrict__ valBits,
                                                             int* __restrict__ nCand, int* __restrict__ status) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
   const int b = blockIdx.z;
   const float* eig = eigAll + (size_t)b * H * W;
-  const int x = blockIdx.x * 32 + threadIdx.x, y = blockIdx.y * 8 + threadIdx.y;
+  const int x = blockIdx.x * 32 + threadIdx.x, w = threadIdx.y, l = threadIdx.x;
   const float thr = (float)((double)__uint_as_float(maxBits[b]) * quality);      // threshold(eig, eig, maxVal * qualityLevel, 0, THRESH_TOZERO)
-  bool cand = false;
-  float v = 0.f;
-  if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
-    const float raw = eig[(size_t)y * W + x];
-    v = raw > thr ? raw : 0.f;
-    if (v != 0.f) {
-      cand = true;
+  float v[kCandRows];
+  unsigned mask = 0;
 #pragma unroll
-      for (int dy = -1; dy <= 1; ++dy)
+  for (int j = 0; j < kCandRows; ++j) {
+    const int y = blockIdx.y * (8 * kCandRows) + j * 8 + w;
+    v[j] = 0.f;
+    if (x >= 1 && x < W - 1 && y >= 1 && y < H - 1) {
+      const float raw = eig[(size_t)y * W + x];
+      v[j] = raw > thr ? raw : 0.f;
+      if (v[j] != 0.f) {
+        bool cand = true;
 #pragma unroll
-        for (int dx = -1; dx <= 1; ++dx) {
-          const float n = eig[(size_t)(y + dy) * W + (x + dx)];
-          if ((n > thr ? n : 0.f) > v) cand = false;
-        }
+        for (int dy = -1; dy <= 1; ++dy)
+#pragma unroll
+          for (int dx = -1; dx <= 1; ++dx) {
+            const float n = eig[(size_t)(y + dy) * W + (x + dx)];
+            if ((n > thr ? n : 0.f) > v[j]) cand = false;
+          }
+        if (cand) mask |= 1u << j;
+      }
     }
   }
-  const unsigned m = __ballot_sync(0xffffffffu, cand);
-  if (m == 0u) return;
-  int base = 0;
-  if (threadIdx.x == __ffs(m) - 1) base = atomicAdd(&nCand[b], __popc(m));
-  base = __shfl_sync(0xffffffffu, base, __ffs(m) - 1);
-  if (cand) {
-    const int pos = base + __popc(m & ((1u << threadIdx.x) - 1u));
+  // exclusive position of this thread's candidates inside the CTA: lanes, then warps
+  const int mine = __popc(mask);
+  int incl = mine;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, incl, o); if (l >= o) incl += t; }
+  if (l == 31) s_warp[w] = incl;
+  __syncthreads();
+  if (w == 0 && l == 0) {
+    int tot = 0;
+    for (int i = 0; i < 8; ++i) { const int c = s_warp[i]; s_warp[i] = tot; tot += c; }
+    s_base = tot ? atomicAdd(&nCand[b], tot) : 0;
+  }
+  __syncthreads();
+  int pos = s_base + s_warp[w] + incl - mine;
+#pragma unroll
+  for (int j = 0; j < kCandRows; ++j) {
+    if (!((mask >> j) & 1u)) continue;
     if (pos < capCand) {
+      const int y = blockIdx.y * (8 * kCandRows) + j * 8 + w;
       // ascending sort of the complements = descending value, then descending address (greaterThanPtr, featureselect.cpp)
       keyOfs[(size_t)b * capCand + pos] = (unsigned)(H * W - 1 - (y * W + x));
-      valBits[(size_t)b * capCand + pos] = ~__float_as_uint(v);
+      valBits[(size_t)b * capCand + pos] = ~__float_as_uint(v[j]);
     } else {
       status[b] = 1;
     }
+    ++pos;
   }
 }
 
 // grid (B), block 1024, dynamic shared memory = sizeof(SortSmem)
-__global__ void __launch_bounds__(1024) vo_select_corners(int H, int W, int capCand, int cells, int gw, int gh, int cell, float minDist2,
+__global__ void __launch_bounds__(1024, 1) vo_select_corners(int H, int W, int capCand, int cells, int gw, int gh, int cell, float minDist2,
                                                           int maxCorners, const int* __restrict__ nCand, unsigned* kAall, unsigned* vAall,
                                                           unsigned* kBall, unsigned* vBall, uint8_t* __restrict__ stateAll, int* __restrict__ cellStartAll,
                                                           int* __restrict__ cellFillAll, int* __restrict__ cellItemsAll, float* __restrict__ cornersAll,
@@ -187,16 +247,20 @@ __global__ void __launch_bounds__(1024) vo_select_corners(int H, int W, int capC
   __syncthreads();
   cur = cta_radix_sort(v1, k1, v2, k2, n, 32, S);                                // (key = response', value = address')
   const unsigned* ofsSorted = cur ? k2 : k1;                                      // rank -> complemented address
+  unsigned* pos = cur ? k1 : k2;                                                   // the other buffer pair is free now:
+  unsigned* cellxy = cur ? v1 : v2;                                                // rank -> x | y << 16 and its cell, same packing
   __syncthreads();
   // ---- candidates grouped by 'cell' x 'cell' pixel cells (featureselect.cpp's grid; cell >= min_distance)
   for (int c = tid; c <= cells; c += 1024) { cellStart[c] = 0; if (c < cells) cellFill[c] = 0; }
   __syncthreads();
-  auto cell_of = [&](int r, int& x, int& y) {
+  for (int r = tid; r < n; r += 1024) {
     const int ofs = H * W - 1 - (int)ofsSorted[r];
-    y = ofs / W; x = ofs - y * W;
-    return (y / cell) * gw + (x / cell);
-  };
-  for (int r = tid; r < n; r += 1024) { int x, y; atomicAdd(&cellStart[cell_of(r, x, y)], 1); state[r] = 0; }
+    const int y = ofs / W, x = ofs - y * W, xc = x / cell, yc = y / cell;
+    pos[r] = (unsigned)x | ((unsigned)y << 16);
+    cellxy[r] = (unsigned)xc | ((unsigned)yc << 16);
+    atomicAdd(&cellStart[yc * gw + xc], 1);
+    state[r] = 0;
+  }
   __syncthreads();
   {  // exclusive scan of the cell counts, a contiguous chunk per thread
     const int per = (cells + 1023) / 1024;
@@ -208,48 +272,59 @@ __global__ void __launch_bounds__(1024) vo_select_corners(int H, int W, int capC
     if (tid == 0) cellStart[cells] = n;
   }
   __syncthreads();
-  for (int r = tid; r < n; r += 1024) { int x, y; const int c = cell_of(r, x, y); cellItems[cellStart[c] + atomicAdd(&cellFill[c], 1)] = r; }
+  for (int r = tid; r < n; r += 1024) {
+    const unsigned cc = cellxy[r];
+    const int c = (int)(cc >> 16) * gw + (int)(cc & 0xffffu);
+    cellItems[cellStart[c] + atomicAdd(&cellFill[c], 1)] = r;
+  }
   __syncthreads();
-  // ---- the greedy spacing pass as rounds (see the file header)
-  for (int round = 0; round < n + 1; ++round) {
-    int undecided = 0;
-    for (int r = tid; r < n; r += 1024) {
-      if (state[r] != 0) continue;
-      int x, y;
-      cell_of(r, x, y);
-      const int xc = x / cell, yc = y / cell;
-      bool dropped = false, wait = false;
-      for (int yy = max(yc - 1, 0); yy <= min(yc + 1, gh - 1) && !dropped; ++yy)
-        for (int xx = max(xc - 1, 0); xx <= min(xc + 1, gw - 1) && !dropped; ++xx) {
-          const int c = yy * gw + xx;
-          for (int t = cellStart[c]; t < cellStart[c + 1]; ++t) {
-            const int q = cellItems[t];
-            if (q >= r) continue;                                  // only earlier candidates can have been kept before this one
-            int qx, qy;
-            cell_of(q, qx, qy);
-            const float dx = (float)(x - qx), dy = (float)(y - qy);
-            if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < minDist2)) continue;
-            const uint8_t sq = state[q];
-            if (sq == 1) { dropped = true; break; }
-            if (sq == 0) wait = true;
+  // ---- the greedy spacing pass as rounds (see the file header), over a growing prefix of the ranking: a candidate depends on
+  // earlier ranks only and the output is the first maxCorners kept ones, so the pass stops at the first chunk boundary behind
+  // which maxCorners candidates are kept (featureselect.cpp breaks out of its loop at the same count)
+  constexpr int kChunk = 2048;
+  int limit = 0, keptTotal = 0;
+  while (limit < n && keptTotal < maxCorners) {
+    const int lo = limit, hi = min(n, lo + kChunk);
+    for (int round = 0; round <= hi - lo; ++round) {
+      int undecided = 0;
+      for (int r = lo + tid; r < hi; r += 1024) {
+        if (state[r] != 0) continue;
+        const unsigned p = pos[r], cc = cellxy[r];
+        const int x = (int)(p & 0xffffu), y = (int)(p >> 16), xc = (int)(cc & 0xffffu), yc = (int)(cc >> 16);
+        bool dropped = false, wait = false;
+        for (int yy = max(yc - 1, 0); yy <= min(yc + 1, gh - 1) && !dropped; ++yy)
+          for (int xx = max(xc - 1, 0); xx <= min(xc + 1, gw - 1) && !dropped; ++xx) {
+            const int c = yy * gw + xx;
+            for (int t = cellStart[c]; t < cellStart[c + 1]; ++t) {
+              const int q = cellItems[t];
+              if (q >= r) continue;                                  // only earlier candidates can have been kept before this one
+              const unsigned pq = pos[q];
+              const float dx = (float)(x - (int)(pq & 0xffffu)), dy = (float)(y - (int)(pq >> 16));
+              if (!(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)) < minDist2)) continue;
+              const uint8_t sq = state[q];
+              if (sq == 1) { dropped = true; break; }
+              if (sq == 0) wait = true;
+            }
           }
-        }
-      if (dropped) state[r] = 2;
-      else if (!wait) state[r] = 1;
-      else undecided = 1;
+        if (dropped) state[r] = 2;
+        else if (!wait) state[r] = 1;
+        else undecided = 1;
+      }
+      if (!__syncthreads_or(undecided)) break;
     }
-    if (!__syncthreads_or(undecided)) break;
+    for (int r0 = lo; r0 < hi; r0 += 1024) keptTotal += __syncthreads_count(r0 + tid < hi && state[r0 + tid] == 1);
+    limit = hi;
   }
   // ---- the first maxCorners kept candidates, in rank order
   {
-    const int per = (n + 1023) / 1024;
-    const int r0 = min(tid * per, n), r1 = min(r0 + per, n);
+    const int per = (limit + 1023) / 1024;
+    const int r0 = min(tid * per, limit), r1 = min(r0 + per, limit);
     int cnt = 0;
     for (int r = r0; r < r1; ++r) cnt += state[r] == 1 ? 1 : 0;
-    int pos = block_exclusive_scan1024(cnt, S);
+    int p = block_exclusive_scan1024(cnt, S);
     const int total = S.total;
-    for (int r = r0; r < r1 && pos < maxCorners; ++r)
-      if (state[r] == 1) { int x, y; cell_of(r, x, y); corners[2 * pos] = (float)x; corners[2 * pos + 1] = (float)y; ++pos; }
+    for (int r = r0; r < r1 && p < maxCorners; ++r)
+      if (state[r] == 1) { const unsigned q = pos[r]; corners[2 * p] = (float)(q & 0xffffu); corners[2 * p + 1] = (float)(q >> 16); ++p; }
     if (tid == 0) nCorners[b] = min(total, maxCorners);
   }
 }
@@ -297,7 +372,7 @@ cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B,
   if (e == cudaSuccess) e = cudaMemsetAsync(d->status, 0, B * sizeof(int), st);
   if (e != cudaSuccess) return e;
   VB_LAUNCH(prof, K_VO_DETECT, st, vo_min_eigen<<<dim3((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B), 256, 0, st>>>(d->img, H, W, d->eig, d->maxBits));
-  VB_LAUNCH(prof, K_VO_DETECT, st, vo_corner_candidates<<<dim3((W + 31) / 32, (H + 7) / 8, B), dim3(32, 8), 0, st>>>(d->eig, H, W, d->maxBits, quality, d->capCand, d->kA, d->vA, d->nCand, d->status));
+  VB_LAUNCH(prof, K_VO_DETECT, st, vo_corner_candidates<<<dim3((W + 31) / 32, (H + 8 * kCandRows - 1) / (8 * kCandRows), B), dim3(32, 8), 0, st>>>(d->eig, H, W, d->maxBits, quality, d->capCand, d->kA, d->vA, d->nCand, d->status));
   VB_LAUNCH(prof, K_VO_DETECT, st, vo_select_corners<<<B, 1024, sizeof(SortSmem), st>>>(H, W, d->capCand, d->cells, gw, gh, cell, (float)(minDistance * minDistance), maxCorners,
                                                                                       d->nCand, d->kA, d->vA, d->kB, d->vB, d->state, d->cellStart, d->cellFill,
                                                                                       d->cellItems, d->corners, d->nCorners));

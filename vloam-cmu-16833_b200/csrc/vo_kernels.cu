@@ -15,6 +15,8 @@
 //                     staged in shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier)
 //   vo_solve          CostFunctor32 / CostFunctor22 (ceres_cost_function.h:54-96, 147-185) with analytic Jacobians of
 //                     ceres::AngleAxisRotatePoint + ceres::Solve (<= 100 iterations, Huber 0.1, no manifold) in one launch
+#include <cooperative_groups.h>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <vector>
@@ -539,6 +541,112 @@ __global__ void __launch_bounds__(kMatchThreads) vo_bf_match(const uint8_t* __re
   if (threadIdx.x == 0) nMatches[b] = s_base;
 }
 
+// vo_bf_match_cluster: the same matcher with a stream's queries dealt to the CTAs of a thread-block cluster — grid (kMatchClCtas, B),
+// cluster (kMatchClCtas, 1, 1), block kMatchClThreads — so that a small batch still covers the chip (32 streams: 256 CTAs instead of
+// 32).  Round by round (kMatchClCtas * kMatchClThreads consecutive queries, CTA `rank` owns a contiguous slice) every CTA scans the
+// whole train set from its own TMA-staged copy; the ordered compaction needs the number of accepted matches in the lower-ranked
+// CTAs, which each CTA reads from its peers' shared memory (DSMEM) after one cluster barrier per round.
+constexpr int kMatchClCtas = 8, kMatchClThreads = 128;
+__global__ void __launch_bounds__(kMatchClThreads) vo_bf_match_cluster(const uint8_t* __restrict__ descQ, const int* __restrict__ nQ,
+                                                                        const uint8_t* __restrict__ descT, const int* __restrict__ nT, int maxK,
+                                                                        const float* __restrict__ kpQ, const float* __restrict__ kpT, double ratio,
+                                                                        int* __restrict__ matches, int* __restrict__ nMatches,
+                                                                        float* __restrict__ uvQ, float* __restrict__ uvT, int4* __restrict__ knn) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
+  extern __shared__ __align__(128) unsigned char match_smem[];
+  uint4* sT = reinterpret_cast<uint4*>(match_smem);                                         // [kMatchChunk][2]
+  uint64_t* mbar = reinterpret_cast<uint64_t*>(match_smem + (size_t)kMatchChunk * 32);
+  __shared__ int s_wsum[kMatchClThreads / 32];
+  __shared__ int s_cnt[2];                           // this CTA's accepted matches of the round, two generations
+  const int b = blockIdx.y, rank = (int)cluster.block_rank(), cs = (int)cluster.num_blocks();
+  const int nq = min(max(nQ[b], 0), maxK), nt = min(max(nT[b], 0), maxK);
+  const uint4* gQ = reinterpret_cast<const uint4*>(descQ + (size_t)b * maxK * 32);
+  const unsigned char* gT = descT + (size_t)b * maxK * 32;
+  if (threadIdx.x == 0) { mbar_init(mbar, 1); mbar_fence_init(); }
+  __syncthreads();
+  unsigned phase = 0;
+  int accepted = 0, gen = 0;                         // matches accepted in the rounds so far (the same value in every CTA)
+  for (int q0 = 0; q0 < nq; q0 += cs * kMatchClThreads) {
+    const int q = q0 + rank * kMatchClThreads + (int)threadIdx.x;
+    uint4 a0 = make_uint4(0, 0, 0, 0), a1 = a0;
+    if (q < nq) { a0 = gQ[2 * q]; a1 = gQ[2 * q + 1]; }
+    int d0 = 0x7fffffff, d1 = 0x7fffffff, i0 = -1, i1 = -1;
+    for (int t0 = 0; t0 < nt; t0 += kMatchChunk) {
+      const int m = min(kMatchChunk, nt - t0);
+      if (threadIdx.x == 0) {
+        fence_proxy_async();
+        mbar_arrive_expect_tx(mbar, (unsigned)m * 32u);
+        bulk_g2s(sT, gT + (size_t)t0 * 32, (unsigned)m * 32u, mbar);
+      }
+      mbar_wait(mbar, phase);
+      phase ^= 1u;
+      if (q < nq) {
+        for (int t = 0; t < m; ++t) {
+          const uint4 b0 = sT[2 * t], b1 = sT[2 * t + 1];
+          const int d = __popc(a0.x ^ b0.x) + __popc(a0.y ^ b0.y) + __popc(a0.z ^ b0.z) + __popc(a0.w ^ b0.w) +
+                        __popc(a1.x ^ b1.x) + __popc(a1.y ^ b1.y) + __popc(a1.z ^ b1.z) + __popc(a1.w ^ b1.w);
+          if (d < d1) {
+            if (d < d0) { d1 = d0; i1 = i0; d0 = d; i0 = t0 + t; } else { d1 = d; i1 = t0 + t; }
+          }
+        }
+      }
+      __syncthreads();
+    }
+    if (q < nq) knn[(size_t)b * maxK + q] = make_int4(i0, i1, i0 >= 0 ? d0 : -1, i1 >= 0 ? d1 : -1);
+    const bool ok = q < nq && i1 >= 0 && (double)(float)d0 < ratio * (double)(float)d1;
+    const unsigned bal = __ballot_sync(0xffffffffu, ok);
+    const int w = threadIdx.x >> 5, l = lane_id();
+    if (l == 0) s_wsum[w] = __popc(bal);
+    __syncthreads();
+    if (threadIdx.x == 0) { int tot = 0; for (int i = 0; i < kMatchClThreads / 32; ++i) tot += s_wsum[i]; s_cnt[gen] = tot; }
+    cluster.sync();                                  // (also orders s_cnt within the CTA)
+    int before = accepted, total = 0;
+    for (int r = 0; r < cs; ++r) {
+      const int c = *cluster.map_shared_rank(&s_cnt[gen], r);
+      if (r < rank) before += c;
+      total += c;
+    }
+    for (int i = 0; i < w; ++i) before += s_wsum[i];
+    if (ok) {
+      const int o = before + __popc(bal & ((1u << l) - 1u));
+      int* mo = matches + ((size_t)b * maxK + o) * 3;
+      mo[0] = q; mo[1] = i0; mo[2] = d0;
+      if (kpQ && kpT) {
+        const size_t oq = ((size_t)b * maxK + q) * 2, ot = ((size_t)b * maxK + i0) * 2, oo = ((size_t)b * maxK + o) * 2;
+        uvQ[oo] = kpQ[oq]; uvQ[oo + 1] = kpQ[oq + 1];
+        uvT[oo] = kpT[ot]; uvT[oo + 1] = kpT[ot + 1];
+      }
+    }
+    accepted += total;
+    gen ^= 1;
+    __syncthreads();                                 // s_wsum is rewritten in the next round
+  }
+  cluster.sync();                                    // nobody leaves while a peer may still read its count
+  if (rank == 0 && threadIdx.x == 0) nMatches[b] = accepted;
+}
+
+// The matcher launch: the cluster kernel unless VLOAM_VO_MATCH_CLUSTER=0 asks for the one-CTA-per-stream kernel.
+static cudaError_t launch_vo_bf_match(vb::Profiler* prof, cudaStream_t st, int B, const uint8_t* descQ, const int* nQ, const uint8_t* descT, const int* nT,
+                                      int maxK, const float* kpQ, const float* kpT, double ratio, int* matches, int* nMatches, float* uvQ, float* uvT,
+                                      int4* knn) {
+  static const bool use_cluster = [] { const char* e = getenv("VLOAM_VO_MATCH_CLUSTER"); return !(e && atoi(e) == 0); }();
+  if (use_cluster) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kMatchClCtas, B); cfg.blockDim = dim3(kMatchClThreads); cfg.dynamicSmemBytes = kMatchChunk * 32 + 16; cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kMatchClCtas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaSuccess;
+    VB_LAUNCH(prof, K_VO_MATCH, st, e = cudaLaunchKernelEx(&cfg, vo_bf_match_cluster, descQ, nQ, descT, nT, maxK, kpQ, kpT, ratio, matches, nMatches, uvQ, uvT, knn));
+    return e;
+  }
+  VB_LAUNCH(prof, K_VO_MATCH, st, vo_bf_match<<<B, kMatchThreads, kMatchChunk * 32 + 16, st>>>(descQ, nQ, descT, nT, maxK, kpQ, kpT, ratio, matches, nMatches,
+                                                                                            uvQ, uvT, knn));
+  return cudaGetLastError();
+}
+
 struct vloam_vo {
   vloam_ctx* ctx = nullptr;
   int B = 0, cap = 0, maxM = 0;
@@ -810,10 +918,8 @@ int vloam_vo_match_descriptors(vloam_vo* h, const uint8_t* desc_query, const int
     VCU(c, cudaMemcpyAsync(h->d_kp[1], kp_train, B * M * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
   }
   (void)cudaGetLastError();
-  VB_LAUNCH(&c->prof, K_VO_MATCH, st, vo_bf_match<<<h->B, kMatchThreads, kMatchChunk * 32 + 16, st>>>(
-                                          h->d_desc[0], h->d_nkp[0], h->d_desc[1], h->d_nkp[1], h->maxM, kp_query ? h->d_kp[0] : nullptr,
-                                          kp_query ? h->d_kp[1] : nullptr, ratio, h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
-  VCU(c, cudaGetLastError());
+  VCU(c, launch_vo_bf_match(&c->prof, st, h->B, h->d_desc[0], h->d_nkp[0], h->d_desc[1], h->d_nkp[1], h->maxM, kp_query ? h->d_kp[0] : nullptr,
+                            kp_query ? h->d_kp[1] : nullptr, ratio, h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
   if (matches_out) VCU(c, cudaMemcpyAsync(matches_out, h->d_matches, B * M * 3 * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (n_matches_out) VCU(c, cudaMemcpyAsync(n_matches_out, h->d_nmatch, B * sizeof(int), cudaMemcpyDeviceToHost, st));
   VCU(c, cudaStreamSynchronize(st));
@@ -852,7 +958,7 @@ int vloam_vo_get_match_buffers(vloam_vo* h, const float** query_uv_dev, const fl
 int vloam_vo_detect_corners(vloam_vo* h, const uint8_t* images, int height, int width, int max_corners, double quality_level,
                             double min_distance, float* corners_xy, int* n_corners) {
   if (!h || !images || height < 3 || width < 3 || max_corners < 1 || !(quality_level > 0.0) || !(min_distance >= 1.0)) return VLOAM_E_INVALID;
-  if ((long long)height * width > (1ll << 28)) return VLOAM_E_CAPACITY;
+  if ((long long)height * width > (1ll << 28) || height > 65535 || width > 65535) return VLOAM_E_CAPACITY;
   vloam_ctx* c = h->ctx;
   VCU(c, cudaSetDevice(c->device));
   int status = 0;
@@ -938,7 +1044,7 @@ int vloam_vo_describe_orb(vloam_vo* h, const uint8_t* images, int height, int wi
 // images -> keypoints[i], descriptors[i] -> (count > 0) matches of descriptors[1 - i] (query, previous frame) in descriptors[i] (train).
 int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int width, int* n_keypoints, int* n_matches) {
   if (!h || !images || height < 3 || width < 3) return VLOAM_E_INVALID;
-  if ((long long)height * width > (1ll << 28)) return VLOAM_E_CAPACITY;
+  if ((long long)height * width > (1ll << 28) || height > 65535 || width > 65535) return VLOAM_E_CAPACITY;
   vloam_ctx* c = h->ctx;
   if (h->count < 0) return vfail(c, VLOAM_E_STATE, "vloam_vo_process_image before vloam_vo_reset");
   if (h->maxM < 1024) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_process_image: max_matches must hold the detector's 1024 corners");
@@ -951,10 +1057,8 @@ int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int w
   if (int rc = vo_enqueue_describe(h, vb::vo_detect_image_device(h->det), height, width, vb::vo_detect_corners_device(h->det),
                                    vb::vo_detect_counts_device(h->det), 1024, i)) return rc;
   if (h->count > 0) {
-    VB_LAUNCH(&c->prof, K_VO_MATCH, st, vo_bf_match<<<h->B, kMatchThreads, kMatchChunk * 32 + 16, st>>>(
-                                            h->d_fdesc[1 - i], h->d_fn[1 - i], h->d_fdesc[i], h->d_fn[i], h->maxM, h->d_fkp[1 - i], h->d_fkp[i], 0.8,
-                                            h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
-    VCU(c, cudaGetLastError());
+    VCU(c, launch_vo_bf_match(&c->prof, st, h->B, h->d_fdesc[1 - i], h->d_fn[1 - i], h->d_fdesc[i], h->d_fn[i], h->maxM, h->d_fkp[1 - i], h->d_fkp[i], 0.8,
+                              h->d_matches, h->d_nmatch, h->d_muv[0], h->d_muv[1], h->d_knn));
   } else {
     VCU(c, cudaMemsetAsync(h->d_nmatch, 0, h->B * sizeof(int), st));
   }
