@@ -5,12 +5,14 @@
 //   vo_min_eigen         cornerMinEigenVal: 3 x 3 Sobel derivatives (scale folded into the smoothing taps), the products
 //                        (Dx^2, Dx Dy, Dy^2), a 5 x 5 box sum in double precision (rows, then columns), the smaller eigenvalue;
 //                        per-image maximum on the way out
-//   vo_corner_candidates threshold at quality * max, 3 x 3 local maxima away from the border -> unordered candidate list
+//   vo_corner_candidates threshold at quality * max, 3 x 3 local maxima away from the border -> unordered candidate list (one
+//                        atomic per CTA on the stream's counter)
 //   vo_select_corners    sort by (value descending, address descending), then the greedy spacing pass.  The reference walks
 //                        the sorted list serially ("keep a corner if no kept corner is closer than min_distance"); the same set
 //                        comes out of rounds in which every undecided candidate looks at the earlier candidates within the
 //                        radius: any of them kept -> dropped; all of them dropped -> kept; otherwise wait.  The earliest
-//                        undecided candidate is always decided, a round decides thousands at once.
+//                        undecided candidate is always decided, a round decides thousands at once.  The rounds walk a growing
+//                        prefix of the ranking and stop once max_corners are kept.
 // Every float operation that OpenCV's vectorised path fuses or does not fuse is written with the explicit intrinsic, so the
 // response map carries the oracle's bits.
 #include <cuda_runtime.h>

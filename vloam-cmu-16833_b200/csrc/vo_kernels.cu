@@ -12,7 +12,8 @@
 //                     depth lookup, back-projection through P_rect0 (float column-pivoted Householder 3x3)
 //   vo_bf_match       ImageUtil::matchDescriptors (image_util.cpp:214-296) in the configuration visual_odometry.cpp:34-37 selects:
 //                     brute-force Hamming 2-NN over 256-bit ORB descriptors + the 0.8 ratio test; the train descriptors are
-//                     staged in shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier)
+//                     staged in shared memory by 1-D TMA bulk copies (cp.async.bulk + mbarrier); vo_bf_match_cluster deals a
+//                     stream's queries to an 8-CTA thread-block cluster (accepted counts exchanged through DSMEM)
 //   vo_solve          CostFunctor32 / CostFunctor22 (ceres_cost_function.h:54-96, 147-185) with analytic Jacobians of
 //                     ceres::AngleAxisRotatePoint + ceres::Solve (<= 100 iterations, Huber 0.1, no manifold) in one launch
 #include <cooperative_groups.h>
