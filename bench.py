@@ -932,7 +932,59 @@ def run_ours(args, rank, world, local_rank):
                                    + (f"; LM iterations executed in the last scan's passes: {pipe.lm_iterations()}" if do_map else "")},
         "clocks": clocks,
     }
+    if world == 1 and args.legs == "all" and args.workload == "sr_lo_lm":
+        line["vo_frontend"] = frontend_leg(V, local_rank)
     print(json.dumps(line), flush=True)
+
+
+def frontend_leg(V, device_index, frames_per_call=32, reps=10):
+    """Supplementary line item (not part of `value` / `e2e`): VisualOdometry::processImage on the device (vloam_vo_process_image:
+    Shi-Tomasi detection, ORB description, descriptor matching) on `frames_per_call` KITTI-sized frames
+    per call, wall time through the host API with the image upload inside, per-kernel CUDA-event times, and the same three OpenCV
+    calls on one host thread when cv2 is importable.  Any failure is reported in the object instead of failing the bench."""
+    try:
+        g = np.load(os.path.join(ROOT, "tests", "golden", "vo_detect_cv2.npz"))
+        base = g["kitti_image"]
+        rng = np.random.default_rng(5)
+        shifts = [int(rng.integers(0, 300)) for _ in range(frames_per_call)]
+        frames = [np.stack([np.roll(base, (0, s_ + 4 * k), axis=(0, 1)) for s_ in shifts]) for k in range(2)]
+        ctx = V.Context(device=device_index)
+        vo = V.VisualOdometry(ctx, batch=frames_per_call, max_points=1024, max_matches=1024)
+        for k in range(4):
+            vo.reset(); vo.processImage(frames[k % 2])
+        ctx.enable_timing(True)
+        t0 = time.perf_counter()
+        for k in range(reps):
+            vo.reset(); r = vo.processImage(frames[k % 2])
+        dt = (time.perf_counter() - t0) / reps
+        kt = ctx.kernel_timings()
+        out = {"call": "vloam_vo_process_image (detection + ORB description + matching), image upload inside the timed region",
+               "frames_per_call": frames_per_call, "image": list(base.shape), "ms_per_call": dt * 1e3, "frames_per_s": frames_per_call / dt,
+               "kernel_ms_per_call": {k_: v_[0] / reps for k_, v_ in kt.items()}, "gpu_launches_per_call": sum(v_[1] for v_ in kt.values()) / reps,
+               "keypoints_stream0": int(r["n_keypoints"][0]), "matches_stream0": int(r["n_matches"][0]), "h2d_bytes_per_call": int(frames[0].nbytes)}
+        vo.close(); ctx.close()
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            orb, bf = cv2.ORB_create(), cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+            t0 = time.perf_counter()
+            for b_ in range(min(frames_per_call, 4)):
+                prev = None
+                for k in range(3):                    # (the first frame of a stream has nothing to match against)
+                    img = frames[k % 2][b_]
+                    c = cv2.goodFeaturesToTrack(img, 1024, 0.03, 7.5, None, blockSize=5, useHarrisDetector=False, k=0.04).reshape(-1, 2)
+                    _, d = orb.compute(img, [cv2.KeyPoint(float(x), float(y), 5.0) for x, y in c])
+                    if prev is not None:
+                        knn = bf.knnMatch(prev, d, 2)
+                        _ = [m[0] for m in knn if m[0].distance < 0.8 * m[1].distance]
+                    prev = d
+            out["cv2_ms_per_frame_1_thread"] = (time.perf_counter() - t0) / (3 * min(frames_per_call, 4)) * 1e3
+            out["cv2_version"] = cv2.__version__
+        except ImportError:
+            out["cv2_ms_per_frame_1_thread"] = None
+        return out
+    except Exception as e:      # noqa: BLE001
+        return {"error": f"{type(e).__name__}: {e}"}
 
 
 def exchange_report(args, world, do_map):
