@@ -91,5 +91,5 @@ def test_cpp_host_mirror_matches_python_mirror(synth, tmp_path):
     # (the mirror is at its fourth frame there: the chain's first image is matched against the slot descKeypoints just filled — the same
     # descriptors, of which the periodic pattern makes many identical, so only the unique ones pass the ratio test)
     assert [int(v) for v in line[1:5]] == [len(kept), len(F.match_descriptors(desc, desc)), len(kept2), len(wm)]
-    assert int(line[6]) == checksum(wm.ravel() & 0xFFFFFFFF)
+    assert int(line[6]) == checksum(wm.ravel())
     lom.close(); vo.close()
