@@ -356,3 +356,38 @@ def test_cuda_process_image_chain_hits_the_opencv_vectors(detect_golden, orb_gol
     assert np.array_equal(vo.matches()[0], F.match_descriptors(g["kitti_next_desc"], g["kitti_desc"]))
     assert r2["n_matches"][0] == len(vo.matches()[0])
     vo.close()
+
+
+@pytest.mark.gpu
+def test_cuda_front_end_against_restatement_across_image_sizes():
+    """Detection, description and matching on images whose sizes exercise every tile shape of the kernels — smaller than one
+    min-eigen tile (all CTAs mirror their accesses), one pixel short of / past the staged-interior condition, partial last tiles,
+    widths that are and are not multiples of 32 (fused / unfused tails of the Sobel and blur passes), too small for ORB to keep any
+    key point — against the numpy restatement: response map bit for bit, corners, surviving key points, descriptors, matches."""
+    import vloam_b200 as V
+    from oracle import vo_frontend as F
+    rng = np.random.default_rng(20261017)
+    for (h, w) in ((17, 23), (22, 70), (23, 71), (40, 69), (63, 63), (64, 100), (97, 131), (129, 257), (150, 352), (211, 1055)):
+        img = rng.integers(0, 256, (h, w)).astype(np.uint8)
+        img = np.clip(np.round(0.25 * (img.astype(np.float32) + np.roll(img, 1, 0) + np.roll(img, 1, 1) + np.roll(img, (1, 1), (0, 1)))), 0, 255).astype(np.uint8)
+        nxt = np.ascontiguousarray(np.roll(img, (1, -2), axis=(0, 1)))
+        vo = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+        feats = []
+        for k, frame in enumerate((np.stack([img, nxt]), np.stack([nxt, img]))):
+            vo.reset()
+            r = vo.processImage(frame)
+            cur = vo.frame_features(0)
+            for b in range(2):
+                resp = F.min_eigen_response(frame[b])
+                assert np.array_equal(vo.corner_response(b).view(np.uint32), resp.view(np.uint32)), (h, w, k, b, "response map")
+                corners = F.select_corners(resp)
+                kept, desc = F.orb_describe(frame[b], corners)
+                assert np.array_equal(cur[b]["keypoints"], corners[kept]) and np.array_equal(cur[b]["descriptors"], desc), (h, w, k, b)
+                assert r["n_keypoints"][b] == len(kept)
+                if h < 63 or w < 63:
+                    assert len(kept) == 0
+            feats.append(cur)
+        m = vo.matches()
+        for b in range(2):
+            assert np.array_equal(m[b], F.match_descriptors(feats[0][b]["descriptors"], feats[1][b]["descriptors"])), (h, w, b)
+        vo.close()
