@@ -297,7 +297,7 @@ int vloam_vo_get_result(vloam_vo* h, double* out /* [batch][8] as vloam_vo_solve
  * cv::goodFeaturesToTrack(img, max_corners = 1024, quality_level = 0.03, min_distance = 7.5, Mat(), blockSize = 5, false, 0.04)
  * = the minimum-eigenvalue response of cv::cornerMinEigenVal(img, 5, 3), thresholded at quality_level * max, its 3 x 3 local
  * maxima sorted by response, and the greedy pass that keeps a corner when no kept corner is closer than min_distance.
- * images: host, [batch][height][width] bytes (8-bit grey, the cv::Mat rows packed).  corners_xy[batch][max_corners][2] =
+ * images: host or device memory, [batch][height][width] bytes (8-bit grey, the cv::Mat rows packed).  corners_xy[batch][max_corners][2] =
  * cv::Point2f (x, y) of the corners in OpenCV's order, n_corners[batch]; both may be NULL (results stay on the device:
  * vloam_vo_get_corner_buffers).  The block size is the reference's 5.  VLOAM_E_CAPACITY: an image whose response has more
  * local maxima than a quarter of its pixels (large plateaus of exactly equal response). */
@@ -323,10 +323,13 @@ int vloam_vo_describe_orb(vloam_vo* h, const uint8_t* images, int height, int wi
  * ORB, BF matcher, kNN selector): keypoints[i] = detKeypoints(img), descriptors[i] = descKeypoints(keypoints[i], img) and, from
  * the second frame on (count > 0), matches = matchDescriptors(descriptors[1 - i], descriptors[i]) — one upload of the images,
  * everything else on the device; the matched pixel pairs land in the buffers vloam_vo_get_match_buffers names, in solveNlsAll's
- * layout.  Call vloam_vo_reset first (visual_odometry.cpp:86-90), as the reference's frame loop does.  images: host
- * [batch][height][width] bytes; n_keypoints / n_matches [batch]: optional host read-outs (NULL, NULL = no synchronisation
- * after the launches; the first frame reports 0 matches).  max_matches must be >= 1024 (the detector's maxCorners). */
+ * layout.  Call vloam_vo_reset first (visual_odometry.cpp:86-90), as the reference's frame loop does.  images:
+ * [batch][height][width] bytes in host memory (pinned for an asynchronous upload) or already in device memory; n_keypoints /
+ * n_matches [batch]: optional host read-outs (NULL, NULL = nothing is read back and the stream is not synchronised: the call
+ * only enqueues; vloam_vo_get_detect_status then tells whether a frame overflowed the candidate list; the first frame reports
+ * 0 matches).  max_matches must be >= 1024 (the detector's maxCorners). */
 int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int width, int* n_keypoints, int* n_matches);
+int vloam_vo_get_detect_status(vloam_vo* h, int* overflowed);
 /* keypoints[slot] / descriptors[slot] of that chain (slot 0 = current frame, 1 = previous frame): keypoints_xy
  * [batch][max_matches][2], descriptors [batch][max_matches][32], n_keypoints[batch]; each may be NULL. */
 int vloam_vo_get_frame_features(vloam_vo* h, int slot, float* keypoints_xy, uint8_t* descriptors, int* n_keypoints);

@@ -356,6 +356,16 @@ def test_cuda_process_image_chain_hits_the_opencv_vectors(detect_golden, orb_gol
     assert np.array_equal(vo.matches()[0], F.match_descriptors(g["kitti_next_desc"], g["kitti_desc"]))
     assert r2["n_matches"][0] == len(vo.matches()[0])
     vo.close()
+    # the same two frames from device memory, enqueued without any read-back (the call does not synchronise): same results
+    import torch
+    vd = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+    for f in frames:
+        vd.reset()
+        assert vd.processImage(torch.from_numpy(f).cuda(), fetch=False) is None
+    assert vd.detect_status() == 0
+    assert np.array_equal(vd.matches()[0], g["chain_matches"]) and np.array_equal(vd.matches()[1], m[1])
+    assert np.array_equal(vd.frame_features(0)[0]["descriptors"], g["kitti_next_desc"])
+    vd.close()
 
 
 @pytest.mark.gpu

@@ -121,6 +121,7 @@ def lib():
             "vloam_vo_describe_orb": [vp, vp, C.c_int, C.c_int, vp, vp, vp, vp, vp, vp],
             "vloam_vo_process_image": [vp, vp, C.c_int, C.c_int, vp, vp],
             "vloam_vo_get_frame_features": [vp, C.c_int, vp, vp, vp], "vloam_vo_get_matches": [vp, vp, vp],
+            "vloam_vo_get_detect_status": [vp, c_ip],
         }
         for name, args in sig.items():
             fn = getattr(L, name)
@@ -712,15 +713,25 @@ class VisualOdometry:
         """VisualOdometry::processImage: detection, description and (from the second frame on) matching against the previous
         frame on the device; call reset() first, like the reference's frame loop.  fetch: return per stream
         {"n_keypoints", "n_matches"}; the features and matches are read with frame_features() / matches()."""
-        a = np.ascontiguousarray(images, np.uint8)
-        if a.ndim == 2:
-            a = a[None]
+        if hasattr(images, "data_ptr"):            # a torch tensor: pinned host memory or device memory, used in place
+            a = images
+            assert a.dtype.itemsize == 1 and a.is_contiguous() and a.dim() == 3
+        else:
+            a = np.ascontiguousarray(images, np.uint8)
+            if a.ndim == 2:
+                a = a[None]
         assert a.shape[0] == self.batch, a.shape
         nk = np.zeros(self.batch, np.int32) if fetch else None
         nm = np.zeros(self.batch, np.int32) if fetch else None
-        self.ctx.check(lib().vloam_vo_process_image(self._h, _ptr(a), a.shape[1], a.shape[2], _ptr(nk), _ptr(nm)))
-        self._det_shape = a.shape[1:]
+        self.ctx.check(lib().vloam_vo_process_image(self._h, _ptr(a), int(a.shape[1]), int(a.shape[2]), _ptr(nk), _ptr(nm)))
+        self._det_shape = (int(a.shape[1]), int(a.shape[2]))
         return {"n_keypoints": nk, "n_matches": nm} if fetch else None
+
+    def detect_status(self) -> int:
+        """1 when a frame of the last detection overflowed its candidate list (only of interest after processImage(fetch=False))."""
+        s = C.c_int(0)
+        self.ctx.check(lib().vloam_vo_get_detect_status(self._h, C.byref(s)))
+        return s.value
 
     def frame_features(self, slot: int = 0):
         """keypoints[slot] / descriptors[slot] of the processImage chain (0 = current frame, 1 = previous), per stream."""

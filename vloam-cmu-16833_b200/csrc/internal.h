@@ -102,6 +102,7 @@ cudaError_t lm_set_cube(LMDevice* lm, cudaStream_t st, int stream, int kind, int
 struct VODetect;
 cudaError_t vo_detect_run(VODetect** d, Profiler* prof, cudaStream_t st, int B, const uint8_t* images, int H, int W, int maxCorners,
                           double quality, double minDistance, int* status_out);
+cudaError_t vo_detect_status(VODetect* d, cudaStream_t st, int* status_out);
 cudaError_t vo_detect_read(VODetect* d, cudaStream_t st, float* corners, int* n);
 cudaError_t vo_detect_response(VODetect* d, cudaStream_t st, int stream, float* out, size_t pixels);
 const float* vo_detect_corners_device(const VODetect* d);

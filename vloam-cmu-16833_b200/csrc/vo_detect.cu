@@ -360,7 +360,8 @@ static cudaError_t vo_detect_alloc(VODetect** pd, int B, int H, int W, int cell,
   return e;
 }
 
-// images: host [B][H][W] (8-bit).  Results stay on the device until read with vo_detect_read.
+// images: [B][H][W] (8-bit), host or device memory (the copy direction is inferred).  Results stay on the device until read with
+// vo_detect_read.  status_out == NULL: nothing is read back and the stream is not synchronised (vo_detect_status reads the flag later).
 cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B, const uint8_t* images, int H, int W, int maxCorners,
                           double quality, double minDistance, int* status_out) {
   const int cell = (int)nearbyint(minDistance) > 0 ? (int)nearbyint(minDistance) : 1;     // cvRound (half to even)
@@ -368,7 +369,7 @@ cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B,
   if (e != cudaSuccess) return e;
   VODetect* d = *pd;
   const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
-  e = cudaMemcpyAsync(d->img, images, (size_t)B * H * W, cudaMemcpyHostToDevice, st);
+  e = cudaMemcpyAsync(d->img, images, (size_t)B * H * W, cudaMemcpyDefault, st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d->maxBits, 0, B * sizeof(unsigned), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d->nCand, 0, B * sizeof(int), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d->status, 0, B * sizeof(int), st);
@@ -379,11 +380,17 @@ cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B,
                                                                                       d->nCand, d->kA, d->vA, d->kB, d->vB, d->state, d->cellStart, d->cellFill,
                                                                                       d->cellItems, d->corners, d->nCorners));
   e = cudaGetLastError();
-  if (e != cudaSuccess) return e;
-  std::vector<int> stt(B);
-  e = cudaMemcpyAsync(stt.data(), d->status, B * sizeof(int), cudaMemcpyDeviceToHost, st);
+  if (e != cudaSuccess || !status_out) return e;
+  return vo_detect_status(d, st, status_out);
+}
+
+// 1 when a stream's candidate list overflowed in the last run (synchronises the stream)
+cudaError_t vo_detect_status(VODetect* d, cudaStream_t st, int* status_out) {
+  std::vector<int> stt(d->B);
+  cudaError_t e = cudaMemcpyAsync(stt.data(), d->status, d->B * sizeof(int), cudaMemcpyDeviceToHost, st);
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  if (e == cudaSuccess && status_out) { *status_out = 0; for (int b = 0; b < B; ++b) *status_out |= stt[b]; }
+  *status_out = 0;
+  if (e == cudaSuccess) for (int b = 0; b < d->B; ++b) *status_out |= stt[b];
   return e;
 }
 

@@ -1051,8 +1051,9 @@ int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int w
   if (h->maxM < 1024) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_process_image: max_matches must hold the detector's 1024 corners");
   VCU(c, cudaSetDevice(c->device));
   cudaStream_t st = c->stream;
+  const bool fetch = n_keypoints || n_matches;
   int status = 0;
-  VCU(c, vb::vo_detect_run(&h->det, &c->prof, st, h->B, images, height, width, 1024, 0.03, 7.5, &status));      // image_util.cpp:13-26
+  VCU(c, vb::vo_detect_run(&h->det, &c->prof, st, h->B, images, height, width, 1024, 0.03, 7.5, fetch ? &status : nullptr));      // image_util.cpp:13-26
   if (status) return vfail(c, VLOAM_E_CAPACITY, "vloam_vo_process_image: more local maxima than a quarter of the pixels (plateaus of equal response)");
   const int i = h->slot();
   if (int rc = vo_enqueue_describe(h, vb::vo_detect_image_device(h->det), height, width, vb::vo_detect_corners_device(h->det),
@@ -1065,7 +1066,18 @@ int vloam_vo_process_image(vloam_vo* h, const uint8_t* images, int height, int w
   }
   if (n_keypoints) VCU(c, cudaMemcpyAsync(n_keypoints, h->d_fn[i], h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
   if (n_matches) VCU(c, cudaMemcpyAsync(n_matches, h->d_nmatch, h->B * sizeof(int), cudaMemcpyDeviceToHost, st));
-  if (n_keypoints || n_matches) VCU(c, cudaStreamSynchronize(st));
+  if (fetch) VCU(c, cudaStreamSynchronize(st));
+  return VLOAM_OK;
+}
+
+// The capacity flag of the last detection (vloam_vo_detect_corners / vloam_vo_process_image), for callers that did not synchronise:
+// *overflowed = 1 when a stream's response map had more local maxima than a quarter of its pixels (the corners of that frame are
+// then those of a truncated candidate list).  Synchronises the stream.
+int vloam_vo_get_detect_status(vloam_vo* h, int* overflowed) {
+  if (!h || !overflowed) return VLOAM_E_INVALID;
+  if (!h->det) return vfail(h->ctx, VLOAM_E_STATE, "vloam_vo_get_detect_status before a detection");
+  VCU(h->ctx, cudaSetDevice(h->ctx->device));
+  VCU(h->ctx, vb::vo_detect_status(h->det, h->ctx->stream, overflowed));
   return VLOAM_OK;
 }
 
