@@ -152,14 +152,54 @@ def make_base_scans(rank: int, needed, world: int = 1, batch: int = N_BASE, with
     return (seqs, streams) if with_streams else seqs
 
 
+_FRAME_BASE = None
+
+
+def frame_of(stream_index: int, step: int):
+    """configs[3]: the camera frame of stream `stream_index` at replay step `step` — the committed KITTI-sized test image
+    (376 x 1241) moved horizontally by a per-stream offset, 4 px further on odd steps.  The frames feed the image front end
+    (detection, ORB description, matching: its cost is in the step); they do not depict the LiDAR scene, so the solve takes
+    the geometry-consistent synthetic matches of synth.make_matches."""
+    global _FRAME_BASE
+    if _FRAME_BASE is None:
+        _FRAME_BASE = np.load(os.path.join(ROOT, "tests", "golden", "vo_detect_cv2.npz"))["kitti_image"]
+    return np.roll(_FRAME_BASE, (stream_index * 37) % 300 + 4 * (step % 2), axis=1)
+
+
+class CpuFrontEnd:
+    """VisualOdometry::processImage as the reference runs it (visual_odometry.cpp:92-130): the three OpenCV calls, one thread."""
+
+    def __init__(self):
+        try:
+            import cv2
+            cv2.setNumThreads(1)
+            self.cv2, self.orb, self.bf = cv2, cv2.ORB_create(), cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+        except ImportError:
+            self.cv2 = None
+        self.prev = None
+
+    def process(self, img):
+        if self.cv2 is None:
+            return
+        cv2 = self.cv2
+        c = cv2.goodFeaturesToTrack(img, 1024, 0.03, 7.5, None, blockSize=5, useHarrisDetector=False, k=0.04)
+        c = np.zeros((0, 2), np.float32) if c is None else c.reshape(-1, 2)
+        _, d = self.orb.compute(img, [cv2.KeyPoint(float(x), float(y), 5.0) for x, y in c])
+        if self.prev is not None and d is not None and len(self.prev) and len(d):
+            knn = self.bf.knnMatch(self.prev, d, 2)
+            _ = [m[0] for m in knn if len(m) == 2 and m[0].distance < 0.8 * m[1].distance]
+        self.prev = d
+
+
 class CpuChain:
     """One stream through the oracle in the order of vloam_main_node.cpp:125-180 (CPU arm / cpu_baseline).
     workload: sr_lo | sr_lo_lm | vloam (adds VisualOdometry and feeds its result to laserOdometry as the prior)."""
 
     def __init__(self, O, workload, map_cubes, lm_iterations=4):
         self.O, self.workload = O, workload
-        self.t = {"sr_ms": 0.0, "lo_ms": 0.0, "lm_ms": 0.0, "vo_ms": 0.0, "scans": 0}
+        self.t = {"sr_ms": 0.0, "lo_ms": 0.0, "lm_ms": 0.0, "vo_ms": 0.0, "fe_ms": 0.0, "scans": 0}
         if workload == "vloam":
+            self.fe = CpuFrontEnd()
             from vloam_b200 import synth
             self.calib = synth.kitti_like_calibration()
             self.velo_T_cam0 = np.linalg.inv(self.calib[0].astype(np.float64))
@@ -174,13 +214,17 @@ class CpuChain:
         for (kind, cube), pts in map_cubes.items():
             self.lm.set_cube(kind, cube, pts)
 
-    def process(self, scan, matches=None):
+    def process(self, scan, matches=None, frame=None):
         O = self.O
         if self.workload != "vloam":
             self.pipe.process(scan, do_mapping=self.workload == "sr_lo_lm")
             self.t.update(self.pipe.timings())
             return
+        tf = time.perf_counter()
+        if frame is not None:
+            self.fe.process(frame)
         t0 = time.perf_counter()
+        self.t["fe_ms"] += 1e3 * (t0 - tf)
         self.vo.reset()
         self.vo.process_cloud(scan)
         prior = np.r_[0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0]
@@ -222,8 +266,9 @@ WORKLOAD_NAME = {
     "sr_lo": ("scanRegistration+laserOdometry", "configs[1]: scanRegistration + laserOdometry on 1xB200, synthetic 64x2048 range-image stream"),
     "sr_lo_lm": ("scanRegistration+laserOdometry+laserMapping",
                  "configs[2]: laserOdometry + laserMapping scan-to-submap (1M-pt voxel map, 10 GN iters) on 1xB200, fed by scanRegistration"),
-    "vloam": ("visualOdometry(depth+solve)+scanRegistration+laserOdometry(VO prior)+laserMapping",
-              "configs[3]: full VLOAM, visual odometry depth association + solve feeding LiDAR odometry and mapping"),
+    "vloam": ("visualOdometry(image front end+depth+solve)+scanRegistration+laserOdometry(VO prior)+laserMapping",
+              "configs[3]: full VLOAM, visual odometry (Shi-Tomasi + ORB + BF matching on 1241x376 frames, depth association, solve) "
+              "feeding LiDAR odometry and mapping"),
 }
 
 
@@ -274,7 +319,7 @@ def run_reference(args, rank):
         if args.workload == "vloam" else {}
 
     def one(t, i):
-        pipes[t].process(seqs[t % N_BASE][scan_index(i)], mt.get((t % N_BASE, i)))
+        pipes[t].process(seqs[t % N_BASE][scan_index(i)], mt.get((t % N_BASE, i)), frame_of(t, i) if args.workload == "vloam" else None)
 
     with ThreadPoolExecutor(T) as ex:
         for i in range(args.warmup):
@@ -295,7 +340,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": value, "unit": "scans/s", "cores": T, "kind": "port",
                          "sample": f"{T} threads x {args.steps} scans, one stream per thread (the GPU arm's streams_per_gpu streams are a batch "
                                    f"dimension this CPU path does not have); per-thread SR {tm['sr_ms']/max(1,tm['scans']):.1f} ms, "
-                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"
+                                   f"LO {tm['lo_ms']/max(1,tm['scans']):.1f} ms, LM {tm['lm_ms']/max(1,tm['scans']):.1f} ms, VO {tm.get('vo_ms', 0.0)/max(1,tm['scans']):.1f} ms, image front end (OpenCV) {tm.get('fe_ms', 0.0)/max(1,tm['scans']):.1f} ms per scan"
                                    + (f"; LM iterations executed in the last scan's passes: {its}" if its else "")},
         "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -447,6 +492,9 @@ def run_ours(args, rank, world, local_rank):
                 hp[b, :len(pu)] = torch.from_numpy(pu); hc[b, :len(cu)] = torch.from_numpy(cu); hn[b] = len(pu)
             match_host[(kp, k)] = (hp, hc, hn)
             match_dev[(kp, k)] = (hp.to(dev), hc.to(dev), hn.to(dev))
+        # camera frames: one per stream and step parity (frame_of), pinned on the host and resident on the device
+        frames_host = [torch.from_numpy(np.stack([frame_of(rank * B + b, par) for b in range(B)])).pin_memory() for par in range(2)]
+        frames_dev = [f.to(dev) for f in frames_host]
     torch.cuda.synchronize()
 
     stream = torch.cuda.Stream(device=dev)
@@ -478,8 +526,9 @@ def run_ours(args, rank, world, local_rank):
                 self.nm = torch.zeros((self.nb,), dtype=torch.int32, device=dev)
             self.steps = 0
 
-        def _vo(self, i, xyz, n, stride, slab, pu, cu, nm):
+        def _vo(self, i, xyz, n, stride, slab, pu, cu, nm, frames):
             self.vo.reset()
+            self.vo.processImage(frames, fetch=False)                # visual_odometry.cpp:92-130: enqueues, no synchronisation
             self.vo.processPointCloudDevice(xyz, n, stride, slab)
             if self.steps > 0:
                 self.vo.solveNlsAllDevice(pu, cu, nm)
@@ -497,7 +546,7 @@ def run_ours(args, rank, world, local_rank):
             if do_vo:
                 pu, cu, nm = match_dev[(scan_index(i - 1), k)] if i > 0 else (None, None, None)
                 self._vo(i, dev_pool[k][sl], n_dev[sl], 3, cap, None if pu is None else pu[sl], None if cu is None else cu[sl],
-                         None if nm is None else nm[sl])
+                         None if nm is None else nm[sl], frames_dev[i % 2][sl])
             self.lom.laserOdometryIO(prior=self.prior, fetch=False)
             if do_map:
                 self.lom.laserMappingIO(fetch=False)
@@ -520,7 +569,7 @@ def run_ours(args, rank, world, local_rank):
                     hp, hc, hn = match_host[(scan_index(i - 1), k)]
                     self.uv[0].copy_(hp[sl], non_blocking=True); self.uv[1].copy_(hc[sl], non_blocking=True)
                     self.nm.copy_(hn[sl], non_blocking=True)
-                self._vo(i, xyz, n, stride, slab, self.uv[0], self.uv[1], self.nm)
+                self._vo(i, xyz, n, stride, slab, self.uv[0], self.uv[1], self.nm, frames_host[i % 2][sl])
                 self.lom.input_consumed()
             self.lom.laserOdometryIO(prior=self.prior, fetch=False)
             if do_map:
@@ -722,7 +771,7 @@ def run_ours(args, rank, world, local_rank):
         ms_e2e = max(ms_e2e_ranks)
     pose_host = {kk: np.concatenate([p_[kk] for p_ in poses_h]) for kk in poses_h[0]}
     e2e_value = (1 if point else world) * B * args.steps / (ms_e2e * 1e-3)
-    h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) if do_vo else 0))
+    h2d = int(B * cap * 12 + B * 4 + (B * (2 * M * 2 * 4 + 4) + int(frames_host[0].numel()) if do_vo else 0))
     d2h = int(B * 16 * 8)
     shard_err = g2.lom.shard_status() if (point and not point_nccl) else 0
     # same inputs, same number of steps -> both legs must end on identical poses
@@ -872,7 +921,7 @@ def run_ours(args, rank, world, local_rank):
     cpu_m = [cpu_matches(scan_streams[0], i) for i in range(n_cpu)] if do_vo else [None] * n_cpu
     t0 = time.perf_counter()
     for i in range(n_cpu):
-        pipe.process(seqs[0][scan_index(i)], cpu_m[i])
+        pipe.process(seqs[0][scan_index(i)], cpu_m[i], frame_of(0, i) if do_vo else None)
     cpu_dt = time.perf_counter() - t0
     tm = pipe.timings()
     cpu_value = n_cpu / cpu_dt
@@ -928,7 +977,7 @@ def run_ours(args, rank, world, local_rank):
                     "(the reference filters them again and gets the same cloud back)"},
         "cpu_baseline": {"value": cpu_value, "unit": "scans/s", "cores": 1, "kind": "port",
                          "sample": f"{n_cpu} scans of one stream, 1 thread: SR {tm['sr_ms']/n_cpu:.1f} ms + LO {tm['lo_ms']/n_cpu:.1f} ms"
-                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"
+                                   + (f" + LM {tm['lm_ms']/n_cpu:.1f} ms" if do_map else "") + (f" + VO {tm['vo_ms']/n_cpu:.1f} ms + image front end (OpenCV, 1 thread) {tm['fe_ms']/n_cpu:.1f} ms" if do_vo else "") + " per scan"
                                    + (f"; LM iterations executed in the last scan's passes: {pipe.lm_iterations()}" if do_map else "")},
         "clocks": clocks,
     }
