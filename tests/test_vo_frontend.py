@@ -187,6 +187,14 @@ def test_cuda_detector_hits_the_opencv_vectors(detect_golden):
         few = vo.detKeypoints(np.stack([img, np.full_like(img, 77)]), max_corners=100, quality_level=0.1, min_distance=20.0)
         assert np.array_equal(few[0], F.good_features_to_track(img, 100, 0.1, 20.0))
         assert few[1].shape == (0, 2)
+        if name == "kitti":
+            # ~13 000 candidates: only the strongest ~4 100 are ranked at first.  Spacing 12: the 1024th corner sits inside that
+            # prefix; spacing 20: the frame holds fewer than 1024 such corners, the prefix runs out and the whole list is ranked
+            for md in (12.0, 20.0):
+                wide = vo.detKeypoints(pair2 := np.stack([img, flipped]), max_corners=1024, quality_level=0.03, min_distance=md)
+                for b in range(2):
+                    assert np.array_equal(wide[b], F.good_features_to_track(pair2[b], 1024, 0.03, md)), (md, b)
+            assert len(wide[0]) < 1024
         vo.close()
 
 

@@ -12,7 +12,8 @@
 //                        comes out of rounds in which every undecided candidate looks at the earlier candidates within the
 //                        radius: any of them kept -> dropped; all of them dropped -> kept; otherwise wait.  The earliest
 //                        undecided candidate is always decided, a round decides thousands at once.  The rounds walk a growing
-//                        prefix of the ranking and stop once max_corners are kept.
+//                        prefix of the ranking and stop once max_corners are kept; with many candidates only the strongest ~4096
+//                        (a histogram cut on the response) are ranked at all, the rest only if that prefix runs out.
 // Every float operation that OpenCV's vectorised path fuses or does not fuse is written with the explicit intrinsic, so the
 // response map carries the oracle's bits.
 #include <cuda_runtime.h>
@@ -33,7 +34,7 @@ struct VODetect {
   float* eig = nullptr;          // [B][H][W]
   unsigned* maxBits = nullptr;   // [B] bits of the largest (positive) response
   int* nCand = nullptr;          // [B]
-  unsigned *kA = nullptr, *vA = nullptr, *kB = nullptr, *vB = nullptr;   // [B][capCand] sort buffers
+  unsigned *kA = nullptr, *vA = nullptr, *kB = nullptr, *vB = nullptr, *kC = nullptr, *vC = nullptr;   // [B][capCand] sort buffers
   uint8_t* state = nullptr;      // [B][capCand] 0 undecided, 1 kept, 2 dropped
   int* cellStart = nullptr;      // [B][cells + 1]
   int* cellFill = nullptr;       // [B][cells]
@@ -224,28 +225,70 @@ __global__ void __launch_bounds__(256) vo_corner_candidates(const float* __restr
 
 // grid (B), block 1024, dynamic shared memory = sizeof(SortSmem)
 __global__ void __launch_bounds__(1024, 1) vo_select_corners(int H, int W, int capCand, int cells, int gw, int gh, int cell, float minDist2,
-                                                          int maxCorners, const int* __restrict__ nCand, unsigned* kAall, unsigned* vAall,
-                                                          unsigned* kBall, unsigned* vBall, uint8_t* __restrict__ stateAll, int* __restrict__ cellStartAll,
+                                                          int maxCorners, const int* __restrict__ nCand, const unsigned* __restrict__ maxBits, double quality,
+                                                          unsigned* kAall, unsigned* vAall, unsigned* kBall, unsigned* vBall, unsigned* kCall, unsigned* vCall,
+                                                          uint8_t* __restrict__ stateAll, int* __restrict__ cellStartAll,
                                                           int* __restrict__ cellFillAll, int* __restrict__ cellItemsAll, float* __restrict__ cornersAll,
                                                           int* __restrict__ nCorners) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   SortSmem& S = *reinterpret_cast<SortSmem*>(smem_raw);
   const int b = blockIdx.x, tid = threadIdx.x;
-  const int n = min(nCand[b], capCand);
+  const int nAll = min(nCand[b], capCand);
   unsigned* kA = kAall + (size_t)b * capCand; unsigned* vA = vAall + (size_t)b * capCand;
   unsigned* kB = kBall + (size_t)b * capCand; unsigned* vB = vBall + (size_t)b * capCand;
+  unsigned* kC = kCall + (size_t)b * capCand; unsigned* vC = vCall + (size_t)b * capCand;
+  __shared__ int s_cut, s_kept;
   volatile uint8_t* state = stateAll + (size_t)b * capCand;
   int* cellStart = cellStartAll + (size_t)b * (cells + 1);
   int* cellFill = cellFillAll + (size_t)b * cells;
   int* cellItems = cellItemsAll + (size_t)b * capCand;
   float* corners = cornersAll + (size_t)b * maxCorners * 2;
-  if (n == 0) { if (tid == 0) nCorners[b] = 0; return; }
-  // ---- order: address descending (unique, makes the unordered candidate list canonical), then value descending (stable)
+  if (nAll == 0) { if (tid == 0) nCorners[b] = 0; return; }
   int bitsOfs = 1;
   while ((1ll << bitsOfs) < (long long)H * W) ++bitsOfs;
-  int cur = cta_radix_sort(kA, vA, kB, vB, n, bitsOfs, S);                       // (key = address', value = response')
-  unsigned* k1 = cur ? kB : kA; unsigned* v1 = cur ? vB : vA;
-  unsigned* k2 = cur ? kA : kB; unsigned* v2 = cur ? vA : vB;
+  // The output is the first maxCorners kept candidates of the ranking and the spacing pass below walks a prefix of it, so when
+  // there are many candidates only the strongest kCutTarget (plus the rest of the response bin the cut falls into) are ranked:
+  // a 4096-bin histogram of the (complemented) response bits between the frame's maximum and the threshold gives the bin, the
+  // candidates up to it are copied aside and sorted.  Should that prefix run out before maxCorners are kept (dense clusters), the
+  // whole list is ranked in a second attempt — the source list (kA, vA) is still intact then.
+  constexpr int kCutTarget = 4096, kCutBins = 4096;
+  for (int attempt = nAll > 2 * kCutTarget ? 0 : 1; attempt < 2; ++attempt) {
+  int n = nAll;
+  unsigned* kS = kA; unsigned* vS = vA;
+  if (attempt == 0) {
+    const float vmax = __uint_as_float(maxBits[b]);
+    const unsigned lo = ~maxBits[b], hi = ~__float_as_uint((float)((double)vmax * quality));     // response' of every candidate lies in [lo, hi)
+    int shift = 0;
+    while (((hi - lo) >> shift) >= (unsigned)kCutBins) ++shift;
+    int* hist = &S.off[0][0];
+    for (int i = tid; i < kCutBins; i += 1024) hist[i] = 0;
+    if (tid == 0) { s_cut = kCutBins - 1; s_kept = 0; }
+    __syncthreads();
+    for (int r = tid; r < nAll; r += 1024) atomicAdd(&hist[min((vA[r] - lo) >> shift, (unsigned)(kCutBins - 1))], 1);
+    __syncthreads();
+    int c4[kCutBins / 1024], sum = 0;
+#pragma unroll
+    for (int j = 0; j < kCutBins / 1024; ++j) { c4[j] = hist[tid * (kCutBins / 1024) + j]; sum += c4[j]; }
+    int run = block_exclusive_scan1024(sum, S);
+#pragma unroll
+    for (int j = 0; j < kCutBins / 1024; ++j) {
+      if (run < kCutTarget && run + c4[j] >= kCutTarget) s_cut = tid * (kCutBins / 1024) + j;      // exactly one bin crosses the target
+      run += c4[j];
+    }
+    __syncthreads();
+    const unsigned cutBin = (unsigned)s_cut;
+    for (int r = tid; r < nAll; r += 1024) {
+      const unsigned v = vA[r];
+      if (min((v - lo) >> shift, (unsigned)(kCutBins - 1)) <= cutBin) { const int dst = atomicAdd(&s_kept, 1); kC[dst] = kA[r]; vC[dst] = v; }
+    }
+    __syncthreads();
+    n = s_kept; kS = kC; vS = vC;
+    __syncthreads();
+  }
+  // ---- order: address descending (unique, makes the unordered candidate list canonical), then value descending (stable)
+  int cur = cta_radix_sort(kS, vS, kB, vB, n, bitsOfs, S);                       // (key = address', value = response')
+  unsigned* k1 = cur ? kB : kS; unsigned* v1 = cur ? vB : vS;
+  unsigned* k2 = cur ? kS : kB; unsigned* v2 = cur ? vS : vB;
   __syncthreads();
   cur = cta_radix_sort(v1, k1, v2, k2, n, 32, S);                                // (key = response', value = address')
   const unsigned* ofsSorted = cur ? k2 : k1;                                      // rank -> complemented address
@@ -317,6 +360,7 @@ __global__ void __launch_bounds__(1024, 1) vo_select_corners(int H, int W, int c
     for (int r0 = lo; r0 < hi; r0 += 1024) keptTotal += __syncthreads_count(r0 + tid < hi && state[r0 + tid] == 1);
     limit = hi;
   }
+  if (attempt == 0 && keptTotal < maxCorners && n < nAll) { __syncthreads(); continue; }      // the prefix ran out: rank everything
   // ---- the first maxCorners kept candidates, in rank order
   {
     const int per = (limit + 1023) / 1024;
@@ -329,13 +373,15 @@ __global__ void __launch_bounds__(1024, 1) vo_select_corners(int H, int W, int c
       if (state[r] == 1) { const unsigned q = pos[r]; corners[2 * p] = (float)(q & 0xffffu); corners[2 * p + 1] = (float)(q >> 16); ++p; }
     if (tid == 0) nCorners[b] = min(total, maxCorners);
   }
+  break;
+  }
 }
 
 }  // namespace
 
 void vo_detect_destroy(VODetect* d) {
   if (!d) return;
-  cudaFree(d->img); cudaFree(d->eig); cudaFree(d->maxBits); cudaFree(d->nCand); cudaFree(d->kA); cudaFree(d->vA); cudaFree(d->kB); cudaFree(d->vB);
+  cudaFree(d->img); cudaFree(d->eig); cudaFree(d->maxBits); cudaFree(d->nCand); cudaFree(d->kA); cudaFree(d->vA); cudaFree(d->kB); cudaFree(d->vB); cudaFree(d->kC); cudaFree(d->vC);
   cudaFree(d->state); cudaFree(d->cellStart); cudaFree(d->cellFill); cudaFree(d->cellItems); cudaFree(d->corners); cudaFree(d->nCorners); cudaFree(d->status);
   delete d;
 }
@@ -352,7 +398,7 @@ static cudaError_t vo_detect_alloc(VODetect** pd, int B, int H, int W, int cell,
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 4); };
   const size_t px = (size_t)B * H * W, nc = (size_t)B * d->capCand;
   A((void**)&d->img, px); A((void**)&d->eig, px * sizeof(float)); A((void**)&d->maxBits, B * sizeof(unsigned)); A((void**)&d->nCand, B * sizeof(int));
-  A((void**)&d->kA, nc * 4); A((void**)&d->vA, nc * 4); A((void**)&d->kB, nc * 4); A((void**)&d->vB, nc * 4); A((void**)&d->state, nc);
+  A((void**)&d->kA, nc * 4); A((void**)&d->vA, nc * 4); A((void**)&d->kB, nc * 4); A((void**)&d->vB, nc * 4); A((void**)&d->kC, nc * 4); A((void**)&d->vC, nc * 4); A((void**)&d->state, nc);
   A((void**)&d->cellStart, (size_t)B * (d->cells + 1) * sizeof(int)); A((void**)&d->cellFill, (size_t)B * d->cells * sizeof(int));
   A((void**)&d->cellItems, nc * sizeof(int)); A((void**)&d->corners, (size_t)B * maxCorners * 2 * sizeof(float));
   A((void**)&d->nCorners, B * sizeof(int)); A((void**)&d->status, B * sizeof(int));
@@ -377,7 +423,7 @@ cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B,
   VB_LAUNCH(prof, K_VO_DETECT, st, vo_min_eigen<<<dim3((W + kTileW - 1) / kTileW, (H + kTileH - 1) / kTileH, B), 256, 0, st>>>(d->img, H, W, d->eig, d->maxBits));
   VB_LAUNCH(prof, K_VO_DETECT, st, vo_corner_candidates<<<dim3((W + 31) / 32, (H + 8 * kCandRows - 1) / (8 * kCandRows), B), dim3(32, 8), 0, st>>>(d->eig, H, W, d->maxBits, quality, d->capCand, d->kA, d->vA, d->nCand, d->status));
   VB_LAUNCH(prof, K_VO_DETECT, st, vo_select_corners<<<B, 1024, sizeof(SortSmem), st>>>(H, W, d->capCand, d->cells, gw, gh, cell, (float)(minDistance * minDistance), maxCorners,
-                                                                                      d->nCand, d->kA, d->vA, d->kB, d->vB, d->state, d->cellStart, d->cellFill,
+                                                                                      d->nCand, d->maxBits, quality, d->kA, d->vA, d->kB, d->vB, d->kC, d->vC, d->state, d->cellStart, d->cellFill,
                                                                                       d->cellItems, d->corners, d->nCorners));
   e = cudaGetLastError();
   if (e != cudaSuccess || !status_out) return e;
