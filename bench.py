@@ -1012,25 +1012,17 @@ def frontend_leg(V, device_index, frames_per_call=32, reps=10):
                "kernel_ms_per_call": {k_: v_[0] / reps for k_, v_ in kt.items()}, "gpu_launches_per_call": sum(v_[1] for v_ in kt.values()) / reps,
                "keypoints_stream0": int(r["n_keypoints"][0]), "matches_stream0": int(r["n_matches"][0]), "h2d_bytes_per_call": int(frames[0].nbytes)}
         vo.close(); ctx.close()
-        try:
-            import cv2
-            cv2.setNumThreads(1)
-            orb, bf = cv2.ORB_create(), cv2.BFMatcher(cv2.NORM_HAMMING, crossCheck=False)
+        fe = CpuFrontEnd()
+        out["cv2_ms_per_frame_1_thread"] = None
+        if fe.cv2 is not None:
+            n_cpu = min(frames_per_call, 4)
             t0 = time.perf_counter()
-            for b_ in range(min(frames_per_call, 4)):
-                prev = None
+            for b_ in range(n_cpu):
+                fe.prev = None
                 for k in range(3):                    # (the first frame of a stream has nothing to match against)
-                    img = frames[k % 2][b_]
-                    c = cv2.goodFeaturesToTrack(img, 1024, 0.03, 7.5, None, blockSize=5, useHarrisDetector=False, k=0.04).reshape(-1, 2)
-                    _, d = orb.compute(img, [cv2.KeyPoint(float(x), float(y), 5.0) for x, y in c])
-                    if prev is not None:
-                        knn = bf.knnMatch(prev, d, 2)
-                        _ = [m[0] for m in knn if m[0].distance < 0.8 * m[1].distance]
-                    prev = d
-            out["cv2_ms_per_frame_1_thread"] = (time.perf_counter() - t0) / (3 * min(frames_per_call, 4)) * 1e3
-            out["cv2_version"] = cv2.__version__
-        except ImportError:
-            out["cv2_ms_per_frame_1_thread"] = None
+                    fe.process(frames[k % 2][b_])
+            out["cv2_ms_per_frame_1_thread"] = (time.perf_counter() - t0) / (3 * n_cpu) * 1e3
+            out["cv2_version"] = fe.cv2.__version__
         return out
     except Exception as e:      # noqa: BLE001
         return {"error": f"{type(e).__name__}: {e}"}
