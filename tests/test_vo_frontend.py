@@ -374,6 +374,17 @@ def test_cuda_process_image_chain_hits_the_opencv_vectors(detect_golden, orb_gol
     assert np.array_equal(vd.matches()[0], g["chain_matches"]) and np.array_equal(vd.matches()[1], m[1])
     assert np.array_equal(vd.frame_features(0)[0]["descriptors"], g["kitti_next_desc"])
     vd.close()
+    # ... and from pinned host memory: the frames are double-buffered and uploaded on the handle's copy stream while the previous
+    # frame's kernels run; four frames enqueued back to back reuse both buffers
+    vp = V.VisualOdometry(batch=2, max_points=1024, max_matches=1024)
+    pinned = [torch.from_numpy(f).pin_memory() for f in frames]
+    for k in range(4):
+        vp.reset()
+        vp.processImage(pinned[k % 2], fetch=False)
+    assert vp.detect_status() == 0
+    assert np.array_equal(vp.matches()[0], g["chain_matches"]) and np.array_equal(vp.matches()[1], m[1])
+    assert np.array_equal(vp.frame_features(0)[0]["descriptors"], g["kitti_next_desc"]) and np.array_equal(vp.frame_features(1)[0]["descriptors"], g["kitti_desc"])
+    vp.close()
 
 
 @pytest.mark.gpu

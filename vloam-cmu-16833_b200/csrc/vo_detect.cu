@@ -30,7 +30,15 @@ namespace vb {
 
 struct VODetect {
   int B = 0, H = 0, W = 0, capCand = 0, cells = 0, maxCorners = 0;
-  uint8_t* img = nullptr;        // [B][H][W]
+  uint8_t* img = nullptr;        // [B][H][W]: the frame the last run detected on (one of imgBuf)
+  // Frames are double-buffered and uploaded on a copy stream of their own, so the upload of frame k + 1 (from pinned host
+  // memory) overlaps the kernels of frame k: uploaded[j] orders the compute stream after the copy; freed[j], recorded on the
+  // compute stream at the start of the NEXT run, tells the copy stream that everything enqueued for the frame in buffer j is done.
+  uint8_t* imgBuf[2] = {nullptr, nullptr};
+  cudaStream_t copyStream = nullptr;
+  cudaEvent_t uploaded[2] = {nullptr, nullptr}, freed[2] = {nullptr, nullptr};
+  bool freedValid[2] = {false, false};
+  int cur = -1;                  // buffer of the last run (-1: none yet)
   float* eig = nullptr;          // [B][H][W]
   unsigned* maxBits = nullptr;   // [B] bits of the largest (positive) response
   int* nCand = nullptr;          // [B]
@@ -381,7 +389,13 @@ __global__ void __launch_bounds__(1024, 1) vo_select_corners(int H, int W, int c
 
 void vo_detect_destroy(VODetect* d) {
   if (!d) return;
-  cudaFree(d->img); cudaFree(d->eig); cudaFree(d->maxBits); cudaFree(d->nCand); cudaFree(d->kA); cudaFree(d->vA); cudaFree(d->kB); cudaFree(d->vB); cudaFree(d->kC); cudaFree(d->vC);
+  for (int j = 0; j < 2; ++j) {
+    cudaFree(d->imgBuf[j]);
+    if (d->uploaded[j]) cudaEventDestroy(d->uploaded[j]);
+    if (d->freed[j]) cudaEventDestroy(d->freed[j]);
+  }
+  if (d->copyStream) { cudaStreamSynchronize(d->copyStream); cudaStreamDestroy(d->copyStream); }
+  cudaFree(d->eig); cudaFree(d->maxBits); cudaFree(d->nCand); cudaFree(d->kA); cudaFree(d->vA); cudaFree(d->kB); cudaFree(d->vB); cudaFree(d->kC); cudaFree(d->vC);
   cudaFree(d->state); cudaFree(d->cellStart); cudaFree(d->cellFill); cudaFree(d->cellItems); cudaFree(d->corners); cudaFree(d->nCorners); cudaFree(d->status);
   delete d;
 }
@@ -397,7 +411,12 @@ static cudaError_t vo_detect_alloc(VODetect** pd, int B, int H, int W, int cell,
   cudaError_t e = cudaSuccess;
   auto A = [&](void** p, size_t bytes) { if (e == cudaSuccess) e = cudaMalloc(p, bytes ? bytes : 4); };
   const size_t px = (size_t)B * H * W, nc = (size_t)B * d->capCand;
-  A((void**)&d->img, px); A((void**)&d->eig, px * sizeof(float)); A((void**)&d->maxBits, B * sizeof(unsigned)); A((void**)&d->nCand, B * sizeof(int));
+  A((void**)&d->imgBuf[0], px); A((void**)&d->imgBuf[1], px); A((void**)&d->eig, px * sizeof(float));
+  if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&d->copyStream, cudaStreamNonBlocking);
+  for (int j = 0; j < 2; ++j) {
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->uploaded[j], cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&d->freed[j], cudaEventDisableTiming);
+  } A((void**)&d->maxBits, B * sizeof(unsigned)); A((void**)&d->nCand, B * sizeof(int));
   A((void**)&d->kA, nc * 4); A((void**)&d->vA, nc * 4); A((void**)&d->kB, nc * 4); A((void**)&d->vB, nc * 4); A((void**)&d->kC, nc * 4); A((void**)&d->vC, nc * 4); A((void**)&d->state, nc);
   A((void**)&d->cellStart, (size_t)B * (d->cells + 1) * sizeof(int)); A((void**)&d->cellFill, (size_t)B * d->cells * sizeof(int));
   A((void**)&d->cellItems, nc * sizeof(int)); A((void**)&d->corners, (size_t)B * maxCorners * 2 * sizeof(float));
@@ -415,7 +434,25 @@ cudaError_t vo_detect_run(VODetect** pd, Profiler* prof, cudaStream_t st, int B,
   if (e != cudaSuccess) return e;
   VODetect* d = *pd;
   const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
-  e = cudaMemcpyAsync(d->img, images, (size_t)B * H * W, cudaMemcpyDefault, st);
+  // this frame goes to the buffer the last one did not use; everything enqueued so far may still read the last one's
+  const int j = d->cur < 0 ? 0 : d->cur ^ 1;
+  if (d->cur >= 0) {
+    e = cudaEventRecord(d->freed[d->cur], st);
+    if (e != cudaSuccess) return e;
+    d->freedValid[d->cur] = true;
+  }
+  cudaPointerAttributes pa{};
+  const bool pinned_src = cudaPointerGetAttributes(&pa, images) == cudaSuccess && pa.type == cudaMemoryTypeHost;
+  (void)cudaGetLastError();
+  if (pinned_src) {     // pinned host memory: copy on the copy stream, overlapping the kernels still running for the last frame
+    if (d->freedValid[j]) e = cudaStreamWaitEvent(d->copyStream, d->freed[j], 0);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d->imgBuf[j], images, (size_t)B * H * W, cudaMemcpyDefault, d->copyStream);
+    if (e == cudaSuccess) e = cudaEventRecord(d->uploaded[j], d->copyStream);
+    if (e == cudaSuccess) e = cudaStreamWaitEvent(st, d->uploaded[j], 0);
+  } else {              // pageable memory (the driver stages the copy and returns when the source may be reused) or device memory
+    e = cudaMemcpyAsync(d->imgBuf[j], images, (size_t)B * H * W, cudaMemcpyDefault, st);      // (whose producer is ordered by this stream)
+  }
+  d->cur = j; d->img = d->imgBuf[j];
   if (e == cudaSuccess) e = cudaMemsetAsync(d->maxBits, 0, B * sizeof(unsigned), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d->nCand, 0, B * sizeof(int), st);
   if (e == cudaSuccess) e = cudaMemsetAsync(d->status, 0, B * sizeof(int), st);
