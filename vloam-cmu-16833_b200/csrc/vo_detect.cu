@@ -422,6 +422,7 @@ static cudaError_t vo_detect_alloc(VODetect** pd, int B, int H, int W, int cell,
   A((void**)&d->cellItems, nc * sizeof(int)); A((void**)&d->corners, (size_t)B * maxCorners * 2 * sizeof(float));
   A((void**)&d->nCorners, B * sizeof(int)); A((void**)&d->status, B * sizeof(int));
   if (e == cudaSuccess) e = cudaFuncSetAttribute(vo_select_corners, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SortSmem));
+  if (e != cudaSuccess) { vo_detect_destroy(d); *pd = nullptr; }      // (a half-built state must not pass the shape test of the next call)
   return e;
 }
 
