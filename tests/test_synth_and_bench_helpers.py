@@ -79,6 +79,14 @@ def test_bench_helpers():
         assert b.algorithmic_bytes(name, tot) > 0, name
     assert b.algorithmic_bytes("sr_curvature", tot) == 80 * 21                      # 16 B read + 4 + 1 written per kept point
     assert set(b.NCU_KERNELS["lm_place"]) == {"lm_place", "lm_compact_copy", "lm_write_back"}
+    # configs[3]: the camera frames of the image front end — KITTI-sized, deterministic, distinct per stream and step parity
+    f00, f01, f10 = b.frame_of(0, 0), b.frame_of(0, 1), b.frame_of(1, 0)
+    assert f00.shape == (376, 1241) and f00.dtype == np.uint8 and np.array_equal(f00, b.frame_of(0, 2))
+    assert np.array_equal(f01, np.roll(f00, 4, axis=1)) and not np.array_equal(f00, f10)
+    fe = b.CpuFrontEnd()                       # the reference's processImage calls (OpenCV), when cv2 is importable
+    if fe.cv2 is not None:
+        fe.process(f00); fe.process(f01)
+        assert fe.prev is not None and fe.prev.shape[1] == 32 and len(fe.prev) > 500
 
 
 def test_c_ray_caster_reproduces_the_numpy_ray_caster_bit_for_bit(synth):
