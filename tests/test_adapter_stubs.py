@@ -143,6 +143,11 @@ def test_vo_adapter_runs_the_callers_frame_loop(tmp_path, synth):
             res = vo.solveNlsAll(prev["keypoints"][m[:, 0]], cur["keypoints"][m[:, 1]])
             assert np.array_equal(motion, np.r_[res["angles_0to1"][0], res["t_0to1"][0]]), (k, motion)
             assert res["counter32"][0] + res["counter22"][0] > 50
+            # the same solve without the host in between: the matched pixels processImage left on the device go straight in
+            vo.solveNlsAllDevice(*vo.match_buffers())
+            dres = vo.result()
+            assert np.array_equal(dres["angles_0to1"], res["angles_0to1"]) and np.array_equal(dres["t_0to1"], res["t_0to1"])
+            assert dres["counter32"][0] == res["counter32"][0] and dres["counter22"][0] == res["counter22"][0]
         prev = cur
     published = {l.split()[1]: int(l.split()[2]) for l in out.stdout.splitlines() if l.startswith("published")}
     assert published == {"/point_cloud_follow_VO": 3, "/visual_odom_to_init": 3, "/visual_odom_path": 3}
